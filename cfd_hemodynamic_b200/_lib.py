@@ -1,0 +1,295 @@
+"""ctypes binding of libhemo_sm100.so (the C-ABI declared in include/hemo.h).
+
+PyTorch is used only for device buffers: every array argument is a torch
+tensor whose `data_ptr()` is handed to the library.  There is no CPU
+fallback: if the shared library is missing, or no CUDA device is present when
+a context is created, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhemo_sm100.so")
+
+HEMO_DIVERGED = -100
+Q_FU, Q_FP, Q_UU, Q_UP, Q_PU, Q_PP = range(6)
+
+
+class HemoError(RuntimeError):
+    pass
+
+
+class HemoDiverged(HemoError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("dt", C.c_double), ("rho", C.c_double), ("mu", C.c_double),
+                ("f", C.c_double * 2), ("eps0", C.c_double)]
+
+
+class FacetCoef(C.Structure):
+    _fields_ = [(k, C.c_double) for k in
+                ("a_p", "pconst", "a_g", "a_s", "a_n", "beta_n", "a_b", "beta_b")]
+
+
+class SolverOpts(C.Structure):
+    _fields_ = [("restart", C.c_int), ("max_it", C.c_int), ("rtol", C.c_double),
+                ("atol", C.c_double), ("amg_cycles_u", C.c_int), ("amg_cycles_p", C.c_int),
+                ("cheb_degree", C.c_int), ("project_pressure", C.c_int), ("pc_mode", C.c_int),
+                ("schur_mass_coef", C.c_double), ("schur_lap_coef", C.c_double),
+                ("cheb_ratio", C.c_double)]
+
+
+# name -> (restype, argtypes); every symbol include/hemo.h declares
+_VP, _I, _L, _D = C.c_void_p, C.c_int, C.c_int64, C.c_double
+SYMBOLS = {
+    "hemo_ctx_create": (_I, [_I, C.POINTER(_VP)]),
+    "hemo_ctx_destroy": (_I, [_VP]),
+    "hemo_last_error": (C.c_char_p, [_VP]),
+    "hemo_set_stream": (_I, [_VP, _VP]),
+    "hemo_launch_count": (_L, [_VP]),
+    "hemo_set_mesh": (_I, [_VP, _VP, _I, _VP, _I, _VP]),
+    "hemo_set_node_graph": (_I, [_VP, _VP, _VP, _L]),
+    "hemo_matrix_nnz": (_I, [_VP, C.POINTER(_L)]),
+    "hemo_get_pattern": (_I, [_VP, _VP, _VP]),
+    "hemo_set_quadrature": (_I, [_VP, _I, _VP, _VP, _I]),
+    "hemo_set_facet_quadrature": (_I, [_VP, _VP, _VP, _I]),
+    "hemo_set_params": (_I, [_VP, C.POINTER(Params)]),
+    "hemo_set_facet_set": (_I, [_VP, _I, _VP, _VP, _I, C.POINTER(FacetCoef)]),
+    "hemo_set_facet_coef": (_I, [_VP, _I, C.POINTER(FacetCoef)]),
+    "hemo_set_bc": (_I, [_VP, _VP, _VP, _VP]),
+    "hemo_assemble_jacobian": (_I, [_VP, _VP, _VP, _VP]),
+    "hemo_assemble_residual": (_I, [_VP, _VP, _VP, _VP, _VP]),
+    "hemo_outlet_flux": (_I, [_VP, _I, _VP, C.POINTER(_D)]),
+    "hemo_assemble_laplace_mass": (_I, [_VP, _VP, _VP]),
+    "hemo_spmv": (_I, [_VP, _VP, _VP, _VP]),
+    "hemo_axpy": (_I, [_VP, _L, _D, _VP, _VP]),
+    "hemo_dot": (_I, [_VP, _L, _VP, _VP, C.POINTER(_D)]),
+    "hemo_norm2": (_I, [_VP, _L, _VP, C.POINTER(_D)]),
+    "hemo_amg_set_level": (_I, [_VP, _I, _I, _I, _I] + [_VP] * 10),
+    "hemo_amg_finalize": (_I, [_VP, _I, _I]),
+    "hemo_host_aggregate": (_I, [_I, _VP, _VP, _VP, _VP, C.POINTER(_I)]),
+    "hemo_set_solver_opts": (_I, [_VP, C.POINTER(SolverOpts)]),
+    "hemo_pc_setup": (_I, [_VP, _VP, _VP, _VP]),
+    "hemo_amg_apply": (_I, [_VP, _I, _VP, _VP, _I]),
+    "hemo_amg_get_level_values": (_I, [_VP, _I, _I, _VP, _L]),
+    "hemo_pc_apply": (_I, [_VP, _VP, _VP, _VP]),
+    "hemo_fgmres": (_I, [_VP, _VP, _VP, _VP, C.POINTER(_I), C.POINTER(_D)]),
+}
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """dlopen the in-tree shared library and bind every declared symbol."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise HemoError(
+            f"{p} not found: build it with `python -m cfd_hemodynamic_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(p)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if a symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _np_ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Hemo:
+    """One library context bound to one CUDA device."""
+
+    def __init__(self, device: int = 0):
+        import torch
+        if not torch.cuda.is_available():
+            raise HemoError("no CUDA device: the hot path only exists as sm_100a kernels")
+        self.lib = load_library()
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        self._ctx = C.c_void_p()
+        rc = self.lib.hemo_ctx_create(device, C.byref(self._ctx))
+        if rc != 0:
+            raise HemoError(f"hemo_ctx_create failed ({rc})")
+        self.lib.hemo_set_stream(self._ctx, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        self._keep = {}     # borrowed tensors must outlive the context
+
+    def close(self):
+        if self._ctx:
+            self.torch.cuda.synchronize(self.device)
+            self.lib.hemo_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc == 0:
+            return
+        msg = self.lib.hemo_last_error(self._ctx)
+        msg = msg.decode() if msg else ""
+        if rc == HEMO_DIVERGED:
+            raise HemoDiverged(f"{what}: {msg}")
+        raise HemoError(f"{what} failed (code {rc}): {msg}")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.hemo_launch_count(self._ctx))
+
+    # ---- setup ---------------------------------------------------------
+    def set_mesh(self, x2, cells, h):
+        self._keep.update(x=x2, cells=cells, h=h)
+        self.n = x2.shape[0]
+        self.E = cells.shape[0]
+        self._check(self.lib.hemo_set_mesh(self._ctx, _ptr(x2), self.n, _ptr(cells), self.E, _ptr(h)),
+                    "hemo_set_mesh")
+
+    def set_node_graph(self, nrowptr, ncol):
+        self._keep.update(nrowptr=nrowptr, ncol=ncol)
+        self.nnz_node = int(ncol.shape[0])
+        self._check(self.lib.hemo_set_node_graph(self._ctx, _ptr(nrowptr), _ptr(ncol), self.nnz_node),
+                    "hemo_set_node_graph")
+        self.nnz = 9 * self.nnz_node
+
+    def get_pattern(self):
+        t = self.torch
+        rowptr = t.empty(3 * self.n + 1, dtype=t.int64, device=self.device)
+        col = t.empty(self.nnz, dtype=t.int32, device=self.device)
+        self._check(self.lib.hemo_get_pattern(self._ctx, _ptr(rowptr), _ptr(col)), "hemo_get_pattern")
+        return rowptr, col
+
+    def set_quadrature(self, block: int, pts: np.ndarray, wts: np.ndarray):
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        wts = np.ascontiguousarray(wts, dtype=np.float64)
+        self._check(self.lib.hemo_set_quadrature(self._ctx, block, _np_ptr(pts), _np_ptr(wts), len(wts)),
+                    "hemo_set_quadrature")
+
+    def set_facet_quadrature(self, pts, wts):
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        wts = np.ascontiguousarray(wts, dtype=np.float64)
+        self._check(self.lib.hemo_set_facet_quadrature(self._ctx, _np_ptr(pts), _np_ptr(wts), len(wts)),
+                    "hemo_set_facet_quadrature")
+
+    def set_params(self, dt, rho, mu, f, eps0):
+        p = Params(dt=dt, rho=rho, mu=mu, eps0=eps0)
+        p.f[0], p.f[1] = float(f[0]), float(f[1])
+        self._check(self.lib.hemo_set_params(self._ctx, C.byref(p)), "hemo_set_params")
+
+    def set_facet_set(self, set_id: int, cells, mask, **coef):
+        c = FacetCoef(**coef)
+        m = 0 if cells is None else int(cells.shape[0])
+        self._check(self.lib.hemo_set_facet_set(self._ctx, set_id, _ptr(cells), _ptr(mask), m, C.byref(c)),
+                    "hemo_set_facet_set")
+
+    def set_facet_coef(self, set_id: int, **coef):
+        c = FacetCoef(**coef)
+        self._check(self.lib.hemo_set_facet_coef(self._ctx, set_id, C.byref(c)), "hemo_set_facet_coef")
+
+    def set_bc(self, dofflag, dofmult, cellflag):
+        self._check(self.lib.hemo_set_bc(self._ctx, _ptr(dofflag), _ptr(dofmult), _ptr(cellflag)), "hemo_set_bc")
+
+    # ---- assembly ------------------------------------------------------
+    def assemble_jacobian(self, x, un, vals):
+        self._check(self.lib.hemo_assemble_jacobian(self._ctx, _ptr(x), _ptr(un), _ptr(vals)),
+                    "hemo_assemble_jacobian")
+
+    def assemble_residual(self, x, un, g, b):
+        self._check(self.lib.hemo_assemble_residual(self._ctx, _ptr(x), _ptr(un), _ptr(g), _ptr(b)),
+                    "hemo_assemble_residual")
+
+    def outlet_flux(self, set_id, un) -> float:
+        q = C.c_double()
+        self._check(self.lib.hemo_outlet_flux(self._ctx, set_id, _ptr(un), C.byref(q)), "hemo_outlet_flux")
+        return q.value
+
+    def assemble_laplace_mass(self):
+        t = self.torch
+        lap = t.empty(self.nnz_node, dtype=t.float64, device=self.device)
+        mass = t.empty(self.n, dtype=t.float64, device=self.device)
+        self._check(self.lib.hemo_assemble_laplace_mass(self._ctx, _ptr(lap), _ptr(mass)),
+                    "hemo_assemble_laplace_mass")
+        return lap, mass
+
+    # ---- linear algebra --------------------------------------------------
+    def spmv(self, vals, x, y):
+        self._check(self.lib.hemo_spmv(self._ctx, _ptr(vals), _ptr(x), _ptr(y)), "hemo_spmv")
+
+    def axpy(self, a, x, y):
+        self._check(self.lib.hemo_axpy(self._ctx, x.numel(), float(a), _ptr(x), _ptr(y)), "hemo_axpy")
+
+    def dot(self, x, y) -> float:
+        out = C.c_double()
+        self._check(self.lib.hemo_dot(self._ctx, x.numel(), _ptr(x), _ptr(y), C.byref(out)), "hemo_dot")
+        return out.value
+
+    def norm2(self, x) -> float:
+        out = C.c_double()
+        self._check(self.lib.hemo_norm2(self._ctx, x.numel(), _ptr(x), C.byref(out)), "hemo_norm2")
+        return out.value
+
+    # ---- AMG / solve -------------------------------------------------------
+    def amg_set_level(self, which, level, P, R, AP_pattern, C_pattern):
+        """P, R: scipy CSR (float64); AP_pattern, C_pattern: scipy CSR patterns."""
+        def i32(a):
+            return np.ascontiguousarray(a, dtype=np.int32)
+        p_rp, p_c, p_v = i32(P.indptr), i32(P.indices), np.ascontiguousarray(P.data, dtype=np.float64)
+        r_rp, r_c, r_v = i32(R.indptr), i32(R.indices), np.ascontiguousarray(R.data, dtype=np.float64)
+        ap_rp, ap_c = i32(AP_pattern.indptr), i32(AP_pattern.indices)
+        c_rp, c_c = i32(C_pattern.indptr), i32(C_pattern.indices)
+        self._check(self.lib.hemo_amg_set_level(
+            self._ctx, which, level, P.shape[0], P.shape[1],
+            _np_ptr(p_rp), _np_ptr(p_c), _np_ptr(p_v), _np_ptr(r_rp), _np_ptr(r_c), _np_ptr(r_v),
+            _np_ptr(ap_rp), _np_ptr(ap_c), _np_ptr(c_rp), _np_ptr(c_c)), "hemo_amg_set_level")
+
+    def amg_finalize(self, which, n_levels):
+        self._check(self.lib.hemo_amg_finalize(self._ctx, which, n_levels), "hemo_amg_finalize")
+
+    def set_solver_opts(self, **kw):
+        o = SolverOpts(**kw)
+        self._check(self.lib.hemo_set_solver_opts(self._ctx, C.byref(o)), "hemo_set_solver_opts")
+
+    def pc_setup(self, vals, lap=None, mass=None):
+        if lap is not None:
+            self._keep.update(mass=mass)
+        self._check(self.lib.hemo_pc_setup(self._ctx, _ptr(vals), _ptr(lap), _ptr(mass)), "hemo_pc_setup")
+
+    def amg_apply(self, which, b, x, ncycles=1):
+        self._check(self.lib.hemo_amg_apply(self._ctx, which, _ptr(b), _ptr(x), ncycles), "hemo_amg_apply")
+
+    def amg_level_values(self, which, level, count):
+        t = self.torch
+        out = t.empty(count, dtype=t.float64, device=self.device)
+        self._check(self.lib.hemo_amg_get_level_values(self._ctx, which, level, _ptr(out), count),
+                    "hemo_amg_get_level_values")
+        return out
+
+    def pc_apply(self, vals, r, z):
+        self._check(self.lib.hemo_pc_apply(self._ctx, _ptr(vals), _ptr(r), _ptr(z)), "hemo_pc_apply")
+
+    def fgmres(self, vals, b, y):
+        its = C.c_int()
+        res = C.c_double()
+        rc = self.lib.hemo_fgmres(self._ctx, _ptr(vals), _ptr(b), _ptr(y), C.byref(its), C.byref(res))
+        self._check(rc, "hemo_fgmres")
+        return its.value, res.value

@@ -1,0 +1,574 @@
+// Aggregation-AMG V-cycle on node-block CSR operators (bs = 2: velocity block
+// A00, bs = 1: pressure Laplacian of the Schur-complement approximation).
+//
+// Replaces, by design with a different algorithm, the PETSc sub-solvers
+// `gmres + asm/ilu(0)` on A00 and `preonly + asm/ilu(0)` on Sp configured at
+// reference src/solvers/stabilized_schur.py:256-267 (ILU triangular solves are
+// sequential; a multigrid cycle is all SpMV-shaped, HBM-bound work).
+//
+// The prolongators (aggregates, optional Jacobi smoothing) depend only on the
+// mesh graph and are built once by the host; what runs here every Newton
+// iteration is the numeric Galerkin product R*A*P on fixed patterns, the
+// smoother set-up, and the cycles.
+#include "hemo_internal.cuh"
+
+int hemo_bsr_spmv_ex(hemo_ctx* ctx, int bs, int n, const int32_t* rowptr, const int32_t* col, const double* val,
+                     const double* x, double alpha, const double* b, double* y);
+
+// ---------------------------------------------------------------------------
+// numeric Galerkin product
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int find_col(const int32_t* __restrict__ col, int lo, int hi, int key) {
+    // binary search in col[lo, hi)
+    int a = lo, b = hi - 1;
+    while (a <= b) {
+        const int m = (a + b) >> 1;
+        const int c = col[m];
+        if (c == key) return m;
+        if (c < key) a = m + 1; else b = m - 1;
+    }
+    return -1;
+}
+
+// AP = A * (P (x) I_bs): one thread per fine block row
+template <int BS>
+__global__ void __launch_bounds__(128)
+k_numeric_ap(int n, const int32_t* __restrict__ a_rowptr, const int32_t* __restrict__ a_col,
+             const double* __restrict__ a_val, const int32_t* __restrict__ p_rowptr,
+             const int32_t* __restrict__ p_col, const double* __restrict__ p_val,
+             const int32_t* __restrict__ ap_rowptr, const int32_t* __restrict__ ap_col,
+             double* __restrict__ ap_val) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int o0 = ap_rowptr[i], o1 = ap_rowptr[i + 1];
+    for (int s = o0; s < o1; ++s)
+#pragma unroll
+        for (int k = 0; k < BS * BS; ++k) ap_val[(int64_t)s * BS * BS + k] = 0.0;
+    for (int t = a_rowptr[i]; t < a_rowptr[i + 1]; ++t) {
+        const int j = a_col[t];
+        double blk[BS * BS];
+#pragma unroll
+        for (int k = 0; k < BS * BS; ++k) blk[k] = a_val[(int64_t)t * BS * BS + k];
+        for (int u = p_rowptr[j]; u < p_rowptr[j + 1]; ++u) {
+            const int pos = find_col(ap_col, o0, o1, p_col[u]);
+            if (pos < 0) continue;   // pattern given by the host always contains it
+            const double w = p_val[u];
+#pragma unroll
+            for (int k = 0; k < BS * BS; ++k) ap_val[(int64_t)pos * BS * BS + k] += w * blk[k];
+        }
+    }
+}
+
+// Ac = (R (x) I_bs) * AP: one thread per coarse block row
+template <int BS>
+__global__ void __launch_bounds__(128)
+k_numeric_rap(int nc, const int32_t* __restrict__ r_rowptr, const int32_t* __restrict__ r_col,
+              const double* __restrict__ r_val, const int32_t* __restrict__ ap_rowptr,
+              const int32_t* __restrict__ ap_col, const double* __restrict__ ap_val,
+              const int32_t* __restrict__ c_rowptr, const int32_t* __restrict__ c_col,
+              double* __restrict__ c_val) {
+    const int I = blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= nc) return;
+    const int o0 = c_rowptr[I], o1 = c_rowptr[I + 1];
+    for (int s = o0; s < o1; ++s)
+#pragma unroll
+        for (int k = 0; k < BS * BS; ++k) c_val[(int64_t)s * BS * BS + k] = 0.0;
+    for (int t = r_rowptr[I]; t < r_rowptr[I + 1]; ++t) {
+        const int i = r_col[t];
+        const double w = r_val[t];
+        for (int u = ap_rowptr[i]; u < ap_rowptr[i + 1]; ++u) {
+            const int pos = find_col(c_col, o0, o1, ap_col[u]);
+            if (pos < 0) continue;
+#pragma unroll
+            for (int k = 0; k < BS * BS; ++k) c_val[(int64_t)pos * BS * BS + k] += w * ap_val[(int64_t)u * BS * BS + k];
+        }
+    }
+}
+
+// inverse diagonal and Gershgorin bound of D^-1 A (per-block max)
+template <int BS>
+__global__ void __launch_bounds__(256)
+k_diag_bound(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+             const double* __restrict__ val, double* __restrict__ dinv, double* __restrict__ partial_max) {
+    __shared__ double sh[256];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double bound = 0.0;
+    if (i < n) {
+        double diag[BS], rs[BS];
+#pragma unroll
+        for (int k = 0; k < BS; ++k) { diag[k] = 0.0; rs[k] = 0.0; }
+        for (int t = rowptr[i]; t < rowptr[i + 1]; ++t) {
+            const int j = col[t];
+#pragma unroll
+            for (int k = 0; k < BS; ++k)
+#pragma unroll
+                for (int l = 0; l < BS; ++l) {
+                    const double v = val[(int64_t)t * BS * BS + k * BS + l];
+                    rs[k] += fabs(v);
+                    if (j == i && k == l) diag[k] = v;
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < BS; ++k) {
+            const double d = (diag[k] != 0.0) ? diag[k] : 1.0;
+            dinv[(int64_t)i * BS + k] = 1.0 / d;
+            bound = fmax(bound, rs[k] / fabs(d));
+        }
+    }
+    sh[threadIdx.x] = bound;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial_max[blockIdx.x] = sh[0];
+}
+
+__global__ void k_max_final(int m, const double* __restrict__ partial, double* __restrict__ out) {
+    __shared__ double sh[256];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) v = fmax(v, partial[i]);
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+// ---------------------------------------------------------------------------
+// Chebyshev smoother on D^-1 A (fused SpMV + three-term update per step)
+// ---------------------------------------------------------------------------
+// start from x = 0:  r = D^-1 b ; d = r / theta ; x = d
+template <int BS>
+__global__ void k_cheb_start_zero(int64_t N, const double* __restrict__ dinv, const double* __restrict__ b,
+                                  double inv_theta, double* __restrict__ r, double* __restrict__ d,
+                                  double* __restrict__ x) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double rv = dinv[i] * b[i];
+    r[i] = rv;
+    const double dv = rv * inv_theta;
+    d[i] = dv;
+    x[i] = dv;
+}
+
+// start from x != 0: r = D^-1 (b - A x) ; d = r / theta   (one thread per block row).
+// x is NOT updated here (other rows still read it); the update x += d is folded
+// into the first k_cheb_step (add_old) or done by an axpy when degree == 1.
+template <int BS>
+__global__ void __launch_bounds__(256)
+k_cheb_start(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+             const double* __restrict__ val, const double* __restrict__ dinv, const double* __restrict__ b,
+             double inv_theta, const double* __restrict__ xin, double* __restrict__ r, double* __restrict__ d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc[BS];
+#pragma unroll
+    for (int k = 0; k < BS; ++k) acc[k] = 0.0;
+    for (int t = rowptr[i]; t < rowptr[i + 1]; ++t) {
+        const int j = col[t];
+#pragma unroll
+        for (int k = 0; k < BS; ++k)
+#pragma unroll
+            for (int l = 0; l < BS; ++l) acc[k] += val[(int64_t)t * BS * BS + k * BS + l] * xin[(int64_t)j * BS + l];
+    }
+#pragma unroll
+    for (int k = 0; k < BS; ++k) {
+        const int64_t q = (int64_t)i * BS + k;
+        const double rv = dinv[q] * (b[q] - acc[k]);
+        r[q] = rv;
+        d[q] = rv * inv_theta;
+    }
+}
+
+// one step: r -= D^-1 A d_old ; d_new = c1 d_old + c2 r ; x += d_new
+template <int BS>
+__global__ void __launch_bounds__(256)
+k_cheb_step(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+            const double* __restrict__ val, const double* __restrict__ dinv, double c1, double c2,
+            const double* __restrict__ dold, double* __restrict__ dnew, double* __restrict__ r,
+            double* __restrict__ x, int add_old) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc[BS];
+#pragma unroll
+    for (int k = 0; k < BS; ++k) acc[k] = 0.0;
+    for (int t = rowptr[i]; t < rowptr[i + 1]; ++t) {
+        const int j = col[t];
+#pragma unroll
+        for (int k = 0; k < BS; ++k)
+#pragma unroll
+            for (int l = 0; l < BS; ++l) acc[k] += val[(int64_t)t * BS * BS + k * BS + l] * dold[(int64_t)j * BS + l];
+    }
+#pragma unroll
+    for (int k = 0; k < BS; ++k) {
+        const int64_t q = (int64_t)i * BS + k;
+        const double rv = r[q] - dinv[q] * acc[k];
+        r[q] = rv;
+        const double dv = c1 * dold[q] + c2 * rv;
+        dnew[q] = dv;
+        x[q] += add_old ? (dv + dold[q]) : dv;
+    }
+}
+
+// y[I] (+)= sum_t w_t x[col_t]  with bs components per node (restriction / prolongation)
+template <int BS, bool ADD>
+__global__ void __launch_bounds__(256)
+k_transfer(int nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+           const double* __restrict__ w, const double* __restrict__ x, double* __restrict__ y) {
+    const int I = blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= nrows) return;
+    double acc[BS];
+#pragma unroll
+    for (int k = 0; k < BS; ++k) acc[k] = 0.0;
+    for (int t = rowptr[I]; t < rowptr[I + 1]; ++t) {
+        const int j = col[t];
+        const double wt = w[t];
+#pragma unroll
+        for (int k = 0; k < BS; ++k) acc[k] += wt * x[(int64_t)j * BS + k];
+    }
+#pragma unroll
+    for (int k = 0; k < BS; ++k) {
+        if (ADD) y[(int64_t)I * BS + k] += acc[k];
+        else y[(int64_t)I * BS + k] = acc[k];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// dense coarsest-level solve: explicit inverse by Gauss–Jordan with partial
+// pivoting, one CTA (N <= HEMO_DENSE_MAX)
+// ---------------------------------------------------------------------------
+template <int BS>
+__global__ void k_dense_fill(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                             const double* __restrict__ val, int N, double* __restrict__ M /*N x 2N*/) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int t = rowptr[i]; t < rowptr[i + 1]; ++t) {
+        const int j = col[t];
+#pragma unroll
+        for (int k = 0; k < BS; ++k)
+#pragma unroll
+            for (int l = 0; l < BS; ++l)
+                M[(int64_t)(i * BS + k) * 2 * N + (j * BS + l)] = val[(int64_t)t * BS * BS + k * BS + l];
+    }
+}
+
+__global__ void k_dense_identity(int N, double shift_rel, double* __restrict__ M) {
+    // right half = I; optional relative diagonal shift (singular Neumann operator)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    M[(int64_t)i * 2 * N + N + i] = 1.0;
+    if (shift_rel > 0.0) M[(int64_t)i * 2 * N + i] *= (1.0 + shift_rel);
+}
+
+__global__ void __launch_bounds__(1024)
+k_dense_invert(int N, double* __restrict__ M /*N x 2N augmented*/, int* __restrict__ fail) {
+    __shared__ double smax[1024];
+    __shared__ int sidx[1024];
+    __shared__ double pivrow_scale;
+    __shared__ double fcol[HEMO_DENSE_MAX];
+    const int tid = threadIdx.x;
+    const int W = 2 * N;
+    for (int p = 0; p < N; ++p) {
+        // pivot search in column p, rows p..N-1
+        double best = -1.0;
+        int bi = p;
+        for (int r = p + tid; r < N; r += blockDim.x) {
+            const double v = fabs(M[(int64_t)r * W + p]);
+            if (v > best) { best = v; bi = r; }
+        }
+        smax[tid] = best; sidx[tid] = bi;
+        __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if (tid < s) {
+                if (smax[tid + s] > smax[tid] || (smax[tid + s] == smax[tid] && sidx[tid + s] < sidx[tid])) {
+                    smax[tid] = smax[tid + s]; sidx[tid] = sidx[tid + s];
+                }
+            }
+            __syncthreads();
+        }
+        const int piv = sidx[0];
+        if (tid == 0) {
+            if (!(smax[0] > 0.0)) *fail = 1;
+        }
+        // swap rows p and piv
+        if (piv != p) {
+            for (int c = tid; c < W; c += blockDim.x) {
+                const double a = M[(int64_t)p * W + c];
+                M[(int64_t)p * W + c] = M[(int64_t)piv * W + c];
+                M[(int64_t)piv * W + c] = a;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) pivrow_scale = 1.0 / M[(int64_t)p * W + p];
+        __syncthreads();
+        const double sc = pivrow_scale;
+        for (int c = tid; c < W; c += blockDim.x) M[(int64_t)p * W + c] *= sc;
+        __syncthreads();
+        // eliminate column p from all other rows: stage the multipliers, then
+        // update the whole matrix without further synchronisation
+        for (int r = tid; r < N; r += blockDim.x) fcol[r] = (r == p) ? 0.0 : M[(int64_t)r * W + p];
+        __syncthreads();
+        const int64_t total = (int64_t)N * W;
+        for (int64_t q = tid; q < total; q += blockDim.x) {
+            const int r = (int)(q / W);
+            const int c = (int)(q - (int64_t)r * W);
+            const double f = fcol[r];
+            if (f != 0.0) M[q] -= f * M[(int64_t)p * W + c];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_dense_extract(int N, const double* __restrict__ M, double* __restrict__ inv) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= (int64_t)N * N) return;
+    const int r = (int)(q / N), c = (int)(q % N);
+    inv[q] = M[(int64_t)r * 2 * N + N + c];
+}
+
+// y = inv * b : one warp per row
+__global__ void __launch_bounds__(256)
+k_dense_gemv(int N, const double* __restrict__ inv, const double* __restrict__ b, double* __restrict__ y) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    if (row < N)
+        for (int c = lane; c < N; c += 32) acc += inv[(int64_t)row * N + c] * b[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (row < N && lane == 0) y[row] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static void free_level(HemoAmgLevel& L) {
+    cudaFree(L.p_rowptr); cudaFree(L.p_col); cudaFree(L.p_val);
+    cudaFree(L.r_rowptr); cudaFree(L.r_col); cudaFree(L.r_val);
+    cudaFree(L.ap_rowptr); cudaFree(L.ap_col); cudaFree(L.ap_val);
+    cudaFree(L.c_rowptr); cudaFree(L.c_col);
+    L = HemoAmgLevel();
+}
+
+void hemo_amg_free(HemoAmg* amg) {
+    for (int l = 0; l < HEMO_MAX_LEVELS; ++l) {
+        free_level(amg->lev[l]);
+        HemoAmgOp& o = amg->op[l];
+        cudaFree(o.val); cudaFree(o.dinv); cudaFree(o.x); cudaFree(o.b); cudaFree(o.r); cudaFree(o.d);
+        o = HemoAmgOp();
+    }
+    cudaFree(amg->dense_inv); cudaFree(amg->dense_work);
+    amg->dense_inv = amg->dense_work = nullptr;
+    amg->nlev = 0;
+    amg->ready = false;
+}
+
+extern "C" int hemo_amg_set_level(hemo_ctx* ctx, int which, int level, int n_fine, int n_coarse,
+                                  const int32_t* p_rowptr, const int32_t* p_col, const double* p_val,
+                                  const int32_t* r_rowptr, const int32_t* r_col, const double* r_val,
+                                  const int32_t* ap_rowptr, const int32_t* ap_col,
+                                  const int32_t* c_rowptr, const int32_t* c_col) {
+    if (!ctx || which < 0 || which > 1 || level < 0 || level >= HEMO_MAX_LEVELS - 1) return HEMO_EINVAL;
+    if (!p_rowptr || !p_col || !p_val || !r_rowptr || !r_col || !r_val || !ap_rowptr || !ap_col || !c_rowptr || !c_col)
+        return HEMO_EINVAL;
+    HemoAmg& amg = ctx->amg[which];
+    amg.bs = (which == 0) ? 2 : 1;
+    amg.ready = false;
+    HemoAmgLevel& L = amg.lev[level];
+    free_level(L);
+    L.n_fine = n_fine; L.n_coarse = n_coarse;
+    L.nnz_p = p_rowptr[n_fine];
+    L.nnz_ap = ap_rowptr[n_fine];
+    L.nnz_c = c_rowptr[n_coarse];
+    if (r_rowptr[n_coarse] != L.nnz_p) HEMO_FAIL(ctx, HEMO_EINVAL, "R is not the transpose pattern of P");
+    int rc;
+    if ((rc = hemo_upload(ctx, &L.p_rowptr, p_rowptr, (size_t)n_fine + 1, false))) return rc;
+    if ((rc = hemo_upload(ctx, &L.p_col, p_col, (size_t)L.nnz_p, false))) return rc;
+    if ((rc = hemo_upload(ctx, &L.p_val, p_val, (size_t)L.nnz_p, false))) return rc;
+    if ((rc = hemo_upload(ctx, &L.r_rowptr, r_rowptr, (size_t)n_coarse + 1, false))) return rc;
+    if ((rc = hemo_upload(ctx, &L.r_col, r_col, (size_t)L.nnz_p, false))) return rc;
+    if ((rc = hemo_upload(ctx, &L.r_val, r_val, (size_t)L.nnz_p, false))) return rc;
+    if ((rc = hemo_upload(ctx, &L.ap_rowptr, ap_rowptr, (size_t)n_fine + 1, false))) return rc;
+    if ((rc = hemo_upload(ctx, &L.ap_col, ap_col, (size_t)L.nnz_ap, false))) return rc;
+    if ((rc = hemo_upload(ctx, &L.c_rowptr, c_rowptr, (size_t)n_coarse + 1, false))) return rc;
+    if ((rc = hemo_upload(ctx, &L.c_col, c_col, (size_t)L.nnz_c, false))) return rc;
+    if ((rc = hemo_alloc(ctx, &L.ap_val, (size_t)L.nnz_ap * amg.bs * amg.bs))) return rc;
+    // host arrays may be released by the caller as soon as we return
+    HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int hemo_amg_finalize(hemo_ctx* ctx, int which, int n_levels) {
+    if (!ctx || which < 0 || which > 1 || n_levels < 1 || n_levels > HEMO_MAX_LEVELS) return HEMO_EINVAL;
+    if (!ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "node graph not set");
+    HemoAmg& amg = ctx->amg[which];
+    amg.bs = (which == 0) ? 2 : 1;
+    const int bs = amg.bs;
+    amg.nlev = n_levels;
+    int rc;
+    for (int l = 0; l < n_levels; ++l) {
+        HemoAmgOp& o = amg.op[l];
+        if (l == 0) {
+            o.n = ctx->n; o.nnzb = ctx->nnz_node; o.rowptr = ctx->nrowptr; o.col = ctx->ncol;
+        } else {
+            const HemoAmgLevel& L = amg.lev[l - 1];
+            if (L.n_coarse <= 0) HEMO_FAIL(ctx, HEMO_ESTATE, "missing AMG level");
+            if (l == 1 ? (L.n_fine != ctx->n) : (L.n_fine != amg.lev[l - 2].n_coarse))
+                HEMO_FAIL(ctx, HEMO_EINVAL, "AMG level sizes do not chain");
+            o.n = L.n_coarse; o.nnzb = L.nnz_c; o.rowptr = L.c_rowptr; o.col = L.c_col;
+        }
+        if ((rc = hemo_alloc(ctx, &o.val, (size_t)o.nnzb * bs * bs))) return rc;
+        if ((rc = hemo_alloc(ctx, &o.dinv, (size_t)o.n * bs))) return rc;
+        if ((rc = hemo_alloc(ctx, &o.x, (size_t)o.n * bs))) return rc;
+        if ((rc = hemo_alloc(ctx, &o.b, (size_t)o.n * bs))) return rc;
+        if ((rc = hemo_alloc(ctx, &o.r, (size_t)o.n * bs))) return rc;
+        if ((rc = hemo_alloc(ctx, &o.d, (size_t)o.n * bs * 2))) return rc;   // ping-pong
+    }
+    const int Nc = amg.op[n_levels - 1].n * bs;
+    if (Nc > HEMO_DENSE_MAX) HEMO_FAIL(ctx, HEMO_EINVAL, "coarsest AMG level too large for the dense solve");
+    amg.dense_n = Nc;
+    if ((rc = hemo_alloc(ctx, &amg.dense_inv, (size_t)Nc * Nc))) return rc;
+    if ((rc = hemo_alloc(ctx, &amg.dense_work, (size_t)Nc * 2 * Nc + 8))) return rc;
+    if ((rc = hemo_ensure_reduce(ctx, (size_t)hemo_grid(ctx->n, 256) + 1184 * 8, 512))) return rc;
+    amg.ready = true;
+    return 0;
+}
+
+template <int BS>
+static int amg_numeric_t(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift) {
+    cudaStream_t st = ctx->stream;
+    for (int l = 0; l + 1 < amg->nlev; ++l) {
+        const HemoAmgOp& A = amg->op[l];
+        HemoAmgOp& C = amg->op[l + 1];
+        const HemoAmgLevel& L = amg->lev[l];
+        k_numeric_ap<BS><<<hemo_grid(A.n, 128), 128, 0, st>>>(A.n, A.rowptr, A.col, A.val, L.p_rowptr, L.p_col, L.p_val,
+                                                              L.ap_rowptr, L.ap_col, L.ap_val);
+        HEMO_LAUNCH_CHECK(ctx);
+        k_numeric_rap<BS><<<hemo_grid(C.n, 128), 128, 0, st>>>(C.n, L.r_rowptr, L.r_col, L.r_val, L.ap_rowptr, L.ap_col,
+                                                               L.ap_val, L.c_rowptr, L.c_col, C.val);
+        HEMO_LAUNCH_CHECK(ctx);
+    }
+    // smoother data; bounds are read back in one copy
+    for (int l = 0; l + 1 < amg->nlev; ++l) {
+        HemoAmgOp& A = amg->op[l];
+        const int g = hemo_grid(A.n, 256);
+        k_diag_bound<BS><<<g, 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, A.dinv, ctx->red_partial);
+        HEMO_LAUNCH_CHECK(ctx);
+        k_max_final<<<1, 256, 0, st>>>(g, ctx->red_partial, ctx->red_out + 64 + l);
+        HEMO_LAUNCH_CHECK(ctx);
+    }
+    if (amg->nlev > 1) {
+        HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->red_host + 64, ctx->red_out + 64, sizeof(double) * (amg->nlev - 1),
+                                             cudaMemcpyDeviceToHost, st));
+    }
+    // dense inverse of the coarsest operator
+    {
+        const HemoAmgOp& A = amg->op[amg->nlev - 1];
+        const int N = amg->dense_n;
+        int* fail = reinterpret_cast<int*>(amg->dense_work + (size_t)N * 2 * N);
+        HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(amg->dense_work, 0, sizeof(double) * ((size_t)N * 2 * N + 8), st));
+        k_dense_fill<BS><<<hemo_grid(A.n, 128), 128, 0, st>>>(A.n, A.rowptr, A.col, A.val, N, amg->dense_work);
+        HEMO_LAUNCH_CHECK(ctx);
+        k_dense_identity<<<hemo_grid(N, 128), 128, 0, st>>>(N, coarse_shift, amg->dense_work);
+        HEMO_LAUNCH_CHECK(ctx);
+        k_dense_invert<<<1, 1024, 0, st>>>(N, amg->dense_work, fail);
+        HEMO_LAUNCH_CHECK(ctx);
+        k_dense_extract<<<hemo_grid((int64_t)N * N, 256), 256, 0, st>>>(N, amg->dense_work, amg->dense_inv);
+        HEMO_LAUNCH_CHECK(ctx);
+        int fail_h = 0;
+        HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(&fail_h, fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+        HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+        if (fail_h) HEMO_FAIL(ctx, HEMO_DIVERGED, "coarsest AMG operator is singular");
+    }
+    for (int l = 0; l + 1 < amg->nlev; ++l) {
+        double b = ctx->red_host[64 + l];
+        if (!(b > 0.0) || !isfinite(b)) HEMO_FAIL(ctx, HEMO_DIVERGED, "AMG operator has a non-finite Gershgorin bound");
+        amg->op[l].lmax = b;
+    }
+    return 0;
+}
+
+// coarse_shift is carried in amg via dense_n sign-free field; passed explicitly by the caller
+int hemo_amg_numeric_shift(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift) {
+    if (!amg->ready) HEMO_FAIL(ctx, HEMO_ESTATE, "AMG hierarchy not finalized");
+    if (amg->bs == 2) return amg_numeric_t<2>(ctx, amg, coarse_shift);
+    return amg_numeric_t<1>(ctx, amg, coarse_shift);
+}
+
+int hemo_amg_numeric(hemo_ctx* ctx, HemoAmg* amg) { return hemo_amg_numeric_shift(ctx, amg, 0.0); }
+
+template <int BS>
+static int smooth_t(hemo_ctx* ctx, const HemoAmgOp& A, const double* b, double* x, bool x_is_zero, int degree,
+                    double ratio) {
+    cudaStream_t st = ctx->stream;
+    const double lmax = A.lmax, lmin = lmax / ratio;
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
+    const double sigma = theta / delta;
+    double rho = 1.0 / sigma;
+    const int64_t N = (int64_t)A.n * BS;
+    double* d0 = A.d;
+    double* d1 = A.d + N;
+    if (x_is_zero) {
+        k_cheb_start_zero<BS><<<hemo_grid(N, 256), 256, 0, st>>>(N, A.dinv, b, 1.0 / theta, A.r, d0, x);
+    } else {
+        k_cheb_start<BS><<<hemo_grid(A.n, 256), 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, A.dinv, b, 1.0 / theta, x,
+                                                              A.r, d0);
+    }
+    HEMO_LAUNCH_CHECK(ctx);
+    bool pending = !x_is_zero;   // x += d0 still to be applied
+    for (int k = 1; k < degree; ++k) {
+        const double rho_new = 1.0 / (2.0 * sigma - rho);
+        const double c1 = rho_new * rho, c2 = 2.0 * rho_new / delta;
+        k_cheb_step<BS><<<hemo_grid(A.n, 256), 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, A.dinv, c1, c2, d0, d1, A.r, x,
+                                                             pending ? 1 : 0);
+        HEMO_LAUNCH_CHECK(ctx);
+        pending = false;
+        double* t = d0; d0 = d1; d1 = t;
+        rho = rho_new;
+    }
+    if (pending) return hemo_axpy(ctx, N, 1.0, d0, x);
+    return 0;
+}
+
+template <int BS>
+static int vcycle_t(hemo_ctx* ctx, HemoAmg* amg, int l, const double* b, double* x, bool x_is_zero) {
+    cudaStream_t st = ctx->stream;
+    const HemoAmgOp& A = amg->op[l];
+    const int degree = ctx->opts.cheb_degree > 0 ? ctx->opts.cheb_degree : 2;
+    const double ratio = ctx->opts.cheb_ratio > 1.0 ? ctx->opts.cheb_ratio : 4.0;
+    if (l == amg->nlev - 1) {
+        const int N = amg->dense_n;
+        // exact solve: any previous iterate is simply replaced
+        k_dense_gemv<<<hemo_grid((int64_t)N * 32, 256), 256, 0, st>>>(N, amg->dense_inv, b, x);
+        HEMO_LAUNCH_CHECK(ctx);
+        return 0;
+    }
+    int rc;
+    if ((rc = smooth_t<BS>(ctx, A, b, x, x_is_zero, degree, ratio))) return rc;
+    // residual and restriction
+    if ((rc = hemo_bsr_spmv_ex(ctx, BS, A.n, A.rowptr, A.col, A.val, x, -1.0, b, A.r))) return rc;
+    const HemoAmgLevel& L = amg->lev[l];
+    HemoAmgOp& C = amg->op[l + 1];
+    k_transfer<BS, false><<<hemo_grid(C.n, 256), 256, 0, st>>>(C.n, L.r_rowptr, L.r_col, L.r_val, A.r, C.b);
+    HEMO_LAUNCH_CHECK(ctx);
+    if ((rc = vcycle_t<BS>(ctx, amg, l + 1, C.b, C.x, true))) return rc;
+    k_transfer<BS, true><<<hemo_grid(A.n, 256), 256, 0, st>>>(A.n, L.p_rowptr, L.p_col, L.p_val, C.x, x);
+    HEMO_LAUNCH_CHECK(ctx);
+    if ((rc = smooth_t<BS>(ctx, A, b, x, false, degree, ratio))) return rc;
+    return 0;
+}
+
+// x = (ncycles V-cycles applied to A x = b, zero initial guess)
+int hemo_amg_vcycle(hemo_ctx* ctx, HemoAmg* amg, const double* b, double* x, int ncycles) {
+    if (!amg->ready) HEMO_FAIL(ctx, HEMO_ESTATE, "AMG hierarchy not finalized");
+    int rc;
+    for (int c = 0; c < (ncycles > 0 ? ncycles : 1); ++c) {
+        if (amg->bs == 2) rc = vcycle_t<2>(ctx, amg, 0, b, x, c == 0);
+        else rc = vcycle_t<1>(ctx, amg, 0, b, x, c == 0);
+        if (rc) return rc;
+    }
+    return 0;
+}

@@ -1,0 +1,191 @@
+// Internal declarations shared by the translation units of libhemo_sm100.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/hemo.h"
+
+#define HEMO_MAXQ 80          // max cell quadrature points per rule (P2 needs 79)
+#define HEMO_MAXFQ 8          // max facet quadrature points
+#define HEMO_NRULES 6
+#define HEMO_MAX_FACET_SETS 8
+#define HEMO_MAX_LEVELS 16
+#define HEMO_DENSE_MAX 1024   // max dofs of the dense coarsest-level solve
+
+struct HemoRule {
+    int nq;
+    int alias;                // lowest block id with an identical rule
+    double phi[HEMO_MAXQ][3];
+    double w[HEMO_MAXQ];
+    double m0, m1[3], m2[6];  // polynomial moments of the rule (reference cell)
+};
+
+struct HemoFacetRule {
+    int nq;
+    double s[HEMO_MAXFQ];
+    double w[HEMO_MAXFQ];
+};
+
+struct HemoFacetSet {
+    int m = 0;
+    int32_t* cells = nullptr;
+    int32_t* mask = nullptr;
+    hemo_facet_coef coef{};
+};
+
+// One operator of a multigrid hierarchy in node-block CSR (BSR with bs x bs blocks).
+struct HemoAmgOp {
+    int n = 0;                 // nodes
+    int64_t nnzb = 0;          // blocks
+    const int32_t* rowptr = nullptr;
+    const int32_t* col = nullptr;
+    double* val = nullptr;     // nnzb*bs*bs
+    double* dinv = nullptr;    // n*bs   inverse diagonal
+    double lmax = 2.0;         // bound of spectrum of D^-1 A
+    double *x = nullptr, *b = nullptr, *r = nullptr, *d = nullptr;  // n*bs work vectors
+};
+
+struct HemoAmgLevel {
+    int n_fine = 0, n_coarse = 0;
+    int32_t *p_rowptr = nullptr, *p_col = nullptr; double* p_val = nullptr;
+    int32_t *r_rowptr = nullptr, *r_col = nullptr; double* r_val = nullptr;
+    int32_t *ap_rowptr = nullptr, *ap_col = nullptr; double* ap_val = nullptr;
+    int32_t *c_rowptr = nullptr, *c_col = nullptr;
+    int64_t nnz_p = 0, nnz_ap = 0, nnz_c = 0;
+};
+
+struct HemoAmg {
+    int bs = 1;
+    int nlev = 0;              // number of operators (levels); nlev-1 transfer levels
+    bool ready = false;
+    HemoAmgLevel lev[HEMO_MAX_LEVELS];
+    HemoAmgOp op[HEMO_MAX_LEVELS];
+    double* dense_inv = nullptr;   // (nc*bs)^2 inverse of the coarsest operator
+    double* dense_work = nullptr;
+    int dense_n = 0;
+};
+
+struct hemo_ctx {
+    int device = 0;
+    cudaStream_t stream = 0;
+    std::string err;
+    int64_t launches = 0;
+
+    // mesh (borrowed)
+    const double* x = nullptr;
+    const int32_t* cells = nullptr;
+    const double* h = nullptr;
+    int n = 0, E = 0;
+    // node graph (borrowed) and derived maps (owned)
+    const int32_t* nrowptr = nullptr;
+    const int32_t* ncol = nullptr;
+    int64_t nnz_node = 0;
+    int32_t* cellpos = nullptr;     // E*9: slot of node b in row of node a
+    int32_t* mseg_ptr = nullptr;    // nnz_node+1 gather segments (matrix)
+    int32_t* mseg_src = nullptr;    // 9E: c*9 + a*3 + b
+    int32_t* vseg_ptr = nullptr;    // n+1 gather segments (vector)
+    int32_t* vseg_src = nullptr;    // 3E: c*3 + a
+    int32_t* diagslot = nullptr;    // n: slot of node i in its own row
+    int32_t* rowof = nullptr;       // nnz_node: row (node) of each slot
+    double* Ae = nullptr;           // 81*E element matrices, SoA [81][E]
+    double* Fe = nullptr;           // 9*E element vectors, SoA [9][E]
+    double* dvec = nullptr;         // 3n lifting vector (g - x on bc dofs)
+
+    // forms
+    hemo_params par{};
+    bool have_par = false;
+    HemoRule rules[HEMO_NRULES];
+    bool have_rule[HEMO_NRULES] = {false, false, false, false, false, false};
+    bool rules_dirty = true;
+    HemoFacetRule frule{};
+    HemoFacetSet fsets[HEMO_MAX_FACET_SETS];
+    uint8_t* dofflag = nullptr;
+    double* dofmult = nullptr;
+    uint8_t* cellflag = nullptr;
+    bool have_bc = false;
+
+    // reductions
+    double* red_partial = nullptr;  // device partial sums
+    size_t red_partial_n = 0;
+    double* red_out = nullptr;      // device results
+    double* red_host = nullptr;     // pinned host staging
+    size_t red_out_n = 0;
+
+    // solver
+    hemo_solver_opts opts{};
+    double schur_mass_coef = 0.0, schur_lap_coef = 0.0;
+    HemoAmg amg[2];
+    const double* mass = nullptr;   // lumped pressure mass (borrowed, n)
+    double* pc_tmp_u = nullptr;     // 2n
+    double* pc_tmp_u2 = nullptr;    // 2n
+    double* pc_tmp_p = nullptr;     // n
+    double* pc_tmp_p2 = nullptr;    // n
+    double* kry_V = nullptr;        // (restart+1)*N
+    double* kry_Z = nullptr;        // restart*N
+    double* kry_w = nullptr;        // N
+    int kry_restart = 0;
+};
+
+#define HEMO_CHECK_CUDA(ctx, expr)                                                     \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess) {                                                       \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);           \
+            return (int)_e;                                                            \
+        }                                                                              \
+    } while (0)
+
+#define HEMO_FAIL(ctx, code, msg)  \
+    do {                           \
+        (ctx)->err = (msg);        \
+        return (code);             \
+    } while (0)
+
+#define HEMO_LAUNCH_CHECK(ctx)                                       \
+    do {                                                             \
+        (ctx)->launches++;                                           \
+        cudaError_t _e = cudaGetLastError();                         \
+        if (_e != cudaSuccess) {                                     \
+            (ctx)->err = std::string("kernel launch: ") +            \
+                         cudaGetErrorString(_e) + " at " + __FILE__ + ":" + std::to_string(__LINE__); \
+            return (int)_e;                                          \
+        }                                                            \
+    } while (0)
+
+template <typename T>
+static inline int hemo_alloc(hemo_ctx* ctx, T** p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) return 0;
+    HEMO_CHECK_CUDA(ctx, cudaMalloc((void**)p, count * sizeof(T)));
+    return 0;
+}
+
+template <typename T>
+static inline int hemo_upload(hemo_ctx* ctx, T** p, const T* src, size_t count, bool src_is_device) {
+    int rc = hemo_alloc(ctx, p, count);
+    if (rc) return rc;
+    if (count == 0) return 0;
+    HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(*p, src, count * sizeof(T),
+                                         src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                         ctx->stream));
+    return 0;
+}
+
+static inline int hemo_grid(int64_t n, int block) {
+    int64_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// implemented in linalg.cu
+int hemo_ensure_reduce(hemo_ctx* ctx, size_t partial_n, size_t out_n);
+int hemo_dot_dev(hemo_ctx* ctx, int64_t n, const double* x, const double* y, double* out_host);
+int hemo_bsr_spmv(hemo_ctx* ctx, int bs, int n, const int32_t* rowptr, const int32_t* col,
+                  const double* val, const double* x, double* y);
+// implemented in amg.cu
+int hemo_amg_numeric(hemo_ctx* ctx, HemoAmg* amg);
+int hemo_amg_vcycle(hemo_ctx* ctx, HemoAmg* amg, const double* b, double* x, int ncycles);
+void hemo_amg_free(HemoAmg* amg);

@@ -1,0 +1,423 @@
+// Sparse matrix-vector products and Krylov vector kernels (fp64, HBM-bound).
+//
+// Replaces PETSc MatMult / VecMDot / VecMAXPY / VecNorm used inside
+// KSPSolve(fgmres) configured at reference src/solvers/stabilized_schur.py:226-229.
+//
+// The monolithic Jacobian keeps the reference CSR layout (rows [u|p], columns
+// ascending), but all three rows of a mesh node share one column structure,
+// so the SpMV walks the *node graph*: 4 bytes of index per 72 bytes of values.
+// All reductions are two-stage with a fixed grid and a fixed summation order
+// (bitwise reproducible, no atomics).
+#include "hemo_internal.cuh"
+
+#define RED_BLOCKS 1184   // 148 SMs * 8
+#define RED_THREADS 256
+
+int hemo_ensure_reduce(hemo_ctx* ctx, size_t partial_n, size_t out_n) {
+    if (partial_n > ctx->red_partial_n) {
+        int rc = hemo_alloc(ctx, &ctx->red_partial, partial_n);
+        if (rc) return rc;
+        ctx->red_partial_n = partial_n;
+    }
+    if (out_n > ctx->red_out_n) {
+        int rc = hemo_alloc(ctx, &ctx->red_out, out_n);
+        if (rc) return rc;
+        if (ctx->red_host) cudaFreeHost(ctx->red_host);
+        HEMO_CHECK_CUDA(ctx, cudaMallocHost((void**)&ctx->red_host, out_n * sizeof(double)));
+        ctx->red_out_n = out_n;
+    }
+    return 0;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    // blockDim.x == RED_THREADS (8 warps); result valid in thread 0
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (wid == 0) {
+        r = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;
+}
+
+// ---------------------------------------------------------------------------
+// node-structured SpMV on the monolithic matrix:  y = b + alpha * A[rows, cols] x
+// 8 lanes per node row-group.
+// ---------------------------------------------------------------------------
+template <bool RU, bool RP, bool CU, bool CP>
+__global__ void __launch_bounds__(256)
+k_spmv_node(int n, int64_t nnz_node, const int32_t* __restrict__ nrowptr, const int32_t* __restrict__ ncol,
+            const double* __restrict__ vals, const double* __restrict__ xu, const double* __restrict__ xp,
+            double alpha, const double* __restrict__ bu, const double* __restrict__ bp,
+            double* __restrict__ yu, double* __restrict__ yp) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt >> 3;
+    const int lane = gt & 7;
+    const bool ok = i < n;   // no early return: full-mask shuffles below
+    const int r0 = ok ? nrowptr[i] : 0;
+    const int deg = ok ? nrowptr[i + 1] - r0 : 0;
+    const int64_t ru0 = 6 * (int64_t)r0, ru1 = ru0 + 3 * deg, rp = 6 * nnz_node + 3 * (int64_t)r0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int t = lane; t < deg; t += 8) {
+        const int j = ncol[r0 + t];
+        double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+        if (CU) {
+            const double2 xv = reinterpret_cast<const double2*>(xu)[j];
+            x0 = xv.x; x1 = xv.y;
+        }
+        if (CP) x2 = xp[j];
+        if (RU) {
+            if (CU) {
+                a0 += vals[ru0 + 2 * t] * x0 + vals[ru0 + 2 * t + 1] * x1;
+                a1 += vals[ru1 + 2 * t] * x0 + vals[ru1 + 2 * t + 1] * x1;
+            }
+            if (CP) {
+                a0 += vals[ru0 + 2 * deg + t] * x2;
+                a1 += vals[ru1 + 2 * deg + t] * x2;
+            }
+        }
+        if (RP) {
+            if (CU) a2 += vals[rp + 2 * t] * x0 + vals[rp + 2 * t + 1] * x1;
+            if (CP) a2 += vals[rp + 2 * deg + t] * x2;
+        }
+    }
+    // reduce over the 8 lanes of the group
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        a0 += __shfl_down_sync(0xffffffffu, a0, o, 8);
+        a1 += __shfl_down_sync(0xffffffffu, a1, o, 8);
+        a2 += __shfl_down_sync(0xffffffffu, a2, o, 8);
+    }
+    if (ok && lane == 0) {
+        if (RU) {
+            double r0v = alpha * a0, r1v = alpha * a1;
+            if (bu) { r0v += bu[2 * (int64_t)i]; r1v += bu[2 * (int64_t)i + 1]; }
+            yu[2 * (int64_t)i] = r0v;
+            yu[2 * (int64_t)i + 1] = r1v;
+        }
+        if (RP) {
+            double r2v = alpha * a2;
+            if (bp) r2v += bp[i];
+            yp[i] = r2v;
+        }
+    }
+}
+
+// sub-block dispatch used by the preconditioner (rows/cols: 1 = u, 2 = p, 3 = both)
+int hemo_spmv_block(hemo_ctx* ctx, int rows, int cols, const double* vals, const double* xu, const double* xp,
+                    double alpha, const double* bu, const double* bp, double* yu, double* yp) {
+    const int n = ctx->n;
+    const int grid = hemo_grid((int64_t)n * 8, 256);
+    cudaStream_t st = ctx->stream;
+#define LAUNCH(RU, RP, CU, CP)                                                                        \
+    k_spmv_node<RU, RP, CU, CP><<<grid, 256, 0, st>>>(n, ctx->nnz_node, ctx->nrowptr, ctx->ncol, vals, \
+                                                      xu, xp, alpha, bu, bp, yu, yp)
+    if (rows == 3 && cols == 3) LAUNCH(true, true, true, true);
+    else if (rows == 1 && cols == 1) LAUNCH(true, false, true, false);
+    else if (rows == 1 && cols == 2) LAUNCH(true, false, false, true);
+    else if (rows == 2 && cols == 1) LAUNCH(false, true, true, false);
+    else if (rows == 2 && cols == 2) LAUNCH(false, true, false, true);
+    else HEMO_FAIL(ctx, HEMO_EINVAL, "unsupported sub-block");
+#undef LAUNCH
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+extern "C" int hemo_spmv(hemo_ctx* ctx, const double* vals_dev, const double* x_dev, double* y_dev) {
+    if (!ctx || !vals_dev || !x_dev || !y_dev) return HEMO_EINVAL;
+    if (!ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "node graph not set");
+    const int64_t n = ctx->n;
+    return hemo_spmv_block(ctx, 3, 3, vals_dev, x_dev, x_dev + 2 * n, 1.0, nullptr, nullptr, y_dev, y_dev + 2 * n);
+}
+
+// ---------------------------------------------------------------------------
+// BSR SpMV for multigrid operators: y = b + alpha * A x (bs = 1 or 2)
+// ---------------------------------------------------------------------------
+template <int BS>
+__global__ void __launch_bounds__(256)
+k_bsr_spmv(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+           const double* __restrict__ val, const double* __restrict__ x, double alpha,
+           const double* __restrict__ b, double* __restrict__ y) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt >> 2;        // 4 lanes per block row
+    const int lane = gt & 3;
+    const bool ok = i < n;
+    const int r0 = ok ? rowptr[i] : 0, r1 = ok ? rowptr[i + 1] : 0;
+    double a0 = 0.0, a1 = 0.0;
+    for (int t = r0 + lane; t < r1; t += 4) {
+        const int j = col[t];
+        if (BS == 1) {
+            a0 += val[t] * x[j];
+        } else {
+            const double2 xv = reinterpret_cast<const double2*>(x)[j];
+            const double2 v0 = reinterpret_cast<const double2*>(val)[2 * (int64_t)t];
+            const double2 v1 = reinterpret_cast<const double2*>(val)[2 * (int64_t)t + 1];
+            a0 += v0.x * xv.x + v0.y * xv.y;
+            a1 += v1.x * xv.x + v1.y * xv.y;
+        }
+    }
+#pragma unroll
+    for (int o = 2; o > 0; o >>= 1) {
+        a0 += __shfl_down_sync(0xffffffffu, a0, o, 4);
+        if (BS == 2) a1 += __shfl_down_sync(0xffffffffu, a1, o, 4);
+    }
+    if (ok && lane == 0) {
+        if (BS == 1) {
+            y[i] = (b ? b[i] : 0.0) + alpha * a0;
+        } else {
+            y[2 * (int64_t)i] = (b ? b[2 * (int64_t)i] : 0.0) + alpha * a0;
+            y[2 * (int64_t)i + 1] = (b ? b[2 * (int64_t)i + 1] : 0.0) + alpha * a1;
+        }
+    }
+}
+
+int hemo_bsr_spmv_ex(hemo_ctx* ctx, int bs, int n, const int32_t* rowptr, const int32_t* col, const double* val,
+                     const double* x, double alpha, const double* b, double* y) {
+    const int grid = hemo_grid((int64_t)n * 4, 256);
+    if (bs == 1) k_bsr_spmv<1><<<grid, 256, 0, ctx->stream>>>(n, rowptr, col, val, x, alpha, b, y);
+    else k_bsr_spmv<2><<<grid, 256, 0, ctx->stream>>>(n, rowptr, col, val, x, alpha, b, y);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int hemo_bsr_spmv(hemo_ctx* ctx, int bs, int n, const int32_t* rowptr, const int32_t* col, const double* val,
+                  const double* x, double* y) {
+    return hemo_bsr_spmv_ex(ctx, bs, n, rowptr, col, val, x, 1.0, nullptr, y);
+}
+
+// ---------------------------------------------------------------------------
+// vector kernels
+// ---------------------------------------------------------------------------
+__global__ void k_axpy(int64_t n, double a, const double* __restrict__ x, double* __restrict__ y) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = fma(a, x[i], y[i]);
+}
+
+__global__ void k_scale_copy(int64_t n, double a, const double* __restrict__ x, double* __restrict__ y) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = a * x[i];
+}
+
+// y = x * (1 / s[0]) with s on the device
+__global__ void k_scale_inv_dev(int64_t n, const double* __restrict__ s, const double* __restrict__ x,
+                                double* __restrict__ y) {
+    const double a = 1.0 / s[0];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = a * x[i];
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+k_dot_partial(int64_t n, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ partial) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc = fma(x[i], y[i], acc);
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+// out[k] = sum_b partial[k * nblk + b], one block per k, fixed order
+__global__ void __launch_bounds__(RED_THREADS)
+k_reduce_final(int nblk, const double* __restrict__ partial, double* __restrict__ out, int sqrt_last_k) {
+    __shared__ double sh[32];
+    const int k = blockIdx.x;
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) acc += partial[(int64_t)k * nblk + b];
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) out[k] = (sqrt_last_k >= 0 && k == sqrt_last_k) ? sqrt(acc) : acc;
+}
+
+static int grid_for(int64_t n) {
+    int64_t g = (n + RED_THREADS - 1) / RED_THREADS;
+    if (g > RED_BLOCKS) g = RED_BLOCKS;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+extern "C" int hemo_axpy(hemo_ctx* ctx, int64_t n, double a, const double* x_dev, double* y_dev) {
+    if (!ctx || !x_dev || !y_dev || n < 0) return HEMO_EINVAL;
+    k_axpy<<<grid_for(n), RED_THREADS, 0, ctx->stream>>>(n, a, x_dev, y_dev);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int hemo_scale_copy(hemo_ctx* ctx, int64_t n, double a, const double* x, double* y) {
+    k_scale_copy<<<grid_for(n), RED_THREADS, 0, ctx->stream>>>(n, a, x, y);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int hemo_scale_inv_dev(hemo_ctx* ctx, int64_t n, const double* s_dev, const double* x, double* y) {
+    k_scale_inv_dev<<<grid_for(n), RED_THREADS, 0, ctx->stream>>>(n, s_dev, x, y);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// dot product left on the device in ctx->red_out[slot]
+int hemo_dot_to_slot(hemo_ctx* ctx, int64_t n, const double* x, const double* y, int slot, bool take_sqrt) {
+    int rc = hemo_ensure_reduce(ctx, RED_BLOCKS * 8, 512);
+    if (rc) return rc;
+    const int g = grid_for(n);
+    k_dot_partial<<<g, RED_THREADS, 0, ctx->stream>>>(n, x, y, ctx->red_partial);
+    HEMO_LAUNCH_CHECK(ctx);
+    k_reduce_final<<<1, RED_THREADS, 0, ctx->stream>>>(g, ctx->red_partial, ctx->red_out + slot, take_sqrt ? 0 : -1);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int hemo_dot_dev(hemo_ctx* ctx, int64_t n, const double* x, const double* y, double* out_host) {
+    int rc = hemo_dot_to_slot(ctx, n, x, y, 0, false);
+    if (rc) return rc;
+    HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->red_host, ctx->red_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out_host = ctx->red_host[0];
+    return 0;
+}
+
+extern "C" int hemo_dot(hemo_ctx* ctx, int64_t n, const double* x_dev, const double* y_dev, double* out_host) {
+    if (!ctx || !x_dev || !y_dev || !out_host || n < 0) return HEMO_EINVAL;
+    return hemo_dot_dev(ctx, n, x_dev, y_dev, out_host);
+}
+
+extern "C" int hemo_norm2(hemo_ctx* ctx, int64_t n, const double* x_dev, double* out_host) {
+    if (!ctx || !x_dev || !out_host || n < 0) return HEMO_EINVAL;
+    double d = 0.0;
+    int rc = hemo_dot_dev(ctx, n, x_dev, x_dev, &d);
+    if (rc) return rc;
+    *out_host = sqrt(d);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Gram–Schmidt kernels for (F)GMRES: classical GS, one pass each
+//   mdot:  h[i] = V_i . w  for i < k  (w read once per tile, V streamed)
+//   maxpy: w -= sum_i h[i] V_i ; partial ||w||^2 in the same pass
+// ---------------------------------------------------------------------------
+#define MD_TILE 8   // elements per thread held in registers
+
+__global__ void __launch_bounds__(RED_THREADS)
+k_mdot_partial(int64_t n, int k, const double* __restrict__ V, int64_t ldv, const double* __restrict__ w,
+               double* __restrict__ partial /*[k][gridDim.x]*/) {
+    __shared__ double sh[32];
+    extern __shared__ double acc_sh[];   // k running sums of this block (thread 0 only)
+    const int64_t tile = (int64_t)RED_THREADS * MD_TILE;
+    const int64_t ntiles = (n + tile - 1) / tile;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) acc_sh[i] = 0.0;
+    __syncthreads();
+    for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+        const int64_t base = tl * tile + threadIdx.x;
+        double wr[MD_TILE];
+#pragma unroll
+        for (int e = 0; e < MD_TILE; ++e) {
+            const int64_t idx = base + (int64_t)e * RED_THREADS;
+            wr[e] = (idx < n) ? w[idx] : 0.0;
+        }
+        for (int i = 0; i < k; ++i) {
+            const double* Vi = V + (int64_t)i * ldv;
+            double a = 0.0;
+#pragma unroll
+            for (int e = 0; e < MD_TILE; ++e) {
+                const int64_t idx = base + (int64_t)e * RED_THREADS;
+                if (idx < n) a = fma(Vi[idx], wr[e], a);
+            }
+            a = block_sum(a, sh);
+            if (threadIdx.x == 0) acc_sh[i] += a;   // fixed tile order per block
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < k; i += blockDim.x) partial[(int64_t)i * gridDim.x + blockIdx.x] = acc_sh[i];
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+k_maxpy_norm(int64_t n, int k, const double* __restrict__ V, int64_t ldv, const double* __restrict__ hcoef,
+             double sign, double* __restrict__ w, double* __restrict__ partial) {
+    __shared__ double sh[32];
+    extern __shared__ double hsh[];
+    for (int i = threadIdx.x; i < k; i += blockDim.x) hsh[i] = hcoef[i];
+    __syncthreads();
+    double nrm = 0.0;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+        double acc = w[idx];
+        for (int i = 0; i < k; ++i) acc = fma(sign * hsh[i], V[(int64_t)i * ldv + idx], acc);
+        w[idx] = acc;
+        nrm = fma(acc, acc, nrm);
+    }
+    nrm = block_sum(nrm, sh);
+    if (threadIdx.x == 0 && partial) partial[blockIdx.x] = nrm;
+}
+
+// h (device, ctx->red_out[0..k)) = V^T w ; copies h to red_host and syncs
+int hemo_mdot(hemo_ctx* ctx, int64_t n, int k, const double* V, int64_t ldv, const double* w, double* h_host) {
+    int rc = hemo_ensure_reduce(ctx, (size_t)RED_BLOCKS * (size_t)(k + 2), 512 > k + 2 ? 512 : (size_t)k + 2);
+    if (rc) return rc;
+    // w is re-read once per basis vector from L2/HBM; V dominates the traffic.
+    int g = grid_for((n + MD_TILE - 1) / MD_TILE);
+    k_mdot_partial<<<g, RED_THREADS, sizeof(double) * k, ctx->stream>>>(n, k, V, ldv, w, ctx->red_partial);
+    HEMO_LAUNCH_CHECK(ctx);
+    k_reduce_final<<<k, RED_THREADS, 0, ctx->stream>>>(g, ctx->red_partial, ctx->red_out, -1);
+    HEMO_LAUNCH_CHECK(ctx);
+    HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->red_host, ctx->red_out, sizeof(double) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < k; ++i) h_host[i] = ctx->red_host[i];
+    return 0;
+}
+
+// w += sign * sum_i h[i] V_i using the coefficients in hcoef_dev; returns ||w|| if norm_host
+int hemo_maxpy(hemo_ctx* ctx, int64_t n, int k, const double* V, int64_t ldv, const double* hcoef_dev, double sign,
+               double* w, double* norm_host) {
+    int rc = hemo_ensure_reduce(ctx, (size_t)RED_BLOCKS * 2, 512);
+    if (rc) return rc;
+    const int g = grid_for(n);
+    k_maxpy_norm<<<g, RED_THREADS, sizeof(double) * (k > 0 ? k : 1), ctx->stream>>>(
+        n, k, V, ldv, hcoef_dev, sign, w, norm_host ? ctx->red_partial : nullptr);
+    HEMO_LAUNCH_CHECK(ctx);
+    if (norm_host) {
+        k_reduce_final<<<1, RED_THREADS, 0, ctx->stream>>>(g, ctx->red_partial, ctx->red_out + 500, 0);
+        HEMO_LAUNCH_CHECK(ctx);
+        HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->red_host + 500, ctx->red_out + 500, sizeof(double),
+                                             cudaMemcpyDeviceToHost, ctx->stream));
+        HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *norm_host = ctx->red_host[500];
+    }
+    return 0;
+}
+
+// mean removal on the device (constant-pressure null space): x -= sum(x)/n
+__global__ void k_sub_mean(int64_t n, const double* __restrict__ sum, double* __restrict__ x) {
+    const double m = sum[0] / (double)n;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        x[i] -= m;
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+k_sum_partial(int64_t n, const double* __restrict__ x, double* __restrict__ partial) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc += x[i];
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+int hemo_remove_mean(hemo_ctx* ctx, int64_t n, double* x) {
+    int rc = hemo_ensure_reduce(ctx, (size_t)RED_BLOCKS * 2, 512);
+    if (rc) return rc;
+    const int g = grid_for(n);
+    k_sum_partial<<<g, RED_THREADS, 0, ctx->stream>>>(n, x, ctx->red_partial);
+    HEMO_LAUNCH_CHECK(ctx);
+    k_reduce_final<<<1, RED_THREADS, 0, ctx->stream>>>(g, ctx->red_partial, ctx->red_out + 501, -1);
+    HEMO_LAUNCH_CHECK(ctx);
+    k_sub_mean<<<g, RED_THREADS, 0, ctx->stream>>>(n, ctx->red_out + 501, x);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}

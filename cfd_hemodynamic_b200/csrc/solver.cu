@@ -1,0 +1,303 @@
+// Block-Schur preconditioner and right-preconditioned FGMRES.
+//
+// Replaces KSP(fgmres) + PC(fieldsplit, SCHUR) configured by the reference at
+// src/solvers/stabilized_schur.py:226-275.  Differences by design:
+//   * upper block-triangular factorisation (one A00^-1 per application) instead of FULL;
+//   * A00^-1 ~ AMG V-cycle(s) instead of GMRES(30)+ASM/ILU(0);
+//   * S^-1 ~ c_m diag(Mp)^-1 + c_L Lp^-1 (Cahouet–Chabard) with an AMG V-cycle on
+//     the pressure Laplacian instead of ILU(0) on SELFP.
+// Parity with the reference is therefore on the converged solution, never on
+// iteration counts.
+#include <math.h>
+
+#include "hemo_internal.cuh"
+
+int hemo_spmv_block(hemo_ctx* ctx, int rows, int cols, const double* vals, const double* xu, const double* xp,
+                    double alpha, const double* bu, const double* bp, double* yu, double* yp);
+int hemo_scale_copy(hemo_ctx* ctx, int64_t n, double a, const double* x, double* y);
+int hemo_mdot(hemo_ctx* ctx, int64_t n, int k, const double* V, int64_t ldv, const double* w, double* h_host);
+int hemo_maxpy(hemo_ctx* ctx, int64_t n, int k, const double* V, int64_t ldv, const double* hcoef_dev, double sign,
+               double* w, double* norm_host);
+int hemo_remove_mean(hemo_ctx* ctx, int64_t n, double* x);
+int hemo_amg_numeric_shift(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift);
+
+// A00 (2x2 node blocks) out of the monolithic CSR values
+__global__ void __launch_bounds__(256)
+k_extract_a00(int64_t nnz_node, const int32_t* __restrict__ nrowptr, const int32_t* __restrict__ rowof,
+              const double* __restrict__ vals, double* __restrict__ out) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= nnz_node) return;
+    const int i = rowof[s];
+    const int r0 = nrowptr[i];
+    const int deg = nrowptr[i + 1] - r0;
+    const int t = (int)(s - r0);
+    const int64_t ru0 = 6 * (int64_t)r0, ru1 = ru0 + 3 * deg;
+    double2 a, b;
+    a.x = vals[ru0 + 2 * t]; a.y = vals[ru0 + 2 * t + 1];
+    b.x = vals[ru1 + 2 * t]; b.y = vals[ru1 + 2 * t + 1];
+    reinterpret_cast<double2*>(out)[2 * s] = a;
+    reinterpret_cast<double2*>(out)[2 * s + 1] = b;
+}
+
+// pressure Laplacian with identity rows/cols on Dirichlet pressure dofs
+__global__ void __launch_bounds__(256)
+k_lap_with_bc(int n, int64_t nnz_node, const int32_t* __restrict__ rowof, const int32_t* __restrict__ ncol,
+              const double* __restrict__ lap, const uint8_t* __restrict__ dofflag, double* __restrict__ out) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= nnz_node) return;
+    double v = lap[s];
+    if (dofflag) {
+        const int i = rowof[s], j = ncol[s];
+        const bool fi = dofflag[2 * (int64_t)n + i] != 0, fj = dofflag[2 * (int64_t)n + j] != 0;
+        if (fi || fj) v = (i == j) ? 1.0 : 0.0;
+    }
+    out[s] = v;
+}
+
+// z_p = c_m t_p / mass + c_L q_p ; Dirichlet pressure dofs: z_p = r_p
+__global__ void k_schur_combine(int n, double cm, double cl, const double* __restrict__ tp,
+                                const double* __restrict__ mass, const double* __restrict__ qp,
+                                const uint8_t* __restrict__ dofflag, const double* __restrict__ rp,
+                                double* __restrict__ zp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = cm * tp[i] / mass[i] + cl * qp[i];
+    if (dofflag && dofflag[2 * (int64_t)n + i]) v = rp[i];
+    zp[i] = v;
+}
+
+extern "C" int hemo_set_solver_opts(hemo_ctx* ctx, const hemo_solver_opts* o) {
+    if (!ctx || !o) return HEMO_EINVAL;
+    if (o->restart < 1 || o->restart > 400 || o->max_it < 1) return HEMO_EINVAL;
+    ctx->opts = *o;
+    return 0;
+}
+
+extern "C" int hemo_pc_setup(hemo_ctx* ctx, const double* vals_dev, const double* lap_vals_dev,
+                             const double* mass_dev) {
+    if (!ctx || !vals_dev) return HEMO_EINVAL;
+    if (!ctx->amg[0].ready || !ctx->amg[1].ready) HEMO_FAIL(ctx, HEMO_ESTATE, "AMG hierarchies not finalized");
+    const int n = ctx->n;
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if (!ctx->pc_tmp_u) {
+        if ((rc = hemo_alloc(ctx, &ctx->pc_tmp_u, (size_t)2 * n))) return rc;
+        if ((rc = hemo_alloc(ctx, &ctx->pc_tmp_u2, (size_t)2 * n))) return rc;
+        if ((rc = hemo_alloc(ctx, &ctx->pc_tmp_p, (size_t)n))) return rc;
+        if ((rc = hemo_alloc(ctx, &ctx->pc_tmp_p2, (size_t)n))) return rc;
+    }
+    k_extract_a00<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(ctx->nnz_node, ctx->nrowptr, ctx->rowof, vals_dev,
+                                                                 ctx->amg[0].op[0].val);
+    HEMO_LAUNCH_CHECK(ctx);
+    if ((rc = hemo_amg_numeric_shift(ctx, &ctx->amg[0], 0.0))) return rc;
+    if (lap_vals_dev) {
+        if (!mass_dev) return HEMO_EINVAL;
+        ctx->mass = mass_dev;
+        k_lap_with_bc<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(n, ctx->nnz_node, ctx->rowof, ctx->ncol, lap_vals_dev,
+                                                                     ctx->have_bc ? ctx->dofflag : nullptr,
+                                                                     ctx->amg[1].op[0].val);
+        HEMO_LAUNCH_CHECK(ctx);
+        if ((rc = hemo_amg_numeric_shift(ctx, &ctx->amg[1], ctx->opts.project_pressure ? 1e-8 : 0.0))) return rc;
+    }
+    if (!ctx->mass) HEMO_FAIL(ctx, HEMO_ESTATE, "first hemo_pc_setup call needs lap_vals and mass");
+    return 0;
+}
+
+extern "C" int hemo_amg_apply(hemo_ctx* ctx, int which, const double* b_dev, double* x_dev, int ncycles) {
+    if (!ctx || which < 0 || which > 1 || !b_dev || !x_dev) return HEMO_EINVAL;
+    return hemo_amg_vcycle(ctx, &ctx->amg[which], b_dev, x_dev, ncycles);
+}
+
+extern "C" int hemo_amg_get_level_values(hemo_ctx* ctx, int which, int level, double* vals_dev, int64_t capacity) {
+    if (!ctx || which < 0 || which > 1 || !vals_dev) return HEMO_EINVAL;
+    HemoAmg& amg = ctx->amg[which];
+    if (!amg.ready || level < 0 || level >= amg.nlev) return HEMO_EINVAL;
+    const int64_t cnt = amg.op[level].nnzb * amg.bs * amg.bs;
+    if (capacity < cnt) return HEMO_EINVAL;
+    HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(vals_dev, amg.op[level].val, sizeof(double) * cnt, cudaMemcpyDeviceToDevice,
+                                         ctx->stream));
+    return 0;
+}
+
+extern "C" int hemo_pc_apply(hemo_ctx* ctx, const double* vals_dev, const double* r_dev, double* z_dev) {
+    if (!ctx || !vals_dev || !r_dev || !z_dev) return HEMO_EINVAL;
+    if (!ctx->mass || !ctx->pc_tmp_u) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_pc_setup not called");
+    const int n = ctx->n;
+    cudaStream_t st = ctx->stream;
+    const double* ru = r_dev;
+    const double* rp = r_dev + 2 * (int64_t)n;
+    double* zu = z_dev;
+    double* zp = z_dev + 2 * (int64_t)n;
+    double* tp = ctx->pc_tmp_p;
+    double* qp = ctx->pc_tmp_p2;
+    double* tu = ctx->pc_tmp_u;
+    int rc;
+    HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(tp, rp, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    if (ctx->opts.project_pressure && (rc = hemo_remove_mean(ctx, n, tp))) return rc;
+    if ((rc = hemo_amg_vcycle(ctx, &ctx->amg[1], tp, qp, ctx->opts.amg_cycles_p))) return rc;
+    k_schur_combine<<<hemo_grid(n, 256), 256, 0, st>>>(n, ctx->opts.schur_mass_coef, ctx->opts.schur_lap_coef, tp,
+                                                       ctx->mass, qp, ctx->have_bc ? ctx->dofflag : nullptr, rp, zp);
+    HEMO_LAUNCH_CHECK(ctx);
+    if (ctx->opts.project_pressure && (rc = hemo_remove_mean(ctx, n, zp))) return rc;
+    // t_u = r_u - A01 z_p
+    if ((rc = hemo_spmv_block(ctx, 1, 2, vals_dev, nullptr, zp, -1.0, ru, nullptr, tu, nullptr))) return rc;
+    if ((rc = hemo_amg_vcycle(ctx, &ctx->amg[0], tu, zu, ctx->opts.amg_cycles_u))) return rc;
+    return 0;
+}
+
+static int ensure_krylov(hemo_ctx* ctx, int restart, int64_t ldv) {
+    if (ctx->kry_restart >= restart && ctx->kry_V) return 0;
+    int rc;
+    if ((rc = hemo_alloc(ctx, &ctx->kry_V, (size_t)(restart + 1) * ldv))) return rc;
+    if ((rc = hemo_alloc(ctx, &ctx->kry_Z, (size_t)restart * ldv))) return rc;
+    if ((rc = hemo_alloc(ctx, &ctx->kry_w, (size_t)ldv + 512))) return rc;
+    ctx->kry_restart = restart;
+    return 0;
+}
+
+extern "C" int hemo_fgmres(hemo_ctx* ctx, const double* vals_dev, const double* b_dev, double* y_dev,
+                           int* its_out, double* rel_resid_out) {
+    if (!ctx || !vals_dev || !b_dev || !y_dev) return HEMO_EINVAL;
+    const int n = ctx->n;
+    const int64_t N = 3 * (int64_t)n;
+    const int64_t ldv = (N + 31) / 32 * 32;
+    const int m = ctx->opts.restart;
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if ((rc = ensure_krylov(ctx, m, ldv))) return rc;
+    if ((rc = hemo_ensure_reduce(ctx, (size_t)1184 * (m + 3), 512))) return rc;
+    double* V = ctx->kry_V;
+    double* Z = ctx->kry_Z;
+    double* w = ctx->kry_w;
+    double* coef_dev = ctx->kry_w + ldv;   // m+1 doubles of device scratch for the update coefficients
+    std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), hcol(m + 2), yk(m);
+
+    HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(y_dev, 0, sizeof(double) * N, st));
+    double bnorm = 0.0;
+    if ((rc = hemo_norm2(ctx, N, b_dev, &bnorm))) return rc;
+    int its = 0;
+    double res = bnorm;
+    const double tol = fmax(ctx->opts.rtol * bnorm, ctx->opts.atol);
+    if (bnorm == 0.0 || bnorm <= ctx->opts.atol) {
+        if (its_out) *its_out = 0;
+        if (rel_resid_out) *rel_resid_out = 0.0;
+        return 0;
+    }
+    bool converged = false;
+    double beta = bnorm;
+    // r0 = b (zero initial guess)
+    if ((rc = hemo_scale_copy(ctx, N, 1.0 / beta, b_dev, V))) return rc;
+    while (!converged && its < ctx->opts.max_it) {
+        for (int i = 0; i <= m; ++i) g[i] = 0.0;
+        g[0] = beta;
+        int j = 0;
+        for (; j < m && its < ctx->opts.max_it; ++j) {
+            double* vj = V + (int64_t)j * ldv;
+            double* zj = Z + (int64_t)j * ldv;
+            if ((rc = hemo_pc_apply(ctx, vals_dev, vj, zj))) return rc;
+            if ((rc = hemo_spmv(ctx, vals_dev, zj, w))) return rc;
+            // classical Gram–Schmidt (PETSc default: no refinement)
+            if ((rc = hemo_mdot(ctx, N, j + 1, V, ldv, w, hcol.data()))) return rc;
+            double hn = 0.0;
+            if ((rc = hemo_maxpy(ctx, N, j + 1, V, ldv, ctx->red_out, -1.0, w, &hn))) return rc;
+            for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = hcol[i];
+            H[(size_t)(j + 1) * m + j] = hn;
+            if (hn > 0.0) {
+                if ((rc = hemo_scale_copy(ctx, N, 1.0 / hn, w, V + (int64_t)(j + 1) * ldv))) return rc;
+            }
+            // Givens rotations
+            for (int i = 0; i < j; ++i) {
+                const double a = H[(size_t)i * m + j], b2 = H[(size_t)(i + 1) * m + j];
+                H[(size_t)i * m + j] = cs[i] * a + sn[i] * b2;
+                H[(size_t)(i + 1) * m + j] = -sn[i] * a + cs[i] * b2;
+            }
+            const double a = H[(size_t)j * m + j], b2 = H[(size_t)(j + 1) * m + j];
+            const double d = hypot(a, b2);
+            cs[j] = (d > 0.0) ? a / d : 1.0;
+            sn[j] = (d > 0.0) ? b2 / d : 0.0;
+            H[(size_t)j * m + j] = d;
+            H[(size_t)(j + 1) * m + j] = 0.0;
+            g[j + 1] = -sn[j] * g[j];
+            g[j] = cs[j] * g[j];
+            ++its;
+            res = fabs(g[j + 1]);
+            if (!isfinite(res)) HEMO_FAIL(ctx, HEMO_DIVERGED, "FGMRES residual is not finite");
+            if (res <= tol || hn == 0.0) { converged = true; ++j; break; }
+        }
+        // y += Z_k * (H_k^-1 g_k)
+        const int k = j;
+        for (int i = k - 1; i >= 0; --i) {
+            double s = g[i];
+            for (int l = i + 1; l < k; ++l) s -= H[(size_t)i * m + l] * yk[l];
+            yk[i] = s / H[(size_t)i * m + i];
+        }
+        for (int i = 0; i < k; ++i) ctx->red_host[i] = yk[i];
+        HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(coef_dev, ctx->red_host, sizeof(double) * k, cudaMemcpyHostToDevice, st));
+        if ((rc = hemo_maxpy(ctx, N, k, Z, ldv, coef_dev, 1.0, y_dev, nullptr))) return rc;
+        HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(st));   // red_host is reused below
+        if (converged) break;
+        // restart: r = b - A y
+        if ((rc = hemo_spmv_block(ctx, 3, 3, vals_dev, y_dev, y_dev + 2 * (int64_t)n, -1.0, b_dev, b_dev + 2 * (int64_t)n,
+                                  w, w + 2 * (int64_t)n)))
+            return rc;
+        if ((rc = hemo_norm2(ctx, N, w, &beta))) return rc;
+        res = beta;
+        if (beta <= tol) { converged = true; break; }
+        if ((rc = hemo_scale_copy(ctx, N, 1.0 / beta, w, V))) return rc;
+    }
+    if (its_out) *its_out = its;
+    if (rel_resid_out) *rel_resid_out = res / bnorm;
+    if (!converged) HEMO_FAIL(ctx, HEMO_DIVERGED, "FGMRES reached max_it without converging");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+extern "C" int hemo_ctx_create(int device, hemo_ctx** out) {
+    if (!out) return HEMO_EINVAL;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return (int)e;
+    hemo_ctx* ctx = new hemo_ctx();
+    ctx->device = device;
+    ctx->opts.restart = 60;
+    ctx->opts.max_it = 1000;
+    ctx->opts.rtol = 1e-5;
+    ctx->opts.atol = 1e-50;
+    ctx->opts.amg_cycles_u = 1;
+    ctx->opts.amg_cycles_p = 1;
+    ctx->opts.cheb_degree = 2;
+    ctx->opts.project_pressure = 0;
+    ctx->opts.pc_mode = 0;
+    ctx->opts.schur_mass_coef = 0.0;
+    ctx->opts.schur_lap_coef = 1.0;
+    ctx->opts.cheb_ratio = 4.0;
+    *out = ctx;
+    return 0;
+}
+
+extern "C" int hemo_ctx_destroy(hemo_ctx* ctx) {
+    if (!ctx) return HEMO_EINVAL;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->cellpos); cudaFree(ctx->mseg_ptr); cudaFree(ctx->mseg_src); cudaFree(ctx->vseg_ptr);
+    cudaFree(ctx->vseg_src); cudaFree(ctx->diagslot); cudaFree(ctx->rowof); cudaFree(ctx->Ae); cudaFree(ctx->Fe);
+    cudaFree(ctx->dvec); cudaFree(ctx->dofflag); cudaFree(ctx->dofmult); cudaFree(ctx->cellflag);
+    for (int s = 0; s < HEMO_MAX_FACET_SETS; ++s) { cudaFree(ctx->fsets[s].cells); cudaFree(ctx->fsets[s].mask); }
+    cudaFree(ctx->red_partial); cudaFree(ctx->red_out);
+    if (ctx->red_host) cudaFreeHost(ctx->red_host);
+    hemo_amg_free(&ctx->amg[0]); hemo_amg_free(&ctx->amg[1]);
+    cudaFree(ctx->pc_tmp_u); cudaFree(ctx->pc_tmp_u2); cudaFree(ctx->pc_tmp_p); cudaFree(ctx->pc_tmp_p2);
+    cudaFree(ctx->kry_V); cudaFree(ctx->kry_Z); cudaFree(ctx->kry_w);
+    delete ctx;
+    return 0;
+}
+
+extern "C" const char* hemo_last_error(hemo_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int hemo_set_stream(hemo_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return HEMO_EINVAL;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+extern "C" int64_t hemo_launch_count(hemo_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -1,0 +1,73 @@
+"""Host-side, one-time tables the CUDA library needs: node graph, exterior-facet
+sets grouped by cell, Dirichlet flags.
+
+3P behaviour restated: `create_matrix_block` builds the
+full FE sparsity pattern (trigger: reference src/solvers/stabilized_schur.py:191);
+for P1–P1 that pattern is the node adjacency graph expanded to the
+[u interleaved | p] layout, which the library does on the device
+(`hemo_get_pattern`).  Here we only build the scalar node graph.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+from .mesh import Mesh, exterior_facet_indices
+
+
+def node_graph(cells: np.ndarray, n_nodes: int):
+    """Sorted CSR adjacency (diagonal included) of the P1 dof graph."""
+    c = cells.astype(np.int64)
+    nv = c.shape[1]
+    rows = np.repeat(c, nv, axis=1).reshape(-1)
+    cols = np.tile(c, (1, nv)).reshape(-1)
+    key = np.unique(rows * np.int64(n_nodes) + cols)
+    r = (key // n_nodes).astype(np.int64)
+    ncol = (key % n_nodes).astype(np.int32)
+    nrowptr = np.zeros(n_nodes + 1, dtype=np.int64)
+    nrowptr[1:] = np.bincount(r, minlength=n_nodes)
+    nrowptr = np.cumsum(nrowptr).astype(np.int32)
+    return nrowptr, ncol
+
+
+def facet_set_by_cell(mesh: Mesh, facets: np.ndarray):
+    """Group exterior facets by their cell: (cells (m,), mask (m,)) with bit
+    `lf` of mask set when local facet lf of the cell is in the set."""
+    pairs = mesh.topology.facet_cell_pairs(np.asarray(facets))
+    if pairs.shape[0] == 0:
+        return np.zeros(0, np.int32), np.zeros(0, np.int32)
+    order = np.argsort(pairs[:, 0], kind="stable")
+    pc = pairs[order, 0]
+    bits = (1 << pairs[order, 1]).astype(np.int32)
+    cells, start = np.unique(pc, return_index=True)
+    mask = np.add.reduceat(bits, start).astype(np.int32)
+    return cells.astype(np.int32), mask
+
+
+def all_exterior_facets(mesh: Mesh) -> np.ndarray:
+    return exterior_facet_indices(mesh.topology)
+
+
+def dirichlet_arrays(n_nodes: int, cells: np.ndarray, bcs):
+    """bcs: list of (block 'u'|'p', block dof indices, value array (block-sized)).
+    Returns dofflag (3n uint8), dofmult (3n f64), cellflag (E uint8), g (3n f64).
+    Semantics (3P): diagonal += 1 per DirichletBC containing the
+    dof; on shared dofs the last BC in the list provides the value."""
+    N = 3 * n_nodes
+    flag = np.zeros(N, dtype=np.uint8)
+    mult = np.zeros(N, dtype=np.float64)
+    g = np.zeros(N, dtype=np.float64)
+    for block, nodes, values in bcs:
+        nodes = np.asarray(nodes, dtype=np.int64)
+        if block == "u":
+            d = (2 * nodes[:, None] + np.arange(2)[None, :]).reshape(-1)
+            vals = np.asarray(values, dtype=np.float64)[d]
+        else:
+            d = 2 * n_nodes + nodes
+            vals = np.asarray(values, dtype=np.float64)[nodes]
+        flag[d] = 1
+        mult[d] += 1.0
+        g[d] = vals
+    nodeflag = (flag[0:2 * n_nodes:2] | flag[1:2 * n_nodes:2] | flag[2 * n_nodes:]).astype(bool)
+    cellflag = nodeflag[cells].any(axis=1).astype(np.uint8)
+    return flag, mult, cellflag, g

@@ -1,0 +1,72 @@
+"""Host driver for the linear solve of one Newton iteration.
+
+Mirrors the PETSc objects the reference configures in `Solver.setup`
+(reference src/solvers/stabilized_schur.py:226-275): an outer FGMRES and a
+Schur-complement block preconditioner, rebuilt for every new Jacobian.
+All numerics run in libhemo_sm100.so; this file only sequences calls.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+from .fem import amg_setup
+
+
+class BlockSchurSolver:
+    """KSP(fgmres) + PC(block Schur, AMG) for the monolithic Jacobian."""
+
+    def __init__(self, hemo, nrowptr: np.ndarray, ncol: np.ndarray, u_dirichlet_nodes: np.ndarray,
+                 p_dirichlet_nodes: np.ndarray, *, dt: float, rho: float, mu: float,
+                 restart: int = 60, max_it: int = 1000, rtol: float = 1e-5, atol: float = 1e-50,
+                 amg_cycles_u: int = 1, amg_cycles_p: int = 2, cheb_degree: int = 2, cheb_ratio: float = 4.0,
+                 project_pressure: bool = False, smooth_prolongator: bool = True, strength_theta: float = 0.08,
+                 schur_mass_coef: float | None = None, schur_lap_coef: float | None = None):
+        self.hemo = hemo
+        n = nrowptr.shape[0] - 1
+        self.n = n
+        # Schur complement of the mid-point scheme:
+        #   S ~ 1/2 B (rho/dt M + mu/2 K)^-1 B^T  =>  S^-1 ~ mu Mp^-1 + (2 rho/dt) Lp^-1
+        self.opts = dict(restart=restart, max_it=max_it, rtol=rtol, atol=atol, amg_cycles_u=amg_cycles_u,
+                         amg_cycles_p=amg_cycles_p, cheb_degree=cheb_degree,
+                         project_pressure=int(bool(project_pressure)), pc_mode=0,
+                         schur_mass_coef=mu if schur_mass_coef is None else schur_mass_coef,
+                         schur_lap_coef=2.0 * rho / dt if schur_lap_coef is None else schur_lap_coef,
+                         cheb_ratio=cheb_ratio)
+        hemo.set_solver_opts(**self.opts)
+        # constant operators of the Schur approximation, assembled on the device
+        self.lap, self.mass = hemo.assemble_laplace_mass()
+        lap_host = self.lap.cpu().numpy()
+        L = sp.csr_matrix((lap_host, ncol, nrowptr), shape=(n, n))
+        umask = np.zeros(n, dtype=bool)
+        umask[np.asarray(u_dirichlet_nodes, dtype=np.int64)] = True
+        pmask = np.zeros(n, dtype=bool)
+        pmask[np.asarray(p_dirichlet_nodes, dtype=np.int64)] = True
+        self.levels = []
+        for which, mask, max_coarse in ((0, umask, 400), (1, pmask, 800)):
+            lv = amg_setup.build_hierarchy(L, mask, max_coarse=max_coarse, theta=strength_theta,
+                                           smooth=smooth_prolongator)
+            for l, d in enumerate(lv):
+                hemo.amg_set_level(which, l, d["P"], d["R"], d["AP"], d["C"])
+            hemo.amg_finalize(which, len(lv) + 1)
+            self.levels.append(lv)
+        self._first = True
+
+    def set_tolerances(self, rtol=None, max_it=None):
+        if rtol is not None:
+            self.opts["rtol"] = rtol
+        if max_it is not None:
+            self.opts["max_it"] = max_it
+        self.hemo.set_solver_opts(**self.opts)
+
+    def setup(self, vals):
+        """pc.setUp() for a new Jacobian."""
+        if self._first:
+            self.hemo.pc_setup(vals, self.lap, self.mass)
+            self._first = False
+        else:
+            self.hemo.pc_setup(vals)
+
+    def solve(self, vals, b, y):
+        """KSPSolve with zero initial guess; returns (iterations, relative residual)."""
+        return self.hemo.fgmres(vals, b, y)

@@ -1,0 +1,195 @@
+/*
+ * hemo.h — C-ABI of libhemo_sm100.so: the B200-native replacement for the
+ * DOLFINx/PETSc calls made by the reference's `stabilized_schur` solvers.
+ *
+ * Every entry point names the reference interface it replaces (file:line
+ * relative to the reference repository root).  Conventions:
+ *   - plain pointers and sizes only; "dev" pointers are CUDA device addresses
+ *     owned by the caller (torch tensors: tensor.data_ptr()); "host" pointers
+ *     are ordinary host memory.  The library keeps the pointer, not a copy,
+ *     for arrays documented as "borrowed".
+ *   - every function returns 0 on success, <0 for an invalid argument or
+ *     call order, >0 for a CUDA error (the cudaError_t), HEMO_DIVERGED for a
+ *     linear solve that hit max iterations; hemo_last_error() gives the text.
+ *   - work is enqueued on the stream given to hemo_set_stream (default 0);
+ *     functions that return scalars to the host synchronise that stream.
+ *   - one context per GPU per host thread; a context is not re-entrant.
+ *
+ * Global dof layout (3P `create_vector_block`, trigger
+ * src/solvers/stabilized_schur.py:191-193): x = [u interleaved (2*n) | p (n)].
+ * Matrix: one CSR, rows in that order, columns ascending, full FE pattern
+ * (explicit zeros kept), int32 indices (nnz = 9 * nnz_node).
+ */
+#ifndef HEMO_H
+#define HEMO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hemo_ctx hemo_ctx;
+
+#define HEMO_OK 0
+#define HEMO_EINVAL (-1)
+#define HEMO_ESTATE (-2)
+#define HEMO_DIVERGED (-100)
+
+/* Constants of the weak form: SolverBase.__init__ (src/solverBase.py:36-40)
+ * and eps (src/solvers/stabilized_schur.py:100). */
+typedef struct hemo_params {
+    double dt, rho, mu;
+    double f[2];
+    double eps0;
+} hemo_params;
+
+/* Coefficients of one tagged exterior-facet integral; see FacetSet in
+ * oracle/ns_oracle.py for the term each one multiplies
+ * (src/solvers/stabilized_schur.py:79;
+ *  src/solvers/stabilized_schur_pressure_backflow.py:192-217). */
+typedef struct hemo_facet_coef {
+    double a_p, pconst, a_g, a_s, a_n, beta_n, a_b, beta_b;
+} hemo_facet_coef;
+
+/* Block-form ids for hemo_set_quadrature: each block of
+ * form(extract_blocks(F)) / form(extract_blocks(J)) is its own UFL form with
+ * its own estimated degree (src/solvers/stabilized_schur.py:188-189). */
+enum { HEMO_Q_FU = 0, HEMO_Q_FP = 1, HEMO_Q_UU = 2, HEMO_Q_UP = 3, HEMO_Q_PU = 4, HEMO_Q_PP = 5 };
+
+/* Krylov / preconditioner options (mirrors the PETSc options set at
+ * src/solvers/stabilized_schur.py:226-275). */
+typedef struct hemo_solver_opts {
+    int restart;          /* ksp_gmres_restart (reference: 200) */
+    int max_it;           /* ksp_max_it (reference: 1000) */
+    double rtol;          /* ksp_rtol (PETSc default 1e-5) */
+    double atol;          /* ksp_atol (1e-50) */
+    int amg_cycles_u;     /* V-cycles per A00^{-1} application */
+    int amg_cycles_p;     /* V-cycles per Lp^{-1} application */
+    int cheb_degree;      /* Chebyshev smoother degree per pre/post smoothing */
+    int project_pressure; /* 1: remove the constant-pressure mode (nullsp attached,
+                             src/solvers/stabilized_schur.py:314-317) */
+    int pc_mode;          /* 0: upper block-triangular Schur (only mode implemented) */
+    /* Schur-complement approximation S^-1 ~ schur_mass_coef * diag(Mp)^-1
+     *                                       + schur_lap_coef * Lp^-1
+     * (replaces SELFP, src/solvers/stabilized_schur.py:235) */
+    double schur_mass_coef;
+    double schur_lap_coef;
+    double cheb_ratio;    /* Chebyshev smoothing interval [lmax/ratio, lmax] (default 4) */
+} hemo_solver_opts;
+
+/* ---- context ----------------------------------------------------------- */
+int hemo_ctx_create(int device, hemo_ctx** out);
+int hemo_ctx_destroy(hemo_ctx* ctx);
+const char* hemo_last_error(hemo_ctx* ctx);
+int hemo_set_stream(hemo_ctx* ctx, void* cuda_stream);
+/* number of kernels this context has launched so far (bench.py gpu_launches) */
+int64_t hemo_launch_count(hemo_ctx* ctx);
+
+/* ---- mesh, spaces, pattern ---------------------------------------------- */
+/* mesh.geometry.x / .dofmap / mesh.h (src/solvers/stabilized_schur.py:55-58,83-88).
+ * x: n_nodes*2 doubles, cells: n_cells*3 int32, h: n_cells doubles; borrowed. */
+int hemo_set_mesh(hemo_ctx* ctx, const double* x_dev, int n_nodes,
+                  const int32_t* cells_dev, int n_cells, const double* h_dev);
+/* Node adjacency (CSR, sorted, diagonal included) = scalar P1 sparsity graph;
+ * borrowed.  From it the library derives the block CSR pattern that
+ * create_matrix_block builds (src/solvers/stabilized_schur.py:191), the
+ * cell->nnz map and the atomic-free gather segments. */
+int hemo_set_node_graph(hemo_ctx* ctx, const int32_t* nrowptr_dev, const int32_t* ncol_dev,
+                        int64_t nnz_node);
+int hemo_matrix_nnz(hemo_ctx* ctx, int64_t* nnz);
+/* A.getValuesCSR() pattern part: rowptr (3n+1 int64) and colind (nnz int32), device. */
+int hemo_get_pattern(hemo_ctx* ctx, int64_t* rowptr_dev, int32_t* colind_dev);
+
+/* ---- forms ---------------------------------------------------------------- */
+/* Quadrature rule of one block form (host arrays; pts = nq*2 reference coords,
+ * wts sum to 1/2).  Basix rule selected by FFCx at form() (:188-189). */
+int hemo_set_quadrature(hemo_ctx* ctx, int block, const double* pts_host,
+                        const double* wts_host, int nq);
+/* Facet rule on [0,1] shared by all exterior-facet integrals. */
+int hemo_set_facet_quadrature(hemo_ctx* ctx, const double* pts_host, const double* wts_host, int nq);
+int hemo_set_params(hemo_ctx* ctx, const hemo_params* p);
+/* One tagged ds integral: unique boundary cells with a 3-bit mask of the
+ * local facets that carry the tag (Measure("ds", subdomain_id=...),
+ * src/solvers/stabilized_schur_pressure_backflow.py:170-181).  m = 0 removes
+ * the set.  Arrays are copied. */
+int hemo_set_facet_set(hemo_ctx* ctx, int set_id, const int32_t* cells_dev,
+                       const int32_t* facet_mask_dev, int m, const hemo_facet_coef* coef);
+int hemo_set_facet_coef(hemo_ctx* ctx, int set_id, const hemo_facet_coef* coef);
+/* Dirichlet data (src/solvers/stabilized_schur.py:198-199): per global dof a
+ * flag (1 = constrained) and the diagonal multiplicity (number of DirichletBC
+ * objects containing the dof); per cell a flag (1 = touches a constrained dof).
+ * Copied. */
+int hemo_set_bc(hemo_ctx* ctx, const uint8_t* dofflag_dev, const double* dofmult_dev,
+                const uint8_t* cellflag_dev);
+
+/* ---- assembly --------------------------------------------------------------- */
+/* assembleJacobian → assemble_matrix_block (src/solvers/stabilized_schur.py:144-155):
+ * vals (nnz doubles, device) receives J(x) with Dirichlet rows/cols zeroed and
+ * the diagonal multiplicity set.  x = [u|p] (3n), un = u_prev (2n). */
+int hemo_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const double* un_dev,
+                           double* vals_dev);
+/* assembleResidual → assemble_vector_block(..., x0=x, alpha=-1) (:157-175):
+ * b = F(x) + lifting; b[bc] = x[bc] - g[bc].  g: 3n Dirichlet values. */
+int hemo_assemble_residual(hemo_ctx* ctx, const double* x_dev, const double* un_dev,
+                           const double* g_dev, double* b_dev);
+/* assemble_scalar(dot(u_prev, n) * ds_out)
+ * (src/solvers/stabilized_schur_pressure_backflow.py:383-385). */
+int hemo_outlet_flux(hemo_ctx* ctx, int set_id, const double* un_dev, double* q_host);
+/* Pressure Laplacian (node-graph CSR values, nnz_node doubles) and lumped
+ * pressure mass (n doubles) for the Schur-complement approximation. */
+int hemo_assemble_laplace_mass(hemo_ctx* ctx, double* lap_vals_dev, double* mass_dev);
+
+/* ---- linear algebra ----------------------------------------------------------- */
+/* MatMult on the monolithic Jacobian (PETSc KSP inner loop, :226-229). */
+int hemo_spmv(hemo_ctx* ctx, const double* vals_dev, const double* x_dev, double* y_dev);
+/* y = a*x + y ; dot ; 2-norm on n-vectors (VecAXPY / VecDot / VecNorm). */
+int hemo_axpy(hemo_ctx* ctx, int64_t n, double a, const double* x_dev, double* y_dev);
+int hemo_dot(hemo_ctx* ctx, int64_t n, const double* x_dev, const double* y_dev, double* out_host);
+int hemo_norm2(hemo_ctx* ctx, int64_t n, const double* x_dev, double* out_host);
+
+/* ---- algebraic multigrid hierarchy -------------------------------------------- */
+/* One level of a prolongator chain built by the host from the node graph
+ * (aggregation + optional smoothing); all arrays here are HOST pointers.  which: 0 = velocity block A00 (2 dofs
+ * per node, P (x) I2), 1 = pressure Laplacian.  Level l maps n_l → n_{l+1}
+ * nodes.  All CSR arrays are copied.  The coarse node graph (pattern of
+ * R*A*P) and the pattern of A*P are given so the numeric Galerkin product
+ * runs with fixed structure each Newton iteration. */
+int hemo_amg_set_level(hemo_ctx* ctx, int which, int level, int n_fine, int n_coarse,
+                       const int32_t* p_rowptr, const int32_t* p_col, const double* p_val,
+                       const int32_t* r_rowptr, const int32_t* r_col, const double* r_val,
+                       const int32_t* ap_rowptr, const int32_t* ap_col,
+                       const int32_t* c_rowptr, const int32_t* c_col);
+int hemo_amg_finalize(hemo_ctx* ctx, int which, int n_levels);
+
+/* Host (CPU) helper, one-time setup: greedy aggregation on a strength graph
+ * (CSR without diagonal, host arrays).  exclude[i] != 0 leaves node i out
+ * (agg[i] = -1).  No reference equivalent (PETSc builds ILU factors instead). */
+int hemo_host_aggregate(int n, const int32_t* rowptr, const int32_t* col, const uint8_t* exclude,
+                        int32_t* agg, int32_t* n_agg_out);
+
+/* ---- solve ------------------------------------------------------------------------ */
+int hemo_set_solver_opts(hemo_ctx* ctx, const hemo_solver_opts* o);
+/* PCSetUp (pc.setUp(), src/solvers/stabilized_schur.py:253 and every Newton
+ * iteration): numeric Galerkin products of the A00 hierarchy from the current
+ * Jacobian values, smoother bounds, pressure hierarchy from lap_vals (first
+ * call or when lap_vals changes). */
+int hemo_pc_setup(hemo_ctx* ctx, const double* vals_dev, const double* lap_vals_dev,
+                  const double* mass_dev);
+/* One V-cycle solve with hierarchy `which` (0: A00, 2n values; 1: Lp, n values):
+ * x = V^ncycles(b) from a zero initial guess.  Exposed for the parity tests. */
+int hemo_amg_apply(hemo_ctx* ctx, int which, const double* b_dev, double* x_dev, int ncycles);
+/* Level operator of hierarchy `which` after hemo_pc_setup (device copy out;
+ * nnzb*bs*bs doubles).  Exposed for the Galerkin-product parity test. */
+int hemo_amg_get_level_values(hemo_ctx* ctx, int which, int level, double* vals_dev, int64_t capacity);
+/* z = M^{-1} r (one application of the block preconditioner). */
+int hemo_pc_apply(hemo_ctx* ctx, const double* vals_dev, const double* r_dev, double* z_dev);
+/* KSPSolve: right-preconditioned FGMRES(restart) on J y = b with zero initial
+ * guess (:226-229,272-273).  its_out/resid_out on host. */
+int hemo_fgmres(hemo_ctx* ctx, const double* vals_dev, const double* b_dev, double* y_dev,
+                int* its_out, double* rel_resid_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEMO_H */

@@ -1,0 +1,141 @@
+"""GPU parity: CUDA assembly through the C-ABI vs the numpy oracle on the same
+seeded inputs.  Tolerance: 1e-12 relative Frobenius (north_star), written below."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from tests import common as T
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def hemo():
+    from cfd_hemodynamic_b200._lib import Hemo
+    h = Hemo(0)
+    yield h
+    h.close()
+
+
+def _case(hemo, nx, ny, facet_mode, with_bc, seed=0, **pk):
+    from cfd_hemodynamic_b200.fem import mesh as M
+    from oracle import ns_oracle as O
+    mesh = T.perturbed_square(nx, ny, seed=seed)
+    prob = T.make_problem(mesh, **pk)
+    ext = M.exterior_facet_indices(mesh.topology)
+    x = prob.x
+    fsets = []
+    if facet_mode == "all":
+        fsets = [(ext, dict(a_p=1.0, a_g=1.0))]
+    elif facet_mode == "hemo":
+        inlet = M.locate_entities_boundary(mesh, 1, lambda X: np.isclose(X[0], 0.0))
+        outlet = M.locate_entities_boundary(mesh, 1, lambda X: np.isclose(X[0], 1.0))
+        fsets = [(inlet, dict(pconst=2 * 3.7, a_n=2.0, beta_n=100.0)),
+                 (outlet, dict(pconst=0.5 * 1.1 + 0.5 * 0.4, a_s=2.0, a_b=2.0, beta_b=0.2))]
+    bcs = []
+    if with_bc:
+        n = prob.n
+        walls = np.nonzero(np.isclose(x[:, 1], 0.0) | np.isclose(x[:, 1], 1.0))[0]
+        left = np.nonzero(np.isclose(x[:, 0], 0.0))[0]
+        rng = np.random.default_rng(5)
+        g0 = rng.standard_normal(2 * n)
+        g1 = rng.standard_normal(2 * n)
+        gp = rng.standard_normal(n)
+        bcs = [("u", walls, g0), ("u", left, g1)]      # corner nodes are in both → diagonal 2
+        if facet_mode != "hemo":
+            right = np.nonzero(np.isclose(x[:, 0], 1.0))[0]
+            bcs.append(("p", right, gp))
+    prob.facet_sets = [O.FacetSet(pairs=mesh.topology.facet_cell_pairs(f), **c) for f, c in fsets]
+    prob.bcs = T.oracle_bcs(prob, bcs)
+    g, graph = T.setup_gpu(hemo, mesh, prob, fsets, bcs)
+    for sid in range(len(fsets), 8):
+        hemo.set_facet_set(sid, None, None)
+    if not bcs:
+        hemo.set_bc(None, None, None)
+    return mesh, prob, g
+
+
+@pytest.mark.parametrize("facet_mode,with_bc", [("none", False), ("all", False), ("all", True), ("hemo", True)])
+def test_jacobian_parity(hemo, facet_mode, with_bc):
+    from oracle import ns_oracle as O
+    mesh, prob, g = _case(hemo, 9, 7, facet_mode, with_bc)
+    u, p, un = T.smooth_fields(prob.x)
+    dev = hemo.device
+    xd = torch.tensor(np.concatenate([u, p]), device=dev)
+    und = torch.tensor(un, device=dev)
+    vals = torch.zeros(hemo.nnz, dtype=torch.float64, device=dev)
+    hemo.assemble_jacobian(xd, und, vals)
+    rowptr, col = hemo.get_pattern()
+    torch.cuda.synchronize()
+    A_ref = O.assemble_J(prob, u, p, un) if with_bc else O.assemble_J_raw(prob, u, p, un)
+    ip, idx = O.sparsity_pattern(prob)
+    # sparsity pattern bit-exact
+    assert np.array_equal(rowptr.cpu().numpy(), ip)
+    assert np.array_equal(col.cpu().numpy(), idx)
+    A_gpu = sp.csr_matrix((vals.cpu().numpy(), idx, ip), shape=A_ref.shape)
+    diff = (A_gpu - A_ref)
+    rel = np.sqrt(diff.multiply(diff).sum()) / np.sqrt(A_ref.multiply(A_ref).sum())
+    assert rel < REL_TOL, rel
+    if with_bc:
+        marker, _, mult = O.bc_arrays(prob)
+        d = A_gpu.diagonal()
+        assert np.array_equal(d[marker], mult[marker])
+        assert mult.max() == 2.0
+
+
+@pytest.mark.parametrize("facet_mode,with_bc", [("none", False), ("all", True), ("hemo", True)])
+def test_residual_parity(hemo, facet_mode, with_bc):
+    from oracle import ns_oracle as O
+    mesh, prob, g = _case(hemo, 8, 11, facet_mode, with_bc, seed=3)
+    u, p, un = T.smooth_fields(prob.x, seed=4)
+    dev = hemo.device
+    x = np.concatenate([u, p])
+    xd = torch.tensor(x, device=dev)
+    und = torch.tensor(un, device=dev)
+    b = torch.zeros(3 * prob.n, dtype=torch.float64, device=dev)
+    hemo.assemble_residual(xd, und, g, b)
+    torch.cuda.synchronize()
+    b_ref = O.assemble_F(prob, x, un) if with_bc else O.assemble_F_raw(prob, u, p, un)
+    rel = np.linalg.norm(b.cpu().numpy() - b_ref) / np.linalg.norm(b_ref)
+    assert rel < REL_TOL, rel
+
+
+def test_zero_previous_velocity_branch(hemo):
+    """u_n == 0 exercises the eps0 branch of tau_supg1 (stabilized_schur.py:100-103)."""
+    from oracle import ns_oracle as O
+    mesh, prob, g = _case(hemo, 6, 6, "all", False, mu=1e-3, dt=0.05)
+    u, p, _ = T.smooth_fields(prob.x)
+    un = np.zeros_like(u)
+    dev = hemo.device
+    vals = torch.zeros(hemo.nnz, dtype=torch.float64, device=dev)
+    hemo.assemble_jacobian(torch.tensor(np.concatenate([u, p]), device=dev), torch.tensor(un, device=dev), vals)
+    A_ref = O.assemble_J_raw(prob, u, p, un)
+    rel = np.linalg.norm(vals.cpu().numpy() - A_ref.data) / np.linalg.norm(A_ref.data)
+    assert rel < REL_TOL, rel
+
+
+def test_deterministic(hemo):
+    mesh, prob, g = _case(hemo, 12, 12, "all", True)
+    u, p, un = T.smooth_fields(prob.x)
+    dev = hemo.device
+    xd = torch.tensor(np.concatenate([u, p]), device=dev)
+    und = torch.tensor(un, device=dev)
+    v1 = torch.zeros(hemo.nnz, dtype=torch.float64, device=dev)
+    v2 = torch.zeros_like(v1)
+    hemo.assemble_jacobian(xd, und, v1)
+    hemo.assemble_jacobian(xd, und, v2)
+    assert torch.equal(v1, v2)
+
+
+def test_outlet_flux(hemo):
+    from cfd_hemodynamic_b200.fem import mesh as M
+    from oracle import ns_oracle as O
+    mesh, prob, g = _case(hemo, 7, 9, "hemo", True)
+    _, _, un = T.smooth_fields(prob.x)
+    outlet = M.locate_entities_boundary(mesh, 1, lambda X: np.isclose(X[0], 1.0))
+    q_ref = O.outlet_flux(prob, mesh.topology.facet_cell_pairs(outlet), un)
+    q = hemo.outlet_flux(1, torch.tensor(un, device=hemo.device))
+    assert abs(q - q_ref) <= 1e-13 * max(1.0, abs(q_ref))
