@@ -71,6 +71,7 @@ SYMBOLS = {
     "hemo_axpy": (_I, [_VP, _L, _D, _VP, _VP]),
     "hemo_dot": (_I, [_VP, _L, _VP, _VP, C.POINTER(_D)]),
     "hemo_norm2": (_I, [_VP, _L, _VP, C.POINTER(_D)]),
+    "hemo_remove_mean_vec": (_I, [_VP, _L, _VP]),
     "hemo_amg_set_level": (_I, [_VP, _I, _I, _I, _I] + [_VP] * 10),
     "hemo_amg_finalize": (_I, [_VP, _I, _I]),
     "hemo_host_aggregate": (_I, [_I, _VP, _VP, _VP, _VP, C.POINTER(_I)]),
@@ -247,6 +248,9 @@ class Hemo:
         out = C.c_double()
         self._check(self.lib.hemo_norm2(self._ctx, x.numel(), _ptr(x), C.byref(out)), "hemo_norm2")
         return out.value
+
+    def remove_mean(self, x):
+        self._check(self.lib.hemo_remove_mean_vec(self._ctx, x.numel(), _ptr(x)), "hemo_remove_mean_vec")
 
     # ---- AMG / solve -------------------------------------------------------
     def amg_set_level(self, which, level, P, R, AP_pattern, C_pattern):

@@ -66,6 +66,11 @@ __global__ void k_schur_combine(int n, double cm, double cl, const double* __res
     zp[i] = v;
 }
 
+extern "C" int hemo_remove_mean_vec(hemo_ctx* ctx, int64_t n, double* x_dev) {
+    if (!ctx || !x_dev || n <= 0) return HEMO_EINVAL;
+    return hemo_remove_mean(ctx, n, x_dev);
+}
+
 extern "C" int hemo_set_solver_opts(hemo_ctx* ctx, const hemo_solver_opts* o) {
     if (!ctx || !o) return HEMO_EINVAL;
     if (o->restart < 1 || o->restart > 400 || o->max_it < 1) return HEMO_EINVAL;

@@ -17,7 +17,7 @@ class BlockSchurSolver:
     """KSP(fgmres) + PC(block Schur, AMG) for the monolithic Jacobian."""
 
     def __init__(self, hemo, nrowptr: np.ndarray, ncol: np.ndarray, u_dirichlet_nodes: np.ndarray,
-                 p_dirichlet_nodes: np.ndarray, *, dt: float, rho: float, mu: float,
+                 p_dirichlet_nodes: np.ndarray, *, p_open_nodes: np.ndarray | None = None, dt: float, rho: float, mu: float,
                  restart: int = 60, max_it: int = 1000, rtol: float = 1e-5, atol: float = 1e-50,
                  amg_cycles_u: int = 1, amg_cycles_p: int = 2, cheb_degree: int = 2, cheb_ratio: float = 4.0,
                  project_pressure: bool = False, smooth_prolongator: bool = True, strength_theta: float = 0.08,
@@ -42,6 +42,17 @@ class BlockSchurSolver:
         umask[np.asarray(u_dirichlet_nodes, dtype=np.int64)] = True
         pmask = np.zeros(n, dtype=bool)
         pmask[np.asarray(p_dirichlet_nodes, dtype=np.int64)] = True
+        if p_open_nodes is not None and len(p_open_nodes):
+            # open (traction) boundary: Dirichlet condition for the Schur-complement Laplacian
+            # (identity rows/cols), applied once on the host and uploaded
+            omask = np.zeros(n, dtype=bool)
+            omask[np.asarray(p_open_nodes, dtype=np.int64)] = True
+            rows = np.repeat(np.arange(n), np.diff(nrowptr))
+            hit = omask[rows] | omask[ncol]
+            lap_host = np.where(hit, (rows == ncol).astype(np.float64), lap_host)
+            self.lap = hemo.torch.from_numpy(np.ascontiguousarray(lap_host)).to(hemo.device)
+            L = sp.csr_matrix((lap_host, ncol, nrowptr), shape=(n, n))
+            pmask |= omask
         self.levels = []
         for which, mask, max_coarse in ((0, umask, 400), (1, pmask, 800)):
             lv = amg_setup.build_hierarchy(L, mask, max_coarse=max_coarse, theta=strength_theta,

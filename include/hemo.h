@@ -148,6 +148,10 @@ int hemo_axpy(hemo_ctx* ctx, int64_t n, double a, const double* x_dev, double* y
 int hemo_dot(hemo_ctx* ctx, int64_t n, const double* x_dev, const double* y_dev, double* out_host);
 int hemo_norm2(hemo_ctx* ctx, int64_t n, const double* x_dev, double* out_host);
 
+/* MatNullSpaceRemove for the constant vector on an n-vector: x -= mean(x)
+ * (nullsp.remove(x_n), src/solvers/stabilized_schur.py:319). */
+int hemo_remove_mean_vec(hemo_ctx* ctx, int64_t n, double* x_dev);
+
 /* ---- algebraic multigrid hierarchy -------------------------------------------- */
 /* One level of a prolongator chain built by the host from the node graph
  * (aggregation + optional smoothing); all arrays here are HOST pointers.  which: 0 = velocity block A00 (2 dofs

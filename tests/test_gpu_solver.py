@@ -1,0 +1,79 @@
+"""End-to-end parity through the reference-facing plugin API: the B200
+`stabilized_schur` solver vs the oracle's Newton + sparse-LU on the same mesh
+and inputs.  Tolerance 1e-8 relative L2 after N steps (north_star), both sides
+converged tightly; pressure compared modulo the mean over dofs."""
+import numpy as np
+import pytest
+
+from tests import common as T
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TIGHT = dict(snes_rtol=1e-12, snes_stol=0.0, ksp_rtol=1e-11, ksp_restart=100)
+
+
+def _oracle_lid(nx, mu, dt, steps, rules):
+    from cfd_hemodynamic_b200.fem import mesh as M
+    from oracle import ns_oracle as O
+    mesh = M.create_unit_square(None, nx, nx)
+    prob = T.make_problem(mesh, dt=dt, rho=1.0, mu=mu, f=(0.0, 0.0), rules=rules)
+    x = prob.x
+    n = prob.n
+    ext = M.exterior_facet_indices(mesh.topology)
+    prob.facet_sets = [O.FacetSet(pairs=mesh.topology.facet_cell_pairs(ext), a_p=1.0, a_g=1.0)]
+    walls = np.nonzero(np.isclose(x[:, 0], 0) | np.isclose(x[:, 0], 1) | np.isclose(x[:, 1], 0))[0]
+    lidf = M.locate_entities_boundary(mesh, 1, lambda X: np.isclose(X[1], 1.0) & (X[0] > 1e-10) & (X[0] < 1 - 1e-10))
+    lid = np.unique(mesh.topology.facet_vertices[lidf])
+    g1 = np.zeros(2 * n); g1[0::2] = 1.0
+    prob.bcs = T.oracle_bcs(prob, [("u", walls, np.zeros(2 * n)), ("u", lid, g1)])
+    xk = np.zeros(3 * n)
+    un = np.zeros(2 * n)
+    for _ in range(steps):
+        xk = O.remove_nullspace(prob, xk)
+        xk, its, reason = O.newton_solve(prob, xk, un, rtol=1e-12, stol=0.0)
+        assert reason > 0
+        un = xk[:2 * n].copy()
+    return xk, n
+
+
+def test_lid_cavity_matches_oracle():
+    from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation
+    nx, mu, dt, steps = 16, 0.01, 0.01, 3
+    sc = LidDriven2DSimulation("stabilized_schur", dt, steps * dt, rho=1, mu=mu, nx=nx, **TIGHT)
+    s = sc.solver
+    assert s._nullspace                      # all-Dirichlet velocity: constant pressure mode detected
+    for _ in range(steps):
+        s.solveStep()
+        s.u_prev.x.array[:] = s.u_sol.x.array[:]
+        s.p_prev.x.array[:] = s.p_sol.x.array[:]
+    xk, n = _oracle_lid(nx, mu, dt, steps, T.default_rules())
+    u_ref, p_ref = xk[:2 * n], xk[2 * n:]
+    u = s.u_sol.x.array
+    p = s.p_sol.x.array
+    eu = np.linalg.norm(u - u_ref) / np.linalg.norm(u_ref)
+    ep = np.linalg.norm((p - p.mean()) - (p_ref - p_ref.mean())) / np.linalg.norm(p_ref - p_ref.mean())
+    assert eu < 1e-8, eu
+    assert ep < 1e-8, ep
+    # lid BC satisfied exactly, corner (wall ∩ lid-closure) dofs follow the last BC in the list
+    assert abs(u).max() <= 1.0 + 1e-12
+
+
+def test_scenario_time_loop(tmp_path):
+    """Scenario.solve drives solveStep, shifts u_prev on the host and writes norms.txt."""
+    from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation
+    sc = LidDriven2DSimulation("stabilized_schur", 0.01, 0.05, rho=1, mu=0.01, nx=12)
+    sc.setup()                               # second setup(), like Simulation.run (simulation.py:269)
+    sc.write_output = False
+    out = sc.solve(str(tmp_path / "run"))
+    assert sc.steps_done == 5
+    txt = open(f"{out}/norms.txt").read()
+    assert "L2 norm of velocity" in txt
+    assert np.isfinite(sc.solver.u_sol.x.array).all()
+
+
+def test_divergence_raises():
+    from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation
+    sc = LidDriven2DSimulation("stabilized_schur", 0.01, 0.01, rho=1, mu=0.01, nx=8, ksp_max_it=1, ksp_rtol=1e-14)
+    with pytest.raises(RuntimeError, match="Did not converge"):
+        sc.solver.solveStep()
