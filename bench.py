@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the stabilized_schur per-timestep hot path (BASELINE.json metric:
+DOF-timesteps/s; assembly cells/s and nnz/s are reported beside it).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port
+                                                           # (DOLFINx/PETSc cannot be installed)
+
+A "step" is one time step (`Solver.solveStep`) of the workload: Newton with
+Jacobian + residual assemblies and a preconditioned FGMRES solve per
+iteration.  `value` is measured with everything resident in HBM
+(`Solver.step_device`), `e2e` through the reference-facing plugin API with host
+buffers (`Solver.solveStep` + the host-side u_prev <- u_sol shift the
+reference's time loop performs, src/scenario.py:306-307).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: lid_driven2D on a refined structured mesh (~1M cells)
+    "lid_driven2D_nx707": dict(scenario="lid_driven2D", nx=707, mu=0.01, rho=1.0, dt=0.01),
+    "lid_driven2D_nx1414": dict(scenario="lid_driven2D", nx=1414, mu=0.01, rho=1.0, dt=0.01),
+    "lid_driven2D_nx2828": dict(scenario="lid_driven2D", nx=2828, mu=0.01, rho=1.0, dt=0.01),
+    "lid_driven2D_nx64": dict(scenario="lid_driven2D", nx=64, mu=0.01, rho=1.0, dt=0.01),
+}
+CPU_SAMPLE_NX = 64   # bounded CPU sample of the same workload (same physics, coarser mesh)
+
+PROF_CLASSES = {0: "spmv_node(J)", 1: "cell_jacobian", 2: "gather_matrix", 3: "cell_residual",
+                4: "cheb_step<2>(A00,l0)", 5: "cheb_step<1>(Lp,l0)", 6: "mdot", 7: "maxpy_norm",
+                8: "numeric_rap<2>(l0)"}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scenario(w, **solver_kw):
+    from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation
+    assert w["scenario"] == "lid_driven2D"
+    return LidDriven2DSimulation("stabilized_schur", w["dt"], 1.0, rho=w["rho"], mu=w["mu"], nx=w["nx"], **solver_kw)
+
+
+def oracle_steps(w, nx, steps):
+    """The CPU port (oracle/ns_oracle.py): same scenario, Newton + sparse LU, `steps`
+    time steps at mesh size nx.  Returns (ndof, seconds)."""
+    from cfd_hemodynamic_b200.fem import mesh as M
+    from oracle import ns_oracle as O
+    from tests import common as T
+    mesh = M.create_unit_square(None, nx, nx)
+    prob = T.make_problem(mesh, dt=w["dt"], rho=w["rho"], mu=w["mu"], f=(0.0, 0.0))
+    x = prob.x
+    n = prob.n
+    ext = M.exterior_facet_indices(mesh.topology)
+    prob.facet_sets = [O.FacetSet(pairs=mesh.topology.facet_cell_pairs(ext), a_p=1.0, a_g=1.0)]
+    walls = np.nonzero(np.isclose(x[:, 0], 0) | np.isclose(x[:, 0], 1) | np.isclose(x[:, 1], 0))[0]
+    lidf = M.locate_entities_boundary(mesh, 1, lambda X: np.isclose(X[1], 1.0) & (X[0] > 1e-10) & (X[0] < 1 - 1e-10))
+    lid = np.unique(mesh.topology.facet_vertices[lidf])
+    g1 = np.zeros(2 * n)
+    g1[0::2] = 1.0
+    prob.bcs = T.oracle_bcs(prob, [("u", walls, np.zeros(2 * n)), ("u", lid, g1)])
+    xk = np.zeros(3 * n)
+    un = np.zeros(2 * n)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        xk = O.remove_nullspace(prob, xk)
+        xk, its, reason = O.newton_solve(prob, xk, un)
+        un = xk[:2 * n].copy()
+    return 3 * n, time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    for _ in range(min(args.warmup, 1)):
+        oracle_steps(w, 16, 1)
+    ndof, secs = oracle_steps(w, CPU_SAMPLE_NX, max(1, args.steps))
+    steps = max(1, args.steps)
+    val = ndof * steps / secs
+    line = {
+        "impl": "reference", "metric": "DOF-timesteps/s", "value": val, "unit": "DOF-timesteps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "solver": "stabilized_schur",
+                   "note": "DOLFINx/PETSc are not installable in this image; CPU arm = oracle port "
+                           "(numpy element kernels + SciPy SuperLU Newton) on a bounded sample of the workload"},
+        "cpu_baseline": {"value": val, "unit": "DOF-timesteps/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} time step(s) of {w['scenario']} at nx={CPU_SAMPLE_NX} "
+                                   f"({ndof} DOFs), numpy/SciPy threads as configured by the BLAS/OpenMP runtime"},
+        "e2e": {"value": val, "unit": "DOF-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lid_driven2D_nx707", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path exists only as sm_100a kernels (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    w = WORKLOADS[args.workload]
+
+    sc = build_scenario(w, device=local_rank)
+    s = sc.solver
+    hemo = s.hemo
+    ndof = s.N
+    E = s._cells_host.shape[0]
+    nnz = hemo.nnz
+    dev = hemo.device
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---- device-resident timed region --------------------------------------
+    for _ in range(W):
+        s.step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    hemo.prof_enable(True)
+    launches0 = hemo.launches
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    newton = ksp = 0
+    e0.record()
+    for _ in range(K):
+        s.step_device()
+        newton += s.its_snes
+        ksp += s.its_ksp
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = hemo.launches - launches0
+    prof = {c: hemo.prof_get(c) for c in PROF_CLASSES}
+    hemo.prof_enable(False)
+    clocks = sampler.stop()
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    value = world * ndof * K / (ms * 1e-3)
+
+    # ---- isolated assembly timings (cells/s, nnz/s) ------------------------------
+    def time_fn(fn, reps=5):
+        fn()
+        torch.cuda.synchronize(dev)
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps
+
+    jac_ms = time_fn(lambda: hemo.assemble_jacobian(s.d_x, s.d_un, s.d_vals))
+    res_ms = time_fn(lambda: hemo.assemble_residual(s.d_x, s.d_un, s.d_bcval, s.d_g))
+
+    # ---- end to end through the plugin API (host buffers) ------------------------
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            s.solveStep()
+            s.u_prev.x.array[:] = s.u_sol.x.array[:]
+            s.p_prev.x.array[:] = s.p_sol.x.array[:]
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            s.solveStep()
+            s.u_prev.x.array[:] = s.u_sol.x.array[:]
+            s.p_prev.x.array[:] = s.p_sol.x.array[:]
+        barrier()
+        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * ndof * K / float(t_e2e.item()), "unit": "DOF-timesteps/s",
+               "h2d_bytes_per_step": s.h2d_bytes_per_step, "d2h_bytes_per_step": s.d2h_bytes_per_step}
+
+    # ---- roofline of the dominant kernel -------------------------------------------
+    n = s.n
+    nnz_node = hemo.nnz_node
+    alg_bytes = {
+        0: 76 * nnz_node + 52 * n,                        # J values + node cols + rowptr + x + y
+        1: 12 * E + 8 * E + 56 * n + 648 * E,             # cells, h, nodal gathers, element matrices out
+        2: 648 * E + 36 * E + 12 * nnz_node + 72 * nnz_node,
+        3: 12 * E + 8 * E + 56 * n + 72 * E,
+        4: 36 * nnz_node + 4 * n + 112 * n,               # A00 BSR2 values + cols + rowptr + 7 vectors of 2n
+        5: 12 * nnz_node + 4 * n + 56 * n,
+        6: None, 7: None,
+        8: None,
+    }
+    peak, peak_kind = measured_peaks()
+    dom = max((c for c in prof if prof[c][1] > 0 and alg_bytes[c]), key=lambda c: prof[c][0], default=0)
+    dms, dcnt = prof[dom]
+    achieved = alg_bytes[dom] / (dms / dcnt * 1e-3) / 1e9 if dcnt else 0.0
+    roofline = {"bound": "hbm", "kernel": PROF_CLASSES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                "launches_timed": dcnt, "avg_us": 1e3 * dms / max(dcnt, 1),
+                "share_of_step": dms / ms,
+                "other_kernels": {PROF_CLASSES[c]: {"ms_total": prof[c][0], "launches": prof[c][1],
+                                                    "GBps": (alg_bytes[c] / (prof[c][0] / prof[c][1] * 1e-3) / 1e9
+                                                             if alg_bytes[c] and prof[c][1] else None)}
+                                  for c in prof if c != dom}}
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample --------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cdof, csecs = oracle_steps(w, CPU_SAMPLE_NX, 1)
+        cpu = {"value": cdof / csecs, "unit": "DOF-timesteps/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"1 time step of {w['scenario']} at nx={CPU_SAMPLE_NX} ({cdof} DOFs) with the numpy/SciPy "
+                         f"oracle port ({csecs:.1f} s); DOLFINx/PETSc not installable here"}
+
+    if rank == 0:
+        line = {
+            "metric": "DOF-timesteps/s", "value": value, "unit": "DOF-timesteps/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "solver": "stabilized_schur", "cells": E, "dofs": ndof,
+                       "nnz": nnz, "dt": w["dt"], "mu": w["mu"], "rho": w["rho"],
+                       "newton_its_per_step": newton / K, "fgmres_its_per_step": ksp / K,
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (one mesh per GPU)",
+                       "l2": "inputs larger than L2 (matrix %.0f MB, element buffer %.0f MB vs 126 MB L2)"
+                             % (8 * nnz / 1e6, 648 * E / 1e6)},
+            "assembly": {"jacobian_cells_per_s": world * E / (jac_ms * 1e-3), "jacobian_nnz_per_s": world * nnz / (jac_ms * 1e-3),
+                         "residual_cells_per_s": world * E / (res_ms * 1e-3), "jacobian_ms": jac_ms, "residual_ms": res_ms},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

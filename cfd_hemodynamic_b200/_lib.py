@@ -53,6 +53,8 @@ SYMBOLS = {
     "hemo_last_error": (C.c_char_p, [_VP]),
     "hemo_set_stream": (_I, [_VP, _VP]),
     "hemo_launch_count": (_L, [_VP]),
+    "hemo_prof_enable": (_I, [_VP, _I]),
+    "hemo_prof_get": (_I, [_VP, _I, C.POINTER(_D), C.POINTER(_L)]),
     "hemo_set_mesh": (_I, [_VP, _VP, _I, _VP, _I, _VP]),
     "hemo_set_node_graph": (_I, [_VP, _VP, _VP, _L]),
     "hemo_matrix_nnz": (_I, [_VP, C.POINTER(_L)]),
@@ -157,6 +159,15 @@ class Hemo:
     @property
     def launches(self) -> int:
         return int(self.lib.hemo_launch_count(self._ctx))
+
+    def prof_enable(self, on: bool):
+        self._check(self.lib.hemo_prof_enable(self._ctx, int(on)), "hemo_prof_enable")
+
+    def prof_get(self, cls: int):
+        ms = C.c_double()
+        cnt = C.c_int64()
+        self._check(self.lib.hemo_prof_get(self._ctx, cls, C.byref(ms), C.byref(cnt)), "hemo_prof_get")
+        return ms.value, cnt.value
 
     # ---- setup ---------------------------------------------------------
     def set_mesh(self, x2, cells, h):

@@ -59,28 +59,41 @@ k_numeric_ap(int n, const int32_t* __restrict__ a_rowptr, const int32_t* __restr
     }
 }
 
-// Ac = (R (x) I_bs) * AP: one thread per coarse block row
+// Ac = (R (x) I_bs) * AP: one warp per coarse block row; each lane owns one
+// output block and scans the (R entry, AP entry) pairs of the row (uniform,
+// broadcast loads) — deterministic, no atomics, no searches.
 template <int BS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_numeric_rap(int nc, const int32_t* __restrict__ r_rowptr, const int32_t* __restrict__ r_col,
               const double* __restrict__ r_val, const int32_t* __restrict__ ap_rowptr,
               const int32_t* __restrict__ ap_col, const double* __restrict__ ap_val,
               const int32_t* __restrict__ c_rowptr, const int32_t* __restrict__ c_col,
               double* __restrict__ c_val) {
-    const int I = blockIdx.x * blockDim.x + threadIdx.x;
+    const int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (I >= nc) return;
     const int o0 = c_rowptr[I], o1 = c_rowptr[I + 1];
-    for (int s = o0; s < o1; ++s)
+    const int t0 = r_rowptr[I], t1 = r_rowptr[I + 1];
+    for (int base = o0; base < o1; base += 32) {
+        const int s = base + lane;
+        const int myc = (s < o1) ? c_col[s] : -1;
+        double acc[BS * BS];
 #pragma unroll
-        for (int k = 0; k < BS * BS; ++k) c_val[(int64_t)s * BS * BS + k] = 0.0;
-    for (int t = r_rowptr[I]; t < r_rowptr[I + 1]; ++t) {
-        const int i = r_col[t];
-        const double w = r_val[t];
-        for (int u = ap_rowptr[i]; u < ap_rowptr[i + 1]; ++u) {
-            const int pos = find_col(c_col, o0, o1, ap_col[u]);
-            if (pos < 0) continue;
+        for (int k = 0; k < BS * BS; ++k) acc[k] = 0.0;
+        for (int t = t0; t < t1; ++t) {
+            const int i = r_col[t];
+            const double w = r_val[t];
+            const int u1 = ap_rowptr[i + 1];
+            for (int u = ap_rowptr[i]; u < u1; ++u) {
+                if (ap_col[u] == myc) {
 #pragma unroll
-            for (int k = 0; k < BS * BS; ++k) c_val[(int64_t)pos * BS * BS + k] += w * ap_val[(int64_t)u * BS * BS + k];
+                    for (int k = 0; k < BS * BS; ++k) acc[k] = fma(w, ap_val[(int64_t)u * BS * BS + k], acc[k]);
+                }
+            }
+        }
+        if (s < o1) {
+#pragma unroll
+            for (int k = 0; k < BS * BS; ++k) c_val[(int64_t)s * BS * BS + k] = acc[k];
         }
     }
 }
@@ -154,7 +167,35 @@ __global__ void k_cheb_start_zero(int64_t N, const double* __restrict__ dinv, co
     x[i] = dv;
 }
 
-// start from x != 0: r = D^-1 (b - A x) ; d = r / theta   (one thread per block row).
+// (A x)_i for block row i, computed by the 4 lanes of a row group; every lane
+// of the group returns the full sum.
+template <int BS>
+__device__ __forceinline__ void row_product(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                            const double* __restrict__ val, const double* __restrict__ x,
+                                            int i, bool ok, int lane, double acc[BS]) {
+#pragma unroll
+    for (int k = 0; k < BS; ++k) acc[k] = 0.0;
+    const int r0 = ok ? rowptr[i] : 0, r1 = ok ? rowptr[i + 1] : 0;
+    for (int t = r0 + lane; t < r1; t += 4) {
+        const int j = col[t];
+        if (BS == 1) {
+            acc[0] = fma(val[t], x[j], acc[0]);
+        } else {
+            const double2 xv = reinterpret_cast<const double2*>(x)[j];
+            const double2 v0 = reinterpret_cast<const double2*>(val)[2 * (int64_t)t];
+            const double2 v1 = reinterpret_cast<const double2*>(val)[2 * (int64_t)t + 1];
+            acc[0] += v0.x * xv.x + v0.y * xv.y;
+            acc[BS - 1] += v1.x * xv.x + v1.y * xv.y;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < BS; ++k) {
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1, 4);
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2, 4);
+    }
+}
+
+// start from x != 0: r = D^-1 (b - A x) ; d = r / theta   (4 lanes per block row).
 // x is NOT updated here (other rows still read it); the update x += d is folded
 // into the first k_cheb_step (add_old) or done by an axpy when degree == 1.
 template <int BS>
@@ -162,50 +203,34 @@ __global__ void __launch_bounds__(256)
 k_cheb_start(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
              const double* __restrict__ val, const double* __restrict__ dinv, const double* __restrict__ b,
              double inv_theta, const double* __restrict__ xin, double* __restrict__ r, double* __restrict__ d) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt >> 2, lane = gt & 3;
+    const bool ok = i < n;
     double acc[BS];
-#pragma unroll
-    for (int k = 0; k < BS; ++k) acc[k] = 0.0;
-    for (int t = rowptr[i]; t < rowptr[i + 1]; ++t) {
-        const int j = col[t];
-#pragma unroll
-        for (int k = 0; k < BS; ++k)
-#pragma unroll
-            for (int l = 0; l < BS; ++l) acc[k] += val[(int64_t)t * BS * BS + k * BS + l] * xin[(int64_t)j * BS + l];
-    }
-#pragma unroll
-    for (int k = 0; k < BS; ++k) {
-        const int64_t q = (int64_t)i * BS + k;
-        const double rv = dinv[q] * (b[q] - acc[k]);
+    row_product<BS>(rowptr, col, val, xin, i, ok, lane, acc);
+    if (ok && lane < BS) {
+        const int64_t q = (int64_t)i * BS + lane;
+        const double rv = dinv[q] * (b[q] - (lane == 0 ? acc[0] : acc[BS - 1]));
         r[q] = rv;
         d[q] = rv * inv_theta;
     }
 }
 
-// one step: r -= D^-1 A d_old ; d_new = c1 d_old + c2 r ; x += d_new
+// one step: r -= D^-1 A d_old ; d_new = c1 d_old + c2 r ; x += d_new (+ d_old)
 template <int BS>
 __global__ void __launch_bounds__(256)
 k_cheb_step(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
             const double* __restrict__ val, const double* __restrict__ dinv, double c1, double c2,
             const double* __restrict__ dold, double* __restrict__ dnew, double* __restrict__ r,
             double* __restrict__ x, int add_old) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt >> 2, lane = gt & 3;
+    const bool ok = i < n;
     double acc[BS];
-#pragma unroll
-    for (int k = 0; k < BS; ++k) acc[k] = 0.0;
-    for (int t = rowptr[i]; t < rowptr[i + 1]; ++t) {
-        const int j = col[t];
-#pragma unroll
-        for (int k = 0; k < BS; ++k)
-#pragma unroll
-            for (int l = 0; l < BS; ++l) acc[k] += val[(int64_t)t * BS * BS + k * BS + l] * dold[(int64_t)j * BS + l];
-    }
-#pragma unroll
-    for (int k = 0; k < BS; ++k) {
-        const int64_t q = (int64_t)i * BS + k;
-        const double rv = r[q] - dinv[q] * acc[k];
+    row_product<BS>(rowptr, col, val, dold, i, ok, lane, acc);
+    if (ok && lane < BS) {
+        const int64_t q = (int64_t)i * BS + lane;
+        const double rv = r[q] - dinv[q] * (lane == 0 ? acc[0] : acc[BS - 1]);
         r[q] = rv;
         const double dv = c1 * dold[q] + c2 * rv;
         dnew[q] = dv;
@@ -242,7 +267,7 @@ k_transfer(int nrows, const int32_t* __restrict__ rowptr, const int32_t* __restr
 // ---------------------------------------------------------------------------
 template <int BS>
 __global__ void k_dense_fill(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                             const double* __restrict__ val, int N, double* __restrict__ M /*N x 2N*/) {
+                             const double* __restrict__ val, int N, double shift_rel, double* __restrict__ M /*N x N*/) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     for (int t = rowptr[i]; t < rowptr[i + 1]; ++t) {
@@ -250,83 +275,51 @@ __global__ void k_dense_fill(int n, const int32_t* __restrict__ rowptr, const in
 #pragma unroll
         for (int k = 0; k < BS; ++k)
 #pragma unroll
-            for (int l = 0; l < BS; ++l)
-                M[(int64_t)(i * BS + k) * 2 * N + (j * BS + l)] = val[(int64_t)t * BS * BS + k * BS + l];
+            for (int l = 0; l < BS; ++l) {
+                double v = val[(int64_t)t * BS * BS + k * BS + l];
+                // optional relative diagonal shift (singular Neumann operator)
+                if (i == j && k == l) v *= (1.0 + shift_rel);
+                M[(int64_t)(i * BS + k) * N + (j * BS + l)] = v;
+            }
     }
 }
 
-__global__ void k_dense_identity(int N, double shift_rel, double* __restrict__ M) {
-    // right half = I; optional relative diagonal shift (singular Neumann operator)
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    M[(int64_t)i * 2 * N + N + i] = 1.0;
-    if (shift_rel > 0.0) M[(int64_t)i * 2 * N + i] *= (1.0 + shift_rel);
-}
-
+// In-place Gauss–Jordan inversion of an N x N matrix held in shared memory by
+// one CTA (N <= HEMO_DENSE_MAX).  No pivoting: the coarsest Galerkin operators
+// are (shifted) M-matrix-like / diagonally dominated; a vanishing pivot sets *fail.
 __global__ void __launch_bounds__(1024)
-k_dense_invert(int N, double* __restrict__ M /*N x 2N augmented*/, int* __restrict__ fail) {
-    __shared__ double smax[1024];
-    __shared__ int sidx[1024];
-    __shared__ double pivrow_scale;
+k_dense_invert(int N, const double* __restrict__ Min, double* __restrict__ inv, int* __restrict__ fail) {
+    extern __shared__ double A[];          // N*N
     __shared__ double fcol[HEMO_DENSE_MAX];
+    __shared__ double pivinv;
     const int tid = threadIdx.x;
-    const int W = 2 * N;
+    const int total = N * N;
+    for (int q = tid; q < total; q += blockDim.x) A[q] = Min[q];
+    __syncthreads();
     for (int p = 0; p < N; ++p) {
-        // pivot search in column p, rows p..N-1
-        double best = -1.0;
-        int bi = p;
-        for (int r = p + tid; r < N; r += blockDim.x) {
-            const double v = fabs(M[(int64_t)r * W + p]);
-            if (v > best) { best = v; bi = r; }
-        }
-        smax[tid] = best; sidx[tid] = bi;
-        __syncthreads();
-        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-            if (tid < s) {
-                if (smax[tid + s] > smax[tid] || (smax[tid + s] == smax[tid] && sidx[tid + s] < sidx[tid])) {
-                    smax[tid] = smax[tid + s]; sidx[tid] = sidx[tid + s];
-                }
-            }
-            __syncthreads();
-        }
-        const int piv = sidx[0];
         if (tid == 0) {
-            if (!(smax[0] > 0.0)) *fail = 1;
-        }
-        // swap rows p and piv
-        if (piv != p) {
-            for (int c = tid; c < W; c += blockDim.x) {
-                const double a = M[(int64_t)p * W + c];
-                M[(int64_t)p * W + c] = M[(int64_t)piv * W + c];
-                M[(int64_t)piv * W + c] = a;
-            }
+            const double piv = A[p * N + p];
+            if (!(fabs(piv) > 0.0) || !isfinite(piv)) *fail = 1;
+            pivinv = 1.0 / piv;
+            A[p * N + p] = 1.0;
         }
         __syncthreads();
-        if (tid == 0) pivrow_scale = 1.0 / M[(int64_t)p * W + p];
+        const double pi = pivinv;
+        for (int c = tid; c < N; c += blockDim.x) A[p * N + c] *= pi;
+        for (int r = tid; r < N; r += blockDim.x) {
+            if (r != p) { fcol[r] = A[r * N + p]; A[r * N + p] = 0.0; }
+            else fcol[r] = 0.0;
+        }
         __syncthreads();
-        const double sc = pivrow_scale;
-        for (int c = tid; c < W; c += blockDim.x) M[(int64_t)p * W + c] *= sc;
-        __syncthreads();
-        // eliminate column p from all other rows: stage the multipliers, then
-        // update the whole matrix without further synchronisation
-        for (int r = tid; r < N; r += blockDim.x) fcol[r] = (r == p) ? 0.0 : M[(int64_t)r * W + p];
-        __syncthreads();
-        const int64_t total = (int64_t)N * W;
-        for (int64_t q = tid; q < total; q += blockDim.x) {
-            const int r = (int)(q / W);
-            const int c = (int)(q - (int64_t)r * W);
+        for (int q = tid; q < total; q += blockDim.x) {
+            const int r = q / N;
+            const int c = q - r * N;
             const double f = fcol[r];
-            if (f != 0.0) M[q] -= f * M[(int64_t)p * W + c];
+            if (f != 0.0) A[q] -= f * A[p * N + c];
         }
         __syncthreads();
     }
-}
-
-__global__ void k_dense_extract(int N, const double* __restrict__ M, double* __restrict__ inv) {
-    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (q >= (int64_t)N * N) return;
-    const int r = (int)(q / N), c = (int)(q % N);
-    inv[q] = M[(int64_t)r * 2 * N + N + c];
+    for (int q = tid; q < total; q += blockDim.x) inv[q] = A[q];
 }
 
 // y = inv * b : one warp per row
@@ -431,7 +424,7 @@ extern "C" int hemo_amg_finalize(hemo_ctx* ctx, int which, int n_levels) {
     if (Nc > HEMO_DENSE_MAX) HEMO_FAIL(ctx, HEMO_EINVAL, "coarsest AMG level too large for the dense solve");
     amg.dense_n = Nc;
     if ((rc = hemo_alloc(ctx, &amg.dense_inv, (size_t)Nc * Nc))) return rc;
-    if ((rc = hemo_alloc(ctx, &amg.dense_work, (size_t)Nc * 2 * Nc + 8))) return rc;
+    if ((rc = hemo_alloc(ctx, &amg.dense_work, (size_t)Nc * Nc + 8))) return rc;
     if ((rc = hemo_ensure_reduce(ctx, (size_t)hemo_grid(ctx->n, 256) + 1184 * 8, 512))) return rc;
     amg.ready = true;
     return 0;
@@ -447,9 +440,11 @@ static int amg_numeric_t(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift) {
         k_numeric_ap<BS><<<hemo_grid(A.n, 128), 128, 0, st>>>(A.n, A.rowptr, A.col, A.val, L.p_rowptr, L.p_col, L.p_val,
                                                               L.ap_rowptr, L.ap_col, L.ap_val);
         HEMO_LAUNCH_CHECK(ctx);
-        k_numeric_rap<BS><<<hemo_grid(C.n, 128), 128, 0, st>>>(C.n, L.r_rowptr, L.r_col, L.r_val, L.ap_rowptr, L.ap_col,
+        if (l == 0) HEMO_PROF_BEGIN(ctx, HEMO_PROF_RAP);
+        k_numeric_rap<BS><<<hemo_grid((int64_t)C.n * 32, 256), 256, 0, st>>>(C.n, L.r_rowptr, L.r_col, L.r_val, L.ap_rowptr, L.ap_col,
                                                                L.ap_val, L.c_rowptr, L.c_col, C.val);
         HEMO_LAUNCH_CHECK(ctx);
+        if (l == 0) HEMO_PROF_END(ctx, HEMO_PROF_RAP);
     }
     // smoother data; bounds are read back in one copy
     for (int l = 0; l + 1 < amg->nlev; ++l) {
@@ -468,15 +463,13 @@ static int amg_numeric_t(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift) {
     {
         const HemoAmgOp& A = amg->op[amg->nlev - 1];
         const int N = amg->dense_n;
-        int* fail = reinterpret_cast<int*>(amg->dense_work + (size_t)N * 2 * N);
-        HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(amg->dense_work, 0, sizeof(double) * ((size_t)N * 2 * N + 8), st));
-        k_dense_fill<BS><<<hemo_grid(A.n, 128), 128, 0, st>>>(A.n, A.rowptr, A.col, A.val, N, amg->dense_work);
+        int* fail = reinterpret_cast<int*>(amg->dense_work + (size_t)N * N);
+        HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(amg->dense_work, 0, sizeof(double) * ((size_t)N * N + 8), st));
+        k_dense_fill<BS><<<hemo_grid(A.n, 128), 128, 0, st>>>(A.n, A.rowptr, A.col, A.val, N, coarse_shift, amg->dense_work);
         HEMO_LAUNCH_CHECK(ctx);
-        k_dense_identity<<<hemo_grid(N, 128), 128, 0, st>>>(N, coarse_shift, amg->dense_work);
-        HEMO_LAUNCH_CHECK(ctx);
-        k_dense_invert<<<1, 1024, 0, st>>>(N, amg->dense_work, fail);
-        HEMO_LAUNCH_CHECK(ctx);
-        k_dense_extract<<<hemo_grid((int64_t)N * N, 256), 256, 0, st>>>(N, amg->dense_work, amg->dense_inv);
+        const size_t smem = sizeof(double) * (size_t)N * N;
+        HEMO_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_dense_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_dense_invert<<<1, 1024, smem, st>>>(N, amg->dense_work, amg->dense_inv, fail);
         HEMO_LAUNCH_CHECK(ctx);
         int fail_h = 0;
         HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(&fail_h, fail, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -514,7 +507,7 @@ static int smooth_t(hemo_ctx* ctx, const HemoAmgOp& A, const double* b, double* 
     if (x_is_zero) {
         k_cheb_start_zero<BS><<<hemo_grid(N, 256), 256, 0, st>>>(N, A.dinv, b, 1.0 / theta, A.r, d0, x);
     } else {
-        k_cheb_start<BS><<<hemo_grid(A.n, 256), 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, A.dinv, b, 1.0 / theta, x,
+        k_cheb_start<BS><<<hemo_grid((int64_t)A.n * 4, 256), 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, A.dinv, b, 1.0 / theta, x,
                                                               A.r, d0);
     }
     HEMO_LAUNCH_CHECK(ctx);
@@ -522,9 +515,12 @@ static int smooth_t(hemo_ctx* ctx, const HemoAmgOp& A, const double* b, double* 
     for (int k = 1; k < degree; ++k) {
         const double rho_new = 1.0 / (2.0 * sigma - rho);
         const double c1 = rho_new * rho, c2 = 2.0 * rho_new / delta;
-        k_cheb_step<BS><<<hemo_grid(A.n, 256), 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, A.dinv, c1, c2, d0, d1, A.r, x,
+        const bool fine = (A.n == ctx->n);
+        if (fine) HEMO_PROF_BEGIN(ctx, BS == 2 ? HEMO_PROF_CHEB_U0 : HEMO_PROF_CHEB_P0);
+        k_cheb_step<BS><<<hemo_grid((int64_t)A.n * 4, 256), 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, A.dinv, c1, c2, d0, d1, A.r, x,
                                                              pending ? 1 : 0);
         HEMO_LAUNCH_CHECK(ctx);
+        if (fine) HEMO_PROF_END(ctx, BS == 2 ? HEMO_PROF_CHEB_U0 : HEMO_PROF_CHEB_P0);
         pending = false;
         double* t = d0; d0 = d1; d1 = t;
         rho = rho_new;

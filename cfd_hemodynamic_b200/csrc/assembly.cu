@@ -1017,8 +1017,10 @@ extern "C" int hemo_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const 
     if (rc) return rc;
     const int E = ctx->E, n = ctx->n;
     cudaStream_t st = ctx->stream;
+    HEMO_PROF_BEGIN(ctx, HEMO_PROF_CELL_JAC);
     k_cell_jacobian<<<hemo_grid(E, 128), 128, 0, st>>>(E, n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, ctx->Ae);
     HEMO_LAUNCH_CHECK(ctx);
+    HEMO_PROF_END(ctx, HEMO_PROF_CELL_JAC);
     for (int s = 0; s < HEMO_MAX_FACET_SETS; ++s) {
         const HemoFacetSet& fs = ctx->fsets[s];
         if (fs.m == 0) continue;
@@ -1026,10 +1028,12 @@ extern "C" int hemo_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const 
                                                           ctx->h, x_dev, un_dev, nullptr, nullptr, ctx->Ae);
         HEMO_LAUNCH_CHECK(ctx);
     }
+    HEMO_PROF_BEGIN(ctx, HEMO_PROF_GATHER_MAT);
     k_gather_matrix<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(
         n, ctx->nnz_node, E, ctx->nrowptr, ctx->ncol, ctx->rowof, ctx->mseg_ptr, ctx->mseg_src, ctx->Ae,
         ctx->have_bc ? ctx->dofflag : nullptr, ctx->dofmult, vals_dev);
     HEMO_LAUNCH_CHECK(ctx);
+    HEMO_PROF_END(ctx, HEMO_PROF_GATHER_MAT);
     return 0;
 }
 
@@ -1046,8 +1050,10 @@ extern "C" int hemo_assemble_residual(hemo_ctx* ctx, const double* x_dev, const 
         k_lift_vector<<<hemo_grid(3 * (int64_t)n, 256), 256, 0, st>>>(3 * (int64_t)n, ctx->dofflag, x_dev, g_dev, ctx->dvec);
         HEMO_LAUNCH_CHECK(ctx);
     }
+    HEMO_PROF_BEGIN(ctx, HEMO_PROF_CELL_RES);
     k_cell_residual<<<hemo_grid(E, 128), 128, 0, st>>>(E, n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, cf, ctx->dvec, ctx->Fe);
     HEMO_LAUNCH_CHECK(ctx);
+    HEMO_PROF_END(ctx, HEMO_PROF_CELL_RES);
     for (int s = 0; s < HEMO_MAX_FACET_SETS; ++s) {
         const HemoFacetSet& fs = ctx->fsets[s];
         if (fs.m == 0) continue;

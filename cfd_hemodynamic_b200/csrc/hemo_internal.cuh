@@ -13,7 +13,7 @@
 #define HEMO_NRULES 6
 #define HEMO_MAX_FACET_SETS 8
 #define HEMO_MAX_LEVELS 16
-#define HEMO_DENSE_MAX 1024   // max dofs of the dense coarsest-level solve
+#define HEMO_DENSE_MAX 160    // max dofs of the dense coarsest-level solve (N*N doubles in shared memory)
 
 struct HemoRule {
     int nq;
@@ -68,7 +68,19 @@ struct HemoAmg {
     int dense_n = 0;
 };
 
+// kernel classes timed by the optional CUDA-event profiler (hemo_prof_*)
+enum { HEMO_PROF_SPMV = 0, HEMO_PROF_CELL_JAC = 1, HEMO_PROF_GATHER_MAT = 2, HEMO_PROF_CELL_RES = 3,
+       HEMO_PROF_CHEB_U0 = 4, HEMO_PROF_CHEB_P0 = 5, HEMO_PROF_MDOT = 6, HEMO_PROF_MAXPY = 7,
+       HEMO_PROF_RAP = 8, HEMO_PROF_NCLASS = 9 };
+
+struct HemoProf {
+    bool on = false;
+    std::vector<cudaEvent_t> ev[HEMO_PROF_NCLASS];   // begin/end pairs
+    size_t used[HEMO_PROF_NCLASS] = {0};
+};
+
 struct hemo_ctx {
+    HemoProf prof;
     int device = 0;
     cudaStream_t stream = 0;
     std::string err;
@@ -154,6 +166,19 @@ struct hemo_ctx {
             return (int)_e;                                          \
         }                                                            \
     } while (0)
+
+static inline void hemo_prof_mark(hemo_ctx* ctx, int cls) {
+    if (!ctx->prof.on) return;
+    HemoProf& p = ctx->prof;
+    if (p.used[cls] == p.ev[cls].size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        p.ev[cls].push_back(e);
+    }
+    cudaEventRecord(p.ev[cls][p.used[cls]++], ctx->stream);
+}
+#define HEMO_PROF_BEGIN(ctx, cls) hemo_prof_mark(ctx, cls)
+#define HEMO_PROF_END(ctx, cls) hemo_prof_mark(ctx, cls)
 
 template <typename T>
 static inline int hemo_alloc(hemo_ctx* ctx, T** p, size_t count) {

@@ -362,8 +362,10 @@ int hemo_mdot(hemo_ctx* ctx, int64_t n, int k, const double* V, int64_t ldv, con
     if (rc) return rc;
     // w is re-read once per basis vector from L2/HBM; V dominates the traffic.
     int g = grid_for((n + MD_TILE - 1) / MD_TILE);
+    HEMO_PROF_BEGIN(ctx, HEMO_PROF_MDOT);
     k_mdot_partial<<<g, RED_THREADS, sizeof(double) * k, ctx->stream>>>(n, k, V, ldv, w, ctx->red_partial);
     HEMO_LAUNCH_CHECK(ctx);
+    HEMO_PROF_END(ctx, HEMO_PROF_MDOT);
     k_reduce_final<<<k, RED_THREADS, 0, ctx->stream>>>(g, ctx->red_partial, ctx->red_out, -1);
     HEMO_LAUNCH_CHECK(ctx);
     HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->red_host, ctx->red_out, sizeof(double) * k, cudaMemcpyDeviceToHost, ctx->stream));
@@ -378,9 +380,11 @@ int hemo_maxpy(hemo_ctx* ctx, int64_t n, int k, const double* V, int64_t ldv, co
     int rc = hemo_ensure_reduce(ctx, (size_t)RED_BLOCKS * 2, 512);
     if (rc) return rc;
     const int g = grid_for(n);
+    HEMO_PROF_BEGIN(ctx, HEMO_PROF_MAXPY);
     k_maxpy_norm<<<g, RED_THREADS, sizeof(double) * (k > 0 ? k : 1), ctx->stream>>>(
         n, k, V, ldv, hcoef_dev, sign, w, norm_host ? ctx->red_partial : nullptr);
     HEMO_LAUNCH_CHECK(ctx);
+    HEMO_PROF_END(ctx, HEMO_PROF_MAXPY);
     if (norm_host) {
         k_reduce_final<<<1, RED_THREADS, 0, ctx->stream>>>(g, ctx->red_partial, ctx->red_out + 500, 0);
         HEMO_LAUNCH_CHECK(ctx);

@@ -200,7 +200,9 @@ extern "C" int hemo_fgmres(hemo_ctx* ctx, const double* vals_dev, const double* 
             double* vj = V + (int64_t)j * ldv;
             double* zj = Z + (int64_t)j * ldv;
             if ((rc = hemo_pc_apply(ctx, vals_dev, vj, zj))) return rc;
+            HEMO_PROF_BEGIN(ctx, HEMO_PROF_SPMV);
             if ((rc = hemo_spmv(ctx, vals_dev, zj, w))) return rc;
+            HEMO_PROF_END(ctx, HEMO_PROF_SPMV);
             // classical Gram–Schmidt (PETSc default: no refinement)
             if ((rc = hemo_mdot(ctx, N, j + 1, V, ldv, w, hcol.data()))) return rc;
             double hn = 0.0;
@@ -302,6 +304,29 @@ extern "C" const char* hemo_last_error(hemo_ctx* ctx) { return ctx ? ctx->err.c_
 extern "C" int hemo_set_stream(hemo_ctx* ctx, void* cuda_stream) {
     if (!ctx) return HEMO_EINVAL;
     ctx->stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+extern "C" int hemo_prof_enable(hemo_ctx* ctx, int on) {
+    if (!ctx) return HEMO_EINVAL;
+    ctx->prof.on = on != 0;
+    for (int c = 0; c < HEMO_PROF_NCLASS; ++c) ctx->prof.used[c] = 0;
+    return 0;
+}
+
+extern "C" int hemo_prof_get(hemo_ctx* ctx, int cls, double* ms_total, int64_t* launches) {
+    if (!ctx || cls < 0 || cls >= HEMO_PROF_NCLASS || !ms_total || !launches) return HEMO_EINVAL;
+    HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HemoProf& p = ctx->prof;
+    double tot = 0.0;
+    const size_t pairs = p.used[cls] / 2;
+    for (size_t i = 0; i < pairs; ++i) {
+        float ms = 0.f;
+        HEMO_CHECK_CUDA(ctx, cudaEventElapsedTime(&ms, p.ev[cls][2 * i], p.ev[cls][2 * i + 1]));
+        tot += ms;
+    }
+    *ms_total = tot;
+    *launches = (int64_t)pairs;
     return 0;
 }
 

@@ -54,7 +54,7 @@ class BlockSchurSolver:
             L = sp.csr_matrix((lap_host, ncol, nrowptr), shape=(n, n))
             pmask |= omask
         self.levels = []
-        for which, mask, max_coarse in ((0, umask, 400), (1, pmask, 800)):
+        for which, mask, max_coarse in ((0, umask, 80), (1, pmask, 160)):
             lv = amg_setup.build_hierarchy(L, mask, max_coarse=max_coarse, theta=strength_theta,
                                            smooth=smooth_prolongator)
             for l, d in enumerate(lv):

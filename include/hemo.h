@@ -86,6 +86,14 @@ int hemo_set_stream(hemo_ctx* ctx, void* cuda_stream);
 /* number of kernels this context has launched so far (bench.py gpu_launches) */
 int64_t hemo_launch_count(hemo_ctx* ctx);
 
+/* Optional CUDA-event timing of selected kernel classes on the context's
+ * stream (bench.py roofline): 0 SpMV(J), 1 cell Jacobian, 2 matrix gather,
+ * 3 cell residual, 4 Chebyshev step A00 level 0, 5 Chebyshev step Lp level 0,
+ * 6 multi-dot, 7 multi-axpy+norm, 8 Galerkin R*AP level 0.  enable(on) resets
+ * the counters; get() synchronises the stream. */
+int hemo_prof_enable(hemo_ctx* ctx, int on);
+int hemo_prof_get(hemo_ctx* ctx, int kernel_class, double* ms_total, int64_t* launches);
+
 /* ---- mesh, spaces, pattern ---------------------------------------------- */
 /* mesh.geometry.x / .dofmap / mesh.h (src/solvers/stabilized_schur.py:55-58,83-88).
  * x: n_nodes*2 doubles, cells: n_cells*3 int32, h: n_cells doubles; borrowed. */
