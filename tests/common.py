@@ -97,3 +97,33 @@ def oracle_bcs(prob, bcs):
             d = nodes
         out.append((block, d, np.asarray(values, dtype=float)))
     return out
+
+
+def oracle_problem_from_solver(s, facet_tags=None, tags=None):
+    """Build the oracle Problem that mirrors a B200 solver instance after setup():
+    same mesh, parameters, quadrature rules, Dirichlet objects (in list order) and the
+    boundary terms of its variant with the setup() multiplicity."""
+    from cfd_hemodynamic_b200.fem import mesh as M
+    mesh = s.mesh
+    fval = np.asarray(s.f.value, dtype=float).reshape(-1)[:2]
+    prob = make_problem(mesh, dt=float(s.dt.value), rho=float(s.rho.value), mu=float(s.mu.value), f=fval)
+    bcs = [("u", bc.block_dofs, bc.g.x.array.copy()) for bc in s.bcu_d]
+    bcs += [("p", bc.block_dofs, bc.g.x.array.copy()) for bc in s.bcp_d]
+    prob.bcs = oracle_bcs(prob, bcs)
+    c = float(s._setup_count)
+    fs = []
+    if s.variant == "schur":
+        ext = M.exterior_facet_indices(mesh.topology)
+        fs.append(O.FacetSet(pairs=mesh.topology.facet_cell_pairs(ext), a_p=1.0, a_g=1.0))
+    elif s.variant == "backflow":
+        out = facet_tags.find(tags["outlet"])
+        fs.append(O.FacetSet(pairs=mesh.topology.facet_cell_pairs(out), a_b=c, beta_b=s.beta_backflow))
+    else:
+        fin = facet_tags.find(tags["inlet"])
+        out = facet_tags.find(tags["outlet"])
+        fs.append(O.FacetSet(pairs=mesh.topology.facet_cell_pairs(fin), pconst=c * s.p_inlet, a_n=c,
+                             beta_n=s.beta_nitsche))
+        fs.append(O.FacetSet(pairs=mesh.topology.facet_cell_pairs(out), pconst=0.0, a_s=c, a_b=c,
+                             beta_b=s.beta_backflow))
+    prob.facet_sets = fs
+    return prob
