@@ -78,6 +78,7 @@ SYMBOLS = {
     "hemo_amg_finalize": (_I, [_VP, _I, _I]),
     "hemo_host_aggregate": (_I, [_I, _VP, _VP, _VP, _VP, C.POINTER(_I)]),
     "hemo_set_solver_opts": (_I, [_VP, C.POINTER(SolverOpts)]),
+    "hemo_use_graph": (_I, [_VP, _I]),
     "hemo_pc_setup": (_I, [_VP, _VP, _VP, _VP]),
     "hemo_amg_apply": (_I, [_VP, _I, _VP, _VP, _I]),
     "hemo_amg_get_level_values": (_I, [_VP, _I, _I, _VP, _L]),
@@ -132,7 +133,14 @@ class Hemo:
         rc = self.lib.hemo_ctx_create(device, C.byref(self._ctx))
         if rc != 0:
             raise HemoError(f"hemo_ctx_create failed ({rc})")
-        self.lib.hemo_set_stream(self._ctx, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        # all work (library kernels and torch copies) runs on one non-default stream, which
+        # the preconditioner's CUDA-graph capture requires; it becomes torch's current stream
+        if torch.cuda.current_stream(self.device).cuda_stream == 0:
+            self.stream = torch.cuda.Stream(self.device)
+            torch.cuda.set_stream(self.stream)
+        else:
+            self.stream = torch.cuda.current_stream(self.device)
+        self.lib.hemo_set_stream(self._ctx, C.c_void_p(self.stream.cuda_stream))
         self._keep = {}     # borrowed tensors must outlive the context
 
     def close(self):
@@ -283,6 +291,9 @@ class Hemo:
     def set_solver_opts(self, **kw):
         o = SolverOpts(**kw)
         self._check(self.lib.hemo_set_solver_opts(self._ctx, C.byref(o)), "hemo_set_solver_opts")
+
+    def use_graph(self, on: bool):
+        self._check(self.lib.hemo_use_graph(self._ctx, int(on)), "hemo_use_graph")
 
     def pc_setup(self, vals, lap=None, mass=None):
         if lap is not None:

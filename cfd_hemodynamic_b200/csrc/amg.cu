@@ -30,31 +30,41 @@ __device__ __forceinline__ int find_col(const int32_t* __restrict__ col, int lo,
     return -1;
 }
 
-// AP = A * (P (x) I_bs): one thread per fine block row
+// AP = A * (P (x) I_bs): 8 lanes per fine block row; each lane owns one output
+// block of the row and scans the (A entry, P entry) pairs — no searches, no
+// read-modify-write on global memory, fixed summation order.
 template <int BS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_numeric_ap(int n, const int32_t* __restrict__ a_rowptr, const int32_t* __restrict__ a_col,
              const double* __restrict__ a_val, const int32_t* __restrict__ p_rowptr,
              const int32_t* __restrict__ p_col, const double* __restrict__ p_val,
              const int32_t* __restrict__ ap_rowptr, const int32_t* __restrict__ ap_col,
              double* __restrict__ ap_val) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt >> 3, lane = gt & 7;
     if (i >= n) return;
     const int o0 = ap_rowptr[i], o1 = ap_rowptr[i + 1];
-    for (int s = o0; s < o1; ++s)
+    const int t0 = a_rowptr[i], t1 = a_rowptr[i + 1];
+    for (int base = o0; base < o1; base += 8) {
+        const int s = base + lane;
+        const int myc = (s < o1) ? ap_col[s] : -1;
+        double acc[BS * BS];
 #pragma unroll
-        for (int k = 0; k < BS * BS; ++k) ap_val[(int64_t)s * BS * BS + k] = 0.0;
-    for (int t = a_rowptr[i]; t < a_rowptr[i + 1]; ++t) {
-        const int j = a_col[t];
-        double blk[BS * BS];
+        for (int k = 0; k < BS * BS; ++k) acc[k] = 0.0;
+        for (int t = t0; t < t1; ++t) {
+            const int j = a_col[t];
+            const int u1 = p_rowptr[j + 1];
+            for (int u = p_rowptr[j]; u < u1; ++u) {
+                if (p_col[u] == myc) {
+                    const double w = p_val[u];
 #pragma unroll
-        for (int k = 0; k < BS * BS; ++k) blk[k] = a_val[(int64_t)t * BS * BS + k];
-        for (int u = p_rowptr[j]; u < p_rowptr[j + 1]; ++u) {
-            const int pos = find_col(ap_col, o0, o1, p_col[u]);
-            if (pos < 0) continue;   // pattern given by the host always contains it
-            const double w = p_val[u];
+                    for (int k = 0; k < BS * BS; ++k) acc[k] = fma(w, a_val[(int64_t)t * BS * BS + k], acc[k]);
+                }
+            }
+        }
+        if (s < o1) {
 #pragma unroll
-            for (int k = 0; k < BS * BS; ++k) ap_val[(int64_t)pos * BS * BS + k] += w * blk[k];
+            for (int k = 0; k < BS * BS; ++k) ap_val[(int64_t)s * BS * BS + k] = acc[k];
         }
     }
 }
@@ -262,6 +272,152 @@ k_transfer(int nrows, const int32_t* __restrict__ rowptr, const int32_t* __restr
 }
 
 // ---------------------------------------------------------------------------
+// fused coarse V-cycle: all levels with n <= HEMO_FUSE_MAX_NODES run inside one
+// CTA (phases separated by __syncthreads), replacing ~10 launches per level.
+// ---------------------------------------------------------------------------
+template <int BS>
+__device__ __forceinline__ void row_product_serial(const HemoCoarseLevel& L, const double* __restrict__ x, int i,
+                                                   double acc[BS]) {
+#pragma unroll
+    for (int k = 0; k < BS; ++k) acc[k] = 0.0;
+    for (int t = L.rowptr[i]; t < L.rowptr[i + 1]; ++t) {
+        const int j = L.col[t];
+#pragma unroll
+        for (int k = 0; k < BS; ++k)
+#pragma unroll
+            for (int l = 0; l < BS; ++l) acc[k] = fma(L.val[(int64_t)t * BS * BS + k * BS + l], x[(int64_t)j * BS + l], acc[k]);
+    }
+}
+
+template <int BS>
+__device__ void fused_smooth(const HemoCoarseLevel& L, const double* __restrict__ b, double* __restrict__ x,
+                             bool x_is_zero, int degree, double ratio) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int N = L.n * BS;
+    const double lmax = *L.lmax, lmin = lmax / ratio;
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+    double rho = 1.0 / sigma;
+    double* dold = L.d0;
+    double* dnew = L.d1;
+    if (x_is_zero) {
+        for (int q = tid; q < N; q += T) {
+            const double rv = L.dinv[q] * b[q];
+            L.r[q] = rv;
+            dold[q] = rv / theta;
+            x[q] = rv / theta;
+        }
+    } else {
+        for (int i = tid; i < L.n; i += T) {
+            double acc[BS];
+            row_product_serial<BS>(L, x, i, acc);
+#pragma unroll
+            for (int k = 0; k < BS; ++k) {
+                const int q = i * BS + k;
+                const double rv = L.dinv[q] * (b[q] - acc[k]);
+                L.r[q] = rv;
+                dold[q] = rv / theta;
+            }
+        }
+    }
+    __syncthreads();
+    bool pending = !x_is_zero;
+    for (int s = 1; s < degree; ++s) {
+        const double rho_new = 1.0 / (2.0 * sigma - rho);
+        const double c1 = rho_new * rho, c2 = 2.0 * rho_new / delta;
+        for (int i = tid; i < L.n; i += T) {
+            double acc[BS];
+            row_product_serial<BS>(L, dold, i, acc);
+#pragma unroll
+            for (int k = 0; k < BS; ++k) {
+                const int q = i * BS + k;
+                const double rv = L.r[q] - L.dinv[q] * acc[k];
+                L.r[q] = rv;
+                const double dv = c1 * dold[q] + c2 * rv;
+                dnew[q] = dv;
+                x[q] += pending ? (dv + dold[q]) : dv;
+            }
+        }
+        __syncthreads();
+        pending = false;
+        double* t = dold; dold = dnew; dnew = t;
+        rho = rho_new;
+    }
+    if (pending) {
+        for (int q = tid; q < N; q += T) x[q] += dold[q];
+        __syncthreads();
+    }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(1024)
+k_coarse_vcycle(const HemoCoarseLevel* __restrict__ desc, int nl, const double* __restrict__ b0, double* __restrict__ x0,
+                int degree, double ratio, const double* __restrict__ dense_inv, int dense_n) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    // down sweep
+    for (int l = 0; l + 1 < nl; ++l) {
+        const HemoCoarseLevel L = desc[l];
+        const double* b = (l == 0) ? b0 : L.b;
+        double* x = (l == 0) ? x0 : L.x;
+        fused_smooth<BS>(L, b, x, true, degree, ratio);
+        for (int i = tid; i < L.n; i += T) {
+            double acc[BS];
+            row_product_serial<BS>(L, x, i, acc);
+#pragma unroll
+            for (int k = 0; k < BS; ++k) L.r[i * BS + k] = b[i * BS + k] - acc[k];
+        }
+        __syncthreads();
+        double* bc = desc[l + 1].b;
+        for (int I = tid; I < L.nc; I += T) {
+            double acc[BS];
+#pragma unroll
+            for (int k = 0; k < BS; ++k) acc[k] = 0.0;
+            for (int t = L.r_rowptr[I]; t < L.r_rowptr[I + 1]; ++t) {
+                const int j = L.r_col[t];
+                const double w = L.r_val[t];
+#pragma unroll
+                for (int k = 0; k < BS; ++k) acc[k] = fma(w, L.r[j * BS + k], acc[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < BS; ++k) bc[I * BS + k] = acc[k];
+        }
+        __syncthreads();
+    }
+    // coarsest: dense inverse
+    {
+        const double* b = (nl == 1) ? b0 : desc[nl - 1].b;
+        double* x = (nl == 1) ? x0 : desc[nl - 1].x;
+        for (int row = tid; row < dense_n; row += T) {
+            double acc = 0.0;
+            for (int c = 0; c < dense_n; ++c) acc = fma(dense_inv[(int64_t)row * dense_n + c], b[c], acc);
+            x[row] = acc;
+        }
+        __syncthreads();
+    }
+    // up sweep
+    for (int l = nl - 2; l >= 0; --l) {
+        const HemoCoarseLevel L = desc[l];
+        const double* b = (l == 0) ? b0 : L.b;
+        double* x = (l == 0) ? x0 : L.x;
+        const double* xc = desc[l + 1].x;
+        for (int i = tid; i < L.n; i += T) {
+            double acc[BS];
+#pragma unroll
+            for (int k = 0; k < BS; ++k) acc[k] = 0.0;
+            for (int t = L.p_rowptr[i]; t < L.p_rowptr[i + 1]; ++t) {
+                const int j = L.p_col[t];
+                const double w = L.p_val[t];
+#pragma unroll
+                for (int k = 0; k < BS; ++k) acc[k] = fma(w, xc[j * BS + k], acc[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < BS; ++k) x[i * BS + k] += acc[k];
+        }
+        __syncthreads();
+        fused_smooth<BS>(L, b, x, false, degree, ratio);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // dense coarsest-level solve: explicit inverse by Gauss–Jordan with partial
 // pivoting, one CTA (N <= HEMO_DENSE_MAX)
 // ---------------------------------------------------------------------------
@@ -353,7 +509,8 @@ void hemo_amg_free(HemoAmg* amg) {
         cudaFree(o.val); cudaFree(o.dinv); cudaFree(o.x); cudaFree(o.b); cudaFree(o.r); cudaFree(o.d);
         o = HemoAmgOp();
     }
-    cudaFree(amg->dense_inv); cudaFree(amg->dense_work);
+    cudaFree(amg->dense_inv); cudaFree(amg->dense_work); cudaFree(amg->fuse_desc); cudaFree(amg->lmax_dev);
+    amg->fuse_desc = nullptr; amg->lmax_dev = nullptr; amg->fuse_level = -1;
     amg->dense_inv = amg->dense_work = nullptr;
     amg->nlev = 0;
     amg->ready = false;
@@ -426,6 +583,32 @@ extern "C" int hemo_amg_finalize(hemo_ctx* ctx, int which, int n_levels) {
     if ((rc = hemo_alloc(ctx, &amg.dense_inv, (size_t)Nc * Nc))) return rc;
     if ((rc = hemo_alloc(ctx, &amg.dense_work, (size_t)Nc * Nc + 8))) return rc;
     if ((rc = hemo_ensure_reduce(ctx, (size_t)hemo_grid(ctx->n, 256) + 1184 * 8, 512))) return rc;
+    if ((rc = hemo_alloc(ctx, &amg.lmax_dev, (size_t)HEMO_MAX_LEVELS))) return rc;
+    // levels small enough for the single-CTA fused cycle
+    amg.fuse_level = -1;
+    for (int l = 0; l < n_levels; ++l)
+        if (amg.op[l].n <= HEMO_FUSE_MAX_NODES) { amg.fuse_level = l; break; }
+    if (amg.fuse_level >= 0) {
+        std::vector<HemoCoarseLevel> d;
+        for (int l = amg.fuse_level; l < n_levels; ++l) {
+            const HemoAmgOp& o = amg.op[l];
+            HemoCoarseLevel c{};
+            c.n = o.n; c.rowptr = o.rowptr; c.col = o.col; c.val = o.val; c.dinv = o.dinv;
+            c.x = o.x; c.b = o.b; c.r = o.r; c.d0 = o.d; c.d1 = o.d + (size_t)o.n * bs;
+            c.lmax = amg.lmax_dev + l;
+            if (l + 1 < n_levels) {
+                const HemoAmgLevel& L = amg.lev[l];
+                c.nc = L.n_coarse;
+                c.p_rowptr = L.p_rowptr; c.p_col = L.p_col; c.p_val = L.p_val;
+                c.r_rowptr = L.r_rowptr; c.r_col = L.r_col; c.r_val = L.r_val;
+            }
+            d.push_back(c);
+        }
+        if ((rc = hemo_alloc(ctx, &amg.fuse_desc, d.size()))) return rc;
+        HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(amg.fuse_desc, d.data(), sizeof(HemoCoarseLevel) * d.size(),
+                                             cudaMemcpyHostToDevice, ctx->stream));
+        HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     amg.ready = true;
     return 0;
 }
@@ -437,7 +620,7 @@ static int amg_numeric_t(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift) {
         const HemoAmgOp& A = amg->op[l];
         HemoAmgOp& C = amg->op[l + 1];
         const HemoAmgLevel& L = amg->lev[l];
-        k_numeric_ap<BS><<<hemo_grid(A.n, 128), 128, 0, st>>>(A.n, A.rowptr, A.col, A.val, L.p_rowptr, L.p_col, L.p_val,
+        k_numeric_ap<BS><<<hemo_grid((int64_t)A.n * 8, 256), 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, L.p_rowptr, L.p_col, L.p_val,
                                                               L.ap_rowptr, L.ap_col, L.ap_val);
         HEMO_LAUNCH_CHECK(ctx);
         if (l == 0) HEMO_PROF_BEGIN(ctx, HEMO_PROF_RAP);
@@ -452,11 +635,11 @@ static int amg_numeric_t(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift) {
         const int g = hemo_grid(A.n, 256);
         k_diag_bound<BS><<<g, 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, A.dinv, ctx->red_partial);
         HEMO_LAUNCH_CHECK(ctx);
-        k_max_final<<<1, 256, 0, st>>>(g, ctx->red_partial, ctx->red_out + 64 + l);
+        k_max_final<<<1, 256, 0, st>>>(g, ctx->red_partial, amg->lmax_dev + l);
         HEMO_LAUNCH_CHECK(ctx);
     }
     if (amg->nlev > 1) {
-        HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->red_host + 64, ctx->red_out + 64, sizeof(double) * (amg->nlev - 1),
+        HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->red_host + 64, amg->lmax_dev, sizeof(double) * (amg->nlev - 1),
                                              cudaMemcpyDeviceToHost, st));
     }
     // dense inverse of the coarsest operator
@@ -535,6 +718,13 @@ static int vcycle_t(hemo_ctx* ctx, HemoAmg* amg, int l, const double* b, double*
     const HemoAmgOp& A = amg->op[l];
     const int degree = ctx->opts.cheb_degree > 0 ? ctx->opts.cheb_degree : 2;
     const double ratio = ctx->opts.cheb_ratio > 1.0 ? ctx->opts.cheb_ratio : 4.0;
+    if (l == amg->fuse_level) {
+        // every remaining level fits one CTA
+        k_coarse_vcycle<BS><<<1, 1024, 0, st>>>(amg->fuse_desc, amg->nlev - l, b, x, degree, ratio, amg->dense_inv,
+                                                amg->dense_n);
+        HEMO_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     if (l == amg->nlev - 1) {
         const int N = amg->dense_n;
         // exact solve: any previous iterate is simply replaced

@@ -57,7 +57,23 @@ struct HemoAmgLevel {
     int64_t nnz_p = 0, nnz_ap = 0, nnz_c = 0;
 };
 
+// device-visible descriptor of one level for the fused coarse V-cycle kernel
+struct HemoCoarseLevel {
+    int n, nc;
+    const int32_t *rowptr, *col;
+    const double *val, *dinv;
+    double *x, *b, *r, *d0, *d1;
+    const int32_t *p_rowptr, *p_col; const double* p_val;
+    const int32_t *r_rowptr, *r_col; const double* r_val;
+    const double* lmax;
+};
+
+#define HEMO_FUSE_MAX_NODES 256    // levels at or below this size run inside one CTA
+
 struct HemoAmg {
+    int fuse_level = -1;           // first level handled by the fused kernel (-1: none)
+    HemoCoarseLevel* fuse_desc = nullptr;   // device array, one per level from fuse_level
+    double* lmax_dev = nullptr;    // HEMO_MAX_LEVELS Gershgorin bounds kept on the device
     int bs = 1;
     int nlev = 0;              // number of operators (levels); nlev-1 transfer levels
     bool ready = false;
@@ -131,6 +147,14 @@ struct hemo_ctx {
     double schur_mass_coef = 0.0, schur_lap_coef = 0.0;
     HemoAmg amg[2];
     const double* mass = nullptr;   // lumped pressure mass (borrowed, n)
+    // CUDA graph of one preconditioner application (captured per hemo_pc_setup)
+    cudaGraph_t pc_graph = nullptr;
+    cudaGraphExec_t pc_graph_exec = nullptr;
+    int64_t pc_graph_nodes = 0;
+    bool capturing = false;
+    int use_graph = 1;
+    double* pc_in = nullptr;        // 3n (padded) staging of the graph's input / output
+    double* pc_out = nullptr;
     double* pc_tmp_u = nullptr;     // 2n
     double* pc_tmp_u2 = nullptr;    // 2n
     double* pc_tmp_p = nullptr;     // n
@@ -168,7 +192,7 @@ struct hemo_ctx {
     } while (0)
 
 static inline void hemo_prof_mark(hemo_ctx* ctx, int cls) {
-    if (!ctx->prof.on) return;
+    if (!ctx->prof.on || ctx->capturing) return;
     HemoProf& p = ctx->prof;
     if (p.used[cls] == p.ev[cls].size()) {
         cudaEvent_t e;

@@ -66,9 +66,17 @@ __global__ void k_schur_combine(int n, double cm, double cl, const double* __res
     zp[i] = v;
 }
 
+static int pc_build_graph(hemo_ctx* ctx, const double* vals_dev);
+
 extern "C" int hemo_remove_mean_vec(hemo_ctx* ctx, int64_t n, double* x_dev) {
     if (!ctx || !x_dev || n <= 0) return HEMO_EINVAL;
     return hemo_remove_mean(ctx, n, x_dev);
+}
+
+extern "C" int hemo_use_graph(hemo_ctx* ctx, int on) {
+    if (!ctx) return HEMO_EINVAL;
+    ctx->use_graph = on != 0;
+    return 0;
 }
 
 extern "C" int hemo_set_solver_opts(hemo_ctx* ctx, const hemo_solver_opts* o) {
@@ -90,6 +98,8 @@ extern "C" int hemo_pc_setup(hemo_ctx* ctx, const double* vals_dev, const double
         if ((rc = hemo_alloc(ctx, &ctx->pc_tmp_u2, (size_t)2 * n))) return rc;
         if ((rc = hemo_alloc(ctx, &ctx->pc_tmp_p, (size_t)n))) return rc;
         if ((rc = hemo_alloc(ctx, &ctx->pc_tmp_p2, (size_t)n))) return rc;
+        if ((rc = hemo_alloc(ctx, &ctx->pc_in, (size_t)3 * n + 32))) return rc;
+        if ((rc = hemo_alloc(ctx, &ctx->pc_out, (size_t)3 * n + 32))) return rc;
     }
     k_extract_a00<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(ctx->nnz_node, ctx->nrowptr, ctx->rowof, vals_dev,
                                                                  ctx->amg[0].op[0].val);
@@ -105,7 +115,7 @@ extern "C" int hemo_pc_setup(hemo_ctx* ctx, const double* vals_dev, const double
         if ((rc = hemo_amg_numeric_shift(ctx, &ctx->amg[1], ctx->opts.project_pressure ? 1e-8 : 0.0))) return rc;
     }
     if (!ctx->mass) HEMO_FAIL(ctx, HEMO_ESTATE, "first hemo_pc_setup call needs lap_vals and mass");
-    return 0;
+    return pc_build_graph(ctx, vals_dev);
 }
 
 extern "C" int hemo_amg_apply(hemo_ctx* ctx, int which, const double* b_dev, double* x_dev, int ncycles) {
@@ -124,9 +134,7 @@ extern "C" int hemo_amg_get_level_values(hemo_ctx* ctx, int which, int level, do
     return 0;
 }
 
-extern "C" int hemo_pc_apply(hemo_ctx* ctx, const double* vals_dev, const double* r_dev, double* z_dev) {
-    if (!ctx || !vals_dev || !r_dev || !z_dev) return HEMO_EINVAL;
-    if (!ctx->mass || !ctx->pc_tmp_u) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_pc_setup not called");
+static int pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_dev, double* z_dev) {
     const int n = ctx->n;
     cudaStream_t st = ctx->stream;
     const double* ru = r_dev;
@@ -148,6 +156,64 @@ extern "C" int hemo_pc_apply(hemo_ctx* ctx, const double* vals_dev, const double
     if ((rc = hemo_spmv_block(ctx, 1, 2, vals_dev, nullptr, zp, -1.0, ru, nullptr, tu, nullptr))) return rc;
     if ((rc = hemo_amg_vcycle(ctx, &ctx->amg[0], tu, zu, ctx->opts.amg_cycles_u))) return rc;
     return 0;
+}
+
+// (Re)capture the preconditioner application as a CUDA graph on ctx->stream:
+// ~100 small kernels per application replay with one launch.  Needs a
+// non-default stream; on the legacy default stream the direct path is used.
+static int pc_build_graph(hemo_ctx* ctx, const double* vals_dev) {
+    if (!ctx->use_graph || ctx->stream == 0) return 0;
+    cudaStream_t st = ctx->stream;
+    int rc = hemo_ensure_reduce(ctx, (size_t)1184 * 8, 512);   // no allocation may happen while capturing
+    if (rc) return rc;
+    HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    const int64_t before = ctx->launches;
+    ctx->capturing = true;
+    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) {
+        ctx->capturing = false;
+        cudaGetLastError();
+        ctx->use_graph = 0;            // capture unsupported here: fall back to direct launches
+        return 0;
+    }
+    rc = pc_apply_body(ctx, vals_dev, ctx->pc_in, ctx->pc_out);
+    cudaGraph_t g = nullptr;
+    e = cudaStreamEndCapture(st, &g);
+    ctx->capturing = false;
+    ctx->pc_graph_nodes = ctx->launches - before;
+    ctx->launches = before;
+    if (rc != 0 || e != cudaSuccess || !g) {
+        cudaGetLastError();
+        if (g) cudaGraphDestroy(g);
+        ctx->use_graph = 0;
+        if (rc) return rc;
+        return 0;
+    }
+    bool updated = false;
+    if (ctx->pc_graph_exec) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(ctx->pc_graph_exec, g, &info) == cudaSuccess) updated = true;
+        else { cudaGetLastError(); cudaGraphExecDestroy(ctx->pc_graph_exec); ctx->pc_graph_exec = nullptr; }
+    }
+    if (!updated) HEMO_CHECK_CUDA(ctx, cudaGraphInstantiate(&ctx->pc_graph_exec, g, 0));
+    if (ctx->pc_graph) cudaGraphDestroy(ctx->pc_graph);
+    ctx->pc_graph = g;
+    return 0;
+}
+
+extern "C" int hemo_pc_apply(hemo_ctx* ctx, const double* vals_dev, const double* r_dev, double* z_dev) {
+    if (!ctx || !vals_dev || !r_dev || !z_dev) return HEMO_EINVAL;
+    if (!ctx->mass || !ctx->pc_tmp_u) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_pc_setup not called");
+    if (ctx->use_graph && ctx->pc_graph_exec) {
+        const size_t bytes = sizeof(double) * 3 * (size_t)ctx->n;
+        cudaStream_t st = ctx->stream;
+        HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->pc_in, r_dev, bytes, cudaMemcpyDeviceToDevice, st));
+        HEMO_CHECK_CUDA(ctx, cudaGraphLaunch(ctx->pc_graph_exec, st));
+        HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(z_dev, ctx->pc_out, bytes, cudaMemcpyDeviceToDevice, st));
+        ctx->launches += ctx->pc_graph_nodes;
+        return 0;
+    }
+    return pc_apply_body(ctx, vals_dev, r_dev, z_dev);
 }
 
 static int ensure_krylov(hemo_ctx* ctx, int restart, int64_t ldv) {
@@ -293,6 +359,9 @@ extern "C" int hemo_ctx_destroy(hemo_ctx* ctx) {
     cudaFree(ctx->red_partial); cudaFree(ctx->red_out);
     if (ctx->red_host) cudaFreeHost(ctx->red_host);
     hemo_amg_free(&ctx->amg[0]); hemo_amg_free(&ctx->amg[1]);
+    if (ctx->pc_graph_exec) cudaGraphExecDestroy(ctx->pc_graph_exec);
+    if (ctx->pc_graph) cudaGraphDestroy(ctx->pc_graph);
+    cudaFree(ctx->pc_in); cudaFree(ctx->pc_out);
     cudaFree(ctx->pc_tmp_u); cudaFree(ctx->pc_tmp_u2); cudaFree(ctx->pc_tmp_p); cudaFree(ctx->pc_tmp_p2);
     cudaFree(ctx->kry_V); cudaFree(ctx->kry_Z); cudaFree(ctx->kry_w);
     delete ctx;

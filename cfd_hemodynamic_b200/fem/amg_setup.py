@@ -62,9 +62,13 @@ def build_hierarchy(L: sp.csr_matrix, dirichlet: np.ndarray, *, max_coarse: int,
         nl = A.shape[0]
         if nl <= max_coarse:
             break
-        S = _strength(A, theta)
-        agg, na = _aggregate(S, excl)
-        if na == 0 or na >= 0.9 * nl:
+        # dense coarse operators lose "strong" couplings: relax the threshold before giving up
+        for th in (theta, 0.25 * theta, 0.0):
+            S = _strength(A, th)
+            agg, na = _aggregate(S, excl)
+            if 0 < na < 0.75 * nl:
+                break
+        else:
             raise RuntimeError(f"AMG coarsening stalled at level {lev}: {nl} -> {na}")
         rows = np.nonzero(agg >= 0)[0]
         T = sp.csr_matrix((np.ones(rows.shape[0]), (rows, agg[rows])), shape=(nl, na))

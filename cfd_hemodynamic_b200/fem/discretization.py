@@ -17,17 +17,13 @@ from .mesh import Mesh, exterior_facet_indices
 
 def node_graph(cells: np.ndarray, n_nodes: int):
     """Sorted CSR adjacency (diagonal included) of the P1 dof graph."""
-    c = cells.astype(np.int64)
+    c = cells.astype(np.int32)
     nv = c.shape[1]
     rows = np.repeat(c, nv, axis=1).reshape(-1)
     cols = np.tile(c, (1, nv)).reshape(-1)
-    key = np.unique(rows * np.int64(n_nodes) + cols)
-    r = (key // n_nodes).astype(np.int64)
-    ncol = (key % n_nodes).astype(np.int32)
-    nrowptr = np.zeros(n_nodes + 1, dtype=np.int64)
-    nrowptr[1:] = np.bincount(r, minlength=n_nodes)
-    nrowptr = np.cumsum(nrowptr).astype(np.int32)
-    return nrowptr, ncol
+    A = sp.coo_matrix((np.ones(rows.shape[0], dtype=np.int8), (rows, cols)), shape=(n_nodes, n_nodes)).tocsr()
+    A.sort_indices()
+    return A.indptr.astype(np.int32), A.indices.astype(np.int32)
 
 
 def facet_set_by_cell(mesh: Mesh, facets: np.ndarray):

@@ -194,6 +194,9 @@ int hemo_amg_apply(hemo_ctx* ctx, int which, const double* b_dev, double* x_dev,
 /* Level operator of hierarchy `which` after hemo_pc_setup (device copy out;
  * nnzb*bs*bs doubles).  Exposed for the Galerkin-product parity test. */
 int hemo_amg_get_level_values(hemo_ctx* ctx, int which, int level, double* vals_dev, int64_t capacity);
+/* 1 (default): hemo_pc_setup captures one preconditioner application as a CUDA
+ * graph (needs a non-default stream) and hemo_pc_apply replays it; 0: direct launches. */
+int hemo_use_graph(hemo_ctx* ctx, int on);
 /* z = M^{-1} r (one application of the block preconditioner). */
 int hemo_pc_apply(hemo_ctx* ctx, const double* vals_dev, const double* r_dev, double* z_dev);
 /* KSPSolve: right-preconditioned FGMRES(restart) on J y = b with zero initial
