@@ -142,6 +142,8 @@ class Hemo:
             self.stream = torch.cuda.current_stream(self.device)
         self.lib.hemo_set_stream(self._ctx, C.c_void_p(self.stream.cuda_stream))
         self._keep = {}     # borrowed tensors must outlive the context
+        if os.environ.get("HEMO_NO_GRAPH"):
+            self.lib.hemo_use_graph(self._ctx, 0)
 
     def close(self):
         if self._ctx:

@@ -10,6 +10,8 @@
 // mesh graph and are built once by the host; what runs here every Newton
 // iteration is the numeric Galerkin product R*A*P on fixed patterns, the
 // smoother set-up, and the cycles.
+#include <cub/device/device_scan.cuh>
+
 #include "hemo_internal.cuh"
 
 int hemo_bsr_spmv_ex(hemo_ctx* ctx, int bs, int n, const int32_t* rowptr, const int32_t* col, const double* val,
@@ -106,6 +108,117 @@ k_numeric_rap(int nc, const int32_t* __restrict__ r_rowptr, const int32_t* __res
             for (int k = 0; k < BS * BS; ++k) c_val[(int64_t)s * BS * BS + k] = acc[k];
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// Galerkin product through precomputed gather lists (hierarchy 0, rebuilt every
+// Newton iteration): one thread per output block, contributions summed in a
+// fixed order, no searches at run time.  The lists are built once on the device.
+// ---------------------------------------------------------------------------
+// count / fill pass over "rows x inner entries x outer entries":
+//   AP:  row i,  t in A-row(i),  u in P-row(a_col[t])  -> slot of p_col[u] in AP-row(i);  src = (u, t)
+//   RAP: row I,  t in R-row(I),  u in AP-row(r_col[t]) -> slot of ap_col[u] in C-row(I);  src = (t, u)
+template <bool FILL, bool SWAP>
+__global__ void k_product_lists(int nrows, const int32_t* __restrict__ a_rowptr, const int32_t* __restrict__ a_col,
+                                const int32_t* __restrict__ b_rowptr, const int32_t* __restrict__ b_col,
+                                const int32_t* __restrict__ o_rowptr, const int32_t* __restrict__ o_col,
+                                int32_t* __restrict__ count, const int32_t* __restrict__ seg_ptr,
+                                int2* __restrict__ seg_src, int* __restrict__ bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    const int o0 = o_rowptr[i], o1 = o_rowptr[i + 1];
+    for (int t = a_rowptr[i]; t < a_rowptr[i + 1]; ++t) {
+        const int j = a_col[t];
+        for (int u = b_rowptr[j]; u < b_rowptr[j + 1]; ++u) {
+            const int pos = find_col(o_col, o0, o1, b_col[u]);
+            if (pos < 0) { atomicExch(bad, 1); continue; }
+            const int k = atomicAdd(&count[pos], 1);
+            if (FILL) seg_src[seg_ptr[pos] + k] = SWAP ? make_int2(u, t) : make_int2(t, u);
+        }
+    }
+}
+
+__global__ void k_sort_pairs(int64_t nseg, const int32_t* __restrict__ ptr, int2* __restrict__ src) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    const int b0 = ptr[s], b1 = ptr[s + 1];
+    for (int i = b0 + 1; i < b1; ++i) {
+        const int2 key = src[i];
+        int j = i - 1;
+        while (j >= b0 && (src[j].y > key.y || (src[j].y == key.y && src[j].x > key.x))) { src[j + 1] = src[j]; --j; }
+        src[j + 1] = key;
+    }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(256)
+k_gather_product(int64_t nseg, const int32_t* __restrict__ seg_ptr, const int2* __restrict__ seg_src,
+                 const double* __restrict__ w, const double* __restrict__ blk, double* __restrict__ out) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    double acc[BS * BS];
+#pragma unroll
+    for (int k = 0; k < BS * BS; ++k) acc[k] = 0.0;
+    const int b1 = seg_ptr[s + 1];
+    for (int q = seg_ptr[s]; q < b1; ++q) {
+        const int2 src = seg_src[q];
+        const double wt = w[src.x];
+        if (BS == 2) {
+            const double2 v0 = reinterpret_cast<const double2*>(blk)[2 * (int64_t)src.y];
+            const double2 v1 = reinterpret_cast<const double2*>(blk)[2 * (int64_t)src.y + 1];
+            acc[0] = fma(wt, v0.x, acc[0]); acc[1] = fma(wt, v0.y, acc[1]);
+            acc[BS * BS - 2] = fma(wt, v1.x, acc[BS * BS - 2]); acc[BS * BS - 1] = fma(wt, v1.y, acc[BS * BS - 1]);
+        } else {
+            acc[0] = fma(wt, blk[src.y], acc[0]);
+        }
+    }
+    if (BS == 2) {
+        reinterpret_cast<double2*>(out)[2 * s] = make_double2(acc[0], acc[1]);
+        reinterpret_cast<double2*>(out)[2 * s + 1] = make_double2(acc[BS * BS - 2], acc[BS * BS - 1]);
+    } else {
+        out[s] = acc[0];
+    }
+}
+
+static int build_one_list(hemo_ctx* ctx, bool swap, int nrows, const int32_t* a_rowptr, const int32_t* a_col,
+                          const int32_t* b_rowptr, const int32_t* b_col, const int32_t* o_rowptr, const int32_t* o_col,
+                          int64_t nseg, int32_t** seg_ptr, int2** seg_src) {
+    cudaStream_t st = ctx->stream;
+    int rc;
+    int32_t* count = nullptr;
+    int* bad = nullptr;
+    if ((rc = hemo_alloc(ctx, &count, (size_t)nseg + 1))) return rc;
+    if ((rc = hemo_alloc(ctx, &bad, 1))) return rc;
+    if ((rc = hemo_alloc(ctx, seg_ptr, (size_t)nseg + 1))) return rc;
+    HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int32_t) * (nseg + 1), st));
+    HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(bad, 0, sizeof(int), st));
+    const int g = hemo_grid(nrows, 128);
+    if (swap) k_product_lists<false, true><<<g, 128, 0, st>>>(nrows, a_rowptr, a_col, b_rowptr, b_col, o_rowptr, o_col, count, nullptr, nullptr, bad);
+    else k_product_lists<false, false><<<g, 128, 0, st>>>(nrows, a_rowptr, a_col, b_rowptr, b_col, o_rowptr, o_col, count, nullptr, nullptr, bad);
+    HEMO_LAUNCH_CHECK(ctx);
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, count, *seg_ptr, (int)(nseg + 1), st);
+    HEMO_CHECK_CUDA(ctx, cudaMalloc(&tmp, tmp_bytes));
+    HEMO_CHECK_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, count, *seg_ptr, (int)(nseg + 1), st));
+    int32_t total = 0;
+    HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(&total, *seg_ptr + nseg, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaFree(tmp);
+    if (total < 0) { cudaFree(count); cudaFree(bad); HEMO_FAIL(ctx, HEMO_EINVAL, "Galerkin gather list exceeds int32"); }
+    if ((rc = hemo_alloc(ctx, seg_src, (size_t)total))) return rc;
+    HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int32_t) * (nseg + 1), st));
+    if (swap) k_product_lists<true, true><<<g, 128, 0, st>>>(nrows, a_rowptr, a_col, b_rowptr, b_col, o_rowptr, o_col, count, *seg_ptr, *seg_src, bad);
+    else k_product_lists<true, false><<<g, 128, 0, st>>>(nrows, a_rowptr, a_col, b_rowptr, b_col, o_rowptr, o_col, count, *seg_ptr, *seg_src, bad);
+    HEMO_LAUNCH_CHECK(ctx);
+    k_sort_pairs<<<hemo_grid(nseg, 256), 256, 0, st>>>(nseg, *seg_ptr, *seg_src);
+    HEMO_LAUNCH_CHECK(ctx);
+    int bad_h = 0;
+    HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(&bad_h, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaFree(count); cudaFree(bad);
+    if (bad_h) HEMO_FAIL(ctx, HEMO_EINVAL, "AMG product pattern does not cover the product");
+    return 0;
 }
 
 // inverse diagonal and Gershgorin bound of D^-1 A (per-block max)
@@ -499,6 +612,7 @@ static void free_level(HemoAmgLevel& L) {
     cudaFree(L.r_rowptr); cudaFree(L.r_col); cudaFree(L.r_val);
     cudaFree(L.ap_rowptr); cudaFree(L.ap_col); cudaFree(L.ap_val);
     cudaFree(L.c_rowptr); cudaFree(L.c_col);
+    cudaFree(L.ap_seg_ptr); cudaFree(L.ap_seg_src); cudaFree(L.c_seg_ptr); cudaFree(L.c_seg_src);
     L = HemoAmgLevel();
 }
 
@@ -584,6 +698,17 @@ extern "C" int hemo_amg_finalize(hemo_ctx* ctx, int which, int n_levels) {
     if ((rc = hemo_alloc(ctx, &amg.dense_work, (size_t)Nc * Nc + 8))) return rc;
     if ((rc = hemo_ensure_reduce(ctx, (size_t)hemo_grid(ctx->n, 256) + 1184 * 8, 512))) return rc;
     if ((rc = hemo_alloc(ctx, &amg.lmax_dev, (size_t)HEMO_MAX_LEVELS))) return rc;
+    if (which == 0) {
+        // the velocity hierarchy is re-formed every Newton iteration: precompute its gather lists
+        for (int l = 0; l + 1 < n_levels; ++l) {
+            HemoAmgLevel& L = amg.lev[l];
+            const HemoAmgOp& A = amg.op[l];
+            if ((rc = build_one_list(ctx, true, A.n, A.rowptr, A.col, L.p_rowptr, L.p_col, L.ap_rowptr, L.ap_col,
+                                     L.nnz_ap, &L.ap_seg_ptr, &L.ap_seg_src))) return rc;
+            if ((rc = build_one_list(ctx, false, L.n_coarse, L.r_rowptr, L.r_col, L.ap_rowptr, L.ap_col, L.c_rowptr,
+                                     L.c_col, L.nnz_c, &L.c_seg_ptr, &L.c_seg_src))) return rc;
+        }
+    }
     // levels small enough for the single-CTA fused cycle
     amg.fuse_level = -1;
     for (int l = 0; l < n_levels; ++l)
@@ -620,13 +745,22 @@ static int amg_numeric_t(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift) {
         const HemoAmgOp& A = amg->op[l];
         HemoAmgOp& C = amg->op[l + 1];
         const HemoAmgLevel& L = amg->lev[l];
-        k_numeric_ap<BS><<<hemo_grid((int64_t)A.n * 8, 256), 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, L.p_rowptr, L.p_col, L.p_val,
-                                                              L.ap_rowptr, L.ap_col, L.ap_val);
-        HEMO_LAUNCH_CHECK(ctx);
         if (l == 0) HEMO_PROF_BEGIN(ctx, HEMO_PROF_RAP);
-        k_numeric_rap<BS><<<hemo_grid((int64_t)C.n * 32, 256), 256, 0, st>>>(C.n, L.r_rowptr, L.r_col, L.r_val, L.ap_rowptr, L.ap_col,
-                                                               L.ap_val, L.c_rowptr, L.c_col, C.val);
-        HEMO_LAUNCH_CHECK(ctx);
+        if (L.ap_seg_ptr && L.c_seg_ptr) {
+            k_gather_product<BS><<<hemo_grid(L.nnz_ap, 256), 256, 0, st>>>(L.nnz_ap, L.ap_seg_ptr, L.ap_seg_src, L.p_val,
+                                                                            A.val, L.ap_val);
+            HEMO_LAUNCH_CHECK(ctx);
+            k_gather_product<BS><<<hemo_grid(L.nnz_c, 256), 256, 0, st>>>(L.nnz_c, L.c_seg_ptr, L.c_seg_src, L.r_val,
+                                                                           L.ap_val, C.val);
+            HEMO_LAUNCH_CHECK(ctx);
+        } else {
+            k_numeric_ap<BS><<<hemo_grid((int64_t)A.n * 8, 256), 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, L.p_rowptr, L.p_col,
+                                                                              L.p_val, L.ap_rowptr, L.ap_col, L.ap_val);
+            HEMO_LAUNCH_CHECK(ctx);
+            k_numeric_rap<BS><<<hemo_grid((int64_t)C.n * 32, 256), 256, 0, st>>>(C.n, L.r_rowptr, L.r_col, L.r_val, L.ap_rowptr,
+                                                                                L.ap_col, L.ap_val, L.c_rowptr, L.c_col, C.val);
+            HEMO_LAUNCH_CHECK(ctx);
+        }
         if (l == 0) HEMO_PROF_END(ctx, HEMO_PROF_RAP);
     }
     // smoother data; bounds are read back in one copy

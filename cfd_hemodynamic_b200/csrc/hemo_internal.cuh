@@ -55,6 +55,10 @@ struct HemoAmgLevel {
     int32_t *ap_rowptr = nullptr, *ap_col = nullptr; double* ap_val = nullptr;
     int32_t *c_rowptr = nullptr, *c_col = nullptr;
     int64_t nnz_p = 0, nnz_ap = 0, nnz_c = 0;
+    // precomputed gather lists of the numeric Galerkin product (hierarchy 0 only):
+    // AP[s] = sum_k p_val[src.x] * A[src.y],  C[s] = sum_k r_val[src.x] * AP[src.y]
+    int32_t* ap_seg_ptr = nullptr; int2* ap_seg_src = nullptr;
+    int32_t* c_seg_ptr = nullptr;  int2* c_seg_src = nullptr;
 };
 
 // device-visible descriptor of one level for the fused coarse V-cycle kernel

@@ -59,6 +59,9 @@ class StabilizedSchurB200(SolverBase):
         self.ksp_max_it = int(kw.pop("ksp_max_it", 1000))
         self.ksp_restart = int(kw.pop("ksp_restart", 60))
         self.verbose = bool(kw.pop("verbose", False))
+        # "newton": PCSetUp for every Jacobian like the reference (SNES lag 1);
+        # "step": once per time step, later Newton iterations reuse the hierarchy
+        self.pc_rebuild = str(kw.pop("pc_rebuild", "step"))
         self._pc_kw = {k: kw.pop(k) for k in list(kw) if k in (
             "amg_cycles_u", "amg_cycles_p", "cheb_degree", "cheb_ratio", "smooth_prolongator",
             "strength_theta", "schur_mass_coef", "schur_lap_coef")}
@@ -239,7 +242,8 @@ class StabilizedSchurB200(SolverBase):
             return 0, 0, 2
         for it in range(self.snes_max_it):
             hemo.assemble_jacobian(x, self.d_un, self.d_vals)
-            self.linear.setup(self.d_vals)
+            if it == 0 or self.pc_rebuild == "newton":
+                self.linear.setup(self.d_vals)
             try:
                 kits, _ = self.linear.solve(self.d_vals, f, y)
             except HemoDiverged:
