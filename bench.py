@@ -185,7 +185,9 @@ def main():
     K = max(1, args.steps)
     w = WORKLOADS[args.workload]
 
-    sc = build_scenario(w, device=local_rank)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):       # stdout carries exactly one JSON line
+        sc = build_scenario(w, device=local_rank)
     s = sc.solver
     hemo = s.hemo
     ndof = s.N
@@ -222,6 +224,26 @@ def main():
     prof = {c: hemo.prof_get(c) for c in PROF_CLASSES}
     hemo.prof_enable(False)
     clocks = sampler.stop()
+    # The preconditioner replays as a CUDA graph, so its kernels carry no event pairs in the
+    # timed region above.  Two extra steps with direct launches (same kernels, same data) time
+    # them with the same CUDA-event mechanism; their share is scaled to the timed region.
+    hemo.use_graph(False)
+    s.step_device()
+    hemo.prof_enable(True)
+    g0 = torch.cuda.Event(enable_timing=True)
+    g1 = torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(2):
+        s.step_device()
+    g1.record()
+    torch.cuda.synchronize(dev)
+    ms_nograph = g0.elapsed_time(g1)
+    for c in (4, 5):
+        t, k = hemo.prof_get(c)
+        prof[c] = (t * (ms / ms_nograph) if ms_nograph > 0 else t, int(round(k * K / 2)))
+    hemo.prof_enable(False)
+    hemo.use_graph(True)
+    s.step_device()          # re-captures the graph
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -281,8 +303,14 @@ def main():
     dom = max((c for c in prof if prof[c][1] > 0 and alg_bytes[c]), key=lambda c: prof[c][0], default=0)
     dms, dcnt = prof[dom]
     achieved = alg_bytes[dom] / (dms / dcnt * 1e-3) / 1e9 if dcnt else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("workload") == args.workload:
+            traffic = tj.get("dram_bytes_per_launch", {}).get(PROF_CLASSES[dom])
     roofline = {"bound": "hbm", "kernel": PROF_CLASSES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
                 "launches_timed": dcnt, "avg_us": 1e3 * dms / max(dcnt, 1),
                 "share_of_step": dms / ms,
                 "other_kernels": {PROF_CLASSES[c]: {"ms_total": prof[c][0], "launches": prof[c][1],
