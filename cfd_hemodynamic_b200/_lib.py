@@ -78,6 +78,11 @@ SYMBOLS = {
     "hemo_amg_finalize": (_I, [_VP, _I, _I]),
     "hemo_host_aggregate": (_I, [_I, _VP, _VP, _VP, _VP, C.POINTER(_I)]),
     "hemo_set_solver_opts": (_I, [_VP, C.POINTER(SolverOpts)]),
+    "hemo_set_pc_mask": (_I, [_VP, _VP]),
+    "hemo_mask_nodes": (_I, [_VP, _VP, _VP]),
+    "hemo_vec_mdot": (_I, [_VP, _L, _I, _VP, _L, _VP, _VP]),
+    "hemo_vec_maxpy": (_I, [_VP, _L, _I, _VP, _L, _VP, _D, _VP, C.POINTER(_D)]),
+    "hemo_vec_scale": (_I, [_VP, _L, _D, _VP, _VP]),
     "hemo_use_graph": (_I, [_VP, _I]),
     "hemo_pc_setup": (_I, [_VP, _VP, _VP, _VP]),
     "hemo_amg_apply": (_I, [_VP, _I, _VP, _VP, _I]),
@@ -293,6 +298,28 @@ class Hemo:
     def set_solver_opts(self, **kw):
         o = SolverOpts(**kw)
         self._check(self.lib.hemo_set_solver_opts(self._ctx, C.byref(o)), "hemo_set_solver_opts")
+
+    # ---- multi-GPU building blocks ---------------------------------------------
+    def set_pc_mask(self, node_mask):
+        self._check(self.lib.hemo_set_pc_mask(self._ctx, _ptr(node_mask)), "hemo_set_pc_mask")
+
+    def mask_nodes(self, node_mask, x):
+        self._check(self.lib.hemo_mask_nodes(self._ctx, _ptr(node_mask), _ptr(x)), "hemo_mask_nodes")
+
+    def vec_mdot(self, V, ldv, k, w) -> np.ndarray:
+        h = np.empty(k, dtype=np.float64)
+        self._check(self.lib.hemo_vec_mdot(self._ctx, w.numel(), k, _ptr(V), ldv, _ptr(w), _np_ptr(h)), "hemo_vec_mdot")
+        return h
+
+    def vec_maxpy(self, V, ldv, coef: np.ndarray, sign, w, want_normsq=False):
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        out = C.c_double()
+        self._check(self.lib.hemo_vec_maxpy(self._ctx, w.numel(), len(coef), _ptr(V), ldv, _np_ptr(coef), float(sign),
+                                            _ptr(w), C.byref(out) if want_normsq else None), "hemo_vec_maxpy")
+        return out.value if want_normsq else None
+
+    def vec_scale(self, a, x, y):
+        self._check(self.lib.hemo_vec_scale(self._ctx, x.numel(), float(a), _ptr(x), _ptr(y)), "hemo_vec_scale")
 
     def use_graph(self, on: bool):
         self._check(self.lib.hemo_use_graph(self._ctx, int(on)), "hemo_use_graph")

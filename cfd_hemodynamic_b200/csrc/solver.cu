@@ -24,10 +24,20 @@ int hemo_amg_numeric_shift(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift);
 // A00 (2x2 node blocks) out of the monolithic CSR values
 __global__ void __launch_bounds__(256)
 k_extract_a00(int64_t nnz_node, const int32_t* __restrict__ nrowptr, const int32_t* __restrict__ rowof,
+              const int32_t* __restrict__ ncol, const uint8_t* __restrict__ mask,
               const double* __restrict__ vals, double* __restrict__ out) {
     const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nnz_node) return;
     const int i = rowof[s];
+    if (mask) {
+        const int j = ncol[s];
+        if (mask[i] || mask[j]) {      // ghost node of a partition: identity row/column in the local PC
+            const double d = (i == j) ? 1.0 : 0.0;
+            reinterpret_cast<double2*>(out)[2 * s] = make_double2(d, 0.0);
+            reinterpret_cast<double2*>(out)[2 * s + 1] = make_double2(0.0, d);
+            return;
+        }
+    }
     const int r0 = nrowptr[i];
     const int deg = nrowptr[i + 1] - r0;
     const int t = (int)(s - r0);
@@ -54,6 +64,13 @@ k_lap_with_bc(int n, int64_t nnz_node, const int32_t* __restrict__ rowof, const 
     out[s] = v;
 }
 
+// x[node*bs + k] = 0 on masked nodes
+__global__ void k_mask_nodes(int n, int bs, const uint8_t* __restrict__ mask, double* __restrict__ x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !mask[i]) return;
+    for (int k = 0; k < bs; ++k) x[(int64_t)i * bs + k] = 0.0;
+}
+
 // z_p = c_m t_p / mass + c_L q_p ; Dirichlet pressure dofs: z_p = r_p
 __global__ void k_schur_combine(int n, double cm, double cl, const double* __restrict__ tp,
                                 const double* __restrict__ mass, const double* __restrict__ qp,
@@ -71,6 +88,55 @@ static int pc_build_graph(hemo_ctx* ctx, const double* vals_dev);
 extern "C" int hemo_remove_mean_vec(hemo_ctx* ctx, int64_t n, double* x_dev) {
     if (!ctx || !x_dev || n <= 0) return HEMO_EINVAL;
     return hemo_remove_mean(ctx, n, x_dev);
+}
+
+extern "C" int hemo_set_pc_mask(hemo_ctx* ctx, const uint8_t* node_mask_dev) {
+    if (!ctx) return HEMO_EINVAL;
+    if (!ctx->cells) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_set_mesh must precede hemo_set_pc_mask");
+    if (!node_mask_dev) {
+        cudaFree(ctx->pc_mask);
+        ctx->pc_mask = nullptr;
+        return 0;
+    }
+    return hemo_upload(ctx, &ctx->pc_mask, node_mask_dev, (size_t)ctx->n, true);
+}
+
+extern "C" int hemo_mask_nodes(hemo_ctx* ctx, const uint8_t* node_mask_dev, double* x_dev) {
+    if (!ctx || !node_mask_dev || !x_dev) return HEMO_EINVAL;
+    const int n = ctx->n;
+    k_mask_nodes<<<hemo_grid(n, 256), 256, 0, ctx->stream>>>(n, 2, node_mask_dev, x_dev);
+    HEMO_LAUNCH_CHECK(ctx);
+    k_mask_nodes<<<hemo_grid(n, 256), 256, 0, ctx->stream>>>(n, 1, node_mask_dev, x_dev + 2 * (int64_t)n);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+extern "C" int hemo_vec_mdot(hemo_ctx* ctx, int64_t n, int k, const double* V_dev, int64_t ldv, const double* w_dev,
+                             double* h_host) {
+    if (!ctx || !V_dev || !w_dev || !h_host || k < 1 || k > 400 || n < 1) return HEMO_EINVAL;
+    return hemo_mdot(ctx, n, k, V_dev, ldv, w_dev, h_host);
+}
+
+extern "C" int hemo_vec_maxpy(hemo_ctx* ctx, int64_t n, int k, const double* V_dev, int64_t ldv,
+                              const double* coef_host, double sign, double* w_dev, double* normsq_host) {
+    if (!ctx || !V_dev || !w_dev || !coef_host || k < 1 || k > 400 || n < 1) return HEMO_EINVAL;
+    int rc = hemo_ensure_reduce(ctx, (size_t)1184 * 2, 512);
+    if (rc) return rc;
+    if (!ctx->kry_coef && (rc = hemo_alloc(ctx, &ctx->kry_coef, 512))) return rc;
+    for (int i = 0; i < k; ++i) ctx->red_host[i] = coef_host[i];
+    HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->kry_coef, ctx->red_host, sizeof(double) * k, cudaMemcpyHostToDevice,
+                                         ctx->stream));
+    double nrm = 0.0;
+    rc = hemo_maxpy(ctx, n, k, V_dev, ldv, ctx->kry_coef, sign, w_dev, normsq_host ? &nrm : nullptr);
+    if (rc) return rc;
+    if (normsq_host) *normsq_host = nrm * nrm;      // local ||w||^2, to be summed over ranks
+    else HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // red_host is reused by the next call
+    return 0;
+}
+
+extern "C" int hemo_vec_scale(hemo_ctx* ctx, int64_t n, double a, const double* x_dev, double* y_dev) {
+    if (!ctx || !x_dev || !y_dev || n < 1) return HEMO_EINVAL;
+    return hemo_scale_copy(ctx, n, a, x_dev, y_dev);
 }
 
 extern "C" int hemo_use_graph(hemo_ctx* ctx, int on) {
@@ -101,8 +167,8 @@ extern "C" int hemo_pc_setup(hemo_ctx* ctx, const double* vals_dev, const double
         if ((rc = hemo_alloc(ctx, &ctx->pc_in, (size_t)3 * n + 32))) return rc;
         if ((rc = hemo_alloc(ctx, &ctx->pc_out, (size_t)3 * n + 32))) return rc;
     }
-    k_extract_a00<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(ctx->nnz_node, ctx->nrowptr, ctx->rowof, vals_dev,
-                                                                 ctx->amg[0].op[0].val);
+    k_extract_a00<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(ctx->nnz_node, ctx->nrowptr, ctx->rowof, ctx->ncol,
+                                                                 ctx->pc_mask, vals_dev, ctx->amg[0].op[0].val);
     HEMO_LAUNCH_CHECK(ctx);
     if ((rc = hemo_amg_numeric_shift(ctx, &ctx->amg[0], 0.0))) return rc;
     if (lap_vals_dev) {
@@ -146,6 +212,10 @@ static int pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_
     double* tu = ctx->pc_tmp_u;
     int rc;
     HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(tp, rp, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    if (ctx->pc_mask) {
+        k_mask_nodes<<<hemo_grid(n, 256), 256, 0, st>>>(n, 1, ctx->pc_mask, tp);
+        HEMO_LAUNCH_CHECK(ctx);
+    }
     if (ctx->opts.project_pressure && (rc = hemo_remove_mean(ctx, n, tp))) return rc;
     if ((rc = hemo_amg_vcycle(ctx, &ctx->amg[1], tp, qp, ctx->opts.amg_cycles_p))) return rc;
     k_schur_combine<<<hemo_grid(n, 256), 256, 0, st>>>(n, ctx->opts.schur_mass_coef, ctx->opts.schur_lap_coef, tp,
@@ -154,6 +224,10 @@ static int pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_
     if (ctx->opts.project_pressure && (rc = hemo_remove_mean(ctx, n, zp))) return rc;
     // t_u = r_u - A01 z_p
     if ((rc = hemo_spmv_block(ctx, 1, 2, vals_dev, nullptr, zp, -1.0, ru, nullptr, tu, nullptr))) return rc;
+    if (ctx->pc_mask) {
+        k_mask_nodes<<<hemo_grid(n, 256), 256, 0, st>>>(n, 2, ctx->pc_mask, tu);
+        HEMO_LAUNCH_CHECK(ctx);
+    }
     if ((rc = hemo_amg_vcycle(ctx, &ctx->amg[0], tu, zu, ctx->opts.amg_cycles_u))) return rc;
     return 0;
 }
@@ -361,7 +435,7 @@ extern "C" int hemo_ctx_destroy(hemo_ctx* ctx) {
     hemo_amg_free(&ctx->amg[0]); hemo_amg_free(&ctx->amg[1]);
     if (ctx->pc_graph_exec) cudaGraphExecDestroy(ctx->pc_graph_exec);
     if (ctx->pc_graph) cudaGraphDestroy(ctx->pc_graph);
-    cudaFree(ctx->pc_in); cudaFree(ctx->pc_out);
+    cudaFree(ctx->pc_in); cudaFree(ctx->pc_out); cudaFree(ctx->pc_mask); cudaFree(ctx->kry_coef);
     cudaFree(ctx->pc_tmp_u); cudaFree(ctx->pc_tmp_u2); cudaFree(ctx->pc_tmp_p); cudaFree(ctx->pc_tmp_p2);
     cudaFree(ctx->kry_V); cudaFree(ctx->kry_Z); cudaFree(ctx->kry_w);
     delete ctx;

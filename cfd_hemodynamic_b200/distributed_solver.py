@@ -1,0 +1,345 @@
+"""Multi-GPU `stabilized_schur`: one mesh partition per GPU (one process per GPU).
+
+Mirrors what the reference gets from `mpirun -n N`: vertex
+(row) ownership, one layer of ghost cells so every owned row is assembled locally
+(no communication in assembly), a forward ghost update before each operator
+application and residual evaluation (`ghostUpdate`, stabilized_schur.py:137-142,168),
+global reductions in the Krylov and Newton loops (PETSc VecMDot/VecNorm allreduces),
+and a preconditioner restricted to the partition (PETSc's ASM sub-solves are rank-local
+too, :256-267).  NCCL (torch.distributed) is used only for the halo exchange and the
+allreduces; every kernel is libhemo_sm100.so.
+
+Supported: variants whose boundary-term coefficients are static ("schur", "backflow").
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._lib import Hemo, Q_FP, Q_FU, Q_PP, Q_PU, Q_UP, Q_UU
+from .fem import discretization as D
+from .fem import quadrature as Q
+from .linear_solver import BlockSchurSolver
+from .parallel import HaloExchange, Partition
+
+BLOCK_DEGREE = {Q_FU: 12, Q_FP: 11, Q_UU: 12, Q_UP: 11, Q_PU: 11, Q_PP: 10}
+
+
+def _cell_diameter(x, cells):
+    X = x[cells]
+    e = [np.linalg.norm(X[:, i] - X[:, j], axis=1) for i, j in ((0, 1), (0, 2), (1, 2))]
+    return np.maximum(np.maximum(e[0], e[1]), e[2])
+
+
+class DistributedStabilizedSchur:
+    def __init__(self, tables: dict, owner: np.ndarray, device_index: int, group=None, verbose=False):
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.group = group
+        self.verbose = verbose and self.rank == 0
+        if tables["variant"] != "schur":
+            raise NotImplementedError("multi-GPU driver: only the plain stabilized_schur variant so far")
+        self.part = part = Partition(tables["x"], tables["cells"], owner, self.rank)
+        self.n_global = tables["x"].shape[0]
+        self.hemo = hemo = Hemo(device_index)
+        dev = hemo.device
+        nl = part.n_local
+        self.n = nl
+        self.N = 3 * nl
+        par = tables["params"]
+        kw = tables["solver_kw"]
+        self.snes_rtol, self.snes_atol, self.snes_stol = kw["snes_rtol"], kw["snes_atol"], kw["snes_stol"]
+        self.snes_max_it, self.ksp_rtol, self.ksp_max_it = kw["snes_max_it"], kw["ksp_rtol"], kw["ksp_max_it"]
+        self.restart = min(kw["ksp_restart"], 100)
+        # ---- local tables -------------------------------------------------------
+        h = _cell_diameter(part.x, part.cells)
+        hemo.set_mesh(torch.from_numpy(part.x).to(dev), torch.from_numpy(part.cells).to(dev),
+                      torch.from_numpy(np.ascontiguousarray(h)).to(dev))
+        nrowptr, ncol = D.node_graph(part.cells, nl)
+        hemo.set_node_graph(torch.from_numpy(nrowptr).to(dev), torch.from_numpy(ncol).to(dev))
+        for block, deg in BLOCK_DEGREE.items():
+            hemo.set_quadrature(block, *Q.triangle_rule(deg))
+        hemo.set_facet_quadrature(*Q.interval_gauss(2))
+        hemo.set_params(par["dt"], par["rho"], par["mu"], par["f"], float(np.finfo(np.float64).resolution))
+        g2l = part.g2l
+        cell_g2l = -np.ones(tables["cells"].shape[0], dtype=np.int64)
+        cell_g2l[part.cell_glob] = np.arange(part.cell_glob.shape[0])
+        for sid, (pairs, coef) in tables["facet_sets"].items():
+            lc = cell_g2l[pairs[:, 0]]
+            keep = lc >= 0
+            lp = np.stack([lc[keep], pairs[keep, 1]], axis=1)
+            if lp.shape[0] == 0:
+                continue
+            order = np.argsort(lp[:, 0], kind="stable")
+            cells_u, start = np.unique(lp[order, 0], return_index=True)
+            mask = np.add.reduceat((1 << lp[order, 1]).astype(np.int32), start).astype(np.int32)
+            hemo.set_facet_set(sid, torch.from_numpy(cells_u.astype(np.int32)).to(dev),
+                               torch.from_numpy(mask).to(dev), **coef)
+        bcs = []
+        for block, nodes, values in tables["bcs"]:
+            ln = g2l[np.asarray(nodes, dtype=np.int64)]
+            sel = ln >= 0
+            ln = ln[sel]
+            gn = np.asarray(nodes, dtype=np.int64)[sel]
+            if block == "u":
+                vals = np.zeros(2 * nl)
+                vals[2 * ln] = values[2 * gn]
+                vals[2 * ln + 1] = values[2 * gn + 1]
+            else:
+                vals = np.zeros(nl)
+                vals[ln] = values[gn]
+            bcs.append((block, ln, vals))
+        flag, mult, cellflag, g = D.dirichlet_arrays(nl, part.cells, bcs)
+        self._has_bc = bool(flag.any())
+        if self._has_bc:
+            hemo.set_bc(torch.from_numpy(flag).to(dev), torch.from_numpy(mult).to(dev),
+                        torch.from_numpy(cellflag).to(dev))
+        self.ghost_mask = torch.from_numpy(part.ghost_mask).to(dev)
+        hemo.set_pc_mask(self.ghost_mask)
+        self.halo = HaloExchange(part, dev, group)
+        f64 = torch.float64
+        self.d_bcval = torch.from_numpy(g).to(dev)
+        self.d_x = torch.zeros(self.N, dtype=f64, device=dev)
+        self.d_un = torch.zeros(2 * nl, dtype=f64, device=dev)
+        self.d_f = torch.zeros(self.N, dtype=f64, device=dev)
+        self.d_y = torch.zeros(self.N, dtype=f64, device=dev)
+        self.d_w = torch.zeros(self.N, dtype=f64, device=dev)
+        self.d_g = torch.zeros(self.N, dtype=f64, device=dev)
+        self.d_t = torch.zeros(self.N, dtype=f64, device=dev)
+        self.d_vals = torch.zeros(hemo.nnz, dtype=f64, device=dev)
+        self.ldv = (self.N + 31) // 32 * 32
+        self.V = torch.zeros((self.restart + 1) * self.ldv, dtype=f64, device=dev)
+        self.Z = torch.zeros(self.restart * self.ldv, dtype=f64, device=dev)
+        self._red = torch.zeros(self.restart + 2, dtype=f64, device=dev)
+        gl = part.glob_nodes
+        up = tables["u_prev"].reshape(-1, 2)[gl].reshape(-1)
+        self.d_un.copy_(torch.from_numpy(np.ascontiguousarray(up)))
+        self.d_x[:2 * nl].copy_(self.d_un)
+        self.d_x[2 * nl:].copy_(torch.from_numpy(np.ascontiguousarray(tables["p_prev"][gl])))
+        # ---- preconditioner: local block-Schur AMG, ghosts excluded -----------------------
+        hemo.assemble_jacobian(self.d_x, self.d_un, self.d_vals)
+        u_nodes = np.nonzero(flag[0:2 * nl:2] | flag[1:2 * nl:2])[0]
+        p_nodes = np.nonzero(flag[2 * nl:])[0]
+        ghosts = np.arange(part.n_owned, nl)
+        p_open = ghosts
+        self._nullspace = self._test_nullspace()
+        self.linear = BlockSchurSolver(hemo, nrowptr, ncol, np.union1d(u_nodes, ghosts), p_nodes, p_open_nodes=p_open,
+                                       dt=par["dt"], rho=par["rho"], mu=par["mu"], restart=self.restart,
+                                       max_it=self.ksp_max_it, rtol=self.ksp_rtol, project_pressure=False,
+                                       **kw["pc_kw"])
+        self.linear.setup(self.d_vals)
+        self.its_snes = self.its_ksp = 0
+        self.reason = 0
+        self.n_pressure_global = self.n_global
+
+    # ---- global reductions ---------------------------------------------------------------
+    def _allreduce(self, values):
+        k = len(values)
+        t = self._red[:k]
+        t.copy_(torch.as_tensor(values, dtype=torch.float64))
+        dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy().copy()
+
+    def gdot(self, a, b):
+        """Global dot product; at least one operand must have zero ghost entries."""
+        return float(self._allreduce([self.hemo.dot(a, b)])[0])
+
+    def gnorm(self, a_zero_ghosts):
+        return math.sqrt(max(self.gdot(a_zero_ghosts, a_zero_ghosts), 0.0))
+
+    def _remove_pressure_mean(self, v):
+        """MatNullSpaceRemove with the constant-pressure vector over *global* pressure dofs."""
+        nl, no = self.n, self.part.n_owned
+        p = v[2 * nl:]
+        s = float(self._allreduce([float(p[:no].sum().item())])[0])
+        p -= s / self.n_pressure_global
+
+    def _test_nullspace(self):
+        nl = self.n
+        c = self.d_t
+        c.zero_()
+        c[2 * nl:] = 1.0 / math.sqrt(self.n_global)
+        self.hemo.spmv(self.d_vals, c, self.d_w)
+        self.hemo.mask_nodes(self.ghost_mask, self.d_w)
+        r = self.gnorm(self.d_w)
+        scale = math.sqrt(float(self._allreduce([self.hemo.dot(self.d_vals, self.d_vals)])[0])) / math.sqrt(3 * self.n_global)
+        return bool(r < 1e-8 * max(scale, 1e-300))
+
+    # ---- operators ---------------------------------------------------------------------------
+    def _residual(self, x, out):
+        """x must carry valid ghost values; out has zero ghost entries."""
+        self.hemo.assemble_residual(x, self.d_un, self.d_bcval if self._has_bc else None, out)
+        self.hemo.mask_nodes(self.ghost_mask, out)
+
+    def _fgmres(self, b, y):
+        """Right-preconditioned FGMRES(restart) with global reductions; zero initial guess.
+        b has zero ghosts; y gets valid ghost values."""
+        hemo = self.hemo
+        N, ldv, m = self.N, self.ldv, self.restart
+        V, Z = self.V, self.Z
+        y.zero_()
+        bnorm = self.gnorm(b)
+        if bnorm == 0.0:
+            return 0, 0.0
+        tol = max(self.ksp_rtol * bnorm, 1e-50)
+        its = 0
+        beta = bnorm
+        hemo.vec_scale(1.0 / beta, b, V[:N])
+        res = bnorm
+        while its < self.ksp_max_it:
+            H = np.zeros((m + 1, m))
+            cs = np.zeros(m)
+            sn = np.zeros(m)
+            gvec = np.zeros(m + 1)
+            gvec[0] = beta
+            j = 0
+            converged = False
+            while j < m and its < self.ksp_max_it:
+                vj = V[j * ldv:j * ldv + N]
+                zj = Z[j * ldv:j * ldv + N]
+                hemo.pc_apply(self.d_vals, vj, zj)                # local, ghosts stay zero
+                if self._nullspace:
+                    self._remove_pressure_mean(zj)
+                    hemo.mask_nodes(self.ghost_mask, zj)
+                self.halo.update(zj)                              # ghost values from the owners
+                w = self.d_w
+                hemo.spmv(self.d_vals, zj, w)
+                hemo.mask_nodes(self.ghost_mask, w)
+                h = self._allreduce(hemo.vec_mdot(V, ldv, j + 1, w))
+                nsq = hemo.vec_maxpy(V, ldv, h, -1.0, w, want_normsq=True)
+                hn = math.sqrt(max(float(self._allreduce([nsq])[0]), 0.0))
+                H[:j + 1, j] = h
+                H[j + 1, j] = hn
+                if hn > 0.0:
+                    hemo.vec_scale(1.0 / hn, w, V[(j + 1) * ldv:(j + 1) * ldv + N])
+                for i in range(j):
+                    a, b2 = H[i, j], H[i + 1, j]
+                    H[i, j] = cs[i] * a + sn[i] * b2
+                    H[i + 1, j] = -sn[i] * a + cs[i] * b2
+                a, b2 = H[j, j], H[j + 1, j]
+                d = math.hypot(a, b2)
+                cs[j], sn[j] = (a / d, b2 / d) if d > 0 else (1.0, 0.0)
+                H[j, j], H[j + 1, j] = d, 0.0
+                gvec[j + 1] = -sn[j] * gvec[j]
+                gvec[j] = cs[j] * gvec[j]
+                its += 1
+                res = abs(gvec[j + 1])
+                if self.verbose and (its <= 5 or its % 10 == 0):
+                    print(f"      KSP {its:4d} {res / bnorm:.3e}")
+                j += 1
+                if res <= tol or hn == 0.0:
+                    converged = True
+                    break
+            k = j
+            yk = np.linalg.solve(np.triu(H[:k, :k]), gvec[:k])
+            hemo.vec_maxpy(Z, ldv, yk, 1.0, y)
+            if converged:
+                return its, res / bnorm
+            # restart: r = b - A y (y has valid ghosts)
+            hemo.spmv(self.d_vals, y, self.d_t)
+            self.d_t.mul_(-1.0).add_(b)
+            hemo.mask_nodes(self.ghost_mask, self.d_t)
+            beta = self.gnorm(self.d_t)
+            if beta <= tol:
+                return its, beta / bnorm
+            hemo.vec_scale(1.0 / beta, self.d_t, V[:N])
+        raise RuntimeError("FGMRES reached max_it without converging")
+
+    def _newton(self):
+        hemo = self.hemo
+        x, f, y, w, g = self.d_x, self.d_f, self.d_y, self.d_w, self.d_g
+        self._residual(x, f)
+        fnorm = self.gnorm(f)
+        if self.verbose:
+            print(f"  0 SNES Function norm {fnorm:.12e}")
+        ttol = self.snes_rtol * fnorm
+        lin_its = 0
+        if fnorm < self.snes_atol:
+            return 0, 0, 2
+        for it in range(self.snes_max_it):
+            hemo.assemble_jacobian(x, self.d_un, self.d_vals)
+            if it == 0:
+                self.linear.setup(self.d_vals)
+            try:
+                kits, _ = self._fgmres(f, y)
+            except RuntimeError:
+                return it, lin_its, -3
+            lin_its += kits
+            hemo.spmv(self.d_vals, y, self.d_t)
+            hemo.mask_nodes(self.ghost_mask, self.d_t)
+            slope = self.gdot(f, self.d_t)
+            slope = -abs(slope) if slope != 0.0 else -1.0
+            alpha, lam = 1e-4, 1.0
+            f2 = 0.5 * fnorm * fnorm
+            lam_prev = g_prev = None
+            accepted = False
+            trial = torch.empty_like(x)
+            for _ in range(40):
+                trial.copy_(x)
+                hemo.axpy(-lam, y, trial)                 # y and x both carry valid ghosts
+                self._residual(trial, g)
+                gnorm = self.gnorm(g)
+                g2 = 0.5 * gnorm * gnorm
+                if math.isfinite(gnorm) and g2 <= f2 + lam * alpha * slope:
+                    accepted = True
+                    break
+                if not math.isfinite(gnorm):
+                    lam_new = 0.5 * lam
+                elif lam_prev is None:
+                    lam_new = -slope / (2.0 * (g2 - f2 - slope))
+                else:
+                    t1 = g2 - f2 - lam * slope
+                    t2 = g_prev - f2 - lam_prev * slope
+                    a = (t1 / lam ** 2 - t2 / lam_prev ** 2) / (lam - lam_prev)
+                    b = (-lam_prev * t1 / lam ** 2 + lam * t2 / lam_prev ** 2) / (lam - lam_prev)
+                    disc = max(b * b - 3.0 * a * slope, 0.0)
+                    lam_new = -slope / (2.0 * b) if a == 0.0 else (-b + math.sqrt(disc)) / (3.0 * a)
+                lam_new = min(max(lam_new, 0.1 * lam), 0.5 * lam)
+                lam_prev, g_prev = lam, g2
+                lam = lam_new
+            if not accepted:
+                return it + 1, lin_its, -6
+            w.copy_(y)
+            hemo.mask_nodes(self.ghost_mask, w)
+            ynorm = lam * self.gnorm(w)
+            x.copy_(trial)
+            f.copy_(g)
+            fnorm = gnorm
+            if self.verbose:
+                print(f"  {it + 1} SNES Function norm {fnorm:.12e}")
+            if fnorm < self.snes_atol:
+                return it + 1, lin_its, 2
+            if fnorm <= ttol:
+                return it + 1, lin_its, 3
+            w.copy_(x)
+            hemo.mask_nodes(self.ghost_mask, w)
+            if ynorm < self.snes_stol * self.gnorm(w):
+                return it + 1, lin_its, 4
+        return self.snes_max_it, lin_its, -5
+
+    def step_device(self):
+        """One time step, everything resident on the GPUs; u_prev <- u_sol on the device."""
+        self._remove_pressure_mean(self.d_x)      # nullsp.remove(x_n), unconditional (:319)
+        self.its_snes, self.its_ksp, self.reason = self._newton()
+        if self.reason < 0:
+            raise RuntimeError(f"Did not converge, reason: {self.reason}.")
+        self.d_un.copy_(self.d_x[:2 * self.n])
+
+    def gather_solution(self):
+        """(u, p) in global numbering on every rank (test / output helper)."""
+        part = self.part
+        no = part.n_owned
+        xl = self.d_x.cpu().numpy()
+        u_own = xl[:2 * self.n].reshape(-1, 2)[:no]
+        p_own = xl[2 * self.n:][:no]
+        objs = [None] * self.world
+        dist.all_gather_object(objs, (part.glob_nodes[:no], u_own, p_own), group=self.group)
+        u = np.zeros((self.n_global, 2))
+        p = np.zeros(self.n_global)
+        for nodes, uu, pp in objs:
+            u[nodes] = uu
+            p[nodes] = pp
+        return u.reshape(-1), p

@@ -67,13 +67,25 @@ class StabilizedSchurB200(SolverBase):
             "strength_theta", "schur_mass_coef", "schur_lap_coef")}
         self._rules = kw.pop("quadrature", None)
         self._device_index = int(kw.pop("device", 0))
+        # host_only: build spaces / BC tables / facet tables but create no CUDA context
+        # (used by every rank of the multi-GPU driver to derive its partition's tables)
+        self._host_only = bool(kw.pop("host_only", False))
+        self._facet_tables = {}
         self._setup_count = 0
         self._p_c_frozen: list[float] = []
         self._p_c = 0.0
         self.its_snes = 0
         self.its_ksp = 0
         self.reason = 0
-        self._init_device()
+        self.hemo = None
+        if self._host_only:
+            self.n = mesh.geometry.x.shape[0]
+            self.N = 3 * self.n
+            self._cells_host = np.ascontiguousarray(mesh.geometry.dofmap, dtype=np.int32)
+            if self.variant == "schur":
+                self._register_facets(SET_ALL, exterior_facet_indices(mesh.topology), a_p=1.0, a_g=1.0)
+        else:
+            self._init_device()
 
     # ------------------------------------------------------------------
     def _init_device(self):
@@ -121,11 +133,34 @@ class StabilizedSchurB200(SolverBase):
             self._pin[name] = t
         # stabilized_schur.py:79 — the all-facet term is part of F in the ctor
         if self.variant == "schur":
-            ext = exterior_facet_indices(mesh.topology)
-            fc, fm = D.facet_set_by_cell(mesh, ext)
-            self.hemo.set_facet_set(SET_ALL, torch.from_numpy(fc).to(dev), torch.from_numpy(fm).to(dev),
-                                    a_p=1.0, a_g=1.0)
+            self._register_facets(SET_ALL, exterior_facet_indices(mesh.topology), a_p=1.0, a_g=1.0)
         self.linear = None
+
+    def _register_facets(self, set_id: int, facets, **coef):
+        """One tagged ds integral: remembered on the host (export_tables) and, when a
+        device context exists, uploaded grouped by cell."""
+        self._facet_tables[set_id] = (np.asarray(facets, dtype=np.int64), dict(coef))
+        if self.hemo is not None:
+            torch = self._torch
+            dev = self.hemo.device
+            fc, fm = D.facet_set_by_cell(self.mesh, facets)
+            self.hemo.set_facet_set(set_id, torch.from_numpy(fc).to(dev), torch.from_numpy(fm).to(dev), **coef)
+
+    def export_tables(self) -> dict:
+        """Everything the device needs, as host arrays in global numbering: mesh, Dirichlet
+        objects in list order, facet sets as (cell, local facet) pairs with coefficients."""
+        topo = self.mesh.topology
+        return dict(
+            x=np.ascontiguousarray(self.mesh.geometry.x[:, :2]), cells=self._cells_host,
+            bcs=[("u", bc.block_dofs.copy(), bc.g.x.array.copy()) for bc in self.bcu_d]
+                + [("p", bc.block_dofs.copy(), bc.g.x.array.copy()) for bc in self.bcp_d],
+            facet_sets={sid: (topo.facet_cell_pairs(f), c) for sid, (f, c) in self._facet_tables.items()},
+            params=dict(dt=float(self.dt.value), rho=float(self.rho.value), mu=float(self.mu.value),
+                        f=np.asarray(self.f.value, dtype=float).reshape(-1)[:2]),
+            variant=self.variant, u_prev=self.u_prev.x.array.copy(), p_prev=self.p_prev.x.array.copy(),
+            solver_kw=dict(snes_rtol=self.snes_rtol, snes_atol=self.snes_atol, snes_stol=self.snes_stol,
+                           snes_max_it=self.snes_max_it, ksp_rtol=self.ksp_rtol, ksp_max_it=self.ksp_max_it,
+                           ksp_restart=self.ksp_restart, pc_kw=dict(self._pc_kw)))
 
     # ------------------------------------------------------------------
     def _facet_setup(self, facet_tags, tags):
@@ -168,13 +203,15 @@ class StabilizedSchurB200(SolverBase):
             self._g_last = compact
 
     def setup(self, bcu: list[BoundaryCondition], bcp: list[BoundaryCondition], facet_tags=None, tags=None) -> None:
-        torch = self._torch
-        dev = self.hemo.device
         n = self.n
         self._setup_count += 1
         self._facet_setup(facet_tags, tags)
 
         bcs = self._bc_tables(bcu, bcp)
+        if self._host_only:
+            return
+        torch = self._torch
+        dev = self.hemo.device
         flag, mult, cellflag, g = D.dirichlet_arrays(n, self._cells_host, bcs)
         self._g_host = g
         self._g_last = None

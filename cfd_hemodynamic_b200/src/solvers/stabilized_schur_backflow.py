@@ -25,10 +25,6 @@ class Solver(StabilizedSchurB200):
         super().__init__(mesh, dt, rho, mu, f, initial_velocity, p_grade=p_grade, **kwargs)
 
     def _facet_setup(self, facet_tags, tags):
-        torch = self._torch
-        dev = self.hemo.device
-        facets = facet_tags.find(tags["outlet"])
-        fc, fm = D.facet_set_by_cell(self.mesh, facets)
         # `self.F -= ...` runs on every setup() call → multiplicity = setup count
-        self.hemo.set_facet_set(SET_OUTLET, torch.from_numpy(fc).to(dev), torch.from_numpy(fm).to(dev),
-                                a_b=float(self._setup_count), beta_b=self.beta_backflow)
+        self._register_facets(SET_OUTLET, facet_tags.find(tags["outlet"]),
+                              a_b=float(self._setup_count), beta_b=self.beta_backflow)

@@ -48,21 +48,20 @@ class Solver(StabilizedSchurB200):
         return dict(pconst=0.5 * pc_sum, a_s=c, a_b=c, beta_b=self.beta_backflow)
 
     def _facet_setup(self, facet_tags, tags):
+        if self._host_only:
+            raise NotImplementedError("pressure_backflow needs the outlet flux on the device; "
+                                      "the multi-GPU driver does not support it yet")
         torch = self._torch
         dev = self.hemo.device
         fin = facet_tags.find(tags["inlet"])
         fout = facet_tags.find(tags["outlet"])
-        ic, im = D.facet_set_by_cell(self.mesh, fin)
-        oc, om = D.facet_set_by_cell(self.mesh, fout)
-        self.hemo.set_facet_set(SET_OUTLET, torch.from_numpy(oc).to(dev), torch.from_numpy(om).to(dev),
-                                **self._outlet_coef())
+        self._register_facets(SET_OUTLET, fout, **self._outlet_coef())
         # Q_init from the host u_prev (:204-205); the previous live constant becomes frozen
         if self._setup_count > 1:
             self._p_c_frozen.append(self._p_c)
         q_init = self.hemo.outlet_flux(SET_OUTLET, torch.from_numpy(self.u_prev.x.array).to(dev))
         self._p_c = self.R_resistance * abs(q_init)
-        self.hemo.set_facet_set(SET_INLET, torch.from_numpy(ic).to(dev), torch.from_numpy(im).to(dev),
-                                **self._inlet_coef())
+        self._register_facets(SET_INLET, fin, **self._inlet_coef())
         self.hemo.set_facet_coef(SET_OUTLET, **self._outlet_coef())
 
     def _update_facet_coefs(self):

@@ -194,6 +194,20 @@ int hemo_amg_apply(hemo_ctx* ctx, int which, const double* b_dev, double* x_dev,
 /* Level operator of hierarchy `which` after hemo_pc_setup (device copy out;
  * nnzb*bs*bs doubles).  Exposed for the Galerkin-product parity test. */
 int hemo_amg_get_level_values(hemo_ctx* ctx, int which, int level, double* vals_dev, int64_t capacity);
+/* ---- multi-GPU building blocks (domain decomposition, one partition per GPU) ----------
+ * The host driver (cfd_hemodynamic_b200/parallel.py) exchanges ghost values and sums the
+ * Krylov reductions with torch.distributed (NCCL); these entry points are the local,
+ * per-partition pieces: PETSc VecMDot / VecMAXPY / VecScale before their MPI_Allreduce
+ * (KSPSolve inside SNES, src/solvers/stabilized_schur.py:321), and the restriction of the
+ * preconditioner to the partition (PCASM-like: ghost nodes are excluded, :256-267). */
+int hemo_set_pc_mask(hemo_ctx* ctx, const uint8_t* node_mask_dev);
+int hemo_mask_nodes(hemo_ctx* ctx, const uint8_t* node_mask_dev, double* x_dev);
+int hemo_vec_mdot(hemo_ctx* ctx, int64_t n, int k, const double* V_dev, int64_t ldv, const double* w_dev,
+                  double* h_host);
+int hemo_vec_maxpy(hemo_ctx* ctx, int64_t n, int k, const double* V_dev, int64_t ldv,
+                   const double* coef_host, double sign, double* w_dev, double* normsq_host);
+int hemo_vec_scale(hemo_ctx* ctx, int64_t n, double a, const double* x_dev, double* y_dev);
+
 /* 1 (default): hemo_pc_setup captures one preconditioner application as a CUDA
  * graph (needs a non-default stream) and hemo_pc_apply replays it; 0: direct launches. */
 int hemo_use_graph(hemo_ctx* ctx, int on);

@@ -1,0 +1,72 @@
+"""world_size-2 gloo test of the domain-decomposition plumbing: partition + halo plan must
+reproduce the global SpMV (owned rows from local columns after a ghost update) and the global
+dot products (sum of owned parts) on the oracle's Jacobian."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import scipy.sparse as sp
+    from cfd_hemodynamic_b200.parallel import HaloExchange, Partition, slab_partition
+    from oracle import ns_oracle as O
+    from tests import common as T
+    mesh = T.perturbed_square(9, 6, seed=4)
+    prob = T.make_problem(mesh)
+    n = prob.n
+    u, p, un = T.smooth_fields(prob.x)
+    A = O.assemble_J_raw(prob, u, p, un).tocsr()
+    owner = slab_partition(prob.x[:, 0], world)
+    part = Partition(prob.x, prob.cells, owner, rank)
+    # local matrix: rows/cols of the local nodes in local [u|p] numbering
+    gl = part.glob_nodes
+    gdof = np.concatenate([np.stack([2 * gl, 2 * gl + 1], 1).ravel(), 2 * n + gl])
+    Aloc = A[gdof][:, gdof]
+    rng = np.random.default_rng(0)
+    xg = rng.standard_normal(3 * n)
+    xl = torch.tensor(xg[gdof].copy())
+    ghost_dofs = part.dof_index(np.arange(part.n_owned, part.n_local))
+    # local [u|p] layout interleaves u per node: build the same layout for the local vector
+    perm = np.concatenate([np.stack([2 * np.arange(part.n_local), 2 * np.arange(part.n_local) + 1], 1).ravel(),
+                           2 * part.n_local + np.arange(part.n_local)])
+    assert np.array_equal(perm, np.arange(3 * part.n_local))
+    xl[torch.as_tensor(ghost_dofs)] = 0.0            # forget ghost values ...
+    HaloExchange(part, torch.device("cpu")).update(xl)   # ... and get them back from the owners
+    assert np.allclose(xl.numpy(), xg[gdof], rtol=0, atol=0)
+    yl = Aloc @ xl.numpy()
+    owned_dofs = part.dof_index(np.arange(part.n_owned))
+    y_ref = (A @ xg)[gdof][owned_dofs]
+    err = np.abs(yl[owned_dofs] - y_ref).max() / np.abs(y_ref).max()
+    # distributed dot = allreduce of owned parts
+    t = torch.tensor([float(xg[gdof][owned_dofs] @ xg[gdof][owned_dofs])], dtype=torch.float64)
+    dist.all_reduce(t)
+    out.put((rank, err, float(t.item()), float(xg @ xg), part.n_owned, part.n_local))
+    dist.destroy_process_group()
+
+
+def test_partition_halo_world2():
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, dsum, dref, n_owned, n_local in res:
+        assert err < 1e-14, err
+        assert abs(dsum - dref) < 1e-12 * dref
+        assert n_local > n_owned
+    assert res[0][4] + res[1][4] == 70

@@ -1,0 +1,50 @@
+"""Partition invariance on real GPUs (run under torchrun, one rank per GPU):
+the N-partition solve must reproduce the single-GPU solve of the same mesh.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
+"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import contextlib
+import numpy as np, torch, torch.distributed as dist
+
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation
+from cfd_hemodynamic_b200.distributed_solver import DistributedStabilizedSchur
+from cfd_hemodynamic_b200.parallel import slab_partition
+
+nx = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+tight = dict(snes_rtol=1e-11, snes_stol=0.0, ksp_rtol=1e-9, ksp_restart=100) if nx <= 64 else {}
+with contextlib.redirect_stdout(sys.stderr):
+    sc = LidDriven2DSimulation("stabilized_schur", 0.01, 1.0, rho=1, mu=0.01, nx=nx, host_only=True, **tight)
+tables = sc.solver.export_tables()
+owner = slab_partition(tables["x"][:, 0], world)
+ds = DistributedStabilizedSchur(tables, owner, lr, verbose=bool(os.environ.get('DIST_VERBOSE')))
+torch.cuda.synchronize(); dist.barrier()
+t0 = time.time()
+its = []
+for k in range(steps):
+    ds.step_device()
+    its.append((ds.its_snes, ds.its_ksp))
+torch.cuda.synchronize(); dist.barrier()
+dt = (time.time() - t0) / steps
+u, p = ds.gather_solution()
+if rank == 0:
+    print(f"distributed: world {world} nx {nx} ms/step {1e3*dt:.1f} its {its} owned {ds.part.n_owned} local {ds.part.n_local} halo bytes {ds.halo.bytes_per_update}")
+    if nx <= 128:
+        with contextlib.redirect_stdout(sys.stderr):
+            ref = LidDriven2DSimulation("stabilized_schur", 0.01, 1.0, rho=1, mu=0.01, nx=nx, device=lr, **tight)
+        s = ref.solver
+        for k in range(steps):
+            s.step_device()
+        x = s.d_x.cpu().numpy(); n = s.n
+        ur, pr = x[:2 * n], x[2 * n:]
+        eu = np.linalg.norm(u - ur) / np.linalg.norm(ur)
+        ep = np.linalg.norm((p - p.mean()) - (pr - pr.mean())) / np.linalg.norm(pr - pr.mean())
+        print(f"partition invariance: rel err u {eu:.3e} p {ep:.3e} (serial its {s.its_snes},{s.its_ksp})")
+        assert eu < 1e-8 and ep < 1e-8, (eu, ep)
+dist.barrier()
+dist.destroy_process_group()
