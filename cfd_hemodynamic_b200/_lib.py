@@ -79,6 +79,8 @@ SYMBOLS = {
     "hemo_host_aggregate": (_I, [_I, _VP, _VP, _VP, _VP, C.POINTER(_I)]),
     "hemo_set_solver_opts": (_I, [_VP, C.POINTER(SolverOpts)]),
     "hemo_set_pc_mask": (_I, [_VP, _VP]),
+    "hemo_set_external_schur": (_I, [_VP, _I]),
+    "hemo_amg_setup_scalar": (_I, [_VP, _VP, _D]),
     "hemo_mask_nodes": (_I, [_VP, _VP, _VP]),
     "hemo_vec_mdot": (_I, [_VP, _L, _I, _VP, _L, _VP, _VP]),
     "hemo_vec_maxpy": (_I, [_VP, _L, _I, _VP, _L, _VP, _D, _VP, C.POINTER(_D)]),
@@ -302,6 +304,12 @@ class Hemo:
     # ---- multi-GPU building blocks ---------------------------------------------
     def set_pc_mask(self, node_mask):
         self._check(self.lib.hemo_set_pc_mask(self._ctx, _ptr(node_mask)), "hemo_set_pc_mask")
+
+    def set_external_schur(self, on: bool):
+        self._check(self.lib.hemo_set_external_schur(self._ctx, int(on)), "hemo_set_external_schur")
+
+    def amg_setup_scalar(self, lap, coarse_shift=0.0):
+        self._check(self.lib.hemo_amg_setup_scalar(self._ctx, _ptr(lap), float(coarse_shift)), "hemo_amg_setup_scalar")
 
     def mask_nodes(self, node_mask, x):
         self._check(self.lib.hemo_mask_nodes(self._ctx, _ptr(node_mask), _ptr(x)), "hemo_mask_nodes")

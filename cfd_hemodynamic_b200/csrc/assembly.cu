@@ -829,8 +829,9 @@ extern "C" int hemo_set_mesh(hemo_ctx* ctx, const double* x_dev, int n_nodes, co
     ctx->x = x_dev; ctx->cells = cells_dev; ctx->h = h_dev;
     ctx->n = n_nodes; ctx->E = n_cells;
     int rc;
-    if ((rc = hemo_alloc(ctx, &ctx->Ae, (size_t)81 * n_cells))) return rc;
-    if ((rc = hemo_alloc(ctx, &ctx->Fe, (size_t)9 * n_cells))) return rc;
+    cudaFree(ctx->Ae); cudaFree(ctx->Fe);
+    ctx->Ae = ctx->Fe = nullptr;
+    ctx->Ae_count = ctx->Fe_count = 0;
     if ((rc = hemo_alloc(ctx, &ctx->dvec, (size_t)3 * n_nodes))) return rc;
     HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->dvec, 0, sizeof(double) * 3 * n_nodes, ctx->stream));
     return 0;
@@ -1006,6 +1007,21 @@ extern "C" int hemo_set_bc(hemo_ctx* ctx, const uint8_t* dofflag_dev, const doub
     return 0;
 }
 
+// element buffers are allocated on first use (a context that only serves the pressure
+// Laplacian never pays for the 81*E Jacobian buffer)
+static int ensure_elem(hemo_ctx* ctx, size_t ae_count, size_t fe_count) {
+    int rc;
+    if (ae_count > ctx->Ae_count) {
+        if ((rc = hemo_alloc(ctx, &ctx->Ae, ae_count))) return rc;
+        ctx->Ae_count = ae_count;
+    }
+    if (fe_count > ctx->Fe_count) {
+        if ((rc = hemo_alloc(ctx, &ctx->Fe, fe_count))) return rc;
+        ctx->Fe_count = fe_count;
+    }
+    return 0;
+}
+
 static int check_ready(hemo_ctx* ctx) {
     if (!ctx->cells || !ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / node graph not set");
     return upload_constants(ctx);
@@ -1016,6 +1032,7 @@ extern "C" int hemo_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const 
     int rc = check_ready(ctx);
     if (rc) return rc;
     const int E = ctx->E, n = ctx->n;
+    if ((rc = ensure_elem(ctx, (size_t)81 * E, 0))) return rc;
     cudaStream_t st = ctx->stream;
     HEMO_PROF_BEGIN(ctx, HEMO_PROF_CELL_JAC);
     k_cell_jacobian<<<hemo_grid(E, 128), 128, 0, st>>>(E, n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, ctx->Ae);
@@ -1044,6 +1061,7 @@ extern "C" int hemo_assemble_residual(hemo_ctx* ctx, const double* x_dev, const 
     int rc = check_ready(ctx);
     if (rc) return rc;
     const int E = ctx->E, n = ctx->n;
+    if ((rc = ensure_elem(ctx, 0, (size_t)9 * E))) return rc;
     cudaStream_t st = ctx->stream;
     const uint8_t* cf = ctx->have_bc ? ctx->cellflag : nullptr;
     if (ctx->have_bc) {
@@ -1088,6 +1106,8 @@ extern "C" int hemo_assemble_laplace_mass(hemo_ctx* ctx, double* lap_vals_dev, d
     if (!ctx || !lap_vals_dev || !mass_dev) return HEMO_EINVAL;
     if (!ctx->cells || !ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / node graph not set");
     const int E = ctx->E, n = ctx->n;
+    int rc;
+    if ((rc = ensure_elem(ctx, (size_t)9 * E, (size_t)3 * E))) return rc;
     cudaStream_t st = ctx->stream;
     // reuse the element buffers: Ke -> Ae[0..9E), Me -> Fe[0..3E)
     k_cell_laplace<<<hemo_grid(E, 256), 256, 0, st>>>(E, ctx->cells, ctx->x, ctx->Ae, ctx->Fe);

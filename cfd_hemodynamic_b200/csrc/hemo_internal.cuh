@@ -122,8 +122,10 @@ struct hemo_ctx {
     int32_t* vseg_src = nullptr;    // 3E: c*3 + a
     int32_t* diagslot = nullptr;    // n: slot of node i in its own row
     int32_t* rowof = nullptr;       // nnz_node: row (node) of each slot
-    double* Ae = nullptr;           // 81*E element matrices, SoA [81][E]
+    double* Ae = nullptr;           // 81*E element matrices, SoA [81][E] (allocated on first use)
     double* Fe = nullptr;           // 9*E element vectors, SoA [9][E]
+    size_t Ae_count = 0, Fe_count = 0;
+    int external_schur = 0;         // 1: hemo_pc_apply takes z_p from the caller (multi-GPU global pressure solve)
     double* dvec = nullptr;         // 3n lifting vector (g - x on bc dofs)
 
     // forms

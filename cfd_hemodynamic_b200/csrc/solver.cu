@@ -90,6 +90,25 @@ extern "C" int hemo_remove_mean_vec(hemo_ctx* ctx, int64_t n, double* x_dev) {
     return hemo_remove_mean(ctx, n, x_dev);
 }
 
+extern "C" int hemo_set_external_schur(hemo_ctx* ctx, int on) {
+    if (!ctx) return HEMO_EINVAL;
+    ctx->external_schur = on != 0;
+    return 0;
+}
+
+// Numeric setup of the scalar (pressure Laplacian) hierarchy alone: used by a context that
+// only serves the replicated global pressure solve of the multi-GPU driver.
+extern "C" int hemo_amg_setup_scalar(hemo_ctx* ctx, const double* lap_vals_dev, double coarse_shift) {
+    if (!ctx || !lap_vals_dev) return HEMO_EINVAL;
+    if (!ctx->amg[1].ready) HEMO_FAIL(ctx, HEMO_ESTATE, "pressure AMG hierarchy not finalized");
+    k_lap_with_bc<<<hemo_grid(ctx->nnz_node, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->nnz_node, ctx->rowof, ctx->ncol,
+                                                                          lap_vals_dev,
+                                                                          ctx->have_bc ? ctx->dofflag : nullptr,
+                                                                          ctx->amg[1].op[0].val);
+    HEMO_LAUNCH_CHECK(ctx);
+    return hemo_amg_numeric_shift(ctx, &ctx->amg[1], coarse_shift);
+}
+
 extern "C" int hemo_set_pc_mask(hemo_ctx* ctx, const uint8_t* node_mask_dev) {
     if (!ctx) return HEMO_EINVAL;
     if (!ctx->cells) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_set_mesh must precede hemo_set_pc_mask");
@@ -211,6 +230,7 @@ static int pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_
     double* qp = ctx->pc_tmp_p2;
     double* tu = ctx->pc_tmp_u;
     int rc;
+    if (!ctx->external_schur) {
     HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(tp, rp, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     if (ctx->pc_mask) {
         k_mask_nodes<<<hemo_grid(n, 256), 256, 0, st>>>(n, 1, ctx->pc_mask, tp);
@@ -222,6 +242,7 @@ static int pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_
                                                        ctx->mass, qp, ctx->have_bc ? ctx->dofflag : nullptr, rp, zp);
     HEMO_LAUNCH_CHECK(ctx);
     if (ctx->opts.project_pressure && (rc = hemo_remove_mean(ctx, n, zp))) return rc;
+    }   // else: z_p was provided by the caller (global pressure solve of the multi-GPU driver)
     // t_u = r_u - A01 z_p
     if ((rc = hemo_spmv_block(ctx, 1, 2, vals_dev, nullptr, zp, -1.0, ru, nullptr, tu, nullptr))) return rc;
     if (ctx->pc_mask) {
@@ -282,6 +303,9 @@ extern "C" int hemo_pc_apply(hemo_ctx* ctx, const double* vals_dev, const double
         const size_t bytes = sizeof(double) * 3 * (size_t)ctx->n;
         cudaStream_t st = ctx->stream;
         HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->pc_in, r_dev, bytes, cudaMemcpyDeviceToDevice, st));
+        if (ctx->external_schur)
+            HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->pc_out + 2 * (size_t)ctx->n, z_dev + 2 * (size_t)ctx->n,
+                                                 sizeof(double) * ctx->n, cudaMemcpyDeviceToDevice, st));
         HEMO_CHECK_CUDA(ctx, cudaGraphLaunch(ctx->pc_graph_exec, st));
         HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(z_dev, ctx->pc_out, bytes, cudaMemcpyDeviceToDevice, st));
         ctx->launches += ctx->pc_graph_nodes;

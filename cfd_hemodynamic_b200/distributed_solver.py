@@ -23,7 +23,7 @@ from ._lib import Hemo, Q_FP, Q_FU, Q_PP, Q_PU, Q_UP, Q_UU
 from .fem import discretization as D
 from .fem import quadrature as Q
 from .linear_solver import BlockSchurSolver
-from .parallel import HaloExchange, Partition
+from .parallel import HaloExchange, HaloExchangeAllGather, Partition
 
 BLOCK_DEGREE = {Q_FU: 12, Q_FP: 11, Q_UU: 12, Q_UP: 11, Q_PU: 11, Q_PP: 10}
 
@@ -35,14 +35,16 @@ def _cell_diameter(x, cells):
 
 
 class DistributedStabilizedSchur:
-    def __init__(self, tables: dict, owner: np.ndarray, device_index: int, group=None, verbose=False):
+    def __init__(self, tables: dict, owner: np.ndarray, device_index: int, group=None, verbose=False,
+                 global_pressure: bool = True, overlap: int = 8):
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.group = group
         self.verbose = verbose and self.rank == 0
         if tables["variant"] != "schur":
             raise NotImplementedError("multi-GPU driver: only the plain stabilized_schur variant so far")
-        self.part = part = Partition(tables["x"], tables["cells"], owner, self.rank)
+        self.overlap = int(overlap) if dist.get_world_size(group) > 1 else 1
+        self.part = part = Partition(tables["x"], tables["cells"], owner, self.rank, overlap=self.overlap)
         self.n_global = tables["x"].shape[0]
         self.hemo = hemo = Hemo(device_index)
         dev = hemo.device
@@ -98,8 +100,10 @@ class DistributedStabilizedSchur:
             hemo.set_bc(torch.from_numpy(flag).to(dev), torch.from_numpy(mult).to(dev),
                         torch.from_numpy(cellflag).to(dev))
         self.ghost_mask = torch.from_numpy(part.ghost_mask).to(dev)
-        hemo.set_pc_mask(self.ghost_mask)
-        self.halo = HaloExchange(part, dev, group)
+        # the local preconditioner acts on owned + overlap vertices; only vertices with
+        # incomplete rows (outermost layer) are held fixed
+        hemo.set_pc_mask(torch.from_numpy(part.incomplete_mask).to(dev))
+        self.halo = HaloExchangeAllGather(part, owner, tables["cells"], dev, group)
         f64 = torch.float64
         self.d_bcval = torch.from_numpy(g).to(dev)
         self.d_x = torch.zeros(self.N, dtype=f64, device=dev)
@@ -123,7 +127,7 @@ class DistributedStabilizedSchur:
         hemo.assemble_jacobian(self.d_x, self.d_un, self.d_vals)
         u_nodes = np.nonzero(flag[0:2 * nl:2] | flag[1:2 * nl:2])[0]
         p_nodes = np.nonzero(flag[2 * nl:])[0]
-        ghosts = np.arange(part.n_owned, nl)
+        ghosts = np.nonzero(part.incomplete_mask)[0]
         p_open = ghosts
         self._nullspace = self._test_nullspace()
         self.linear = BlockSchurSolver(hemo, nrowptr, ncol, np.union1d(u_nodes, ghosts), p_nodes, p_open_nodes=p_open,
@@ -133,7 +137,87 @@ class DistributedStabilizedSchur:
         self.linear.setup(self.d_vals)
         self.its_snes = self.its_ksp = 0
         self.reason = 0
+        import os
+        self._profile = bool(os.environ.get("HEMO_DIST_PROFILE"))
+        self.timers = {}
+        self._last_key = None
+        self._last_t = 0.0
         self.n_pressure_global = self.n_global
+        self.global_pressure = bool(global_pressure) and self.world > 1
+        if self.global_pressure:
+            self._setup_global_pressure(tables, owner, device_index)
+
+    # ---- replicated global pressure solve -------------------------------------------------
+    def _setup_global_pressure(self, tables, owner, device_index):
+        """The Schur-complement approximation needs L_p^-1 with *global* coupling (a
+        partition-local Laplacian solve loses the low modes and the Krylov iteration count
+        grows ~4x).  The scalar pressure problem is small next to the 3x3-block Jacobian, so
+        every rank keeps the global pressure Laplacian hierarchy and applies the V-cycle
+        redundantly; only the pressure residual is all-gathered over NVLink."""
+        from .fem import amg_setup
+        import scipy.sparse as sp
+        dev = self.hemo.device
+        xg = np.ascontiguousarray(tables["x"])
+        cg = np.ascontiguousarray(tables["cells"], dtype=np.int32)
+        ng = xg.shape[0]
+        self.hemo_p = hp = Hemo(device_index)
+        hp.set_mesh(torch.from_numpy(xg).to(dev), torch.from_numpy(cg).to(dev),
+                    torch.from_numpy(np.ascontiguousarray(_cell_diameter(xg, cg))).to(dev))
+        nrp, nc = D.node_graph(cg, ng)
+        hp.set_node_graph(torch.from_numpy(nrp).to(dev), torch.from_numpy(nc).to(dev))
+        pbc = [(b, nodes, vals) for b, nodes, vals in tables["bcs"] if b == "p"]
+        pmask = np.zeros(ng, dtype=bool)
+        if pbc:
+            flag, mult, cellflag, _ = D.dirichlet_arrays(ng, cg, pbc)
+            hp.set_bc(torch.from_numpy(flag).to(dev), torch.from_numpy(mult).to(dev), torch.from_numpy(cellflag).to(dev))
+            pmask = flag[2 * ng:].astype(bool)
+        self.g_lap, self.g_mass = hp.assemble_laplace_mass()
+        L = sp.csr_matrix((self.g_lap.cpu().numpy(), nc, nrp), shape=(ng, ng))
+        lv = amg_setup.build_hierarchy(L, pmask, max_coarse=160)
+        for l, d in enumerate(lv):
+            hp.amg_set_level(1, l, d["P"], d["R"], d["AP"], d["C"])
+        hp.amg_finalize(1, len(lv) + 1)
+        hp.set_solver_opts(**{**self.linear.opts, "project_pressure": 0})
+        hp.amg_setup_scalar(self.g_lap, 1e-8 if self._nullspace else 0.0)
+        self.hemo.set_external_schur(True)
+        self.hemo.use_graph(True)
+        self.linear._first = False
+        self.hemo.pc_setup(self.d_vals)            # re-capture the graph without the local pressure part
+        # gather plan: owned pressure values of every rank -> global vector
+        counts = [int((owner == q).sum()) for q in range(self.world)]
+        self._gmax = max(counts)
+        idx = torch.full((self.world, self._gmax), ng, dtype=torch.int64)      # padding -> dummy slot ng
+        for q in range(self.world):
+            own_q = np.nonzero(owner == q)[0]
+            idx[q, :counts[q]] = torch.from_numpy(own_q)
+        self._gidx = idx.reshape(-1).to(dev)
+        self._gsend = torch.zeros(self._gmax, dtype=torch.float64, device=dev)
+        self._grecv = torch.zeros(self.world * self._gmax, dtype=torch.float64, device=dev)
+        self._rp_g = torch.zeros(ng + 1, dtype=torch.float64, device=dev)
+        self._q_g = torch.zeros(ng, dtype=torch.float64, device=dev)
+        self._loc_nodes = torch.from_numpy(self.part.glob_nodes).to(dev)
+        self._pbc_g = torch.from_numpy(np.nonzero(pmask)[0]).to(dev) if pmask.any() else None
+        self._cm = self.linear.opts["schur_mass_coef"]
+        self._cl = self.linear.opts["schur_lap_coef"]
+        self._cyc_p = self.linear.opts["amg_cycles_p"]
+
+    def _global_schur(self, r, z):
+        """z_p (all local nodes, ghosts included) = c_m r_p / m + c_L L_glob^-1 r_p."""
+        nl, no, ng = self.n, self.part.n_owned, self.n_global
+        self._gsend[:no].copy_(r[2 * nl:2 * nl + no])
+        dist.all_gather_into_tensor(self._grecv, self._gsend, group=self.group)
+        self._rp_g.index_copy_(0, self._gidx, self._grecv)
+        rp = self._rp_g[:ng]
+        if self._nullspace:
+            rp -= rp.mean()
+        self.hemo_p.amg_apply(1, rp, self._q_g, self._cyc_p)
+        zg = self._q_g
+        zg.mul_(self._cl).add_(rp / self.g_mass, alpha=self._cm)
+        if self._pbc_g is not None:
+            zg.index_copy_(0, self._pbc_g, rp.index_select(0, self._pbc_g))
+        if self._nullspace:
+            zg -= zg.mean()
+        torch.index_select(zg, 0, self._loc_nodes, out=z[2 * nl:])
 
     # ---- global reductions ---------------------------------------------------------------
     def _allreduce(self, values):
@@ -174,6 +258,17 @@ class DistributedStabilizedSchur:
         self.hemo.assemble_residual(x, self.d_un, self.d_bcval if self._has_bc else None, out)
         self.hemo.mask_nodes(self.ghost_mask, out)
 
+    def _tic(self, key):
+        """Optional wall-clock section timing (HEMO_DIST_PROFILE=1): synchronises the stream."""
+        if not self._profile:
+            return
+        import time
+        torch.cuda.synchronize(self.hemo.device)
+        now = time.perf_counter()
+        if self._last_key is not None:
+            self.timers[self._last_key] = self.timers.get(self._last_key, 0.0) + now - self._last_t
+        self._last_key, self._last_t = key, now
+
     def _fgmres(self, b, y):
         """Right-preconditioned FGMRES(restart) with global reductions; zero initial guess.
         b has zero ghosts; y gets valid ghost values."""
@@ -200,17 +295,36 @@ class DistributedStabilizedSchur:
             while j < m and its < self.ksp_max_it:
                 vj = V[j * ldv:j * ldv + N]
                 zj = Z[j * ldv:j * ldv + N]
-                hemo.pc_apply(self.d_vals, vj, zj)                # local, ghosts stay zero
-                if self._nullspace:
-                    self._remove_pressure_mean(zj)
-                    hemo.mask_nodes(self.ghost_mask, zj)
+                rin = vj
+                if self.overlap > 1:
+                    # restricted additive Schwarz: the local solve sees the residual on its overlap
+                    self._tic("halo")
+                    rin = self.d_t
+                    rin.copy_(vj)
+                    self.halo.update(rin)
+                if self.global_pressure:
+                    self._tic("schur_global")
+                    self._global_schur(vj, zj)                    # z_p with global coupling (incl. ghosts)
+                    self._tic("pc_u")
+                    hemo.pc_apply(self.d_vals, rin, zj)           # z_u = A00_loc^-1 (r_u - A01 z_p)
+                else:
+                    hemo.pc_apply(self.d_vals, rin, zj)
+                    if self._nullspace:
+                        self._remove_pressure_mean(zj)
+                if self.overlap > 1 or not self.global_pressure:
+                    hemo.mask_nodes(self.ghost_mask, zj)          # keep the owned part only
+                self._tic("halo")
                 self.halo.update(zj)                              # ghost values from the owners
+                self._tic("spmv")
                 w = self.d_w
                 hemo.spmv(self.d_vals, zj, w)
                 hemo.mask_nodes(self.ghost_mask, w)
+                self._tic("mdot+allreduce")
                 h = self._allreduce(hemo.vec_mdot(V, ldv, j + 1, w))
+                self._tic("maxpy+allreduce")
                 nsq = hemo.vec_maxpy(V, ldv, h, -1.0, w, want_normsq=True)
                 hn = math.sqrt(max(float(self._allreduce([nsq])[0]), 0.0))
+                self._tic("host")
                 H[:j + 1, j] = h
                 H[j + 1, j] = hn
                 if hn > 0.0:

@@ -64,12 +64,19 @@ class Partition:
     """The part of a mesh one rank works on: every cell touching an owned vertex,
     owned vertices first, ghost vertices after; halo plan towards the neighbours."""
 
-    def __init__(self, x, cells, owner, rank: int):
+    def __init__(self, x, cells, owner, rank: int, overlap: int = 1):
+        """overlap = number of cell layers around the owned vertices (1 = the minimal ghost
+        layer that completes every owned row; more layers widen the subdomain on which the
+        rank-local preconditioner acts — restricted additive Schwarz)."""
         import numpy as np
         owner = np.asarray(owner)
         cell_owner = owner[cells]                                 # (E, 3)
         mine = (cell_owner == rank).any(axis=1)
         self.rank = rank
+        for _ in range(max(1, int(overlap)) - 1):
+            inside = np.zeros(owner.shape[0], dtype=bool)
+            inside[cells[mine]] = True
+            mine = inside[cells].any(axis=1)
         self.cell_glob = np.nonzero(mine)[0]
         lc = cells[self.cell_glob]
         nodes = np.unique(lc)
@@ -85,6 +92,11 @@ class Partition:
         self.x = np.ascontiguousarray(x[self.glob_nodes])
         self.ghost_mask = np.zeros(self.n_local, dtype=np.uint8)
         self.ghost_mask[self.n_owned:] = 1
+        # local vertices whose rows are incomplete (some incident cell is not local)
+        cnt_glob = np.bincount(cells.reshape(-1), minlength=owner.shape[0])[self.glob_nodes]
+        cnt_loc = np.bincount(self.cells.reshape(-1), minlength=self.n_local)
+        self.incomplete_mask = (cnt_loc != cnt_glob).astype(np.uint8)
+        assert not self.incomplete_mask[:self.n_owned].any()
         # halo plan: recv = my ghosts owned by q; send = my owned vertices in cells that touch q
         self.neighbors = {}
         for q in np.unique(owner[ghosts]):
@@ -128,3 +140,56 @@ class HaloExchange:
             w.wait()
         for q, si, ri, sbuf, rbuf in self.plan:
             v.index_copy_(0, ri, rbuf)
+
+
+class HaloExchangeAllGather:
+    """Same forward ghost update as `HaloExchange`, but as ONE all-gather of every rank's
+    interface values (padded to the largest interface) instead of per-neighbour send/recv
+    pairs: KB-sized messages are latency-bound, and one NCCL all-gather over NVSwitch costs a
+    fraction of a grouped P2P round (measured 3 ms -> ~0.1 ms per update on 2 B200s)."""
+
+    def __init__(self, part: Partition, owner, cells, device, group=None):
+        import numpy as np
+        self.group = group
+        world = dist.get_world_size(group)
+        owner = np.asarray(owner)
+        # every rank publishes which vertices it ghosts; rank q then sends the union of the
+        # requests that it owns (sorted by global id, so all ranks agree on the layout)
+        ghost_lists = [None] * world
+        dist.all_gather_object(ghost_lists, part.glob_nodes[part.n_owned:], group=group)
+        wanted = np.unique(np.concatenate([np.asarray(g, dtype=np.int64) for g in ghost_lists] + [np.zeros(0, np.int64)]))
+        lists = [wanted[owner[wanted] == q] for q in range(world)]
+        self.maxn = max(1, max(len(l) for l in lists))
+        mine = lists[part.rank]
+        loc = part.g2l[mine]
+        assert (loc >= 0).all() and (loc < part.n_owned).all()
+        self.n_mine = len(mine)
+        self.send_idx = torch.as_tensor(part.dof_index(loc).reshape(3, -1).T.reshape(-1).copy(), dtype=torch.int64,
+                                        device=device)          # (node, [ux, uy, p]) order
+        self.sbuf = torch.zeros(3 * self.maxn, dtype=torch.float64, device=device)
+        self.rbuf = torch.zeros(world * 3 * self.maxn, dtype=torch.float64, device=device)
+        # where each of my ghost dofs sits in the gathered buffer
+        ghosts = part.glob_nodes[part.n_owned:]
+        src = np.empty((len(ghosts), 3), dtype=np.int64)
+        pos_in_list = {}
+        for q in range(world):
+            pos_in_list[q] = dict(zip(lists[q].tolist(), range(len(lists[q]))))
+        for k, g in enumerate(ghosts.tolist()):
+            q = int(owner[g])
+            p = pos_in_list[q][g]
+            base = q * 3 * self.maxn + 3 * p
+            src[k] = (base, base + 1, base + 2)
+        gl = np.arange(part.n_owned, part.n_local)
+        dst = np.stack([2 * gl, 2 * gl + 1, 2 * part.n_local + gl], axis=1)
+        self.src = torch.as_tensor(src.reshape(-1), dtype=torch.int64, device=device)
+        self.dst = torch.as_tensor(dst.reshape(-1), dtype=torch.int64, device=device)
+        self.bytes_per_update = 8 * 3 * self.maxn * world
+
+    def update(self, v: torch.Tensor):
+        if self.src.numel() == 0 and self.n_mine == 0:
+            return
+        if self.n_mine:
+            self.sbuf[:3 * self.n_mine] = v.index_select(0, self.send_idx)
+        dist.all_gather_into_tensor(self.rbuf, self.sbuf, group=self.group)
+        if self.src.numel():
+            v.index_copy_(0, self.dst, self.rbuf.index_select(0, self.src))

@@ -201,6 +201,12 @@ int hemo_amg_get_level_values(hemo_ctx* ctx, int which, int level, double* vals_
  * (KSPSolve inside SNES, src/solvers/stabilized_schur.py:321), and the restriction of the
  * preconditioner to the partition (PCASM-like: ghost nodes are excluded, :256-267). */
 int hemo_set_pc_mask(hemo_ctx* ctx, const uint8_t* node_mask_dev);
+/* 1: hemo_pc_apply reads z_p from the pressure part of z (computed by the caller with a
+ * global pressure solve) and only performs the velocity block solve. */
+int hemo_set_external_schur(hemo_ctx* ctx, int on);
+/* Numeric setup of the pressure-Laplacian hierarchy alone (contexts that only serve the
+ * replicated global pressure solve). */
+int hemo_amg_setup_scalar(hemo_ctx* ctx, const double* lap_vals_dev, double coarse_shift);
 int hemo_mask_nodes(hemo_ctx* ctx, const uint8_t* node_mask_dev, double* x_dev);
 int hemo_vec_mdot(hemo_ctx* ctx, int64_t n, int k, const double* V_dev, int64_t ldv, const double* w_dev,
                   double* h_host);

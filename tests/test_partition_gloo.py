@@ -15,7 +15,7 @@ def _worker(rank, world, port, out):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import scipy.sparse as sp
-    from cfd_hemodynamic_b200.parallel import HaloExchange, Partition, slab_partition
+    from cfd_hemodynamic_b200.parallel import HaloExchange, HaloExchangeAllGather, Partition, slab_partition
     from oracle import ns_oracle as O
     from tests import common as T
     mesh = T.perturbed_square(9, 6, seed=4)
@@ -39,6 +39,9 @@ def _worker(rank, world, port, out):
     assert np.array_equal(perm, np.arange(3 * part.n_local))
     xl[torch.as_tensor(ghost_dofs)] = 0.0            # forget ghost values ...
     HaloExchange(part, torch.device("cpu")).update(xl)   # ... and get them back from the owners
+    assert np.allclose(xl.numpy(), xg[gdof], rtol=0, atol=0)
+    xl[torch.as_tensor(ghost_dofs)] = -7.0           # same through the single all-gather variant
+    HaloExchangeAllGather(part, owner, prob.cells, torch.device("cpu")).update(xl)
     assert np.allclose(xl.numpy(), xg[gdof], rtol=0, atol=0)
     yl = Aloc @ xl.numpy()
     owned_dofs = part.dof_index(np.arange(part.n_owned))

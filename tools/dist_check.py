@@ -32,6 +32,8 @@ for k in range(steps):
 torch.cuda.synchronize(); dist.barrier()
 dt = (time.time() - t0) / steps
 u, p = ds.gather_solution()
+if rank == 0 and ds.timers:
+    print("section seconds:", {k: round(v, 3) for k, v in ds.timers.items()}, "its", sum(i[1] for i in its))
 if rank == 0:
     print(f"distributed: world {world} nx {nx} ms/step {1e3*dt:.1f} its {its} owned {ds.part.n_owned} local {ds.part.n_local} halo bytes {ds.halo.bytes_per_update}")
     if nx <= 128:
