@@ -1,0 +1,33 @@
+"""DFG 2D-1 (Re = 20) validation run on the GPU: march to steady state and report drag, lift and
+pressure difference next to the literature bounds (Schäfer–Turek 1996: Cd 5.57–5.59,
+Cl 0.0104–0.0110, dp 0.1172–0.1176)."""
+import os, sys, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import contextlib
+import numpy as np, torch
+from cfd_hemodynamic_b200.src.scenarios.dfg_1 import DFG1Benchmark
+
+refine = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+T = float(sys.argv[2]) if len(sys.argv) > 2 else 8.0
+dt = float(sys.argv[3]) if len(sys.argv) > 3 else 0.01
+with contextlib.redirect_stdout(sys.stderr):
+    sc = DFG1Benchmark("stabilized_schur", dt, T, lc_min=0.05 / 6 / refine, lc_max=0.41 / 13 / refine)
+s = sc.solver
+print(f"cells {s._cells_host.shape[0]} dofs {s.N}")
+t = 0.0
+i = 0
+t0 = time.time()
+hist = []
+while t < T:
+    s.solveStep()
+    i += 1
+    t += dt
+    if i % 100 == 0 or t >= T:
+        cd, cl = sc.drag_lift()
+        dp = sc.pressure_difference()
+        rel = np.abs(s.u_sol.x.array - s.u_prev.x.array).max() / max(np.abs(s.u_sol.x.array).max(), 1e-12) / dt
+        hist.append((round(t, 3), cd, cl, dp))
+        print(f"t={t:6.2f} Cd={cd:.5f} Cl={cl:.6f} dp={dp:.6f} du/dt_rel={rel:.2e} its=({s.its_snes},{s.its_ksp}) wall={time.time()-t0:.1f}s")
+    s.u_prev.x.array[:] = s.u_sol.x.array[:]
+    s.p_prev.x.array[:] = s.p_sol.x.array[:]
+print(json.dumps({"refine": refine, "cells": int(s._cells_host.shape[0]), "final": hist[-1]}))
