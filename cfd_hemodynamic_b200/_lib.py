@@ -42,7 +42,7 @@ class SolverOpts(C.Structure):
                 ("atol", C.c_double), ("amg_cycles_u", C.c_int), ("amg_cycles_p", C.c_int),
                 ("cheb_degree", C.c_int), ("project_pressure", C.c_int), ("pc_mode", C.c_int),
                 ("schur_mass_coef", C.c_double), ("schur_lap_coef", C.c_double),
-                ("cheb_ratio", C.c_double)]
+                ("cheb_ratio", C.c_double), ("cheb_degree_pre", C.c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/hemo.h declares

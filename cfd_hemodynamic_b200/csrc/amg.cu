@@ -851,6 +851,7 @@ static int vcycle_t(hemo_ctx* ctx, HemoAmg* amg, int l, const double* b, double*
     cudaStream_t st = ctx->stream;
     const HemoAmgOp& A = amg->op[l];
     const int degree = ctx->opts.cheb_degree > 0 ? ctx->opts.cheb_degree : 2;
+    const int degree_pre = ctx->opts.cheb_degree_pre > 0 ? ctx->opts.cheb_degree_pre : degree;
     const double ratio = ctx->opts.cheb_ratio > 1.0 ? ctx->opts.cheb_ratio : 4.0;
     if (l == amg->fuse_level) {
         // every remaining level fits one CTA
@@ -867,7 +868,7 @@ static int vcycle_t(hemo_ctx* ctx, HemoAmg* amg, int l, const double* b, double*
         return 0;
     }
     int rc;
-    if ((rc = smooth_t<BS>(ctx, A, b, x, x_is_zero, degree, ratio))) return rc;
+    if ((rc = smooth_t<BS>(ctx, A, b, x, x_is_zero, degree_pre, ratio))) return rc;
     // residual and restriction
     if ((rc = hemo_bsr_spmv_ex(ctx, BS, A.n, A.rowptr, A.col, A.val, x, -1.0, b, A.r))) return rc;
     const HemoAmgLevel& L = amg->lev[l];

@@ -296,6 +296,38 @@ k_cell_jacobian(int E, int n, const int32_t* __restrict__ cells, const double* _
     element_jacobian(cd, d, [&](int slot, double val) { out[slot * stride] = val; });
 }
 
+// lifting: be += Ae[:, j] * (g - x)_j over constrained dofs j (3P apply_lifting with
+// x0 = x, alpha = -1; reference src/solvers/stabilized_schur.py:172-174).  Kept out of line:
+// only boundary-adjacent cells take this path and it would otherwise set the register
+// count of the whole residual kernel.
+__device__ __noinline__ void lift_cell(const CellData& cd, const CellDerived& d, const int v[3], int n,
+                                       const double* __restrict__ dvec, double Fu[3][2], double Fp[3]) {
+    double dl[3][3];
+    bool any = false;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        dl[b][0] = dvec[2 * (int64_t)v[b]];
+        dl[b][1] = dvec[2 * (int64_t)v[b] + 1];
+        dl[b][2] = dvec[2 * (int64_t)n + v[b]];
+        any = any || dl[b][0] != 0.0 || dl[b][1] != 0.0 || dl[b][2] != 0.0;
+    }
+    if (!any) return;
+    double lift[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) lift[a][0] = lift[a][1] = lift[a][2] = 0.0;
+    element_jacobian(cd, d, [&](int slot, double val) {
+        const int ab = slot / 9, rc = slot % 9;
+        const int a = ab / 3, b = ab % 3, ri = rc / 3, ci = rc % 3;
+        lift[a][ri] += val * dl[b][ci];
+    });
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        Fu[a][0] += lift[a][0];
+        Fu[a][1] += lift[a][1];
+        Fp[a] += lift[a][2];
+    }
+}
+
 __global__ void __launch_bounds__(128)
 k_cell_residual(int E, int n, const int32_t* __restrict__ cells, const double* __restrict__ x,
                 const double* __restrict__ h, const double* __restrict__ sol,
@@ -310,36 +342,7 @@ k_cell_residual(int E, int n, const int32_t* __restrict__ cells, const double* _
     derive_cell(cd, d);
     double Fu[3][2], Fp[3];
     element_residual(cd, d, Fu, Fp);
-    if (cellflag != nullptr && cellflag[c]) {
-        // lifting: be += Ae[:, j] * (g - x)_j over constrained dofs j
-        // (3P apply_lifting with x0 = x, alpha = -1; reference
-        //  src/solvers/stabilized_schur.py:172-174)
-        double dl[3][3];
-        bool any = false;
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-            dl[b][0] = dvec[2 * (int64_t)v[b]];
-            dl[b][1] = dvec[2 * (int64_t)v[b] + 1];
-            dl[b][2] = dvec[2 * (int64_t)n + v[b]];
-            any = any || dl[b][0] != 0.0 || dl[b][1] != 0.0 || dl[b][2] != 0.0;
-        }
-        if (any) {
-            double lift[3][3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) lift[a][0] = lift[a][1] = lift[a][2] = 0.0;
-            element_jacobian(cd, d, [&](int slot, double val) {
-                const int ab = slot / 9, rc = slot % 9;
-                const int a = ab / 3, b = ab % 3, ri = rc / 3, ci = rc % 3;
-                lift[a][ri] += val * dl[b][ci];
-            });
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                Fu[a][0] += lift[a][0];
-                Fu[a][1] += lift[a][1];
-                Fp[a] += lift[a][2];
-            }
-        }
-    }
+    if (cellflag != nullptr && cellflag[c]) lift_cell(cd, d, v, n, dvec, Fu, Fp);
     const int64_t stride = E;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {

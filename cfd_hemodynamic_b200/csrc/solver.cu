@@ -443,6 +443,7 @@ extern "C" int hemo_ctx_create(int device, hemo_ctx** out) {
     ctx->opts.schur_mass_coef = 0.0;
     ctx->opts.schur_lap_coef = 1.0;
     ctx->opts.cheb_ratio = 4.0;
+    ctx->opts.cheb_degree_pre = 0;
     *out = ctx;
     return 0;
 }

@@ -19,7 +19,7 @@ class BlockSchurSolver:
     def __init__(self, hemo, nrowptr: np.ndarray, ncol: np.ndarray, u_dirichlet_nodes: np.ndarray,
                  p_dirichlet_nodes: np.ndarray, *, p_open_nodes: np.ndarray | None = None, dt: float, rho: float, mu: float,
                  restart: int = 60, max_it: int = 1000, rtol: float = 1e-5, atol: float = 1e-50,
-                 amg_cycles_u: int = 1, amg_cycles_p: int = 1, cheb_degree: int = 2, cheb_ratio: float = 4.0,
+                 amg_cycles_u: int = 1, amg_cycles_p: int = 1, cheb_degree: int = 2, cheb_ratio: float = 4.0, cheb_degree_pre: int = 1,
                  project_pressure: bool = False, smooth_prolongator: bool = True, strength_theta: float = 0.08,
                  schur_mass_coef: float | None = None, schur_lap_coef: float | None = None):
         self.hemo = hemo
@@ -32,7 +32,7 @@ class BlockSchurSolver:
                          project_pressure=int(bool(project_pressure)), pc_mode=0,
                          schur_mass_coef=mu if schur_mass_coef is None else schur_mass_coef,
                          schur_lap_coef=2.0 * rho / dt if schur_lap_coef is None else schur_lap_coef,
-                         cheb_ratio=cheb_ratio)
+                         cheb_ratio=cheb_ratio, cheb_degree_pre=cheb_degree_pre)
         hemo.set_solver_opts(**self.opts)
         # constant operators of the Schur approximation, assembled on the device
         self.lap, self.mass = hemo.assemble_laplace_mass()

@@ -63,7 +63,7 @@ class StabilizedSchurB200(SolverBase):
         # "step": once per time step, later Newton iterations reuse the hierarchy
         self.pc_rebuild = str(kw.pop("pc_rebuild", "step"))
         self._pc_kw = {k: kw.pop(k) for k in list(kw) if k in (
-            "amg_cycles_u", "amg_cycles_p", "cheb_degree", "cheb_ratio", "smooth_prolongator",
+            "amg_cycles_u", "amg_cycles_p", "cheb_degree", "cheb_ratio", "cheb_degree_pre", "smooth_prolongator",
             "strength_theta", "schur_mass_coef", "schur_lap_coef")}
         self._rules = kw.pop("quadrature", None)
         self._device_index = int(kw.pop("device", 0))

@@ -76,6 +76,7 @@ typedef struct hemo_solver_opts {
     double schur_mass_coef;
     double schur_lap_coef;
     double cheb_ratio;    /* Chebyshev smoothing interval [lmax/ratio, lmax] (default 4) */
+    int cheb_degree_pre;  /* degree of the pre-smoother (0: same as cheb_degree) */
 } hemo_solver_opts;
 
 /* ---- context ----------------------------------------------------------- */
