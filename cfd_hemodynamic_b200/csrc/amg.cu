@@ -14,8 +14,8 @@
 
 #include "hemo_internal.cuh"
 
-int hemo_bsr_spmv_ex(hemo_ctx* ctx, int bs, int n, const int32_t* rowptr, const int32_t* col, const double* val,
-                     const double* x, double alpha, const double* b, double* y);
+int hemo_bsr_spmv_ex(hemo_ctx* ctx, int bs, int n, const int32_t* rowptr, const int32_t* col, const areal* val,
+                     const areal* x, double alpha, const areal* b, areal* y);
 
 // ---------------------------------------------------------------------------
 // numeric Galerkin product
@@ -38,10 +38,10 @@ __device__ __forceinline__ int find_col(const int32_t* __restrict__ col, int lo,
 template <int BS>
 __global__ void __launch_bounds__(256)
 k_numeric_ap(int n, const int32_t* __restrict__ a_rowptr, const int32_t* __restrict__ a_col,
-             const double* __restrict__ a_val, const int32_t* __restrict__ p_rowptr,
+             const areal* __restrict__ a_val, const int32_t* __restrict__ p_rowptr,
              const int32_t* __restrict__ p_col, const double* __restrict__ p_val,
              const int32_t* __restrict__ ap_rowptr, const int32_t* __restrict__ ap_col,
-             double* __restrict__ ap_val) {
+             areal* __restrict__ ap_val) {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = gt >> 3, lane = gt & 7;
     if (i >= n) return;
@@ -60,7 +60,7 @@ k_numeric_ap(int n, const int32_t* __restrict__ a_rowptr, const int32_t* __restr
                 if (p_col[u] == myc) {
                     const double w = p_val[u];
 #pragma unroll
-                    for (int k = 0; k < BS * BS; ++k) acc[k] = fma(w, a_val[(int64_t)t * BS * BS + k], acc[k]);
+                    for (int k = 0; k < BS * BS; ++k) acc[k] = fma(w, (double)a_val[(int64_t)t * BS * BS + k], acc[k]);
                 }
             }
         }
@@ -78,9 +78,9 @@ template <int BS>
 __global__ void __launch_bounds__(256)
 k_numeric_rap(int nc, const int32_t* __restrict__ r_rowptr, const int32_t* __restrict__ r_col,
               const double* __restrict__ r_val, const int32_t* __restrict__ ap_rowptr,
-              const int32_t* __restrict__ ap_col, const double* __restrict__ ap_val,
+              const int32_t* __restrict__ ap_col, const areal* __restrict__ ap_val,
               const int32_t* __restrict__ c_rowptr, const int32_t* __restrict__ c_col,
-              double* __restrict__ c_val) {
+              areal* __restrict__ c_val) {
     const int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (I >= nc) return;
@@ -99,7 +99,7 @@ k_numeric_rap(int nc, const int32_t* __restrict__ r_rowptr, const int32_t* __res
             for (int u = ap_rowptr[i]; u < u1; ++u) {
                 if (ap_col[u] == myc) {
 #pragma unroll
-                    for (int k = 0; k < BS * BS; ++k) acc[k] = fma(w, ap_val[(int64_t)u * BS * BS + k], acc[k]);
+                    for (int k = 0; k < BS * BS; ++k) acc[k] = fma(w, (double)ap_val[(int64_t)u * BS * BS + k], acc[k]);
                 }
             }
         }
@@ -153,7 +153,7 @@ __global__ void k_sort_pairs(int64_t nseg, const int32_t* __restrict__ ptr, int2
 template <int BS>
 __global__ void __launch_bounds__(256)
 k_gather_product(int64_t nseg, const int32_t* __restrict__ seg_ptr, const int2* __restrict__ seg_src,
-                 const double* __restrict__ w, const double* __restrict__ blk, double* __restrict__ out) {
+                 const double* __restrict__ w, const areal* __restrict__ blk, areal* __restrict__ out) {
     const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nseg) return;
     double acc[BS * BS];
@@ -164,19 +164,23 @@ k_gather_product(int64_t nseg, const int32_t* __restrict__ seg_ptr, const int2* 
         const int2 src = seg_src[q];
         const double wt = w[src.x];
         if (BS == 2) {
-            const double2 v0 = reinterpret_cast<const double2*>(blk)[2 * (int64_t)src.y];
-            const double2 v1 = reinterpret_cast<const double2*>(blk)[2 * (int64_t)src.y + 1];
-            acc[0] = fma(wt, v0.x, acc[0]); acc[1] = fma(wt, v0.y, acc[1]);
-            acc[BS * BS - 2] = fma(wt, v1.x, acc[BS * BS - 2]); acc[BS * BS - 1] = fma(wt, v1.y, acc[BS * BS - 1]);
+            const areal2 v0 = reinterpret_cast<const areal2*>(blk)[2 * (int64_t)src.y];
+            const areal2 v1 = reinterpret_cast<const areal2*>(blk)[2 * (int64_t)src.y + 1];
+            acc[0] = fma(wt, (double)v0.x, acc[0]); acc[1] = fma(wt, (double)v0.y, acc[1]);
+            acc[BS * BS - 2] = fma(wt, (double)v1.x, acc[BS * BS - 2]);
+            acc[BS * BS - 1] = fma(wt, (double)v1.y, acc[BS * BS - 1]);
         } else {
-            acc[0] = fma(wt, blk[src.y], acc[0]);
+            acc[0] = fma(wt, (double)blk[src.y], acc[0]);
         }
     }
     if (BS == 2) {
-        reinterpret_cast<double2*>(out)[2 * s] = make_double2(acc[0], acc[1]);
-        reinterpret_cast<double2*>(out)[2 * s + 1] = make_double2(acc[BS * BS - 2], acc[BS * BS - 1]);
+        areal2 o0, o1;
+        o0.x = (areal)acc[0]; o0.y = (areal)acc[1];
+        o1.x = (areal)acc[BS * BS - 2]; o1.y = (areal)acc[BS * BS - 1];
+        reinterpret_cast<areal2*>(out)[2 * s] = o0;
+        reinterpret_cast<areal2*>(out)[2 * s + 1] = o1;
     } else {
-        out[s] = acc[0];
+        out[s] = (areal)acc[0];
     }
 }
 
@@ -225,7 +229,7 @@ static int build_one_list(hemo_ctx* ctx, bool swap, int nrows, const int32_t* a_
 template <int BS>
 __global__ void __launch_bounds__(256)
 k_diag_bound(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-             const double* __restrict__ val, double* __restrict__ dinv, double* __restrict__ partial_max) {
+             const areal* __restrict__ val, areal* __restrict__ dinv, double* __restrict__ partial_max) {
     __shared__ double sh[256];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double bound = 0.0;
@@ -273,14 +277,29 @@ __global__ void k_max_final(int m, const double* __restrict__ partial, double* _
     if (threadIdx.x == 0) out[0] = sh[0];
 }
 
+__global__ void k_axpy_areal(int64_t n, double a, const areal* __restrict__ x, areal* __restrict__ y) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) y[i] = (areal)fma(a, (double)x[i], (double)y[i]);
+}
+
+__global__ void k_to_areal(int64_t n, const double* __restrict__ x, areal* __restrict__ y) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) y[i] = (areal)x[i];
+}
+
+__global__ void k_from_areal(int64_t n, const areal* __restrict__ x, double* __restrict__ y) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) y[i] = (double)x[i];
+}
+
 // ---------------------------------------------------------------------------
 // Chebyshev smoother on D^-1 A (fused SpMV + three-term update per step)
 // ---------------------------------------------------------------------------
 // start from x = 0:  r = D^-1 b ; d = r / theta ; x = d
 template <int BS>
-__global__ void k_cheb_start_zero(int64_t N, const double* __restrict__ dinv, const double* __restrict__ b,
-                                  double inv_theta, double* __restrict__ r, double* __restrict__ d,
-                                  double* __restrict__ x) {
+__global__ void k_cheb_start_zero(int64_t N, const areal* __restrict__ dinv, const areal* __restrict__ b,
+                                  double inv_theta, areal* __restrict__ r, areal* __restrict__ d,
+                                  areal* __restrict__ x) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= N) return;
     const double rv = dinv[i] * b[i];
@@ -294,7 +313,7 @@ __global__ void k_cheb_start_zero(int64_t N, const double* __restrict__ dinv, co
 // of the group returns the full sum.
 template <int BS>
 __device__ __forceinline__ void row_product(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                            const double* __restrict__ val, const double* __restrict__ x,
+                                            const areal* __restrict__ val, const areal* __restrict__ x,
                                             int i, bool ok, int lane, double acc[BS]) {
 #pragma unroll
     for (int k = 0; k < BS; ++k) acc[k] = 0.0;
@@ -302,13 +321,13 @@ __device__ __forceinline__ void row_product(const int32_t* __restrict__ rowptr, 
     for (int t = r0 + lane; t < r1; t += 4) {
         const int j = col[t];
         if (BS == 1) {
-            acc[0] = fma(val[t], x[j], acc[0]);
+            acc[0] = fma((double)val[t], (double)x[j], acc[0]);
         } else {
-            const double2 xv = reinterpret_cast<const double2*>(x)[j];
-            const double2 v0 = reinterpret_cast<const double2*>(val)[2 * (int64_t)t];
-            const double2 v1 = reinterpret_cast<const double2*>(val)[2 * (int64_t)t + 1];
-            acc[0] += v0.x * xv.x + v0.y * xv.y;
-            acc[BS - 1] += v1.x * xv.x + v1.y * xv.y;
+            const areal2 xv = reinterpret_cast<const areal2*>(x)[j];
+            const areal2 v0 = reinterpret_cast<const areal2*>(val)[2 * (int64_t)t];
+            const areal2 v1 = reinterpret_cast<const areal2*>(val)[2 * (int64_t)t + 1];
+            acc[0] += (double)v0.x * xv.x + (double)v0.y * xv.y;
+            acc[BS - 1] += (double)v1.x * xv.x + (double)v1.y * xv.y;
         }
     }
 #pragma unroll
@@ -324,8 +343,8 @@ __device__ __forceinline__ void row_product(const int32_t* __restrict__ rowptr, 
 template <int BS>
 __global__ void __launch_bounds__(256)
 k_cheb_start(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-             const double* __restrict__ val, const double* __restrict__ dinv, const double* __restrict__ b,
-             double inv_theta, const double* __restrict__ xin, double* __restrict__ r, double* __restrict__ d) {
+             const areal* __restrict__ val, const areal* __restrict__ dinv, const areal* __restrict__ b,
+             double inv_theta, const areal* __restrict__ xin, areal* __restrict__ r, areal* __restrict__ d) {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = gt >> 2, lane = gt & 3;
     const bool ok = i < n;
@@ -343,9 +362,9 @@ k_cheb_start(int n, const int32_t* __restrict__ rowptr, const int32_t* __restric
 template <int BS>
 __global__ void __launch_bounds__(256)
 k_cheb_step(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-            const double* __restrict__ val, const double* __restrict__ dinv, double c1, double c2,
-            const double* __restrict__ dold, double* __restrict__ dnew, double* __restrict__ r,
-            double* __restrict__ x, int add_old) {
+            const areal* __restrict__ val, const areal* __restrict__ dinv, double c1, double c2,
+            const areal* __restrict__ dold, areal* __restrict__ dnew, areal* __restrict__ r,
+            areal* __restrict__ x, int add_old) {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = gt >> 2, lane = gt & 3;
     const bool ok = i < n;
@@ -365,7 +384,7 @@ k_cheb_step(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict
 template <int BS, bool ADD>
 __global__ void __launch_bounds__(256)
 k_transfer(int nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-           const double* __restrict__ w, const double* __restrict__ x, double* __restrict__ y) {
+           const double* __restrict__ w, const areal* __restrict__ x, areal* __restrict__ y) {
     const int I = blockIdx.x * blockDim.x + threadIdx.x;
     if (I >= nrows) return;
     double acc[BS];
@@ -389,7 +408,7 @@ k_transfer(int nrows, const int32_t* __restrict__ rowptr, const int32_t* __restr
 // CTA (phases separated by __syncthreads), replacing ~10 launches per level.
 // ---------------------------------------------------------------------------
 template <int BS>
-__device__ __forceinline__ void row_product_serial(const HemoCoarseLevel& L, const double* __restrict__ x, int i,
+__device__ __forceinline__ void row_product_serial(const HemoCoarseLevel& L, const areal* __restrict__ x, int i,
                                                    double acc[BS]) {
 #pragma unroll
     for (int k = 0; k < BS; ++k) acc[k] = 0.0;
@@ -398,20 +417,20 @@ __device__ __forceinline__ void row_product_serial(const HemoCoarseLevel& L, con
 #pragma unroll
         for (int k = 0; k < BS; ++k)
 #pragma unroll
-            for (int l = 0; l < BS; ++l) acc[k] = fma(L.val[(int64_t)t * BS * BS + k * BS + l], x[(int64_t)j * BS + l], acc[k]);
+            for (int l = 0; l < BS; ++l) acc[k] = fma((double)L.val[(int64_t)t * BS * BS + k * BS + l], (double)x[(int64_t)j * BS + l], acc[k]);
     }
 }
 
 template <int BS>
-__device__ void fused_smooth(const HemoCoarseLevel& L, const double* __restrict__ b, double* __restrict__ x,
+__device__ void fused_smooth(const HemoCoarseLevel& L, const areal* __restrict__ b, areal* __restrict__ x,
                              bool x_is_zero, int degree, double ratio) {
     const int tid = threadIdx.x, T = blockDim.x;
     const int N = L.n * BS;
     const double lmax = *L.lmax, lmin = lmax / ratio;
     const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
     double rho = 1.0 / sigma;
-    double* dold = L.d0;
-    double* dnew = L.d1;
+    areal* dold = L.d0;
+    areal* dnew = L.d1;
     if (x_is_zero) {
         for (int q = tid; q < N; q += T) {
             const double rv = L.dinv[q] * b[q];
@@ -452,7 +471,7 @@ __device__ void fused_smooth(const HemoCoarseLevel& L, const double* __restrict_
         }
         __syncthreads();
         pending = false;
-        double* t = dold; dold = dnew; dnew = t;
+        areal* t = dold; dold = dnew; dnew = t;
         rho = rho_new;
     }
     if (pending) {
@@ -463,14 +482,14 @@ __device__ void fused_smooth(const HemoCoarseLevel& L, const double* __restrict_
 
 template <int BS>
 __global__ void __launch_bounds__(1024)
-k_coarse_vcycle(const HemoCoarseLevel* __restrict__ desc, int nl, const double* __restrict__ b0, double* __restrict__ x0,
+k_coarse_vcycle(const HemoCoarseLevel* __restrict__ desc, int nl, const areal* __restrict__ b0, areal* __restrict__ x0,
                 int degree, double ratio, const double* __restrict__ dense_inv, int dense_n) {
     const int tid = threadIdx.x, T = blockDim.x;
     // down sweep
     for (int l = 0; l + 1 < nl; ++l) {
         const HemoCoarseLevel L = desc[l];
-        const double* b = (l == 0) ? b0 : L.b;
-        double* x = (l == 0) ? x0 : L.x;
+        const areal* b = (l == 0) ? b0 : L.b;
+        areal* x = (l == 0) ? x0 : L.x;
         fused_smooth<BS>(L, b, x, true, degree, ratio);
         for (int i = tid; i < L.n; i += T) {
             double acc[BS];
@@ -479,7 +498,7 @@ k_coarse_vcycle(const HemoCoarseLevel* __restrict__ desc, int nl, const double* 
             for (int k = 0; k < BS; ++k) L.r[i * BS + k] = b[i * BS + k] - acc[k];
         }
         __syncthreads();
-        double* bc = desc[l + 1].b;
+        areal* bc = desc[l + 1].b;
         for (int I = tid; I < L.nc; I += T) {
             double acc[BS];
 #pragma unroll
@@ -488,7 +507,7 @@ k_coarse_vcycle(const HemoCoarseLevel* __restrict__ desc, int nl, const double* 
                 const int j = L.r_col[t];
                 const double w = L.r_val[t];
 #pragma unroll
-                for (int k = 0; k < BS; ++k) acc[k] = fma(w, L.r[j * BS + k], acc[k]);
+                for (int k = 0; k < BS; ++k) acc[k] = fma(w, (double)L.r[j * BS + k], acc[k]);
             }
 #pragma unroll
             for (int k = 0; k < BS; ++k) bc[I * BS + k] = acc[k];
@@ -497,11 +516,11 @@ k_coarse_vcycle(const HemoCoarseLevel* __restrict__ desc, int nl, const double* 
     }
     // coarsest: dense inverse
     {
-        const double* b = (nl == 1) ? b0 : desc[nl - 1].b;
-        double* x = (nl == 1) ? x0 : desc[nl - 1].x;
+        const areal* b = (nl == 1) ? b0 : desc[nl - 1].b;
+        areal* x = (nl == 1) ? x0 : desc[nl - 1].x;
         for (int row = tid; row < dense_n; row += T) {
             double acc = 0.0;
-            for (int c = 0; c < dense_n; ++c) acc = fma(dense_inv[(int64_t)row * dense_n + c], b[c], acc);
+            for (int c = 0; c < dense_n; ++c) acc = fma(dense_inv[(int64_t)row * dense_n + c], (double)b[c], acc);
             x[row] = acc;
         }
         __syncthreads();
@@ -509,9 +528,9 @@ k_coarse_vcycle(const HemoCoarseLevel* __restrict__ desc, int nl, const double* 
     // up sweep
     for (int l = nl - 2; l >= 0; --l) {
         const HemoCoarseLevel L = desc[l];
-        const double* b = (l == 0) ? b0 : L.b;
-        double* x = (l == 0) ? x0 : L.x;
-        const double* xc = desc[l + 1].x;
+        const areal* b = (l == 0) ? b0 : L.b;
+        areal* x = (l == 0) ? x0 : L.x;
+        const areal* xc = desc[l + 1].x;
         for (int i = tid; i < L.n; i += T) {
             double acc[BS];
 #pragma unroll
@@ -520,7 +539,7 @@ k_coarse_vcycle(const HemoCoarseLevel* __restrict__ desc, int nl, const double* 
                 const int j = L.p_col[t];
                 const double w = L.p_val[t];
 #pragma unroll
-                for (int k = 0; k < BS; ++k) acc[k] = fma(w, xc[j * BS + k], acc[k]);
+                for (int k = 0; k < BS; ++k) acc[k] = fma(w, (double)xc[j * BS + k], acc[k]);
             }
 #pragma unroll
             for (int k = 0; k < BS; ++k) x[i * BS + k] += acc[k];
@@ -536,7 +555,7 @@ k_coarse_vcycle(const HemoCoarseLevel* __restrict__ desc, int nl, const double* 
 // ---------------------------------------------------------------------------
 template <int BS>
 __global__ void k_dense_fill(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                             const double* __restrict__ val, int N, double shift_rel, double* __restrict__ M /*N x N*/) {
+                             const areal* __restrict__ val, int N, double shift_rel, double* __restrict__ M /*N x N*/) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     for (int t = rowptr[i]; t < rowptr[i + 1]; ++t) {
@@ -593,7 +612,7 @@ k_dense_invert(int N, const double* __restrict__ Min, double* __restrict__ inv, 
 
 // y = inv * b : one warp per row
 __global__ void __launch_bounds__(256)
-k_dense_gemv(int N, const double* __restrict__ inv, const double* __restrict__ b, double* __restrict__ y) {
+k_dense_gemv(int N, const double* __restrict__ inv, const areal* __restrict__ b, areal* __restrict__ y) {
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     double acc = 0.0;
@@ -811,7 +830,7 @@ int hemo_amg_numeric_shift(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift) {
 int hemo_amg_numeric(hemo_ctx* ctx, HemoAmg* amg) { return hemo_amg_numeric_shift(ctx, amg, 0.0); }
 
 template <int BS>
-static int smooth_t(hemo_ctx* ctx, const HemoAmgOp& A, const double* b, double* x, bool x_is_zero, int degree,
+static int smooth_t(hemo_ctx* ctx, const HemoAmgOp& A, const areal* b, areal* x, bool x_is_zero, int degree,
                     double ratio) {
     cudaStream_t st = ctx->stream;
     const double lmax = A.lmax, lmin = lmax / ratio;
@@ -819,8 +838,8 @@ static int smooth_t(hemo_ctx* ctx, const HemoAmgOp& A, const double* b, double* 
     const double sigma = theta / delta;
     double rho = 1.0 / sigma;
     const int64_t N = (int64_t)A.n * BS;
-    double* d0 = A.d;
-    double* d1 = A.d + N;
+    areal* d0 = A.d;
+    areal* d1 = A.d + N;
     if (x_is_zero) {
         k_cheb_start_zero<BS><<<hemo_grid(N, 256), 256, 0, st>>>(N, A.dinv, b, 1.0 / theta, A.r, d0, x);
     } else {
@@ -839,15 +858,18 @@ static int smooth_t(hemo_ctx* ctx, const HemoAmgOp& A, const double* b, double* 
         HEMO_LAUNCH_CHECK(ctx);
         if (fine) HEMO_PROF_END(ctx, BS == 2 ? HEMO_PROF_CHEB_U0 : HEMO_PROF_CHEB_P0);
         pending = false;
-        double* t = d0; d0 = d1; d1 = t;
+        areal* t = d0; d0 = d1; d1 = t;
         rho = rho_new;
     }
-    if (pending) return hemo_axpy(ctx, N, 1.0, d0, x);
+    if (pending) {
+        k_axpy_areal<<<hemo_grid(N, 256), 256, 0, st>>>(N, 1.0, d0, x);
+        HEMO_LAUNCH_CHECK(ctx);
+    }
     return 0;
 }
 
 template <int BS>
-static int vcycle_t(hemo_ctx* ctx, HemoAmg* amg, int l, const double* b, double* x, bool x_is_zero) {
+static int vcycle_t(hemo_ctx* ctx, HemoAmg* amg, int l, const areal* b, areal* x, bool x_is_zero) {
     cudaStream_t st = ctx->stream;
     const HemoAmgOp& A = amg->op[l];
     const int degree = ctx->opts.cheb_degree > 0 ? ctx->opts.cheb_degree : 2;
@@ -882,14 +904,21 @@ static int vcycle_t(hemo_ctx* ctx, HemoAmg* amg, int l, const double* b, double*
     return 0;
 }
 
-// x = (ncycles V-cycles applied to A x = b, zero initial guess)
+// x = (ncycles V-cycles applied to A x = b, zero initial guess); fp64 in / out, the
+// cycle itself runs on the hierarchy's storage type
 int hemo_amg_vcycle(hemo_ctx* ctx, HemoAmg* amg, const double* b, double* x, int ncycles) {
     if (!amg->ready) HEMO_FAIL(ctx, HEMO_ESTATE, "AMG hierarchy not finalized");
     int rc;
+    HemoAmgOp& top = amg->op[0];
+    const int64_t N = (int64_t)top.n * amg->bs;
+    k_to_areal<<<hemo_grid(N, 256), 256, 0, ctx->stream>>>(N, b, top.b);
+    HEMO_LAUNCH_CHECK(ctx);
     for (int c = 0; c < (ncycles > 0 ? ncycles : 1); ++c) {
-        if (amg->bs == 2) rc = vcycle_t<2>(ctx, amg, 0, b, x, c == 0);
-        else rc = vcycle_t<1>(ctx, amg, 0, b, x, c == 0);
+        if (amg->bs == 2) rc = vcycle_t<2>(ctx, amg, 0, top.b, top.x, c == 0);
+        else rc = vcycle_t<1>(ctx, amg, 0, top.b, top.x, c == 0);
         if (rc) return rc;
     }
+    k_from_areal<<<hemo_grid(N, 256), 256, 0, ctx->stream>>>(N, top.x, x);
+    HEMO_LAUNCH_CHECK(ctx);
     return 0;
 }

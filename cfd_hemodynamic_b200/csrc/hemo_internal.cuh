@@ -15,6 +15,19 @@
 #define HEMO_MAX_LEVELS 16
 #define HEMO_DENSE_MAX 160    // max dofs of the dense coarsest-level solve (N*N doubles in shared memory)
 
+// Storage type of the multigrid hierarchies (operators, smoother data, cycle vectors).
+// The preconditioner only has to be a good approximate inverse: single-precision storage
+// halves its HBM traffic, accumulation stays in fp64 registers, and the outer FGMRES,
+// the Jacobian, the residuals and every reduction remain fp64 (results are unchanged to the
+// solver tolerance; -DHEMO_AMG_FP64 switches back).
+#ifdef HEMO_AMG_FP64
+typedef double areal;
+typedef double2 areal2;
+#else
+typedef float areal;
+typedef float2 areal2;
+#endif
+
 struct HemoRule {
     int nq;
     int alias;                // lowest block id with an identical rule
@@ -42,17 +55,17 @@ struct HemoAmgOp {
     int64_t nnzb = 0;          // blocks
     const int32_t* rowptr = nullptr;
     const int32_t* col = nullptr;
-    double* val = nullptr;     // nnzb*bs*bs
-    double* dinv = nullptr;    // n*bs   inverse diagonal
+    areal* val = nullptr;      // nnzb*bs*bs
+    areal* dinv = nullptr;     // n*bs   inverse diagonal
     double lmax = 2.0;         // bound of spectrum of D^-1 A
-    double *x = nullptr, *b = nullptr, *r = nullptr, *d = nullptr;  // n*bs work vectors
+    areal *x = nullptr, *b = nullptr, *r = nullptr, *d = nullptr;  // n*bs work vectors
 };
 
 struct HemoAmgLevel {
     int n_fine = 0, n_coarse = 0;
     int32_t *p_rowptr = nullptr, *p_col = nullptr; double* p_val = nullptr;
     int32_t *r_rowptr = nullptr, *r_col = nullptr; double* r_val = nullptr;
-    int32_t *ap_rowptr = nullptr, *ap_col = nullptr; double* ap_val = nullptr;
+    int32_t *ap_rowptr = nullptr, *ap_col = nullptr; areal* ap_val = nullptr;
     int32_t *c_rowptr = nullptr, *c_col = nullptr;
     int64_t nnz_p = 0, nnz_ap = 0, nnz_c = 0;
     // precomputed gather lists of the numeric Galerkin product (hierarchy 0 only):
@@ -65,8 +78,8 @@ struct HemoAmgLevel {
 struct HemoCoarseLevel {
     int n, nc;
     const int32_t *rowptr, *col;
-    const double *val, *dinv;
-    double *x, *b, *r, *d0, *d1;
+    const areal *val, *dinv;
+    areal *x, *b, *r, *d0, *d1;
     const int32_t *p_rowptr, *p_col; const double* p_val;
     const int32_t *r_rowptr, *r_col; const double* r_val;
     const double* lmax;
@@ -241,7 +254,7 @@ static inline int hemo_grid(int64_t n, int block) {
 int hemo_ensure_reduce(hemo_ctx* ctx, size_t partial_n, size_t out_n);
 int hemo_dot_dev(hemo_ctx* ctx, int64_t n, const double* x, const double* y, double* out_host);
 int hemo_bsr_spmv(hemo_ctx* ctx, int bs, int n, const int32_t* rowptr, const int32_t* col,
-                  const double* val, const double* x, double* y);
+                  const areal* val, const areal* x, areal* y);
 // implemented in amg.cu
 int hemo_amg_numeric(hemo_ctx* ctx, HemoAmg* amg);
 int hemo_amg_vcycle(hemo_ctx* ctx, HemoAmg* amg, const double* b, double* x, int ncycles);

@@ -141,13 +141,14 @@ extern "C" int hemo_spmv(hemo_ctx* ctx, const double* vals_dev, const double* x_
 }
 
 // ---------------------------------------------------------------------------
-// BSR SpMV for multigrid operators: y = b + alpha * A x (bs = 1 or 2)
+// BSR SpMV for multigrid operators: y = b + alpha * A x (bs = 1 or 2), hierarchy storage
+// type `areal`, fp64 accumulation
 // ---------------------------------------------------------------------------
 template <int BS>
 __global__ void __launch_bounds__(256)
 k_bsr_spmv(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-           const double* __restrict__ val, const double* __restrict__ x, double alpha,
-           const double* __restrict__ b, double* __restrict__ y) {
+           const areal* __restrict__ val, const areal* __restrict__ x, double alpha,
+           const areal* __restrict__ b, areal* __restrict__ y) {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = gt >> 2;        // 4 lanes per block row
     const int lane = gt & 3;
@@ -157,13 +158,13 @@ k_bsr_spmv(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     for (int t = r0 + lane; t < r1; t += 4) {
         const int j = col[t];
         if (BS == 1) {
-            a0 += val[t] * x[j];
+            a0 += (double)val[t] * (double)x[j];
         } else {
-            const double2 xv = reinterpret_cast<const double2*>(x)[j];
-            const double2 v0 = reinterpret_cast<const double2*>(val)[2 * (int64_t)t];
-            const double2 v1 = reinterpret_cast<const double2*>(val)[2 * (int64_t)t + 1];
-            a0 += v0.x * xv.x + v0.y * xv.y;
-            a1 += v1.x * xv.x + v1.y * xv.y;
+            const areal2 xv = reinterpret_cast<const areal2*>(x)[j];
+            const areal2 v0 = reinterpret_cast<const areal2*>(val)[2 * (int64_t)t];
+            const areal2 v1 = reinterpret_cast<const areal2*>(val)[2 * (int64_t)t + 1];
+            a0 += (double)v0.x * xv.x + (double)v0.y * xv.y;
+            a1 += (double)v1.x * xv.x + (double)v1.y * xv.y;
         }
     }
 #pragma unroll
@@ -173,16 +174,16 @@ k_bsr_spmv(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     }
     if (ok && lane == 0) {
         if (BS == 1) {
-            y[i] = (b ? b[i] : 0.0) + alpha * a0;
+            y[i] = (areal)((b ? (double)b[i] : 0.0) + alpha * a0);
         } else {
-            y[2 * (int64_t)i] = (b ? b[2 * (int64_t)i] : 0.0) + alpha * a0;
-            y[2 * (int64_t)i + 1] = (b ? b[2 * (int64_t)i + 1] : 0.0) + alpha * a1;
+            y[2 * (int64_t)i] = (areal)((b ? (double)b[2 * (int64_t)i] : 0.0) + alpha * a0);
+            y[2 * (int64_t)i + 1] = (areal)((b ? (double)b[2 * (int64_t)i + 1] : 0.0) + alpha * a1);
         }
     }
 }
 
-int hemo_bsr_spmv_ex(hemo_ctx* ctx, int bs, int n, const int32_t* rowptr, const int32_t* col, const double* val,
-                     const double* x, double alpha, const double* b, double* y) {
+int hemo_bsr_spmv_ex(hemo_ctx* ctx, int bs, int n, const int32_t* rowptr, const int32_t* col, const areal* val,
+                     const areal* x, double alpha, const areal* b, areal* y) {
     const int grid = hemo_grid((int64_t)n * 4, 256);
     if (bs == 1) k_bsr_spmv<1><<<grid, 256, 0, ctx->stream>>>(n, rowptr, col, val, x, alpha, b, y);
     else k_bsr_spmv<2><<<grid, 256, 0, ctx->stream>>>(n, rowptr, col, val, x, alpha, b, y);
@@ -190,8 +191,8 @@ int hemo_bsr_spmv_ex(hemo_ctx* ctx, int bs, int n, const int32_t* rowptr, const 
     return 0;
 }
 
-int hemo_bsr_spmv(hemo_ctx* ctx, int bs, int n, const int32_t* rowptr, const int32_t* col, const double* val,
-                  const double* x, double* y) {
+int hemo_bsr_spmv(hemo_ctx* ctx, int bs, int n, const int32_t* rowptr, const int32_t* col, const areal* val,
+                  const areal* x, areal* y) {
     return hemo_bsr_spmv_ex(ctx, bs, n, rowptr, col, val, x, 1.0, nullptr, y);
 }
 

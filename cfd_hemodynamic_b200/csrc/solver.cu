@@ -25,16 +25,18 @@ int hemo_amg_numeric_shift(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift);
 __global__ void __launch_bounds__(256)
 k_extract_a00(int64_t nnz_node, const int32_t* __restrict__ nrowptr, const int32_t* __restrict__ rowof,
               const int32_t* __restrict__ ncol, const uint8_t* __restrict__ mask,
-              const double* __restrict__ vals, double* __restrict__ out) {
+              const double* __restrict__ vals, areal* __restrict__ out) {
     const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nnz_node) return;
     const int i = rowof[s];
     if (mask) {
         const int j = ncol[s];
         if (mask[i] || mask[j]) {      // ghost node of a partition: identity row/column in the local PC
-            const double d = (i == j) ? 1.0 : 0.0;
-            reinterpret_cast<double2*>(out)[2 * s] = make_double2(d, 0.0);
-            reinterpret_cast<double2*>(out)[2 * s + 1] = make_double2(0.0, d);
+            const areal d = (i == j) ? (areal)1 : (areal)0;
+            areal2 r0v, r1v;
+            r0v.x = d; r0v.y = 0; r1v.x = 0; r1v.y = d;
+            reinterpret_cast<areal2*>(out)[2 * s] = r0v;
+            reinterpret_cast<areal2*>(out)[2 * s + 1] = r1v;
             return;
         }
     }
@@ -42,17 +44,17 @@ k_extract_a00(int64_t nnz_node, const int32_t* __restrict__ nrowptr, const int32
     const int deg = nrowptr[i + 1] - r0;
     const int t = (int)(s - r0);
     const int64_t ru0 = 6 * (int64_t)r0, ru1 = ru0 + 3 * deg;
-    double2 a, b;
-    a.x = vals[ru0 + 2 * t]; a.y = vals[ru0 + 2 * t + 1];
-    b.x = vals[ru1 + 2 * t]; b.y = vals[ru1 + 2 * t + 1];
-    reinterpret_cast<double2*>(out)[2 * s] = a;
-    reinterpret_cast<double2*>(out)[2 * s + 1] = b;
+    areal2 a, b;
+    a.x = (areal)vals[ru0 + 2 * t]; a.y = (areal)vals[ru0 + 2 * t + 1];
+    b.x = (areal)vals[ru1 + 2 * t]; b.y = (areal)vals[ru1 + 2 * t + 1];
+    reinterpret_cast<areal2*>(out)[2 * s] = a;
+    reinterpret_cast<areal2*>(out)[2 * s + 1] = b;
 }
 
 // pressure Laplacian with identity rows/cols on Dirichlet pressure dofs
 __global__ void __launch_bounds__(256)
 k_lap_with_bc(int n, int64_t nnz_node, const int32_t* __restrict__ rowof, const int32_t* __restrict__ ncol,
-              const double* __restrict__ lap, const uint8_t* __restrict__ dofflag, double* __restrict__ out) {
+              const double* __restrict__ lap, const uint8_t* __restrict__ dofflag, areal* __restrict__ out) {
     const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nnz_node) return;
     double v = lap[s];
@@ -61,7 +63,12 @@ k_lap_with_bc(int n, int64_t nnz_node, const int32_t* __restrict__ rowof, const 
         const bool fi = dofflag[2 * (int64_t)n + i] != 0, fj = dofflag[2 * (int64_t)n + j] != 0;
         if (fi || fj) v = (i == j) ? 1.0 : 0.0;
     }
-    out[s] = v;
+    out[s] = (areal)v;
+}
+
+__global__ void k_areal_to_double(int64_t n, const areal* __restrict__ x, double* __restrict__ y) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) y[i] = (double)x[i];
 }
 
 // x[node*bs + k] = 0 on masked nodes
@@ -214,8 +221,8 @@ extern "C" int hemo_amg_get_level_values(hemo_ctx* ctx, int which, int level, do
     if (!amg.ready || level < 0 || level >= amg.nlev) return HEMO_EINVAL;
     const int64_t cnt = amg.op[level].nnzb * amg.bs * amg.bs;
     if (capacity < cnt) return HEMO_EINVAL;
-    HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(vals_dev, amg.op[level].val, sizeof(double) * cnt, cudaMemcpyDeviceToDevice,
-                                         ctx->stream));
+    k_areal_to_double<<<hemo_grid(cnt, 256), 256, 0, ctx->stream>>>(cnt, amg.op[level].val, vals_dev);
+    HEMO_LAUNCH_CHECK(ctx);
     return 0;
 }
 

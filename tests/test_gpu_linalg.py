@@ -90,7 +90,8 @@ def test_galerkin_product_and_vcycle(setup):
     vals1 = h.amg_level_values(0, 1, Cpat.nnz * 4).cpu().numpy().reshape(-1, 2, 2)
     Ac_gpu = sp.bsr_matrix((vals1, Cpat.indices, Cpat.indptr), shape=Ac_ref.shape).tocsr()
     err = abs(Ac_gpu - Ac_ref).max() / abs(Ac_ref).max()
-    assert err < 1e-13, err
+    # the hierarchies are stored in single precision (fp64 accumulation): DESIGN.md §5
+    assert err < 5e-7, err
     # V-cycle is a contraction on A00 e = r
     rng = np.random.default_rng(3)
     b = rng.standard_normal(2 * n)
