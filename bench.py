@@ -383,8 +383,8 @@ def main():
         1: 12 * E + 8 * E + 56 * n + 648 * E,             # cells, h, nodal gathers, element matrices out
         2: 648 * E + 36 * E + 12 * nnz_node + 72 * nnz_node,
         3: 12 * E + 8 * E + 56 * n + 72 * E,
-        4: 36 * nnz_node + 4 * n + 112 * n,               # A00 BSR2 values + cols + rowptr + 7 vectors of 2n
-        5: 12 * nnz_node + 4 * n + 56 * n,
+        4: 20 * nnz_node + 4 * n + 56 * n,                # A00 BSR2 fp32 values + cols + rowptr + 7 fp32 vectors of 2n
+        5: 8 * nnz_node + 4 * n + 28 * n,
         6: None, 7: None,
         8: None,
     }

@@ -166,6 +166,7 @@ struct hemo_ctx {
     double schur_mass_coef = 0.0, schur_lap_coef = 0.0;
     HemoAmg amg[2];
     const double* mass = nullptr;   // lumped pressure mass (borrowed, n)
+    areal2* a01 = nullptr;          // nnz_node: compact copy of the A01 block (u rows x p cols) for the PC
     uint8_t* pc_mask = nullptr;     // n: nodes excluded from the local preconditioner (ghosts)
     double* kry_coef = nullptr;     // device scratch for hemo_vec_maxpy coefficients (512)
     // CUDA graph of one preconditioner application (captured per hemo_pc_setup)

@@ -25,10 +25,21 @@ int hemo_amg_numeric_shift(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift);
 __global__ void __launch_bounds__(256)
 k_extract_a00(int64_t nnz_node, const int32_t* __restrict__ nrowptr, const int32_t* __restrict__ rowof,
               const int32_t* __restrict__ ncol, const uint8_t* __restrict__ mask,
-              const double* __restrict__ vals, areal* __restrict__ out) {
+              const double* __restrict__ vals, areal* __restrict__ out, areal2* __restrict__ a01) {
     const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nnz_node) return;
     const int i = rowof[s];
+    {
+        // compact single-precision copy of A01 (rows u_x, u_y of node i, pressure column of node j)
+        const int r0 = nrowptr[i];
+        const int deg = nrowptr[i + 1] - r0;
+        const int t = (int)(s - r0);
+        const int64_t ru0 = 6 * (int64_t)r0, ru1 = ru0 + 3 * deg;
+        areal2 g;
+        g.x = (areal)vals[ru0 + 2 * deg + t];
+        g.y = (areal)vals[ru1 + 2 * deg + t];
+        a01[s] = g;
+    }
     if (mask) {
         const int j = ncol[s];
         if (mask[i] || mask[j]) {      // ghost node of a partition: identity row/column in the local PC
@@ -76,6 +87,33 @@ __global__ void k_mask_nodes(int n, int bs, const uint8_t* __restrict__ mask, do
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !mask[i]) return;
     for (int k = 0; k < bs; ++k) x[(int64_t)i * bs + k] = 0.0;
+}
+
+// t_u = r_u - A01 z_p on the compact single-precision copy of A01 (4 lanes per node row)
+__global__ void __launch_bounds__(256)
+k_a01_residual(int n, const int32_t* __restrict__ nrowptr, const int32_t* __restrict__ ncol,
+               const areal2* __restrict__ a01, const double* __restrict__ zp, const double* __restrict__ ru,
+               double* __restrict__ tu) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt >> 2, lane = gt & 3;
+    const bool ok = i < n;
+    const int r0 = ok ? nrowptr[i] : 0, r1 = ok ? nrowptr[i + 1] : 0;
+    double a0 = 0.0, a1 = 0.0;
+    for (int s = r0 + lane; s < r1; s += 4) {
+        const areal2 g = a01[s];
+        const double z = zp[ncol[s]];
+        a0 = fma((double)g.x, z, a0);
+        a1 = fma((double)g.y, z, a1);
+    }
+#pragma unroll
+    for (int o = 2; o > 0; o >>= 1) {
+        a0 += __shfl_down_sync(0xffffffffu, a0, o, 4);
+        a1 += __shfl_down_sync(0xffffffffu, a1, o, 4);
+    }
+    if (ok && lane == 0) {
+        tu[2 * (int64_t)i] = ru[2 * (int64_t)i] - a0;
+        tu[2 * (int64_t)i + 1] = ru[2 * (int64_t)i + 1] - a1;
+    }
 }
 
 // z_p = c_m t_p / mass + c_L q_p ; Dirichlet pressure dofs: z_p = r_p
@@ -190,11 +228,12 @@ extern "C" int hemo_pc_setup(hemo_ctx* ctx, const double* vals_dev, const double
         if ((rc = hemo_alloc(ctx, &ctx->pc_tmp_u2, (size_t)2 * n))) return rc;
         if ((rc = hemo_alloc(ctx, &ctx->pc_tmp_p, (size_t)n))) return rc;
         if ((rc = hemo_alloc(ctx, &ctx->pc_tmp_p2, (size_t)n))) return rc;
+        if ((rc = hemo_alloc(ctx, &ctx->a01, (size_t)ctx->nnz_node))) return rc;
         if ((rc = hemo_alloc(ctx, &ctx->pc_in, (size_t)3 * n + 32))) return rc;
         if ((rc = hemo_alloc(ctx, &ctx->pc_out, (size_t)3 * n + 32))) return rc;
     }
     k_extract_a00<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(ctx->nnz_node, ctx->nrowptr, ctx->rowof, ctx->ncol,
-                                                                 ctx->pc_mask, vals_dev, ctx->amg[0].op[0].val);
+                                                                 ctx->pc_mask, vals_dev, ctx->amg[0].op[0].val, ctx->a01);
     HEMO_LAUNCH_CHECK(ctx);
     if ((rc = hemo_amg_numeric_shift(ctx, &ctx->amg[0], 0.0))) return rc;
     if (lap_vals_dev) {
@@ -251,7 +290,8 @@ static int pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_
     if (ctx->opts.project_pressure && (rc = hemo_remove_mean(ctx, n, zp))) return rc;
     }   // else: z_p was provided by the caller (global pressure solve of the multi-GPU driver)
     // t_u = r_u - A01 z_p
-    if ((rc = hemo_spmv_block(ctx, 1, 2, vals_dev, nullptr, zp, -1.0, ru, nullptr, tu, nullptr))) return rc;
+    k_a01_residual<<<hemo_grid((int64_t)n * 4, 256), 256, 0, st>>>(n, ctx->nrowptr, ctx->ncol, ctx->a01, zp, ru, tu);
+    HEMO_LAUNCH_CHECK(ctx);
     if (ctx->pc_mask) {
         k_mask_nodes<<<hemo_grid(n, 256), 256, 0, st>>>(n, 2, ctx->pc_mask, tu);
         HEMO_LAUNCH_CHECK(ctx);
@@ -467,7 +507,7 @@ extern "C" int hemo_ctx_destroy(hemo_ctx* ctx) {
     hemo_amg_free(&ctx->amg[0]); hemo_amg_free(&ctx->amg[1]);
     if (ctx->pc_graph_exec) cudaGraphExecDestroy(ctx->pc_graph_exec);
     if (ctx->pc_graph) cudaGraphDestroy(ctx->pc_graph);
-    cudaFree(ctx->pc_in); cudaFree(ctx->pc_out); cudaFree(ctx->pc_mask); cudaFree(ctx->kry_coef);
+    cudaFree(ctx->pc_in); cudaFree(ctx->pc_out); cudaFree(ctx->pc_mask); cudaFree(ctx->kry_coef); cudaFree(ctx->a01);
     cudaFree(ctx->pc_tmp_u); cudaFree(ctx->pc_tmp_u2); cudaFree(ctx->pc_tmp_p); cudaFree(ctx->pc_tmp_p2);
     cudaFree(ctx->kry_V); cudaFree(ctx->kry_Z); cudaFree(ctx->kry_w);
     delete ctx;
