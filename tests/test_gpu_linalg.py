@@ -133,3 +133,56 @@ def test_fgmres_matches_direct_solve(setup):
     assert its < 80, its
     # pressure part has zero mean (null space removed)
     assert abs(y[2 * n:].mean()) < 1e-10 * max(1.0, np.abs(y[2 * n:]).max())
+
+
+def test_multi_gpu_building_blocks(setup):
+    """Per-partition pieces of the multi-GPU driver vs numpy: multi-dot, multi-axpy with
+    squared norm, scaling, node masking."""
+    h, n = setup["hemo"], setup["n"]
+    N = 3 * n
+    ldv = (N + 31) // 32 * 32
+    rng = np.random.default_rng(7)
+    k = 5
+    Vh = np.zeros((k, ldv))
+    Vh[:, :N] = rng.standard_normal((k, N))
+    w = rng.standard_normal(N)
+    V = torch.tensor(Vh.reshape(-1), device=h.device)
+    wd = torch.tensor(w, device=h.device)
+    hh = h.vec_mdot(V, ldv, k, wd)
+    assert np.allclose(hh, Vh[:, :N] @ w, rtol=1e-13, atol=1e-13)
+    nsq = h.vec_maxpy(V, ldv, hh, -1.0, wd, want_normsq=True)
+    ref = w - Vh[:, :N].T @ hh
+    assert np.allclose(wd.cpu().numpy(), ref, rtol=1e-13, atol=1e-13)
+    assert abs(nsq - ref @ ref) <= 1e-12 * (ref @ ref)
+    y = torch.empty_like(wd)
+    h.vec_scale(0.25, wd, y)
+    assert np.allclose(y.cpu().numpy(), 0.25 * ref)
+    mask = np.zeros(n, dtype=np.uint8)
+    mask[::3] = 1
+    h.mask_nodes(torch.tensor(mask, device=h.device), y)
+    yy = y.cpu().numpy()
+    assert np.all(yy[:2 * n].reshape(-1, 2)[mask == 1] == 0) and np.all(yy[2 * n:][mask == 1] == 0)
+    assert np.allclose(yy[2 * n:][mask == 0], 0.25 * ref[2 * n:][mask == 0])
+
+
+def test_masked_preconditioner_ignores_ghost_nodes(setup):
+    """hemo_set_pc_mask: masked nodes get identity rows in the local A00 and a zero correction."""
+    h, n = setup["hemo"], setup["n"]
+    s = _solver(setup)
+    mask = np.zeros(n, dtype=np.uint8)
+    mask[-41:] = 1                                   # the last mesh row plays the ghost layer
+    md = torch.tensor(mask, device=h.device)
+    h.set_pc_mask(md)
+    try:
+        s._first = True
+        s.setup(setup["vals"])
+        rng = np.random.default_rng(9)
+        r = torch.tensor(rng.standard_normal(3 * n), device=h.device)
+        h.mask_nodes(md, r)
+        z = torch.zeros_like(r)
+        h.pc_apply(setup["vals"], r, z)
+        zu = z.cpu().numpy()[:2 * n].reshape(-1, 2)
+        assert np.all(zu[mask == 1] == 0.0)
+        assert np.isfinite(z.cpu().numpy()).all() and np.abs(zu[mask == 0]).max() > 0
+    finally:
+        h.set_pc_mask(None)
