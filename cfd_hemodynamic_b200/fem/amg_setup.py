@@ -65,10 +65,15 @@ def build_hierarchy(L: sp.csr_matrix, dirichlet: np.ndarray, *, max_coarse: int,
         # dense coarse operators lose "strong" couplings: relax the threshold before giving up
         for th in (theta, 0.25 * theta, 0.0):
             S = _strength(A, th)
-            agg, na = _aggregate(S, excl)
+            # vertices without any strong coupling are left to the smoother (no coarse-grid
+            # correction, empty row of P) instead of becoming singleton aggregates
+            lonely = np.diff(S.indptr) == 0
+            agg, na = _aggregate(S, excl | lonely)
             if 0 < na < 0.75 * nl:
                 break
         else:
+            if na == 0:
+                raise RuntimeError(f"AMG coarsening found no couplings at level {lev} ({nl} vertices)")
             raise RuntimeError(f"AMG coarsening stalled at level {lev}: {nl} -> {na}")
         rows = np.nonzero(agg >= 0)[0]
         T = sp.csr_matrix((np.ones(rows.shape[0]), (rows, agg[rows])), shape=(nl, na))
