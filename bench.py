@@ -35,6 +35,12 @@ WORKLOADS = {
     "lid_driven2D_nx1414": dict(scenario="lid_driven2D", nx=1414, mu=0.01, rho=1.0, dt=0.01),
     "lid_driven2D_nx2828": dict(scenario="lid_driven2D", nx=2828, mu=0.01, rho=1.0, dt=0.01),
     "lid_driven2D_nx64": dict(scenario="lid_driven2D", nx=64, mu=0.01, rho=1.0, dt=0.01),
+    # BASELINE.json configs[2..4] on the mapped split-triangle stenosis channel
+    "stenosis_backflow_1m": dict(scenario="stenosis_mesh_variable", res=0.03, dt=1e-3, v_max=100.0),
+    "stenosis_backflow_4m": dict(scenario="stenosis_mesh_variable", res=0.015, dt=1e-3, v_max=100.0),
+    "stenosis_pressure_4m": dict(scenario="stenosis_pressure", res=0.015, dt=1e-3, p_inlet=80.0, R_resistance=10.0),
+    "stenosis_pressure_structured_16m": dict(scenario="stenosis_pressure_structured", res=0.0075, dt=1e-3,
+                                             p_inlet=80.0, R_resistance=10.0),
 }
 CPU_SAMPLE_NX = 64   # bounded CPU sample of the same workload (same physics, coarser mesh)
 
@@ -99,9 +105,17 @@ class ClockSampler:
 
 
 def build_scenario(w, **solver_kw):
-    from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation
-    assert w["scenario"] == "lid_driven2D"
-    return LidDriven2DSimulation("stabilized_schur", w["dt"], 1.0, rho=w["rho"], mu=w["mu"], nx=w["nx"], **solver_kw)
+    if w["scenario"] == "lid_driven2D":
+        from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation
+        return LidDriven2DSimulation("stabilized_schur", w["dt"], 1.0, rho=w["rho"], mu=w["mu"], nx=w["nx"], **solver_kw)
+    if w["scenario"] == "stenosis_mesh_variable":
+        from cfd_hemodynamic_b200.src.scenarios.stenosis_mesh_variable import StenosisMeshVariableSimulation
+        return StenosisMeshVariableSimulation("stabilized_schur_backflow", w["dt"], 1.0, grade="severe",
+                                              v_max=w["v_max"], res=w["res"], **solver_kw)
+    from cfd_hemodynamic_b200.src.scenarios.stenosis_pressure_structured import StenosisPressureStructuredSimulation
+    return StenosisPressureStructuredSimulation("stabilized_schur_pressure_backflow", w["dt"], 1.0, grade="severe",
+                                                p_inlet=w["p_inlet"], R_resistance=w["R_resistance"], res=w["res"],
+                                                **solver_kw)
 
 
 def oracle_steps(w, nx, steps):
@@ -137,6 +151,8 @@ def run_reference(args):
     if rank != 0:
         return
     w = WORKLOADS[args.workload]
+    if w["scenario"] != "lid_driven2D":
+        w = WORKLOADS["lid_driven2D_nx707"]      # the CPU arm is only wired for the default workload
     cores = os.cpu_count() or 1
     for _ in range(min(args.warmup, 1)):
         oracle_steps(w, 16, 1)
@@ -409,7 +425,7 @@ def main():
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample --------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and w["scenario"] == "lid_driven2D":
         cdof, csecs = oracle_steps(w, CPU_SAMPLE_NX, 1)
         cpu = {"value": cdof / csecs, "unit": "DOF-timesteps/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"1 time step of {w['scenario']} at nx={CPU_SAMPLE_NX} ({cdof} DOFs) with the numpy/SciPy "
@@ -420,8 +436,8 @@ def main():
             "metric": "DOF-timesteps/s", "value": value, "unit": "DOF-timesteps/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "solver": "stabilized_schur", "cells": E, "dofs": ndof,
-                       "nnz": nnz, "dt": w["dt"], "mu": w["mu"], "rho": w["rho"],
+            "config": {"workload": args.workload, "solver": sc.solver_name, "cells": E, "dofs": ndof,
+                       "nnz": nnz, "dt": w["dt"], "mu": float(s.mu.value), "rho": float(s.rho.value),
                        "newton_its_per_step": newton / K, "fgmres_its_per_step": ksp / K,
                        "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (one mesh per GPU)",
                        "l2": "inputs larger than L2 (matrix %.0f MB, element buffer %.0f MB vs 126 MB L2)"

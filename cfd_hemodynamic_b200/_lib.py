@@ -86,6 +86,11 @@ SYMBOLS = {
     "hemo_vec_maxpy": (_I, [_VP, _L, _I, _VP, _L, _VP, _D, _VP, C.POINTER(_D)]),
     "hemo_vec_scale": (_I, [_VP, _L, _D, _VP, _VP]),
     "hemo_use_graph": (_I, [_VP, _I]),
+    "hemo_set_schur_mask": (_I, [_VP, _VP]),
+    "hemo_pc_set_schur_operator": (_I, [_VP, _VP, _VP, _VP, _D, _D]),
+    "hemo_amg_set_fine_pattern": (_I, [_VP, _I, _VP, _VP]),
+    "hemo_pc_set_schur_selfp": (_I, [_VP, _VP, _D]),
+    "hemo_pc_set_convection": (_I, [_VP, _VP, _VP, _D]),
     "hemo_pc_setup": (_I, [_VP, _VP, _VP, _VP]),
     "hemo_amg_apply": (_I, [_VP, _I, _VP, _VP, _I]),
     "hemo_amg_get_level_values": (_I, [_VP, _I, _I, _VP, _L]),
@@ -331,6 +336,30 @@ class Hemo:
 
     def use_graph(self, on: bool):
         self._check(self.lib.hemo_use_graph(self._ctx, int(on)), "hemo_use_graph")
+
+    def set_schur_mask(self, node_mask):
+        self._check(self.lib.hemo_set_schur_mask(self._ctx, _ptr(node_mask)), "hemo_set_schur_mask")
+
+    def pc_set_schur_operator(self, x, un, vals, c_u=1.0, coarse_shift=0.0):
+        self._check(self.lib.hemo_pc_set_schur_operator(self._ctx, _ptr(x), _ptr(un), _ptr(vals), float(c_u),
+                                                        float(coarse_shift)),
+                    "hemo_pc_set_schur_operator")
+
+    def amg_set_fine_pattern(self, which, pattern):
+        """pattern: scipy CSR (values ignored) or None to fall back to the node graph."""
+        if pattern is None:
+            self._check(self.lib.hemo_amg_set_fine_pattern(self._ctx, which, None, None), "hemo_amg_set_fine_pattern")
+            return
+        rp = np.ascontiguousarray(pattern.indptr, dtype=np.int32)
+        ci = np.ascontiguousarray(pattern.indices, dtype=np.int32)
+        self._check(self.lib.hemo_amg_set_fine_pattern(self._ctx, which, _np_ptr(rp), _np_ptr(ci)),
+                    "hemo_amg_set_fine_pattern")
+
+    def pc_set_schur_selfp(self, vals, coarse_shift=0.0):
+        self._check(self.lib.hemo_pc_set_schur_selfp(self._ctx, _ptr(vals), float(coarse_shift)), "hemo_pc_set_schur_selfp")
+
+    def pc_set_convection(self, x, un, coef):
+        self._check(self.lib.hemo_pc_set_convection(self._ctx, _ptr(x), _ptr(un), float(coef)), "hemo_pc_set_convection")
 
     def pc_setup(self, vals, lap=None, mass=None):
         if lap is not None:

@@ -642,6 +642,8 @@ void hemo_amg_free(HemoAmg* amg) {
         cudaFree(o.val); cudaFree(o.dinv); cudaFree(o.x); cudaFree(o.b); cudaFree(o.r); cudaFree(o.d);
         o = HemoAmgOp();
     }
+    cudaFree(amg->fine_rowptr); cudaFree(amg->fine_col); cudaFree(amg->fine_rowof);
+    amg->fine_rowptr = amg->fine_col = amg->fine_rowof = nullptr; amg->fine_nnz = 0;
     cudaFree(amg->dense_inv); cudaFree(amg->dense_work); cudaFree(amg->fuse_desc); cudaFree(amg->lmax_dev);
     amg->fuse_desc = nullptr; amg->lmax_dev = nullptr; amg->fuse_level = -1;
     amg->dense_inv = amg->dense_work = nullptr;
@@ -684,6 +686,34 @@ extern "C" int hemo_amg_set_level(hemo_ctx* ctx, int which, int level, int n_fin
     return 0;
 }
 
+__global__ void k_rowof_generic(int n, const int32_t* __restrict__ rowptr, int32_t* __restrict__ rowof) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int s = rowptr[i]; s < rowptr[i + 1]; ++s) rowof[s] = i;
+}
+
+extern "C" int hemo_amg_set_fine_pattern(hemo_ctx* ctx, int which, const int32_t* rowptr_host, const int32_t* col_host) {
+    if (!ctx || which < 0 || which > 1) return HEMO_EINVAL;
+    if (!ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "node graph not set");
+    HemoAmg& amg = ctx->amg[which];
+    cudaFree(amg.fine_rowptr); cudaFree(amg.fine_col); cudaFree(amg.fine_rowof);
+    amg.fine_rowptr = amg.fine_col = amg.fine_rowof = nullptr;
+    amg.fine_nnz = 0;
+    amg.ready = false;
+    if (!rowptr_host || !col_host) return 0;
+    const int n = ctx->n;
+    const int64_t nnz = rowptr_host[n];
+    int rc;
+    if ((rc = hemo_upload(ctx, &amg.fine_rowptr, rowptr_host, (size_t)n + 1, false))) return rc;
+    if ((rc = hemo_upload(ctx, &amg.fine_col, col_host, (size_t)nnz, false))) return rc;
+    if ((rc = hemo_alloc(ctx, &amg.fine_rowof, (size_t)nnz))) return rc;
+    k_rowof_generic<<<hemo_grid(n, 256), 256, 0, ctx->stream>>>(n, amg.fine_rowptr, amg.fine_rowof);
+    HEMO_LAUNCH_CHECK(ctx);
+    HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    amg.fine_nnz = nnz;
+    return 0;
+}
+
 extern "C" int hemo_amg_finalize(hemo_ctx* ctx, int which, int n_levels) {
     if (!ctx || which < 0 || which > 1 || n_levels < 1 || n_levels > HEMO_MAX_LEVELS) return HEMO_EINVAL;
     if (!ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "node graph not set");
@@ -696,6 +726,7 @@ extern "C" int hemo_amg_finalize(hemo_ctx* ctx, int which, int n_levels) {
         HemoAmgOp& o = amg.op[l];
         if (l == 0) {
             o.n = ctx->n; o.nnzb = ctx->nnz_node; o.rowptr = ctx->nrowptr; o.col = ctx->ncol;
+            if (amg.fine_rowptr) { o.nnzb = amg.fine_nnz; o.rowptr = amg.fine_rowptr; o.col = amg.fine_col; }
         } else {
             const HemoAmgLevel& L = amg.lev[l - 1];
             if (L.n_coarse <= 0) HEMO_FAIL(ctx, HEMO_ESTATE, "missing AMG level");
@@ -717,8 +748,8 @@ extern "C" int hemo_amg_finalize(hemo_ctx* ctx, int which, int n_levels) {
     if ((rc = hemo_alloc(ctx, &amg.dense_work, (size_t)Nc * Nc + 8))) return rc;
     if ((rc = hemo_ensure_reduce(ctx, (size_t)hemo_grid(ctx->n, 256) + 1184 * 8, 512))) return rc;
     if ((rc = hemo_alloc(ctx, &amg.lmax_dev, (size_t)HEMO_MAX_LEVELS))) return rc;
-    if (which == 0) {
-        // the velocity hierarchy is re-formed every Newton iteration: precompute its gather lists
+    {
+        // hierarchies are re-formed for every new Jacobian: precompute their gather lists
         for (int l = 0; l + 1 < n_levels; ++l) {
             HemoAmgLevel& L = amg.lev[l];
             const HemoAmgOp& A = amg.op[l];

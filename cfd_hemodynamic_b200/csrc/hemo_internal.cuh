@@ -88,6 +88,9 @@ struct HemoCoarseLevel {
 #define HEMO_FUSE_MAX_NODES 256    // levels at or below this size run inside one CTA
 
 struct HemoAmg {
+    // optional level-0 pattern that differs from the mesh node graph (SELFP: distance-2 graph)
+    int32_t *fine_rowptr = nullptr, *fine_col = nullptr, *fine_rowof = nullptr;
+    int64_t fine_nnz = 0;
     int fuse_level = -1;           // first level handled by the fused kernel (-1: none)
     HemoCoarseLevel* fuse_desc = nullptr;   // device array, one per level from fuse_level
     double* lmax_dev = nullptr;    // HEMO_MAX_LEVELS Gershgorin bounds kept on the device
@@ -166,6 +169,10 @@ struct hemo_ctx {
     double schur_mass_coef = 0.0, schur_lap_coef = 0.0;
     HemoAmg amg[2];
     const double* mass = nullptr;   // lumped pressure mass (borrowed, n)
+    uint8_t* schur_mask = nullptr;  // n: identity rows/cols of the assembled Schur operator (open / ghost nodes)
+    double* schur_tmp = nullptr;    // nnz_node scratch
+    areal* npconv = nullptr;        // nnz_node: pressure-space convection matrix N_p (PCD term of the Schur approx.)
+    double npconv_coef = 0.0;       // 0: term disabled
     areal2* a01 = nullptr;          // nnz_node: compact copy of the A01 block (u rows x p cols) for the PC
     uint8_t* pc_mask = nullptr;     // n: nodes excluded from the local preconditioner (ghosts)
     double* kry_coef = nullptr;     // device scratch for hemo_vec_maxpy coefficients (512)

@@ -116,14 +116,30 @@ k_a01_residual(int n, const int32_t* __restrict__ nrowptr, const int32_t* __rest
     }
 }
 
-// z_p = c_m t_p / mass + c_L q_p ; Dirichlet pressure dofs: z_p = r_p
-__global__ void k_schur_combine(int n, double cm, double cl, const double* __restrict__ tp,
+// c = N_p q on the node graph (4 lanes per row)
+__global__ void __launch_bounds__(256)
+k_node_spmv_scalar(int n, const int32_t* __restrict__ nrowptr, const int32_t* __restrict__ ncol,
+                   const areal* __restrict__ val, const double* __restrict__ q, double* __restrict__ out) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt >> 2, lane = gt & 3;
+    const bool ok = i < n;
+    const int r0 = ok ? nrowptr[i] : 0, r1 = ok ? nrowptr[i + 1] : 0;
+    double a = 0.0;
+    for (int s = r0 + lane; s < r1; s += 4) a = fma((double)val[s], q[ncol[s]], a);
+    a += __shfl_down_sync(0xffffffffu, a, 2, 4);
+    a += __shfl_down_sync(0xffffffffu, a, 1, 4);
+    if (ok && lane == 0) out[i] = a;
+}
+
+// z_p = (c_m t_p + c_c (N_p q)) / mass + c_L q_p ; Dirichlet pressure dofs: z_p = r_p
+__global__ void k_schur_combine(int n, double cm, double cl, double cc, const double* __restrict__ tp,
                                 const double* __restrict__ mass, const double* __restrict__ qp,
-                                const uint8_t* __restrict__ dofflag, const double* __restrict__ rp,
-                                double* __restrict__ zp) {
+                                const double* __restrict__ conv, const uint8_t* __restrict__ dofflag,
+                                const double* __restrict__ rp, double* __restrict__ zp) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double v = cm * tp[i] / mass[i] + cl * qp[i];
+    if (conv) v += cc * conv[i] / mass[i];
     if (dofflag && dofflag[2 * (int64_t)n + i]) v = rp[i];
     zp[i] = v;
 }
@@ -236,9 +252,9 @@ extern "C" int hemo_pc_setup(hemo_ctx* ctx, const double* vals_dev, const double
                                                                  ctx->pc_mask, vals_dev, ctx->amg[0].op[0].val, ctx->a01);
     HEMO_LAUNCH_CHECK(ctx);
     if ((rc = hemo_amg_numeric_shift(ctx, &ctx->amg[0], 0.0))) return rc;
+    if (mass_dev) ctx->mass = mass_dev;
     if (lap_vals_dev) {
-        if (!mass_dev) return HEMO_EINVAL;
-        ctx->mass = mass_dev;
+        if (!ctx->mass) return HEMO_EINVAL;
         k_lap_with_bc<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(n, ctx->nnz_node, ctx->rowof, ctx->ncol, lap_vals_dev,
                                                                      ctx->have_bc ? ctx->dofflag : nullptr,
                                                                      ctx->amg[1].op[0].val);
@@ -284,8 +300,17 @@ static int pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_
     }
     if (ctx->opts.project_pressure && (rc = hemo_remove_mean(ctx, n, tp))) return rc;
     if ((rc = hemo_amg_vcycle(ctx, &ctx->amg[1], tp, qp, ctx->opts.amg_cycles_p))) return rc;
-    k_schur_combine<<<hemo_grid(n, 256), 256, 0, st>>>(n, ctx->opts.schur_mass_coef, ctx->opts.schur_lap_coef, tp,
-                                                       ctx->mass, qp, ctx->have_bc ? ctx->dofflag : nullptr, rp, zp);
+    const bool pcd = ctx->npconv_coef != 0.0 && ctx->npconv;
+    if (pcd) {
+        // pressure convection-diffusion term: S^-1 ~ 2 Mp^-1 Fp Lp^-1 with Fp = rho/dt Mp + rho/2 Np + mu/2 Lp
+        k_node_spmv_scalar<<<hemo_grid((int64_t)n * 4, 256), 256, 0, st>>>(n, ctx->nrowptr, ctx->ncol, ctx->npconv, qp,
+                                                                          ctx->pc_tmp_u2);
+        HEMO_LAUNCH_CHECK(ctx);
+    }
+    k_schur_combine<<<hemo_grid(n, 256), 256, 0, st>>>(n, ctx->opts.schur_mass_coef, ctx->opts.schur_lap_coef,
+                                                       ctx->npconv_coef, tp, ctx->mass, qp,
+                                                       pcd ? ctx->pc_tmp_u2 : nullptr,
+                                                       ctx->have_bc ? ctx->dofflag : nullptr, rp, zp);
     HEMO_LAUNCH_CHECK(ctx);
     if (ctx->opts.project_pressure && (rc = hemo_remove_mean(ctx, n, zp))) return rc;
     }   // else: z_p was provided by the caller (global pressure solve of the multi-GPU driver)
@@ -507,6 +532,7 @@ extern "C" int hemo_ctx_destroy(hemo_ctx* ctx) {
     hemo_amg_free(&ctx->amg[0]); hemo_amg_free(&ctx->amg[1]);
     if (ctx->pc_graph_exec) cudaGraphExecDestroy(ctx->pc_graph_exec);
     if (ctx->pc_graph) cudaGraphDestroy(ctx->pc_graph);
+    cudaFree(ctx->npconv); cudaFree(ctx->schur_mask); cudaFree(ctx->schur_tmp);
     cudaFree(ctx->pc_in); cudaFree(ctx->pc_out); cudaFree(ctx->pc_mask); cudaFree(ctx->kry_coef); cudaFree(ctx->a01);
     cudaFree(ctx->pc_tmp_u); cudaFree(ctx->pc_tmp_u2); cudaFree(ctx->pc_tmp_p); cudaFree(ctx->pc_tmp_p2);
     cudaFree(ctx->kry_V); cudaFree(ctx->kry_Z); cudaFree(ctx->kry_w);

@@ -44,13 +44,17 @@ def _strength(A: sp.csr_matrix, theta: float) -> sp.csr_matrix:
 
 
 def build_hierarchy(L: sp.csr_matrix, dirichlet: np.ndarray, *, max_coarse: int, theta: float = 0.08,
-                    smooth: bool = True, max_levels: int = 14):
+                    smooth: bool = True, max_levels: int = 14, fine_pattern: sp.csr_matrix | None = None):
     """L: scalar P1 Laplacian on the node graph (fine pattern == node graph).
     dirichlet: bool mask of constrained nodes (their rows of P are empty).
     Returns a list of dicts with P, R (csr), AP and C patterns (csr of ones),
     following the level chain n_0 → n_1 → ... until n_l <= max_coarse."""
     n = L.shape[0]
-    fine_pattern = sp.csr_matrix((np.ones(L.nnz), L.indices, L.indptr), shape=L.shape)
+    if fine_pattern is None:
+        fine_pattern = sp.csr_matrix((np.ones(L.nnz), L.indices, L.indptr), shape=L.shape)
+    else:       # level-0 operator lives on a wider pattern than the aggregation graph (SELFP)
+        fine_pattern = sp.csr_matrix((np.ones(fine_pattern.nnz), fine_pattern.indices, fine_pattern.indptr),
+                                     shape=fine_pattern.shape)
     free = (~dirichlet).astype(np.float64)
     K = sp.diags(free) @ L @ sp.diags(free)            # Dirichlet rows/cols removed
     K = (K + sp.diags(dirichlet.astype(np.float64) * L.diagonal())).tocsr()

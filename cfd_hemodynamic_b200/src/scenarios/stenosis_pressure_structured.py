@@ -33,7 +33,7 @@ class StenosisPressureStructuredSimulation(Scenario):
         solver_kwargs = {k: kwargs.pop(k, defaults[k]) for k in solver_keys}
         # tolerances / preconditioner options are forwarded to the solver, the rest is mesh control
         passthrough = {k: kwargs.pop(k) for k in list(kwargs)
-                       if k.startswith(("snes_", "ksp_", "amg_", "cheb_", "schur_")) or k in ("verbose", "device",
+                       if k.startswith(("snes_", "ksp_", "amg_", "cheb_", "schur_", "pc_", "strength_", "smooth_")) or k in ("verbose", "device",
                                                                                              "smooth_prolongator",
                                                                                              "strength_theta")}
         self.mesh_options = kwargs.copy()
@@ -45,6 +45,9 @@ class StenosisPressureStructuredSimulation(Scenario):
             raise ValueError("R_resistance is required for pressure-driven inlet. "
                              "Pass it via CLI: --R_resistance <value>")
         solver_kwargs.update(p_inlet=float(p_inlet) * self.pressure_unit, R_resistance=float(R_resistance))
+        # convection-dominated channel flow: the reference's SELFP matrix is the better Schur
+        # approximation here (13 vs 48 outer iterations with exact sub-solves)
+        passthrough.setdefault("schur_mode", "selfp")
         solver_kwargs.update(passthrough)
         super().__init__(solver_name, self.scenario_name, rho, mu, dt, T, list(f), **solver_kwargs)
         self.mesh.topology.create_connectivity(self.mesh.topology.dim - 1, self.mesh.topology.dim)

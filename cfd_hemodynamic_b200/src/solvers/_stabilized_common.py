@@ -62,9 +62,15 @@ class StabilizedSchurB200(SolverBase):
         # "newton": PCSetUp for every Jacobian like the reference (SNES lag 1);
         # "step": once per time step, later Newton iterations reuse the hierarchy
         self.pc_rebuild = str(kw.pop("pc_rebuild", "step"))
+        # coefficient of the pressure convection-diffusion term of the Schur approximation in
+        # units of rho (1: S^-1 ~ 2 Mp^-1 Fp Lp^-1 with the convective part of Fp; 0: Cahouet-Chabard)
+        self.schur_convection = float(kw.pop("schur_convection", 0.0))
+        # treatment of open (traction) boundary nodes in the pressure operator of the Schur
+        # approximation: "dirichlet" (identity rows) or "natural" (regular rows)
+        self.schur_open = str(kw.pop("schur_open", "dirichlet"))
         self._pc_kw = {k: kw.pop(k) for k in list(kw) if k in (
             "amg_cycles_u", "amg_cycles_p", "cheb_degree", "cheb_ratio", "cheb_degree_pre", "smooth_prolongator",
-            "strength_theta", "schur_mass_coef", "schur_lap_coef")}
+            "strength_theta", "schur_mass_coef", "schur_lap_coef", "schur_mode", "schur_cu")}
         self._rules = kw.pop("quadrature", None)
         self._device_index = int(kw.pop("device", 0))
         # host_only: build spaces / BC tables / facet tables but create no CUDA context
@@ -233,7 +239,7 @@ class StabilizedSchurB200(SolverBase):
         u_nodes = np.nonzero(flag[0:2 * n:2] | flag[1:2 * n:2])[0]
         p_nodes = np.nonzero(flag[2 * n:])[0]
         p_open = np.zeros(0, dtype=np.int64)
-        if self.variant != "schur":
+        if self.variant != "schur" and self.schur_open == "dirichlet":
             # without the all-facet term of stabilized_schur.py:79 the Schur complement sees a
             # Dirichlet-like pressure condition wherever the velocity is free on the boundary
             ext = exterior_facet_indices(self.mesh.topology)
@@ -245,7 +251,7 @@ class StabilizedSchurB200(SolverBase):
             dt=float(self.dt.value), rho=float(self.rho.value), mu=float(self.mu.value),
             restart=self.ksp_restart, max_it=self.ksp_max_it, rtol=self.ksp_rtol,
             project_pressure=self._nullspace, **self._pc_kw)
-        self.linear.setup(self.d_vals)
+        self.linear.setup(self.d_vals, self.d_x, self.d_un)
 
     def _test_nullspace(self) -> bool:
         """nullsp.test(A): is the constant-pressure vector in the kernel of A?
@@ -280,7 +286,9 @@ class StabilizedSchurB200(SolverBase):
         for it in range(self.snes_max_it):
             hemo.assemble_jacobian(x, self.d_un, self.d_vals)
             if it == 0 or self.pc_rebuild == "newton":
-                self.linear.setup(self.d_vals)
+                if self.schur_convection != 0.0:
+                    hemo.pc_set_convection(x, self.d_un, self.schur_convection * float(self.rho.value))
+                self.linear.setup(self.d_vals, x, self.d_un)
             try:
                 kits, _ = self.linear.solve(self.d_vals, f, y)
             except HemoDiverged:

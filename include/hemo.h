@@ -218,6 +218,28 @@ int hemo_vec_scale(hemo_ctx* ctx, int64_t n, double a, const double* x_dev, doub
 /* 1 (default): hemo_pc_setup captures one preconditioner application as a CUDA
  * graph (needs a non-default stream) and hemo_pc_apply replays it; 0: direct launches. */
 int hemo_use_graph(hemo_ctx* ctx, int on);
+/* Assembled Schur operator (alternative to the constant Laplacian): level 0 of the pressure
+ * hierarchy becomes  S_hat = A11 + K_kappa  with A11 the PSPG block of the current Jacobian
+ * (exact, like SELFP keeps it: src/solvers/stabilized_schur.py:235) and K_kappa a pressure
+ * Laplacian with the per-cell coefficient kappa = 1 / (2 rho (1/dt + c_u |u_m| / h)) standing for
+ * 1/2 B A00^-1 B^T; the hierarchy is re-formed numerically.  Nodes flagged by
+ * hemo_set_schur_mask (open boundaries, ghosts) and Dirichlet pressure dofs get identity rows.
+ * Use with schur_lap_coef = 1. */
+int hemo_set_schur_mask(hemo_ctx* ctx, const uint8_t* node_mask_dev);
+int hemo_pc_set_schur_operator(hemo_ctx* ctx, const double* x_dev, const double* un_dev,
+                               const double* vals_dev, double c_u, double coarse_shift);
+/* SELFP Schur preconditioning matrix like the reference's (src/solvers/stabilized_schur.py:235):
+ * Sp = A11 - A10 diag(A00)^-1 A01, formed on the device from the monolithic Jacobian on the
+ * distance-2 node graph given with hemo_amg_set_fine_pattern(which = 1) (host CSR arrays, before
+ * hemo_amg_set_level / hemo_amg_finalize), then the pressure hierarchy is re-formed numerically.
+ * Use with schur_mass_coef = 0, schur_lap_coef = 1. */
+int hemo_amg_set_fine_pattern(hemo_ctx* ctx, int which, const int32_t* rowptr_host, const int32_t* col_host);
+int hemo_pc_set_schur_selfp(hemo_ctx* ctx, const double* vals_dev, double coarse_shift);
+/* Optional pressure convection-diffusion term of the Schur approximation: assembles
+ * N_p = int phi_a (u_m . grad phi_b) on the pressure space from the current state and adds
+ * coef * Mp^-1 N_p Lp^-1 r to S^-1 r (coef = rho for the mid-point scheme; 0 disables).
+ * Call before hemo_pc_setup. */
+int hemo_pc_set_convection(hemo_ctx* ctx, const double* x_dev, const double* un_dev, double coef);
 /* z = M^{-1} r (one application of the block preconditioner). */
 int hemo_pc_apply(hemo_ctx* ctx, const double* vals_dev, const double* r_dev, double* z_dev);
 /* KSPSolve: right-preconditioned FGMRES(restart) on J y = b with zero initial
