@@ -318,16 +318,34 @@ __device__ __forceinline__ void row_product(const int32_t* __restrict__ rowptr, 
 #pragma unroll
     for (int k = 0; k < BS; ++k) acc[k] = 0.0;
     const int r0 = ok ? rowptr[i] : 0, r1 = ok ? rowptr[i + 1] : 0;
-    for (int t = r0 + lane; t < r1; t += 4) {
-        const int j = col[t];
+    // The dependent chain col -> x is what bounds this kernel (rows are short): issue the
+    // column loads of three strided entries first, then the value / vector loads.
+    for (int t = r0 + lane; t < r1; t += 12) {
+        const int t1 = t + 4, t2 = t + 8;
+        const bool p1 = t1 < r1, p2 = t2 < r1;
+        const int j0 = col[t];
+        const int j1 = p1 ? col[t1] : j0;
+        const int j2 = p2 ? col[t2] : j0;
         if (BS == 1) {
-            acc[0] = fma((double)val[t], (double)x[j], acc[0]);
+            const double v0 = (double)val[t], x0 = (double)x[j0];
+            const double v1 = p1 ? (double)val[t1] : 0.0, x1 = (double)x[j1];
+            const double v2 = p2 ? (double)val[t2] : 0.0, x2 = (double)x[j2];
+            acc[0] = fma(v0, x0, acc[0]);
+            acc[0] = fma(v1, x1, acc[0]);
+            acc[0] = fma(v2, x2, acc[0]);
         } else {
-            const areal2 xv = reinterpret_cast<const areal2*>(x)[j];
-            const areal2 v0 = reinterpret_cast<const areal2*>(val)[2 * (int64_t)t];
-            const areal2 v1 = reinterpret_cast<const areal2*>(val)[2 * (int64_t)t + 1];
-            acc[0] += (double)v0.x * xv.x + (double)v0.y * xv.y;
-            acc[BS - 1] += (double)v1.x * xv.x + (double)v1.y * xv.y;
+            const areal2* v2p = reinterpret_cast<const areal2*>(val);
+            const areal2* x2p = reinterpret_cast<const areal2*>(x);
+            const areal2 a0 = v2p[2 * (int64_t)t], b0 = v2p[2 * (int64_t)t + 1], xa = x2p[j0];
+            areal2 a1, b1, a2, b2;
+            a1.x = a1.y = b1.x = b1.y = a2.x = a2.y = b2.x = b2.y = 0;
+            if (p1) { a1 = v2p[2 * (int64_t)t1]; b1 = v2p[2 * (int64_t)t1 + 1]; }
+            if (p2) { a2 = v2p[2 * (int64_t)t2]; b2 = v2p[2 * (int64_t)t2 + 1]; }
+            const areal2 xb = x2p[j1], xc = x2p[j2];
+            acc[0] += (double)a0.x * xa.x + (double)a0.y * xa.y + (double)a1.x * xb.x + (double)a1.y * xb.y +
+                      (double)a2.x * xc.x + (double)a2.y * xc.y;
+            acc[BS - 1] += (double)b0.x * xa.x + (double)b0.y * xa.y + (double)b1.x * xb.x + (double)b1.y * xb.y +
+                           (double)b2.x * xc.x + (double)b2.y * xc.y;
         }
     }
 #pragma unroll
@@ -380,26 +398,43 @@ k_cheb_step(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict
     }
 }
 
-// y[I] (+)= sum_t w_t x[col_t]  with bs components per node (restriction / prolongation)
+// y[I] (+)= sum_t w_t x[col_t]  with bs components per node (restriction / prolongation);
+// 4 lanes per row, column loads of three strided entries issued first
 template <int BS, bool ADD>
 __global__ void __launch_bounds__(256)
 k_transfer(int nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
            const double* __restrict__ w, const areal* __restrict__ x, areal* __restrict__ y) {
-    const int I = blockIdx.x * blockDim.x + threadIdx.x;
-    if (I >= nrows) return;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int I = gt >> 2, lane = gt & 3;
+    const bool ok = I < nrows;
+    const int r0 = ok ? rowptr[I] : 0, r1 = ok ? rowptr[I + 1] : 0;
     double acc[BS];
 #pragma unroll
     for (int k = 0; k < BS; ++k) acc[k] = 0.0;
-    for (int t = rowptr[I]; t < rowptr[I + 1]; ++t) {
-        const int j = col[t];
-        const double wt = w[t];
+    for (int t = r0 + lane; t < r1; t += 12) {
+        const int t1 = t + 4, t2 = t + 8;
+        const bool p1 = t1 < r1, p2 = t2 < r1;
+        const int j0 = col[t];
+        const int j1 = p1 ? col[t1] : j0;
+        const int j2 = p2 ? col[t2] : j0;
+        const double w0 = w[t], w1 = p1 ? w[t1] : 0.0, w2 = p2 ? w[t2] : 0.0;
 #pragma unroll
-        for (int k = 0; k < BS; ++k) acc[k] += wt * x[(int64_t)j * BS + k];
+        for (int k = 0; k < BS; ++k) {
+            const double x0 = (double)x[(int64_t)j0 * BS + k], x1 = (double)x[(int64_t)j1 * BS + k],
+                         x2 = (double)x[(int64_t)j2 * BS + k];
+            acc[k] += w0 * x0 + w1 * x1 + w2 * x2;
+        }
     }
 #pragma unroll
     for (int k = 0; k < BS; ++k) {
-        if (ADD) y[(int64_t)I * BS + k] += acc[k];
-        else y[(int64_t)I * BS + k] = acc[k];
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1, 4);
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2, 4);
+    }
+    if (ok && lane < BS) {
+        const double v = (lane == 0) ? acc[0] : acc[BS - 1];
+        const int64_t q = (int64_t)I * BS + lane;
+        if (ADD) y[q] = (areal)((double)y[q] + v);
+        else y[q] = (areal)v;
     }
 }
 
@@ -926,10 +961,10 @@ static int vcycle_t(hemo_ctx* ctx, HemoAmg* amg, int l, const areal* b, areal* x
     if ((rc = hemo_bsr_spmv_ex(ctx, BS, A.n, A.rowptr, A.col, A.val, x, -1.0, b, A.r))) return rc;
     const HemoAmgLevel& L = amg->lev[l];
     HemoAmgOp& C = amg->op[l + 1];
-    k_transfer<BS, false><<<hemo_grid(C.n, 256), 256, 0, st>>>(C.n, L.r_rowptr, L.r_col, L.r_val, A.r, C.b);
+    k_transfer<BS, false><<<hemo_grid((int64_t)C.n * 4, 256), 256, 0, st>>>(C.n, L.r_rowptr, L.r_col, L.r_val, A.r, C.b);
     HEMO_LAUNCH_CHECK(ctx);
     if ((rc = vcycle_t<BS>(ctx, amg, l + 1, C.b, C.x, true))) return rc;
-    k_transfer<BS, true><<<hemo_grid(A.n, 256), 256, 0, st>>>(A.n, L.p_rowptr, L.p_col, L.p_val, C.x, x);
+    k_transfer<BS, true><<<hemo_grid((int64_t)A.n * 4, 256), 256, 0, st>>>(A.n, L.p_rowptr, L.p_col, L.p_val, C.x, x);
     HEMO_LAUNCH_CHECK(ctx);
     if ((rc = smooth_t<BS>(ctx, A, b, x, false, degree, ratio))) return rc;
     return 0;

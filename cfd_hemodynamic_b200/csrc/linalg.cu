@@ -155,16 +155,33 @@ k_bsr_spmv(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     const bool ok = i < n;
     const int r0 = ok ? rowptr[i] : 0, r1 = ok ? rowptr[i + 1] : 0;
     double a0 = 0.0, a1 = 0.0;
-    for (int t = r0 + lane; t < r1; t += 4) {
-        const int j = col[t];
+    // column loads of three strided entries first (the col -> x chain bounds short rows)
+    for (int t = r0 + lane; t < r1; t += 12) {
+        const int t1 = t + 4, t2 = t + 8;
+        const bool p1 = t1 < r1, p2 = t2 < r1;
+        const int j0 = col[t];
+        const int j1 = p1 ? col[t1] : j0;
+        const int j2 = p2 ? col[t2] : j0;
         if (BS == 1) {
-            a0 += (double)val[t] * (double)x[j];
+            const double v0 = (double)val[t], x0 = (double)x[j0];
+            const double v1 = p1 ? (double)val[t1] : 0.0, x1 = (double)x[j1];
+            const double v2 = p2 ? (double)val[t2] : 0.0, x2 = (double)x[j2];
+            a0 = fma(v0, x0, a0);
+            a0 = fma(v1, x1, a0);
+            a0 = fma(v2, x2, a0);
         } else {
-            const areal2 xv = reinterpret_cast<const areal2*>(x)[j];
-            const areal2 v0 = reinterpret_cast<const areal2*>(val)[2 * (int64_t)t];
-            const areal2 v1 = reinterpret_cast<const areal2*>(val)[2 * (int64_t)t + 1];
-            a0 += (double)v0.x * xv.x + (double)v0.y * xv.y;
-            a1 += (double)v1.x * xv.x + (double)v1.y * xv.y;
+            const areal2* v2p = reinterpret_cast<const areal2*>(val);
+            const areal2* x2p = reinterpret_cast<const areal2*>(x);
+            const areal2 c0 = v2p[2 * (int64_t)t], d0 = v2p[2 * (int64_t)t + 1], xa = x2p[j0];
+            areal2 c1, d1, c2, d2;
+            c1.x = c1.y = d1.x = d1.y = c2.x = c2.y = d2.x = d2.y = 0;
+            if (p1) { c1 = v2p[2 * (int64_t)t1]; d1 = v2p[2 * (int64_t)t1 + 1]; }
+            if (p2) { c2 = v2p[2 * (int64_t)t2]; d2 = v2p[2 * (int64_t)t2 + 1]; }
+            const areal2 xb = x2p[j1], xc = x2p[j2];
+            a0 += (double)c0.x * xa.x + (double)c0.y * xa.y + (double)c1.x * xb.x + (double)c1.y * xb.y +
+                  (double)c2.x * xc.x + (double)c2.y * xc.y;
+            a1 += (double)d0.x * xa.x + (double)d0.y * xa.y + (double)d1.x * xb.x + (double)d1.y * xb.y +
+                  (double)d2.x * xc.x + (double)d2.y * xc.y;
         }
     }
 #pragma unroll
