@@ -677,6 +677,8 @@ void hemo_amg_free(HemoAmg* amg) {
         cudaFree(o.val); cudaFree(o.dinv); cudaFree(o.x); cudaFree(o.b); cudaFree(o.r); cudaFree(o.d);
         o = HemoAmgOp();
     }
+    if (amg->apply_exec) { cudaGraphExecDestroy(amg->apply_exec); amg->apply_exec = nullptr; }
+    amg->apply_valid = false;
     cudaFree(amg->fine_rowptr); cudaFree(amg->fine_col); cudaFree(amg->fine_rowof);
     amg->fine_rowptr = amg->fine_col = amg->fine_rowof = nullptr; amg->fine_nnz = 0;
     cudaFree(amg->dense_inv); cudaFree(amg->dense_work); cudaFree(amg->fuse_desc); cudaFree(amg->lmax_dev);
@@ -889,6 +891,7 @@ static int amg_numeric_t(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift) {
 // coarse_shift is carried in amg via dense_n sign-free field; passed explicitly by the caller
 int hemo_amg_numeric_shift(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift) {
     if (!amg->ready) HEMO_FAIL(ctx, HEMO_ESTATE, "AMG hierarchy not finalized");
+    amg->apply_valid = false;      // smoother coefficients are baked into a captured cycle
     if (amg->bs == 2) return amg_numeric_t<2>(ctx, amg, coarse_shift);
     return amg_numeric_t<1>(ctx, amg, coarse_shift);
 }

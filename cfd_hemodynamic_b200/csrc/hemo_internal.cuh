@@ -88,6 +88,13 @@ struct HemoCoarseLevel {
 #define HEMO_FUSE_MAX_NODES 256    // levels at or below this size run inside one CTA
 
 struct HemoAmg {
+    // cached CUDA graph of hemo_amg_apply(b, x, ncycles) (replicated global pressure solve)
+    cudaGraphExec_t apply_exec = nullptr;
+    const double* apply_b = nullptr;
+    double* apply_x = nullptr;
+    int apply_cycles = 0;
+    int64_t apply_nodes = 0;
+    bool apply_valid = false;
     // optional level-0 pattern that differs from the mesh node graph (SELFP: distance-2 graph)
     int32_t *fine_rowptr = nullptr, *fine_col = nullptr, *fine_rowof = nullptr;
     int64_t fine_nnz = 0;

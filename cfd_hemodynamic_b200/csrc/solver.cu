@@ -267,7 +267,44 @@ extern "C" int hemo_pc_setup(hemo_ctx* ctx, const double* vals_dev, const double
 
 extern "C" int hemo_amg_apply(hemo_ctx* ctx, int which, const double* b_dev, double* x_dev, int ncycles) {
     if (!ctx || which < 0 || which > 1 || !b_dev || !x_dev) return HEMO_EINVAL;
-    return hemo_amg_vcycle(ctx, &ctx->amg[which], b_dev, x_dev, ncycles);
+    HemoAmg& amg = ctx->amg[which];
+    if (!ctx->use_graph || ctx->stream == 0 || ctx->capturing)
+        return hemo_amg_vcycle(ctx, &amg, b_dev, x_dev, ncycles);
+    // repeated applications with the same buffers (the replicated global pressure solve of the
+    // multi-GPU driver) replay a captured graph
+    if (amg.apply_valid && amg.apply_exec && amg.apply_b == b_dev && amg.apply_x == x_dev && amg.apply_cycles == ncycles) {
+        HEMO_CHECK_CUDA(ctx, cudaGraphLaunch(amg.apply_exec, ctx->stream));
+        ctx->launches += amg.apply_nodes;
+        return 0;
+    }
+    cudaStream_t st = ctx->stream;
+    HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    const int64_t before = ctx->launches;
+    ctx->capturing = true;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        ctx->capturing = false;
+        cudaGetLastError();
+        return hemo_amg_vcycle(ctx, &amg, b_dev, x_dev, ncycles);
+    }
+    int rc = hemo_amg_vcycle(ctx, &amg, b_dev, x_dev, ncycles);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    ctx->capturing = false;
+    amg.apply_nodes = ctx->launches - before;
+    ctx->launches = before;
+    if (rc != 0 || e != cudaSuccess || !g) {
+        cudaGetLastError();
+        if (g) cudaGraphDestroy(g);
+        if (rc) return rc;
+        return hemo_amg_vcycle(ctx, &amg, b_dev, x_dev, ncycles);
+    }
+    if (amg.apply_exec) { cudaGraphExecDestroy(amg.apply_exec); amg.apply_exec = nullptr; }
+    HEMO_CHECK_CUDA(ctx, cudaGraphInstantiate(&amg.apply_exec, g, 0));
+    cudaGraphDestroy(g);
+    amg.apply_b = b_dev; amg.apply_x = x_dev; amg.apply_cycles = ncycles; amg.apply_valid = true;
+    HEMO_CHECK_CUDA(ctx, cudaGraphLaunch(amg.apply_exec, st));
+    ctx->launches += amg.apply_nodes;
+    return 0;
 }
 
 extern "C" int hemo_amg_get_level_values(hemo_ctx* ctx, int which, int level, double* vals_dev, int64_t capacity) {

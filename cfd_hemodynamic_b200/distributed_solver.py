@@ -36,13 +36,20 @@ def _cell_diameter(x, cells):
 
 class DistributedStabilizedSchur:
     def __init__(self, tables: dict, owner: np.ndarray, device_index: int, group=None, verbose=False,
-                 global_pressure: bool = True, overlap: int = 8):
+                 global_pressure: bool = True, overlap: int | None = None):
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.group = group
         self.verbose = verbose and self.rank == 0
         if tables["variant"] != "schur":
             raise NotImplementedError("multi-GPU driver: only the plain stabilized_schur variant so far")
+        if overlap is None:
+            # the velocity block couples over the viscous length sqrt(nu dt); the overlap of the
+            # restricted Schwarz solve has to cover it or the iteration count grows with N
+            par0 = tables["params"]
+            hmin = float(_cell_diameter(tables["x"], tables["cells"][:4096]).min()) / math.sqrt(2.0)
+            visc = math.sqrt(par0["mu"] / par0["rho"] * par0["dt"]) / max(hmin, 1e-300)
+            overlap = int(min(max(math.ceil(1.5 * visc), 4), 32))
         self.overlap = int(overlap) if dist.get_world_size(group) > 1 else 1
         self.part = part = Partition(tables["x"], tables["cells"], owner, self.rank, overlap=self.overlap)
         self.n_global = tables["x"].shape[0]
@@ -117,7 +124,7 @@ class DistributedStabilizedSchur:
         self.ldv = (self.N + 31) // 32 * 32
         self.V = torch.zeros((self.restart + 1) * self.ldv, dtype=f64, device=dev)
         self.Z = torch.zeros(self.restart * self.ldv, dtype=f64, device=dev)
-        self._red = torch.zeros(self.restart + 2, dtype=f64, device=dev)
+        self._red = torch.zeros(self.restart + 4, dtype=f64, device=dev)
         gl = part.glob_nodes
         up = tables["u_prev"].reshape(-1, 2)[gl].reshape(-1)
         self.d_un.copy_(torch.from_numpy(np.ascontiguousarray(up)))
@@ -320,10 +327,21 @@ class DistributedStabilizedSchur:
                 hemo.spmv(self.d_vals, zj, w)
                 hemo.mask_nodes(self.ghost_mask, w)
                 self._tic("mdot+allreduce")
-                h = self._allreduce(hemo.vec_mdot(V, ldv, j + 1, w))
+                # one reduction per iteration: w is stored as basis slot j+1, so the same multi-dot
+                # returns V^T w and w.w; ||w - V h||^2 = w.w - |h|^2, recomputed exactly only when
+                # cancellation makes it unreliable
+                wslot = V[(j + 1) * ldv:(j + 1) * ldv + N]
+                wslot.copy_(w)
+                red = self._allreduce(hemo.vec_mdot(V, ldv, j + 2, w))
+                h, ww = red[:j + 1], float(red[j + 1])
                 self._tic("maxpy+allreduce")
-                nsq = hemo.vec_maxpy(V, ldv, h, -1.0, w, want_normsq=True)
-                hn = math.sqrt(max(float(self._allreduce([nsq])[0]), 0.0))
+                nsq_est = ww - float(h @ h)
+                if self.ksp_rtol >= 1e-7 and nsq_est > 0.05 * ww:
+                    hemo.vec_maxpy(V, ldv, h, -1.0, w)
+                    hn = math.sqrt(nsq_est)
+                else:
+                    nsq = hemo.vec_maxpy(V, ldv, h, -1.0, w, want_normsq=True)
+                    hn = math.sqrt(max(float(self._allreduce([nsq])[0]), 0.0))
                 self._tic("host")
                 H[:j + 1, j] = h
                 H[j + 1, j] = hn

@@ -22,7 +22,8 @@ with contextlib.redirect_stdout(sys.stderr):
     sc = LidDriven2DSimulation("stabilized_schur", 0.01, 1.0, rho=1, mu=0.01, nx=nx, host_only=True, **tight)
 tables = sc.solver.export_tables()
 owner = slab_partition(tables["x"][:, 0], world)
-ds = DistributedStabilizedSchur(tables, owner, lr, verbose=bool(os.environ.get('DIST_VERBOSE')))
+ds = DistributedStabilizedSchur(tables, owner, lr, verbose=bool(os.environ.get('DIST_VERBOSE')),
+                                overlap=int(os.environ['DIST_OVERLAP']) if os.environ.get('DIST_OVERLAP') else None)
 torch.cuda.synchronize(); dist.barrier()
 t0 = time.time()
 its = []
