@@ -29,7 +29,7 @@ class StenosisMeshVariableSimulation(Scenario):
         self._v_max = v_max
         self.grade = grade
         passthrough = {k: kwargs.pop(k) for k in list(kwargs)
-                       if k.startswith(("snes_", "ksp_", "amg_", "cheb_", "schur_", "pc_", "strength_", "smooth_")) or k in ("verbose", "device")}
+                       if k.startswith(("snes_", "ksp_", "amg_", "cheb_", "schur_", "pc_", "strength_", "smooth_")) or k in ("verbose", "device", "host_only", "quadrature")}
         self.mesh_options = kwargs.copy()
         self.mesh_options.setdefault("res", 2.0 * 1.57 / (2 * int(n_elements_radial)))
         # convection-dominated channel flow: the reference's SELFP matrix is the better Schur

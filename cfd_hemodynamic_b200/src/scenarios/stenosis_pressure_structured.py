@@ -33,9 +33,8 @@ class StenosisPressureStructuredSimulation(Scenario):
         solver_kwargs = {k: kwargs.pop(k, defaults[k]) for k in solver_keys}
         # tolerances / preconditioner options are forwarded to the solver, the rest is mesh control
         passthrough = {k: kwargs.pop(k) for k in list(kwargs)
-                       if k.startswith(("snes_", "ksp_", "amg_", "cheb_", "schur_", "pc_", "strength_", "smooth_")) or k in ("verbose", "device",
-                                                                                             "smooth_prolongator",
-                                                                                             "strength_theta")}
+                       if k.startswith(("snes_", "ksp_", "amg_", "cheb_", "schur_", "pc_", "strength_", "smooth_")) or k in ("verbose", "device", "host_only",
+                                                                                             "quadrature")}
         self.mesh_options = kwargs.copy()
         self.grade = grade
         self._bcu = None

@@ -1,0 +1,122 @@
+"""CPU tests of the scenario layer in host_only mode (no CUDA context): mesh generators,
+facet tags, Dirichlet tables and boundary-term tables exported for the device."""
+import numpy as np
+import pytest
+
+from cfd_hemodynamic_b200.fem import generators as G
+from cfd_hemodynamic_b200.fem import mesh as M
+
+
+def test_stenosis_generator_geometry_and_tags():
+    m, ft = G.stenosis_structured("severe", res=0.3)
+    x = m.geometry.x[:, :2]
+    cells = m.geometry.dofmap
+    X = x[cells]
+    area = 0.5 * ((X[:, 1, 0] - X[:, 0, 0]) * (X[:, 2, 1] - X[:, 0, 1]) - (X[:, 2, 0] - X[:, 0, 0]) * (X[:, 1, 1] - X[:, 0, 1]))
+    assert (area > 0).all()
+    o = m.mesh_options
+    assert abs(x[:, 0].max() - o["L"]) < 1e-12 and abs(x[:, 1].max() - 2 * o["R_in"]) < 1e-12
+    # throat radius of the severe grade: R_min = (1 - 0.75) * r_taper(30)
+    r_mid = o["R_in"] + (o["R_out"] - o["R_in"]) * 30.0 / o["L"]
+    throat = x[np.abs(x[:, 0] - 30.0) < 1e-9]
+    assert abs((throat[:, 1].max() - throat[:, 1].min()) / 2 - 0.25 * r_mid) < 1e-9
+    # symmetric about the centre line, even inlet count
+    n_in = len(ft.find(G.INLET))
+    assert n_in % 2 == 0 and n_in == len(ft.find(G.OUTLET))
+    assert set(np.unique(ft.values)) == {G.INLET, G.OUTLET, G.WALL}
+    assert len(ft.indices) == len(M.exterior_facet_indices(m.topology))
+
+
+def test_dfg_generator():
+    m, ft = G.dfg_cylinder(lc_min=0.05 / 3, lc_max=0.41 / 8)
+    x = m.geometry.x[:, :2]
+    X = x[m.geometry.dofmap]
+    area = 0.5 * np.abs((X[:, 1, 0] - X[:, 0, 0]) * (X[:, 2, 1] - X[:, 0, 1]) - (X[:, 2, 0] - X[:, 0, 0]) * (X[:, 1, 1] - X[:, 0, 1]))
+    assert abs(area.sum() - (2.2 * 0.41 - np.pi * 0.05 ** 2)) < 2e-3
+    obst = m.topology.facet_vertices[ft.find(G.OBSTACLE)]
+    r = np.hypot(x[obst.ravel(), 0] - 0.2, x[obst.ravel(), 1] - 0.2)
+    assert np.allclose(r, 0.05, atol=1e-12)
+    assert len(ft.find(G.INLET)) > 0 and len(ft.find(G.OUTLET)) > 0 and len(ft.find(G.WALL)) > 0
+
+
+def test_lid_scenario_tables_host_only():
+    from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation
+    sc = LidDriven2DSimulation("stabilized_schur", 0.01, 0.1, rho=1, mu=0.01, nx=6, host_only=True)
+    s = sc.solver
+    assert s.hemo is None and s._setup_count == 1
+    t = s.export_tables()
+    assert t["variant"] == "schur" and t["cells"].shape == (72, 3)
+    (b0, n0, g0), (b1, n1, g1) = t["bcs"]
+    assert b0 == b1 == "u" and len(n0) == 19 and len(n1) == 5          # walls (3 sides) and open lid interval
+    assert np.all(g1[0::2][n1] == 1.0) and np.all(g0 == 0.0)
+    pairs, coef = t["facet_sets"][0]
+    assert pairs.shape == (24, 2) and coef == {"a_p": 1.0, "a_g": 1.0}
+    sc.setup()                                                          # Simulation.run calls setup() again
+    assert s._setup_count == 2 and s.export_tables()["facet_sets"][0][1] == {"a_p": 1.0, "a_g": 1.0}
+
+
+def test_backflow_scenario_doubles_boundary_term_on_second_setup():
+    from cfd_hemodynamic_b200.src.scenarios.stenosis_mesh_variable import StenosisMeshVariableSimulation
+    sc = StenosisMeshVariableSimulation("stabilized_schur_backflow", 1e-3, 1e-2, grade="moderate", v_max=5.0,
+                                        n_elements_radial=2, L=12.0, x_position_stenosis=5.0, host_only=True)
+    s = sc.solver
+    t1 = s.export_tables()
+    assert t1["variant"] == "backflow" and t1["facet_sets"][2][1]["a_b"] == 1.0
+    sc.setup()
+    t2 = s.export_tables()
+    assert t2["facet_sets"][2][1]["a_b"] == 2.0                         # `self.F -= ...` ran twice
+    # inlet profile on inlet nodes, walls (listed last) win on the corner nodes
+    blocks = [b for b, _, _ in t2["bcs"]]
+    assert blocks == ["u", "u"]
+    n = s.n
+    from cfd_hemodynamic_b200.fem import discretization as D
+    flag, mult, cellflag, g = D.dirichlet_arrays(n, t2["cells"], t2["bcs"])
+    x = t2["x"]
+    corner = np.nonzero((x[:, 0] == 0.0) & ((x[:, 1] == x[:, 1].min()) | (x[:, 1] == x[:, 1].max())))[0]
+    assert np.all(g[2 * corner] == 0.0) and np.all(mult[2 * corner] == 2.0)
+
+
+def test_missing_required_solver_kwargs_raise():
+    from cfd_hemodynamic_b200.src.solvers.stabilized_schur_backflow import Solver as B
+    from cfd_hemodynamic_b200.src.solvers.stabilized_schur_pressure_backflow import Solver as P
+    m = M.create_unit_square(None, 2, 2)
+    with pytest.raises(ValueError, match="v_max is required"):
+        B(m, 0.01, 1.0, 1.0, [0, 0], host_only=True)
+    with pytest.raises(ValueError, match="p_inlet is required"):
+        P(m, 0.01, 1.0, 1.0, [0, 0], host_only=True)
+    with pytest.raises(ValueError, match="R_resistance is required"):
+        P(m, 0.01, 1.0, 1.0, [0, 0], p_inlet=1.0, host_only=True)
+
+
+def test_partition_overlap_layers():
+    from cfd_hemodynamic_b200.parallel import Partition, slab_partition
+    m = M.create_unit_square(None, 12, 4)
+    x = m.geometry.x[:, :2]
+    cells = m.geometry.dofmap
+    owner = slab_partition(x[:, 0], 2)
+    p1 = Partition(x, cells, owner, 0, overlap=1)
+    p3 = Partition(x, cells, owner, 0, overlap=3)
+    assert p3.n_owned == p1.n_owned and p3.n_local > p1.n_local
+    # with one layer every ghost row is incomplete, with three only the outermost ghosts are
+    assert p1.incomplete_mask[p1.n_owned:].all()
+    assert 0 < p3.incomplete_mask.sum() < p3.n_local - p3.n_owned
+    assert not p3.incomplete_mask[:p3.n_owned].any()
+
+
+def test_amg_setup_leaves_uncoupled_vertices_to_the_smoother(hemo_lib_built):
+    import scipy.sparse as sp
+    from cfd_hemodynamic_b200.fem import amg_setup
+    n = 300
+    main = 2.0 * np.ones(n)
+    off = -1.0 * np.ones(n - 1)
+    L = sp.diags([off, main, off], [-1, 0, 1]).tolil()
+    for i in (50, 51, 52):           # three vertices without couplings
+        L[i, :] = 0
+        L[:, i] = 0
+        L[i, i] = 1.0
+    L = L.tocsr()
+    L.sort_indices()
+    lv = amg_setup.build_hierarchy(L, np.zeros(n, dtype=bool), max_coarse=20)
+    P = lv[0]["P"]
+    assert P[[50, 51, 52]].nnz == 0
+    assert lv[-1]["P"].shape[1] <= 20
