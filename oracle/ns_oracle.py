@@ -493,12 +493,16 @@ def has_constant_pressure_nullspace(prob, A, tol=1e-8):
 
 
 def newton_solve(prob, x0, un, rtol=1e-8, atol=1e-50, stol=1e-8, max_it=100,
-                 verbose=False):
+                 verbose=False, asm=None):
     """One SNES.solve (stabilized_schur.py:321) with an exact (sparse LU)
-    linear solve.  Returns (x, iterations, reason>0 converged)."""
+    linear solve.  Returns (x, iterations, reason>0 converged).  `asm`: optional
+    assembler object with J(u, p, un) / F(x, un) (oracle/c_oracle.FastAssembler)."""
     n = prob.n
     x = x0.copy()
-    f = assemble_F(prob, x, un)
+    _F = (lambda xx: asm.F(xx, un)) if asm is not None else (lambda xx: assemble_F(prob, xx, un))
+    _J = (lambda xx: asm.J(xx[:2 * n], xx[2 * n:], un)) if asm is not None else \
+        (lambda xx: assemble_J(prob, xx[:2 * n], xx[2 * n:], un))
+    f = _F(x)
     fnorm = np.linalg.norm(f)
     ttol = rtol * fnorm
     if verbose:
@@ -506,7 +510,7 @@ def newton_solve(prob, x0, un, rtol=1e-8, atol=1e-50, stol=1e-8, max_it=100,
     if fnorm < atol:
         return x, 0, 2
     for it in range(max_it):
-        A = assemble_J(prob, x[:2 * n], x[2 * n:], un)
+        A = _J(x)
         singular = has_constant_pressure_nullspace(prob, A)
         if singular:
             # pin through a bordered system: solve in the orthogonal complement
@@ -526,7 +530,7 @@ def newton_solve(prob, x0, un, rtol=1e-8, atol=1e-50, stol=1e-8, max_it=100,
         f2 = 0.5 * fnorm ** 2
         for _ in range(40):
             w = x - lam * y
-            g = assemble_F(prob, w, un)
+            g = _F(w)
             gnorm = np.linalg.norm(g)
             if 0.5 * gnorm ** 2 <= f2 + lam * alpha * slope:
                 accepted = True

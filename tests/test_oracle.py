@@ -151,3 +151,28 @@ def test_golden_vectors():
     assert np.linalg.norm(A.data - gold["data"]) <= 1e-13 * np.linalg.norm(gold["data"])
     b = O.assemble_F(prob, np.concatenate([gold["u"], gold["p"]]), gold["un"])
     assert np.linalg.norm(b - gold["b"]) <= 1e-13 * np.linalg.norm(gold["b"])
+
+
+def test_c_restatement_matches_numpy_oracle():
+    """oracle/c/p1tri_cells.c (OpenMP, FFCx-style loops) vs the numpy restatement."""
+    from oracle import c_oracle
+    mesh, prob = _small()
+    n = prob.n
+    u, p, un = T.smooth_fields(prob.x)
+    Ae, Fe = c_oracle.element_tensors(prob, u, p, un)
+    Ae_ref = O.element_matrices(prob, u, p, un)
+    U, P, Un = O._gather(prob, u, p, un)
+    Fu, _ = O.element_F(prob, U, P, Un, prob.rules["Fu"])
+    _, Fp = O.element_F(prob, U, P, Un, prob.rules["Fp"])
+    Fe_ref = np.concatenate([Fu.reshape(-1, 6), Fp], axis=1)
+    assert np.linalg.norm(Ae - Ae_ref) <= 1e-13 * np.linalg.norm(Ae_ref)
+    assert np.linalg.norm(Fe - Fe_ref) <= 1e-13 * np.linalg.norm(Fe_ref)
+    x = prob.x
+    left = np.nonzero(np.isclose(x[:, 0], 0.0))[0]
+    prob.bcs = T.oracle_bcs(prob, [("u", left, np.random.default_rng(3).standard_normal(2 * n))])
+    fa = c_oracle.FastAssembler(prob)
+    xx = np.concatenate([u, p])
+    A = fa.J(u, p, un)
+    A_ref = O.assemble_J(prob, u, p, un)
+    assert abs(A - A_ref).max() <= 1e-12 * abs(A_ref).max()
+    assert np.linalg.norm(fa.F(xx, un) - O.assemble_F(prob, xx, un)) <= 1e-12 * np.linalg.norm(O.assemble_F(prob, xx, un))
