@@ -9,8 +9,9 @@ this image, so the XG tables themselves are unavailable.  What ships here:
 * `triangle_symmetric(degree)`: fully symmetric (D3-orbit) rules with the
   same point counts as the XG rules of the degrees the hot path needs
   (10 → 25, 11 → 28, 12 → 33 points), stored in `_tables.py` as orbit
-  parameters found by `tools/make_triangle_rules.py` (moment equations solved
-  to 1e-16) and expanded/verified here.
+  parameters (degrees 10, 11: found by `tools/make_triangle_rules.py` from the
+  moment equations; degree 12: Dunavant's rule polished the same way) and
+  expanded/verified here.
 * `triangle_gauss_jacobi(degree)`: collapsed Gauss–Jacobi tensor rule (what
   Basix uses above degree 30) for any degree — the fallback.
 * `interval_gauss(npts)`: Gauss–Legendre on [0, 1] for exterior facets.
