@@ -41,8 +41,10 @@ class DistributedStabilizedSchur:
         self.world = dist.get_world_size(group)
         self.group = group
         self.verbose = verbose and self.rank == 0
-        if tables["variant"] != "schur":
-            raise NotImplementedError("multi-GPU driver: only the plain stabilized_schur variant so far")
+        if tables["variant"] not in ("schur", "backflow"):
+            raise NotImplementedError("multi-GPU driver: the resistance-outlet variant needs a global outlet-flux "
+                                      "reduction per step (not wired yet)")
+        self.variant = tables["variant"]
         if overlap is None:
             # the velocity block couples over the viscous length sqrt(nu dt); the overlap of the
             # restricted Schwarz solve has to cover it or the iteration count grows with N
@@ -179,7 +181,25 @@ class DistributedStabilizedSchur:
             hp.set_bc(torch.from_numpy(flag).to(dev), torch.from_numpy(mult).to(dev), torch.from_numpy(cellflag).to(dev))
             pmask = flag[2 * ng:].astype(bool)
         self.g_lap, self.g_mass = hp.assemble_laplace_mass()
-        L = sp.csr_matrix((self.g_lap.cpu().numpy(), nc, nrp), shape=(ng, ng))
+        lap_host = self.g_lap.cpu().numpy()
+        if self.variant != "schur":
+            # open (traction) boundaries: Dirichlet rows in the pressure operator of the Schur
+            # approximation, as in the single-GPU solver (_stabilized_common.setup)
+            from .fem.mesh import Mesh, exterior_facet_indices
+            gm = Mesh(xg, cg)
+            ext = exterior_facet_indices(gm.topology)
+            bnodes = np.unique(gm.topology.facet_vertices[ext])
+            unodes = np.unique(np.concatenate([np.asarray(nodes, dtype=np.int64) for b, nodes, _ in tables["bcs"]
+                                               if b == "u"] + [np.zeros(0, np.int64)]))
+            openn = np.setdiff1d(bnodes, unodes)
+            omask = np.zeros(ng, dtype=bool)
+            omask[openn] = True
+            rows = np.repeat(np.arange(ng), np.diff(nrp))
+            hit = omask[rows] | omask[nc]
+            lap_host = np.where(hit, (rows == nc).astype(np.float64), lap_host)
+            self.g_lap = torch.from_numpy(np.ascontiguousarray(lap_host)).to(dev)
+            pmask = pmask | omask
+        L = sp.csr_matrix((lap_host, nc, nrp), shape=(ng, ng))
         lv = amg_setup.build_hierarchy(L, pmask, max_coarse=160)
         for l, d in enumerate(lv):
             hp.amg_set_level(1, l, d["P"], d["R"], d["AP"], d["C"])
