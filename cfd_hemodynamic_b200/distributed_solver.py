@@ -41,9 +41,6 @@ class DistributedStabilizedSchur:
         self.world = dist.get_world_size(group)
         self.group = group
         self.verbose = verbose and self.rank == 0
-        if tables["variant"] not in ("schur", "backflow"):
-            raise NotImplementedError("multi-GPU driver: the resistance-outlet variant needs a global outlet-flux "
-                                      "reduction per step (not wired yet)")
         self.variant = tables["variant"]
         if overlap is None:
             # the velocity block couples over the viscous length sqrt(nu dt); the overlap of the
@@ -78,9 +75,16 @@ class DistributedStabilizedSchur:
         g2l = part.g2l
         cell_g2l = -np.ones(tables["cells"].shape[0], dtype=np.int64)
         cell_g2l[part.cell_glob] = np.arange(part.cell_glob.shape[0])
+        self._outlet = None
         for sid, (pairs, coef) in tables["facet_sets"].items():
             lc = cell_g2l[pairs[:, 0]]
             keep = lc >= 0
+            if self.variant == "pressure_backflow" and sid == 2:
+                # resistance outlet: every overlapping rank sees the outlet cells; the flux is summed over
+                # the cells whose first vertex this rank owns so that each facet counts once
+                first_owner = owner[tables["cells"][pairs[:, 0], 0]]
+                mine = keep & (first_owner == self.rank)
+                self._outlet = dict(coef=dict(coef), flux_cells=lc[mine], flux_lf=pairs[mine, 1], **tables["outlet"])
             lp = np.stack([lc[keep], pairs[keep, 1]], axis=1)
             if lp.shape[0] == 0:
                 continue
@@ -472,12 +476,45 @@ class DistributedStabilizedSchur:
                 return it + 1, lin_its, 4
         return self.snes_max_it, lin_its, -5
 
+    def _update_outlet_pressure(self):
+        """p_c <- alpha R |Q| + (1 - alpha) p_c with Q = global int u_prev.n ds_out
+        (stabilized_schur_pressure_backflow.py:383-396): local flux over owned outlet cells + allreduce."""
+        o = self._outlet
+        part = self.part
+        cells = part.cells[o["flux_cells"]]
+        if cells.shape[0]:
+            X = part.x[cells]
+            lf = o["flux_lf"]
+            ar = np.arange(cells.shape[0])
+            fv = np.array([[1, 2], [0, 2], [0, 1]])
+            va, vb = fv[lf, 0], fv[lf, 1]
+            t = X[ar, vb] - X[ar, va]
+            nrm = np.stack([t[:, 1], -t[:, 0]], axis=1)
+            nrm *= np.sign(np.einsum("ei,ei->e", nrm, X[ar, va] - X[ar, lf]))[:, None]
+            nodes = np.unique(cells)
+            un = np.zeros((self.n, 2))
+            idx = torch.from_numpy(np.concatenate([2 * nodes, 2 * nodes + 1])).to(self.hemo.device)
+            vals = self.d_un.index_select(0, idx).cpu().numpy()
+            un[nodes, 0] = vals[:nodes.shape[0]]
+            un[nodes, 1] = vals[nodes.shape[0]:]
+            U = un[cells]
+            q_loc = float(np.sum(np.einsum("ei,ei->e", 0.5 * (U[ar, va] + U[ar, vb]), nrm)))
+        else:
+            q_loc = 0.0
+        q = float(self._allreduce([q_loc])[0])
+        o["p_c"] = o["alpha_damping"] * o["R_resistance"] * abs(q) + (1.0 - o["alpha_damping"]) * o["p_c"]
+        coef = dict(o["coef"])
+        coef["pconst"] = 0.5 * (sum(o["p_c_frozen"]) + o["p_c"])
+        self.hemo.set_facet_coef(2, **coef)
+
     def step_device(self):
         """One time step, everything resident on the GPUs; u_prev <- u_sol on the device."""
         self._remove_pressure_mean(self.d_x)      # nullsp.remove(x_n), unconditional (:319)
         self.its_snes, self.its_ksp, self.reason = self._newton()
         if self.reason < 0:
             raise RuntimeError(f"Did not converge, reason: {self.reason}.")
+        if self._outlet is not None:
+            self._update_outlet_pressure()        # Q from the old u_prev (one-step lag, scenario.py:306)
         self.d_un.copy_(self.d_x[:2 * self.n])
 
     def gather_solution(self):

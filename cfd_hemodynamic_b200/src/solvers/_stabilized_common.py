@@ -164,6 +164,8 @@ class StabilizedSchurB200(SolverBase):
             params=dict(dt=float(self.dt.value), rho=float(self.rho.value), mu=float(self.mu.value),
                         f=np.asarray(self.f.value, dtype=float).reshape(-1)[:2]),
             variant=self.variant, u_prev=self.u_prev.x.array.copy(), p_prev=self.p_prev.x.array.copy(),
+            outlet=dict(R_resistance=getattr(self, "R_resistance", None), alpha_damping=getattr(self, "alpha_damping", None),
+                        p_c=self._p_c, p_c_frozen=list(self._p_c_frozen), setup_count=self._setup_count),
             solver_kw=dict(snes_rtol=self.snes_rtol, snes_atol=self.snes_atol, snes_stol=self.snes_stol,
                            snes_max_it=self.snes_max_it, ksp_rtol=self.ksp_rtol, ksp_max_it=self.ksp_max_it,
                            ksp_restart=self.ksp_restart, pc_kw=dict(self._pc_kw)))

@@ -48,21 +48,37 @@ class Solver(StabilizedSchurB200):
         return dict(pconst=0.5 * pc_sum, a_s=c, a_b=c, beta_b=self.beta_backflow)
 
     def _facet_setup(self, facet_tags, tags):
-        if self._host_only:
-            raise NotImplementedError("pressure_backflow needs the outlet flux on the device; "
-                                      "the multi-GPU driver does not support it yet")
-        torch = self._torch
-        dev = self.hemo.device
         fin = facet_tags.find(tags["inlet"])
         fout = facet_tags.find(tags["outlet"])
         self._register_facets(SET_OUTLET, fout, **self._outlet_coef())
         # Q_init from the host u_prev (:204-205); the previous live constant becomes frozen
         if self._setup_count > 1:
             self._p_c_frozen.append(self._p_c)
-        q_init = self.hemo.outlet_flux(SET_OUTLET, torch.from_numpy(self.u_prev.x.array).to(dev))
+        if self._host_only:
+            q_init = self._host_outlet_flux(fout)
+        else:
+            q_init = self.hemo.outlet_flux(SET_OUTLET,
+                                           self._torch.from_numpy(self.u_prev.x.array).to(self.hemo.device))
         self._p_c = self.R_resistance * abs(q_init)
         self._register_facets(SET_INLET, fin, **self._inlet_coef())
-        self.hemo.set_facet_coef(SET_OUTLET, **self._outlet_coef())
+        self._register_facets(SET_OUTLET, fout, **self._outlet_coef())
+
+    def _host_outlet_flux(self, facets) -> float:
+        """assemble_scalar(dot(u_prev, n) * ds_out) on the host (host_only mode)."""
+        topo = self.mesh.topology
+        pairs = topo.facet_cell_pairs(facets)
+        x = self.mesh.geometry.x[:, :2]
+        cells = self.mesh.geometry.dofmap[pairs[:, 0]]
+        lf = pairs[:, 1]
+        X = x[cells]
+        ar = np.arange(cells.shape[0])
+        fv = np.array([[1, 2], [0, 2], [0, 1]])
+        va, vb = fv[lf, 0], fv[lf, 1]
+        t = X[ar, vb] - X[ar, va]
+        nrm = np.stack([t[:, 1], -t[:, 0]], axis=1)
+        nrm *= np.sign(np.einsum("ei,ei->e", nrm, X[ar, va] - X[ar, lf]))[:, None]
+        U = self.u_prev.x.array.reshape(-1, 2)[cells]
+        return float(np.sum(np.einsum("ei,ei->e", 0.5 * (U[ar, va] + U[ar, vb]), nrm)))
 
     def _update_facet_coefs(self):
         self.hemo.set_facet_coef(SET_OUTLET, **self._outlet_coef())

@@ -22,6 +22,12 @@ tight = dict(snes_rtol=1e-11, snes_stol=0.0, ksp_rtol=1e-9, ksp_restart=100) if 
 def make(host_only, **kw):
     if case == "lid":
         return LidDriven2DSimulation("stabilized_schur", 0.01, 1.0, rho=1, mu=0.01, nx=nx, host_only=host_only, **kw)
+    if case == "pressure":
+        from cfd_hemodynamic_b200.src.scenarios.stenosis_pressure_structured import StenosisPressureStructuredSimulation
+        return StenosisPressureStructuredSimulation("stabilized_schur_pressure_backflow", 0.005, 1.0, grade="moderate",
+                                                    p_inlet=2.0, R_resistance=50.0, res=3.14 / nx, L=20.0,
+                                                    x_position_stenosis=8.0, schur_mode="laplace",
+                                                    host_only=host_only, **kw)
     from cfd_hemodynamic_b200.src.scenarios.stenosis_mesh_variable import StenosisMeshVariableSimulation
     # stenosis channel with Dirichlet inlet + backflow-stabilised open outlet (nx = cells across the inlet)
     return StenosisMeshVariableSimulation("stabilized_schur_backflow", 0.005, 1.0, grade="moderate", v_max=5.0,
@@ -53,6 +59,8 @@ if rank == 0:
         s = ref.solver
         for k in range(steps):
             s.step_device()
+        if case == "pressure":
+            print(f"outlet pressure p_c: serial {s._p_c:.10e} distributed {ds._outlet['p_c']:.10e}")
         x = s.d_x.cpu().numpy(); n = s.n
         ur, pr = x[:2 * n], x[2 * n:]
         eu = np.linalg.norm(u - ur) / np.linalg.norm(ur)
