@@ -442,17 +442,66 @@ k_transfer(int nrows, const int32_t* __restrict__ rowptr, const int32_t* __restr
 // fused coarse V-cycle: all levels with n <= HEMO_FUSE_MAX_NODES run inside one
 // CTA (phases separated by __syncthreads), replacing ~10 launches per level.
 // ---------------------------------------------------------------------------
-template <int BS>
-__device__ __forceinline__ void row_product_serial(const HemoCoarseLevel& L, const areal* __restrict__ x, int i,
-                                                   double acc[BS]) {
+// Row loops of the fused kernel: 8 lanes cooperate on one block row (coarse Galerkin rows hold
+// 20-60 blocks; a thread-serial walk makes every phase a ~50-deep dependent load chain).  All
+// lanes of a warp execute the same number of outer iterations, so full-mask shuffles are legal.
+template <int BS, typename Epi>
+__device__ __forceinline__ void rows_matvec(const HemoCoarseLevel& L, const areal* __restrict__ x, Epi epi) {
+    const int lane = threadIdx.x & 7, group = threadIdx.x >> 3, ngroups = blockDim.x >> 3;
+    for (int base = 0; base < L.n; base += ngroups) {
+        const int i = base + group;
+        const bool ok = i < L.n;
+        double acc[BS];
 #pragma unroll
-    for (int k = 0; k < BS; ++k) acc[k] = 0.0;
-    for (int t = L.rowptr[i]; t < L.rowptr[i + 1]; ++t) {
-        const int j = L.col[t];
+        for (int k = 0; k < BS; ++k) acc[k] = 0.0;
+        if (ok) {
+            const int r1 = L.rowptr[i + 1];
+            for (int t = L.rowptr[i] + lane; t < r1; t += 8) {
+                const int j = L.col[t];
 #pragma unroll
-        for (int k = 0; k < BS; ++k)
+                for (int k = 0; k < BS; ++k)
 #pragma unroll
-            for (int l = 0; l < BS; ++l) acc[k] = fma((double)L.val[(int64_t)t * BS * BS + k * BS + l], (double)x[(int64_t)j * BS + l], acc[k]);
+                    for (int l = 0; l < BS; ++l)
+                        acc[k] = fma((double)L.val[(int64_t)t * BS * BS + k * BS + l], (double)x[(int64_t)j * BS + l], acc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < BS; ++k) {
+            acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1, 8);
+            acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2, 8);
+            acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 4, 8);
+        }
+        if (ok && lane == 0) epi(i, acc);
+    }
+}
+
+// y-rows of a transfer operator (CSR with fp64 weights) applied to a BS-component vector
+template <int BS, typename Epi>
+__device__ __forceinline__ void rows_transfer(int nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                              const double* __restrict__ w, const areal* __restrict__ x, Epi epi) {
+    const int lane = threadIdx.x & 7, group = threadIdx.x >> 3, ngroups = blockDim.x >> 3;
+    for (int base = 0; base < nrows; base += ngroups) {
+        const int i = base + group;
+        const bool ok = i < nrows;
+        double acc[BS];
+#pragma unroll
+        for (int k = 0; k < BS; ++k) acc[k] = 0.0;
+        if (ok) {
+            const int r1 = rowptr[i + 1];
+            for (int t = rowptr[i] + lane; t < r1; t += 8) {
+                const int j = col[t];
+                const double wt = w[t];
+#pragma unroll
+                for (int k = 0; k < BS; ++k) acc[k] = fma(wt, (double)x[(int64_t)j * BS + k], acc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < BS; ++k) {
+            acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1, 8);
+            acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2, 8);
+            acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 4, 8);
+        }
+        if (ok && lane == 0) epi(i, acc);
     }
 }
 
@@ -468,49 +517,48 @@ __device__ void fused_smooth(const HemoCoarseLevel& L, const areal* __restrict__
     areal* dnew = L.d1;
     if (x_is_zero) {
         for (int q = tid; q < N; q += T) {
-            const double rv = L.dinv[q] * b[q];
-            L.r[q] = rv;
-            dold[q] = rv / theta;
-            x[q] = rv / theta;
+            const double rv = (double)L.dinv[q] * (double)b[q];
+            L.r[q] = (areal)rv;
+            dold[q] = (areal)(rv / theta);
+            x[q] = (areal)(rv / theta);
         }
     } else {
-        for (int i = tid; i < L.n; i += T) {
-            double acc[BS];
-            row_product_serial<BS>(L, x, i, acc);
+        rows_matvec<BS>(L, x, [&](int i, const double* acc) {
 #pragma unroll
             for (int k = 0; k < BS; ++k) {
                 const int q = i * BS + k;
-                const double rv = L.dinv[q] * (b[q] - acc[k]);
-                L.r[q] = rv;
-                dold[q] = rv / theta;
+                const double rv = (double)L.dinv[q] * ((double)b[q] - acc[k]);
+                L.r[q] = (areal)rv;
+                dold[q] = (areal)(rv / theta);
             }
-        }
+        });
     }
     __syncthreads();
     bool pending = !x_is_zero;
     for (int s = 1; s < degree; ++s) {
         const double rho_new = 1.0 / (2.0 * sigma - rho);
         const double c1 = rho_new * rho, c2 = 2.0 * rho_new / delta;
-        for (int i = tid; i < L.n; i += T) {
-            double acc[BS];
-            row_product_serial<BS>(L, dold, i, acc);
+        const areal* dcur = dold;
+        areal* dnext = dnew;
+        const bool add_old = pending;
+        rows_matvec<BS>(L, dcur, [&](int i, const double* acc) {
 #pragma unroll
             for (int k = 0; k < BS; ++k) {
                 const int q = i * BS + k;
-                const double rv = L.r[q] - L.dinv[q] * acc[k];
-                L.r[q] = rv;
-                const double dv = c1 * dold[q] + c2 * rv;
-                dnew[q] = dv;
-                x[q] += pending ? (dv + dold[q]) : dv;
+                const double rv = (double)L.r[q] - (double)L.dinv[q] * acc[k];
+                L.r[q] = (areal)rv;
+                const double dv = c1 * (double)dcur[q] + c2 * rv;
+                dnext[q] = (areal)dv;
+                x[q] = (areal)((double)x[q] + (add_old ? (dv + (double)dcur[q]) : dv));
             }
-        }
+        });
         __syncthreads();
         pending = false;
         areal* t = dold; dold = dnew; dnew = t;
         rho = rho_new;
     }
     if (pending) {
-        for (int q = tid; q < N; q += T) x[q] += dold[q];
+        for (int q = tid; q < N; q += T) x[q] = (areal)((double)x[q] + (double)dold[q]);
         __syncthreads();
     }
 }
@@ -526,37 +574,33 @@ k_coarse_vcycle(const HemoCoarseLevel* __restrict__ desc, int nl, const areal* _
         const areal* b = (l == 0) ? b0 : L.b;
         areal* x = (l == 0) ? x0 : L.x;
         fused_smooth<BS>(L, b, x, true, degree, ratio);
-        for (int i = tid; i < L.n; i += T) {
-            double acc[BS];
-            row_product_serial<BS>(L, x, i, acc);
+        rows_matvec<BS>(L, x, [&](int i, const double* acc) {
 #pragma unroll
-            for (int k = 0; k < BS; ++k) L.r[i * BS + k] = b[i * BS + k] - acc[k];
-        }
+            for (int k = 0; k < BS; ++k) L.r[i * BS + k] = (areal)((double)b[i * BS + k] - acc[k]);
+        });
         __syncthreads();
         areal* bc = desc[l + 1].b;
-        for (int I = tid; I < L.nc; I += T) {
-            double acc[BS];
+        rows_transfer<BS>(L.nc, L.r_rowptr, L.r_col, L.r_val, L.r, [&](int I, const double* acc) {
 #pragma unroll
-            for (int k = 0; k < BS; ++k) acc[k] = 0.0;
-            for (int t = L.r_rowptr[I]; t < L.r_rowptr[I + 1]; ++t) {
-                const int j = L.r_col[t];
-                const double w = L.r_val[t];
-#pragma unroll
-                for (int k = 0; k < BS; ++k) acc[k] = fma(w, (double)L.r[j * BS + k], acc[k]);
-            }
-#pragma unroll
-            for (int k = 0; k < BS; ++k) bc[I * BS + k] = acc[k];
-        }
+            for (int k = 0; k < BS; ++k) bc[I * BS + k] = (areal)acc[k];
+        });
         __syncthreads();
     }
-    // coarsest: dense inverse
+    // coarsest: dense inverse, 8 lanes per row
     {
         const areal* b = (nl == 1) ? b0 : desc[nl - 1].b;
         areal* x = (nl == 1) ? x0 : desc[nl - 1].x;
-        for (int row = tid; row < dense_n; row += T) {
+        const int lane = tid & 7, group = tid >> 3, ngroups = T >> 3;
+        for (int base = 0; base < dense_n; base += ngroups) {
+            const int row = base + group;
+            const bool ok = row < dense_n;
             double acc = 0.0;
-            for (int c = 0; c < dense_n; ++c) acc = fma(dense_inv[(int64_t)row * dense_n + c], (double)b[c], acc);
-            x[row] = acc;
+            if (ok)
+                for (int c = lane; c < dense_n; c += 8) acc = fma(dense_inv[(int64_t)row * dense_n + c], (double)b[c], acc);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1, 8);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2, 8);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4, 8);
+            if (ok && lane == 0) x[row] = (areal)acc;
         }
         __syncthreads();
     }
@@ -566,19 +610,10 @@ k_coarse_vcycle(const HemoCoarseLevel* __restrict__ desc, int nl, const areal* _
         const areal* b = (l == 0) ? b0 : L.b;
         areal* x = (l == 0) ? x0 : L.x;
         const areal* xc = desc[l + 1].x;
-        for (int i = tid; i < L.n; i += T) {
-            double acc[BS];
+        rows_transfer<BS>(L.n, L.p_rowptr, L.p_col, L.p_val, xc, [&](int i, const double* acc) {
 #pragma unroll
-            for (int k = 0; k < BS; ++k) acc[k] = 0.0;
-            for (int t = L.p_rowptr[i]; t < L.p_rowptr[i + 1]; ++t) {
-                const int j = L.p_col[t];
-                const double w = L.p_val[t];
-#pragma unroll
-                for (int k = 0; k < BS; ++k) acc[k] = fma(w, (double)xc[j * BS + k], acc[k]);
-            }
-#pragma unroll
-            for (int k = 0; k < BS; ++k) x[i * BS + k] += acc[k];
-        }
+            for (int k = 0; k < BS; ++k) x[i * BS + k] = (areal)((double)x[i * BS + k] + acc[k]);
+        });
         __syncthreads();
         fused_smooth<BS>(L, b, x, false, degree, ratio);
     }
