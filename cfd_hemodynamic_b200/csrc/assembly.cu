@@ -577,7 +577,7 @@ __global__ void k_sum_serial(int m, const double* __restrict__ partial, double* 
 // ---------------------------------------------------------------------------
 // One thread per node pair (i, j) = one 3x3 scalar block of the CSR matrix.
 __global__ void __launch_bounds__(256)
-k_gather_matrix(int n, int64_t nnz_node, int64_t E, const int32_t* __restrict__ nrowptr,
+k_gather_matrix(int n, int nv2, int64_t nnz_node, int64_t E, const int32_t* __restrict__ nrowptr,
                 const int32_t* __restrict__ ncol, const int32_t* __restrict__ rowof,
                 const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_src,
                 const double* __restrict__ Ae, const uint8_t* __restrict__ dofflag,
@@ -592,8 +592,8 @@ k_gather_matrix(int n, int64_t nnz_node, int64_t E, const int32_t* __restrict__ 
     const int b0 = seg_ptr[s], b1 = seg_ptr[s + 1];
     for (int t = b0; t < b1; ++t) {
         const int src = seg_src[t];
-        const int64_t c = src / 9;
-        const int ab = src - (int)c * 9;
+        const int64_t c = src / nv2;
+        const int ab = src - (int)c * nv2;
         const double* p = Ae + (int64_t)ab * 9 * E + c;
 #pragma unroll
         for (int k = 0; k < 9; ++k) acc[k] += p[k * E];
@@ -632,7 +632,7 @@ k_gather_matrix(int n, int64_t nnz_node, int64_t E, const int32_t* __restrict__ 
 
 // One thread per node: b[2i], b[2i+1], b[2n+i]; then set_bc.
 __global__ void __launch_bounds__(256)
-k_gather_vector(int n, int64_t E, const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_src,
+k_gather_vector(int n, int nv, int64_t E, const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_src,
                 const double* __restrict__ Fe, const uint8_t* __restrict__ dofflag,
                 const double* __restrict__ x, const double* __restrict__ g, double* __restrict__ b) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -640,8 +640,8 @@ k_gather_vector(int n, int64_t E, const int32_t* __restrict__ seg_ptr, const int
     double a0 = 0, a1 = 0, a2 = 0;
     for (int t = seg_ptr[i]; t < seg_ptr[i + 1]; ++t) {
         const int src = seg_src[t];
-        const int64_t c = src / 3;
-        const int a = src - (int)c * 3;
+        const int64_t c = src / nv;
+        const int a = src - (int)c * nv;
         a0 += Fe[(a * 3 + 0) * E + c];
         a1 += Fe[(a * 3 + 1) * E + c];
         a2 += Fe[(a * 3 + 2) * E + c];
@@ -718,7 +718,7 @@ __global__ void k_cell_pconv(int E, const int32_t* __restrict__ cells, const dou
     }
 }
 
-__global__ void k_gather_scalar_matrix_areal(int64_t nnz_node, int64_t E, const int32_t* __restrict__ seg_ptr,
+__global__ void k_gather_scalar_matrix_areal(int nv2, int64_t nnz_node, int64_t E, const int32_t* __restrict__ seg_ptr,
                                              const int32_t* __restrict__ seg_src, const double* __restrict__ Ke,
                                              areal* __restrict__ vals) {
     const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -726,14 +726,14 @@ __global__ void k_gather_scalar_matrix_areal(int64_t nnz_node, int64_t E, const 
     double acc = 0.0;
     for (int t = seg_ptr[s]; t < seg_ptr[s + 1]; ++t) {
         const int src = seg_src[t];
-        const int64_t c = src / 9;
-        const int ab = src - (int)c * 9;
+        const int64_t c = src / nv2;
+        const int ab = src - (int)c * nv2;
         acc += Ke[(int64_t)ab * E + c];
     }
     vals[s] = (areal)acc;
 }
 
-__global__ void k_gather_scalar_matrix(int64_t nnz_node, int64_t E, const int32_t* __restrict__ seg_ptr,
+__global__ void k_gather_scalar_matrix(int nv2, int64_t nnz_node, int64_t E, const int32_t* __restrict__ seg_ptr,
                                        const int32_t* __restrict__ seg_src, const double* __restrict__ Ke,
                                        double* __restrict__ vals) {
     const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -741,14 +741,14 @@ __global__ void k_gather_scalar_matrix(int64_t nnz_node, int64_t E, const int32_
     double acc = 0.0;
     for (int t = seg_ptr[s]; t < seg_ptr[s + 1]; ++t) {
         const int src = seg_src[t];
-        const int64_t c = src / 9;
-        const int ab = src - (int)c * 9;
+        const int64_t c = src / nv2;
+        const int ab = src - (int)c * nv2;
         acc += Ke[(int64_t)ab * E + c];
     }
     vals[s] = acc;
 }
 
-__global__ void k_gather_scalar_vector(int n, int64_t E, const int32_t* __restrict__ seg_ptr,
+__global__ void k_gather_scalar_vector(int n, int nv, int64_t E, const int32_t* __restrict__ seg_ptr,
                                        const int32_t* __restrict__ seg_src, const double* __restrict__ Me,
                                        double* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -756,8 +756,8 @@ __global__ void k_gather_scalar_vector(int n, int64_t E, const int32_t* __restri
     double acc = 0.0;
     for (int t = seg_ptr[i]; t < seg_ptr[i + 1]; ++t) {
         const int src = seg_src[t];
-        const int64_t c = src / 3;
-        const int a = src - (int)c * 3;
+        const int64_t c = src / nv;
+        const int a = src - (int)c * nv;
         acc += Me[(int64_t)a * E + c];
     }
     out[i] = acc;
@@ -776,16 +776,17 @@ __global__ void k_rowof(int n, const int32_t* __restrict__ nrowptr, int32_t* __r
     }
 }
 
-__global__ void k_cellpos(int E, const int32_t* __restrict__ cells, const int32_t* __restrict__ nrowptr,
+__global__ void k_cellpos(int E, int nv, const int32_t* __restrict__ cells, const int32_t* __restrict__ nrowptr,
                           const int32_t* __restrict__ ncol, int32_t* __restrict__ cellpos,
                           int32_t* __restrict__ mcount, int32_t* __restrict__ vcount, int* __restrict__ bad) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= E) return;
-    int v[3] = {cells[3 * (int64_t)c], cells[3 * (int64_t)c + 1], cells[3 * (int64_t)c + 2]};
-    for (int a = 0; a < 3; ++a) {
+    int v[4];
+    for (int a = 0; a < nv; ++a) v[a] = cells[nv * (int64_t)c + a];
+    for (int a = 0; a < nv; ++a) {
         const int r0 = nrowptr[v[a]], r1 = nrowptr[v[a] + 1];
         atomicAdd(&vcount[v[a]], 1);
-        for (int b = 0; b < 3; ++b) {
+        for (int b = 0; b < nv; ++b) {
             int lo = r0, hi = r1 - 1, pos = -1;
             while (lo <= hi) {
                 const int mid = (lo + hi) >> 1;
@@ -794,26 +795,27 @@ __global__ void k_cellpos(int E, const int32_t* __restrict__ cells, const int32_
                 if (cv < v[b]) lo = mid + 1; else hi = mid - 1;
             }
             if (pos < 0) { atomicExch(bad, 1); pos = r0; }
-            cellpos[(int64_t)c * 9 + a * 3 + b] = pos;
+            cellpos[(int64_t)c * nv * nv + a * nv + b] = pos;
             atomicAdd(&mcount[pos], 1);
         }
     }
 }
 
-__global__ void k_fill_segments(int E, const int32_t* __restrict__ cells, const int32_t* __restrict__ cellpos,
+__global__ void k_fill_segments(int E, int nv, const int32_t* __restrict__ cells, const int32_t* __restrict__ cellpos,
                                 const int32_t* __restrict__ mptr, const int32_t* __restrict__ vptr,
                                 int32_t* __restrict__ mfill, int32_t* __restrict__ vfill,
                                 int32_t* __restrict__ msrc, int32_t* __restrict__ vsrc) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= E) return;
-    for (int a = 0; a < 3; ++a) {
-        const int va = cells[3 * (int64_t)c + a];
+    const int nv2 = nv * nv;
+    for (int a = 0; a < nv; ++a) {
+        const int va = cells[nv * (int64_t)c + a];
         const int k = atomicAdd(&vfill[va], 1);
-        vsrc[vptr[va] + k] = c * 3 + a;
-        for (int b = 0; b < 3; ++b) {
-            const int pos = cellpos[(int64_t)c * 9 + a * 3 + b];
+        vsrc[vptr[va] + k] = c * nv + a;
+        for (int b = 0; b < nv; ++b) {
+            const int pos = cellpos[(int64_t)c * nv2 + a * nv + b];
             const int kk = atomicAdd(&mfill[pos], 1);
-            msrc[mptr[pos] + kk] = c * 9 + a * 3 + b;
+            msrc[mptr[pos] + kk] = c * nv2 + a * nv + b;
         }
     }
 }
@@ -870,12 +872,21 @@ static int upload_constants(hemo_ctx* ctx) {
     return 0;
 }
 
+extern "C" int hemo_set_cell_type(hemo_ctx* ctx, int cell_type) {
+    if (!ctx || (cell_type != HEMO_CELL_TRIANGLE && cell_type != HEMO_CELL_QUADRILATERAL)) return HEMO_EINVAL;
+    if (ctx->cells) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_set_cell_type must precede hemo_set_mesh");
+    ctx->nv = (cell_type == HEMO_CELL_QUADRILATERAL) ? 4 : 3;
+    for (int r = 0; r < HEMO_NRULES; ++r) ctx->have_rule[r] = false;
+    return 0;
+}
+
 extern "C" int hemo_set_mesh(hemo_ctx* ctx, const double* x_dev, int n_nodes, const int32_t* cells_dev,
                              int n_cells, const double* h_dev) {
     if (!ctx || !x_dev || !cells_dev || !h_dev || n_nodes <= 0 || n_cells <= 0)
         return HEMO_EINVAL;
-    if ((int64_t)n_cells * 81 >= ((int64_t)1 << 40)) HEMO_FAIL(ctx, HEMO_EINVAL, "mesh too large");
-    if ((int64_t)n_cells * 9 >= ((int64_t)1 << 31)) HEMO_FAIL(ctx, HEMO_EINVAL, "n_cells*9 exceeds int32 gather index");
+    const int64_t nv2 = (int64_t)ctx->nv * ctx->nv;
+    if ((int64_t)n_cells * 9 * nv2 >= ((int64_t)1 << 40)) HEMO_FAIL(ctx, HEMO_EINVAL, "mesh too large");
+    if ((int64_t)n_cells * nv2 >= ((int64_t)1 << 31)) HEMO_FAIL(ctx, HEMO_EINVAL, "n_cells*nv^2 exceeds int32 gather index");
     ctx->x = x_dev; ctx->cells = cells_dev; ctx->h = h_dev;
     ctx->n = n_nodes; ctx->E = n_cells;
     int rc;
@@ -894,15 +905,16 @@ extern "C" int hemo_set_node_graph(hemo_ctx* ctx, const int32_t* nrowptr_dev, co
     if (nnz_node * 9 >= ((int64_t)1 << 40) || nnz_node >= ((int64_t)1 << 31))
         HEMO_FAIL(ctx, HEMO_EINVAL, "node graph too large for int32 slots");
     ctx->nrowptr = nrowptr_dev; ctx->ncol = ncol_dev; ctx->nnz_node = nnz_node;
-    const int n = ctx->n, E = ctx->E;
+    const int n = ctx->n, E = ctx->E, nv = ctx->nv;
+    const size_t nv2 = (size_t)nv * nv;
     int rc;
     if ((rc = hemo_alloc(ctx, &ctx->rowof, (size_t)nnz_node))) return rc;
     if ((rc = hemo_alloc(ctx, &ctx->diagslot, (size_t)n))) return rc;
-    if ((rc = hemo_alloc(ctx, &ctx->cellpos, (size_t)9 * E))) return rc;
+    if ((rc = hemo_alloc(ctx, &ctx->cellpos, nv2 * E))) return rc;
     if ((rc = hemo_alloc(ctx, &ctx->mseg_ptr, (size_t)nnz_node + 1))) return rc;
-    if ((rc = hemo_alloc(ctx, &ctx->mseg_src, (size_t)9 * E))) return rc;
+    if ((rc = hemo_alloc(ctx, &ctx->mseg_src, nv2 * E))) return rc;
     if ((rc = hemo_alloc(ctx, &ctx->vseg_ptr, (size_t)n + 1))) return rc;
-    if ((rc = hemo_alloc(ctx, &ctx->vseg_src, (size_t)3 * E))) return rc;
+    if ((rc = hemo_alloc(ctx, &ctx->vseg_src, (size_t)nv * E))) return rc;
     int32_t *mcount = nullptr, *vcount = nullptr;
     int* bad = nullptr;
     if ((rc = hemo_alloc(ctx, &mcount, (size_t)nnz_node + 1))) return rc;
@@ -915,7 +927,7 @@ extern "C" int hemo_set_node_graph(hemo_ctx* ctx, const int32_t* nrowptr_dev, co
     HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->diagslot, 0xff, sizeof(int32_t) * n, st));
     k_rowof<<<hemo_grid(n, 256), 256, 0, st>>>(n, nrowptr_dev, ctx->rowof, ncol_dev, ctx->diagslot);
     HEMO_LAUNCH_CHECK(ctx);
-    k_cellpos<<<hemo_grid(E, 256), 256, 0, st>>>(E, ctx->cells, nrowptr_dev, ncol_dev, ctx->cellpos, mcount, vcount, bad);
+    k_cellpos<<<hemo_grid(E, 256), 256, 0, st>>>(E, nv, ctx->cells, nrowptr_dev, ncol_dev, ctx->cellpos, mcount, vcount, bad);
     HEMO_LAUNCH_CHECK(ctx);
     // exclusive scans
     void* tmp = nullptr;
@@ -929,7 +941,7 @@ extern "C" int hemo_set_node_graph(hemo_ctx* ctx, const int32_t* nrowptr_dev, co
     ctx->launches += 2;
     HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(mcount, 0, sizeof(int32_t) * (nnz_node + 1), st));
     HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(vcount, 0, sizeof(int32_t) * (n + 1), st));
-    k_fill_segments<<<hemo_grid(E, 256), 256, 0, st>>>(E, ctx->cells, ctx->cellpos, ctx->mseg_ptr, ctx->vseg_ptr,
+    k_fill_segments<<<hemo_grid(E, 256), 256, 0, st>>>(E, nv, ctx->cells, ctx->cellpos, ctx->mseg_ptr, ctx->vseg_ptr,
                                                        mcount, vcount, ctx->mseg_src, ctx->vseg_src);
     HEMO_LAUNCH_CHECK(ctx);
     k_sort_segments<<<hemo_grid(nnz_node, 256), 256, 0, st>>>(nnz_node, ctx->mseg_ptr, ctx->mseg_src);
@@ -960,8 +972,28 @@ extern "C" int hemo_get_pattern(hemo_ctx* ctx, int64_t* rowptr_dev, int32_t* col
     return 0;
 }
 
+// Quadrilateral rules: points on [0,1]^2 and weights as given.  alias = lowest block id of the
+// same group (residual forms F_u, F_p | Jacobian forms J_uu..J_pp) with an identical rule, so a
+// rule shared by several block forms is integrated once.
+static int set_quadrature_quad(hemo_ctx* ctx, int block, const double* pts, const double* wts, int nq) {
+    if (nq > HEMO_MAXQ_QUAD) HEMO_FAIL(ctx, HEMO_EINVAL, "too many quadrature points for a quadrilateral rule");
+    if (!ctx->qrules) {
+        ctx->qrules = (HemoQuadRule*)calloc(HEMO_NRULES, sizeof(HemoQuadRule));
+        if (!ctx->qrules) HEMO_FAIL(ctx, HEMO_EINVAL, "out of host memory");
+    }
+    HemoQuadRule& r = ctx->qrules[block];
+    r.nq = nq;
+    for (int q = 0; q < nq; ++q) { r.pt[q][0] = pts[2 * q]; r.pt[q][1] = pts[2 * q + 1]; r.pt[q][2] = wts[q]; }
+    ctx->have_rule[block] = true;
+    ctx->qrules_dirty = true;
+    hemo_quad_rule_aliases(ctx->qrules, ctx->have_rule, HEMO_NRULES);
+    return 0;
+}
+
 extern "C" int hemo_set_quadrature(hemo_ctx* ctx, int block, const double* pts, const double* wts, int nq) {
-    if (!ctx || block < 0 || block >= HEMO_NRULES || !pts || !wts || nq <= 0 || nq > HEMO_MAXQ) return HEMO_EINVAL;
+    if (!ctx || block < 0 || block >= HEMO_NRULES || !pts || !wts || nq <= 0) return HEMO_EINVAL;
+    if (ctx->nv == 4) return set_quadrature_quad(ctx, block, pts, wts, nq);
+    if (nq > HEMO_MAXQ) return HEMO_EINVAL;
     HemoRule& r = ctx->rules[block];
     r.nq = nq;
     r.m0 = 0.0;
@@ -1005,6 +1037,7 @@ extern "C" int hemo_set_facet_quadrature(hemo_ctx* ctx, const double* pts, const
     ctx->frule.nq = nq;
     for (int q = 0; q < nq; ++q) { ctx->frule.s[q] = pts[q]; ctx->frule.w[q] = wts[q]; }
     ctx->rules_dirty = true;
+    ctx->qrules_dirty = true;
     return 0;
 }
 
@@ -1013,6 +1046,7 @@ extern "C" int hemo_set_params(hemo_ctx* ctx, const hemo_params* p) {
     ctx->par = *p;
     ctx->have_par = true;
     ctx->rules_dirty = true;
+    ctx->qrules_dirty = true;
     return 0;
 }
 
@@ -1074,30 +1108,38 @@ static int ensure_elem(hemo_ctx* ctx, size_t ae_count, size_t fe_count) {
 
 static int check_ready(hemo_ctx* ctx) {
     if (!ctx->cells || !ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / node graph not set");
-    return upload_constants(ctx);
+    return ctx->nv == 3 ? upload_constants(ctx) : 0;   // the quadrilateral kernels upload their own tables
 }
 
 extern "C" int hemo_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const double* un_dev, double* vals_dev) {
     if (!ctx || !x_dev || !un_dev || !vals_dev) return HEMO_EINVAL;
     int rc = check_ready(ctx);
     if (rc) return rc;
-    const int E = ctx->E, n = ctx->n;
-    if ((rc = ensure_elem(ctx, (size_t)81 * E, 0))) return rc;
+    const int E = ctx->E, n = ctx->n, nv = ctx->nv;
+    if ((rc = ensure_elem(ctx, (size_t)9 * nv * nv * E, 0))) return rc;
     cudaStream_t st = ctx->stream;
     HEMO_PROF_BEGIN(ctx, HEMO_PROF_CELL_JAC);
-    k_cell_jacobian<<<hemo_grid(E, 128), 128, 0, st>>>(E, n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, ctx->Ae);
-    HEMO_LAUNCH_CHECK(ctx);
+    if (nv == 4) {
+        if ((rc = hemo_q1_cell_jacobian(ctx, x_dev, un_dev))) return rc;
+    } else {
+        k_cell_jacobian<<<hemo_grid(E, 128), 128, 0, st>>>(E, n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, ctx->Ae);
+        HEMO_LAUNCH_CHECK(ctx);
+    }
     HEMO_PROF_END(ctx, HEMO_PROF_CELL_JAC);
     for (int s = 0; s < HEMO_MAX_FACET_SETS; ++s) {
         const HemoFacetSet& fs = ctx->fsets[s];
         if (fs.m == 0) continue;
+        if (nv == 4) {
+            if ((rc = hemo_q1_facets(ctx, 1, fs, x_dev, un_dev, nullptr))) return rc;
+            continue;
+        }
         k_facets<1><<<hemo_grid(fs.m, 128), 128, 0, st>>>(fs.m, E, n, fs.cells, fs.mask, fs.coef, ctx->cells, ctx->x,
                                                           ctx->h, x_dev, un_dev, nullptr, nullptr, ctx->Ae);
         HEMO_LAUNCH_CHECK(ctx);
     }
     HEMO_PROF_BEGIN(ctx, HEMO_PROF_GATHER_MAT);
     k_gather_matrix<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(
-        n, ctx->nnz_node, E, ctx->nrowptr, ctx->ncol, ctx->rowof, ctx->mseg_ptr, ctx->mseg_src, ctx->Ae,
+        n, nv * nv, ctx->nnz_node, E, ctx->nrowptr, ctx->ncol, ctx->rowof, ctx->mseg_ptr, ctx->mseg_src, ctx->Ae,
         ctx->have_bc ? ctx->dofflag : nullptr, ctx->dofmult, vals_dev);
     HEMO_LAUNCH_CHECK(ctx);
     HEMO_PROF_END(ctx, HEMO_PROF_GATHER_MAT);
@@ -1110,8 +1152,8 @@ extern "C" int hemo_assemble_residual(hemo_ctx* ctx, const double* x_dev, const 
     if (ctx->have_bc && !g_dev) return HEMO_EINVAL;
     int rc = check_ready(ctx);
     if (rc) return rc;
-    const int E = ctx->E, n = ctx->n;
-    if ((rc = ensure_elem(ctx, 0, (size_t)9 * E))) return rc;
+    const int E = ctx->E, n = ctx->n, nv = ctx->nv;
+    if ((rc = ensure_elem(ctx, 0, (size_t)3 * nv * E))) return rc;
     cudaStream_t st = ctx->stream;
     const uint8_t* cf = ctx->have_bc ? ctx->cellflag : nullptr;
     if (ctx->have_bc) {
@@ -1119,17 +1161,25 @@ extern "C" int hemo_assemble_residual(hemo_ctx* ctx, const double* x_dev, const 
         HEMO_LAUNCH_CHECK(ctx);
     }
     HEMO_PROF_BEGIN(ctx, HEMO_PROF_CELL_RES);
-    k_cell_residual<<<hemo_grid(E, 128), 128, 0, st>>>(E, n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, cf, ctx->dvec, ctx->Fe);
-    HEMO_LAUNCH_CHECK(ctx);
+    if (nv == 4) {
+        if ((rc = hemo_q1_cell_residual(ctx, x_dev, un_dev, cf))) return rc;
+    } else {
+        k_cell_residual<<<hemo_grid(E, 128), 128, 0, st>>>(E, n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, cf, ctx->dvec, ctx->Fe);
+        HEMO_LAUNCH_CHECK(ctx);
+    }
     HEMO_PROF_END(ctx, HEMO_PROF_CELL_RES);
     for (int s = 0; s < HEMO_MAX_FACET_SETS; ++s) {
         const HemoFacetSet& fs = ctx->fsets[s];
         if (fs.m == 0) continue;
+        if (nv == 4) {
+            if ((rc = hemo_q1_facets(ctx, 0, fs, x_dev, un_dev, cf))) return rc;
+            continue;
+        }
         k_facets<0><<<hemo_grid(fs.m, 128), 128, 0, st>>>(fs.m, E, n, fs.cells, fs.mask, fs.coef, ctx->cells, ctx->x,
                                                           ctx->h, x_dev, un_dev, cf, ctx->dvec, ctx->Fe);
         HEMO_LAUNCH_CHECK(ctx);
     }
-    k_gather_vector<<<hemo_grid(n, 256), 256, 0, st>>>(n, E, ctx->vseg_ptr, ctx->vseg_src, ctx->Fe,
+    k_gather_vector<<<hemo_grid(n, 256), 256, 0, st>>>(n, nv, E, ctx->vseg_ptr, ctx->vseg_src, ctx->Fe,
                                                        ctx->have_bc ? ctx->dofflag : nullptr, x_dev, g_dev, b_dev);
     HEMO_LAUNCH_CHECK(ctx);
     return 0;
@@ -1142,8 +1192,12 @@ extern "C" int hemo_outlet_flux(hemo_ctx* ctx, int set_id, const double* un_dev,
     int rc = hemo_ensure_reduce(ctx, (size_t)fs.m, 8);
     if (rc) return rc;
     cudaStream_t st = ctx->stream;
-    k_facet_flux<<<hemo_grid(fs.m, 128), 128, 0, st>>>(fs.m, fs.cells, fs.mask, ctx->cells, ctx->x, un_dev, ctx->red_partial);
-    HEMO_LAUNCH_CHECK(ctx);
+    if (ctx->nv == 4) {
+        if ((rc = hemo_q1_facet_flux(ctx, fs, un_dev, ctx->red_partial))) return rc;
+    } else {
+        k_facet_flux<<<hemo_grid(fs.m, 128), 128, 0, st>>>(fs.m, fs.cells, fs.mask, ctx->cells, ctx->x, un_dev, ctx->red_partial);
+        HEMO_LAUNCH_CHECK(ctx);
+    }
     k_sum_serial<<<1, 256, 0, st>>>(fs.m, ctx->red_partial, ctx->red_out);
     HEMO_LAUNCH_CHECK(ctx);
     HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->red_host, ctx->red_out, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1155,17 +1209,21 @@ extern "C" int hemo_outlet_flux(hemo_ctx* ctx, int set_id, const double* un_dev,
 extern "C" int hemo_assemble_laplace_mass(hemo_ctx* ctx, double* lap_vals_dev, double* mass_dev) {
     if (!ctx || !lap_vals_dev || !mass_dev) return HEMO_EINVAL;
     if (!ctx->cells || !ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / node graph not set");
-    const int E = ctx->E, n = ctx->n;
+    const int E = ctx->E, n = ctx->n, nv = ctx->nv;
     int rc;
-    if ((rc = ensure_elem(ctx, (size_t)9 * E, (size_t)3 * E))) return rc;
+    if ((rc = ensure_elem(ctx, (size_t)nv * nv * E, (size_t)nv * E))) return rc;
     cudaStream_t st = ctx->stream;
-    // reuse the element buffers: Ke -> Ae[0..9E), Me -> Fe[0..3E)
-    k_cell_laplace<<<hemo_grid(E, 256), 256, 0, st>>>(E, ctx->cells, ctx->x, ctx->Ae, ctx->Fe);
+    // reuse the element buffers: Ke -> Ae[0..nv*nv*E), Me -> Fe[0..nv*E)
+    if (nv == 4) {
+        if ((rc = hemo_q1_laplace_mass(ctx))) return rc;
+    } else {
+        k_cell_laplace<<<hemo_grid(E, 256), 256, 0, st>>>(E, ctx->cells, ctx->x, ctx->Ae, ctx->Fe);
+        HEMO_LAUNCH_CHECK(ctx);
+    }
+    k_gather_scalar_matrix<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(nv * nv, ctx->nnz_node, E, ctx->mseg_ptr,
+                                                                          ctx->mseg_src, ctx->Ae, lap_vals_dev);
     HEMO_LAUNCH_CHECK(ctx);
-    k_gather_scalar_matrix<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(ctx->nnz_node, E, ctx->mseg_ptr, ctx->mseg_src,
-                                                                          ctx->Ae, lap_vals_dev);
-    HEMO_LAUNCH_CHECK(ctx);
-    k_gather_scalar_vector<<<hemo_grid(n, 256), 256, 0, st>>>(n, E, ctx->vseg_ptr, ctx->vseg_src, ctx->Fe, mass_dev);
+    k_gather_scalar_vector<<<hemo_grid(n, 256), 256, 0, st>>>(n, nv, E, ctx->vseg_ptr, ctx->vseg_src, ctx->Fe, mass_dev);
     HEMO_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -1289,6 +1347,7 @@ extern "C" int hemo_pc_set_schur_operator(hemo_ctx* ctx, const double* x_dev, co
     if (!ctx || !x_dev || !un_dev || !vals_dev) return HEMO_EINVAL;
     if (!ctx->cells || !ctx->nrowptr || !ctx->have_par) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / node graph / params not set");
     if (!ctx->amg[1].ready) HEMO_FAIL(ctx, HEMO_ESTATE, "pressure AMG hierarchy not finalized");
+    if (ctx->nv != 3) HEMO_FAIL(ctx, HEMO_ESTATE, "the assembled Schur operator is implemented for triangles only");
     const int E = ctx->E, n = ctx->n;
     int rc;
     if ((rc = ensure_elem(ctx, (size_t)9 * E, 0))) return rc;
@@ -1297,7 +1356,7 @@ extern "C" int hemo_pc_set_schur_operator(hemo_ctx* ctx, const double* x_dev, co
     k_cell_kappa_laplace<<<hemo_grid(E, 256), 256, 0, st>>>(E, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, ctx->par.rho,
                                                            ctx->par.dt, c_u, ctx->Ae);
     HEMO_LAUNCH_CHECK(ctx);
-    k_gather_scalar_matrix<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(ctx->nnz_node, E, ctx->mseg_ptr, ctx->mseg_src,
+    k_gather_scalar_matrix<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(9, ctx->nnz_node, E, ctx->mseg_ptr, ctx->mseg_src,
                                                                           ctx->Ae, ctx->schur_tmp);
     HEMO_LAUNCH_CHECK(ctx);
     k_build_schur_operator<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(
@@ -1313,6 +1372,7 @@ extern "C" int hemo_pc_set_convection(hemo_ctx* ctx, const double* x_dev, const 
     if (coef == 0.0) return 0;
     if (!x_dev || !un_dev) return HEMO_EINVAL;
     if (!ctx->cells || !ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / node graph not set");
+    if (ctx->nv != 3) HEMO_FAIL(ctx, HEMO_ESTATE, "the pressure convection term is implemented for triangles only");
     const int E = ctx->E;
     int rc;
     if ((rc = ensure_elem(ctx, (size_t)9 * E, 0))) return rc;
@@ -1320,7 +1380,7 @@ extern "C" int hemo_pc_set_convection(hemo_ctx* ctx, const double* x_dev, const 
     cudaStream_t st = ctx->stream;
     k_cell_pconv<<<hemo_grid(E, 256), 256, 0, st>>>(E, ctx->cells, ctx->x, x_dev, un_dev, ctx->Ae);
     HEMO_LAUNCH_CHECK(ctx);
-    k_gather_scalar_matrix_areal<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(ctx->nnz_node, E, ctx->mseg_ptr,
+    k_gather_scalar_matrix_areal<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(9, ctx->nnz_node, E, ctx->mseg_ptr,
                                                                                 ctx->mseg_src, ctx->Ae, ctx->npconv);
     HEMO_LAUNCH_CHECK(ctx);
     return 0;

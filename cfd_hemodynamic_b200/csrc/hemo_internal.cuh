@@ -7,9 +7,9 @@
 #include <vector>
 
 #include "../../include/hemo.h"
+#include "hemo_rules.h"
 
 #define HEMO_MAXQ 80          // max cell quadrature points per rule (P2 needs 79)
-#define HEMO_MAXFQ 8          // max facet quadrature points
 #define HEMO_NRULES 6
 #define HEMO_MAX_FACET_SETS 8
 #define HEMO_MAX_LEVELS 16
@@ -34,12 +34,6 @@ struct HemoRule {
     double phi[HEMO_MAXQ][3];
     double w[HEMO_MAXQ];
     double m0, m1[3], m2[6];  // polynomial moments of the rule (reference cell)
-};
-
-struct HemoFacetRule {
-    int nq;
-    double s[HEMO_MAXFQ];
-    double w[HEMO_MAXFQ];
 };
 
 struct HemoFacetSet {
@@ -130,6 +124,7 @@ struct hemo_ctx {
     int64_t launches = 0;
 
     // mesh (borrowed)
+    int nv = 3;                     // nodes per cell: 3 = P1 triangle, 4 = Q1 quadrilateral (tensor-ordered)
     const double* x = nullptr;
     const int32_t* cells = nullptr;
     const double* h = nullptr;
@@ -138,15 +133,15 @@ struct hemo_ctx {
     const int32_t* nrowptr = nullptr;
     const int32_t* ncol = nullptr;
     int64_t nnz_node = 0;
-    int32_t* cellpos = nullptr;     // E*9: slot of node b in row of node a
+    int32_t* cellpos = nullptr;     // E*nv*nv: slot of node b in row of node a
     int32_t* mseg_ptr = nullptr;    // nnz_node+1 gather segments (matrix)
-    int32_t* mseg_src = nullptr;    // 9E: c*9 + a*3 + b
+    int32_t* mseg_src = nullptr;    // nv*nv*E: c*nv*nv + a*nv + b
     int32_t* vseg_ptr = nullptr;    // n+1 gather segments (vector)
-    int32_t* vseg_src = nullptr;    // 3E: c*3 + a
+    int32_t* vseg_src = nullptr;    // nv*E: c*nv + a
     int32_t* diagslot = nullptr;    // n: slot of node i in its own row
     int32_t* rowof = nullptr;       // nnz_node: row (node) of each slot
-    double* Ae = nullptr;           // 81*E element matrices, SoA [81][E] (allocated on first use)
-    double* Fe = nullptr;           // 9*E element vectors, SoA [9][E]
+    double* Ae = nullptr;           // 9*nv*nv*E element matrices, SoA [(a*nv+b)*9 + ri*3+ci][E] (allocated on first use)
+    double* Fe = nullptr;           // 3*nv*E element vectors, SoA [a*3 + comp][E]
     size_t Ae_count = 0, Fe_count = 0;
     int external_schur = 0;         // 1: hemo_pc_apply takes z_p from the caller (multi-GPU global pressure solve)
     double* dvec = nullptr;         // 3n lifting vector (g - x on bc dofs)
@@ -157,6 +152,8 @@ struct hemo_ctx {
     HemoRule rules[HEMO_NRULES];
     bool have_rule[HEMO_NRULES] = {false, false, false, false, false, false};
     bool rules_dirty = true;
+    HemoQuadRule* qrules = nullptr; // HEMO_NRULES host-side rules of the quadrilateral path (allocated on first use)
+    bool qrules_dirty = true;
     HemoFacetRule frule{};
     HemoFacetSet fsets[HEMO_MAX_FACET_SETS];
     uint8_t* dofflag = nullptr;
@@ -265,6 +262,13 @@ static inline int hemo_grid(int64_t n, int block) {
     return (int)g;
 }
 
+// implemented in assembly_q1.cu (Q1 quadrilateral cell / facet kernels)
+int hemo_q1_cell_jacobian(hemo_ctx* ctx, const double* x_dev, const double* un_dev);
+int hemo_q1_cell_residual(hemo_ctx* ctx, const double* x_dev, const double* un_dev, const uint8_t* cellflag);
+int hemo_q1_facets(hemo_ctx* ctx, int mode, const HemoFacetSet& fs, const double* x_dev, const double* un_dev,
+                   const uint8_t* cellflag);
+int hemo_q1_facet_flux(hemo_ctx* ctx, const HemoFacetSet& fs, const double* un_dev, double* partial);
+int hemo_q1_laplace_mass(hemo_ctx* ctx);
 // implemented in linalg.cu
 int hemo_ensure_reduce(hemo_ctx* ctx, size_t partial_n, size_t out_n);
 int hemo_dot_dev(hemo_ctx* ctx, int64_t n, const double* x, const double* y, double* out_host);

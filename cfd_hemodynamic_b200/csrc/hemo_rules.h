@@ -1,0 +1,42 @@
+// Quadrature-rule tables shared by the device code and the host-compiled checks of the
+// element routines (tests/host_q1): plain structs, no CUDA types.
+#pragma once
+
+#define HEMO_MAXFQ 8          // max facet quadrature points
+
+struct HemoFacetRule {
+    int nq;
+    double s[HEMO_MAXFQ];
+    double w[HEMO_MAXFQ];
+};
+
+// Cell rule of one block form on the reference quadrilateral [0,1]^2: points and weights as
+// given (Basix: tensor Gauss-Jacobi, 12 x 12 points for the degree-22 forms); the Q1 basis
+// and the bilinear geometry are evaluated from (xi, eta) on the fly.
+#define HEMO_MAXQ_QUAD 196
+struct HemoQuadRule {
+    int nq;
+    int alias;                      // lowest block id with an identical rule
+    double pt[HEMO_MAXQ_QUAD][3];   // xi, eta, weight
+};
+
+
+// alias = lowest block id of the same group (residual forms F_u, F_p = ids 0, 1 | Jacobian forms
+// J_uu..J_pp = ids 2..5) with an identical rule, so that a rule shared by several block forms is
+// integrated once.
+static inline void hemo_quad_rule_aliases(HemoQuadRule* rules, const bool* have, int nrules) {
+    for (int b = 0; b < nrules; ++b) {
+        if (!have[b]) continue;
+        HemoQuadRule& rb = rules[b];
+        rb.alias = b;
+        const int first = (b <= 1) ? 0 : 2;
+        for (int a = first; a < b; ++a) {
+            if (!have[a] || rules[a].nq != rb.nq) continue;
+            bool same = true;
+            for (int q = 0; q < rb.nq && same; ++q)
+                same = rules[a].pt[q][0] == rb.pt[q][0] && rules[a].pt[q][1] == rb.pt[q][1] &&
+                       rules[a].pt[q][2] == rb.pt[q][2];
+            if (same) { rb.alias = a; break; }
+        }
+    }
+}

@@ -66,11 +66,17 @@ class _IndexMap:
         self.owners = np.zeros(0, dtype=np.int32)
 
 
-class _Topology:
-    """Cell/facet/vertex connectivity for simplices (triangle, tetrahedron)."""
+# local facets of a tensor-ordered quadrilateral (3P Basix numbering)
+QUAD_FACETS = ((0, 1), (0, 2), (1, 3), (2, 3))
 
-    def __init__(self, cells: np.ndarray, tdim: int, nverts: int):
+
+class _Topology:
+    """Cell/facet/vertex connectivity for simplices (triangle, tetrahedron) and
+    tensor-ordered quadrilaterals."""
+
+    def __init__(self, cells: np.ndarray, tdim: int, nverts: int, cell_type: str | None = None):
         self.dim = tdim
+        self._cell_type = cell_type or {2: "triangle", 3: "tetrahedron"}[tdim]
         self._cells = cells
         self._nverts = nverts
         self._facets = None
@@ -80,29 +86,36 @@ class _Topology:
         self._f2c_local = None
 
     def cell_name(self) -> str:
-        return {2: "triangle", 3: "tetrahedron"}[self.dim]
+        return self._cell_type
 
     # -- lazily built facet tables ------------------------------------
     def _build_facets(self):
         if self._facets is not None:
             return
         c = self._cells
-        nv = c.shape[1]
-        # local facet i = all vertices except vertex i
-        loc = [[j for j in range(nv) if j != i] for i in range(nv)]
-        fv = np.stack([c[:, l] for l in loc], axis=1)            # (E, nv, nv-1)
-        fv_sorted = np.sort(fv.reshape(-1, nv - 1), axis=1)
+        if self._cell_type == "quadrilateral":
+            loc = [list(f) for f in QUAD_FACETS]
+        else:
+            # local facet i = all vertices except vertex i
+            loc = [[j for j in range(c.shape[1]) if j != i] for i in range(c.shape[1])]
+        nfv = len(loc[0])                                        # vertices per facet
+        fv = np.stack([c[:, l] for l in loc], axis=1)            # (E, facets per cell, nfv)
+        self._finish_facets(np.sort(fv.reshape(-1, nfv), axis=1), nfv, len(loc))
+
+    def _finish_facets(self, fv_sorted, nfv, nv):
+        """fv_sorted: (E*nv, nfv) sorted vertex tuples of every (cell, local facet)."""
+        c = self._cells
         # pack the sorted vertex tuple into one int64 key (1-D unique is much
         # faster than axis=0 unique on 10^7 facets)
         n = np.int64(self._nverts)
         key = fv_sorted[:, 0].astype(np.int64)
-        for k in range(1, nv - 1):
+        for k in range(1, nfv):
             key = key * n + fv_sorted[:, k]
         ukey, inv, counts = np.unique(key, return_inverse=True, return_counts=True)
         inv = inv.reshape(-1)
-        uniq = np.empty((ukey.shape[0], nv - 1), dtype=np.int64)
+        uniq = np.empty((ukey.shape[0], nfv), dtype=np.int64)
         rem = ukey
-        for k in range(nv - 2, -1, -1):
+        for k in range(nfv - 1, -1, -1):
             uniq[:, k] = rem % n
             rem = rem // n
         self._facets = uniq.astype(np.int32)
@@ -152,17 +165,26 @@ class _Topology:
 
 
 class Mesh:
-    """Simplicial mesh; P1 geometry (geometry dofmap == vertex list)."""
+    """Simplicial or quadrilateral mesh; degree-1 geometry (geometry dofmap ==
+    vertex list).  `cell_type="quadrilateral"`: 4 tensor-ordered vertices per
+    cell, (0,0),(1,0),(0,1),(1,1) — what gmshio.model_to_mesh yields for the
+    recombined transfinite mesh of the reference
+    (src/scenarios/stenosis_pressure_structured.py:379-386)."""
 
-    def __init__(self, x: np.ndarray, cells: np.ndarray, comm=None):
+    def __init__(self, x: np.ndarray, cells: np.ndarray, comm=None, cell_type: str | None = None):
         x = np.asarray(x, dtype=np.float64)
         if x.shape[1] == 2:
             x = np.hstack([x, np.zeros((x.shape[0], 1))])
         cells = np.ascontiguousarray(cells, dtype=np.int32)
-        tdim = cells.shape[1] - 1
+        if cell_type == "quadrilateral":
+            if cells.shape[1] != 4:
+                raise ValueError("quadrilateral cells need 4 vertices")
+            tdim = 2
+        else:
+            tdim = cells.shape[1] - 1
         # all BASELINE configs have gdim == tdim
         self.geometry = _Geometry(np.ascontiguousarray(x), cells, tdim)
-        self.topology = _Topology(cells, tdim, x.shape[0])
+        self.topology = _Topology(cells, tdim, x.shape[0], cell_type)
         self.comm = comm if comm is not None else SerialComm()
         self.name = "mesh"
 
@@ -226,20 +248,33 @@ def locate_entities_boundary(mesh: Mesh, dim: int, marker) -> np.ndarray:
     return ext[keep]
 
 
-def create_mesh(x, cells, comm=None) -> Mesh:
-    return Mesh(x, cells, comm)
+def create_mesh(x, cells, comm=None, cell_type: str | None = None) -> Mesh:
+    return Mesh(x, cells, comm, cell_type)
 
 
-def create_rectangle(p0, p1, nx: int, ny: int, diagonal: str = "right", comm=None) -> Mesh:
-    """Structured triangle mesh of a rectangle.  "right" diagonal matches
+def create_rectangle(p0, p1, nx: int, ny: int, diagonal: str = "right", comm=None,
+                     cell_type: str = "triangle") -> Mesh:
+    """Structured mesh of a rectangle.  Triangles: "right" diagonal matches
     `dolfinx.mesh.create_unit_square` default used by the lid cavity
-    (reference src/scenarios/lid_driven2D.py:30)."""
+    (reference src/scenarios/lid_driven2D.py:30).  `cell_type="quadrilateral"`
+    gives the tensor-ordered Q1 grid (`CellType.quadrilateral`, reference
+    src/scenarios/unit_square.py:36-38)."""
     xs = np.linspace(p0[0], p1[0], nx + 1)
     ys = np.linspace(p0[1], p1[1], ny + 1)
     X, Y = np.meshgrid(xs, ys, indexing="xy")
     pts = np.stack([X.ravel(), Y.ravel()], axis=1)
+    if cell_type == "quadrilateral":
+        return Mesh(pts, grid_quads(nx, ny), comm, cell_type)
     cells = _split_grid(nx, ny, diagonal)
     return Mesh(pts, cells, comm)
+
+
+def grid_quads(nx: int, ny: int) -> np.ndarray:
+    """(nx*ny, 4) tensor-ordered quadrilaterals of an (nx+1) x (ny+1) vertex grid
+    numbered row by row (x fastest)."""
+    ix, iy = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    v0 = (iy * (nx + 1) + ix).ravel()
+    return np.stack([v0, v0 + 1, v0 + (nx + 1), v0 + (nx + 2)], axis=1).astype(np.int32)
 
 
 def _split_grid(nx: int, ny: int, diagonal: str = "right") -> np.ndarray:
@@ -262,6 +297,6 @@ def _split_grid(nx: int, ny: int, diagonal: str = "right") -> np.ndarray:
     return cells
 
 
-def create_unit_square(comm, nx: int, ny: int, diagonal: str = "right") -> Mesh:
-    """Same call shape as `dolfinx.mesh.create_unit_square(comm, nx, ny)`."""
-    return create_rectangle((0.0, 0.0), (1.0, 1.0), nx, ny, diagonal, comm)
+def create_unit_square(comm, nx: int, ny: int, diagonal: str = "right", cell_type: str = "triangle") -> Mesh:
+    """Same call shape as `dolfinx.mesh.create_unit_square(comm, nx, ny[, cell_type])`."""
+    return create_rectangle((0.0, 0.0), (1.0, 1.0), nx, ny, diagonal, comm, cell_type)

@@ -30,14 +30,31 @@ import numpy as np
 
 __all__ = [
     "triangle_symmetric", "triangle_gauss_jacobi", "interval_gauss",
-    "triangle_rule", "check_triangle_rule", "expand_orbits",
+    "triangle_rule", "check_triangle_rule", "expand_orbits", "quadrilateral_rule",
+    "FACET_POINTS_QUAD",
 ]
+
+# Facet rule on quadrilateral meshes: the traces of Q1 functions are linear, the backflow term
+# (u_n.n)_- (u_m.v) is cubic apart from the kink and grad(u) is rational on non-affine cells;
+# 4 Gauss points (degree 7) for every tagged ds integral.
+FACET_POINTS_QUAD = 4
 
 
 def interval_gauss(npts: int):
     """Gauss–Legendre on [0,1]; npts = (degree + 2)//2 (3P Basix GJ rule)."""
     x, w = np.polynomial.legendre.leggauss(npts)
     return 0.5 * (x + 1.0), 0.5 * w
+
+
+def quadrilateral_rule(degree: int):
+    """Default Basix scheme on the reference quadrilateral [0,1]^2: tensor product of the
+    m-point Gauss–Jacobi (alpha = 0, i.e. Gauss–Legendre) rule, m = (degree + 2) // 2;
+    first coordinate slowest; weights sum to 1."""
+    m = (degree + 2) // 2
+    x, w = interval_gauss(m)
+    pts = np.stack([np.repeat(x, m), np.tile(x, m)], axis=1)
+    wts = np.repeat(w, m) * np.tile(w, m)
+    return pts, wts
 
 
 def _gauss_jacobi(n: int, alpha: float):

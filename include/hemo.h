@@ -18,7 +18,8 @@
  * Global dof layout (3P `create_vector_block`, trigger
  * src/solvers/stabilized_schur.py:191-193): x = [u interleaved (2*n) | p (n)].
  * Matrix: one CSR, rows in that order, columns ascending, full FE pattern
- * (explicit zeros kept), int32 indices (nnz = 9 * nnz_node).
+ * (explicit zeros kept), int32 indices (nnz = 9 * nnz_node).  P1 triangles and Q1
+ * quadrilaterals share this layout: one (u_x, u_y, p) triple per mesh vertex.
  */
 #ifndef HEMO_H
 #define HEMO_H
@@ -96,8 +97,15 @@ int hemo_prof_enable(hemo_ctx* ctx, int on);
 int hemo_prof_get(hemo_ctx* ctx, int kernel_class, double* ms_total, int64_t* launches);
 
 /* ---- mesh, spaces, pattern ---------------------------------------------- */
+/* mesh.topology.cell_name() (src/solvers/stabilized_schur.py:55-58): P1 triangles (default)
+ * or Q1 quadrilaterals with tensor-ordered vertices (0,0),(1,0),(0,1),(1,1) — the cells of the
+ * recombined transfinite mesh, src/scenarios/stenosis_pressure_structured.py:379-386.  Call
+ * before hemo_set_mesh; quadrature rules set earlier are dropped (rules belong to a cell type:
+ * triangle rules have weights summing to 1/2, quadrilateral rules live on [0,1]^2 and sum to 1). */
+enum { HEMO_CELL_TRIANGLE = 0, HEMO_CELL_QUADRILATERAL = 1 };
+int hemo_set_cell_type(hemo_ctx* ctx, int cell_type);
 /* mesh.geometry.x / .dofmap / mesh.h (src/solvers/stabilized_schur.py:55-58,83-88).
- * x: n_nodes*2 doubles, cells: n_cells*3 int32, h: n_cells doubles; borrowed. */
+ * x: n_nodes*2 doubles, cells: n_cells*(3|4) int32, h: n_cells doubles; borrowed. */
 int hemo_set_mesh(hemo_ctx* ctx, const double* x_dev, int n_nodes,
                   const int32_t* cells_dev, int n_cells, const double* h_dev);
 /* Node adjacency (CSR, sorted, diagonal included) = scalar P1 sparsity graph;
@@ -111,14 +119,16 @@ int hemo_matrix_nnz(hemo_ctx* ctx, int64_t* nnz);
 int hemo_get_pattern(hemo_ctx* ctx, int64_t* rowptr_dev, int32_t* colind_dev);
 
 /* ---- forms ---------------------------------------------------------------- */
-/* Quadrature rule of one block form (host arrays; pts = nq*2 reference coords,
- * wts sum to 1/2).  Basix rule selected by FFCx at form() (:188-189). */
+/* Quadrature rule of one block form (host arrays; pts = nq*2 reference coords; triangles:
+ * wts sum to 1/2, nq <= 80; quadrilaterals: points on [0,1]^2, wts sum to 1, nq <= 196).
+ * Basix rule selected by FFCx at form() (:188-189). */
 int hemo_set_quadrature(hemo_ctx* ctx, int block, const double* pts_host,
                         const double* wts_host, int nq);
 /* Facet rule on [0,1] shared by all exterior-facet integrals. */
 int hemo_set_facet_quadrature(hemo_ctx* ctx, const double* pts_host, const double* wts_host, int nq);
 int hemo_set_params(hemo_ctx* ctx, const hemo_params* p);
-/* One tagged ds integral: unique boundary cells with a 3-bit mask of the
+/* One tagged ds integral: unique boundary cells with a 3-bit (triangle) or 4-bit
+ * (quadrilateral: facets (0,1),(0,2),(1,3),(2,3)) mask of the
  * local facets that carry the tag (Measure("ds", subdomain_id=...),
  * src/solvers/stabilized_schur_pressure_backflow.py:170-181).  m = 0 removes
  * the set.  Arrays are copied. */

@@ -72,7 +72,7 @@ class FacetSet:
 @dataclass
 class Problem:
     x: np.ndarray                     # (n, 2)
-    cells: np.ndarray                 # (E, 3) int32
+    cells: np.ndarray                 # (E, 3) int32 triangles | (E, 4) tensor-ordered quadrilaterals
     h: np.ndarray                     # (E,)
     dt: float
     rho: float
@@ -307,7 +307,9 @@ def facet_F(prob, fs: FacetSet, U, P, Un):
 def outlet_flux(prob, pairs, Un_nodal):
     """Q = int u_prev . n ds over the given facets
     (pressure_backflow.py:204-211, 383-385)."""
-    fs = FacetSet(pairs=pairs)
+    if prob.cells.shape[1] == 4:
+        from . import q1_oracle
+        return q1_oracle.outlet_flux(prob, pairs, Un_nodal)
     cells = prob.cells[pairs[:, 0]]
     lf = pairs[:, 1]
     X = prob.x[cells]
@@ -331,12 +333,23 @@ def _gather(prob, u, p, un):
     return u.reshape(-1, 2)[c], p[c], un.reshape(-1, 2)[c]
 
 
+def _kernels(prob):
+    """Element routines for the problem's cell type: this module for P1
+    triangles, oracle/q1_oracle.py for Q1 quadrilaterals (4 nodes per cell)."""
+    if prob.cells.shape[1] == 4:
+        from . import q1_oracle
+        return q1_oracle
+    import sys
+    return sys.modules[__name__]
+
+
 def local_to_global(prob):
-    """(E, 9) global dof of each element-local dof; local order
-    [u(a=0,k=0), u(0,1), u(1,0), ..., p0, p1, p2]; global [u interleaved | p]."""
+    """(E, 3*nv) global dof of each element-local dof; local order
+    [u(a=0,k=0), u(0,1), u(1,0), ..., p0, p1, ...]; global [u interleaved | p]."""
     c = prob.cells.astype(np.int64)
     n = prob.n
-    ud = (2 * c[:, :, None] + np.arange(2)[None, None, :]).reshape(-1, 6)
+    nv = c.shape[1]
+    ud = (2 * c[:, :, None] + np.arange(2)[None, None, :]).reshape(-1, 2 * nv)
     pd = 2 * n + c
     return np.hstack([ud, pd])
 
@@ -345,8 +358,9 @@ def sparsity_pattern(prob):
     """Full FE pattern, sorted unique columns per row (3P create_matrix_block;
     trigger stabilized_schur.py:191)."""
     l2g = local_to_global(prob)
-    rows = np.repeat(l2g, 9, axis=1).reshape(-1)
-    cols = np.tile(l2g, (1, 9)).reshape(-1)
+    nl = l2g.shape[1]
+    rows = np.repeat(l2g, nl, axis=1).reshape(-1)
+    cols = np.tile(l2g, (1, nl)).reshape(-1)
     A = sp.coo_matrix((np.ones(rows.shape[0]), (rows, cols)), shape=(prob.ndof, prob.ndof)).tocsr()
     A.sort_indices()
     return A.indptr.astype(np.int64), A.indices.astype(np.int32)
@@ -354,54 +368,61 @@ def sparsity_pattern(prob):
 
 def assemble_F_raw(prob, u, p, un):
     """Residual without Dirichlet treatment (cells + facets)."""
+    K = _kernels(prob)
     U, P, Un = _gather(prob, u, p, un)
-    Fu, _ = element_F(prob, U, P, Un, prob.rules["Fu"])
-    _, Fp = element_F(prob, U, P, Un, prob.rules["Fp"])
+    nv = prob.cells.shape[1]
+    Fu, _ = K.element_F(prob, U, P, Un, prob.rules["Fu"])
+    _, Fp = K.element_F(prob, U, P, Un, prob.rules["Fp"])
     b = np.zeros(prob.ndof, dtype=Fu.dtype)
     l2g = local_to_global(prob)
-    np.add.at(b, l2g[:, :6].reshape(-1), Fu.reshape(-1))
-    np.add.at(b, l2g[:, 6:].reshape(-1), Fp.reshape(-1))
+    np.add.at(b, l2g[:, :2 * nv].reshape(-1), Fu.reshape(-1))
+    np.add.at(b, l2g[:, 2 * nv:].reshape(-1), Fp.reshape(-1))
     for fs in prob.facet_sets:
         ce = fs.pairs[:, 0]
-        Fu_f = facet_F(prob, fs, U[ce], P[ce], Un[ce])
-        np.add.at(b, l2g[ce][:, :6].reshape(-1), Fu_f.reshape(-1))
+        Fu_f = K.facet_F(prob, fs, U[ce], P[ce], Un[ce])
+        np.add.at(b, l2g[ce][:, :2 * nv].reshape(-1), Fu_f.reshape(-1))
     return b
 
 
 def element_matrices(prob, u, p, un):
-    """(E, 9, 9) cell element matrices with per-block quadrature."""
+    """(E, 3nv, 3nv) cell element matrices with per-block quadrature."""
+    K = _kernels(prob)
     U, P, Un = _gather(prob, u, p, un)
-    E = prob.cells.shape[0]
-    Ae = np.zeros((E, 9, 9))
-    Juu, _, _, _ = element_J(prob, U, P, Un, prob.rules["uu"])
-    _, Jup, _, _ = element_J(prob, U, P, Un, prob.rules["up"])
-    _, _, Jpu, _ = element_J(prob, U, P, Un, prob.rules["pu"])
-    _, _, _, Jpp = element_J(prob, U, P, Un, prob.rules["pp"])
-    Ae[:, :6, :6] = Juu.reshape(E, 6, 6)
-    Ae[:, :6, 6:] = Jup.reshape(E, 6, 3)
-    Ae[:, 6:, :6] = Jpu.reshape(E, 3, 6)
-    Ae[:, 6:, 6:] = Jpp
+    E, nv = prob.cells.shape
+    nu = 2 * nv
+    Ae = np.zeros((E, 3 * nv, 3 * nv))
+    Juu, _, _, _ = K.element_J(prob, U, P, Un, prob.rules["uu"])
+    _, Jup, _, _ = K.element_J(prob, U, P, Un, prob.rules["up"])
+    _, _, Jpu, _ = K.element_J(prob, U, P, Un, prob.rules["pu"])
+    _, _, _, Jpp = K.element_J(prob, U, P, Un, prob.rules["pp"])
+    Ae[:, :nu, :nu] = Juu.reshape(E, nu, nu)
+    Ae[:, :nu, nu:] = Jup.reshape(E, nu, nv)
+    Ae[:, nu:, :nu] = Jpu.reshape(E, nv, nu)
+    Ae[:, nu:, nu:] = Jpp
     return Ae
 
 
 def facet_matrices(prob, fs: FacetSet, un):
-    """(m, 6, 9) d(Fu_facet)/d(U,P): the facet terms are affine in (U,P), so
+    """(m, 2nv, 3nv) d(Fu_facet)/d(U,P): the facet terms are affine in (U,P), so
     the exact derivative is obtained column by column from unit vectors."""
+    K = _kernels(prob)
     ce = fs.pairs[:, 0]
     m = ce.shape[0]
+    nv = prob.cells.shape[1]
+    nu = 2 * nv
     Unc = un.reshape(-1, 2)[prob.cells[ce]]
-    Z2 = np.zeros((m, 3, 2))
-    Z1 = np.zeros((m, 3))
-    F0 = facet_F(prob, fs, Z2, Z1, Unc)
-    out = np.zeros((m, 6, 9))
-    for j in range(9):
+    Z2 = np.zeros((m, nv, 2))
+    Z1 = np.zeros((m, nv))
+    F0 = K.facet_F(prob, fs, Z2, Z1, Unc)
+    out = np.zeros((m, nu, 3 * nv))
+    for j in range(3 * nv):
         U = Z2.copy()
         P = Z1.copy()
-        if j < 6:
+        if j < nu:
             U[:, j // 2, j % 2] = 1.0
         else:
-            P[:, j - 6] = 1.0
-        out[:, :, j] = (facet_F(prob, fs, U, P, Unc) - F0).reshape(m, 6)
+            P[:, j - nu] = 1.0
+        out[:, :, j] = (K.facet_F(prob, fs, U, P, Unc) - F0).reshape(m, nu)
     return out
 
 
@@ -409,15 +430,17 @@ def assemble_J_raw(prob, u, p, un):
     """Jacobian (CSR, full FE pattern, explicit zeros kept) without BCs."""
     Ae = element_matrices(prob, u, p, un)
     l2g = local_to_global(prob)
-    rows = np.repeat(l2g, 9, axis=1).reshape(-1)
-    cols = np.tile(l2g, (1, 9)).reshape(-1)
+    nl = l2g.shape[1]
+    nu = 2 * prob.cells.shape[1]
+    rows = np.repeat(l2g, nl, axis=1).reshape(-1)
+    cols = np.tile(l2g, (1, nl)).reshape(-1)
     vals = Ae.reshape(-1)
     for fs in prob.facet_sets:
         ce = fs.pairs[:, 0]
         Af = facet_matrices(prob, fs, un)
         lg = l2g[ce]
-        rows = np.concatenate([rows, np.repeat(lg[:, :6], 9, axis=1).reshape(-1)])
-        cols = np.concatenate([cols, np.tile(lg, (1, 6)).reshape(-1)])
+        rows = np.concatenate([rows, np.repeat(lg[:, :nu], nl, axis=1).reshape(-1)])
+        cols = np.concatenate([cols, np.tile(lg, (1, nu)).reshape(-1)])
         vals = np.concatenate([vals, Af.reshape(-1)])
     A = sp.coo_matrix((vals, (rows, cols)), shape=(prob.ndof, prob.ndof)).tocsr()
     A.sort_indices()

@@ -10,21 +10,25 @@ from cfd_hemodynamic_b200.fem import discretization as D
 from oracle import ns_oracle as O
 
 BLOCK_DEGREE = {"Fu": 12, "Fp": 11, "uu": 12, "up": 11, "pu": 11, "pp": 10}
+# Q1 quadrilaterals: hand-derived UFL degrees 22 / 20 / 18 -> m = (deg + 2) // 2
+BLOCK_DEGREE_QUAD = {"Fu": 22, "Fp": 20, "uu": 22, "up": 20, "pu": 20, "pp": 18}
 BLOCK_ID = {"Fu": 0, "Fp": 1, "uu": 2, "up": 3, "pu": 4, "pp": 5}
 
 
-def default_rules():
+def default_rules(cell_type="triangle"):
+    if cell_type == "quadrilateral":
+        return {k: Q.quadrilateral_rule(d) for k, d in BLOCK_DEGREE_QUAD.items()}
     return {k: Q.triangle_rule(d) for k, d in BLOCK_DEGREE.items()}
 
 
-def perturbed_square(nx, ny, seed=0, amp=0.25):
-    m = M.create_unit_square(None, nx, ny)
+def perturbed_square(nx, ny, seed=0, amp=0.25, cell_type="triangle"):
+    m = M.create_unit_square(None, nx, ny, cell_type=cell_type)
     x = m.geometry.x[:, :2].copy()
     rng = np.random.default_rng(seed)
     hx = 1.0 / max(nx, ny)
     interior = (np.abs(x - 0.5) < 0.5 - 1e-12).all(axis=1)
     x[interior] += amp * hx * (rng.random((int(interior.sum()), 2)) - 0.5)
-    return M.Mesh(x, m.geometry.dofmap.copy())
+    return M.Mesh(x, m.geometry.dofmap.copy(), cell_type=cell_type)
 
 
 def smooth_fields(x, seed=1, U=1.0):
@@ -44,15 +48,17 @@ def smooth_fields(x, seed=1, U=1.0):
 def make_problem(mesh, dt=0.01, rho=1.3, mu=0.02, f=(0.3, -0.2), rules=None):
     x = mesh.geometry.x[:, :2].copy()
     cells = mesh.geometry.dofmap
-    rules = rules or default_rules()
+    quad = mesh.topology.cell_name() == "quadrilateral"
+    rules = rules or default_rules(mesh.topology.cell_name())
     return O.Problem(x=x, cells=cells, h=mesh.h(2, np.arange(cells.shape[0])), dt=dt, rho=rho, mu=mu,
-                     f=np.asarray(f, dtype=float), rules=rules, facet_rule=Q.interval_gauss(2))
+                     f=np.asarray(f, dtype=float), rules=rules,
+                     facet_rule=Q.interval_gauss(Q.FACET_POINTS_QUAD if quad else 2))
 
 
 def facet_pairs_from_cellmask(cells, mask):
     out = []
     for c, m in zip(cells, mask):
-        for lf in range(3):
+        for lf in range(4):
             if m & (1 << lf):
                 out.append((c, lf))
     return np.asarray(out, dtype=np.int32).reshape(-1, 2)
