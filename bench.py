@@ -41,6 +41,11 @@ WORKLOADS = {
     "stenosis_pressure_4m": dict(scenario="stenosis_pressure", res=0.015, dt=1e-3, p_inlet=80.0, R_resistance=10.0),
     "stenosis_pressure_structured_16m": dict(scenario="stenosis_pressure_structured", res=0.0075, dt=1e-3,
                                              p_inlet=80.0, R_resistance=10.0),
+    # the same transfinite grid with the reference's recombined Q1 cells
+    "stenosis_pressure_structured_q1_1m": dict(scenario="stenosis_pressure_structured", res=0.0212, dt=1e-3,
+                                               p_inlet=80.0, R_resistance=10.0, cell_type="quadrilateral"),
+    "stenosis_pressure_structured_q1_8m": dict(scenario="stenosis_pressure_structured", res=0.0075, dt=1e-3,
+                                               p_inlet=80.0, R_resistance=10.0, cell_type="quadrilateral"),
 }
 CPU_SAMPLE_NX = 128  # bounded CPU sample of the same workload (same physics, coarser mesh)
 
@@ -115,7 +120,7 @@ def build_scenario(w, **solver_kw):
     from cfd_hemodynamic_b200.src.scenarios.stenosis_pressure_structured import StenosisPressureStructuredSimulation
     return StenosisPressureStructuredSimulation("stabilized_schur_pressure_backflow", w["dt"], 1.0, grade="severe",
                                                 p_inlet=w["p_inlet"], R_resistance=w["R_resistance"], res=w["res"],
-                                                **solver_kw)
+                                                cell_type=w.get("cell_type", "triangle"), **solver_kw)
 
 
 def oracle_steps(w, nx, steps):

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libhemo_sm100.so")
 
 HEMO_DIVERGED = -100
 Q_FU, Q_FP, Q_UU, Q_UP, Q_PU, Q_PP = range(6)
+CELL_TRIANGLE, CELL_QUADRILATERAL = 0, 1
 
 
 class HemoError(RuntimeError):
@@ -55,6 +56,7 @@ SYMBOLS = {
     "hemo_launch_count": (_L, [_VP]),
     "hemo_prof_enable": (_I, [_VP, _I]),
     "hemo_prof_get": (_I, [_VP, _I, C.POINTER(_D), C.POINTER(_L)]),
+    "hemo_set_cell_type": (_I, [_VP, _I]),
     "hemo_set_mesh": (_I, [_VP, _VP, _I, _VP, _I, _VP]),
     "hemo_set_node_graph": (_I, [_VP, _VP, _VP, _L]),
     "hemo_matrix_nnz": (_I, [_VP, C.POINTER(_L)]),
@@ -193,6 +195,12 @@ class Hemo:
 
     # ---- setup ---------------------------------------------------------
     def set_mesh(self, x2, cells, h):
+        """cells: (E, 3) P1 triangles or (E, 4) tensor-ordered Q1 quadrilaterals."""
+        if cells.dim() != 2 or cells.shape[1] not in (3, 4) or not cells.is_contiguous():
+            raise HemoError("cells must be a contiguous (E, 3) or (E, 4) int32 tensor")
+        self.nv = int(cells.shape[1])
+        self._check(self.lib.hemo_set_cell_type(self._ctx, CELL_QUADRILATERAL if self.nv == 4 else CELL_TRIANGLE),
+                    "hemo_set_cell_type")
         self._keep.update(x=x2, cells=cells, h=h)
         self.n = x2.shape[0]
         self.E = cells.shape[0]

@@ -874,9 +874,14 @@ static int upload_constants(hemo_ctx* ctx) {
 
 extern "C" int hemo_set_cell_type(hemo_ctx* ctx, int cell_type) {
     if (!ctx || (cell_type != HEMO_CELL_TRIANGLE && cell_type != HEMO_CELL_QUADRILATERAL)) return HEMO_EINVAL;
-    if (ctx->cells) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_set_cell_type must precede hemo_set_mesh");
-    ctx->nv = (cell_type == HEMO_CELL_QUADRILATERAL) ? 4 : 3;
+    const int nv = (cell_type == HEMO_CELL_QUADRILATERAL) ? 4 : 3;
+    if (nv == ctx->nv) return 0;
+    // a different cell type invalidates the mesh, the node graph tables and the rules
+    ctx->nv = nv;
+    ctx->cells = nullptr; ctx->x = nullptr; ctx->h = nullptr; ctx->nrowptr = nullptr; ctx->ncol = nullptr;
+    ctx->n = ctx->E = 0;
     for (int r = 0; r < HEMO_NRULES; ++r) ctx->have_rule[r] = false;
+    ctx->rules_dirty = ctx->qrules_dirty = true;
     return 0;
 }
 

@@ -3,8 +3,9 @@
 Geometry and tags follow the reference scenarios:
   * `stenosis_structured`  — src/scenarios/stenosis_pressure_structured.py:190-393
     (transfinite grid between two walls made of line + 2 cubic Béziers + line;
-    the reference recombines to quadrilaterals, here every quad is split into
-    two triangles, mirrored about the centre line — SURVEY.md §7.3-2)
+    the reference recombines to quadrilaterals: `cell_type="quadrilateral"`;
+    `"triangle"` splits every quad into two triangles, mirrored about the centre
+    line — SURVEY.md §7.3-2)
   * `dfg_cylinder`         — src/scenarios/dfg_1.py:97-171 (channel 2.2 x 0.41,
     cylinder (0.2, 0.2) r = 0.05, graded size field LcMin near the cylinder)
 Facet markers: inlet 2, outlet 3, wall 4, obstacle 5 (dfg_1.py:18-22).
@@ -81,8 +82,10 @@ def stenosis_wall_points(L=138.0, R_in=1.57, R_out=1.2, res=0.15, x_position_ste
     return top, bot, n_inlet
 
 
-def stenosis_structured(grade="severe", comm=None, **mesh_options):
-    """Split-triangle transfinite stenosis channel + facet tags."""
+def stenosis_structured(grade="severe", comm=None, cell_type="triangle", **mesh_options):
+    """Transfinite stenosis channel + facet tags.  `cell_type="quadrilateral"`: the recombined
+    Q1 mesh of the reference (stenosis_pressure_structured.py:379-386, tensor-ordered cells);
+    `"triangle"`: every quad split into two P1 triangles."""
     opts = dict(L=138.0, R_in=1.57, R_out=1.2, res=0.15, x_position_stenosis=30.0, severity=0.567, slope=0.4,
                 tension=0.5)
     opts.update(STENOSIS_GRADES.get(grade, STENOSIS_GRADES["severe"]))
@@ -97,12 +100,17 @@ def stenosis_structured(grade="severe", comm=None, **mesh_options):
     v0 = (iy * (nx + 1) + ix).ravel()
     v1, v2 = v0 + 1, v0 + (nx + 1)
     v3 = v2 + 1
-    lower = (iy.ravel() < ny // 2)
-    cells = np.empty((2 * nx * ny, 3), dtype=np.int32)
-    # mirrored diagonals: "right" below the centre line, "left" above
-    cells[0::2] = np.where(lower[:, None], np.stack([v0, v1, v3], 1), np.stack([v0, v1, v2], 1))
-    cells[1::2] = np.where(lower[:, None], np.stack([v0, v3, v2], 1), np.stack([v1, v3, v2], 1))
-    mesh = Mesh(pts, cells, comm)
+    if cell_type == "quadrilateral":
+        mesh = Mesh(pts, np.stack([v0, v1, v2, v3], axis=1).astype(np.int32), comm, cell_type)
+    elif cell_type == "triangle":
+        lower = (iy.ravel() < ny // 2)
+        cells = np.empty((2 * nx * ny, 3), dtype=np.int32)
+        # mirrored diagonals: "right" below the centre line, "left" above
+        cells[0::2] = np.where(lower[:, None], np.stack([v0, v1, v3], 1), np.stack([v0, v1, v2], 1))
+        cells[1::2] = np.where(lower[:, None], np.stack([v0, v3, v2], 1), np.stack([v1, v3, v2], 1))
+        mesh = Mesh(pts, cells, comm)
+    else:
+        raise ValueError(f"cell_type {cell_type!r}")
     L = opts["L"]
     ext = exterior_facet_indices(mesh.topology)
     fv = mesh.topology.facet_vertices[ext]

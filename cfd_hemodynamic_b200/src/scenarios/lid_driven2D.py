@@ -11,19 +11,20 @@ from ..scenario import Scenario
 
 class LidDriven2DSimulation(Scenario):
     def __init__(self, solver_name, dt, T, f: tuple[float, float] = (0, 0), *, rho=1, mu=1, nx=50,
-                 **solver_kwargs):
+                 cell_type="triangle", **solver_kwargs):
         self._mesh = None
         self._bcu = None
         self._bcp = None
         self.Re = str(int(1 / mu)) if mu <= 1 else "0"
         self.nx = int(nx)
+        self.cell_type = cell_type      # "quadrilateral": create_unit_square(..., CellType.quadrilateral)
         super().__init__(solver_name, "lid_driven2D", rho, mu, dt, T, f, **solver_kwargs)
         self.setup()
 
     @property
     def mesh(self):
         if not self._mesh:
-            self._mesh = create_unit_square(None, self.nx, self.nx)
+            self._mesh = create_unit_square(None, self.nx, self.nx, cell_type=self.cell_type)
         return self._mesh
 
     @property

@@ -7,6 +7,7 @@ from .stenosis_pressure_structured import StenosisPressureStructuredSimulation
 
 class StenosisPressureSimulation(StenosisPressureStructuredSimulation):
     scenario_name = "stenosis_pressure"
+    default_cell_type = "triangle"          # the reference's gmsh mesh here is not recombined
 
     def __init__(self, solver_name, dt, T, f=(0, 0), grade="severe", p_inlet: float = 80.0,
                  R_resistance: float = None, v_max: float = None, *, rho: float = 1.060e-3, mu: float = 3.5e-3,

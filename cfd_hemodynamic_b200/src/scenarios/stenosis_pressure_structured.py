@@ -2,8 +2,9 @@
 src/scenarios/stenosis_pressure_structured.py:30-393): weak inlet pressure +
 Nitsche, resistance outlet, backflow stabilisation, no-slip walls, no Dirichlet
 pressure.  Units mm-g-s; 2-D pressures use _MMHG_2D = 133.322/2 (:23-26).
-The reference mesh is recombined to quadrilaterals; here each quad is split
-into two P1 triangles."""
+The reference mesh is recombined to quadrilaterals (:379-386), which is the
+default here too (`cell_type="quadrilateral"`, Q1-Q1); `cell_type="triangle"`
+splits each quad into two P1 triangles."""
 import numpy as np
 
 from ...fem import generators
@@ -22,6 +23,7 @@ class StenosisPressureStructuredSimulation(Scenario):
     wall_marker = 4
     scenario_name = "stenosis_pressure_structured"
     pressure_unit = _MMHG_2D
+    default_cell_type = "quadrilateral"     # setRecombine, reference :384
 
     def __init__(self, solver_name, dt, T, f: tuple[float, float] = (0, 0), grade="severe", p_inlet: float = 80.0,
                  R_resistance: float = None, v_max: float = None, *, rho: float = 1.060e-3, mu: float = 3.5e-3,
@@ -36,6 +38,7 @@ class StenosisPressureStructuredSimulation(Scenario):
                        if k.startswith(("snes_", "ksp_", "amg_", "cheb_", "schur_", "pc_", "strength_", "smooth_")) or k in ("verbose", "device", "host_only",
                                                                                              "quadrature")}
         self.mesh_options = kwargs.copy()
+        self.mesh_options.setdefault("cell_type", self.default_cell_type)
         self.grade = grade
         self._bcu = None
         self._bcp = None

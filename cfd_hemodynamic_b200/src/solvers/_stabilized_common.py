@@ -5,7 +5,8 @@ What the reference does with UFL/FFCx/DOLFINx/PETSc
 stabilized_schur_pressure_backflow.py) is done here by libhemo_sm100.so:
 this class only sequences C-ABI calls and mirrors the control flow of
 `Solver.__init__` / `setup` / `solveStep` and of PETSc's SNES newtonls + bt
-line search.  P1–P1 triangles.
+line search.  P1–P1 triangles and Q1–Q1 quadrilaterals
+(`mesh.topology.cell_name()`, stabilized_schur.py:55-58).
 """
 from __future__ import annotations
 
@@ -25,6 +26,9 @@ from ..solverBase import SolverBase
 # estimated UFL degree of each block form on P1 triangles (each
 # block of extract_blocks() is its own form: stabilized_schur.py:188-189)
 BLOCK_DEGREE = {Q_FU: 12, Q_FP: 11, Q_UU: 12, Q_UP: 11, Q_PU: 11, Q_PP: 10}
+# Q1 quadrilaterals: Q1 counts as degree 2 and derivatives keep the degree:
+# tau(14) R(4) (u_m.grad v)(4) = 22, PSPG/J_up/J_pu 20, J_pp 18 -> 12x12 / 11x11 / 10x10 Gauss points
+BLOCK_DEGREE_QUAD = {Q_FU: 22, Q_FP: 20, Q_UU: 22, Q_UP: 20, Q_PU: 20, Q_PP: 18}
 
 # facet-set slots in the library
 SET_ALL, SET_INLET, SET_OUTLET = 0, 1, 2
@@ -41,8 +45,10 @@ class StabilizedSchurB200(SolverBase):
     def __init__(self, mesh, dt, rho, mu, f, initial_velocity: Callable | None = None, **kw):
         super().__init__(mesh, dt, rho, mu, f)
         cell = mesh.topology.cell_name()
-        if cell != "triangle":
-            raise NotImplementedError(f"cell type {cell}: only P1-P1 triangles are implemented on the device")
+        if cell not in ("triangle", "quadrilateral"):
+            raise NotImplementedError(
+                f"cell type {cell}: P1-P1 triangles and Q1-Q1 quadrilaterals are implemented on the device")
+        self._quad = cell == "quadrilateral"
         if int(kw.pop("p_grade", 1)) != 1:
             raise NotImplementedError("p_grade != 1: only P1-P1 is implemented on the device")
         super().initVelocitySpace("Lagrange", cell, 1, shape=(mesh.geometry.dim,))
@@ -111,10 +117,13 @@ class StabilizedSchurB200(SolverBase):
                            torch.from_numpy(np.ascontiguousarray(h)).to(dev))
         self._nrowptr, self._ncol = D.node_graph(cells, n)
         self.hemo.set_node_graph(torch.from_numpy(self._nrowptr).to(dev), torch.from_numpy(self._ncol).to(dev))
-        for block, deg in BLOCK_DEGREE.items():
-            pts, wts = (self._rules[block] if self._rules else Q.triangle_rule(deg))
+        for block, deg in (BLOCK_DEGREE_QUAD if self._quad else BLOCK_DEGREE).items():
+            if self._rules:
+                pts, wts = self._rules[block]
+            else:
+                pts, wts = Q.quadrilateral_rule(deg) if self._quad else Q.triangle_rule(deg)
             self.hemo.set_quadrature(block, pts, wts)
-        self.hemo.set_facet_quadrature(*Q.interval_gauss(2))
+        self.hemo.set_facet_quadrature(*Q.interval_gauss(Q.FACET_POINTS_QUAD if self._quad else 2))
         eps0 = float(np.finfo(np.float64).resolution)
         fval = np.asarray(self.f.value, dtype=np.float64).reshape(-1)
         self.hemo.set_params(float(self.dt.value), float(self.rho.value), float(self.mu.value), fval[:2], eps0)

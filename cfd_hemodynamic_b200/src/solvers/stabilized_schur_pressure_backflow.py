@@ -13,6 +13,7 @@ from typing import Callable
 import numpy as np
 
 from ...fem import discretization as D
+from ...fem.mesh import QUAD_FACETS
 from ._stabilized_common import SET_INLET, SET_OUTLET, StabilizedSchurB200
 
 
@@ -72,11 +73,16 @@ class Solver(StabilizedSchurB200):
         lf = pairs[:, 1]
         X = x[cells]
         ar = np.arange(cells.shape[0])
-        fv = np.array([[1, 2], [0, 2], [0, 1]])
+        if cells.shape[1] == 4:
+            fv = np.array(QUAD_FACETS)
+            inside = X.mean(axis=1)                 # outward = away from the centroid
+        else:
+            fv = np.array([[1, 2], [0, 2], [0, 1]])
+            inside = X[ar, lf]                      # outward = away from the opposite vertex
         va, vb = fv[lf, 0], fv[lf, 1]
         t = X[ar, vb] - X[ar, va]
         nrm = np.stack([t[:, 1], -t[:, 0]], axis=1)
-        nrm *= np.sign(np.einsum("ei,ei->e", nrm, X[ar, va] - X[ar, lf]))[:, None]
+        nrm *= np.sign(np.einsum("ei,ei->e", nrm, 0.5 * (X[ar, va] + X[ar, vb]) - inside))[:, None]
         U = self.u_prev.x.array.reshape(-1, 2)[cells]
         return float(np.sum(np.einsum("ei,ei->e", 0.5 * (U[ar, va] + U[ar, vb]), nrm)))
 

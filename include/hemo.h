@@ -100,8 +100,9 @@ int hemo_prof_get(hemo_ctx* ctx, int kernel_class, double* ms_total, int64_t* la
 /* mesh.topology.cell_name() (src/solvers/stabilized_schur.py:55-58): P1 triangles (default)
  * or Q1 quadrilaterals with tensor-ordered vertices (0,0),(1,0),(0,1),(1,1) — the cells of the
  * recombined transfinite mesh, src/scenarios/stenosis_pressure_structured.py:379-386.  Call
- * before hemo_set_mesh; quadrature rules set earlier are dropped (rules belong to a cell type:
- * triangle rules have weights summing to 1/2, quadrilateral rules live on [0,1]^2 and sum to 1). */
+ * before hemo_set_mesh; changing the type drops the mesh, the node graph and the quadrature
+ * rules set earlier (rules belong to a cell type: triangle rules have weights summing to 1/2,
+ * quadrilateral rules live on [0,1]^2 and sum to 1). */
 enum { HEMO_CELL_TRIANGLE = 0, HEMO_CELL_QUADRILATERAL = 1 };
 int hemo_set_cell_type(hemo_ctx* ctx, int cell_type);
 /* mesh.geometry.x / .dofmap / mesh.h (src/solvers/stabilized_schur.py:55-58,83-88).

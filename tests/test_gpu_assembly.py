@@ -20,10 +20,13 @@ def hemo():
     h.close()
 
 
-def _case(hemo, nx, ny, facet_mode, with_bc, seed=0, **pk):
+CELLS = ["triangle", "quadrilateral"]
+
+
+def _case(hemo, nx, ny, facet_mode, with_bc, seed=0, cell_type="triangle", **pk):
     from cfd_hemodynamic_b200.fem import mesh as M
     from oracle import ns_oracle as O
-    mesh = T.perturbed_square(nx, ny, seed=seed)
+    mesh = T.perturbed_square(nx, ny, seed=seed, cell_type=cell_type)
     prob = T.make_problem(mesh, **pk)
     ext = M.exterior_facet_indices(mesh.topology)
     x = prob.x
@@ -58,10 +61,11 @@ def _case(hemo, nx, ny, facet_mode, with_bc, seed=0, **pk):
     return mesh, prob, g
 
 
+@pytest.mark.parametrize("cell_type", CELLS)
 @pytest.mark.parametrize("facet_mode,with_bc", [("none", False), ("all", False), ("all", True), ("hemo", True)])
-def test_jacobian_parity(hemo, facet_mode, with_bc):
+def test_jacobian_parity(hemo, facet_mode, with_bc, cell_type):
     from oracle import ns_oracle as O
-    mesh, prob, g = _case(hemo, 9, 7, facet_mode, with_bc)
+    mesh, prob, g = _case(hemo, 9, 7, facet_mode, with_bc, cell_type=cell_type)
     u, p, un = T.smooth_fields(prob.x)
     dev = hemo.device
     xd = torch.tensor(np.concatenate([u, p]), device=dev)
@@ -86,10 +90,11 @@ def test_jacobian_parity(hemo, facet_mode, with_bc):
         assert mult.max() == 2.0
 
 
+@pytest.mark.parametrize("cell_type", CELLS)
 @pytest.mark.parametrize("facet_mode,with_bc", [("none", False), ("all", True), ("hemo", True)])
-def test_residual_parity(hemo, facet_mode, with_bc):
+def test_residual_parity(hemo, facet_mode, with_bc, cell_type):
     from oracle import ns_oracle as O
-    mesh, prob, g = _case(hemo, 8, 11, facet_mode, with_bc, seed=3)
+    mesh, prob, g = _case(hemo, 8, 11, facet_mode, with_bc, seed=3, cell_type=cell_type)
     u, p, un = T.smooth_fields(prob.x, seed=4)
     dev = hemo.device
     x = np.concatenate([u, p])
@@ -103,10 +108,11 @@ def test_residual_parity(hemo, facet_mode, with_bc):
     assert rel < REL_TOL, rel
 
 
-def test_zero_previous_velocity_branch(hemo):
+@pytest.mark.parametrize("cell_type", CELLS)
+def test_zero_previous_velocity_branch(hemo, cell_type):
     """u_n == 0 exercises the eps0 branch of tau_supg1 (stabilized_schur.py:100-103)."""
     from oracle import ns_oracle as O
-    mesh, prob, g = _case(hemo, 6, 6, "all", False, mu=1e-3, dt=0.05)
+    mesh, prob, g = _case(hemo, 6, 6, "all", False, mu=1e-3, dt=0.05, cell_type=cell_type)
     u, p, _ = T.smooth_fields(prob.x)
     un = np.zeros_like(u)
     dev = hemo.device
@@ -117,8 +123,9 @@ def test_zero_previous_velocity_branch(hemo):
     assert rel < REL_TOL, rel
 
 
-def test_deterministic(hemo):
-    mesh, prob, g = _case(hemo, 12, 12, "all", True)
+@pytest.mark.parametrize("cell_type", CELLS)
+def test_deterministic(hemo, cell_type):
+    mesh, prob, g = _case(hemo, 12, 12, "all", True, cell_type=cell_type)
     u, p, un = T.smooth_fields(prob.x)
     dev = hemo.device
     xd = torch.tensor(np.concatenate([u, p]), device=dev)
@@ -130,12 +137,52 @@ def test_deterministic(hemo):
     assert torch.equal(v1, v2)
 
 
-def test_outlet_flux(hemo):
+@pytest.mark.parametrize("cell_type", CELLS)
+def test_outlet_flux(hemo, cell_type):
     from cfd_hemodynamic_b200.fem import mesh as M
     from oracle import ns_oracle as O
-    mesh, prob, g = _case(hemo, 7, 9, "hemo", True)
+    mesh, prob, g = _case(hemo, 7, 9, "hemo", True, cell_type=cell_type)
     _, _, un = T.smooth_fields(prob.x)
     outlet = M.locate_entities_boundary(mesh, 1, lambda X: np.isclose(X[0], 1.0))
     q_ref = O.outlet_flux(prob, mesh.topology.facet_cell_pairs(outlet), un)
     q = hemo.outlet_flux(1, torch.tensor(un, device=hemo.device))
     assert abs(q - q_ref) <= 1e-13 * max(1.0, abs(q_ref))
+
+
+def test_q1_shared_rule_single_pass(hemo):
+    """One rule for every block form: the quadrilateral kernels integrate all blocks in one pass
+    (rule aliases) and must still match the oracle."""
+    from oracle import ns_oracle as O
+    from oracle import q1_oracle as Q1
+    mesh = T.perturbed_square(6, 5, seed=2, cell_type="quadrilateral")
+    prob = T.make_problem(mesh, rules={k: Q1.tensor_gauss(5) for k in T.BLOCK_ID})
+    T.setup_gpu(hemo, mesh, prob)
+    for sid in range(8):
+        hemo.set_facet_set(sid, None, None)
+    hemo.set_bc(None, None, None)
+    u, p, un = T.smooth_fields(prob.x)
+    dev = hemo.device
+    xd = torch.tensor(np.concatenate([u, p]), device=dev)
+    und = torch.tensor(un, device=dev)
+    vals = torch.zeros(hemo.nnz, dtype=torch.float64, device=dev)
+    b = torch.zeros(3 * prob.n, dtype=torch.float64, device=dev)
+    hemo.assemble_jacobian(xd, und, vals)
+    hemo.assemble_residual(xd, und, None, b)
+    A_ref = O.assemble_J_raw(prob, u, p, un)
+    assert np.linalg.norm(vals.cpu().numpy() - A_ref.data) < REL_TOL * np.linalg.norm(A_ref.data)
+    b_ref = O.assemble_F_raw(prob, u, p, un)
+    assert np.linalg.norm(b.cpu().numpy() - b_ref) < REL_TOL * np.linalg.norm(b_ref)
+
+
+def test_q1_laplace_mass(hemo):
+    """Pressure Laplacian / lumped mass of the Schur approximation on quadrilaterals: symmetric,
+    constants in the kernel, mass sums to the area."""
+    import scipy.sparse as sp
+    mesh = T.perturbed_square(7, 6, seed=4, cell_type="quadrilateral")
+    prob = T.make_problem(mesh)
+    _, (nrowptr, ncol) = T.setup_gpu(hemo, mesh, prob)
+    lap, mass = hemo.assemble_laplace_mass()
+    L = sp.csr_matrix((lap.cpu().numpy(), ncol, nrowptr), shape=(prob.n, prob.n))
+    assert abs(L - L.T).max() < 1e-13
+    assert np.abs(L @ np.ones(prob.n)).max() < 1e-12
+    assert abs(float(mass.sum()) - 1.0) < 1e-13

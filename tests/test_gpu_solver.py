@@ -13,10 +13,10 @@ pytestmark = pytest.mark.gpu
 TIGHT = dict(snes_rtol=1e-12, snes_stol=0.0, ksp_rtol=1e-11, ksp_restart=100)
 
 
-def _oracle_lid(nx, mu, dt, steps, rules):
+def _oracle_lid(nx, mu, dt, steps, rules, cell_type="triangle"):
     from cfd_hemodynamic_b200.fem import mesh as M
     from oracle import ns_oracle as O
-    mesh = M.create_unit_square(None, nx, nx)
+    mesh = M.create_unit_square(None, nx, nx, cell_type=cell_type)
     prob = T.make_problem(mesh, dt=dt, rho=1.0, mu=mu, f=(0.0, 0.0), rules=rules)
     x = prob.x
     n = prob.n
@@ -37,17 +37,18 @@ def _oracle_lid(nx, mu, dt, steps, rules):
     return xk, n
 
 
-def test_lid_cavity_matches_oracle():
+@pytest.mark.parametrize("cell_type", ["triangle", "quadrilateral"])
+def test_lid_cavity_matches_oracle(cell_type):
     from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation
     nx, mu, dt, steps = 16, 0.01, 0.01, 3
-    sc = LidDriven2DSimulation("stabilized_schur", dt, steps * dt, rho=1, mu=mu, nx=nx, **TIGHT)
+    sc = LidDriven2DSimulation("stabilized_schur", dt, steps * dt, rho=1, mu=mu, nx=nx, cell_type=cell_type, **TIGHT)
     s = sc.solver
     assert s._nullspace                      # all-Dirichlet velocity: constant pressure mode detected
     for _ in range(steps):
         s.solveStep()
         s.u_prev.x.array[:] = s.u_sol.x.array[:]
         s.p_prev.x.array[:] = s.p_sol.x.array[:]
-    xk, n = _oracle_lid(nx, mu, dt, steps, T.default_rules())
+    xk, n = _oracle_lid(nx, mu, dt, steps, T.default_rules(cell_type), cell_type)
     u_ref, p_ref = xk[:2 * n], xk[2 * n:]
     u = s.u_sol.x.array
     p = s.p_sol.x.array

@@ -63,15 +63,16 @@ def test_backflow_variant_matches_oracle():
     assert _rel(s.p_sol.x.array, xk[2 * n:]) < 1e-8
 
 
-@pytest.mark.parametrize("double_setup", [False, True])
-def test_pressure_backflow_variant_matches_oracle(double_setup):
+@pytest.mark.parametrize("double_setup,cell_type", [(False, "triangle"), (True, "triangle"),
+                                                    (False, "quadrilateral"), (True, "quadrilateral")])
+def test_pressure_backflow_variant_matches_oracle(double_setup, cell_type):
     """Weak inlet pressure + Nitsche + resistance outlet + backflow; with the second
     setup() call of Simulation.run (simulation.py:269) every boundary term is doubled and
     the first outlet-pressure constant stays frozen."""
     from cfd_hemodynamic_b200.src.scenarios.stenosis_pressure_structured import StenosisPressureStructuredSimulation
     from oracle import ns_oracle as O
     sc = StenosisPressureStructuredSimulation("stabilized_schur_pressure_backflow", 0.005, 0.02, grade="moderate",
-                                              p_inlet=2.0, R_resistance=50.0, res=0.6, L=20.0,
+                                              cell_type=cell_type, p_inlet=2.0, R_resistance=50.0, res=0.6, L=20.0,
                                               x_position_stenosis=8.0, **TIGHT)
     if double_setup:
         sc.setup()
@@ -103,14 +104,15 @@ def test_pressure_backflow_variant_matches_oracle(double_setup):
     assert _rel(s.p_sol.x.array, xk[2 * n:]) < 1e-8
 
 
-def test_golden_case_on_gpu():
+@pytest.mark.parametrize("cell_type", ["triangle", "quadrilateral"])
+def test_golden_case_on_gpu(cell_type):
     """The committed golden vectors (tests/golden) are reproduced by the CUDA path."""
     import os
     import scipy.sparse as sp
     from cfd_hemodynamic_b200._lib import Hemo
-    from tests.golden.make_golden import build_case
-    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "p1tri_small.npz"))
-    mesh, prob, fsets, bcs, u, p, un = build_case()
+    from tests.golden.make_golden import GOLDEN_FILES, build_case
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", GOLDEN_FILES[cell_type]))
+    mesh, prob, fsets, bcs, u, p, un = build_case(cell_type)
     for k in prob.rules:
         prob.rules[k] = (gold[f"rule_{k}_pts"], gold[f"rule_{k}_wts"])
     hemo = Hemo(0)

@@ -137,12 +137,14 @@ def test_outlet_flux_linear_field():
     assert abs(q - 2.5) < 1e-14
 
 
-def test_golden_vectors():
-    """The committed golden case (tests/golden/make_golden.py) is reproduced bit-for-bit in
-    pattern and to 1e-13 in values by the current oracle."""
-    from tests.golden.make_golden import build_case
-    gold = np.load(GOLDEN)
-    mesh, prob, fsets, bcs, u, p, un = build_case()
+@pytest.mark.parametrize("cell_type", ["triangle", "quadrilateral"])
+def test_golden_vectors(cell_type):
+    """The committed golden cases (tests/golden/make_golden.py; P1 triangles and Q1
+    quadrilaterals) are reproduced bit-for-bit in pattern and to 1e-13 in values by the
+    current oracle."""
+    from tests.golden.make_golden import GOLDEN_FILES, build_case
+    gold = np.load(os.path.join(os.path.dirname(GOLDEN), GOLDEN_FILES[cell_type]))
+    mesh, prob, fsets, bcs, u, p, un = build_case(cell_type)
     for k in prob.rules:                       # use the committed rules: golden pins arithmetic, not tables
         prob.rules[k] = (gold[f"rule_{k}_pts"], gold[f"rule_{k}_wts"])
     assert np.array_equal(gold["cells"], prob.cells) and np.array_equal(gold["x"], prob.x)

@@ -24,7 +24,7 @@ def make(host_only, **kw):
         return LidDriven2DSimulation("stabilized_schur", 0.01, 1.0, rho=1, mu=0.01, nx=nx, host_only=host_only, **kw)
     if case == "pressure":
         from cfd_hemodynamic_b200.src.scenarios.stenosis_pressure_structured import StenosisPressureStructuredSimulation
-        return StenosisPressureStructuredSimulation("stabilized_schur_pressure_backflow", 0.005, 1.0, grade="moderate",
+        return StenosisPressureStructuredSimulation("stabilized_schur_pressure_backflow", 0.005, 1.0, grade="moderate", cell_type="triangle",
                                                     p_inlet=2.0, R_resistance=50.0, res=3.14 / nx, L=20.0,
                                                     x_position_stenosis=8.0, schur_mode="laplace",
                                                     host_only=host_only, **kw)

@@ -10,7 +10,7 @@ with contextlib.redirect_stdout(sys.stderr):
     if kind == "pressure":
         from cfd_hemodynamic_b200.src.scenarios.stenosis_pressure_structured import StenosisPressureStructuredSimulation as S
         sc = S("stabilized_schur_pressure_backflow", dt, 1.0, grade="severe", p_inlet=kw.pop("p_inlet", 80.0),
-               R_resistance=kw.pop("R_resistance", 10.0), res=res, **kw)
+               R_resistance=kw.pop("R_resistance", 10.0), res=res, cell_type=kw.pop("cell_type", "triangle"), **kw)
     else:
         from cfd_hemodynamic_b200.src.scenarios.stenosis_mesh_variable import StenosisMeshVariableSimulation as S
         sc = S("stabilized_schur_backflow", dt, 1.0, grade="severe", v_max=kw.pop("v_max", 100.0), res=res, **kw)
