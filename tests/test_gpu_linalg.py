@@ -10,14 +10,14 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def setup():
+@pytest.fixture(scope="module", params=["triangle", "quadrilateral"])
+def setup(request):
     from cfd_hemodynamic_b200._lib import Hemo
     from cfd_hemodynamic_b200.fem import mesh as M
     from oracle import ns_oracle as O
     hemo = Hemo(0)
     nx = 40
-    mesh = M.create_unit_square(None, nx, nx)
+    mesh = M.create_unit_square(None, nx, nx, cell_type=request.param)
     prob = T.make_problem(mesh, dt=0.01, rho=1.0, mu=0.05, f=(0.0, 0.0))
     x = prob.x
     n = prob.n

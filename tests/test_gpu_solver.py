@@ -41,7 +41,14 @@ def _oracle_lid(nx, mu, dt, steps, rules, cell_type="triangle"):
 def test_lid_cavity_matches_oracle(cell_type):
     from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation
     nx, mu, dt, steps = 16, 0.01, 0.01, 3
-    sc = LidDriven2DSimulation("stabilized_schur", dt, steps * dt, rho=1, mu=mu, nx=nx, cell_type=cell_type, **TIGHT)
+    tight = dict(TIGHT)
+    if cell_type == "quadrilateral":
+        # Near convergence the assembled residual carries a round-off component (~1e-11 |b|) along
+        # the left null vector of the singular Jacobian (constant over the pressure rows), which
+        # no Krylov iterate can remove; 1e-11 is just reachable on the triangle mesh (9.7e-12
+        # measured with the oracle) and just not on the quadrilateral one (1.08e-11).
+        tight["ksp_rtol"] = 1e-10
+    sc = LidDriven2DSimulation("stabilized_schur", dt, steps * dt, rho=1, mu=mu, nx=nx, cell_type=cell_type, **tight)
     s = sc.solver
     assert s._nullspace                      # all-Dirichlet velocity: constant pressure mode detected
     for _ in range(steps):

@@ -7,9 +7,11 @@ from cfd_hemodynamic_b200.fem import mesh as M, discretization as D
 from tests import common as T
 
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 707
+cell_type = sys.argv[2] if len(sys.argv) > 2 else "triangle"
 reps = 10
 t0 = time.time()
-mesh = M.create_unit_square(None, nx, nx)
+# perturbed interior vertices: non-affine quadrilaterals take the general path
+mesh = T.perturbed_square(nx, nx, seed=0, amp=0.2, cell_type=cell_type)
 prob = T.make_problem(mesh, dt=0.01, rho=1.0, mu=0.01, f=(0, 0))
 ext = M.exterior_facet_indices(mesh.topology)
 h = Hemo(0)
@@ -42,7 +44,17 @@ out["jacobian_ms"] = timeit(lambda: h.assemble_jacobian(xd, und, vals))
 out["residual_ms"] = timeit(lambda: h.assemble_residual(xd, und, g, b))
 out["spmv_ms"] = timeit(lambda: h.spmv(vals, xd, y))
 out["dot_ms"] = timeit(lambda: h.dot(xd, y))
-out["cells"] = E; out["nnz"] = h.nnz
+out["cells"] = E; out["nnz"] = h.nnz; out["cell_type"] = cell_type
+out["res_Mcells_s"] = E / out["residual_ms"] / 1e3
+out["jac_nnz_per_s"] = h.nnz / out["jacobian_ms"] * 1e3
+if hasattr(h, "prof_enable"):
+    h.prof_enable(True)
+    for _ in range(5):
+        h.assemble_jacobian(xd, und, vals); h.assemble_residual(xd, und, g, b)
+    for cls, name in ((1, "cell_jacobian"), (2, "gather_matrix"), (3, "cell_residual")):
+        ms, cnt = h.prof_get(cls)
+        out[name + "_ms"] = ms / max(cnt, 1)
+    h.prof_enable(False)
 out["jac_Mcells_s"] = E / out["jacobian_ms"] / 1e3
 out["spmv_GBs"] = (8 * h.nnz + 4 * h.nnz_node + 20 * 3 * n) / out["spmv_ms"] / 1e6
 print(json.dumps(out))
