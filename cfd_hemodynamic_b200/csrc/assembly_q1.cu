@@ -8,11 +8,12 @@
 // recombined transfinite mesh of src/scenarios/stenosis_pressure_structured.py:379-386.
 //
 // Work decomposition: at the reference quadrature (12 x 12 points for the degree-22 block
-// forms) the 12 x 12 element tensor costs ~10^5 flops per cell — FP64-pipe bound by two
-// orders of magnitude over its 1.2 kB of output — so the Jacobian kernel uses one thread per
-// (cell, test node): blockIdx.y = a, 36 accumulators in registers, and every store of a warp
-// is one coalesced 256-byte line.  The point geometry is recomputed by the four threads of a
-// cell (~25 % of the point cost) instead of being exchanged through shared memory.
+// forms) the 12 x 12 element tensor costs several 10^5 flops per cell — FP64-pipe bound by two
+// orders of magnitude over its 1.2 kB of output — so the Jacobian kernel splits a cell into
+// three work items (one launch each: J_uu rows {0,1}, J_uu rows {2,3}, J_up + J_pu + J_pp), each one
+// thread with 32-64 accumulators in registers; every store of a warp is one coalesced 256-byte
+// line.  The point set-up (geometry, tau) is recomputed per work item instead of being exchanged
+// through shared memory (LDS bandwidth would cost more than the recomputation).
 #include "hemo_internal.cuh"
 #include "q1_element.cuh"
 
@@ -39,24 +40,23 @@ __device__ __forceinline__ void q1_load(Q1Cell& cd, int c, const int32_t* __rest
     cd.h = h[c];
 }
 
+template <int ITEM>
 __global__ void __launch_bounds__(128)
 k_q1_cell_jacobian(int E, int n, const int32_t* __restrict__ cells, const double* __restrict__ x,
                    const double* __restrict__ h, const double* __restrict__ sol,
                    const double* __restrict__ un, double* __restrict__ Ae) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= E) return;
-    const int a = blockIdx.y;
     Q1Cell cd;
     int v[4];
     q1_load(cd, c, cells, x, h, sol, un, n, v);
-    double acc[4][9];
-    q1_cell_jacobian_row(cd, c_qpar, c_qrules, a, acc);
     const int64_t stride = E;
-    double* out = Ae + (int64_t)a * 36 * stride + c;
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) out[(b * 9 + k) * stride] = acc[b][k];
+    double* out = Ae + c;
+    auto emit = [&](int slot, double val) { out[slot * stride] = val; };
+    // work item: J_uu rows {0,1} | J_uu rows {2,3} | J_up, J_pu, J_pp
+    if (ITEM == 0) q1_cell_jacobian_uu<0>(cd, c_qpar, c_qrules, emit);
+    else if (ITEM == 1) q1_cell_jacobian_uu<2>(cd, c_qpar, c_qrules, emit);
+    else q1_cell_jacobian_p(cd, c_qpar, c_qrules, emit);
 }
 
 __device__ __noinline__ void q1_lift_device(const Q1Cell& cd, const int v[4], int n, const double* __restrict__ dvec,
@@ -200,8 +200,12 @@ int hemo_q1_cell_jacobian(hemo_ctx* ctx, const double* x_dev, const double* un_d
     int rc = q1_upload_constants(ctx);
     if (rc) return rc;
     const int E = ctx->E;
-    dim3 grid(hemo_grid(E, 128), 4);
-    k_q1_cell_jacobian<<<grid, 128, 0, ctx->stream>>>(E, ctx->n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, ctx->Ae);
+    const int grid = hemo_grid(E, 128);
+    k_q1_cell_jacobian<0><<<grid, 128, 0, ctx->stream>>>(E, ctx->n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, ctx->Ae);
+    HEMO_LAUNCH_CHECK(ctx);
+    k_q1_cell_jacobian<1><<<grid, 128, 0, ctx->stream>>>(E, ctx->n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, ctx->Ae);
+    HEMO_LAUNCH_CHECK(ctx);
+    k_q1_cell_jacobian<2><<<grid, 128, 0, ctx->stream>>>(E, ctx->n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, ctx->Ae);
     HEMO_LAUNCH_CHECK(ctx);
     return 0;
 }

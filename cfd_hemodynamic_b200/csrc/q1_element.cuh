@@ -168,49 +168,80 @@ HEMO_HD void q1_cell_residual(const Q1Cell& c, const hemo_params& par, const Hem
 }
 
 // ---- Jacobian ---------------------------------------------------------------------
-// One quadrature point of the rows of test node a: acc[b][ri*3+ci] (ri/ci in u_x, u_y, p).
-HEMO_HD void q1_jacobian_row_point(const hemo_params& par, const Q1Geom& ge, const Q1State& s, double w, int a,
-                                   int blocks, double acc[4][9]) {
+// The 12 x 12 element tensor is produced by three work items per cell so that the point set-up
+// (geometry, state, tau: one division, two square roots and ~200 flops) is repeated as little as
+// the register file allows:
+//   J_uu rows of test nodes {0,1} and {2,3}: 2 x 32 accumulators, rule of the J_uu form;
+//   J_up + J_pu (64 accumulators, their rule(s)) followed by J_pp (16 accumulators, its rule).
+// Slots follow the element buffer layout: (a*4+b)*9 + ri*3 + ci with ri/ci in (u_x, u_y, p).
+
+// One quadrature point of J_uu for the test nodes A0, A0+1: uu[i][b][k*2+l].
+template <int A0>
+HEMO_HD void q1_uu_point(const hemo_params& par, const Q1Geom& ge, const Q1State& s, double w, double uu[2][4][4]) {
     const double rho = par.rho, mu = par.mu, idt = 1.0 / par.dt;
-    const double tr = s.tau / rho;
-    // a is a run-time index (blockIdx.y): select instead of indexing so everything stays in registers
-    double pa = 0.0, ga[2] = {0.0, 0.0}, sa = 0.0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (i == a) { pa = ge.phi[i]; ga[0] = ge.g[i][0]; ga[1] = ge.g[i][1]; sa = s.umg[i]; }
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-        const double gab = ga[0] * ge.g[b][0] + ga[1] * ge.g[b][1];
         const double cb = rho * (ge.phi[b] * idt + 0.5 * s.umg[b]);
         const double hb = 0.5 * rho * ge.phi[b];
         const double vb = 0.5 * mu * ge.theta[b];
-        if (blocks & (Q1_UU | Q1_PU)) {
-            double pu[2] = {0.0, 0.0};
+        double C[2][2], dR[2][2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int l = 0; l < 2; ++l) {
+                const double dkl = (k == l) ? 1.0 : 0.0;
+                C[k][l] = cb * dkl + hb * s.G[l][k];
+                dR[k][l] = C[k][l] - vb * (ge.trk * dkl + ge.k[k][l]);
+            }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int a = A0 + i;
+            const double gab = ge.g[a][0] * ge.g[b][0] + ge.g[a][1] * ge.g[b][1];
 #pragma unroll
             for (int k = 0; k < 2; ++k)
 #pragma unroll
                 for (int l = 0; l < 2; ++l) {
                     const double dkl = (k == l) ? 1.0 : 0.0;
-                    const double C = cb * dkl + hb * s.G[l][k];
-                    const double dR = C - vb * (ge.trk * dkl + ge.k[k][l]);
-                    if (blocks & Q1_UU) {
-                        const double v = pa * C + 0.5 * mu * (gab * dkl + ga[l] * ge.g[b][k]) +
-                                         s.tau * (sa * dR + 0.5 * ge.phi[b] * ga[l] * s.R[k]) +
-                                         0.5 * s.taul * rho * ga[k] * ge.g[b][l];
-                        acc[b][k * 3 + l] += w * v;
-                    }
-                    pu[l] += dR * ga[k];
+                    const double v = ge.phi[a] * C[k][l] + 0.5 * mu * (gab * dkl + ge.g[a][l] * ge.g[b][k]) +
+                                     s.tau * (s.umg[a] * dR[k][l] + 0.5 * ge.phi[b] * ge.g[a][l] * s.R[k]) +
+                                     0.5 * s.taul * rho * ge.g[a][k] * ge.g[b][l];
+                    uu[i][b][k * 2 + l] += w * v;
                 }
-            if (blocks & Q1_PU) {
-                acc[b][6] += w * (0.5 * pa * ge.g[b][0] + tr * pu[0]);
-                acc[b][7] += w * (0.5 * pa * ge.g[b][1] + tr * pu[1]);
+        }
+    }
+}
+
+// One quadrature point of J_up (up[a][b][k]) and / or J_pu (pu[a][b][l]).
+HEMO_HD void q1_uppu_point(const hemo_params& par, const Q1Geom& ge, const Q1State& s, double w, bool do_up,
+                           bool do_pu, double up[4][4][2], double pu[4][4][2]) {
+    const double rho = par.rho, mu = par.mu, idt = 1.0 / par.dt;
+    const double tr = s.tau / rho;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        double dR[2][2];
+        if (do_pu) {
+            const double cb = rho * (ge.phi[b] * idt + 0.5 * s.umg[b]);
+            const double hb = 0.5 * rho * ge.phi[b];
+            const double vb = 0.5 * mu * ge.theta[b];
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+                for (int l = 0; l < 2; ++l) {
+                    const double dkl = (k == l) ? 1.0 : 0.0;
+                    dR[k][l] = cb * dkl + hb * s.G[l][k] - vb * (ge.trk * dkl + ge.k[k][l]);
+                }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            if (do_up) {
+                up[a][b][0] += w * (-ge.phi[b] * ge.g[a][0] + s.tau * s.umg[a] * ge.g[b][0]);
+                up[a][b][1] += w * (-ge.phi[b] * ge.g[a][1] + s.tau * s.umg[a] * ge.g[b][1]);
+            }
+            if (do_pu) {
+                pu[a][b][0] += w * (0.5 * ge.phi[a] * ge.g[b][0] + tr * (dR[0][0] * ge.g[a][0] + dR[1][0] * ge.g[a][1]));
+                pu[a][b][1] += w * (0.5 * ge.phi[a] * ge.g[b][1] + tr * (dR[0][1] * ge.g[a][0] + dR[1][1] * ge.g[a][1]));
             }
         }
-        if (blocks & Q1_UP) {
-            acc[b][2] += w * (-ge.phi[b] * ga[0] + s.tau * sa * ge.g[b][0]);
-            acc[b][5] += w * (-ge.phi[b] * ga[1] + s.tau * sa * ge.g[b][1]);
-        }
-        if (blocks & Q1_PP) acc[b][8] += w * tr * gab;
     }
 }
 
@@ -224,25 +255,90 @@ HEMO_HD int q1_blocks_of_rule(const HemoQuadRule* rules, int r) {
     return m;
 }
 
-// Rows of test node a of the 12x12 element Jacobian, every block with its own rule.
-HEMO_HD void q1_cell_jacobian_row(const Q1Cell& c, const hemo_params& par, const HemoQuadRule* rules, int a,
-                                  double acc[4][9]) {
+// Work items 0 / 1: J_uu rows of test nodes A0, A0+1 with the J_uu rule; emit(slot, value).
+template <int A0, typename Emit>
+HEMO_HD void q1_cell_jacobian_uu(const Q1Cell& c, const hemo_params& par, const HemoQuadRule* rules, Emit emit) {
+    double uu[2][4][4];
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int k = 0; k < 9; ++k) acc[b][k] = 0.0;
-    for (int r = HEMO_Q_UU; r <= HEMO_Q_PP; ++r) {
-        const int blocks = q1_blocks_of_rule(rules, r);
-        if (blocks == 0) continue;
-        const HemoQuadRule& ru = rules[r];
-        for (int q = 0; q < ru.nq; ++q) {
-            Q1Geom ge;
-            Q1State s;
-            q1_geom(c, ru.pt[q][0], ru.pt[q][1], ge);
-            q1_state(c, par, ge, s);
-            q1_jacobian_row_point(par, ge, s, ru.pt[q][2] * ge.adet, a, blocks, acc);
-        }
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) uu[i][b][k] = 0.0;
+    const HemoQuadRule& ru = rules[HEMO_Q_UU];
+    for (int q = 0; q < ru.nq; ++q) {
+        Q1Geom ge;
+        Q1State s;
+        q1_geom(c, ru.pt[q][0], ru.pt[q][1], ge);
+        q1_state(c, par, ge, s);
+        q1_uu_point<A0>(par, ge, s, ru.pt[q][2] * ge.adet, uu);
     }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+                for (int l = 0; l < 2; ++l) emit(((A0 + i) * 4 + b) * 9 + k * 3 + l, uu[i][b][k * 2 + l]);
+}
+
+// Work item 2: J_up and J_pu (one pass when their rules coincide), then J_pp.
+template <typename Emit>
+HEMO_HD void q1_cell_jacobian_p(const Q1Cell& c, const hemo_params& par, const HemoQuadRule* rules, Emit emit) {
+    {
+        double up[4][4][2], pu[4][4][2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) up[a][b][0] = up[a][b][1] = pu[a][b][0] = pu[a][b][1] = 0.0;
+        const bool shared = rules[HEMO_Q_PU].alias == rules[HEMO_Q_UP].alias;
+        for (int pass = 0; pass < (shared ? 1 : 2); ++pass) {
+            const HemoQuadRule& ru = rules[pass == 0 ? HEMO_Q_UP : HEMO_Q_PU];
+            const bool do_up = pass == 0, do_pu = shared || pass == 1;
+            for (int q = 0; q < ru.nq; ++q) {
+                Q1Geom ge;
+                Q1State s;
+                q1_geom(c, ru.pt[q][0], ru.pt[q][1], ge);
+                q1_state(c, par, ge, s);
+                q1_uppu_point(par, ge, s, ru.pt[q][2] * ge.adet, do_up, do_pu, up, pu);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                emit((a * 4 + b) * 9 + 2, up[a][b][0]);
+                emit((a * 4 + b) * 9 + 5, up[a][b][1]);
+                emit((a * 4 + b) * 9 + 6, pu[a][b][0]);
+                emit((a * 4 + b) * 9 + 7, pu[a][b][1]);
+            }
+    }
+    double pp[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) pp[a][b] = 0.0;
+    const HemoQuadRule& ru = rules[HEMO_Q_PP];
+    for (int q = 0; q < ru.nq; ++q) {
+        Q1Geom ge;
+        q1_geom(c, ru.pt[q][0], ru.pt[q][1], ge);
+        // only tau is needed from the state: previous velocity at the point
+        double un0 = 0.0, un1 = 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { un0 += ge.phi[a] * c.N[a][0]; un1 += ge.phi[a] * c.N[a][1]; }
+        double tau, taul;
+        q1_tau(par, c.h, un0, un1, tau, taul);
+        const double wt = ru.pt[q][2] * ge.adet * tau / par.rho;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) pp[a][b] += wt * (ge.g[a][0] * ge.g[b][0] + ge.g[a][1] * ge.g[b][1]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) emit((a * 4 + b) * 9 + 8, pp[a][b]);
 }
 
 // ---- lifting ----------------------------------------------------------------------

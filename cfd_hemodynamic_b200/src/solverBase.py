@@ -141,6 +141,8 @@ class SolverBase(ABC):
         X = x[cells]
         m = cells.shape[0]
         ar = np.arange(m)
+        if cells.shape[1] == 4:
+            return self._assemble_wss_quadrilateral(X, cells, lf)
         fv = np.array([[1, 2], [0, 2], [0, 1]])
         va, vb = fv[lf, 0], fv[lf, 1]
         t = X[ar, vb] - X[ar, va]
@@ -164,3 +166,35 @@ class SolverBase(ABC):
         out[:] = 0.0
         np.add.at(out, cells[ar, va], 0.5 * Tt)
         np.add.at(out, cells[ar, vb], 0.5 * Tt)
+
+    def _assemble_wss_quadrilateral(self, X, cells, lf):
+        """Same traction form on Q1 quadrilaterals: grad(u) varies along the facet, so
+        (1/|F|) int_F phi_a Tt ds is integrated with 3 Gauss points per facet (the trace of
+        phi_a is linear, eps(u) rational on non-affine cells)."""
+        from ..fem.mesh import QUAD_FACETS
+        from ..fem.quadrature import interval_gauss
+        m = cells.shape[0]
+        ar = np.arange(m)
+        fv = np.array(QUAD_FACETS)
+        va, vb = fv[lf, 0], fv[lf, 1]
+        t = X[ar, vb] - X[ar, va]
+        nrm = np.stack([t[:, 1], -t[:, 0]], axis=1) / np.linalg.norm(t, axis=1)[:, None]
+        mid = 0.5 * (X[ar, va] + X[ar, vb])
+        nrm *= np.sign(np.einsum("ei,ei->e", nrm, mid - X.mean(axis=1)))[:, None]
+        U = self.u_sol.x.array.reshape(-1, 2)[cells]
+        mu = float(self.mu.value)
+        out = self.shear_stress.x.array.reshape(-1, 2)
+        out[:] = 0.0
+        for s_q, w_q in zip(*interval_gauss(3)):
+            xi = np.where((lf == 0) | (lf == 3), s_q, np.where(lf == 1, 0.0, 1.0))
+            eta = np.where(lf == 0, 0.0, np.where(lf == 3, 1.0, s_q))
+            dref = np.stack([np.stack([-(1 - eta), -(1 - xi)], 1), np.stack([(1 - eta), -xi], 1),
+                             np.stack([-eta, (1 - xi)], 1), np.stack([eta, xi], 1)], axis=1)      # (m, 4, 2)
+            Jm = np.einsum("eai,eaj->eij", X, dref)
+            dphi = np.einsum("eaj,eji->eai", dref, np.linalg.inv(Jm))
+            G = np.einsum("eai,eaj->eij", dphi, U)
+            eps = 0.5 * (G + np.swapaxes(G, 1, 2))
+            T = -2.0 * mu * np.einsum("eij,ej->ei", eps, nrm)
+            Tt = T - np.einsum("ei,ei->e", T, nrm)[:, None] * nrm
+            np.add.at(out, cells[ar, va], (w_q * (1.0 - s_q)) * Tt)
+            np.add.at(out, cells[ar, vb], (w_q * s_q) * Tt)

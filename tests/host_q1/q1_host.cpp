@@ -49,12 +49,10 @@ void q1h_cell_jacobian(int E, int n, const int32_t* cells, const double* x, cons
     for (int c = 0; c < E; ++c) {
         Q1Cell cd; int v[4];
         load(cd, c, cells, x, h, sol, un, n, v);
-        for (int a = 0; a < 4; ++a) {
-            double acc[4][9];
-            q1_cell_jacobian_row(cd, g_par, g_rules, a, acc);
-            for (int b = 0; b < 4; ++b)
-                for (int k = 0; k < 9; ++k) Ae[((int64_t)(a * 4 + b) * 9 + k) * E + c] = acc[b][k];
-        }
+        auto emit = [&](int slot, double val) { Ae[(int64_t)slot * E + c] = val; };
+        q1_cell_jacobian_uu<0>(cd, g_par, g_rules, emit);
+        q1_cell_jacobian_uu<2>(cd, g_par, g_rules, emit);
+        q1_cell_jacobian_p(cd, g_par, g_rules, emit);
     }
 }
 
