@@ -404,11 +404,13 @@ def main():
     # ---- roofline of the dominant kernel -------------------------------------------
     n = s.n
     nnz_node = hemo.nnz_node
+    nv = int(s._cells_host.shape[1])                      # 3: P1 triangles, 4: Q1 quadrilaterals
+    ae_bytes = 72 * nv * nv * E                           # element matrices, 9 doubles per node pair
     alg_bytes = {
         0: 76 * nnz_node + 52 * n,                        # J values + node cols + rowptr + x + y
-        1: 12 * E + 8 * E + 56 * n + 648 * E,             # cells, h, nodal gathers, element matrices out
-        2: 648 * E + 36 * E + 12 * nnz_node + 72 * nnz_node,
-        3: 12 * E + 8 * E + 56 * n + 72 * E,
+        1: 4 * nv * E + 8 * E + 56 * n + ae_bytes,        # cells, h, nodal gathers, element matrices out
+        2: ae_bytes + 4 * nv * nv * E + 12 * nnz_node + 72 * nnz_node,
+        3: 4 * nv * E + 8 * E + 56 * n + 24 * nv * E,
         4: 20 * nnz_node + 4 * n + 56 * n,                # A00 BSR2 fp32 values + cols + rowptr + 7 fp32 vectors of 2n
         5: 8 * nnz_node + 4 * n + 28 * n,
         6: None, 7: None,
@@ -452,7 +454,8 @@ def main():
                        "newton_its_per_step": newton / K, "fgmres_its_per_step": ksp / K,
                        "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (one mesh per GPU)",
                        "l2": "inputs larger than L2 (matrix %.0f MB, element buffer %.0f MB vs 126 MB L2)"
-                             % (8 * nnz / 1e6, 648 * E / 1e6)},
+                             % (8 * nnz / 1e6, 72 * int(s._cells_host.shape[1]) ** 2 * E / 1e6),
+                       "cell_type": s.mesh.topology.cell_name()},
             "assembly": {"jacobian_cells_per_s": world * E / (jac_ms * 1e-3), "jacobian_nnz_per_s": world * nnz / (jac_ms * 1e-3),
                          "residual_cells_per_s": world * E / (res_ms * 1e-3), "jacobian_ms": jac_ms, "residual_ms": res_ms},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

@@ -2,7 +2,9 @@
 src/scenarios/stenosis_mesh_variable.py:30-450), the natural scenario for
 `stabilized_schur_backflow`: parabolic inlet of peak `v_max`, no-slip walls,
 do-nothing outlet with backflow stabilisation.  Plain `stabilized_schur`
-ignores the pressure kwargs through **kwargs (stabilized_schur.py:51)."""
+ignores the pressure kwargs through **kwargs (stabilized_schur.py:51);
+`stabilized_schur_velocity_vascular_backflow` additionally takes
+`R_resistance` / `alpha_damping` for its resistance outlet."""
 import numpy as np
 
 from ...fem import generators
@@ -40,6 +42,9 @@ class StenosisMeshVariableSimulation(Scenario):
             solver_kwargs["beta_backflow"] = float(beta_backflow)
         if v_max is not None:
             solver_kwargs["v_max"] = float(v_max)
+        for k in ("R_resistance", "alpha_damping"):
+            if k in self.mesh_options:
+                solver_kwargs[k] = float(self.mesh_options.pop(k))
         super().__init__(solver_name, "stenosis_mesh_variable", rho, mu, dt, T, f, **solver_kwargs)
         self.mesh.topology.create_connectivity(self.mesh.topology.dim - 1, self.mesh.topology.dim)
         self.setup()

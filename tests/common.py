@@ -124,6 +124,10 @@ def oracle_problem_from_solver(s, facet_tags=None, tags=None):
     elif s.variant == "backflow":
         out = facet_tags.find(tags["outlet"])
         fs.append(O.FacetSet(pairs=mesh.topology.facet_cell_pairs(out), a_b=c, beta_b=s.beta_backflow))
+    elif s.variant == "velocity_vascular_backflow":
+        out = facet_tags.find(tags["outlet"])
+        fs.append(O.FacetSet(pairs=mesh.topology.facet_cell_pairs(out), pconst=0.0, a_s=c, a_b=c,
+                             beta_b=s.beta_backflow))
     else:
         fin = facet_tags.find(tags["inlet"])
         out = facet_tags.find(tags["outlet"])

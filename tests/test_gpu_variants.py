@@ -63,6 +63,48 @@ def test_backflow_variant_matches_oracle():
     assert _rel(s.p_sol.x.array, xk[2 * n:]) < 1e-8
 
 
+@pytest.mark.parametrize("double_setup", [False, True])
+def test_velocity_vascular_backflow_variant_matches_oracle(double_setup):
+    """Dirichlet inlet velocity + resistance outlet + backflow stabilization (reference
+    stabilized_schur_velocity_vascular_backflow.py:163-205, 377-391): the outlet pressure follows
+    p_c <- alpha R |Q| + (1 - alpha) p_c with Q from the previous u_prev; a second setup() doubles
+    the outlet terms and freezes the first constant."""
+    from cfd_hemodynamic_b200.src.scenarios.stenosis_mesh_variable import StenosisMeshVariableSimulation
+    from oracle import ns_oracle as O
+    sc = StenosisMeshVariableSimulation("stabilized_schur_velocity_vascular_backflow", 0.01, 0.04, grade="moderate",
+                                        v_max=5.0, R_resistance=3.0, n_elements_radial=3, L=20.0,
+                                        x_position_stenosis=8.0, **TIGHT)
+    if double_setup:
+        sc.setup()
+    s = sc.solver
+    assert s.variant == "velocity_vascular_backflow" and s._setup_count == (2 if double_setup else 1)
+    prob = T.oracle_problem_from_solver(s, sc.facet_tags, sc.tags)
+    assert len(prob.facet_sets) == 1 and len(prob.bcs) == 2          # outlet terms only; inlet + wall Dirichlet
+    n = s.n
+    out_pairs = prob.facet_sets[0].pairs
+    state = {"frozen": [0.0] * (s._setup_count - 1), "pc": 0.0}      # zero initial velocity: R|Q_init| = 0
+
+    def refresh():
+        prob.facet_sets[0].pconst = 0.5 * (sum(state["frozen"]) + state["pc"])
+
+    def after_step(prob_, un_old):
+        q = O.outlet_flux(prob_, out_pairs, un_old)
+        state["pc"] = s.alpha_damping * s.R_resistance * abs(q) + (1 - s.alpha_damping) * state["pc"]
+        refresh()
+
+    refresh()
+    steps = 4
+    for _ in range(steps):
+        s.solveStep()
+        s.u_prev.x.array[:] = s.u_sol.x.array[:]
+        s.p_prev.x.array[:] = s.p_sol.x.array[:]
+    xk = _march_oracle(prob, np.zeros(3 * n), np.zeros(2 * n), steps, after_step)
+    assert abs(s._p_c - state["pc"]) <= 1e-9 * max(1.0, abs(state["pc"]))
+    assert state["pc"] > 0.0
+    assert _rel(s.u_sol.x.array, xk[:2 * n]) < 1e-8
+    assert _rel(s.p_sol.x.array, xk[2 * n:]) < 1e-8
+
+
 @pytest.mark.parametrize("double_setup,cell_type", [(False, "triangle"), (True, "triangle"),
                                                     (False, "quadrilateral"), (True, "quadrilateral")])
 def test_pressure_backflow_variant_matches_oracle(double_setup, cell_type):

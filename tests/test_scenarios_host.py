@@ -120,3 +120,49 @@ def test_amg_setup_leaves_uncoupled_vertices_to_the_smoother(hemo_lib_built):
     P = lv[0]["P"]
     assert P[[50, 51, 52]].nnz == 0
     assert lv[-1]["P"].shape[1] <= 20
+
+
+def test_velocity_vascular_backflow_tables_host_only():
+    """Plugin discovery by name + outlet-only boundary tables with the setup() multiplicity."""
+    from cfd_hemodynamic_b200.src.scenarios.stenosis_mesh_variable import StenosisMeshVariableSimulation
+    with pytest.raises(RuntimeError, match="R_resistance is required"):      # Scenario wraps ctor errors (scenario.py:101-110)
+        StenosisMeshVariableSimulation("stabilized_schur_velocity_vascular_backflow", 1e-3, 1e-2, grade="moderate",
+                                       v_max=5.0, n_elements_radial=3, L=20.0, x_position_stenosis=8.0, host_only=True)
+    sc = StenosisMeshVariableSimulation("stabilized_schur_velocity_vascular_backflow", 1e-3, 1e-2, grade="moderate",
+                                        v_max=5.0, R_resistance=3.0, alpha_damping=0.5, n_elements_radial=3, L=20.0,
+                                        x_position_stenosis=8.0, host_only=True)
+    s = sc.solver
+    assert s.variant == "velocity_vascular_backflow" and s.alpha_damping == 0.5 and s.R_resistance == 3.0
+    t = s.export_tables()
+    assert sorted(t["facet_sets"]) == [2]                                # outlet set only, no inlet terms
+    assert t["facet_sets"][2][1] == dict(pconst=0.0, a_s=1.0, a_b=1.0, beta_b=0.2)
+    assert [b for b, _, _ in t["bcs"]] == ["u", "u"]                     # inlet profile + walls
+    sc.setup()
+    assert s.export_tables()["facet_sets"][2][1]["a_s"] == 2.0 and s._p_c_frozen == [0.0]
+
+
+def test_quadrilateral_scenario_tables_host_only():
+    """stenosis_pressure_structured defaults to the reference's recombined Q1 mesh."""
+    from cfd_hemodynamic_b200.src.scenarios.stenosis_pressure import StenosisPressureSimulation
+    from cfd_hemodynamic_b200.src.scenarios.stenosis_pressure_structured import StenosisPressureStructuredSimulation
+    kw = dict(grade="moderate", p_inlet=2.0, R_resistance=50.0, res=0.6, L=20.0, x_position_stenosis=8.0, host_only=True)
+    sq = StenosisPressureStructuredSimulation("stabilized_schur_pressure_backflow", 0.005, 0.02, **kw)
+    st = StenosisPressureSimulation("stabilized_schur_pressure_backflow", 0.005, 0.02, **kw)
+    assert sq.mesh.topology.cell_name() == "quadrilateral" and st.mesh.topology.cell_name() == "triangle"
+    assert sq.solver.n == st.solver.n and 2 * sq.mesh.num_cells == st.mesh.num_cells
+    tq = sq.solver.export_tables()
+    assert tq["cells"].shape[1] == 4
+    # inlet facets are local facet 1 = (0,2) of the first cell column, outlet facets local facet 2 = (1,3)
+    assert set(tq["facet_sets"][1][0][:, 1]) == {1} and set(tq["facet_sets"][2][0][:, 1]) == {2}
+    # WSS post-processing on quadrilaterals: Couette field u = (y, 0) gives |tau_w| = mu on straight walls
+    s = sq.solver
+    s.initStressForm()
+    x = s.mesh.geometry.x
+    u = np.zeros((x.shape[0], 2))
+    u[:, 0] = x[:, 1]
+    s.u_sol.x.array[:] = u.reshape(-1)
+    s.assemble_wss()
+    w = s.shear_stress.x.array.reshape(-1, 2)
+    row = int(tq["cells"][0][2])                     # vertices 0..row-1 form the bottom wall (slightly tapered)
+    straight = (np.arange(x.shape[0]) < row) & (x[:, 0] > 0.5) & (x[:, 0] < 2.0)
+    assert straight.any() and np.allclose(np.linalg.norm(w[straight], axis=1), float(s.mu.value), rtol=2e-2)
