@@ -64,6 +64,7 @@ SYMBOLS = {
     "hemo_set_quadrature": (_I, [_VP, _I, _VP, _VP, _I]),
     "hemo_set_facet_quadrature": (_I, [_VP, _VP, _VP, _I]),
     "hemo_set_params": (_I, [_VP, C.POINTER(Params)]),
+    "hemo_set_time_scheme": (_I, [_VP, _D, _D, _VP]),
     "hemo_set_facet_set": (_I, [_VP, _I, _VP, _VP, _I, C.POINTER(FacetCoef)]),
     "hemo_set_facet_coef": (_I, [_VP, _I, C.POINTER(FacetCoef)]),
     "hemo_set_bc": (_I, [_VP, _VP, _VP, _VP]),
@@ -226,6 +227,12 @@ class Hemo:
         wts = np.ascontiguousarray(wts, dtype=np.float64)
         self._check(self.lib.hemo_set_quadrature(self._ctx, block, _np_ptr(pts), _np_ptr(wts), len(wts)),
                     "hemo_set_quadrature")
+
+    def set_time_scheme(self, theta: float, a0: float, uh=None):
+        """theta = d(u_e)/du, a0 = leading BDF coefficient, uh = history vector (2n, device) or None."""
+        self._keep["uh"] = uh
+        self._check(self.lib.hemo_set_time_scheme(self._ctx, float(theta), float(a0), _ptr(uh)),
+                    "hemo_set_time_scheme")
 
     def set_facet_quadrature(self, pts, wts):
         pts = np.ascontiguousarray(pts, dtype=np.float64)

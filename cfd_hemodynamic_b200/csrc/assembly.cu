@@ -24,7 +24,7 @@ int hemo_amg_numeric_shift(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift);
 
 __constant__ HemoRule c_rules[HEMO_NRULES];
 __constant__ HemoFacetRule c_frule;
-__constant__ hemo_params c_par;
+__constant__ HemoForm c_par;
 
 // symmetric 3x3 index: (0,0)=0 (1,1)=1 (2,2)=2 (0,1)=3 (0,2)=4 (1,2)=5
 __device__ __forceinline__ constexpr int sym3(int a, int b) {
@@ -35,13 +35,14 @@ struct CellData {
     double g[3][2];    // grad phi_a
     double detJ;       // |det J|
     double U[3][2], N[3][2], P[3];
+    double H[3][2];    // history of the time derivative: dudt = (a0 U - H) / dt
     double h;
 };
 
 __device__ __forceinline__ void load_cell(CellData& cd, int c, int E, const int32_t* __restrict__ cells,
                                           const double* __restrict__ x, const double* __restrict__ h,
                                           const double* __restrict__ sol, const double* __restrict__ un,
-                                          int n, int v[3]) {
+                                          const double* __restrict__ uh, int n, int v[3]) {
     v[0] = cells[3 * (int64_t)c + 0];
     v[1] = cells[3 * (int64_t)c + 1];
     v[2] = cells[3 * (int64_t)c + 2];
@@ -54,6 +55,8 @@ __device__ __forceinline__ void load_cell(CellData& cd, int c, int E, const int3
         cd.U[a][0] = uv.x; cd.U[a][1] = uv.y;
         const double2 nv = reinterpret_cast<const double2*>(un)[v[a]];
         cd.N[a][0] = nv.x; cd.N[a][1] = nv.y;
+        const double2 hv = reinterpret_cast<const double2*>(uh)[v[a]];
+        cd.H[a][0] = hv.x; cd.H[a][1] = hv.y;
         cd.P[a] = sol[2 * (int64_t)n + v[a]];
     }
     const double j00 = X[1][0] - X[0][0], j01 = X[2][0] - X[0][0];
@@ -126,11 +129,11 @@ struct CellDerived {
 };
 
 __device__ __forceinline__ void derive_cell(const CellData& cd, CellDerived& d) {
-    const double idt = 1.0 / c_par.dt;
+    const double idt = 1.0 / c_par.dt, th = c_par.theta, a0 = c_par.a0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        d.M[a][0] = 0.5 * (cd.U[a][0] + cd.N[a][0]);
-        d.M[a][1] = 0.5 * (cd.U[a][1] + cd.N[a][1]);
+        d.M[a][0] = th * cd.U[a][0] + (1.0 - th) * cd.N[a][0];
+        d.M[a][1] = th * cd.U[a][1] + (1.0 - th) * cd.N[a][1];
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -147,7 +150,7 @@ __device__ __forceinline__ void derive_cell(const CellData& cd, CellDerived& d) 
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const double conv = d.M[c][0] * d.G[0][k] + d.M[c][1] * d.G[1][k];
-            d.A[c][k] = (cd.U[c][k] - cd.N[c][k]) * idt + conv - c_par.f[k];
+            d.A[c][k] = (a0 * cd.U[c][k] - cd.H[c][k]) * idt + conv - c_par.f[k];
             d.R[c][k] = c_par.rho * d.A[c][k] + d.gp[k];
         }
     }
@@ -198,7 +201,8 @@ __device__ __forceinline__ void element_residual(const CellData& cd, const CellD
 // slot = (a*3+b)*9 + ri*3 + ci; ri/ci in (u_x, u_y, p).
 template <typename Emit>
 __device__ __forceinline__ void element_jacobian(const CellData& cd, const CellDerived& d, Emit emit) {
-    const double rho = c_par.rho, mu = c_par.mu, idt = 1.0 / c_par.dt;
+    // th = d(u_e)/du and idt = d(dudt)/du carry the time scheme (1/2 and 1/dt for the mid-point rule)
+    const double rho = c_par.rho, mu = c_par.mu, idt = c_par.a0 / c_par.dt, th = c_par.theta;
     double T2[6], L0, T1up[3], T1pu[3], T0pp;
     rule_moments(HEMO_Q_UU, cd, T2, L0);
     {
@@ -253,15 +257,15 @@ __device__ __forceinline__ void element_jacobian(const CellData& cd, const CellD
             double Qab = 0.0;
 #pragma unroll
             for (int c = 0; c < 3; ++c) Qab += cd.detJ * ruu.m2[sym3(a, c)] * d.s[c][b];
-            const double diag = rho * m2ab * idt + 0.5 * rho * Qab + 0.5 * mu * m0 * gab +
-                                rho * Wab * idt + 0.5 * rho * Zab;
-            const double cG = 0.5 * rho * (m2ab + Wab);
+            const double diag = rho * m2ab * idt + th * rho * Qab + th * mu * m0 * gab +
+                                rho * Wab * idt + th * rho * Zab;
+            const double cG = th * rho * (m2ab + Wab);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
 #pragma unroll
                 for (int l = 0; l < 2; ++l) {
-                    double v = cG * d.G[l][k] + 0.5 * mu * m0 * cd.g[a][l] * cd.g[b][k] +
-                               0.5 * cd.g[a][l] * RT[b][k] + 0.5 * L0 * rho * cd.g[a][k] * cd.g[b][l];
+                    double v = cG * d.G[l][k] + th * mu * m0 * cd.g[a][l] * cd.g[b][k] +
+                               th * cd.g[a][l] * RT[b][k] + th * L0 * rho * cd.g[a][k] * cd.g[b][l];
                     if (k == l) v += diag;
                     emit(base + k * 3 + l, v);
                 }
@@ -270,9 +274,9 @@ __device__ __forceinline__ void element_jacobian(const CellData& cd, const CellD
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 emit(base + k * 3 + 2, -m1b_up * cd.g[a][k] + cd.g[b][k] * V[a]);              // J_up
-                emit(base + 6 + k, 0.5 * m1a_pu * cd.g[b][k] +
-                                       cd.g[a][k] * (T1pu[b] * idt + 0.5 * Y[b]) +
-                                       0.5 * T1pu[b] * Gga[k]);                                  // J_pu
+                emit(base + 6 + k, th * m1a_pu * cd.g[b][k] +
+                                       cd.g[a][k] * (T1pu[b] * idt + th * Y[b]) +
+                                       th * T1pu[b] * Gga[k]);                                   // J_pu
             }
             emit(base + 8, T0pp / rho * gab);                                                    // J_pp
         }
@@ -285,12 +289,12 @@ __device__ __forceinline__ void element_jacobian(const CellData& cd, const CellD
 __global__ void __launch_bounds__(128)
 k_cell_jacobian(int E, int n, const int32_t* __restrict__ cells, const double* __restrict__ x,
                 const double* __restrict__ h, const double* __restrict__ sol,
-                const double* __restrict__ un, double* __restrict__ Ae) {
+                const double* __restrict__ un, const double* __restrict__ uh, double* __restrict__ Ae) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= E) return;
     CellData cd;
     int v[3];
-    load_cell(cd, c, E, cells, x, h, sol, un, n, v);
+    load_cell(cd, c, E, cells, x, h, sol, un, uh, n, v);
     CellDerived d;
     derive_cell(cd, d);
     double* out = Ae + c;
@@ -333,13 +337,13 @@ __device__ __noinline__ void lift_cell(const CellData& cd, const CellDerived& d,
 __global__ void __launch_bounds__(128)
 k_cell_residual(int E, int n, const int32_t* __restrict__ cells, const double* __restrict__ x,
                 const double* __restrict__ h, const double* __restrict__ sol,
-                const double* __restrict__ un, const uint8_t* __restrict__ cellflag,
-                const double* __restrict__ dvec, double* __restrict__ Fe) {
+                const double* __restrict__ un, const double* __restrict__ uh,
+                const uint8_t* __restrict__ cellflag, const double* __restrict__ dvec, double* __restrict__ Fe) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= E) return;
     CellData cd;
     int v[3];
-    load_cell(cd, c, E, cells, x, h, sol, un, n, v);
+    load_cell(cd, c, E, cells, x, h, sol, un, uh, n, v);
     CellDerived d;
     derive_cell(cd, d);
     double Fu[3][2], Fp[3];
@@ -364,7 +368,7 @@ __global__ void __launch_bounds__(128)
 k_facets(int m, int E, int n, const int32_t* __restrict__ fcells, const int32_t* __restrict__ fmask,
          hemo_facet_coef co, const int32_t* __restrict__ cells, const double* __restrict__ x,
          const double* __restrict__ h, const double* __restrict__ sol, const double* __restrict__ un,
-         const uint8_t* __restrict__ cellflag, const double* __restrict__ dvec,
+         const double* __restrict__ uh, const uint8_t* __restrict__ cellflag, const double* __restrict__ dvec,
          double* __restrict__ out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m) return;
@@ -372,18 +376,19 @@ k_facets(int m, int E, int n, const int32_t* __restrict__ fcells, const int32_t*
     const int mask = fmask[t];
     CellData cd;
     int v[3];
-    load_cell(cd, c, E, cells, x, h, sol, un, n, v);
+    load_cell(cd, c, E, cells, x, h, sol, un, uh, n, v);
     double X[3][2];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         X[a][0] = x[2 * (int64_t)v[a]];
         X[a][1] = x[2 * (int64_t)v[a] + 1];
     }
+    const double th = c_par.theta;     // d(u_e)/du of the time scheme (1/2: mid-point rule)
     double M[3][2];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        M[a][0] = 0.5 * (cd.U[a][0] + cd.N[a][0]);
-        M[a][1] = 0.5 * (cd.U[a][1] + cd.N[a][1]);
+        M[a][0] = th * cd.U[a][0] + (1.0 - th) * cd.N[a][0];
+        M[a][1] = th * cd.U[a][1] + (1.0 - th) * cd.N[a][1];
     }
     double G[2][2];
 #pragma unroll
@@ -465,12 +470,12 @@ k_facets(int m, int E, int n, const int32_t* __restrict__ fcells, const int32_t*
 #pragma unroll
                         for (int l = 0; l < 2; ++l) {
                             const double dkl = (k == l) ? 1.0 : 0.0;
-                            double vv = -0.5 * co.a_g * mu * cd.g[b][k] * nr[l] * Ph[a];
-                            vv -= 0.5 * co.a_s * mu * (cd.g[b][k] * nr[l] + dn[b] * dkl) * Ph[a];
-                            vv -= 0.5 * co.a_n * mu * (Png[b][k] * nr[l] + dn[b] * Pn[k][l]) * Ph[a];
-                            vv -= 0.5 * co.a_n * mu * (Png[a][l] * nr[k] + dn[a] * Pn[k][l]) * Ph[b];
-                            vv += 0.5 * pen * Pn[k][l] * Ph2[a][b];
-                            vv -= 0.5 * bf * B[a][b] * dkl;
+                            double vv = -th * co.a_g * mu * cd.g[b][k] * nr[l] * Ph[a];
+                            vv -= th * co.a_s * mu * (cd.g[b][k] * nr[l] + dn[b] * dkl) * Ph[a];
+                            vv -= th * co.a_n * mu * (Png[b][k] * nr[l] + dn[b] * Pn[k][l]) * Ph[a];
+                            vv -= th * co.a_n * mu * (Png[a][l] * nr[k] + dn[a] * Pn[k][l]) * Ph[b];
+                            vv += th * pen * Pn[k][l] * Ph2[a][b];
+                            vv -= th * bf * B[a][b] * dkl;
                             juu[k][l] = vv;
                         }
                     }
@@ -865,7 +870,7 @@ static int upload_constants(hemo_ctx* ctx) {
                                                  cudaMemcpyHostToDevice, ctx->stream));
     HEMO_CHECK_CUDA(ctx, cudaMemcpyToSymbolAsync(c_frule, &ctx->frule, sizeof(HemoFacetRule), 0,
                                                  cudaMemcpyHostToDevice, ctx->stream));
-    HEMO_CHECK_CUDA(ctx, cudaMemcpyToSymbolAsync(c_par, &ctx->par, sizeof(hemo_params), 0,
+    HEMO_CHECK_CUDA(ctx, cudaMemcpyToSymbolAsync(c_par, &ctx->par, sizeof(HemoForm), 0,
                                                  cudaMemcpyHostToDevice, ctx->stream));
     // constants are read by kernels on the same stream, in order
     ctx->rules_dirty = false;
@@ -1048,8 +1053,20 @@ extern "C" int hemo_set_facet_quadrature(hemo_ctx* ctx, const double* pts, const
 
 extern "C" int hemo_set_params(hemo_ctx* ctx, const hemo_params* p) {
     if (!ctx || !p || !(p->dt > 0) || !(p->rho > 0) || !(p->mu > 0)) return HEMO_EINVAL;
-    ctx->par = *p;
+    ctx->par.dt = p->dt; ctx->par.rho = p->rho; ctx->par.mu = p->mu;
+    ctx->par.f[0] = p->f[0]; ctx->par.f[1] = p->f[1];
+    ctx->par.eps0 = p->eps0;
     ctx->have_par = true;
+    ctx->rules_dirty = true;
+    ctx->qrules_dirty = true;
+    return 0;
+}
+
+extern "C" int hemo_set_time_scheme(hemo_ctx* ctx, double theta, double a0, const double* uh_dev) {
+    if (!ctx || !(theta > 0.0) || !(theta <= 1.0) || !(a0 > 0.0)) return HEMO_EINVAL;
+    ctx->par.theta = theta;
+    ctx->par.a0 = a0;
+    ctx->uh = uh_dev;
     ctx->rules_dirty = true;
     ctx->qrules_dirty = true;
     return 0;
@@ -1123,11 +1140,12 @@ extern "C" int hemo_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const 
     const int E = ctx->E, n = ctx->n, nv = ctx->nv;
     if ((rc = ensure_elem(ctx, (size_t)9 * nv * nv * E, 0))) return rc;
     cudaStream_t st = ctx->stream;
+    const double* uh = ctx->uh ? ctx->uh : un_dev;
     HEMO_PROF_BEGIN(ctx, HEMO_PROF_CELL_JAC);
     if (nv == 4) {
         if ((rc = hemo_q1_cell_jacobian(ctx, x_dev, un_dev))) return rc;
     } else {
-        k_cell_jacobian<<<hemo_grid(E, 128), 128, 0, st>>>(E, n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, ctx->Ae);
+        k_cell_jacobian<<<hemo_grid(E, 128), 128, 0, st>>>(E, n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, uh, ctx->Ae);
         HEMO_LAUNCH_CHECK(ctx);
     }
     HEMO_PROF_END(ctx, HEMO_PROF_CELL_JAC);
@@ -1139,7 +1157,7 @@ extern "C" int hemo_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const 
             continue;
         }
         k_facets<1><<<hemo_grid(fs.m, 128), 128, 0, st>>>(fs.m, E, n, fs.cells, fs.mask, fs.coef, ctx->cells, ctx->x,
-                                                          ctx->h, x_dev, un_dev, nullptr, nullptr, ctx->Ae);
+                                                          ctx->h, x_dev, un_dev, uh, nullptr, nullptr, ctx->Ae);
         HEMO_LAUNCH_CHECK(ctx);
     }
     HEMO_PROF_BEGIN(ctx, HEMO_PROF_GATHER_MAT);
@@ -1160,6 +1178,7 @@ extern "C" int hemo_assemble_residual(hemo_ctx* ctx, const double* x_dev, const 
     const int E = ctx->E, n = ctx->n, nv = ctx->nv;
     if ((rc = ensure_elem(ctx, 0, (size_t)3 * nv * E))) return rc;
     cudaStream_t st = ctx->stream;
+    const double* uh = ctx->uh ? ctx->uh : un_dev;
     const uint8_t* cf = ctx->have_bc ? ctx->cellflag : nullptr;
     if (ctx->have_bc) {
         k_lift_vector<<<hemo_grid(3 * (int64_t)n, 256), 256, 0, st>>>(3 * (int64_t)n, ctx->dofflag, x_dev, g_dev, ctx->dvec);
@@ -1169,7 +1188,7 @@ extern "C" int hemo_assemble_residual(hemo_ctx* ctx, const double* x_dev, const 
     if (nv == 4) {
         if ((rc = hemo_q1_cell_residual(ctx, x_dev, un_dev, cf))) return rc;
     } else {
-        k_cell_residual<<<hemo_grid(E, 128), 128, 0, st>>>(E, n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, cf, ctx->dvec, ctx->Fe);
+        k_cell_residual<<<hemo_grid(E, 128), 128, 0, st>>>(E, n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, uh, cf, ctx->dvec, ctx->Fe);
         HEMO_LAUNCH_CHECK(ctx);
     }
     HEMO_PROF_END(ctx, HEMO_PROF_CELL_RES);
@@ -1181,7 +1200,7 @@ extern "C" int hemo_assemble_residual(hemo_ctx* ctx, const double* x_dev, const 
             continue;
         }
         k_facets<0><<<hemo_grid(fs.m, 128), 128, 0, st>>>(fs.m, E, n, fs.cells, fs.mask, fs.coef, ctx->cells, ctx->x,
-                                                          ctx->h, x_dev, un_dev, cf, ctx->dvec, ctx->Fe);
+                                                          ctx->h, x_dev, un_dev, uh, cf, ctx->dvec, ctx->Fe);
         HEMO_LAUNCH_CHECK(ctx);
     }
     k_gather_vector<<<hemo_grid(n, 256), 256, 0, st>>>(n, nv, E, ctx->vseg_ptr, ctx->vseg_src, ctx->Fe,

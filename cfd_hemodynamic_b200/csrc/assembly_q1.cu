@@ -19,12 +19,12 @@
 
 __constant__ HemoQuadRule c_qrules[HEMO_NRULES];
 __constant__ HemoFacetRule c_qfrule;
-__constant__ hemo_params c_qpar;
+__constant__ HemoForm c_qpar;
 
 __device__ __forceinline__ void q1_load(Q1Cell& cd, int c, const int32_t* __restrict__ cells,
                                         const double* __restrict__ x, const double* __restrict__ h,
-                                        const double* __restrict__ sol, const double* __restrict__ un, int n,
-                                        int v[4]) {
+                                        const double* __restrict__ sol, const double* __restrict__ un,
+                                        const double* __restrict__ uh, int n, int v[4]) {
     const int4 vv = reinterpret_cast<const int4*>(cells)[c];
     v[0] = vv.x; v[1] = vv.y; v[2] = vv.z; v[3] = vv.w;
 #pragma unroll
@@ -35,6 +35,8 @@ __device__ __forceinline__ void q1_load(Q1Cell& cd, int c, const int32_t* __rest
         cd.U[a][0] = uv.x; cd.U[a][1] = uv.y;
         const double2 nv = reinterpret_cast<const double2*>(un)[v[a]];
         cd.N[a][0] = nv.x; cd.N[a][1] = nv.y;
+        const double2 hv = reinterpret_cast<const double2*>(uh)[v[a]];
+        cd.H[a][0] = hv.x; cd.H[a][1] = hv.y;
         cd.P[a] = sol[2 * (int64_t)n + v[a]];
     }
     cd.h = h[c];
@@ -44,12 +46,12 @@ template <int ITEM>
 __global__ void __launch_bounds__(128)
 k_q1_cell_jacobian(int E, int n, const int32_t* __restrict__ cells, const double* __restrict__ x,
                    const double* __restrict__ h, const double* __restrict__ sol,
-                   const double* __restrict__ un, double* __restrict__ Ae) {
+                   const double* __restrict__ un, const double* __restrict__ uh, double* __restrict__ Ae) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= E) return;
     Q1Cell cd;
     int v[4];
-    q1_load(cd, c, cells, x, h, sol, un, n, v);
+    q1_load(cd, c, cells, x, h, sol, un, uh, n, v);
     const int64_t stride = E;
     double* out = Ae + c;
     auto emit = [&](int slot, double val) { out[slot * stride] = val; };
@@ -77,13 +79,13 @@ __device__ __noinline__ void q1_lift_device(const Q1Cell& cd, const int v[4], in
 __global__ void __launch_bounds__(128)
 k_q1_cell_residual(int E, int n, const int32_t* __restrict__ cells, const double* __restrict__ x,
                    const double* __restrict__ h, const double* __restrict__ sol,
-                   const double* __restrict__ un, const uint8_t* __restrict__ cellflag,
-                   const double* __restrict__ dvec, double* __restrict__ Fe) {
+                   const double* __restrict__ un, const double* __restrict__ uh,
+                   const uint8_t* __restrict__ cellflag, const double* __restrict__ dvec, double* __restrict__ Fe) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= E) return;
     Q1Cell cd;
     int v[4];
-    q1_load(cd, c, cells, x, h, sol, un, n, v);
+    q1_load(cd, c, cells, x, h, sol, un, uh, n, v);
     double Fu[4][2], Fp[4];
     q1_cell_residual(cd, c_qpar, c_qrules, Fu, Fp);
     if (cellflag != nullptr && cellflag[c]) q1_lift_device(cd, v, n, dvec, Fu, Fp);
@@ -103,14 +105,15 @@ __global__ void __launch_bounds__(128)
 k_q1_facets(int m, int E, int n, const int32_t* __restrict__ fcells, const int32_t* __restrict__ fmask,
             hemo_facet_coef co, const int32_t* __restrict__ cells, const double* __restrict__ x,
             const double* __restrict__ h, const double* __restrict__ sol, const double* __restrict__ un,
-            const uint8_t* __restrict__ cellflag, const double* __restrict__ dvec, double* __restrict__ out) {
+            const double* __restrict__ uh, const uint8_t* __restrict__ cellflag, const double* __restrict__ dvec,
+            double* __restrict__ out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m) return;
     const int c = fcells[t];
     const int mask = fmask[t];
     Q1Cell cd;
     int v[4];
-    q1_load(cd, c, cells, x, h, sol, un, n, v);
+    q1_load(cd, c, cells, x, h, sol, un, uh, n, v);
     const int64_t stride = E;
     if (MODE == 1) {
         q1_cell_facets(cd, c_qpar, c_qfrule, co, mask, false, true,
@@ -189,7 +192,7 @@ static int q1_upload_constants(hemo_ctx* ctx) {
                                                  cudaMemcpyHostToDevice, ctx->stream));
     HEMO_CHECK_CUDA(ctx, cudaMemcpyToSymbolAsync(c_qfrule, &ctx->frule, sizeof(HemoFacetRule), 0,
                                                  cudaMemcpyHostToDevice, ctx->stream));
-    HEMO_CHECK_CUDA(ctx, cudaMemcpyToSymbolAsync(c_qpar, &ctx->par, sizeof(hemo_params), 0,
+    HEMO_CHECK_CUDA(ctx, cudaMemcpyToSymbolAsync(c_qpar, &ctx->par, sizeof(HemoForm), 0,
                                                  cudaMemcpyHostToDevice, ctx->stream));
     // the host copies above are read when the (pageable-memory) copy is staged, i.e. before return
     ctx->qrules_dirty = false;
@@ -200,12 +203,13 @@ int hemo_q1_cell_jacobian(hemo_ctx* ctx, const double* x_dev, const double* un_d
     int rc = q1_upload_constants(ctx);
     if (rc) return rc;
     const int E = ctx->E;
+    const double* uh = ctx->uh ? ctx->uh : un_dev;
     const int grid = hemo_grid(E, 128);
-    k_q1_cell_jacobian<0><<<grid, 128, 0, ctx->stream>>>(E, ctx->n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, ctx->Ae);
+    k_q1_cell_jacobian<0><<<grid, 128, 0, ctx->stream>>>(E, ctx->n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, uh, ctx->Ae);
     HEMO_LAUNCH_CHECK(ctx);
-    k_q1_cell_jacobian<1><<<grid, 128, 0, ctx->stream>>>(E, ctx->n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, ctx->Ae);
+    k_q1_cell_jacobian<1><<<grid, 128, 0, ctx->stream>>>(E, ctx->n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, uh, ctx->Ae);
     HEMO_LAUNCH_CHECK(ctx);
-    k_q1_cell_jacobian<2><<<grid, 128, 0, ctx->stream>>>(E, ctx->n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, ctx->Ae);
+    k_q1_cell_jacobian<2><<<grid, 128, 0, ctx->stream>>>(E, ctx->n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, uh, ctx->Ae);
     HEMO_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -214,8 +218,9 @@ int hemo_q1_cell_residual(hemo_ctx* ctx, const double* x_dev, const double* un_d
     int rc = q1_upload_constants(ctx);
     if (rc) return rc;
     const int E = ctx->E;
+    const double* uh = ctx->uh ? ctx->uh : un_dev;
     k_q1_cell_residual<<<hemo_grid(E, 128), 128, 0, ctx->stream>>>(E, ctx->n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev,
-                                                                   cellflag, ctx->dvec, ctx->Fe);
+                                                                   uh, cellflag, ctx->dvec, ctx->Fe);
     HEMO_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -225,13 +230,14 @@ int hemo_q1_facets(hemo_ctx* ctx, int mode, const HemoFacetSet& fs, const double
     int rc = q1_upload_constants(ctx);
     if (rc) return rc;
     const int E = ctx->E, n = ctx->n;
+    const double* uh = ctx->uh ? ctx->uh : un_dev;
     if (mode == 1)
         k_q1_facets<1><<<hemo_grid(fs.m, 128), 128, 0, ctx->stream>>>(fs.m, E, n, fs.cells, fs.mask, fs.coef, ctx->cells,
-                                                                      ctx->x, ctx->h, x_dev, un_dev, nullptr, nullptr,
+                                                                      ctx->x, ctx->h, x_dev, un_dev, uh, nullptr, nullptr,
                                                                       ctx->Ae);
     else
         k_q1_facets<0><<<hemo_grid(fs.m, 128), 128, 0, ctx->stream>>>(fs.m, E, n, fs.cells, fs.mask, fs.coef, ctx->cells,
-                                                                      ctx->x, ctx->h, x_dev, un_dev, cellflag, ctx->dvec,
+                                                                      ctx->x, ctx->h, x_dev, un_dev, uh, cellflag, ctx->dvec,
                                                                       ctx->Fe);
     HEMO_LAUNCH_CHECK(ctx);
     return 0;

@@ -147,8 +147,9 @@ struct hemo_ctx {
     double* dvec = nullptr;         // 3n lifting vector (g - x on bc dofs)
 
     // forms
-    hemo_params par{};
+    HemoForm par{0, 0, 0, {0, 0}, 0, 0.5, 1.0};
     bool have_par = false;
+    const double* uh = nullptr;     // history vector of the time derivative (borrowed, 2n); null: u_n
     HemoRule rules[HEMO_NRULES];
     bool have_rule[HEMO_NRULES] = {false, false, false, false, false, false};
     bool rules_dirty = true;

@@ -4,6 +4,18 @@
 
 #define HEMO_MAXFQ 8          // max facet quadrature points
 
+// Constants of the weak form as the kernels see them: hemo_params (include/hemo.h) plus the time
+// scheme of hemo_set_time_scheme.  The forms are evaluated at u_e = theta u + (1 - theta) u_n with
+// the time derivative (a0 u - u_h) / dt; theta = 1/2, a0 = 1, u_h = u_n is the mid-point scheme of
+// src/solvers/stabilized_schur.py:69-80, theta = 1 with a0 u - u_h = a0 u + a1 u_n + a2 u_nn the
+// BDF scheme of src/solvers/stabilized_schur_bdf2.py:76-110.
+struct HemoForm {
+    double dt, rho, mu;
+    double f[2];
+    double eps0;
+    double theta, a0;
+};
+
 struct HemoFacetRule {
     int nq;
     double s[HEMO_MAXFQ];

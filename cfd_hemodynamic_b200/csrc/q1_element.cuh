@@ -35,6 +35,7 @@
 struct Q1Cell {
     double X[4][2];
     double U[4][2], N[4][2], P[4];
+    double H[4][2];     // history of the time derivative: dudt = (a0 U - H) / dt (mid-point scheme: H = N)
     double h;
 };
 
@@ -79,7 +80,7 @@ HEMO_HD void q1_geom(const Q1Cell& c, double xi, double eta, Q1Geom& o) {
 }
 
 // tau_supg and tau_lsic at a point (stabilized_schur.py:91-118)
-HEMO_HD void q1_tau(const hemo_params& par, double h, double unx, double uny, double& tau, double& taul) {
+HEMO_HD void q1_tau(const HemoForm& par, double h, double unx, double uny, double& tau, double& taul) {
     const double nu = par.mu / par.rho;
     const double inv_h2 = 1.0 / (h * h);
     const double t2inv = 2.0 / par.dt;
@@ -93,22 +94,24 @@ HEMO_HD void q1_tau(const hemo_params& par, double h, double unx, double uny, do
     taul = 0.5 * v * h * z;
 }
 
-HEMO_HD void q1_state(const Q1Cell& c, const hemo_params& par, const Q1Geom& ge, Q1State& s) {
-    double u[2] = {0, 0}, un[2] = {0, 0}, wv[2] = {0, 0}, gp[2] = {0, 0};
+HEMO_HD void q1_state(const Q1Cell& c, const HemoForm& par, const Q1Geom& ge, Q1State& s) {
+    double u[2] = {0, 0}, un[2] = {0, 0}, uh[2] = {0, 0}, wv[2] = {0, 0}, gp[2] = {0, 0};
+    const double th = par.theta;
     s.p = 0.0;
     s.G[0][0] = s.G[0][1] = s.G[1][0] = s.G[1][1] = 0.0;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-        const double m0 = 0.5 * (c.U[a][0] + c.N[a][0]), m1 = 0.5 * (c.U[a][1] + c.N[a][1]);
+        const double m0 = th * c.U[a][0] + (1.0 - th) * c.N[a][0], m1 = th * c.U[a][1] + (1.0 - th) * c.N[a][1];
         u[0] += ge.phi[a] * c.U[a][0]; u[1] += ge.phi[a] * c.U[a][1];
         un[0] += ge.phi[a] * c.N[a][0]; un[1] += ge.phi[a] * c.N[a][1];
+        uh[0] += ge.phi[a] * c.H[a][0]; uh[1] += ge.phi[a] * c.H[a][1];
         s.p += ge.phi[a] * c.P[a];
         s.G[0][0] += ge.g[a][0] * m0; s.G[0][1] += ge.g[a][0] * m1;
         s.G[1][0] += ge.g[a][1] * m0; s.G[1][1] += ge.g[a][1] * m1;
         gp[0] += ge.g[a][0] * c.P[a]; gp[1] += ge.g[a][1] * c.P[a];
         wv[0] += ge.theta[a] * m0; wv[1] += ge.theta[a] * m1;
     }
-    s.um[0] = 0.5 * (u[0] + un[0]); s.um[1] = 0.5 * (u[1] + un[1]);
+    s.um[0] = th * u[0] + (1.0 - th) * un[0]; s.um[1] = th * u[1] + (1.0 - th) * un[1];
     s.divu = s.G[0][0] + s.G[1][1];
     const double idt = 1.0 / par.dt;
 #pragma unroll
@@ -116,7 +119,7 @@ HEMO_HD void q1_state(const Q1Cell& c, const hemo_params& par, const Q1Geom& ge,
         const double conv = s.um[0] * s.G[0][k] + s.um[1] * s.G[1][k];
         // div(2 mu eps(u_m)) = mu (lap u_m + grad div u_m)
         const double visc = par.mu * (wv[k] * ge.trk + ge.k[k][0] * wv[0] + ge.k[k][1] * wv[1]);
-        s.acc[k] = (u[k] - un[k]) * idt + conv - par.f[k];
+        s.acc[k] = (par.a0 * u[k] - uh[k]) * idt + conv - par.f[k];
         s.R[k] = par.rho * s.acc[k] + gp[k] - visc;
     }
     q1_tau(par, c.h, un[0], un[1], s.tau, s.taul);
@@ -126,7 +129,7 @@ HEMO_HD void q1_state(const Q1Cell& c, const hemo_params& par, const Q1Geom& ge,
 
 // ---- residual ---------------------------------------------------------------------
 // One quadrature point of F_u (do_u) and / or F_p (do_p); w = weight * |det J|.
-HEMO_HD void q1_residual_point(const hemo_params& par, const Q1Geom& ge, const Q1State& s, double w,
+HEMO_HD void q1_residual_point(const HemoForm& par, const Q1Geom& ge, const Q1State& s, double w,
                                bool do_u, bool do_p, double Fu[4][2], double Fp[4]) {
     const double rho = par.rho, mu = par.mu;
     if (do_u) {
@@ -148,7 +151,7 @@ HEMO_HD void q1_residual_point(const hemo_params& par, const Q1Geom& ge, const Q
 }
 
 // Element residual with the rules of the F_u and F_p block forms (ids HEMO_Q_FU, HEMO_Q_FP).
-HEMO_HD void q1_cell_residual(const Q1Cell& c, const hemo_params& par, const HemoQuadRule* rules,
+HEMO_HD void q1_cell_residual(const Q1Cell& c, const HemoForm& par, const HemoQuadRule* rules,
                               double Fu[4][2], double Fp[4]) {
 #pragma unroll
     for (int a = 0; a < 4; ++a) { Fu[a][0] = Fu[a][1] = 0.0; Fp[a] = 0.0; }
@@ -177,13 +180,14 @@ HEMO_HD void q1_cell_residual(const Q1Cell& c, const hemo_params& par, const Hem
 
 // One quadrature point of J_uu for the test nodes A0, A0+1: uu[i][b][k*2+l].
 template <int A0>
-HEMO_HD void q1_uu_point(const hemo_params& par, const Q1Geom& ge, const Q1State& s, double w, double uu[2][4][4]) {
-    const double rho = par.rho, mu = par.mu, idt = 1.0 / par.dt;
+HEMO_HD void q1_uu_point(const HemoForm& par, const Q1Geom& ge, const Q1State& s, double w, double uu[2][4][4]) {
+    // th = d(u_e)/du and idt = d(dudt)/du carry the time scheme (1/2 and 1/dt for the mid-point rule)
+    const double rho = par.rho, mu = par.mu, idt = par.a0 / par.dt, th = par.theta;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-        const double cb = rho * (ge.phi[b] * idt + 0.5 * s.umg[b]);
-        const double hb = 0.5 * rho * ge.phi[b];
-        const double vb = 0.5 * mu * ge.theta[b];
+        const double cb = rho * (ge.phi[b] * idt + th * s.umg[b]);
+        const double hb = th * rho * ge.phi[b];
+        const double vb = th * mu * ge.theta[b];
         double C[2][2], dR[2][2];
 #pragma unroll
         for (int k = 0; k < 2; ++k)
@@ -202,9 +206,9 @@ HEMO_HD void q1_uu_point(const hemo_params& par, const Q1Geom& ge, const Q1State
 #pragma unroll
                 for (int l = 0; l < 2; ++l) {
                     const double dkl = (k == l) ? 1.0 : 0.0;
-                    const double v = ge.phi[a] * C[k][l] + 0.5 * mu * (gab * dkl + ge.g[a][l] * ge.g[b][k]) +
-                                     s.tau * (s.umg[a] * dR[k][l] + 0.5 * ge.phi[b] * ge.g[a][l] * s.R[k]) +
-                                     0.5 * s.taul * rho * ge.g[a][k] * ge.g[b][l];
+                    const double v = ge.phi[a] * C[k][l] + th * mu * (gab * dkl + ge.g[a][l] * ge.g[b][k]) +
+                                     s.tau * (s.umg[a] * dR[k][l] + th * ge.phi[b] * ge.g[a][l] * s.R[k]) +
+                                     th * s.taul * rho * ge.g[a][k] * ge.g[b][l];
                     uu[i][b][k * 2 + l] += w * v;
                 }
         }
@@ -212,17 +216,17 @@ HEMO_HD void q1_uu_point(const hemo_params& par, const Q1Geom& ge, const Q1State
 }
 
 // One quadrature point of J_up (up[a][b][k]) and / or J_pu (pu[a][b][l]).
-HEMO_HD void q1_uppu_point(const hemo_params& par, const Q1Geom& ge, const Q1State& s, double w, bool do_up,
+HEMO_HD void q1_uppu_point(const HemoForm& par, const Q1Geom& ge, const Q1State& s, double w, bool do_up,
                            bool do_pu, double up[4][4][2], double pu[4][4][2]) {
-    const double rho = par.rho, mu = par.mu, idt = 1.0 / par.dt;
+    const double rho = par.rho, mu = par.mu, idt = par.a0 / par.dt, th = par.theta;
     const double tr = s.tau / rho;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
         double dR[2][2];
         if (do_pu) {
-            const double cb = rho * (ge.phi[b] * idt + 0.5 * s.umg[b]);
-            const double hb = 0.5 * rho * ge.phi[b];
-            const double vb = 0.5 * mu * ge.theta[b];
+            const double cb = rho * (ge.phi[b] * idt + th * s.umg[b]);
+            const double hb = th * rho * ge.phi[b];
+            const double vb = th * mu * ge.theta[b];
 #pragma unroll
             for (int k = 0; k < 2; ++k)
 #pragma unroll
@@ -238,8 +242,8 @@ HEMO_HD void q1_uppu_point(const hemo_params& par, const Q1Geom& ge, const Q1Sta
                 up[a][b][1] += w * (-ge.phi[b] * ge.g[a][1] + s.tau * s.umg[a] * ge.g[b][1]);
             }
             if (do_pu) {
-                pu[a][b][0] += w * (0.5 * ge.phi[a] * ge.g[b][0] + tr * (dR[0][0] * ge.g[a][0] + dR[1][0] * ge.g[a][1]));
-                pu[a][b][1] += w * (0.5 * ge.phi[a] * ge.g[b][1] + tr * (dR[0][1] * ge.g[a][0] + dR[1][1] * ge.g[a][1]));
+                pu[a][b][0] += w * (th * ge.phi[a] * ge.g[b][0] + tr * (dR[0][0] * ge.g[a][0] + dR[1][0] * ge.g[a][1]));
+                pu[a][b][1] += w * (th * ge.phi[a] * ge.g[b][1] + tr * (dR[0][1] * ge.g[a][0] + dR[1][1] * ge.g[a][1]));
             }
         }
     }
@@ -257,7 +261,7 @@ HEMO_HD int q1_blocks_of_rule(const HemoQuadRule* rules, int r) {
 
 // Work items 0 / 1: J_uu rows of test nodes A0, A0+1 with the J_uu rule; emit(slot, value).
 template <int A0, typename Emit>
-HEMO_HD void q1_cell_jacobian_uu(const Q1Cell& c, const hemo_params& par, const HemoQuadRule* rules, Emit emit) {
+HEMO_HD void q1_cell_jacobian_uu(const Q1Cell& c, const HemoForm& par, const HemoQuadRule* rules, Emit emit) {
     double uu[2][4][4];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -285,7 +289,7 @@ HEMO_HD void q1_cell_jacobian_uu(const Q1Cell& c, const hemo_params& par, const 
 
 // Work item 2: J_up and J_pu (one pass when their rules coincide), then J_pp.
 template <typename Emit>
-HEMO_HD void q1_cell_jacobian_p(const Q1Cell& c, const hemo_params& par, const HemoQuadRule* rules, Emit emit) {
+HEMO_HD void q1_cell_jacobian_p(const Q1Cell& c, const HemoForm& par, const HemoQuadRule* rules, Emit emit) {
     {
         double up[4][4][2], pu[4][4][2];
 #pragma unroll
@@ -345,9 +349,9 @@ HEMO_HD void q1_cell_jacobian_p(const Q1Cell& c, const hemo_params& par, const H
 // F += A_e d with d = (g - x) on constrained dofs (3P apply_lifting with x0 = x, alpha = -1;
 // trigger src/solvers/stabilized_schur.py:172-174): the element Jacobian is contracted with
 // dl[b] = (dU_x, dU_y, dP) point by point, block by block (each block with its own rule).
-HEMO_HD void q1_cell_lift(const Q1Cell& c, const hemo_params& par, const HemoQuadRule* rules,
+HEMO_HD void q1_cell_lift(const Q1Cell& c, const HemoForm& par, const HemoQuadRule* rules,
                           const double dl[4][3], double Fu[4][2], double Fp[4]) {
-    const double rho = par.rho, mu = par.mu, idt = 1.0 / par.dt;
+    const double rho = par.rho, mu = par.mu, idt = par.a0 / par.dt, th = par.theta;
     for (int r = HEMO_Q_UU; r <= HEMO_Q_PP; ++r) {
         const int blocks = q1_blocks_of_rule(rules, r);
         if (blocks == 0) continue;
@@ -371,9 +375,9 @@ HEMO_HD void q1_cell_lift(const Q1Cell& c, const hemo_params& par, const HemoQua
             double dC[2], dRu[2];
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                dC[k] = rho * (du[k] * idt + 0.5 * (du[0] * s.G[0][k] + du[1] * s.G[1][k]) +
-                               0.5 * (s.um[0] * dgu[0][k] + s.um[1] * dgu[1][k]));
-                dRu[k] = dC[k] - 0.5 * mu * (dw[k] * ge.trk + ge.k[k][0] * dw[0] + ge.k[k][1] * dw[1]);
+                dC[k] = rho * (du[k] * idt + th * (du[0] * s.G[0][k] + du[1] * s.G[1][k]) +
+                               th * (s.um[0] * dgu[0][k] + s.um[1] * dgu[1][k]));
+                dRu[k] = dC[k] - th * mu * (dw[k] * ge.trk + ge.k[k][0] * dw[0] + ge.k[k][1] * dw[1]);
             }
             const double ddiv = dgu[0][0] + dgu[1][1];
 #pragma unroll
@@ -384,14 +388,14 @@ HEMO_HD void q1_cell_lift(const Q1Cell& c, const hemo_params& par, const HemoQua
                     double v = 0.0;
                     if (blocks & Q1_UU)
                         v += ge.phi[a] * dC[k] +
-                             0.5 * mu * (ge.g[a][0] * (dgu[0][k] + dgu[k][0]) + ge.g[a][1] * (dgu[1][k] + dgu[k][1])) +
-                             s.tau * (s.umg[a] * dRu[k] + 0.5 * dug * s.R[k]) + 0.5 * s.taul * rho * ge.g[a][k] * ddiv;
+                             th * mu * (ge.g[a][0] * (dgu[0][k] + dgu[k][0]) + ge.g[a][1] * (dgu[1][k] + dgu[k][1])) +
+                             s.tau * (s.umg[a] * dRu[k] + th * dug * s.R[k]) + th * s.taul * rho * ge.g[a][k] * ddiv;
                     if (blocks & Q1_UP) v += -dp * ge.g[a][k] + s.tau * s.umg[a] * dgp[k];
                     Fu[a][k] += w * v;
                 }
                 double vp = 0.0;
                 if (blocks & Q1_PU)
-                    vp += 0.5 * ge.phi[a] * ddiv + s.tau / rho * (dRu[0] * ge.g[a][0] + dRu[1] * ge.g[a][1]);
+                    vp += th * ge.phi[a] * ddiv + s.tau / rho * (dRu[0] * ge.g[a][0] + dRu[1] * ge.g[a][1]);
                 if (blocks & Q1_PP) vp += s.tau / rho * (ge.g[a][0] * dgp[0] + ge.g[a][1] * dgp[1]);
                 Fp[a] += w * vp;
             }
@@ -432,9 +436,9 @@ HEMO_HD void q1_facet_normal(const Q1Cell& c, int lf, double nr[2], double& len)
 //   residual(a, k, value)        : += into Fu[a][k]           (want_res)
 //   jac(a, b, ri, ci, value)     : += into d Fu[a][ri] / d (U_b,ci | P_b for ci = 2)   (want_jac)
 template <typename Res, typename Jac>
-HEMO_HD void q1_cell_facets(const Q1Cell& c, const hemo_params& par, const HemoFacetRule& fr,
+HEMO_HD void q1_cell_facets(const Q1Cell& c, const HemoForm& par, const HemoFacetRule& fr,
                             const hemo_facet_coef& co, int mask, bool want_res, bool want_jac, Res residual, Jac jac) {
-    const double mu = par.mu, rho = par.rho;
+    const double mu = par.mu, rho = par.rho, th = par.theta;
     const double pen = co.a_n * co.beta_n * mu / c.h;
     const double bf = co.a_b * co.beta_b * rho;
     for (int lf = 0; lf < 4; ++lf) {
@@ -451,7 +455,7 @@ HEMO_HD void q1_cell_facets(const Q1Cell& c, const hemo_params& par, const HemoF
             double um[2] = {0, 0}, un[2] = {0, 0}, p = 0.0, G[2][2] = {{0, 0}, {0, 0}};
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-                const double m0 = 0.5 * (c.U[a][0] + c.N[a][0]), m1 = 0.5 * (c.U[a][1] + c.N[a][1]);
+                const double m0 = th * c.U[a][0] + (1.0 - th) * c.N[a][0], m1 = th * c.U[a][1] + (1.0 - th) * c.N[a][1];
                 um[0] += ge.phi[a] * m0; um[1] += ge.phi[a] * m1;
                 un[0] += ge.phi[a] * c.N[a][0]; un[1] += ge.phi[a] * c.N[a][1];
                 p += ge.phi[a] * c.P[a];
@@ -501,12 +505,12 @@ HEMO_HD void q1_cell_facets(const Q1Cell& c, const hemo_params& par, const HemoF
 #pragma unroll
                             for (int l = 0; l < 2; ++l) {
                                 const double dkl = (k == l) ? 1.0 : 0.0;
-                                double vv = -0.5 * co.a_g * mu * ge.g[b][k] * nr[l] * ge.phi[a];
-                                vv -= 0.5 * co.a_s * mu * (ge.g[b][k] * nr[l] + dn[b] * dkl) * ge.phi[a];
-                                vv -= 0.5 * co.a_n * mu * (Png[b][k] * nr[l] + dn[b] * Pn[k][l]) * ge.phi[a];
-                                vv -= 0.5 * co.a_n * mu * (Png[a][l] * nr[k] + dn[a] * Pn[k][l]) * ge.phi[b];
-                                vv += 0.5 * pen * Pn[k][l] * pab;
-                                vv -= 0.5 * bf * unm * pab * dkl;
+                                double vv = -th * co.a_g * mu * ge.g[b][k] * nr[l] * ge.phi[a];
+                                vv -= th * co.a_s * mu * (ge.g[b][k] * nr[l] + dn[b] * dkl) * ge.phi[a];
+                                vv -= th * co.a_n * mu * (Png[b][k] * nr[l] + dn[b] * Pn[k][l]) * ge.phi[a];
+                                vv -= th * co.a_n * mu * (Png[a][l] * nr[k] + dn[a] * Pn[k][l]) * ge.phi[b];
+                                vv += th * pen * Pn[k][l] * pab;
+                                vv -= th * bf * unm * pab * dkl;
                                 jac(a, b, k, l, w * vv);
                             }
                             jac(a, b, k, 2, w * co.a_p * nr[k] * pab);

@@ -244,6 +244,7 @@ class StabilizedSchurB200(SolverBase):
         self.d_x[:2 * n].copy_(self._pin["u_prev"], non_blocking=True)
         self.d_x[2 * n:].copy_(self._pin["p_prev"], non_blocking=True)
         self.d_un.copy_(self._pin["u_prev"], non_blocking=True)
+        self._prepare_time_scheme()
 
         # snes.computeJacobian(x_n, A) + pc.setUp()   (:226-253)
         self.hemo.assemble_jacobian(self.d_x, self.d_un, self.d_vals)
@@ -357,9 +358,14 @@ class StabilizedSchurB200(SolverBase):
         """nullsp.remove(x_n) — unconditional in the reference (:319)."""
         self.hemo.remove_mean(self.d_x[2 * self.n:])
 
+    def _prepare_time_scheme(self):
+        """Hook of the variants with another time scheme (stabilized_schur_bdf2)."""
+        return None
+
     def _solve_on_device(self):
         self._remove_pressure_mean()
         self._update_facet_coefs()
+        self._prepare_time_scheme()
         self.its_snes, self.its_ksp, self.reason = self._newton()
         if self.verbose:
             print(f"Solver converged in {self.its_snes} nonlinear iterations"

@@ -128,6 +128,12 @@ int hemo_set_quadrature(hemo_ctx* ctx, int block, const double* pts_host,
 /* Facet rule on [0,1] shared by all exterior-facet integrals. */
 int hemo_set_facet_quadrature(hemo_ctx* ctx, const double* pts_host, const double* wts_host, int nq);
 int hemo_set_params(hemo_ctx* ctx, const hemo_params* p);
+/* Time scheme of the forms: they are evaluated at u_e = theta*u + (1-theta)*u_prev with the time
+ * derivative (a0*u - u_h)/dt.  Default theta = 1/2, a0 = 1, u_h = u_prev: the mid-point scheme of
+ * src/solvers/stabilized_schur.py:69-80.  theta = 1 with u_h = -(a1*u_prev + a2*u_prev2) is the
+ * BDF1/BDF2 scheme of src/solvers/stabilized_schur_bdf2.py:76-110, 300-310 (bdf_a0/a1/a2 Constants).
+ * uh_dev: 2n doubles, borrowed; NULL = u_prev.  tau_supg / tau_lsic always use u_prev (:101-103). */
+int hemo_set_time_scheme(hemo_ctx* ctx, double theta, double a0, const double* uh_dev);
 /* One tagged ds integral: unique boundary cells with a 3-bit (triangle) or 4-bit
  * (quadrilateral: facets (0,1),(0,2),(1,3),(2,3)) mask of the
  * local facets that carry the tag (Measure("ds", subdomain_id=...),

@@ -84,6 +84,14 @@ class Problem:
     # Dirichlet: list of (block 'u'|'p', unrolled dofs within block, g block vector)
     bcs: list = field(default_factory=list)
     eps0: float = EPS0
+    # Time scheme.  The forms are evaluated at u_e = theta u + (1 - theta) u_n with the time
+    # derivative (a0 u - u_h) / dt.  Default = the mid-point scheme of stabilized_schur.py:69-80
+    # (theta = 1/2, a0 = 1, u_h = u_n); stabilized_schur_bdf2.py:76-110 uses theta = 1 and
+    # a0 u + a1 u_n + a2 u_nn, i.e. u_h = -(a1 u_n + a2 u_nn) (nodal vector `uh`, 2n).
+    # tau_supg / tau_lsic always take u_n (u_prev).
+    theta: float = 0.5
+    a0: float = 1.0
+    uh: np.ndarray | None = None
 
     @property
     def n(self):
@@ -136,15 +144,17 @@ def _tau(prob, unq, h):
 # --------------------------------------------------------------------------
 # cell integrals
 # --------------------------------------------------------------------------
-def element_F(prob, U, P, Un, rule):
+def element_F(prob, U, P, Un, rule, Uh=None):
     """Element residual (Fu (E,3,2), Fp (E,3)) with the given cell rule.
     U, Un: (E,3,2) nodal values per cell (may be complex for the complex-step
-    check), P: (E,3)."""
+    check), P: (E,3); Uh: history values of the time derivative (default Un)."""
     det, dphi = cell_geometry(prob.x, prob.cells)
     pts, wts = rule
     rho, mu, dt = prob.rho, prob.mu, prob.dt
+    th, a0 = prob.theta, prob.a0
+    Uh = Un if Uh is None else Uh
     f = np.asarray(prob.f, dtype=np.float64)
-    Um = 0.5 * (U + Un)
+    Um = th * U + (1.0 - th) * Un
     G = np.einsum("eai,eaj->eij", dphi, Um)          # G_ij = d_i u_mj (nabla_grad)
     gradp = np.einsum("eai,ea->ei", dphi, P)
     divu = G[:, 0, 0] + G[:, 1, 1]
@@ -157,11 +167,11 @@ def element_F(prob, U, P, Un, rule):
         w = wts[q] * det                               # (E,)
         u = np.einsum("a,eai->ei", phi, U)
         un = np.einsum("a,eai->ei", phi, Un)
-        um = 0.5 * (u + un)
+        um = th * u + (1.0 - th) * un
         p = np.einsum("a,ea->e", phi, P)
         tau, tau_l = _tau(prob, un.real, prob.h)
         conv = np.einsum("ei,eij->ej", um, G)           # (u_m . nabla) u_m
-        dudt = (u - un) / dt
+        dudt = (a0 * u - np.einsum("a,eai->ei", phi, Uh)) / dt
         sigma = 2.0 * mu * eps - p[:, None, None] * np.eye(2)[None]
         R = rho * (dudt + conv) + gradp - rho * f[None, :]     # -div sigma = grad p (P1)
         um_dphi = np.einsum("ei,eai->ea", um, dphi)     # u_m . grad phi_a
@@ -179,15 +189,19 @@ def element_F(prob, U, P, Un, rule):
     return Fu, Fp
 
 
-def element_J(prob, U, P, Un, rule):
+def element_J(prob, U, P, Un, rule, Uh=None):
     """Element Jacobian blocks by hand-differentiated integrand:
-    Juu (E,3,2,3,2) [a,k ; b,l], Jup (E,3,2,3), Jpu (E,3,3,2), Jpp (E,3,3)."""
+    Juu (E,3,2,3,2) [a,k ; b,l], Jup (E,3,2,3), Jpu (E,3,3,2), Jpp (E,3,3).
+    With the general time scheme d(u_e)/du = theta and d(dudt)/du = a0/dt (theta = 1/2,
+    a0 = 1 reproduce the factors 1/2 and 1/dt of the mid-point scheme)."""
     det, dphi = cell_geometry(prob.x, prob.cells)
     pts, wts = rule
     rho, mu, dt = prob.rho, prob.mu, prob.dt
+    th, a0 = prob.theta, prob.a0
+    Uh = Un if Uh is None else Uh
     f = np.asarray(prob.f, dtype=np.float64)
     E = prob.cells.shape[0]
-    Um = 0.5 * (U + Un)
+    Um = th * U + (1.0 - th) * Un
     G = np.einsum("eai,eaj->eij", dphi, Um)
     gradp = np.einsum("eai,ea->ei", dphi, P)
     I2 = np.eye(2)
@@ -198,39 +212,39 @@ def element_J(prob, U, P, Un, rule):
     # viscous: eps(v):2mu eps(du/2) = mu eps(v):eps(du)
     #   eps(v):eps(du) for v=phi_a e_k, du=phi_b e_l = 1/2 (dphi_a.dphi_b d_kl + d_l phi_a d_k phi_b)
     dd = np.einsum("eai,ebi->eab", dphi, dphi)
-    visc = 0.5 * mu * (dd[:, :, None, :, None] * I2[None, None, :, None, :]
-                       + np.einsum("eal,ebk->eakbl", dphi, dphi))
+    visc = th * mu * (dd[:, :, None, :, None] * I2[None, None, :, None, :]
+                      + np.einsum("eal,ebk->eakbl", dphi, dphi))
     for q in range(len(wts)):
         xi, eta = pts[q]
         phi = np.array([1.0 - xi - eta, xi, eta])
         w = wts[q] * det
         u = np.einsum("a,eai->ei", phi, U)
         un = np.einsum("a,eai->ei", phi, Un)
-        um = 0.5 * (u + un)
+        um = th * u + (1.0 - th) * un
         tau, tau_l = _tau(prob, un, prob.h)
         conv = np.einsum("ei,eij->ej", um, G)
-        R = rho * ((u - un) / dt + conv) + gradp - rho * f[None, :]
+        R = rho * ((a0 * u - np.einsum("a,eai->ei", phi, Uh)) / dt + conv) + gradp - rho * f[None, :]
         um_dphi = np.einsum("ei,eai->ea", um, dphi)
-        # dR_k/d(u_b,l) = rho [ phi_b/dt d_kl + 1/2 phi_b G_lk + 1/2 (um.dphi_b) d_kl ]
-        dR = rho * ((phi[None, :] / dt + 0.5 * um_dphi)[:, None, :, None] * I2[None, :, None, :]
-                    + 0.5 * phi[None, None, :, None] * np.swapaxes(G, 1, 2)[:, :, None, :])   # (E,k,b,l)
+        # dR_k/d(u_b,l) = rho [ a0 phi_b/dt d_kl + theta phi_b G_lk + theta (um.dphi_b) d_kl ]
+        dR = rho * ((a0 * phi[None, :] / dt + th * um_dphi)[:, None, :, None] * I2[None, :, None, :]
+                    + th * phi[None, None, :, None] * np.swapaxes(G, 1, 2)[:, :, None, :])   # (E,k,b,l)
         # Galerkin: rho phi_a [phi_b/dt d_kl + 1/2 phi_b G_lk + 1/2 um.dphi_b d_kl] = phi_a dR
         Juu_q = np.einsum("a,ekbl->eakbl", phi, dR) + visc
-        # SUPG: tau [ dR_k (um.dphi_a) + 1/2 R_k phi_b d_l phi_a ]
+        # SUPG: tau [ dR_k (um.dphi_a) + theta R_k phi_b d_l phi_a ]
         Juu_q = Juu_q + tau[:, None, None, None, None] * (
             np.einsum("ea,ekbl->eakbl", um_dphi, dR)
-            + 0.5 * np.einsum("ek,b,eal->eakbl", R, phi, dphi))
-        # LSIC: 1/2 tau_l rho d_l phi_b d_k phi_a
-        Juu_q = Juu_q + (0.5 * tau_l * rho)[:, None, None, None, None] * np.einsum(
+            + th * np.einsum("ek,b,eal->eakbl", R, phi, dphi))
+        # LSIC: theta tau_l rho d_l phi_b d_k phi_a
+        Juu_q = Juu_q + (th * tau_l * rho)[:, None, None, None, None] * np.einsum(
             "eak,ebl->eakbl", dphi, dphi)
         Juu += w[:, None, None, None, None] * Juu_q
         # J_up: -phi_b d_k phi_a  + tau d_k phi_b (um.dphi_a)
         Jup += w[:, None, None, None] * (
             -np.einsum("b,eak->eakb", phi, dphi)
             + tau[:, None, None, None] * np.einsum("ea,ebk->eakb", um_dphi, dphi))
-        # J_pu: 1/2 phi_a d_l phi_b + (tau/rho) dR_k,bl d_k phi_a
+        # J_pu: theta phi_a d_l phi_b + (tau/rho) dR_k,bl d_k phi_a
         Jpu += w[:, None, None, None] * (
-            0.5 * np.einsum("a,ebl->eabl", phi, dphi)
+            th * np.einsum("a,ebl->eabl", phi, dphi)
             + (tau / rho)[:, None, None, None] * np.einsum("ekbl,eak->eabl", dR, dphi))
         # J_pp: (tau/rho) dphi_a.dphi_b
         Jpp += (w * tau / rho)[:, None, None] * dd
@@ -265,7 +279,7 @@ def facet_F(prob, fs: FacetSet, U, P, Un):
     sgn = np.sign(np.einsum("ei,ei->e", nrm, xa - xo))
     nrm = nrm * sgn[:, None]
     mu, rho = prob.mu, prob.rho
-    Um = 0.5 * (U + Un)
+    Um = prob.theta * U + (1.0 - prob.theta) * Un
     G = np.einsum("eai,eaj->eij", dphi, Um)             # d_i u_mj
     eps = 0.5 * (G + np.swapaxes(G, 1, 2))
     Gn = np.einsum("eij,ej->ei", G, nrm)                # (nabla_grad u) n
@@ -333,6 +347,11 @@ def _gather(prob, u, p, un):
     return u.reshape(-1, 2)[c], p[c], un.reshape(-1, 2)[c]
 
 
+def _gather_history(prob):
+    """Cell values of the history vector of the time derivative (None: u_n is used)."""
+    return None if prob.uh is None else np.asarray(prob.uh).reshape(-1, 2)[prob.cells]
+
+
 def _kernels(prob):
     """Element routines for the problem's cell type: this module for P1
     triangles, oracle/q1_oracle.py for Q1 quadrilaterals (4 nodes per cell)."""
@@ -371,8 +390,9 @@ def assemble_F_raw(prob, u, p, un):
     K = _kernels(prob)
     U, P, Un = _gather(prob, u, p, un)
     nv = prob.cells.shape[1]
-    Fu, _ = K.element_F(prob, U, P, Un, prob.rules["Fu"])
-    _, Fp = K.element_F(prob, U, P, Un, prob.rules["Fp"])
+    Uh = _gather_history(prob)
+    Fu, _ = K.element_F(prob, U, P, Un, prob.rules["Fu"], Uh)
+    _, Fp = K.element_F(prob, U, P, Un, prob.rules["Fp"], Uh)
     b = np.zeros(prob.ndof, dtype=Fu.dtype)
     l2g = local_to_global(prob)
     np.add.at(b, l2g[:, :2 * nv].reshape(-1), Fu.reshape(-1))
@@ -391,10 +411,11 @@ def element_matrices(prob, u, p, un):
     E, nv = prob.cells.shape
     nu = 2 * nv
     Ae = np.zeros((E, 3 * nv, 3 * nv))
-    Juu, _, _, _ = K.element_J(prob, U, P, Un, prob.rules["uu"])
-    _, Jup, _, _ = K.element_J(prob, U, P, Un, prob.rules["up"])
-    _, _, Jpu, _ = K.element_J(prob, U, P, Un, prob.rules["pu"])
-    _, _, _, Jpp = K.element_J(prob, U, P, Un, prob.rules["pp"])
+    Uh = _gather_history(prob)
+    Juu, _, _, _ = K.element_J(prob, U, P, Un, prob.rules["uu"], Uh)
+    _, Jup, _, _ = K.element_J(prob, U, P, Un, prob.rules["up"], Uh)
+    _, _, Jpu, _ = K.element_J(prob, U, P, Un, prob.rules["pu"], Uh)
+    _, _, _, Jpp = K.element_J(prob, U, P, Un, prob.rules["pp"], Uh)
     Ae[:, :nu, :nu] = Juu.reshape(E, nu, nu)
     Ae[:, :nu, nu:] = Jup.reshape(E, nu, nv)
     Ae[:, nu:, :nu] = Jpu.reshape(E, nv, nu)

@@ -74,21 +74,23 @@ def _tau(prob, unq, h):
     return O._tau(prob, unq, h)
 
 
-def _point_state(prob, X, U, P, Un, xi, eta):
+def _point_state(prob, X, U, P, Un, xi, eta, Uh=None):
     rho, mu, dt = prob.rho, prob.mu, prob.dt
+    th, a0 = prob.theta, prob.a0          # time scheme, see ns_oracle.Problem
+    Uh = Un if Uh is None else Uh
     f = np.asarray(prob.f, dtype=np.float64)
     phi, g, det, theta, kappa = point_geometry(X, xi, eta)
-    Um = 0.5 * (U + Un)
+    Um = th * U + (1.0 - th) * Un
     u = np.einsum("a,eai->ei", phi, U)
     un = np.einsum("a,eai->ei", phi, Un)
-    um = 0.5 * (u + un)
+    um = th * u + (1.0 - th) * un
     p = np.einsum("a,ea->e", phi, P)
     G = np.einsum("eai,eaj->eij", g, Um)                  # d_i u_mj
     gradp = np.einsum("eai,ea->ei", g, P)
     divu = G[:, 0, 0] + G[:, 1, 1]
     eps = 0.5 * (G + np.swapaxes(G, 1, 2))
     conv = np.einsum("ei,eij->ej", um, G)
-    dudt = (u - un) / dt
+    dudt = (a0 * u - np.einsum("a,eai->ei", phi, Uh)) / dt
     trk = kappa[:, 0, 0] + kappa[:, 1, 1]
     wv = np.einsum("ea,eak->ek", theta, Um)               # sum_b theta_b M_b
     # div(2 mu eps(u_m)) = mu (lap u + grad div u)
@@ -99,7 +101,7 @@ def _point_state(prob, X, U, P, Un, xi, eta):
                 gradp=gradp, divu=divu, eps=eps, conv=conv, dudt=dudt, R=R, tau=tau, tau_l=tau_l)
 
 
-def element_F(prob, U, P, Un, rule):
+def element_F(prob, U, P, Un, rule, Uh=None):
     """Element residual (Fu (E,4,2), Fp (E,4)) with the given rule (pts on [0,1]^2, wts sum 1)."""
     X = prob.x[prob.cells]
     pts, wts = rule
@@ -108,7 +110,7 @@ def element_F(prob, U, P, Un, rule):
     Fu = np.zeros(U.shape, dtype=U.dtype)
     Fp = np.zeros(P.shape, dtype=U.dtype)
     for q in range(len(wts)):
-        s = _point_state(prob, X, U, P, Un, pts[q, 0], pts[q, 1])
+        s = _point_state(prob, X, U, P, Un, pts[q, 0], pts[q, 1], Uh)
         w = wts[q] * np.abs(s["det"])
         phi, g = s["phi"], s["g"]
         sigma = 2.0 * mu * s["eps"] - s["p"][:, None, None] * np.eye(2)[None]
@@ -123,12 +125,13 @@ def element_F(prob, U, P, Un, rule):
     return Fu, Fp
 
 
-def element_J(prob, U, P, Un, rule):
+def element_J(prob, U, P, Un, rule, Uh=None):
     """Element Jacobian blocks: Juu (E,4,2,4,2) [a,k ; b,l], Jup (E,4,2,4),
     Jpu (E,4,4,2), Jpp (E,4,4)."""
     X = prob.x[prob.cells]
     pts, wts = rule
     rho, mu, dt = prob.rho, prob.mu, prob.dt
+    th, a0 = prob.theta, prob.a0
     E = prob.cells.shape[0]
     I2 = np.eye(2)
     Juu = np.zeros((E, 4, 2, 4, 2))
@@ -136,30 +139,30 @@ def element_J(prob, U, P, Un, rule):
     Jpu = np.zeros((E, 4, 4, 2))
     Jpp = np.zeros((E, 4, 4))
     for q in range(len(wts)):
-        s = _point_state(prob, X, U, P, Un, pts[q, 0], pts[q, 1])
+        s = _point_state(prob, X, U, P, Un, pts[q, 0], pts[q, 1], Uh)
         w = wts[q] * np.abs(s["det"])
         phi, g, G, tau, tau_l = s["phi"], s["g"], s["G"], s["tau"], s["tau_l"]
         um_g = np.einsum("ei,eai->ea", s["um"], g)
         dd = np.einsum("eai,ebi->eab", g, g)
-        # C[k,b,l] = rho [ (phi_b/dt + 1/2 um.g_b) d_kl + 1/2 phi_b G_lk ]
-        C = rho * ((phi[None, :] / dt + 0.5 * um_g)[:, None, :, None] * I2[None, :, None, :]
-                   + 0.5 * phi[None, None, :, None] * np.swapaxes(G, 1, 2)[:, :, None, :])
-        # dR = C - 1/2 mu theta_b (tr(kappa) d_kl + kappa_kl)
-        dR = C - 0.5 * mu * s["theta"][:, None, :, None] * (
+        # C[k,b,l] = rho [ (a0 phi_b/dt + th um.g_b) d_kl + th phi_b G_lk ]   (th = d u_e / d u)
+        C = rho * ((a0 * phi[None, :] / dt + th * um_g)[:, None, :, None] * I2[None, :, None, :]
+                   + th * phi[None, None, :, None] * np.swapaxes(G, 1, 2)[:, :, None, :])
+        # dR = C - th mu theta_b (tr(kappa) d_kl + kappa_kl)
+        dR = C - th * mu * s["theta"][:, None, :, None] * (
             s["trk"][:, None, None, None] * I2[None, :, None, :] + s["kappa"][:, :, None, :])
-        visc = 0.5 * mu * (dd[:, :, None, :, None] * I2[None, None, :, None, :]
-                           + np.einsum("eal,ebk->eakbl", g, g))
+        visc = th * mu * (dd[:, :, None, :, None] * I2[None, None, :, None, :]
+                          + np.einsum("eal,ebk->eakbl", g, g))
         Jq = np.einsum("a,ekbl->eakbl", phi, C) + visc
         Jq = Jq + tau[:, None, None, None, None] * (
             np.einsum("ea,ekbl->eakbl", um_g, dR)
-            + 0.5 * np.einsum("ek,b,eal->eakbl", s["R"], phi, g))
-        Jq = Jq + (0.5 * tau_l * rho)[:, None, None, None, None] * np.einsum("eak,ebl->eakbl", g, g)
+            + th * np.einsum("ek,b,eal->eakbl", s["R"], phi, g))
+        Jq = Jq + (th * tau_l * rho)[:, None, None, None, None] * np.einsum("eak,ebl->eakbl", g, g)
         Juu += w[:, None, None, None, None] * Jq
         Jup += w[:, None, None, None] * (
             -np.einsum("b,eak->eakb", phi, g)
             + tau[:, None, None, None] * np.einsum("ea,ebk->eakb", um_g, g))
         Jpu += w[:, None, None, None] * (
-            0.5 * np.einsum("a,ebl->eabl", phi, g)
+            th * np.einsum("a,ebl->eabl", phi, g)
             + (tau / rho)[:, None, None, None] * np.einsum("ekbl,eak->eabl", dR, g))
         Jpp += (w * tau / rho)[:, None, None] * dd
     return Juu, Jup, Jpu, Jpp
@@ -195,7 +198,7 @@ def facet_F(prob, fs, U, P, Un):
     m = X.shape[0]
     nrm, length, va, vb = facet_normals(X, lf)
     mu, rho = prob.mu, prob.rho
-    Um = 0.5 * (U + Un)
+    Um = prob.theta * U + (1.0 - prob.theta) * Un
     Fu = np.zeros(U.shape, dtype=U.dtype)
     pts, wts = prob.facet_rule
     Pn = np.eye(2)[None] - nrm[:, :, None] * nrm[:, None, :]

@@ -7,13 +7,17 @@
 
 #include "../../cfd_hemodynamic_b200/csrc/q1_element.cuh"
 
+static const double* g_uh = nullptr;   // history vector of the time derivative (null: u_n)
+
 static void load(Q1Cell& cd, int c, const int32_t* cells, const double* x, const double* h, const double* sol,
                  const double* un, int n, int v[4]) {
+    const double* uh = g_uh ? g_uh : un;
     for (int a = 0; a < 4; ++a) {
         v[a] = cells[4 * (int64_t)c + a];
         cd.X[a][0] = x[2 * v[a]]; cd.X[a][1] = x[2 * v[a] + 1];
         cd.U[a][0] = sol[2 * v[a]]; cd.U[a][1] = sol[2 * v[a] + 1];
         cd.N[a][0] = un[2 * v[a]]; cd.N[a][1] = un[2 * v[a] + 1];
+        cd.H[a][0] = uh[2 * v[a]]; cd.H[a][1] = uh[2 * v[a] + 1];
         cd.P[a] = sol[2 * (int64_t)n + v[a]];
     }
     cd.h = h[c];
@@ -21,7 +25,7 @@ static void load(Q1Cell& cd, int c, const int32_t* cells, const double* x, const
 
 static HemoQuadRule g_rules[6];
 static HemoFacetRule g_frule;
-static hemo_params g_par;
+static HemoForm g_par = {0, 0, 0, {0, 0}, 0, 0.5, 1.0};
 
 extern "C" {
 
@@ -39,7 +43,12 @@ void q1h_set_facet_rule(const double* s, const double* w, int nq) {
     for (int q = 0; q < nq; ++q) { g_frule.s[q] = s[q]; g_frule.w[q] = w[q]; }
 }
 
-void q1h_set_params(const hemo_params* p) { g_par = *p; }
+void q1h_set_params(const hemo_params* p) {
+    g_par.dt = p->dt; g_par.rho = p->rho; g_par.mu = p->mu;
+    g_par.f[0] = p->f[0]; g_par.f[1] = p->f[1]; g_par.eps0 = p->eps0;
+}
+
+void q1h_set_time_scheme(double theta, double a0, const double* uh) { g_par.theta = theta; g_par.a0 = a0; g_uh = uh; }
 
 int q1h_alias(int block) { return g_rules[block].alias; }
 

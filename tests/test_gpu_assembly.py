@@ -149,6 +149,47 @@ def test_outlet_flux(hemo, cell_type):
     assert abs(q - q_ref) <= 1e-13 * max(1.0, abs(q_ref))
 
 
+@pytest.mark.parametrize("cell_type", CELLS)
+def test_bdf_time_scheme_parity(hemo, cell_type):
+    """hemo_set_time_scheme(theta = 1, a0 = 3/2, u_h = 2 u_n - u_nn / 2): the kernels of the
+    stabilized_schur_bdf2 variant (reference stabilized_schur_bdf2.py:76-110) vs the oracle,
+    Jacobian and residual with facet terms, lifting and Dirichlet rows."""
+    from oracle import ns_oracle as O
+    mesh, prob, g = _case(hemo, 8, 7, "hemo", True, seed=6, cell_type=cell_type)
+    u, p, un = T.smooth_fields(prob.x, seed=8)
+    n = prob.n
+    unn = un + 0.05 * np.random.default_rng(1).standard_normal(2 * n)
+    prob.theta, prob.a0, prob.uh = 1.0, 1.5, 2.0 * un - 0.5 * unn
+    dev = hemo.device
+    x = np.concatenate([u, p])
+    xd = torch.tensor(x, device=dev)
+    und = torch.tensor(un, device=dev)
+    uhd = torch.tensor(prob.uh, device=dev)
+    vals = torch.zeros(hemo.nnz, dtype=torch.float64, device=dev)
+    b = torch.zeros(3 * n, dtype=torch.float64, device=dev)
+    try:
+        hemo.set_time_scheme(1.0, 1.5, uhd)
+        hemo.assemble_jacobian(xd, und, vals)
+        hemo.assemble_residual(xd, und, g, b)
+        torch.cuda.synchronize()
+    finally:
+        hemo.set_time_scheme(0.5, 1.0, None)
+    A_ref = O.assemble_J(prob, u, p, un)
+    ip, idx = O.sparsity_pattern(prob)
+    A_gpu = sp.csr_matrix((vals.cpu().numpy(), idx, ip), shape=A_ref.shape)
+    d = A_gpu - A_ref
+    assert np.sqrt(d.multiply(d).sum()) < REL_TOL * np.sqrt(A_ref.multiply(A_ref).sum())
+    b_ref = O.assemble_F(prob, x, un)
+    assert np.linalg.norm(b.cpu().numpy() - b_ref) < REL_TOL * np.linalg.norm(b_ref)
+    # back on the default scheme the mid-point operators are reproduced
+    prob.theta, prob.a0, prob.uh = 0.5, 1.0, None
+    hemo.assemble_jacobian(xd, und, vals)
+    A_ref = O.assemble_J(prob, u, p, un)
+    A_gpu = sp.csr_matrix((vals.cpu().numpy(), idx, ip), shape=A_ref.shape)
+    d = A_gpu - A_ref
+    assert np.sqrt(d.multiply(d).sum()) < REL_TOL * np.sqrt(A_ref.multiply(A_ref).sum())
+
+
 def test_q1_shared_rule_single_pass(hemo):
     """One rule for every block form: the quadrilateral kernels integrate all blocks in one pass
     (rule aliases) and must still match the oracle."""

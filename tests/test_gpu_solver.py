@@ -67,6 +67,51 @@ def test_lid_cavity_matches_oracle(cell_type):
     assert abs(u).max() <= 1.0 + 1e-12
 
 
+@pytest.mark.parametrize("cell_type", ["triangle", "quadrilateral"])
+def test_bdf2_lid_cavity_matches_oracle(cell_type):
+    """stabilized_schur_bdf2: BDF1 on the first step, BDF2 afterwards, u_prev2 kept by the solver
+    (reference stabilized_schur_bdf2.py:300-327)."""
+    from cfd_hemodynamic_b200.fem import mesh as M
+    from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation
+    from oracle import ns_oracle as O
+    nx, mu, dt, steps = 12, 0.01, 0.01, 4
+    tight = dict(TIGHT, ksp_rtol=1e-10)      # round-off floor of the singular system, see the mid-point test
+    sc = LidDriven2DSimulation("stabilized_schur_bdf2", dt, steps * dt, rho=1, mu=mu, nx=nx, cell_type=cell_type, **tight)
+    s = sc.solver
+    for k in range(steps):
+        s.solveStep()
+        assert (s.bdf_a0, s.bdf_a1, s.bdf_a2) == ((1.0, -1.0, 0.0) if k == 0 else (1.5, -2.0, 0.5))
+        assert np.array_equal(s.u_prev2.x.array, s.u_prev.x.array)
+        s.u_prev.x.array[:] = s.u_sol.x.array[:]
+        s.p_prev.x.array[:] = s.p_sol.x.array[:]
+    assert s.step_count == steps
+    # oracle march with the same coefficients
+    mesh = M.create_unit_square(None, nx, nx, cell_type=cell_type)
+    prob = T.make_problem(mesh, dt=dt, rho=1.0, mu=mu, f=(0.0, 0.0))
+    x = prob.x
+    n = prob.n
+    ext = M.exterior_facet_indices(mesh.topology)
+    prob.facet_sets = [O.FacetSet(pairs=mesh.topology.facet_cell_pairs(ext), a_p=1.0, a_g=1.0)]
+    walls = np.nonzero(np.isclose(x[:, 0], 0) | np.isclose(x[:, 0], 1) | np.isclose(x[:, 1], 0))[0]
+    lidf = M.locate_entities_boundary(mesh, 1, lambda X: np.isclose(X[1], 1.0) & (X[0] > 1e-10) & (X[0] < 1 - 1e-10))
+    lid = np.unique(mesh.topology.facet_vertices[lidf])
+    g1 = np.zeros(2 * n); g1[0::2] = 1.0
+    prob.bcs = T.oracle_bcs(prob, [("u", walls, np.zeros(2 * n)), ("u", lid, g1)])
+    prob.theta = 1.0
+    xk, un, unn = np.zeros(3 * n), np.zeros(2 * n), np.zeros(2 * n)
+    for k in range(steps):
+        a0, a1, a2 = (1.0, -1.0, 0.0) if k == 0 else (1.5, -2.0, 0.5)
+        prob.a0, prob.uh = a0, -(a1 * un + a2 * unn)
+        xk = O.remove_nullspace(prob, xk)
+        xk, its, reason = O.newton_solve(prob, xk, un, rtol=1e-12, stol=0.0)
+        assert reason > 0
+        unn, un = un, xk[:2 * n].copy()
+    u_ref, p_ref = xk[:2 * n], xk[2 * n:]
+    u, p = s.u_sol.x.array, s.p_sol.x.array
+    assert np.linalg.norm(u - u_ref) < 1e-8 * np.linalg.norm(u_ref)
+    assert np.linalg.norm((p - p.mean()) - (p_ref - p_ref.mean())) < 1e-8 * np.linalg.norm(p_ref - p_ref.mean())
+
+
 def test_scenario_time_loop(tmp_path):
     """Scenario.solve drives solveStep, shifts u_prev on the host and writes norms.txt."""
     from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation

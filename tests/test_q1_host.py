@@ -69,6 +69,10 @@ def _load(lib, prob):
     lib.q1h_set_facet_rule(_p(s), _p(w), len(w))
     par = _Params(prob.dt, prob.rho, prob.mu, (ctypes.c_double * 2)(*prob.f), prob.eps0)
     lib.q1h_set_params(ctypes.byref(par))
+    lib.q1h_set_time_scheme.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
+    uh = None if prob.uh is None else np.ascontiguousarray(prob.uh, dtype=np.float64)
+    prob._uh_keepalive = uh
+    lib.q1h_set_time_scheme(prob.theta, prob.a0, None if uh is None else _p(uh))
 
 
 def _gather_matrix(prob, Ae):
@@ -256,6 +260,55 @@ def test_q1_element_residual_host(lib, facet_mode, with_bc):
     else:
         b_ref = O.assemble_F_raw(prob, u, p, un)
     assert np.linalg.norm(b - b_ref) < REL_TOL * np.linalg.norm(b_ref)
+
+
+def test_q1_bdf_time_scheme_host(lib):
+    """theta = 1, a0 = 3/2, u_h = 2 u_n - u_nn / 2 (stabilized_schur_bdf2.py:76-110): element routines
+    vs oracle, Jacobian (cells + facets) and residual with lifting."""
+    mesh, prob = _problem(5, 6, seed=8)
+    n = prob.n
+    rng = np.random.default_rng(12)
+    prob.theta, prob.a0 = 1.0, 1.5
+    u, p, un = T.smooth_fields(prob.x, seed=6)
+    unn = un + 0.05 * rng.standard_normal(2 * n)
+    prob.uh = 2.0 * un - 0.5 * unn
+    _load(lib, prob)
+    fsets = _facet_sets(mesh, "hemo") + _facet_sets(mesh, "all")
+    prob.facet_sets = [O.FacetSet(pairs=mesh.topology.facet_cell_pairs(f), **c) for f, c in fsets]
+    E = prob.cells.shape[0]
+    cells = np.ascontiguousarray(prob.cells, dtype=np.int32)
+    x = np.ascontiguousarray(prob.x)
+    sol = np.concatenate([u, p])
+    walls = np.nonzero(np.isclose(x[:, 1], 0.0) | np.isclose(x[:, 1], 1.0))[0]
+    bcs = [("u", walls, rng.standard_normal(2 * n))]
+    prob.bcs = T.oracle_bcs(prob, bcs)
+    flag, mult, cellflag, g = D.dirichlet_arrays(n, prob.cells, bcs)
+    dvec = np.where(flag != 0, g - sol, 0.0)
+    Ae, Fe = np.zeros(144 * E), np.zeros(12 * E)
+    lib.q1h_cell_jacobian(E, n, _p(cells), _p(x), _p(prob.h), _p(sol), _p(un), _p(Ae))
+    lib.q1h_cell_residual(E, n, _p(cells), _p(x), _p(prob.h), _p(sol), _p(un), _p(cellflag), _p(dvec), _p(Fe))
+    for facets, coef in fsets:
+        fc, fm = D.facet_set_by_cell(mesh, facets)
+        co = _Coef(**{k: coef.get(k, 0.0) for k, _ in _Coef._fields_})
+        args = (len(fc), E, n, _p(fc), _p(fm), ctypes.byref(co), _p(cells), _p(x), _p(prob.h), _p(sol), _p(un))
+        lib.q1h_facets(1, *args, None, None, _p(Ae))
+        lib.q1h_facets(0, *args, _p(cellflag), _p(dvec), _p(Fe))
+    assert _rel(_gather_matrix(prob, Ae), O.assemble_J_raw(prob, u, p, un)) < REL_TOL
+    b = _gather_vector(prob, Fe)
+    b[flag != 0] = (sol - g)[flag != 0]
+    b_ref = O.assemble_F(prob, sol, un)
+    assert np.linalg.norm(b - b_ref) < REL_TOL * np.linalg.norm(b_ref)
+    # and the oracle's Jacobian is the derivative of its residual for this scheme
+    prob.bcs = []
+    prob.rules = {k: Q1.tensor_gauss(4) for k in prob.rules}
+    A = O.assemble_J_raw(prob, u, p, un).toarray()
+    J = np.zeros_like(A)
+    for j in range(3 * n):
+        xc = sol.astype(complex)
+        xc[j] += 1e-30j
+        J[:, j] = O.assemble_F_raw(prob, xc[:2 * n], xc[2 * n:], un).imag / 1e-30
+    assert np.abs(A - J).max() < 1e-13 * np.abs(A).max()
+    lib.q1h_set_time_scheme(0.5, 1.0, None)
 
 
 def test_q1_rule_aliases(lib):
