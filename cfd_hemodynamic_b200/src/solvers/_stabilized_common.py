@@ -62,6 +62,7 @@ class StabilizedSchurB200(SolverBase):
         self.snes_stol = float(kw.pop("snes_stol", 1e-8))
         self.snes_max_it = int(kw.pop("snes_max_it", 100))
         self.ksp_rtol = float(kw.pop("ksp_rtol", 1e-5))
+        self.ksp_atol = float(kw.pop("ksp_atol", 1e-50))      # PETSc: converged when |r| < max(rtol |b|, atol)
         self.ksp_max_it = int(kw.pop("ksp_max_it", 1000))
         self.ksp_restart = int(kw.pop("ksp_restart", 60))
         self.verbose = bool(kw.pop("verbose", False))
@@ -261,7 +262,7 @@ class StabilizedSchurB200(SolverBase):
         self.linear = BlockSchurSolver(
             self.hemo, self._nrowptr, self._ncol, u_nodes, p_nodes, p_open_nodes=p_open,
             dt=float(self.dt.value), rho=float(self.rho.value), mu=float(self.mu.value),
-            restart=self.ksp_restart, max_it=self.ksp_max_it, rtol=self.ksp_rtol,
+            restart=self.ksp_restart, max_it=self.ksp_max_it, rtol=self.ksp_rtol, atol=self.ksp_atol,
             project_pressure=self._nullspace, **self._pc_kw)
         self.linear.setup(self.d_vals, self.d_x, self.d_un)
 
