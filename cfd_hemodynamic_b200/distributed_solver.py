@@ -26,12 +26,18 @@ from .linear_solver import BlockSchurSolver
 from .parallel import HaloExchange, HaloExchangeAllGather, Partition
 
 BLOCK_DEGREE = {Q_FU: 12, Q_FP: 11, Q_UU: 12, Q_UP: 11, Q_PU: 11, Q_PP: 10}
+BLOCK_DEGREE_QUAD = {Q_FU: 22, Q_FP: 20, Q_UU: 22, Q_UP: 20, Q_PU: 20, Q_PP: 18}     # see _stabilized_common.py
 
 
 def _cell_diameter(x, cells):
+    """mesh.h: largest vertex-vertex distance (triangles: longest edge, quadrilaterals: longest diagonal/edge)."""
     X = x[cells]
-    e = [np.linalg.norm(X[:, i] - X[:, j], axis=1) for i, j in ((0, 1), (0, 2), (1, 2))]
-    return np.maximum(np.maximum(e[0], e[1]), e[2])
+    nv = cells.shape[1]
+    h = np.zeros(cells.shape[0])
+    for i in range(nv):
+        for j in range(i + 1, nv):
+            h = np.maximum(h, np.linalg.norm(X[:, i] - X[:, j], axis=1))
+    return h
 
 
 class DistributedStabilizedSchur:
@@ -68,9 +74,10 @@ class DistributedStabilizedSchur:
                       torch.from_numpy(np.ascontiguousarray(h)).to(dev))
         nrowptr, ncol = D.node_graph(part.cells, nl)
         hemo.set_node_graph(torch.from_numpy(nrowptr).to(dev), torch.from_numpy(ncol).to(dev))
-        for block, deg in BLOCK_DEGREE.items():
-            hemo.set_quadrature(block, *Q.triangle_rule(deg))
-        hemo.set_facet_quadrature(*Q.interval_gauss(2))
+        self._quad = quad = part.cells.shape[1] == 4          # Q1 quadrilaterals (tensor-ordered) vs P1 triangles
+        for block, deg in (BLOCK_DEGREE_QUAD if quad else BLOCK_DEGREE).items():
+            hemo.set_quadrature(block, *(Q.quadrilateral_rule(deg) if quad else Q.triangle_rule(deg)))
+        hemo.set_facet_quadrature(*Q.interval_gauss(Q.FACET_POINTS_QUAD if quad else 2))
         hemo.set_params(par["dt"], par["rho"], par["mu"], par["f"], float(np.finfo(np.float64).resolution))
         g2l = part.g2l
         cell_g2l = -np.ones(tables["cells"].shape[0], dtype=np.int64)
@@ -79,7 +86,7 @@ class DistributedStabilizedSchur:
         for sid, (pairs, coef) in tables["facet_sets"].items():
             lc = cell_g2l[pairs[:, 0]]
             keep = lc >= 0
-            if self.variant == "pressure_backflow" and sid == 2:
+            if self.variant in ("pressure_backflow", "velocity_vascular_backflow") and sid == 2:
                 # resistance outlet: every overlapping rank sees the outlet cells; the flux is summed over
                 # the cells whose first vertex this rank owns so that each facet counts once
                 first_owner = owner[tables["cells"][pairs[:, 0], 0]]
@@ -190,7 +197,7 @@ class DistributedStabilizedSchur:
             # open (traction) boundaries: Dirichlet rows in the pressure operator of the Schur
             # approximation, as in the single-GPU solver (_stabilized_common.setup)
             from .fem.mesh import Mesh, exterior_facet_indices
-            gm = Mesh(xg, cg)
+            gm = Mesh(xg, cg, cell_type="quadrilateral" if cg.shape[1] == 4 else None)
             ext = exterior_facet_indices(gm.topology)
             bnodes = np.unique(gm.topology.facet_vertices[ext])
             unodes = np.unique(np.concatenate([np.asarray(nodes, dtype=np.int64) for b, nodes, _ in tables["bcs"]
@@ -486,11 +493,17 @@ class DistributedStabilizedSchur:
             X = part.x[cells]
             lf = o["flux_lf"]
             ar = np.arange(cells.shape[0])
-            fv = np.array([[1, 2], [0, 2], [0, 1]])
+            if cells.shape[1] == 4:
+                from .fem.mesh import QUAD_FACETS
+                fv = np.array(QUAD_FACETS)
+                inside = X.mean(axis=1)
+            else:
+                fv = np.array([[1, 2], [0, 2], [0, 1]])
+                inside = X[ar, lf]
             va, vb = fv[lf, 0], fv[lf, 1]
             t = X[ar, vb] - X[ar, va]
             nrm = np.stack([t[:, 1], -t[:, 0]], axis=1)
-            nrm *= np.sign(np.einsum("ei,ei->e", nrm, X[ar, va] - X[ar, lf]))[:, None]
+            nrm *= np.sign(np.einsum("ei,ei->e", nrm, 0.5 * (X[ar, va] + X[ar, vb]) - inside))[:, None]
             nodes = np.unique(cells)
             un = np.zeros((self.n, 2))
             idx = torch.from_numpy(np.concatenate([2 * nodes, 2 * nodes + 1])).to(self.hemo.device)

@@ -5,12 +5,13 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, cell_type="triangle"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -18,7 +19,7 @@ def _worker(rank, world, port, out):
     from cfd_hemodynamic_b200.parallel import HaloExchange, HaloExchangeAllGather, Partition, slab_partition
     from oracle import ns_oracle as O
     from tests import common as T
-    mesh = T.perturbed_square(9, 6, seed=4)
+    mesh = T.perturbed_square(9, 6, seed=4, cell_type=cell_type)
     prob = T.make_problem(mesh)
     n = prob.n
     u, p, un = T.smooth_fields(prob.x)
@@ -54,14 +55,15 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_partition_halo_world2():
+@pytest.mark.parametrize("cell_type", ["triangle", "quadrilateral"])
+def test_partition_halo_world2(cell_type):
     sock = socket.socket()
     sock.bind(("127.0.0.1", 0))
     port = sock.getsockname()[1]
     sock.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, cell_type)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=180) for _ in range(2))

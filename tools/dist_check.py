@@ -18,13 +18,15 @@ from cfd_hemodynamic_b200.parallel import slab_partition
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 case = sys.argv[3] if len(sys.argv) > 3 else "lid"
+cell_type = sys.argv[4] if len(sys.argv) > 4 else "triangle"
 tight = dict(snes_rtol=1e-11, snes_stol=0.0, ksp_rtol=1e-9, ksp_restart=100) if nx <= 64 else {}
 def make(host_only, **kw):
     if case == "lid":
-        return LidDriven2DSimulation("stabilized_schur", 0.01, 1.0, rho=1, mu=0.01, nx=nx, host_only=host_only, **kw)
+        return LidDriven2DSimulation("stabilized_schur", 0.01, 1.0, rho=1, mu=0.01, nx=nx, cell_type=cell_type,
+                                     host_only=host_only, **kw)
     if case == "pressure":
         from cfd_hemodynamic_b200.src.scenarios.stenosis_pressure_structured import StenosisPressureStructuredSimulation
-        return StenosisPressureStructuredSimulation("stabilized_schur_pressure_backflow", 0.005, 1.0, grade="moderate", cell_type="triangle",
+        return StenosisPressureStructuredSimulation("stabilized_schur_pressure_backflow", 0.005, 1.0, grade="moderate", cell_type=cell_type,
                                                     p_inlet=2.0, R_resistance=50.0, res=3.14 / nx, L=20.0,
                                                     x_position_stenosis=8.0, schur_mode="laplace",
                                                     host_only=host_only, **kw)
