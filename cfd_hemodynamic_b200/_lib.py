@@ -72,6 +72,10 @@ SYMBOLS = {
     "hemo_assemble_residual": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "hemo_outlet_flux": (_I, [_VP, _I, _VP, C.POINTER(_D)]),
     "hemo_assemble_laplace_mass": (_I, [_VP, _VP, _VP]),
+    "hemo_wall_shear_stress": (_I, [_VP, _I, _VP, _VP]),
+    "hemo_boundary_force": (_I, [_VP, _I, _VP, C.POINTER(_D)]),
+    "hemo_early_stop_norms": (_I, [_VP, _L, _VP, _VP, C.POINTER(_D)]),
+    "hemo_l2_norm_sq": (_I, [_VP, _I, _VP, C.POINTER(_D)]),
     "hemo_spmv": (_I, [_VP, _VP, _VP, _VP]),
     "hemo_axpy": (_I, [_VP, _L, _D, _VP, _VP]),
     "hemo_dot": (_I, [_VP, _L, _VP, _VP, C.POINTER(_D)]),
@@ -279,6 +283,25 @@ class Hemo:
         self._check(self.lib.hemo_assemble_laplace_mass(self._ctx, _ptr(lap), _ptr(mass)),
                     "hemo_assemble_laplace_mass")
         return lap, mass
+
+    # ---- post-processing ---------------------------------------------------
+    def wall_shear_stress(self, set_id: int, x, out):
+        self._check(self.lib.hemo_wall_shear_stress(self._ctx, set_id, _ptr(x), _ptr(out)), "hemo_wall_shear_stress")
+
+    def boundary_force(self, set_id: int, x):
+        f = (C.c_double * 2)()
+        self._check(self.lib.hemo_boundary_force(self._ctx, set_id, _ptr(x), f), "hemo_boundary_force")
+        return f[0], f[1]
+
+    def early_stop_norms(self, u, un):
+        f = (C.c_double * 2)()
+        self._check(self.lib.hemo_early_stop_norms(self._ctx, u.numel(), _ptr(u), _ptr(un), f), "hemo_early_stop_norms")
+        return f[0], f[1]
+
+    def l2_norm_sq(self, f, bs: int) -> float:
+        out = C.c_double()
+        self._check(self.lib.hemo_l2_norm_sq(self._ctx, bs, _ptr(f), C.byref(out)), "hemo_l2_norm_sq")
+        return out.value
 
     # ---- linear algebra --------------------------------------------------
     def spmv(self, vals, x, y):

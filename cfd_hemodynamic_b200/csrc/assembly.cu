@@ -1128,6 +1128,13 @@ static int ensure_elem(hemo_ctx* ctx, size_t ae_count, size_t fe_count) {
     return 0;
 }
 
+// a set whose coefficients are all zero carries no form term (it only tags facets for the
+// post-processing kernels): the assembly loops skip it
+static bool facet_set_active(const HemoFacetSet& fs) {
+    const hemo_facet_coef& c = fs.coef;
+    return fs.m > 0 && (c.a_p != 0.0 || c.pconst != 0.0 || c.a_g != 0.0 || c.a_s != 0.0 || c.a_n != 0.0 || c.a_b != 0.0);
+}
+
 static int check_ready(hemo_ctx* ctx) {
     if (!ctx->cells || !ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / node graph not set");
     return ctx->nv == 3 ? upload_constants(ctx) : 0;   // the quadrilateral kernels upload their own tables
@@ -1151,7 +1158,7 @@ extern "C" int hemo_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const 
     HEMO_PROF_END(ctx, HEMO_PROF_CELL_JAC);
     for (int s = 0; s < HEMO_MAX_FACET_SETS; ++s) {
         const HemoFacetSet& fs = ctx->fsets[s];
-        if (fs.m == 0) continue;
+        if (!facet_set_active(fs)) continue;
         if (nv == 4) {
             if ((rc = hemo_q1_facets(ctx, 1, fs, x_dev, un_dev, nullptr))) return rc;
             continue;
@@ -1194,7 +1201,7 @@ extern "C" int hemo_assemble_residual(hemo_ctx* ctx, const double* x_dev, const 
     HEMO_PROF_END(ctx, HEMO_PROF_CELL_RES);
     for (int s = 0; s < HEMO_MAX_FACET_SETS; ++s) {
         const HemoFacetSet& fs = ctx->fsets[s];
-        if (fs.m == 0) continue;
+        if (!facet_set_active(fs)) continue;
         if (nv == 4) {
             if ((rc = hemo_q1_facets(ctx, 0, fs, x_dev, un_dev, cf))) return rc;
             continue;

@@ -44,6 +44,22 @@ def l2_norm_sq(mesh, u: Function) -> float:
     x = mesh.geometry.x[:, :2]
     cells = mesh.geometry.dofmap
     X = x[cells]
+    if cells.shape[1] == 4:
+        # Q1 quadrilaterals: 3 x 3 Gauss points (exact on affine cells)
+        bs = u.function_space.dofmap.index_map_bs
+        vals = u.x.array.reshape(-1, bs)[cells]                # (E, 4, bs)
+        gp = 0.5 + 0.5 * np.array([-np.sqrt(0.6), 0.0, np.sqrt(0.6)])
+        gw = np.array([5.0, 8.0, 5.0]) / 18.0
+        total = 0.0
+        for xi, wx in zip(gp, gw):
+            for eta, wy in zip(gp, gw):
+                phi = np.array([(1 - xi) * (1 - eta), xi * (1 - eta), (1 - xi) * eta, xi * eta])
+                dref = np.array([[-(1 - eta), -(1 - xi)], [(1 - eta), -xi], [-eta, (1 - xi)], [eta, xi]])
+                Jm = np.einsum("eai,aj->eij", X, dref)
+                det = np.abs(Jm[:, 0, 0] * Jm[:, 1, 1] - Jm[:, 0, 1] * Jm[:, 1, 0])
+                f = np.einsum("a,eak->ek", phi, vals)
+                total += float(np.sum(wx * wy * det * np.einsum("ek,ek->e", f, f)))
+        return total
     det = np.abs((X[:, 1, 0] - X[:, 0, 0]) * (X[:, 2, 1] - X[:, 0, 1])
                  - (X[:, 2, 0] - X[:, 0, 0]) * (X[:, 1, 1] - X[:, 0, 1]))
     bs = u.function_space.dofmap.index_map_bs
@@ -218,6 +234,43 @@ class Scenario(ABC):
             error_log.close()
         self.steps_done = i
         return output_folder
+
+    def solve_device(self, output_folder: str | None = None, afterStepCallback: Callable[[float], None] = None):
+        """The same time loop as `solve` with the state resident on the device: `step_device`,
+        wall shear stress, the early-stop test and the final L2 norms all run as kernels
+        (SURVEY.md §8(f) rank 2); the fields are copied to the host Functions once, at the end.
+        No per-step output files (that is what `solve` is for); `norms.txt` is written when
+        `output_folder` is given.  Returns (steps, norm_v, norm_p)."""
+        solver = self.solver
+        if solver.hemo is None:
+            raise RuntimeError("solve_device needs a device context (host_only solver)")
+        solver.initStressForm()
+        t = 0.0
+        i = 0
+        while t < self.T:
+            solver.step_device(shift=False)
+            i += 1
+            t += self.dt
+            solver.assemble_wss_device()
+            if afterStepCallback:
+                afterStepCallback(t)
+            if (i + 1) % 10 == 0:
+                u_diff_norm, u_sol_norm = solver.early_stop_norms_device()
+                rel_diff = (u_diff_norm / max(u_sol_norm, 1e-12)) / self.dt
+                if rel_diff < self.early_stop_tolerance:
+                    print(f"Early stopping at t={t:.3f}, because (||u_sol - u_prev||_inf / ||u_sol||_inf) / dt "
+                          f"= {rel_diff:.20e} < {self.early_stop_tolerance}")
+                    break
+            solver.shift_time_level_device()
+        norm_v, norm_p = solver.l2_norms_device()
+        solver.download_solution()
+        if output_folder is not None and self.mesh.comm.rank == 0:
+            os.makedirs(output_folder, exist_ok=True)
+            with open(os.path.join(output_folder, "norms.txt"), "w") as f:
+                f.write(f"L2 norm of velocity: {norm_v}\n")
+                f.write(f"L2 norm of pressure: {norm_p}\n")
+        self.steps_done = i
+        return i, norm_v, norm_p
 
     @staticmethod
     def compute_error(u: Function, u_aprox: Function, mesh) -> float:

@@ -103,6 +103,11 @@ class DFG1Benchmark(Scenario):
         FL = float(np.sum(-length * (self.mu * dut_dn * n[:, 0] + pbar * n[:, 1])))
         return 500 * FD, 500 * FL
 
+    def drag_lift_device(self):
+        """Same integrals evaluated by `hemo_boundary_force` from the device state (no D2H of the fields)."""
+        fd, fl = self.solver.boundary_force_device(self._ft.find(self.obstacle_marker))
+        return 500 * fd, 500 * fl
+
     def pressure_difference(self):
         """p(0.15, 0.2) - p(0.25, 0.2) (dfg_1.py:213-253) by P1 interpolation."""
         mesh = self.mesh

@@ -30,8 +30,10 @@ BLOCK_DEGREE = {Q_FU: 12, Q_FP: 11, Q_UU: 12, Q_UP: 11, Q_PU: 11, Q_PP: 10}
 # tau(14) R(4) (u_m.grad v)(4) = 22, PSPG/J_up/J_pu 20, J_pp 18 -> 12x12 / 11x11 / 10x10 Gauss points
 BLOCK_DEGREE_QUAD = {Q_FU: 22, Q_FP: 20, Q_UU: 22, Q_UP: 20, Q_PU: 20, Q_PP: 18}
 
-# facet-set slots in the library
+# facet-set slots in the library (SET_WSS: all exterior facets with zero coefficients, only tagged
+# for the device post-processing kernels)
 SET_ALL, SET_INLET, SET_OUTLET = 0, 1, 2
+SET_WSS, SET_FORCE = 7, 6
 
 SNES_DIVERGED_LINEAR_SOLVE = -3
 SNES_DIVERGED_MAX_IT = -5
@@ -154,8 +156,10 @@ class StabilizedSchurB200(SolverBase):
 
     def _register_facets(self, set_id: int, facets, **coef):
         """One tagged ds integral: remembered on the host (export_tables) and, when a
-        device context exists, uploaded grouped by cell."""
-        self._facet_tables[set_id] = (np.asarray(facets, dtype=np.int64), dict(coef))
+        device context exists, uploaded grouped by cell.  Sets without coefficients only tag
+        facets for the post-processing kernels and are not exported as form terms."""
+        if coef:
+            self._facet_tables[set_id] = (np.asarray(facets, dtype=np.int64), dict(coef))
         if self.hemo is not None:
             torch = self._torch
             dev = self.hemo.device
@@ -389,14 +393,61 @@ class StabilizedSchurB200(SolverBase):
         self._torch.cuda.current_stream(self.hemo.device).synchronize()
         self._after_step()
 
-    def step_device(self):
-        """Device-resident time step for benchmarking the kernels alone: same
-        work as solveStep() but u_prev <- u_sol happens on the device and
-        nothing crosses PCIe."""
-        n = self.n
+    def step_device(self, shift: bool = True):
+        """Device-resident time step: same work as solveStep() but nothing crosses PCIe;
+        with `shift` the time-level shift u_prev <- u_sol (scenario.py:306) happens on the
+        device right away, otherwise the caller does it (`shift_time_level_device`) after its
+        own post-processing of (u_sol, u_prev)."""
         self._solve_on_device()
         self._after_step(device=True)
-        self.d_un.copy_(self.d_x[:2 * n])
+        if shift:
+            self.shift_time_level_device()
+
+    def shift_time_level_device(self):
+        self.d_un.copy_(self.d_x[:2 * self.n])
+
+    # ---- per-step post-processing on the device (SURVEY §8(f) rank 2) -------------------
+    def initStressForm(self):
+        """Reference :144-174; additionally tags the exterior facets on the device so that
+        `assemble_wss_device` can run without host work."""
+        super().initStressForm()
+        if self.hemo is not None:
+            self._register_facets(SET_WSS, exterior_facet_indices(self.mesh.topology))
+            self.d_wss = self._torch.zeros(2 * self.n, dtype=self._torch.float64, device=self.hemo.device)
+
+    def assemble_wss_device(self):
+        """`assemble_wss()` (src/solverBase.py:184-195) on the device: d_wss <- shear stress of d_x."""
+        self.hemo.wall_shear_stress(SET_WSS, self.d_x, self.d_wss)
+        return self.d_wss
+
+    def early_stop_norms_device(self):
+        """(max|u_sol - u_prev|, max|u_sol|) of scenario.py:268-304 from the device state."""
+        return self.hemo.early_stop_norms(self.d_x[:2 * self.n], self.d_un)
+
+    def boundary_force_device(self, facets):
+        """Drag / lift integrals of dfg_1.py:189-202 over `facets` (before the factor 500)."""
+        key = np.asarray(facets, dtype=np.int64).tobytes()
+        if getattr(self, "_force_key", None) != key:
+            self._register_facets(SET_FORCE, facets)
+            self._force_key = key
+        return self.hemo.boundary_force(SET_FORCE, self.d_x)
+
+    def l2_norms_device(self):
+        """sqrt(int |u|^2), sqrt(int p^2) of the final state (scenario.py:315-324)."""
+        n = self.n
+        return (math.sqrt(self.hemo.l2_norm_sq(self.d_x[:2 * n], 2)), math.sqrt(self.hemo.l2_norm_sq(self.d_x[2 * n:], 1)))
+
+    def download_solution(self):
+        """Device state -> host Functions (u_sol, p_sol, residuals, u_prev) after a device-resident loop."""
+        n = self.n
+        self._pin["u_sol"].copy_(self.d_x[:2 * n], non_blocking=True)
+        self._pin["p_sol"].copy_(self.d_x[2 * n:], non_blocking=True)
+        self._pin["u_residual"].copy_(self.d_f[:2 * n], non_blocking=True)
+        self._pin["p_residual"].copy_(self.d_f[2 * n:], non_blocking=True)
+        self._pin["u_prev"].copy_(self.d_un, non_blocking=True)
+        if getattr(self, "d_wss", None) is not None and getattr(self, "shear_stress", None) is not None:
+            self.shear_stress.x.array[:] = self.d_wss.cpu().numpy()
+        self._torch.cuda.current_stream(self.hemo.device).synchronize()
 
     def _after_step(self, device=False):
         return None

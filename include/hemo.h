@@ -166,6 +166,22 @@ int hemo_outlet_flux(hemo_ctx* ctx, int set_id, const double* un_dev, double* q_
  * pressure mass (n doubles) for the Schur-complement approximation. */
 int hemo_assemble_laplace_mass(hemo_ctx* ctx, double* lap_vals_dev, double* mass_dev);
 
+/* ---- per-step post-processing on the device ------------------------
+ * What Scenario.solve computes on the host after every solveStep (src/scenario.py:258-304,
+ * 315-324) and the DFG force integrals (src/scenarios/dfg_1.py:183-211), for a device-resident
+ * time loop.  Facet sets come from hemo_set_facet_set (a set with all-zero coefficients only
+ * tags facets: the assembly skips it). */
+/* solver.assemble_wss() (src/solverBase.py:144-195): wss (2n, device) =
+ * sum over the set's facets of (1/|F|) int_F phi_i (T - (T.n) n) ds, T = -2 mu eps(u) n. */
+int hemo_wall_shear_stress(hemo_ctx* ctx, int set_id, const double* x_dev, double* wss_dev);
+/* force_host[0] = int mu d(u.t)/dn n_y - p n_x ds, force_host[1] = -int mu d(u.t)/dn n_x + p n_y ds
+ * over the set, n = -FacetNormal, t = (n_y, -n_x) (drag / lift forms, dfg_1.py:189-202). */
+int hemo_boundary_force(hemo_ctx* ctx, int set_id, const double* x_dev, double* force_host);
+/* norms_host = { max|u - u_prev|, max|u| } over n entries (early stop, scenario.py:268-304). */
+int hemo_early_stop_norms(hemo_ctx* ctx, int64_t n, const double* u_dev, const double* un_dev, double* norms_host);
+/* assemble_scalar(inner(f, f) * dx) for a nodal field with bs = 1 | 2 components (scenario.py:315-324). */
+int hemo_l2_norm_sq(hemo_ctx* ctx, int bs, const double* f_dev, double* out_host);
+
 /* ---- linear algebra ----------------------------------------------------------- */
 /* MatMult on the monolithic Jacobian (PETSc KSP inner loop, :226-229). */
 int hemo_spmv(hemo_ctx* ctx, const double* vals_dev, const double* x_dev, double* y_dev);

@@ -133,3 +133,54 @@ def test_divergence_raises():
     sc = LidDriven2DSimulation("stabilized_schur", 0.01, 0.01, rho=1, mu=0.01, nx=8, ksp_max_it=1, ksp_rtol=1e-14)
     with pytest.raises(RuntimeError, match="Did not converge"):
         sc.solver.solveStep()
+
+
+@pytest.mark.parametrize("cell_type", ["triangle", "quadrilateral"])
+def test_device_postprocessing_matches_host(cell_type, tmp_path):
+    """hemo_wall_shear_stress / hemo_early_stop_norms / hemo_l2_norm_sq vs the host versions that
+    Scenario.solve uses (src/scenario.py:258-324), and the device-resident loop vs the host loop."""
+    from cfd_hemodynamic_b200.src.scenario import l2_norm_sq
+    from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation
+    kw = dict(rho=1, mu=0.01, nx=14, cell_type=cell_type)
+    sc = LidDriven2DSimulation("stabilized_schur", 0.01, 0.03, **kw)
+    s = sc.solver
+    s.initStressForm()
+    for _ in range(2):
+        s.solveStep()
+        s.u_prev.x.array[:] = s.u_sol.x.array[:]
+        s.p_prev.x.array[:] = s.p_sol.x.array[:]
+    s.solveStep()                      # u_prev still holds the previous step: (u_sol, u_prev) differ
+    s.assemble_wss()
+    wss_host = s.shear_stress.x.array.copy()
+    wss_dev = s.assemble_wss_device().cpu().numpy()
+    assert np.abs(wss_host).max() > 0
+    assert np.linalg.norm(wss_dev - wss_host) <= 1e-12 * np.linalg.norm(wss_host)
+    d, a = s.early_stop_norms_device()
+    assert d == np.abs(s.u_sol.x.array - s.u_prev.x.array).max() and a == np.abs(s.u_sol.x.array).max()
+    nv, np_ = s.l2_norms_device()
+    assert abs(nv ** 2 - l2_norm_sq(sc.mesh, s.u_sol)) <= 1e-12 * nv ** 2
+    assert abs(np_ ** 2 - l2_norm_sq(sc.mesh, s.p_sol)) <= 1e-12 * np_ ** 2
+    # device-resident loop == host loop (same kernels, same order of operations)
+    a_ = LidDriven2DSimulation("stabilized_schur", 0.01, 0.05, **kw)
+    b_ = LidDriven2DSimulation("stabilized_schur", 0.01, 0.05, **kw)
+    a_.write_output = False
+    out = a_.solve(str(tmp_path / "host"))
+    steps, norm_v, norm_p = b_.solve_device(str(tmp_path / "dev"))
+    assert steps == a_.steps_done == 5
+    assert np.array_equal(a_.solver.u_sol.x.array, b_.solver.u_sol.x.array)
+    assert np.array_equal(a_.solver.p_sol.x.array, b_.solver.p_sol.x.array)
+    assert np.linalg.norm(a_.solver.shear_stress.x.array - b_.solver.shear_stress.x.array) <= \
+        1e-12 * np.linalg.norm(a_.solver.shear_stress.x.array)
+    host_norms = [float(l.split(":")[1]) for l in open(f"{out}/norms.txt").read().splitlines()]
+    assert abs(host_norms[0] - norm_v) <= 1e-12 * norm_v and abs(host_norms[1] - norm_p) <= 1e-12 * abs(norm_p)
+
+
+def test_dfg_drag_lift_on_device():
+    from cfd_hemodynamic_b200.src.scenarios.dfg_1 import DFG1Benchmark
+    sc = DFG1Benchmark("stabilized_schur", 0.01, 0.02, lc_min=0.05 / 2, lc_max=0.41 / 6)
+    for _ in range(2):
+        sc.solver.solveStep()
+        sc.solver.u_prev.x.array[:] = sc.solver.u_sol.x.array[:]
+    cd, cl = sc.drag_lift()
+    cd_d, cl_d = sc.drag_lift_device()
+    assert abs(cd - cd_d) <= 1e-11 * abs(cd) and abs(cl - cl_d) <= 1e-11 * max(abs(cl), abs(cd))
