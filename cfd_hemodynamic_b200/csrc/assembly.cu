@@ -887,6 +887,15 @@ extern "C" int hemo_set_cell_type(hemo_ctx* ctx, int cell_type) {
     ctx->n = ctx->E = 0;
     for (int r = 0; r < HEMO_NRULES; ++r) ctx->have_rule[r] = false;
     ctx->rules_dirty = ctx->qrules_dirty = true;
+    // facet sets (local facet numbering) and Dirichlet cell flags belong to the old mesh
+    for (int s = 0; s < HEMO_MAX_FACET_SETS; ++s) {
+        HemoFacetSet& fs = ctx->fsets[s];
+        cudaFree(fs.cells); cudaFree(fs.mask);
+        fs.cells = fs.mask = nullptr;
+        fs.m = 0;
+    }
+    ctx->have_bc = false;
+    ctx->amg[0].ready = ctx->amg[1].ready = false;
     return 0;
 }
 

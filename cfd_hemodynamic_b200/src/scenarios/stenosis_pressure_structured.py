@@ -100,11 +100,23 @@ class StenosisPressureStructuredSimulation(Scenario):
         values[0] = np.maximum(v_max_local * (1.0 - (r / R_local) ** 2), 0.0)
         return values
 
-    def ffr(self):
-        """p at (0, R_in) and (L, R_in) and their ratio (reference :344-390)."""
+    def _probe_nodes(self):
         o = self.mesh.mesh_options
         x = self.mesh.geometry.x[:, :2]
-        p = self.solver.p_sol.x.array
         i_in = int(np.argmin(np.hypot(x[:, 0] - 0.0, x[:, 1] - o["R_in"])))
         i_out = int(np.argmin(np.hypot(x[:, 0] - o["L"], x[:, 1] - o["R_in"])))
+        return i_in, i_out
+
+    def ffr(self):
+        """p at (0, R_in) and (L, R_in) and their ratio (reference :344-390)."""
+        p = self.solver.p_sol.x.array
+        i_in, i_out = self._probe_nodes()
         return p[i_in], p[i_out], (p[i_out] / p[i_in] if p[i_in] != 0 else float("nan"))
+
+    def ffr_device(self):
+        """The same two probes read from the device state (two scalars cross PCIe, not the field)."""
+        s = self.solver
+        i_in, i_out = self._probe_nodes()
+        idx = s._torch.tensor([2 * s.n + i_in, 2 * s.n + i_out], device=s.hemo.device)
+        p_in, p_out = (float(v) for v in s.d_x.index_select(0, idx).cpu())
+        return p_in, p_out, (p_out / p_in if p_in != 0 else float("nan"))

@@ -144,6 +144,7 @@ def test_pressure_backflow_variant_matches_oracle(double_setup, cell_type):
     assert state["pc"] > 0.0                                         # the resistance loop is exercised
     assert _rel(s.u_sol.x.array, xk[:2 * n]) < 1e-8
     assert _rel(s.p_sol.x.array, xk[2 * n:]) < 1e-8
+    assert sc.ffr_device() == sc.ffr()                               # FFR probes read from the device state
 
 
 @pytest.mark.parametrize("cell_type", ["triangle", "quadrilateral"])
