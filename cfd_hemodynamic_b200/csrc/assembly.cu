@@ -870,6 +870,7 @@ static int upload_constants(hemo_ctx* ctx) {
                                                  cudaMemcpyHostToDevice, ctx->stream));
     HEMO_CHECK_CUDA(ctx, cudaMemcpyToSymbolAsync(c_frule, &ctx->frule, sizeof(HemoFacetRule), 0,
                                                  cudaMemcpyHostToDevice, ctx->stream));
+    hemo_form_finalize(ctx->par);
     HEMO_CHECK_CUDA(ctx, cudaMemcpyToSymbolAsync(c_par, &ctx->par, sizeof(HemoForm), 0,
                                                  cudaMemcpyHostToDevice, ctx->stream));
     // constants are read by kernels on the same stream, in order

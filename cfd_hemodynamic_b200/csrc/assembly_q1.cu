@@ -40,6 +40,7 @@ __device__ __forceinline__ void q1_load(Q1Cell& cd, int c, const int32_t* __rest
         cd.P[a] = sol[2 * (int64_t)n + v[a]];
     }
     cd.h = h[c];
+    q1_prepare(cd, c_qpar);
 }
 
 template <int ITEM>
@@ -192,6 +193,7 @@ static int q1_upload_constants(hemo_ctx* ctx) {
                                                  cudaMemcpyHostToDevice, ctx->stream));
     HEMO_CHECK_CUDA(ctx, cudaMemcpyToSymbolAsync(c_qfrule, &ctx->frule, sizeof(HemoFacetRule), 0,
                                                  cudaMemcpyHostToDevice, ctx->stream));
+    hemo_form_finalize(ctx->par);
     HEMO_CHECK_CUDA(ctx, cudaMemcpyToSymbolAsync(c_qpar, &ctx->par, sizeof(HemoForm), 0,
                                                  cudaMemcpyHostToDevice, ctx->stream));
     // the host copies above are read when the (pageable-memory) copy is staged, i.e. before return

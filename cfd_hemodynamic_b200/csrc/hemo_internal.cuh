@@ -147,7 +147,7 @@ struct hemo_ctx {
     double* dvec = nullptr;         // 3n lifting vector (g - x on bc dofs)
 
     // forms
-    HemoForm par{0, 0, 0, {0, 0}, 0, 0.5, 1.0};
+    HemoForm par{0, 0, 0, {0, 0}, 0, 0.5, 1.0, 0, 0, 0, 0};
     bool have_par = false;
     const double* uh = nullptr;     // history vector of the time derivative (borrowed, 2n); null: u_n
     HemoRule rules[HEMO_NRULES];

@@ -14,7 +14,16 @@ struct HemoForm {
     double f[2];
     double eps0;
     double theta, a0;
+    // derived on the host before every upload (hemo_form_finalize): divisions the point loops would repeat
+    double inv_dt, a0_dt, inv_rho, nu;
 };
+
+static inline void hemo_form_finalize(HemoForm& f) {
+    f.inv_dt = 1.0 / f.dt;
+    f.a0_dt = f.a0 / f.dt;
+    f.inv_rho = 1.0 / f.rho;
+    f.nu = f.mu / f.rho;
+}
 
 struct HemoFacetRule {
     int nq;

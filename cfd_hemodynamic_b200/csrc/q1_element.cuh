@@ -37,6 +37,8 @@ struct Q1Cell {
     double U[4][2], N[4][2], P[4];
     double H[4][2];     // history of the time derivative: dudt = (a0 U - H) / dt (mid-point scheme: H = N)
     double h;
+    // per-cell constants of tau_supg / tau_lsic (q1_prepare): hoisted out of the quadrature loops
+    double inv_h2, c23, re_fac, half_h;
 };
 
 struct Q1Geom {
@@ -79,19 +81,30 @@ HEMO_HD void q1_geom(const Q1Cell& c, double xi, double eta, Q1Geom& o) {
     o.adet = fabs(det);
 }
 
+// Per-cell constants of the stabilization parameters; call once after the cell data is loaded.
+HEMO_HD void q1_prepare(Q1Cell& c, const HemoForm& par) {
+    const double h = c.h;
+    c.inv_h2 = 1.0 / (h * h);
+    const double t2inv = 2.0 * par.inv_dt;            // 1 / tau_supg2
+    const double t3inv = 4.0 * par.nu * c.inv_h2;     // 1 / tau_supg3
+    c.c23 = t2inv * t2inv + t3inv * t3inv;
+    c.re_fac = h / (2.0 * par.nu);                    // Re = |u_n| h / (2 nu)
+    c.half_h = 0.5 * h;
+}
+
 // tau_supg and tau_lsic at a point (stabilized_schur.py:91-118)
-HEMO_HD void q1_tau(const HemoForm& par, double h, double unx, double uny, double& tau, double& taul) {
-    const double nu = par.mu / par.rho;
-    const double inv_h2 = 1.0 / (h * h);
-    const double t2inv = 2.0 / par.dt;
-    const double t3inv = 4.0 * nu * inv_h2;
+HEMO_HD void q1_tau(const HemoForm& par, const Q1Cell& c, double unx, double uny, double& tau, double& taul) {
     const double v2 = unx * unx + uny * uny;
-    const double t1 = fmax(4.0 * v2, par.eps0 * par.eps0) * inv_h2;   // (max(2|u_n|, eps)/h)^2
-    tau = 1.0 / sqrt(t1 + t2inv * t2inv + t3inv * t3inv);
+    const double t1 = fmax(4.0 * v2, par.eps0 * par.eps0) * c.inv_h2;   // (max(2|u_n|, eps)/h)^2
+#ifdef __CUDA_ARCH__
+    tau = rsqrt(t1 + c.c23);
+#else
+    tau = 1.0 / sqrt(t1 + c.c23);
+#endif
     const double v = sqrt(v2);
-    const double Re = v * h / (2.0 * nu);
-    const double z = (Re <= 3.0) ? Re / 3.0 : 1.0;
-    taul = 0.5 * v * h * z;
+    const double Re = v * c.re_fac;
+    const double z = (Re <= 3.0) ? Re * (1.0 / 3.0) : 1.0;
+    taul = c.half_h * v * z;
 }
 
 HEMO_HD void q1_state(const Q1Cell& c, const HemoForm& par, const Q1Geom& ge, Q1State& s) {
@@ -113,7 +126,7 @@ HEMO_HD void q1_state(const Q1Cell& c, const HemoForm& par, const Q1Geom& ge, Q1
     }
     s.um[0] = th * u[0] + (1.0 - th) * un[0]; s.um[1] = th * u[1] + (1.0 - th) * un[1];
     s.divu = s.G[0][0] + s.G[1][1];
-    const double idt = 1.0 / par.dt;
+    const double idt = par.inv_dt;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const double conv = s.um[0] * s.G[0][k] + s.um[1] * s.G[1][k];
@@ -122,7 +135,7 @@ HEMO_HD void q1_state(const Q1Cell& c, const HemoForm& par, const Q1Geom& ge, Q1
         s.acc[k] = (par.a0 * u[k] - uh[k]) * idt + conv - par.f[k];
         s.R[k] = par.rho * s.acc[k] + gp[k] - visc;
     }
-    q1_tau(par, c.h, un[0], un[1], s.tau, s.taul);
+    q1_tau(par, c, un[0], un[1], s.tau, s.taul);
 #pragma unroll
     for (int a = 0; a < 4; ++a) s.umg[a] = s.um[0] * ge.g[a][0] + s.um[1] * ge.g[a][1];
 }
@@ -146,7 +159,7 @@ HEMO_HD void q1_residual_point(const HemoForm& par, const Q1Geom& ge, const Q1St
     if (do_p) {
 #pragma unroll
         for (int a = 0; a < 4; ++a)
-            Fp[a] += w * (ge.phi[a] * s.divu + s.tau / rho * (s.R[0] * ge.g[a][0] + s.R[1] * ge.g[a][1]));
+            Fp[a] += w * (ge.phi[a] * s.divu + s.tau * par.inv_rho * (s.R[0] * ge.g[a][0] + s.R[1] * ge.g[a][1]));
     }
 }
 
@@ -179,37 +192,59 @@ HEMO_HD void q1_cell_residual(const Q1Cell& c, const HemoForm& par, const HemoQu
 // Slots follow the element buffer layout: (a*4+b)*9 + ri*3 + ci with ri/ci in (u_x, u_y, p).
 
 // One quadrature point of J_uu for the test nodes A0, A0+1: uu[i][b][k*2+l].
+// With C_b[k][l] = cb d_kl + hb G[l][k] and V_b[k][l] = vb (tr(kappa) d_kl + kappa[k][l])
+// (dR = C - V) the integrand
+//   phi_a C + th mu (g_a.g_b d_kl + g_a[l] g_b[k]) + tau (s_a (C - V) + th phi_b g_a[l] R[k]) + th tau_l rho g_a[k] g_b[l]
+// is regrouped into per-test-node factors times per-trial-node factors, 5 fused multiply-adds per entry:
+//   (phi_a + tau s_a) C - tau s_a V + (th mu g_a[l]) g_b[k] + (th tau g_a[l] R[k]) phi_b + (th tau_l rho g_a[k]) g_b[l]
+//   + th mu g_a.g_b d_kl
 template <int A0>
 HEMO_HD void q1_uu_point(const HemoForm& par, const Q1Geom& ge, const Q1State& s, double w, double uu[2][4][4]) {
     // th = d(u_e)/du and idt = d(dudt)/du carry the time scheme (1/2 and 1/dt for the mid-point rule)
-    const double rho = par.rho, mu = par.mu, idt = par.a0 / par.dt, th = par.theta;
+    const double rho = par.rho, mu = par.mu, idt = par.a0_dt, th = par.theta;
+    double a1[2], a2[2], a3[2][2], a4[2][2][2], a5[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int a = A0 + i;
+        a2[i] = w * s.tau * s.umg[a];
+        a1[i] = w * ge.phi[a] + a2[i];
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+            a3[i][l] = w * th * mu * ge.g[a][l];
+            a5[i][l] = w * th * s.taul * rho * ge.g[a][l];
+            const double t = w * th * s.tau * ge.g[a][l];
+            a4[i][l][0] = t * s.R[0];
+            a4[i][l][1] = t * s.R[1];
+        }
+    }
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
         const double cb = rho * (ge.phi[b] * idt + th * s.umg[b]);
         const double hb = th * rho * ge.phi[b];
         const double vb = th * mu * ge.theta[b];
-        double C[2][2], dR[2][2];
+        double C[2][2], V[2][2];
 #pragma unroll
         for (int k = 0; k < 2; ++k)
 #pragma unroll
             for (int l = 0; l < 2; ++l) {
                 const double dkl = (k == l) ? 1.0 : 0.0;
                 C[k][l] = cb * dkl + hb * s.G[l][k];
-                dR[k][l] = C[k][l] - vb * (ge.trk * dkl + ge.k[k][l]);
+                V[k][l] = vb * (ge.trk * dkl + ge.k[k][l]);
             }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const int a = A0 + i;
-            const double gab = ge.g[a][0] * ge.g[b][0] + ge.g[a][1] * ge.g[b][1];
+            // th mu g_a.g_b on the diagonal (k == l)
+            const double dg = a3[i][0] * ge.g[b][0] + a3[i][1] * ge.g[b][1];
 #pragma unroll
             for (int k = 0; k < 2; ++k)
 #pragma unroll
                 for (int l = 0; l < 2; ++l) {
-                    const double dkl = (k == l) ? 1.0 : 0.0;
-                    const double v = ge.phi[a] * C[k][l] + th * mu * (gab * dkl + ge.g[a][l] * ge.g[b][k]) +
-                                     s.tau * (s.umg[a] * dR[k][l] + th * ge.phi[b] * ge.g[a][l] * s.R[k]) +
-                                     th * s.taul * rho * ge.g[a][k] * ge.g[b][l];
-                    uu[i][b][k * 2 + l] += w * v;
+                    double v = a1[i] * C[k][l] - a2[i] * V[k][l];
+                    v += a3[i][l] * ge.g[b][k];
+                    v += a4[i][l][k] * ge.phi[b];
+                    v += a5[i][k] * ge.g[b][l];
+                    if (k == l) v += dg;
+                    uu[i][b][k * 2 + l] += v;
                 }
         }
     }
@@ -218,8 +253,8 @@ HEMO_HD void q1_uu_point(const HemoForm& par, const Q1Geom& ge, const Q1State& s
 // One quadrature point of J_up (up[a][b][k]) and / or J_pu (pu[a][b][l]).
 HEMO_HD void q1_uppu_point(const HemoForm& par, const Q1Geom& ge, const Q1State& s, double w, bool do_up,
                            bool do_pu, double up[4][4][2], double pu[4][4][2]) {
-    const double rho = par.rho, mu = par.mu, idt = par.a0 / par.dt, th = par.theta;
-    const double tr = s.tau / rho;
+    const double rho = par.rho, mu = par.mu, idt = par.a0_dt, th = par.theta;
+    const double tr = s.tau * par.inv_rho;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
         double dR[2][2];
@@ -332,8 +367,8 @@ HEMO_HD void q1_cell_jacobian_p(const Q1Cell& c, const HemoForm& par, const Hemo
 #pragma unroll
         for (int a = 0; a < 4; ++a) { un0 += ge.phi[a] * c.N[a][0]; un1 += ge.phi[a] * c.N[a][1]; }
         double tau, taul;
-        q1_tau(par, c.h, un0, un1, tau, taul);
-        const double wt = ru.pt[q][2] * ge.adet * tau / par.rho;
+        q1_tau(par, c, un0, un1, tau, taul);
+        const double wt = ru.pt[q][2] * ge.adet * tau * par.inv_rho;
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -351,7 +386,7 @@ HEMO_HD void q1_cell_jacobian_p(const Q1Cell& c, const HemoForm& par, const Hemo
 // dl[b] = (dU_x, dU_y, dP) point by point, block by block (each block with its own rule).
 HEMO_HD void q1_cell_lift(const Q1Cell& c, const HemoForm& par, const HemoQuadRule* rules,
                           const double dl[4][3], double Fu[4][2], double Fp[4]) {
-    const double rho = par.rho, mu = par.mu, idt = par.a0 / par.dt, th = par.theta;
+    const double rho = par.rho, mu = par.mu, idt = par.a0_dt, th = par.theta;
     for (int r = HEMO_Q_UU; r <= HEMO_Q_PP; ++r) {
         const int blocks = q1_blocks_of_rule(rules, r);
         if (blocks == 0) continue;
@@ -395,8 +430,8 @@ HEMO_HD void q1_cell_lift(const Q1Cell& c, const HemoForm& par, const HemoQuadRu
                 }
                 double vp = 0.0;
                 if (blocks & Q1_PU)
-                    vp += th * ge.phi[a] * ddiv + s.tau / rho * (dRu[0] * ge.g[a][0] + dRu[1] * ge.g[a][1]);
-                if (blocks & Q1_PP) vp += s.tau / rho * (ge.g[a][0] * dgp[0] + ge.g[a][1] * dgp[1]);
+                    vp += th * ge.phi[a] * ddiv + s.tau * par.inv_rho * (dRu[0] * ge.g[a][0] + dRu[1] * ge.g[a][1]);
+                if (blocks & Q1_PP) vp += s.tau * par.inv_rho * (ge.g[a][0] * dgp[0] + ge.g[a][1] * dgp[1]);
                 Fp[a] += w * vp;
             }
         }

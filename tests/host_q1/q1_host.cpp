@@ -7,6 +7,7 @@
 
 #include "../../cfd_hemodynamic_b200/csrc/q1_element.cuh"
 
+static HemoForm g_par = {0, 0, 0, {0, 0}, 0, 0.5, 1.0, 0, 0, 0, 0};
 static const double* g_uh = nullptr;   // history vector of the time derivative (null: u_n)
 
 static void load(Q1Cell& cd, int c, const int32_t* cells, const double* x, const double* h, const double* sol,
@@ -21,11 +22,12 @@ static void load(Q1Cell& cd, int c, const int32_t* cells, const double* x, const
         cd.P[a] = sol[2 * (int64_t)n + v[a]];
     }
     cd.h = h[c];
+    hemo_form_finalize(g_par);
+    q1_prepare(cd, g_par);
 }
 
 static HemoQuadRule g_rules[6];
 static HemoFacetRule g_frule;
-static HemoForm g_par = {0, 0, 0, {0, 0}, 0, 0.5, 1.0};
 
 extern "C" {
 
