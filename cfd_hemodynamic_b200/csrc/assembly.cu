@@ -306,8 +306,16 @@ k_cell_jacobian(int E, int n, const int32_t* __restrict__ cells, const double* _
 // x0 = x, alpha = -1; reference src/solvers/stabilized_schur.py:172-174).  Kept out of line:
 // only boundary-adjacent cells take this path and it would otherwise set the register
 // count of the whole residual kernel.
-__device__ __noinline__ void lift_cell(const CellData& cd, const CellDerived& d, const int v[3], int n,
-                                       const double* __restrict__ dvec, double Fu[3][2], double Fp[3]) {
+// Self-contained (reloads the cell, adds into Fe after the residual has been stored) so that no
+// array of k_cell_residual has its address taken: its hot path stays in registers.
+__device__ __noinline__ void lift_cell(int c, int E, int n, const int32_t* __restrict__ cells,
+                                       const double* __restrict__ x, const double* __restrict__ h,
+                                       const double* __restrict__ sol, const double* __restrict__ un,
+                                       const double* __restrict__ uh, const double* __restrict__ dvec,
+                                       double* __restrict__ Fe) {
+    CellData cd;
+    int v[3];
+    load_cell(cd, c, E, cells, x, h, sol, un, uh, n, v);
     double dl[3][3];
     bool any = false;
 #pragma unroll
@@ -318,6 +326,8 @@ __device__ __noinline__ void lift_cell(const CellData& cd, const CellDerived& d,
         any = any || dl[b][0] != 0.0 || dl[b][1] != 0.0 || dl[b][2] != 0.0;
     }
     if (!any) return;
+    CellDerived d;
+    derive_cell(cd, d);
     double lift[3][3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) lift[a][0] = lift[a][1] = lift[a][2] = 0.0;
@@ -326,11 +336,12 @@ __device__ __noinline__ void lift_cell(const CellData& cd, const CellDerived& d,
         const int a = ab / 3, b = ab % 3, ri = rc / 3, ci = rc % 3;
         lift[a][ri] += val * dl[b][ci];
     });
+    const int64_t stride = E;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        Fu[a][0] += lift[a][0];
-        Fu[a][1] += lift[a][1];
-        Fp[a] += lift[a][2];
+        Fe[(a * 3 + 0) * stride + c] += lift[a][0];
+        Fe[(a * 3 + 1) * stride + c] += lift[a][1];
+        Fe[(a * 3 + 2) * stride + c] += lift[a][2];
     }
 }
 
@@ -341,21 +352,23 @@ k_cell_residual(int E, int n, const int32_t* __restrict__ cells, const double* _
                 const uint8_t* __restrict__ cellflag, const double* __restrict__ dvec, double* __restrict__ Fe) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= E) return;
-    CellData cd;
-    int v[3];
-    load_cell(cd, c, E, cells, x, h, sol, un, uh, n, v);
-    CellDerived d;
-    derive_cell(cd, d);
-    double Fu[3][2], Fp[3];
-    element_residual(cd, d, Fu, Fp);
-    if (cellflag != nullptr && cellflag[c]) lift_cell(cd, d, v, n, dvec, Fu, Fp);
-    const int64_t stride = E;
+    {
+        CellData cd;
+        int v[3];
+        load_cell(cd, c, E, cells, x, h, sol, un, uh, n, v);
+        CellDerived d;
+        derive_cell(cd, d);
+        double Fu[3][2], Fp[3];
+        element_residual(cd, d, Fu, Fp);
+        const int64_t stride = E;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        Fe[(a * 3 + 0) * stride + c] = Fu[a][0];
-        Fe[(a * 3 + 1) * stride + c] = Fu[a][1];
-        Fe[(a * 3 + 2) * stride + c] = Fp[a];
+        for (int a = 0; a < 3; ++a) {
+            Fe[(a * 3 + 0) * stride + c] = Fu[a][0];
+            Fe[(a * 3 + 1) * stride + c] = Fu[a][1];
+            Fe[(a * 3 + 2) * stride + c] = Fp[a];
+        }
     }
+    if (cellflag != nullptr && cellflag[c]) lift_cell(c, E, n, cells, x, h, sol, un, uh, dvec, Fe);
 }
 
 // ---------------------------------------------------------------------------
