@@ -44,6 +44,8 @@ WORKLOADS = {
     # the same transfinite grid with the reference's recombined Q1 cells
     "stenosis_pressure_structured_q1_1m": dict(scenario="stenosis_pressure_structured", res=0.0212, dt=1e-3,
                                                p_inlet=80.0, R_resistance=10.0, cell_type="quadrilateral"),
+    "stenosis_pressure_structured_q1_4m": dict(scenario="stenosis_pressure_structured", res=0.0106, dt=1e-3,
+                                               p_inlet=80.0, R_resistance=10.0, cell_type="quadrilateral"),
     "stenosis_pressure_structured_q1_8m": dict(scenario="stenosis_pressure_structured", res=0.0075, dt=1e-3,
                                                p_inlet=80.0, R_resistance=10.0, cell_type="quadrilateral"),
 }
