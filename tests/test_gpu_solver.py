@@ -115,6 +115,47 @@ def test_bdf2_lid_cavity_matches_oracle(cell_type):
     assert np.linalg.norm((p - p.mean()) - (p_ref - p_ref.mean())) < 1e-8 * np.linalg.norm(p_ref - p_ref.mean())
 
 
+def test_adaptive_dt_ramp_matches_oracle():
+    """stabilized_schur_adaptive: dt ramps linearly from 1e-4 to the target over the first 10 calls
+    (reference stabilized_schur_adaptive.py:376-393); same forms, dt is a Constant."""
+    from cfd_hemodynamic_b200.fem import mesh as M
+    from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation
+    from oracle import ns_oracle as O
+    nx, mu, dt, steps = 12, 0.01, 0.01, 3
+    sc = LidDriven2DSimulation("stabilized_schur_adaptive", dt, steps * dt, rho=1, mu=mu, nx=nx,
+                               **dict(TIGHT, ksp_atol=1e-16))
+    s = sc.solver
+    dts = []
+    for _ in range(steps):
+        s.solveStep()
+        dts.append(float(s.dt.value))
+        s.u_prev.x.array[:] = s.u_sol.x.array[:]
+        s.p_prev.x.array[:] = s.p_sol.x.array[:]
+    assert np.allclose(dts, [1e-4 + (dt - 1e-4) * k / 10 for k in (1, 2, 3)], rtol=1e-15)
+    mesh = M.create_unit_square(None, nx, nx)
+    prob = T.make_problem(mesh, dt=dt, rho=1.0, mu=mu, f=(0.0, 0.0))
+    x = prob.x
+    n = prob.n
+    ext = M.exterior_facet_indices(mesh.topology)
+    prob.facet_sets = [O.FacetSet(pairs=mesh.topology.facet_cell_pairs(ext), a_p=1.0, a_g=1.0)]
+    walls = np.nonzero(np.isclose(x[:, 0], 0) | np.isclose(x[:, 0], 1) | np.isclose(x[:, 1], 0))[0]
+    lidf = M.locate_entities_boundary(mesh, 1, lambda X: np.isclose(X[1], 1.0) & (X[0] > 1e-10) & (X[0] < 1 - 1e-10))
+    lid = np.unique(mesh.topology.facet_vertices[lidf])
+    g1 = np.zeros(2 * n); g1[0::2] = 1.0
+    prob.bcs = T.oracle_bcs(prob, [("u", walls, np.zeros(2 * n)), ("u", lid, g1)])
+    xk, un = np.zeros(3 * n), np.zeros(2 * n)
+    for k in range(steps):
+        prob.dt = dts[k]
+        xk = O.remove_nullspace(prob, xk)
+        xk, its, reason = O.newton_solve(prob, xk, un, rtol=1e-12, stol=0.0)
+        assert reason > 0
+        un = xk[:2 * n].copy()
+    u_ref, p_ref = xk[:2 * n], xk[2 * n:]
+    u, p = s.u_sol.x.array, s.p_sol.x.array
+    assert np.linalg.norm(u - u_ref) < 1e-8 * np.linalg.norm(u_ref)
+    assert np.linalg.norm((p - p.mean()) - (p_ref - p_ref.mean())) < 1e-8 * np.linalg.norm(p_ref - p_ref.mean())
+
+
 def test_scenario_time_loop(tmp_path):
     """Scenario.solve drives solveStep, shifts u_prev on the host and writes norms.txt."""
     from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation

@@ -166,3 +166,13 @@ def test_quadrilateral_scenario_tables_host_only():
     row = int(tq["cells"][0][2])                     # vertices 0..row-1 form the bottom wall (slightly tapered)
     straight = (np.arange(x.shape[0]) < row) & (x[:, 0] > 0.5) & (x[:, 0] < 2.0)
     assert straight.any() and np.allclose(np.linalg.norm(w[straight], axis=1), float(s.mu.value), rtol=2e-2)
+
+
+def test_adaptive_plugin_ramp_host_only():
+    """dt ramp bookkeeping of stabilized_schur_adaptive without a device (the solve itself is a GPU test)."""
+    from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation
+    sc = LidDriven2DSimulation("stabilized_schur_adaptive", 0.01, 0.1, rho=1, mu=0.01, nx=4, host_only=True)
+    s = sc.solver
+    assert s.target_dt == 0.01 and s.step_count_adapt == 0
+    s._set_dt(0.002)
+    assert float(s.dt.value) == 0.002
