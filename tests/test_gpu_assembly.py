@@ -227,3 +227,45 @@ def test_q1_laplace_mass(hemo):
     assert abs(L - L.T).max() < 1e-13
     assert np.abs(L @ np.ones(prob.n)).max() < 1e-12
     assert abs(float(mass.sum()) - 1.0) < 1e-13
+
+
+def test_edge_cases_and_argument_errors(hemo):
+    """Single-cell meshes (every vertex on the boundary), empty facet sets, rule-size limits and
+    invalid cell types through the C-ABI."""
+    from cfd_hemodynamic_b200._lib import HemoError
+    from cfd_hemodynamic_b200.fem import mesh as M
+    from oracle import ns_oracle as O
+    from oracle import q1_oracle as Q1
+    for cell_type, X in (("triangle", np.array([[0.0, 0.0], [1.0, 0.1], [0.3, 0.9]])),
+                         ("quadrilateral", np.array([[0.0, 0.1], [1.0, 0.0], [0.15, 0.9], [1.2, 1.1]]))):
+        nv = X.shape[0]
+        mesh = M.Mesh(X, np.arange(nv, dtype=np.int32)[None, :], cell_type=cell_type if nv == 4 else None)
+        prob = T.make_problem(mesh)
+        ext = M.exterior_facet_indices(mesh.topology)
+        assert len(ext) == nv
+        fsets = [(ext, dict(a_p=1.0, a_g=1.0, a_s=0.5, a_n=1.0, beta_n=10.0, a_b=1.0, beta_b=0.2, pconst=1.5))]
+        prob.facet_sets = [O.FacetSet(pairs=mesh.topology.facet_cell_pairs(f), **c) for f, c in fsets]
+        T.setup_gpu(hemo, mesh, prob, fsets)
+        for sid in range(1, 8):
+            hemo.set_facet_set(sid, None, None)              # m = 0 removes a set
+        hemo.set_bc(None, None, None)
+        rng = np.random.default_rng(0)
+        u, p, un = rng.standard_normal(2 * nv), rng.standard_normal(nv), rng.standard_normal(2 * nv)
+        dev = hemo.device
+        vals = torch.zeros(hemo.nnz, dtype=torch.float64, device=dev)
+        b = torch.zeros(3 * nv, dtype=torch.float64, device=dev)
+        hemo.assemble_jacobian(torch.tensor(np.concatenate([u, p]), device=dev), torch.tensor(un, device=dev), vals)
+        hemo.assemble_residual(torch.tensor(np.concatenate([u, p]), device=dev), torch.tensor(un, device=dev), None, b)
+        A_ref = O.assemble_J_raw(prob, u, p, un)
+        assert hemo.nnz == (3 * nv) ** 2 == A_ref.nnz          # dense single-cell pattern
+        assert np.linalg.norm(vals.cpu().numpy() - A_ref.data) < REL_TOL * np.linalg.norm(A_ref.data)
+        b_ref = O.assemble_F_raw(prob, u, p, un)
+        assert np.linalg.norm(b.cpu().numpy() - b_ref) < REL_TOL * np.linalg.norm(b_ref)
+        assert hemo.outlet_flux(5, torch.tensor(un, device=dev)) == 0.0   # empty set: zero flux
+    # rule-size limits: 196 points on quadrilaterals (context is in quadrilateral mode here), 80 on triangles
+    pts, wts = Q1.tensor_gauss(15)                            # 225 points
+    with pytest.raises(HemoError):
+        hemo.set_quadrature(0, pts, wts)
+    assert hemo.lib.hemo_set_cell_type(hemo._ctx, 7) < 0       # HEMO_EINVAL
+    assert hemo.lib.hemo_set_time_scheme(hemo._ctx, 0.0, 1.0, None) < 0
+    assert hemo.lib.hemo_set_time_scheme(hemo._ctx, 0.5, 1.0, None) == 0
