@@ -33,8 +33,10 @@ struct HemoFacetRule {
 
 // Cell rule of one block form on the reference quadrilateral [0,1]^2: points and weights as
 // given (Basix: tensor Gauss-Jacobi, 12 x 12 points for the degree-22 forms); the Q1 basis
-// and the bilinear geometry are evaluated from (xi, eta) on the fly.
-#define HEMO_MAXQ_QUAD 196
+// and the bilinear geometry are evaluated from (xi, eta) on the fly.  The limit leaves room for
+// 16 x 16 points (degree 30, where FFCx starts to warn): if UFL adds the degree of det J of the
+// non-affine map to the estimate, the forms come out at degree 26 = 14 x 14 points.
+#define HEMO_MAXQ_QUAD 256
 struct HemoQuadRule {
     int nq;
     int alias;                      // lowest block id with an identical rule

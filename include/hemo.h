@@ -121,7 +121,7 @@ int hemo_get_pattern(hemo_ctx* ctx, int64_t* rowptr_dev, int32_t* colind_dev);
 
 /* ---- forms ---------------------------------------------------------------- */
 /* Quadrature rule of one block form (host arrays; pts = nq*2 reference coords; triangles:
- * wts sum to 1/2, nq <= 80; quadrilaterals: points on [0,1]^2, wts sum to 1, nq <= 196).
+ * wts sum to 1/2, nq <= 80; quadrilaterals: points on [0,1]^2, wts sum to 1, nq <= 256).
  * Basix rule selected by FFCx at form() (:188-189). */
 int hemo_set_quadrature(hemo_ctx* ctx, int block, const double* pts_host,
                         const double* wts_host, int nq);

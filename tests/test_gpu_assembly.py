@@ -215,6 +215,32 @@ def test_q1_shared_rule_single_pass(hemo):
     assert np.linalg.norm(b.cpu().numpy() - b_ref) < REL_TOL * np.linalg.norm(b_ref)
 
 
+def test_q1_degree26_rules(hemo):
+    """14 x 14 / 13 x 13 / 12 x 12 Gauss points (the estimate with the degree of det J added,
+    DESIGN.md §4b): rules are a run-time input, the kernels take them unchanged."""
+    from oracle import ns_oracle as O
+    from oracle import q1_oracle as Q1
+    m = dict(Fu=14, Fp=13, uu=14, up=13, pu=13, pp=12)
+    mesh = T.perturbed_square(4, 3, seed=5, cell_type="quadrilateral")
+    prob = T.make_problem(mesh, rules={k: Q1.tensor_gauss(v) for k, v in m.items()})
+    T.setup_gpu(hemo, mesh, prob)
+    for sid in range(8):
+        hemo.set_facet_set(sid, None, None)
+    hemo.set_bc(None, None, None)
+    u, p, un = T.smooth_fields(prob.x)
+    dev = hemo.device
+    xd = torch.tensor(np.concatenate([u, p]), device=dev)
+    und = torch.tensor(un, device=dev)
+    vals = torch.zeros(hemo.nnz, dtype=torch.float64, device=dev)
+    b = torch.zeros(3 * prob.n, dtype=torch.float64, device=dev)
+    hemo.assemble_jacobian(xd, und, vals)
+    hemo.assemble_residual(xd, und, None, b)
+    A_ref = O.assemble_J_raw(prob, u, p, un)
+    assert np.linalg.norm(vals.cpu().numpy() - A_ref.data) < REL_TOL * np.linalg.norm(A_ref.data)
+    b_ref = O.assemble_F_raw(prob, u, p, un)
+    assert np.linalg.norm(b.cpu().numpy() - b_ref) < REL_TOL * np.linalg.norm(b_ref)
+
+
 def test_q1_laplace_mass(hemo):
     """Pressure Laplacian / lumped mass of the Schur approximation on quadrilaterals: symmetric,
     constants in the kernel, mass sums to the area."""
@@ -262,8 +288,8 @@ def test_edge_cases_and_argument_errors(hemo):
         b_ref = O.assemble_F_raw(prob, u, p, un)
         assert np.linalg.norm(b.cpu().numpy() - b_ref) < REL_TOL * np.linalg.norm(b_ref)
         assert hemo.outlet_flux(5, torch.tensor(un, device=dev)) == 0.0   # empty set: zero flux
-    # rule-size limits: 196 points on quadrilaterals (context is in quadrilateral mode here), 80 on triangles
-    pts, wts = Q1.tensor_gauss(15)                            # 225 points
+    # rule-size limits: 256 points on quadrilaterals (context is in quadrilateral mode here), 80 on triangles
+    pts, wts = Q1.tensor_gauss(17)                            # 289 points
     with pytest.raises(HemoError):
         hemo.set_quadrature(0, pts, wts)
     assert hemo.lib.hemo_set_cell_type(hemo._ctx, 7) < 0       # HEMO_EINVAL
