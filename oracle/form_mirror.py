@@ -187,3 +187,102 @@ class CellForms:
             eta = (1 - s) * ref[va][1] + s * ref[vb][1]
             out += w * length * np.array(fn(xi, eta, *U.reshape(-1), *P), dtype=out.dtype)
         return out.reshape(nv, 2)
+
+
+class SimplexForms:
+    """The same literal transcription for one P1 simplex in d = 2 or 3 dimensions (cell integrals
+    only): cross-check of `simplex_oracle` — groundwork for the tetrahedral kernels."""
+
+    def __init__(self, X, Un, h, dt, rho, mu, f, eps0, theta=0.5, a0=1.0, Uh=None):
+        nv, d = X.shape
+        assert nv == d + 1
+        self.nv, self.d = nv, d
+        xi = sp.symbols(f"xi0:{d}", real=True)
+        phi = [1 - sum(xi)] + list(xi)
+        x = [sum(sp.Float(X[a, i]) * phi[a] for a in range(nv)) for i in range(d)]
+        J = sp.Matrix(d, d, lambda i, j: sp.diff(x[i], xi[j]))
+        detJ = J.det()
+        K = J.inv()
+        R_ = range(d)
+
+        def grad(fn):
+            return [sum(K[j, i] * sp.diff(fn, xi[j]) for j in R_) for i in R_]
+
+        def nabla_grad(v):
+            g = [grad(v[j]) for j in R_]
+            return [[g[j][i] for j in R_] for i in R_]
+
+        def div_vec(v):
+            return sum(grad(v[i])[i] for i in R_)
+
+        def div_ten(A):
+            return [sum(grad(A[i][j])[j] for j in R_) for i in R_]
+
+        def sym(A):
+            return [[(A[i][j] + A[j][i]) / 2 for j in R_] for i in R_]
+
+        def dot_vv(a, b):
+            return sum(a[i] * b[i] for i in R_)
+
+        def dot_v_ng(u, ng):
+            return [sum(u[i] * ng[i][j] for i in R_) for j in R_]
+
+        def inner_tt(A, B):
+            return sum(A[i][j] * B[i][j] for i in R_ for j in R_)
+
+        self.Us = sp.symbols(f"U0:{d * nv}")
+        self.Ps = sp.symbols(f"P0:{nv}")
+        u_sol = [sum(self.Us[d * a + k] * phi[a] for a in range(nv)) for k in R_]
+        p_sol = sum(self.Ps[a] * phi[a] for a in range(nv))
+        u_prev = [sum(sp.Float(Un[a, k]) * phi[a] for a in range(nv)) for k in R_]
+        Uh = Un if Uh is None else Uh
+        u_hist = [sum(sp.Float(Uh[a, k]) * phi[a] for a in range(nv)) for k in R_]
+        dt_, rho_, mu_, h_ = sp.Float(dt), sp.Float(rho), sp.Float(mu), sp.Float(h)
+        fvec = [sp.Float(v) for v in f]
+        th, a0_ = sp.Float(theta), sp.Float(a0)
+
+        def epsilon(u):                   # src/solverBase.py:177-178
+            return sym(nabla_grad(u))
+
+        def sigma(u, p):                  # src/solverBase.py:180-182
+            e = epsilon(u)
+            return [[2 * mu_ * e[i][j] - (p if i == j else 0) for j in R_] for i in R_]
+
+        u_mid = [th * u_sol[k] + (1 - th) * u_prev[k] for k in R_]                  # :71
+        dudt = [(a0_ * u_sol[k] - u_hist[k]) / dt_ for k in R_]                      # :74
+        conv = dot_v_ng(u_mid, nabla_grad(u_mid))                                    # :75
+        sig = sigma(u_mid, p_sol)
+        dsig = div_ten(sig)
+        R = [rho_ * (dudt[k] + conv[k]) - dsig[k] - rho_ * fvec[k] for k in R_]      # :95-97
+        vnorm = sp.sqrt(dot_vv(u_prev, u_prev))                                      # :91-93
+        eps = sp.Float(eps0)
+        tau1 = h_ / sp.Piecewise((2 * vnorm, 2 * vnorm >= eps), (eps, True))         # :101-103
+        tau_supg = (1 / tau1 ** 2 + 1 / (dt_ / 2) ** 2 + 1 / ((h_ * h_) / (4 * (mu_ / rho_))) ** 2) ** sp.Rational(-1, 2)
+        Re = (vnorm * h_) / (2 * (mu_ / rho_))                                       # :116
+        z = sp.Piecewise((Re / 3, Re <= 3), (1, True))                               # :117
+        tau_lsic = (vnorm * h_ * z) / 2                                              # :118
+        integrands = []
+        for a in range(nv):
+            for k in R_:
+                v = [phi[a] if i == k else sp.Integer(0) for i in R_]
+                Fv = rho_ * dot_vv(v, dudt) + rho_ * dot_vv(v, conv)                 # :74-75
+                Fv -= dot_vv(v, [rho_ * fk for fk in fvec])                          # :76
+                Fv += inner_tt(epsilon(v), sig)                                      # :77
+                Fv += tau_supg * dot_vv(R, dot_v_ng(u_mid, nabla_grad(v)))           # :109
+                Fv += tau_lsic * div_vec(u_mid) * rho_ * div_vec(v)                  # :119
+                integrands.append(Fv)
+        for a in range(nv):
+            q = phi[a]
+            integrands.append(q * div_vec(u_mid) + (1 / rho_) * tau_supg * dot_vv(R, grad(q)))   # :80, :113
+        args = tuple(xi) + tuple(self.Us) + tuple(self.Ps)
+        self._f = sp.lambdify(args, integrands + [sp.Abs(detJ)], modules="numpy", cse=True)
+
+    def cell_residual(self, U, P, rule_u, rule_p):
+        nv, d = self.nv, self.d
+        out = np.zeros((d + 1) * nv, dtype=np.result_type(U, P))
+        for rule, sl in ((rule_u, slice(0, d * nv)), (rule_p, slice(d * nv, (d + 1) * nv))):
+            pts, wts = rule
+            for pt, w in zip(pts, wts):
+                vals = self._f(*pt, *U.reshape(-1), *P)
+                out[sl] += w * vals[-1] * np.array(vals[:-1], dtype=out.dtype)[sl]
+        return out[:d * nv].reshape(nv, d), out[d * nv:]
