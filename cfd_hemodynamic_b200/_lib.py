@@ -72,6 +72,8 @@ SYMBOLS = {
     "hemo_assemble_residual": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "hemo_outlet_flux": (_I, [_VP, _I, _VP, C.POINTER(_D)]),
     "hemo_assemble_laplace_mass": (_I, [_VP, _VP, _VP]),
+    "hemo_tet_set_quadrature": (_I, [_VP, _I, _VP, _VP, _I]),
+    "hemo_tet_element_tensors": (_I, [_VP, _I, _I] + [_VP] * 9),
     "hemo_wall_shear_stress": (_I, [_VP, _I, _VP, _VP]),
     "hemo_boundary_force": (_I, [_VP, _I, _VP, C.POINTER(_D)]),
     "hemo_early_stop_norms": (_I, [_VP, _L, _VP, _VP, C.POINTER(_D)]),
@@ -283,6 +285,25 @@ class Hemo:
         self._check(self.lib.hemo_assemble_laplace_mass(self._ctx, _ptr(lap), _ptr(mass)),
                     "hemo_assemble_laplace_mass")
         return lap, mass
+
+    # ---- tetrahedra (element tensors only) ------------------------------------
+    def tet_set_quadrature(self, block: int, pts: np.ndarray, wts: np.ndarray):
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        wts = np.ascontiguousarray(wts, dtype=np.float64)
+        self._check(self.lib.hemo_tet_set_quadrature(self._ctx, block, _np_ptr(pts), _np_ptr(wts), len(wts)),
+                    "hemo_tet_set_quadrature")
+
+    def tet_element_tensors(self, x3, cells, h, sol, un, uh, f3):
+        """Ae (256, E), Fe (16, E) of P1 tetrahedra; see include/hemo.h."""
+        t = self.torch
+        E, n = int(cells.shape[0]), int(x3.shape[0])
+        Ae = t.empty((256, E), dtype=t.float64, device=self.device)
+        Fe = t.empty((16, E), dtype=t.float64, device=self.device)
+        f3 = np.ascontiguousarray(f3, dtype=np.float64)
+        self._check(self.lib.hemo_tet_element_tensors(self._ctx, n, E, _ptr(x3), _ptr(cells), _ptr(h), _ptr(sol), _ptr(un),
+                                                      _ptr(uh), _np_ptr(f3), _ptr(Ae), _ptr(Fe)),
+                    "hemo_tet_element_tensors")
+        return Ae, Fe
 
     # ---- post-processing ---------------------------------------------------
     def wall_shear_stress(self, set_id: int, x, out):

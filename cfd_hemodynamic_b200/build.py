@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhemo_sm100.so")
-SOURCES = ["assembly.cu", "assembly_q1.cu", "postproc.cu", "linalg.cu", "amg.cu", "solver.cu", "host_setup.cu"]
+SOURCES = ["assembly.cu", "assembly_q1.cu", "assembly_tet.cu", "postproc.cu", "linalg.cu", "amg.cu", "solver.cu", "host_setup.cu"]
 
 
 def _stale() -> bool:

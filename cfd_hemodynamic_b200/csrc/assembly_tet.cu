@@ -1,0 +1,205 @@
+// P1–P1 tetrahedron element-tensor kernel for sm_100a: the moment-factorised routines of
+// simplex_element.cuh (D = 3) behind a C-ABI entry that fills the SoA element buffers
+//     Ae[(a*4+b)*16 + ri*4+ci][E]  (ri/ci in u_x, u_y, u_z, p)   and   Fe[a*4+comp][E].
+//
+// Replaces the FFCx tetrahedron `tabulate_tensor` kernels of the forms at
+// src/solvers/stabilized_schur.py:60-123 (reached through `mesh.topology.cell_name()`, e.g.
+// src/scenarios/taylor_green.py:34).  Scope of this first 3-D piece: the batched element tensors
+// (north star, subsystem 1); scattering them into a 4x4-node-block CSR and the 3-D Krylov /
+// multigrid kernels are the follow-up, so there is no 3-D solve yet.
+//
+// One thread per cell.  The rule tables (up to 7^3 collapsed Gauss–Jacobi points per block form,
+// 13.7 kB each) do not fit constant memory and live in global memory: every thread of a warp reads
+// the same entry, so the loads are broadcasts served by L1.  Rules shared by several block forms
+// (alias table from the host) are integrated once.
+#include "hemo_internal.cuh"
+#include "simplex_element.cuh"
+
+struct TetRules {
+    SimplexRule<3> r[HEMO_NRULES];
+    int alias[HEMO_NRULES];          // lowest block id with an identical rule
+};
+
+struct hemo_tet_state {
+    TetRules* host = nullptr;
+    TetRules* dev = nullptr;
+    bool have[HEMO_NRULES] = {false, false, false, false, false, false};
+    bool dirty = true;
+};
+
+static hemo_tet_state* tet_state(hemo_ctx* ctx) {
+    if (!ctx->tet) ctx->tet = new hemo_tet_state();
+    return ctx->tet;
+}
+
+__global__ void __launch_bounds__(128)
+k_tet_cell_tensors(int E, int n, const int32_t* __restrict__ cells, const double* __restrict__ x,
+                   const double* __restrict__ h, const double* __restrict__ sol, const double* __restrict__ un,
+                   const double* __restrict__ uh, HemoForm par, double f0, double f1, double f2,
+                   const TetRules* __restrict__ rules, double* __restrict__ Ae, double* __restrict__ Fe) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= E) return;
+    SimplexCell<3> cd;
+    double X[4][3];
+    const int4 vv = reinterpret_cast<const int4*>(cells)[c];
+    const int v[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            X[a][k] = x[3 * (int64_t)v[a] + k];
+            cd.U[a][k] = sol[3 * (int64_t)v[a] + k];
+            cd.N[a][k] = un[3 * (int64_t)v[a] + k];
+            cd.H[a][k] = uh[3 * (int64_t)v[a] + k];
+        }
+        cd.P[a] = sol[3 * (int64_t)n + v[a]];
+    }
+    cd.fbody[0] = f0; cd.fbody[1] = f1; cd.fbody[2] = f2;
+    cd.h = h[c];
+    simplex_geometry<3>(cd, X);
+    simplex_derive<3>(cd, par);
+    const int64_t stride = E;
+    // moments of the distinct rules, block ids HEMO_Q_FU .. HEMO_Q_PP
+    double T2[HEMO_NRULES > 0 ? 2 : 1][4][4];      // [0]: residual group scratch / J_uu, [1]: scratch
+    double L0;
+    // ---- residual: rules FU, FP
+    {
+        double T2p[4][4], L0p;
+        simplex_moments<3>(cd, par, rules->r[HEMO_Q_FU], T2[0], L0);
+        if (rules->alias[HEMO_Q_FP] == HEMO_Q_FU) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) T2p[a][b] = T2[0][a][b];
+        } else {
+            simplex_moments<3>(cd, par, rules->r[HEMO_Q_FP], T2p, L0p);
+        }
+        double T1p[4], T0;
+        simplex_colsum<3>(T2p, T1p, T0);
+        const SimplexRule<3>& ru = rules->r[HEMO_Q_FU];
+        const SimplexRule<3>& rp = rules->r[HEMO_Q_FP];
+        const double m0 = ru.m0 * cd.detJ;
+        double pbar = 0.0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) pbar += ru.m1[b] * cd.P[b];
+        pbar *= cd.detJ;
+        for (int a = 0; a < 4; ++a) {
+            double Wd[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                double s = 0.0;
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) s += T2[0][cc][d] * cd.s[cc][a];
+                Wd[d] = s;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                double val = 0.0;
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) val += par.rho * cd.detJ * ru.m2[a][cc] * cd.A[cc][k];
+                double sg = 0.0;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) sg += cd.g[a][i] * par.mu * (cd.G[i][k] + cd.G[k][i]);
+                val += m0 * sg - cd.g[a][k] * pbar;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) val += Wd[d] * cd.R[d][k];
+                val += L0 * par.rho * cd.divu * cd.g[a][k];
+                Fe[(a * 4 + k) * stride + c] = val;
+            }
+            double acc = 0.0;
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+                acc += T1p[d] * (cd.R[d][0] * cd.g[a][0] + cd.R[d][1] * cd.g[a][1] + cd.R[d][2] * cd.g[a][2]);
+            Fe[(a * 4 + 3) * stride + c] = cd.detJ * rp.m1[a] * cd.divu + acc / par.rho;
+        }
+    }
+    // ---- Jacobian: rules UU, UP, PU, PP (alias = lowest identical block id among all six)
+    {
+        double T1up[4], T1pu[4], T1[4], T0, T0pp = 0.0, Lt;
+        auto col_of = [&](int blk, double T1out[4], double& T0out) {
+            simplex_moments<3>(cd, par, rules->r[blk], T2[1], Lt);
+            simplex_colsum<3>(T2[1], T1out, T0out);
+        };
+        col_of(HEMO_Q_UP, T1up, T0);
+        if (rules->alias[HEMO_Q_PU] == rules->alias[HEMO_Q_UP]) {
+#pragma unroll
+            for (int d = 0; d < 4; ++d) T1pu[d] = T1up[d];
+        } else {
+            col_of(HEMO_Q_PU, T1pu, T0);
+        }
+        if (rules->alias[HEMO_Q_PP] == rules->alias[HEMO_Q_UP]) {
+            T0pp = T1up[0] + T1up[1] + T1up[2] + T1up[3];
+        } else if (rules->alias[HEMO_Q_PP] == rules->alias[HEMO_Q_PU]) {
+            T0pp = T1pu[0] + T1pu[1] + T1pu[2] + T1pu[3];
+        } else {
+            col_of(HEMO_Q_PP, T1, T0pp);
+        }
+        if (rules->alias[HEMO_Q_UU] != HEMO_Q_FU) simplex_moments<3>(cd, par, rules->r[HEMO_Q_UU], T2[0], L0);
+        // (alias FU: T2[0] / L0 still hold the moments of the identical F_u rule)
+        double* out = Ae + c;
+        simplex_jacobian_from_moments<3>(cd, par, T2[0], L0, T1up, T1pu, T0pp, rules->r[HEMO_Q_UU].m0,
+                                         rules->r[HEMO_Q_UU].m2, rules->r[HEMO_Q_UP].m1, rules->r[HEMO_Q_PU].m1,
+                                         [&](int a, int b, int ri, int ci, double val) {
+                                             out[((a * 4 + b) * 16 + ri * 4 + ci) * stride] = val;
+                                         });
+    }
+}
+
+extern "C" int hemo_tet_set_quadrature(hemo_ctx* ctx, int block, const double* pts, const double* wts, int nq) {
+    if (!ctx || block < 0 || block >= HEMO_NRULES || !pts || !wts || nq <= 0) return HEMO_EINVAL;
+    if (nq > HEMO_SIMPLEX_MAXQ) HEMO_FAIL(ctx, HEMO_EINVAL, "too many quadrature points for a tetrahedron rule");
+    hemo_tet_state* st = tet_state(ctx);
+    if (!st->host) {
+        st->host = (TetRules*)calloc(1, sizeof(TetRules));
+        if (!st->host) HEMO_FAIL(ctx, HEMO_EINVAL, "out of host memory");
+    }
+    simplex_rule_set<3>(st->host->r[block], pts, wts, nq);
+    st->have[block] = true;
+    for (int b = 0; b < HEMO_NRULES; ++b) {
+        if (!st->have[b]) continue;
+        st->host->alias[b] = b;
+        for (int a = 0; a < b; ++a) {
+            if (!st->have[a] || st->host->r[a].nq != st->host->r[b].nq) continue;
+            bool same = true;
+            for (int q = 0; q < st->host->r[b].nq && same; ++q) {
+                same = st->host->r[a].w[q] == st->host->r[b].w[q];
+                for (int k = 0; k < 4 && same; ++k) same = st->host->r[a].phi[q][k] == st->host->r[b].phi[q][k];
+            }
+            if (same) { st->host->alias[b] = st->host->alias[a]; break; }
+        }
+    }
+    st->dirty = true;
+    return 0;
+}
+
+extern "C" int hemo_tet_element_tensors(hemo_ctx* ctx, int n_nodes, int n_cells, const double* x_dev,
+                                        const int32_t* cells_dev, const double* h_dev, const double* sol_dev,
+                                        const double* un_dev, const double* uh_dev, const double* f3_host,
+                                        double* Ae_dev, double* Fe_dev) {
+    if (!ctx || n_nodes <= 0 || n_cells <= 0 || !x_dev || !cells_dev || !h_dev || !sol_dev || !un_dev || !f3_host ||
+        !Ae_dev || !Fe_dev)
+        return HEMO_EINVAL;
+    if (!ctx->have_par) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_set_params not called");
+    hemo_tet_state* st = tet_state(ctx);
+    for (int r = 0; r < HEMO_NRULES; ++r)
+        if (!st->have[r]) HEMO_FAIL(ctx, HEMO_ESTATE, "tetrahedron quadrature rule missing for a block form");
+    if (st->dirty) {
+        if (!st->dev) HEMO_CHECK_CUDA(ctx, cudaMalloc((void**)&st->dev, sizeof(TetRules)));
+        HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(st->dev, st->host, sizeof(TetRules), cudaMemcpyHostToDevice, ctx->stream));
+        st->dirty = false;
+    }
+    hemo_form_finalize(ctx->par);
+    k_tet_cell_tensors<<<hemo_grid(n_cells, 128), 128, 0, ctx->stream>>>(
+        n_cells, n_nodes, cells_dev, x_dev, h_dev, sol_dev, un_dev, uh_dev ? uh_dev : un_dev, ctx->par, f3_host[0],
+        f3_host[1], f3_host[2], st->dev, Ae_dev, Fe_dev);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+void hemo_tet_free(hemo_ctx* ctx) {
+    if (!ctx->tet) return;
+    free(ctx->tet->host);
+    cudaFree(ctx->tet->dev);
+    delete ctx->tet;
+    ctx->tet = nullptr;
+}

@@ -116,8 +116,11 @@ struct HemoProf {
     size_t used[HEMO_PROF_NCLASS] = {0};
 };
 
+struct hemo_tet_state;      // assembly_tet.cu
+
 struct hemo_ctx {
     HemoProf prof;
+    hemo_tet_state* tet = nullptr;   // tetrahedron rule tables (allocated on first use)
     int device = 0;
     cudaStream_t stream = 0;
     std::string err;
@@ -270,6 +273,8 @@ int hemo_q1_facets(hemo_ctx* ctx, int mode, const HemoFacetSet& fs, const double
                    const uint8_t* cellflag);
 int hemo_q1_facet_flux(hemo_ctx* ctx, const HemoFacetSet& fs, const double* un_dev, double* partial);
 int hemo_q1_laplace_mass(hemo_ctx* ctx);
+// implemented in assembly_tet.cu
+void hemo_tet_free(hemo_ctx* ctx);
 // implemented in linalg.cu
 int hemo_ensure_reduce(hemo_ctx* ctx, size_t partial_n, size_t out_n);
 int hemo_dot_dev(hemo_ctx* ctx, int64_t n, const double* x, const double* y, double* out_host);

@@ -166,6 +166,20 @@ int hemo_outlet_flux(hemo_ctx* ctx, int set_id, const double* un_dev, double* q_
  * pressure mass (n doubles) for the Schur-complement approximation. */
 int hemo_assemble_laplace_mass(hemo_ctx* ctx, double* lap_vals_dev, double* mass_dev);
 
+/* ---- tetrahedra: batched element tensors (first 3-D piece) ------------------------------------
+ * FFCx tetrahedron kernels of the same forms (src/solvers/stabilized_schur.py:60-123 with
+ * `mesh.topology.cell_name() == "tetrahedron"`, e.g. src/scenarios/taylor_green.py:34).  Element
+ * tensors only: Ae SoA [(a*4+b)*16 + ri*4+ci][E], Fe SoA [a*4+comp][E] with ri/ci/comp in
+ * (u_x, u_y, u_z, p); there is no 3-D scatter / solve yet.  Uses hemo_set_params (dt, rho, mu,
+ * eps0; f from f3_host) and hemo_set_time_scheme (theta, a0).  x: 3n, cells: 4E, sol = [u (3n) | p (n)],
+ * un / uh: 3n (uh NULL = un).  Rules: points on the reference tetrahedron, weights sum to 1/6,
+ * nq <= 343; one per block form like hemo_set_quadrature. */
+int hemo_tet_set_quadrature(hemo_ctx* ctx, int block, const double* pts_host, const double* wts_host, int nq);
+int hemo_tet_element_tensors(hemo_ctx* ctx, int n_nodes, int n_cells, const double* x_dev,
+                             const int32_t* cells_dev, const double* h_dev, const double* sol_dev,
+                             const double* un_dev, const double* uh_dev, const double* f3_host,
+                             double* Ae_dev, double* Fe_dev);
+
 /* ---- per-step post-processing on the device ------------------------
  * What Scenario.solve computes on the host after every solveStep (src/scenario.py:258-304,
  * 315-324) and the DFG force integrals (src/scenarios/dfg_1.py:183-211), for a device-resident
