@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libhemo_sm100.so")
 
 HEMO_DIVERGED = -100
 Q_FU, Q_FP, Q_UU, Q_UP, Q_PU, Q_PP = range(6)
-CELL_TRIANGLE, CELL_QUADRILATERAL = 0, 1
+CELL_TRIANGLE, CELL_QUADRILATERAL, CELL_TETRAHEDRON = 0, 1, 2
 
 
 class HemoError(RuntimeError):
@@ -72,6 +72,7 @@ SYMBOLS = {
     "hemo_assemble_residual": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "hemo_outlet_flux": (_I, [_VP, _I, _VP, C.POINTER(_D)]),
     "hemo_assemble_laplace_mass": (_I, [_VP, _VP, _VP]),
+    "hemo_set_body_force3": (_I, [_VP, _VP]),
     "hemo_tet_set_quadrature": (_I, [_VP, _I, _VP, _VP, _I]),
     "hemo_tet_element_tensors": (_I, [_VP, _I, _I] + [_VP] * 9),
     "hemo_wall_shear_stress": (_I, [_VP, _I, _VP, _VP]),
@@ -202,12 +203,16 @@ class Hemo:
 
     # ---- setup ---------------------------------------------------------
     def set_mesh(self, x2, cells, h):
-        """cells: (E, 3) P1 triangles or (E, 4) tensor-ordered Q1 quadrilaterals."""
+        """cells: (E, 3) P1 triangles or (E, 4) tensor-ordered Q1 quadrilaterals with x2 (n, 2);
+        (E, 4) P1 tetrahedra with x2 (n, 3) (cell assembly into the CSR only, include/hemo.h)."""
         if cells.dim() != 2 or cells.shape[1] not in (3, 4) or not cells.is_contiguous():
             raise HemoError("cells must be a contiguous (E, 3) or (E, 4) int32 tensor")
         self.nv = int(cells.shape[1])
-        self._check(self.lib.hemo_set_cell_type(self._ctx, CELL_QUADRILATERAL if self.nv == 4 else CELL_TRIANGLE),
-                    "hemo_set_cell_type")
+        self.dim = int(x2.shape[1]) if x2.dim() == 2 else 2
+        if self.dim == 3 and self.nv != 4:
+            raise HemoError("3-D meshes must be tetrahedral: cells (E, 4)")
+        ctype = CELL_TETRAHEDRON if self.dim == 3 else (CELL_QUADRILATERAL if self.nv == 4 else CELL_TRIANGLE)
+        self._check(self.lib.hemo_set_cell_type(self._ctx, ctype), "hemo_set_cell_type")
         self._keep.update(x=x2, cells=cells, h=h)
         self.n = x2.shape[0]
         self.E = cells.shape[0]
@@ -219,11 +224,11 @@ class Hemo:
         self.nnz_node = int(ncol.shape[0])
         self._check(self.lib.hemo_set_node_graph(self._ctx, _ptr(nrowptr), _ptr(ncol), self.nnz_node),
                     "hemo_set_node_graph")
-        self.nnz = 9 * self.nnz_node
+        self.nnz = (getattr(self, "dim", 2) + 1) ** 2 * self.nnz_node
 
     def get_pattern(self):
         t = self.torch
-        rowptr = t.empty(3 * self.n + 1, dtype=t.int64, device=self.device)
+        rowptr = t.empty((getattr(self, "dim", 2) + 1) * self.n + 1, dtype=t.int64, device=self.device)
         col = t.empty(self.nnz, dtype=t.int32, device=self.device)
         self._check(self.lib.hemo_get_pattern(self._ctx, _ptr(rowptr), _ptr(col)), "hemo_get_pattern")
         return rowptr, col
@@ -239,6 +244,10 @@ class Hemo:
         self._keep["uh"] = uh
         self._check(self.lib.hemo_set_time_scheme(self._ctx, float(theta), float(a0), _ptr(uh)),
                     "hemo_set_time_scheme")
+
+    def set_body_force3(self, f3):
+        f3 = np.ascontiguousarray(f3, dtype=np.float64)
+        self._check(self.lib.hemo_set_body_force3(self._ctx, _np_ptr(f3)), "hemo_set_body_force3")
 
     def set_facet_quadrature(self, pts, wts):
         pts = np.ascontiguousarray(pts, dtype=np.float64)

@@ -892,11 +892,15 @@ static int upload_constants(hemo_ctx* ctx) {
 }
 
 extern "C" int hemo_set_cell_type(hemo_ctx* ctx, int cell_type) {
-    if (!ctx || (cell_type != HEMO_CELL_TRIANGLE && cell_type != HEMO_CELL_QUADRILATERAL)) return HEMO_EINVAL;
-    const int nv = (cell_type == HEMO_CELL_QUADRILATERAL) ? 4 : 3;
-    if (nv == ctx->nv) return 0;
+    if (!ctx || (cell_type != HEMO_CELL_TRIANGLE && cell_type != HEMO_CELL_QUADRILATERAL &&
+                 cell_type != HEMO_CELL_TETRAHEDRON))
+        return HEMO_EINVAL;
+    const int nv = (cell_type == HEMO_CELL_TRIANGLE) ? 3 : 4;
+    const int dim = (cell_type == HEMO_CELL_TETRAHEDRON) ? 3 : 2;
+    if (nv == ctx->nv && dim == ctx->dim) return 0;
     // a different cell type invalidates the mesh, the node graph tables and the rules
     ctx->nv = nv;
+    ctx->dim = dim;
     ctx->cells = nullptr; ctx->x = nullptr; ctx->h = nullptr; ctx->nrowptr = nullptr; ctx->ncol = nullptr;
     ctx->n = ctx->E = 0;
     for (int r = 0; r < HEMO_NRULES; ++r) ctx->have_rule[r] = false;
@@ -992,13 +996,14 @@ extern "C" int hemo_set_node_graph(hemo_ctx* ctx, const int32_t* nrowptr_dev, co
 extern "C" int hemo_matrix_nnz(hemo_ctx* ctx, int64_t* nnz) {
     if (!ctx || !nnz) return HEMO_EINVAL;
     if (!ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "node graph not set");
-    *nnz = 9 * ctx->nnz_node;
+    *nnz = (int64_t)(ctx->dim + 1) * (ctx->dim + 1) * ctx->nnz_node;
     return 0;
 }
 
 extern "C" int hemo_get_pattern(hemo_ctx* ctx, int64_t* rowptr_dev, int32_t* colind_dev) {
     if (!ctx || !rowptr_dev || !colind_dev) return HEMO_EINVAL;
     if (!ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "node graph not set");
+    if (ctx->dim == 3) return hemo_tet_pattern(ctx, rowptr_dev, colind_dev);
     k_pattern<<<hemo_grid(ctx->n + 1, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->nnz_node, ctx->nrowptr, ctx->ncol,
                                                                    rowptr_dev, colind_dev);
     HEMO_LAUNCH_CHECK(ctx);
@@ -1025,6 +1030,7 @@ static int set_quadrature_quad(hemo_ctx* ctx, int block, const double* pts, cons
 
 extern "C" int hemo_set_quadrature(hemo_ctx* ctx, int block, const double* pts, const double* wts, int nq) {
     if (!ctx || block < 0 || block >= HEMO_NRULES || !pts || !wts || nq <= 0) return HEMO_EINVAL;
+    if (ctx->dim == 3) return hemo_tet_set_quadrature(ctx, block, pts, wts, nq);
     if (ctx->nv == 4) return set_quadrature_quad(ctx, block, pts, wts, nq);
     if (nq > HEMO_MAXQ) return HEMO_EINVAL;
     HemoRule& r = ctx->rules[block];
@@ -1095,6 +1101,13 @@ extern "C" int hemo_set_time_scheme(hemo_ctx* ctx, double theta, double a0, cons
     return 0;
 }
 
+extern "C" int hemo_set_body_force3(hemo_ctx* ctx, const double* f3_host) {
+    if (!ctx || !f3_host) return HEMO_EINVAL;
+    ctx->par.f[0] = f3_host[0]; ctx->par.f[1] = f3_host[1]; ctx->fz = f3_host[2];
+    ctx->rules_dirty = ctx->qrules_dirty = true;
+    return 0;
+}
+
 extern "C" int hemo_set_facet_set(hemo_ctx* ctx, int set_id, const int32_t* cells_dev, const int32_t* mask_dev,
                                   int m, const hemo_facet_coef* coef) {
     if (!ctx || set_id < 0 || set_id >= HEMO_MAX_FACET_SETS || m < 0) return HEMO_EINVAL;
@@ -1123,6 +1136,7 @@ extern "C" int hemo_set_bc(hemo_ctx* ctx, const uint8_t* dofflag_dev, const doub
                            const uint8_t* cellflag_dev) {
     if (!ctx) return HEMO_EINVAL;
     if (!ctx->cells) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_set_mesh must precede hemo_set_bc");
+    if (ctx->dim == 3 && dofflag_dev) HEMO_FAIL(ctx, HEMO_ESTATE, "Dirichlet conditions are not implemented for tetrahedra yet");
     if (!dofflag_dev) {
         ctx->have_bc = false;
         return 0;
@@ -1138,7 +1152,9 @@ extern "C" int hemo_set_bc(hemo_ctx* ctx, const uint8_t* dofflag_dev, const doub
 
 // element buffers are allocated on first use (a context that only serves the pressure
 // Laplacian never pays for the 81*E Jacobian buffer)
-static int ensure_elem(hemo_ctx* ctx, size_t ae_count, size_t fe_count) {
+int hemo_ensure_elem(hemo_ctx* ctx, size_t ae_count, size_t fe_count);
+static int ensure_elem(hemo_ctx* ctx, size_t ae_count, size_t fe_count) { return hemo_ensure_elem(ctx, ae_count, fe_count); }
+int hemo_ensure_elem(hemo_ctx* ctx, size_t ae_count, size_t fe_count) {
     int rc;
     if (ae_count > ctx->Ae_count) {
         if ((rc = hemo_alloc(ctx, &ctx->Ae, ae_count))) return rc;
@@ -1165,6 +1181,7 @@ static int check_ready(hemo_ctx* ctx) {
 
 extern "C" int hemo_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const double* un_dev, double* vals_dev) {
     if (!ctx || !x_dev || !un_dev || !vals_dev) return HEMO_EINVAL;
+    if (ctx->dim == 3) return hemo_tet_assemble_jacobian(ctx, x_dev, un_dev, vals_dev);
     int rc = check_ready(ctx);
     if (rc) return rc;
     const int E = ctx->E, n = ctx->n, nv = ctx->nv;
@@ -1202,6 +1219,7 @@ extern "C" int hemo_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const 
 extern "C" int hemo_assemble_residual(hemo_ctx* ctx, const double* x_dev, const double* un_dev,
                                       const double* g_dev, double* b_dev) {
     if (!ctx || !x_dev || !un_dev || !b_dev) return HEMO_EINVAL;
+    if (ctx->dim == 3) return hemo_tet_assemble_residual(ctx, x_dev, un_dev, b_dev);
     if (ctx->have_bc && !g_dev) return HEMO_EINVAL;
     int rc = check_ready(ctx);
     if (rc) return rc;
@@ -1243,6 +1261,7 @@ extern "C" int hemo_outlet_flux(hemo_ctx* ctx, int set_id, const double* un_dev,
     if (!ctx || set_id < 0 || set_id >= HEMO_MAX_FACET_SETS || !un_dev || !q_host) return HEMO_EINVAL;
     const HemoFacetSet& fs = ctx->fsets[set_id];
     if (fs.m == 0) { *q_host = 0.0; return 0; }
+    if (ctx->dim == 3) HEMO_FAIL(ctx, HEMO_ESTATE, "facet integrals are not implemented for tetrahedra yet");
     int rc = hemo_ensure_reduce(ctx, (size_t)fs.m, 8);
     if (rc) return rc;
     cudaStream_t st = ctx->stream;
@@ -1263,6 +1282,7 @@ extern "C" int hemo_outlet_flux(hemo_ctx* ctx, int set_id, const double* un_dev,
 extern "C" int hemo_assemble_laplace_mass(hemo_ctx* ctx, double* lap_vals_dev, double* mass_dev) {
     if (!ctx || !lap_vals_dev || !mass_dev) return HEMO_EINVAL;
     if (!ctx->cells || !ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / node graph not set");
+    if (ctx->dim == 3) HEMO_FAIL(ctx, HEMO_ESTATE, "the Schur-approximation operators are not implemented for tetrahedra yet");
     const int E = ctx->E, n = ctx->n, nv = ctx->nv;
     int rc;
     if ((rc = ensure_elem(ctx, (size_t)nv * nv * E, (size_t)nv * E))) return rc;

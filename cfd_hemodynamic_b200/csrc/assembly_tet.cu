@@ -196,6 +196,119 @@ extern "C" int hemo_tet_element_tensors(hemo_ctx* ctx, int n_nodes, int n_cells,
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// 3-D assembly into the CSR the reference's create_matrix_block builds for P1-P1 tetrahedra
+// (src/solvers/stabilized_schur.py:191-193): global vector [u interleaved (3n) | p (n)], rows in
+// that order, columns ascending.  With B = 4 scalars per node, deg = #neighbours of node i and
+// r0 = nrowptr[i]: row 3i+k starts at 12*r0 + 4*k*deg, row 3n+i at 12*nnz_node + 4*r0; inside a row
+// the u-columns of neighbour t sit at 3t..3t+2 and its p-column at 3*deg + t.
+// Same atomic-free gather as the 2-D path (fixed summation order), 16 scalars per node pair.
+// ---------------------------------------------------------------------------
+int hemo_ensure_elem(hemo_ctx* ctx, size_t ae_count, size_t fe_count);
+
+__global__ void k_pattern3d(int n, int64_t nnz_node, const int32_t* __restrict__ nrowptr,
+                            const int32_t* __restrict__ ncol, int64_t* __restrict__ rowptr,
+                            int32_t* __restrict__ colind) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { rowptr[4 * (int64_t)n] = 16 * nnz_node; return; }
+    const int r0 = nrowptr[i];
+    const int deg = nrowptr[i + 1] - r0;
+    int64_t rs[4];
+    for (int k = 0; k < 3; ++k) { rs[k] = 12 * (int64_t)r0 + 4 * (int64_t)k * deg; rowptr[3 * (int64_t)i + k] = rs[k]; }
+    rs[3] = 12 * nnz_node + 4 * (int64_t)r0;
+    rowptr[3 * (int64_t)n + i] = rs[3];
+    for (int t = 0; t < deg; ++t) {
+        const int j = ncol[r0 + t];
+        for (int k = 0; k < 4; ++k) {
+            colind[rs[k] + 3 * t] = 3 * j; colind[rs[k] + 3 * t + 1] = 3 * j + 1; colind[rs[k] + 3 * t + 2] = 3 * j + 2;
+            colind[rs[k] + 3 * deg + t] = 3 * n + j;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_matrix3d(int n, int64_t nnz_node, int64_t E, const int32_t* __restrict__ nrowptr,
+                  const int32_t* __restrict__ rowof, const int32_t* __restrict__ seg_ptr,
+                  const int32_t* __restrict__ seg_src, const double* __restrict__ Ae, double* __restrict__ vals) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= nnz_node) return;
+    const int i = rowof[s];
+    double acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+    for (int t = seg_ptr[s]; t < seg_ptr[s + 1]; ++t) {
+        const int src = seg_src[t];
+        const int64_t c = src / 16;
+        const int ab = src - (int)c * 16;
+        const double* p = Ae + (int64_t)ab * 16 * E + c;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[k] += p[k * E];
+    }
+    const int r0 = nrowptr[i];
+    const int deg = nrowptr[i + 1] - r0;
+    const int tpos = (int)(s - r0);
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) {
+        const int64_t rs = (ri < 3) ? 12 * (int64_t)r0 + 4 * (int64_t)ri * deg : 12 * nnz_node + 4 * (int64_t)r0;
+        vals[rs + 3 * tpos] = acc[ri * 4 + 0];
+        vals[rs + 3 * tpos + 1] = acc[ri * 4 + 1];
+        vals[rs + 3 * tpos + 2] = acc[ri * 4 + 2];
+        vals[rs + 3 * deg + tpos] = acc[ri * 4 + 3];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_vector3d(int n, int64_t E, const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_src,
+                  const double* __restrict__ Fe, double* __restrict__ b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a[4] = {0, 0, 0, 0};
+    for (int t = seg_ptr[i]; t < seg_ptr[i + 1]; ++t) {
+        const int src = seg_src[t];
+        const int64_t c = src / 4;
+        const int la = src - (int)c * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] += Fe[(la * 4 + k) * E + c];
+    }
+    b[3 * (int64_t)i] = a[0]; b[3 * (int64_t)i + 1] = a[1]; b[3 * (int64_t)i + 2] = a[2];
+    b[3 * (int64_t)n + i] = a[3];
+}
+
+int hemo_tet_pattern(hemo_ctx* ctx, int64_t* rowptr_dev, int32_t* colind_dev) {
+    k_pattern3d<<<hemo_grid(ctx->n + 1, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->nnz_node, ctx->nrowptr, ctx->ncol,
+                                                                     rowptr_dev, colind_dev);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+static int tet_cells(hemo_ctx* ctx, const double* x_dev, const double* un_dev) {
+    if (!ctx->cells || !ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / node graph not set");
+    int rc = hemo_ensure_elem(ctx, (size_t)256 * ctx->E, (size_t)16 * ctx->E);
+    if (rc) return rc;
+    const double f3[3] = {ctx->par.f[0], ctx->par.f[1], ctx->fz};
+    return hemo_tet_element_tensors(ctx, ctx->n, ctx->E, ctx->x, ctx->cells, ctx->h, x_dev, un_dev, ctx->uh, f3, ctx->Ae,
+                                    ctx->Fe);
+}
+
+int hemo_tet_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const double* un_dev, double* vals_dev) {
+    int rc = tet_cells(ctx, x_dev, un_dev);
+    if (rc) return rc;
+    k_gather_matrix3d<<<hemo_grid(ctx->nnz_node, 256), 256, 0, ctx->stream>>>(
+        ctx->n, ctx->nnz_node, ctx->E, ctx->nrowptr, ctx->rowof, ctx->mseg_ptr, ctx->mseg_src, ctx->Ae, vals_dev);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int hemo_tet_assemble_residual(hemo_ctx* ctx, const double* x_dev, const double* un_dev, double* b_dev) {
+    int rc = tet_cells(ctx, x_dev, un_dev);
+    if (rc) return rc;
+    k_gather_vector3d<<<hemo_grid(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->E, ctx->vseg_ptr, ctx->vseg_src,
+                                                                       ctx->Fe, b_dev);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 void hemo_tet_free(hemo_ctx* ctx) {
     if (!ctx->tet) return;
     free(ctx->tet->host);

@@ -127,7 +127,9 @@ struct hemo_ctx {
     int64_t launches = 0;
 
     // mesh (borrowed)
-    int nv = 3;                     // nodes per cell: 3 = P1 triangle, 4 = Q1 quadrilateral (tensor-ordered)
+    int nv = 3;                     // nodes per cell: 3 = P1 triangle, 4 = Q1 quadrilateral (tensor-ordered) | P1 tetrahedron
+    int dim = 2;                    // geometric dimension: 3 only for tetrahedra (assembly into CSR; no 3-D solve yet)
+    double fz = 0.0;                // third component of the body force (hemo_set_body_force3)
     const double* x = nullptr;
     const int32_t* cells = nullptr;
     const double* h = nullptr;
@@ -275,6 +277,9 @@ int hemo_q1_facet_flux(hemo_ctx* ctx, const HemoFacetSet& fs, const double* un_d
 int hemo_q1_laplace_mass(hemo_ctx* ctx);
 // implemented in assembly_tet.cu
 void hemo_tet_free(hemo_ctx* ctx);
+int hemo_tet_pattern(hemo_ctx* ctx, int64_t* rowptr_dev, int32_t* colind_dev);
+int hemo_tet_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const double* un_dev, double* vals_dev);
+int hemo_tet_assemble_residual(hemo_ctx* ctx, const double* x_dev, const double* un_dev, double* b_dev);
 // implemented in linalg.cu
 int hemo_ensure_reduce(hemo_ctx* ctx, size_t partial_n, size_t out_n);
 int hemo_dot_dev(hemo_ctx* ctx, int64_t n, const double* x, const double* y, double* out_host);

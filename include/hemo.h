@@ -103,7 +103,7 @@ int hemo_prof_get(hemo_ctx* ctx, int kernel_class, double* ms_total, int64_t* la
  * before hemo_set_mesh; changing the type drops the mesh, the node graph and the quadrature
  * rules set earlier (rules belong to a cell type: triangle rules have weights summing to 1/2,
  * quadrilateral rules live on [0,1]^2 and sum to 1). */
-enum { HEMO_CELL_TRIANGLE = 0, HEMO_CELL_QUADRILATERAL = 1 };
+enum { HEMO_CELL_TRIANGLE = 0, HEMO_CELL_QUADRILATERAL = 1, HEMO_CELL_TETRAHEDRON = 2 };
 int hemo_set_cell_type(hemo_ctx* ctx, int cell_type);
 /* mesh.geometry.x / .dofmap / mesh.h (src/solvers/stabilized_schur.py:55-58,83-88).
  * x: n_nodes*2 doubles, cells: n_cells*(3|4) int32, h: n_cells doubles; borrowed. */
@@ -174,6 +174,12 @@ int hemo_assemble_laplace_mass(hemo_ctx* ctx, double* lap_vals_dev, double* mass
  * eps0; f from f3_host) and hemo_set_time_scheme (theta, a0).  x: 3n, cells: 4E, sol = [u (3n) | p (n)],
  * un / uh: 3n (uh NULL = un).  Rules: points on the reference tetrahedron, weights sum to 1/6,
  * nq <= 343; one per block form like hemo_set_quadrature. */
+/* With hemo_set_cell_type(HEMO_CELL_TETRAHEDRON) (x: 3n doubles, cells: 4E, sol = [u (3n) | p (n)]) the
+ * generic entry points hemo_set_mesh, hemo_set_node_graph, hemo_set_quadrature, hemo_matrix_nnz (16 *
+ * nnz_node), hemo_get_pattern (4n+1 row pointers), hemo_assemble_jacobian and hemo_assemble_residual
+ * assemble the cell integrals into the CSR create_matrix_block builds (:191-193); facet terms,
+ * Dirichlet conditions and the solver are not implemented in 3-D yet (HEMO_ESTATE). */
+int hemo_set_body_force3(hemo_ctx* ctx, const double* f3_host);
 int hemo_tet_set_quadrature(hemo_ctx* ctx, int block, const double* pts_host, const double* wts_host, int nq);
 int hemo_tet_element_tensors(hemo_ctx* ctx, int n_nodes, int n_cells, const double* x_dev,
                              const int32_t* cells_dev, const double* h_dev, const double* sol_dev,
