@@ -190,8 +190,8 @@ class CellForms:
 
 
 class SimplexForms:
-    """The same literal transcription for one P1 simplex in d = 2 or 3 dimensions (cell integrals
-    only): cross-check of `simplex_oracle` — groundwork for the tetrahedral kernels."""
+    """The same literal transcription for one P1 simplex in d = 2 or 3 dimensions (cell and
+    exterior-facet integrals): cross-check of `simplex_oracle` — groundwork for the tetrahedral kernels."""
 
     def __init__(self, X, Un, h, dt, rho, mu, f, eps0, theta=0.5, a0=1.0, Uh=None):
         nv, d = X.shape
@@ -276,6 +276,58 @@ class SimplexForms:
             integrands.append(q * div_vec(u_mid) + (1 / rho_) * tau_supg * dot_vv(R, grad(q)))   # :80, :113
         args = tuple(xi) + tuple(self.Us) + tuple(self.Ps)
         self._f = sp.lambdify(args, integrands + [sp.Abs(detJ)], modules="numpy", cse=True)
+        self._args, self._phi = args, phi
+        self._u_mid, self._u_prev, self._p_sol = u_mid, u_prev, p_sol
+        self._mu, self._rho, self._h = mu_, rho_, h_
+        self._nabla_grad, self._sym = nabla_grad, sym
+
+    def facet_residual(self, U, P, lf, nrm, scale, rule, a_p=0.0, pconst=0.0, a_g=0.0, a_s=0.0, a_n=0.0, beta_n=0.0,
+                       a_b=0.0, beta_b=0.0):
+        """Fu (nv, d) of the ds terms on local facet `lf` (opposite vertex lf) with unit outward normal
+        `nrm` and physical/reference measure ratio `scale`: stabilized_schur.py:79 (a_p, a_g),
+        stabilized_schur_pressure_backflow.py:192-201 (pconst, a_n), :208-209 (pconst, a_s),
+        :214-217 (a_b).  `rule`: points on the reference facet spanned by the facet's vertices in
+        ascending local order."""
+        nv, d = self.nv, self.d
+        R_ = range(d)
+        nabla_grad, sym = self._nabla_grad, self._sym
+        n = [sp.Float(v) for v in nrm]
+        mu_, rho_, h_ = self._mu, self._rho, self._h
+        u, un, p = self._u_mid, self._u_prev, self._p_sol
+        ng = nabla_grad(u)
+        eps_u = sym(ng)
+        t_visc = [sum(2 * mu_ * eps_u[i][j] * n[j] for j in R_) for i in R_]                 # (2 mu eps(u)) n
+        un_n = sum(un[i] * n[i] for i in R_)
+        un_minus = (un_n - sp.Abs(un_n)) / 2                                                 # :215
+        u_n = sum(u[i] * n[i] for i in R_)
+        u_t = [u[i] - u_n * n[i] for i in R_]                                                # :189
+        exprs = []
+        for a in range(nv):
+            for k in R_:
+                v = [self._phi[a] if i == k else sp.Integer(0) for i in R_]
+                v_n = sum(v[i] * n[i] for i in R_)
+                v_t = [v[i] - v_n * n[i] for i in R_]
+                eps_v = sym(nabla_grad(v))
+                tv = [sum(2 * mu_ * eps_v[i][j] * n[j] for j in R_) for i in R_]
+                e = (a_p * p + pconst) * v_n                                                 # p n.v  /  p_c n.v
+                e -= a_g * sum(mu_ * sum(ng[i][j] * n[j] for j in R_) * v[i] for i in R_)    # :79
+                e -= a_s * sum(t_visc[i] * v[i] for i in R_)                                 # :209
+                e -= a_n * sum(t_visc[i] * v_t[i] for i in R_)                               # :195-196
+                e -= a_n * sum(tv[i] * u_t[i] for i in R_)                                   # :197-198
+                e += a_n * (beta_n * mu_ / h_) * sum(u_t[i] * v_t[i] for i in R_)            # :199-201
+                e -= a_b * beta_b * rho_ * un_minus * sum(u[i] * v[i] for i in R_)           # :216
+                exprs.append(e)
+        fn = sp.lambdify(self._args, exprs, modules="numpy", cse=True)
+        ref = np.vstack([np.zeros((1, d)), np.eye(d)])           # reference cell vertices
+        fverts = [v for v in range(nv) if v != lf]
+        out = np.zeros(d * nv, dtype=np.result_type(U, P))
+        pts, wts = rule
+        for pt, w in zip(pts, wts):
+            pt = np.atleast_1d(pt)
+            lam = np.concatenate([[1.0 - pt.sum()], pt])
+            xi = sum(lam[j] * ref[fverts[j]] for j in range(d))
+            out += w * scale * np.array(fn(*xi, *U.reshape(-1), *P), dtype=out.dtype)
+        return out.reshape(nv, d)
 
     def cell_residual(self, U, P, rule_u, rule_p):
         nv, d = self.nv, self.d

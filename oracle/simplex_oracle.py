@@ -159,3 +159,143 @@ def tet_gauss_jacobi(degree: int):
                 pts.append((x0, x1, x2))
                 wts.append(w2[i] * w1[j] * w0[k])
     return np.array(pts), np.array(wts)
+
+
+# --------------------------------------------------------------------------
+# exterior-facet integrals (any d): the ds terms of src/solvers/stabilized_schur.py:79 and
+# src/solvers/stabilized_schur_pressure_backflow.py:189-217, coefficients as in ns_oracle.FacetSet.
+# Local facet i is opposite local vertex i; its vertices are the remaining ones in
+# ascending local order, and the facet rule is given on the reference facet spanned by them
+# (interval [0,1]: points (m,) or (m,1); triangle {s,t >= 0, s+t <= 1}: points (m,2), weights sum 1/2).
+# --------------------------------------------------------------------------
+def facet_vertices(d):
+    return np.array([[v for v in range(d + 1) if v != i] for i in range(d + 1)])
+
+
+def facet_geometry(x, cells, pairs):
+    """Unit outward normal (m, d) and physical/reference measure ratio (m,) of the facets `pairs`
+    (m, 2) = (cell, local facet)."""
+    d = x.shape[1]
+    X = x[cells[pairs[:, 0]]]                              # (m, d+1, d)
+    m = X.shape[0]
+    ar = np.arange(m)
+    fv = facet_vertices(d)[pairs[:, 1]]                    # (m, d)
+    P0 = X[ar, fv[:, 0]]
+    if d == 2:
+        t = X[ar, fv[:, 1]] - P0
+        nrm = np.stack([t[:, 1], -t[:, 0]], axis=1)        # |nrm| = length = length / |[0,1]|
+    else:
+        nrm = np.cross(X[ar, fv[:, 1]] - P0, X[ar, fv[:, 2]] - P0)     # |nrm| = 2 area = area / (1/2)
+    scale = np.linalg.norm(nrm, axis=1)
+    nrm = nrm / scale[:, None]
+    sgn = np.sign(np.einsum("ei,ei->e", nrm, P0 - X[ar, pairs[:, 1]]))  # away from the opposite vertex
+    return nrm * sgn[:, None], scale
+
+
+def _facet_phi(d, lf, pt):
+    """(m, d+1) cell basis at the reference-facet point `pt` of the local facets lf (m,)."""
+    pt = np.atleast_1d(np.asarray(pt, dtype=np.float64))
+    lam = np.concatenate([[1.0 - pt.sum()], pt])           # barycentric on the facet's own vertices
+    fv = facet_vertices(d)[lf]
+    phi = np.zeros((len(lf), d + 1))
+    for j in range(d):
+        phi[np.arange(len(lf)), fv[:, j]] = lam[j]
+    return phi
+
+
+def facet_F(x, cells, h, pairs, coef, U, P, Un, facet_rule, rho, mu, theta=0.5):
+    """Fu (m, d+1, d) of one facet set; U, Un (m, d+1, d), P (m, d+1) are the nodal values of the
+    cells pairs[:, 0].  `coef`: object with a_p, pconst, a_g, a_s, a_n, beta_n, a_b, beta_b."""
+    d = x.shape[1]
+    _, dphi_all = simplex_geometry(x, cells)
+    dphi = dphi_all[pairs[:, 0]]
+    hh = h[pairs[:, 0]]
+    nrm, scale = facet_geometry(x, cells, pairs)
+    Um = theta * U + (1.0 - theta) * Un
+    G = np.einsum("eai,eaj->eij", dphi, Um)                # d_i u_mj = nabla_grad(u_m)
+    eps = 0.5 * (G + np.swapaxes(G, 1, 2))
+    Gn = np.einsum("eij,ej->ei", G, nrm)                   # dot(nabla_grad(u_m), n)   (:79)
+    en = np.einsum("eij,ej->ei", eps, nrm)
+    I = np.eye(d)
+    Pn = I[None] - nrm[:, :, None] * nrm[:, None, :]
+    dn = np.einsum("eai,ei->ea", dphi, nrm)
+    epsv_n = 0.5 * (np.einsum("eai,ek->eaki", dphi, nrm) + dn[:, :, None, None] * I[None, None])
+    Fu = np.zeros(U.shape, dtype=np.result_type(U, P))
+    pts, wts = facet_rule
+    for q in range(len(wts)):
+        phi = _facet_phi(d, pairs[:, 1], pts[q])
+        w = wts[q] * scale
+        um = np.einsum("ea,eai->ei", phi, Um)
+        un = np.einsum("ea,eai->ei", phi, Un).real
+        p = np.einsum("ea,ea->e", phi, P)
+        umT = np.einsum("eij,ej->ei", Pn, um)
+        val = (coef.a_p * p + coef.pconst)[:, None, None] * phi[:, :, None] * nrm[:, None, :]
+        val = val - coef.a_g * mu * phi[:, :, None] * Gn[:, None, :]
+        val = val - coef.a_s * 2.0 * mu * phi[:, :, None] * en[:, None, :]
+        if coef.a_n != 0.0:
+            enT = np.einsum("eik,ei->ek", Pn, en)
+            val = val - coef.a_n * 2.0 * mu * phi[:, :, None] * enT[:, None, :]
+            val = val - coef.a_n * 2.0 * mu * np.einsum("eaki,ei->eak", epsv_n, umT)
+            val = val + coef.a_n * (coef.beta_n * mu / hh)[:, None, None] * phi[:, :, None] * umT[:, None, :]
+        if coef.a_b != 0.0:
+            unn = np.einsum("ei,ei->e", un, nrm)
+            un_minus = 0.5 * (unn - np.abs(unn))
+            val = val - coef.a_b * coef.beta_b * rho * un_minus[:, None, None] * phi[:, :, None] * um[:, None, :]
+        Fu = Fu + w[:, None, None] * val
+    return Fu
+
+
+def facet_J(x, cells, h, pairs, coef, Un, facet_rule, rho, mu, theta=0.5):
+    """(m, d(d+1), (d+1)(d+1)) derivative of facet_F with respect to (U flattened, then P): the facet
+    terms are affine in (U, P), so unit vectors give it exactly."""
+    d = x.shape[1]
+    nv = d + 1
+    m = pairs.shape[0]
+    Z2, Z1 = np.zeros((m, nv, d)), np.zeros((m, nv))
+    F0 = facet_F(x, cells, h, pairs, coef, Z2, Z1, Un, facet_rule, rho, mu, theta)
+    out = np.zeros((m, d * nv, (d + 1) * nv))
+    for j in range((d + 1) * nv):
+        U, P = Z2.copy(), Z1.copy()
+        if j < d * nv:
+            U[:, j // d, j % d] = 1.0
+        else:
+            P[:, j - d * nv] = 1.0
+        out[:, :, j] = (facet_F(x, cells, h, pairs, coef, U, P, Un, facet_rule, rho, mu, theta) - F0).reshape(m, d * nv)
+    return out
+
+
+def outlet_flux(x, cells, pairs, un_nodal):
+    """Q = int u_prev . n ds over the facets (pressure_backflow.py:204-211, 383-385); exact for P1:
+    facet measure times the mean of the facet's nodal values."""
+    d = x.shape[1]
+    nrm, scale = facet_geometry(x, cells, pairs)
+    measure = scale * (1.0 if d == 2 else 0.5)
+    Uc = un_nodal.reshape(-1, d)[cells[pairs[:, 0]]]
+    fv = facet_vertices(d)[pairs[:, 1]]
+    ar = np.arange(pairs.shape[0])
+    mean = sum(Uc[ar, fv[:, j]] for j in range(d)) / d
+    return float(np.sum(np.einsum("ei,ei->e", mean, nrm) * measure))
+
+
+def exterior_facets(cells):
+    """(m, 2) (cell, local facet) pairs of the facets attached to exactly one cell
+    (dolfinx.mesh.exterior_facet_indices + compute_integration_domains), sorted by (cell, facet)."""
+    E, nv = cells.shape
+    d = nv - 1
+    fv = facet_vertices(d)
+    keys = np.sort(cells[:, fv], axis=2).reshape(E * nv, d)               # (E*nv, d) sorted vertex tuples
+    _, inv, cnt = np.unique(keys, axis=0, return_inverse=True, return_counts=True)
+    ext = np.nonzero(cnt[inv.reshape(-1)] == 1)[0]
+    return np.stack([ext // nv, ext % nv], axis=1).astype(np.int32)
+
+
+def triangle_facet_rule(degree=2):
+    """Symmetric rules on the reference triangle for the tetrahedron's facets (weights sum 1/2):
+    degree 2 -> 3 interior points, degree 3/4 -> 6 points (Dunavant)."""
+    if degree <= 2:
+        pts = np.array([[1 / 6, 1 / 6], [2 / 3, 1 / 6], [1 / 6, 2 / 3]])
+        return pts, np.full(3, 1 / 6)
+    a, b = 0.445948490915965, 0.091576213509771
+    wa, wb = 0.223381589678011, 0.109951743655322
+    pts = np.array([[a, a], [1 - 2 * a, a], [a, 1 - 2 * a], [b, b], [1 - 2 * b, b], [b, 1 - 2 * b]])
+    return pts, 0.5 * np.array([wa, wa, wa, wb, wb, wb])
