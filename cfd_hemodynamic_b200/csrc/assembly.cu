@@ -914,6 +914,12 @@ extern "C" int hemo_set_cell_type(hemo_ctx* ctx, int cell_type) {
     }
     ctx->have_bc = false;
     ctx->amg[0].ready = ctx->amg[1].ready = false;
+    // preconditioner work vectors are sized by (dim, n): reallocated by the next hemo_pc_setup
+    cudaFree(ctx->pc_tmp_u); cudaFree(ctx->pc_tmp_u2); cudaFree(ctx->pc_tmp_p); cudaFree(ctx->pc_tmp_p2);
+    cudaFree(ctx->pc_in); cudaFree(ctx->pc_out); cudaFree(ctx->a01);
+    ctx->pc_tmp_u = ctx->pc_tmp_u2 = ctx->pc_tmp_p = ctx->pc_tmp_p2 = ctx->pc_in = ctx->pc_out = nullptr;
+    ctx->a01 = nullptr;
+    if (ctx->pc_graph_exec) { cudaGraphExecDestroy(ctx->pc_graph_exec); ctx->pc_graph_exec = nullptr; }
     return 0;
 }
 
@@ -930,8 +936,9 @@ extern "C" int hemo_set_mesh(hemo_ctx* ctx, const double* x_dev, int n_nodes, co
     cudaFree(ctx->Ae); cudaFree(ctx->Fe);
     ctx->Ae = ctx->Fe = nullptr;
     ctx->Ae_count = ctx->Fe_count = 0;
-    if ((rc = hemo_alloc(ctx, &ctx->dvec, (size_t)3 * n_nodes))) return rc;
-    HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->dvec, 0, sizeof(double) * 3 * n_nodes, ctx->stream));
+    const size_t ndof = (size_t)(ctx->dim + 1) * n_nodes;
+    if ((rc = hemo_alloc(ctx, &ctx->dvec, ndof))) return rc;
+    HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->dvec, 0, sizeof(double) * ndof, ctx->stream));
     return 0;
 }
 
@@ -1072,7 +1079,9 @@ extern "C" int hemo_set_quadrature(hemo_ctx* ctx, int block, const double* pts, 
 }
 
 extern "C" int hemo_set_facet_quadrature(hemo_ctx* ctx, const double* pts, const double* wts, int nq) {
-    if (!ctx || !pts || !wts || nq <= 0 || nq > HEMO_MAXFQ) return HEMO_EINVAL;
+    if (!ctx || !pts || !wts || nq <= 0) return HEMO_EINVAL;
+    if (ctx->dim == 3) return hemo_tet_set_facet_quadrature(ctx, pts, wts, nq);   // (s, t) pairs on the reference triangle
+    if (nq > HEMO_MAXFQ) return HEMO_EINVAL;
     ctx->frule.nq = nq;
     for (int q = 0; q < nq; ++q) { ctx->frule.s[q] = pts[q]; ctx->frule.w[q] = wts[q]; }
     ctx->rules_dirty = true;
@@ -1136,15 +1145,15 @@ extern "C" int hemo_set_bc(hemo_ctx* ctx, const uint8_t* dofflag_dev, const doub
                            const uint8_t* cellflag_dev) {
     if (!ctx) return HEMO_EINVAL;
     if (!ctx->cells) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_set_mesh must precede hemo_set_bc");
-    if (ctx->dim == 3 && dofflag_dev) HEMO_FAIL(ctx, HEMO_ESTATE, "Dirichlet conditions are not implemented for tetrahedra yet");
     if (!dofflag_dev) {
         ctx->have_bc = false;
         return 0;
     }
     if (!dofmult_dev || !cellflag_dev) return HEMO_EINVAL;
     int rc;
-    if ((rc = hemo_upload(ctx, &ctx->dofflag, dofflag_dev, (size_t)3 * ctx->n, true))) return rc;
-    if ((rc = hemo_upload(ctx, &ctx->dofmult, dofmult_dev, (size_t)3 * ctx->n, true))) return rc;
+    const size_t ndof = (size_t)(ctx->dim + 1) * ctx->n;       // [u (dim n) | p (n)]
+    if ((rc = hemo_upload(ctx, &ctx->dofflag, dofflag_dev, ndof, true))) return rc;
+    if ((rc = hemo_upload(ctx, &ctx->dofmult, dofmult_dev, ndof, true))) return rc;
     if ((rc = hemo_upload(ctx, &ctx->cellflag, cellflag_dev, (size_t)ctx->E, true))) return rc;
     ctx->have_bc = true;
     return 0;
@@ -1219,7 +1228,7 @@ extern "C" int hemo_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const 
 extern "C" int hemo_assemble_residual(hemo_ctx* ctx, const double* x_dev, const double* un_dev,
                                       const double* g_dev, double* b_dev) {
     if (!ctx || !x_dev || !un_dev || !b_dev) return HEMO_EINVAL;
-    if (ctx->dim == 3) return hemo_tet_assemble_residual(ctx, x_dev, un_dev, b_dev);
+    if (ctx->dim == 3) return hemo_tet_assemble_residual(ctx, x_dev, un_dev, g_dev, b_dev);
     if (ctx->have_bc && !g_dev) return HEMO_EINVAL;
     int rc = check_ready(ctx);
     if (rc) return rc;
@@ -1261,11 +1270,12 @@ extern "C" int hemo_outlet_flux(hemo_ctx* ctx, int set_id, const double* un_dev,
     if (!ctx || set_id < 0 || set_id >= HEMO_MAX_FACET_SETS || !un_dev || !q_host) return HEMO_EINVAL;
     const HemoFacetSet& fs = ctx->fsets[set_id];
     if (fs.m == 0) { *q_host = 0.0; return 0; }
-    if (ctx->dim == 3) HEMO_FAIL(ctx, HEMO_ESTATE, "facet integrals are not implemented for tetrahedra yet");
     int rc = hemo_ensure_reduce(ctx, (size_t)fs.m, 8);
     if (rc) return rc;
     cudaStream_t st = ctx->stream;
-    if (ctx->nv == 4) {
+    if (ctx->dim == 3) {
+        if ((rc = hemo_tet_facet_flux(ctx, fs, un_dev, ctx->red_partial))) return rc;
+    } else if (ctx->nv == 4) {
         if ((rc = hemo_q1_facet_flux(ctx, fs, un_dev, ctx->red_partial))) return rc;
     } else {
         k_facet_flux<<<hemo_grid(fs.m, 128), 128, 0, st>>>(fs.m, fs.cells, fs.mask, ctx->cells, ctx->x, un_dev, ctx->red_partial);
@@ -1282,13 +1292,14 @@ extern "C" int hemo_outlet_flux(hemo_ctx* ctx, int set_id, const double* un_dev,
 extern "C" int hemo_assemble_laplace_mass(hemo_ctx* ctx, double* lap_vals_dev, double* mass_dev) {
     if (!ctx || !lap_vals_dev || !mass_dev) return HEMO_EINVAL;
     if (!ctx->cells || !ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / node graph not set");
-    if (ctx->dim == 3) HEMO_FAIL(ctx, HEMO_ESTATE, "the Schur-approximation operators are not implemented for tetrahedra yet");
     const int E = ctx->E, n = ctx->n, nv = ctx->nv;
     int rc;
     if ((rc = ensure_elem(ctx, (size_t)nv * nv * E, (size_t)nv * E))) return rc;
     cudaStream_t st = ctx->stream;
     // reuse the element buffers: Ke -> Ae[0..nv*nv*E), Me -> Fe[0..nv*E)
-    if (nv == 4) {
+    if (ctx->dim == 3) {
+        if ((rc = hemo_tet_laplace_mass(ctx))) return rc;
+    } else if (nv == 4) {
         if ((rc = hemo_q1_laplace_mass(ctx))) return rc;
     } else {
         k_cell_laplace<<<hemo_grid(E, 256), 256, 0, st>>>(E, ctx->cells, ctx->x, ctx->Ae, ctx->Fe);
@@ -1400,6 +1411,7 @@ k_selfp(int64_t nnz2, int64_t nnz_node, const int32_t* __restrict__ rowof2, cons
 
 extern "C" int hemo_pc_set_schur_selfp(hemo_ctx* ctx, const double* vals_dev, double coarse_shift) {
     if (!ctx || !vals_dev) return HEMO_EINVAL;
+    HEMO_2D_ONLY(ctx, "the SELFP Schur approximation");
     HemoAmg& amg = ctx->amg[1];
     if (!amg.ready || !amg.fine_rowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "pressure hierarchy needs the distance-2 fine pattern");
     k_selfp<<<hemo_grid(amg.fine_nnz, 256), 256, 0, ctx->stream>>>(amg.fine_nnz, ctx->nnz_node, amg.fine_rowof, amg.fine_col,
@@ -1421,7 +1433,7 @@ extern "C" int hemo_pc_set_schur_operator(hemo_ctx* ctx, const double* x_dev, co
     if (!ctx || !x_dev || !un_dev || !vals_dev) return HEMO_EINVAL;
     if (!ctx->cells || !ctx->nrowptr || !ctx->have_par) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / node graph / params not set");
     if (!ctx->amg[1].ready) HEMO_FAIL(ctx, HEMO_ESTATE, "pressure AMG hierarchy not finalized");
-    if (ctx->nv != 3) HEMO_FAIL(ctx, HEMO_ESTATE, "the assembled Schur operator is implemented for triangles only");
+    if (ctx->nv != 3 || ctx->dim != 2) HEMO_FAIL(ctx, HEMO_ESTATE, "the assembled Schur operator is implemented for triangles only");
     const int E = ctx->E, n = ctx->n;
     int rc;
     if ((rc = ensure_elem(ctx, (size_t)9 * E, 0))) return rc;
@@ -1444,6 +1456,7 @@ extern "C" int hemo_pc_set_convection(hemo_ctx* ctx, const double* x_dev, const 
     if (!ctx) return HEMO_EINVAL;
     ctx->npconv_coef = coef;
     if (coef == 0.0) return 0;
+    HEMO_2D_ONLY(ctx, "the pressure convection term");
     if (!x_dev || !un_dev) return HEMO_EINVAL;
     if (!ctx->cells || !ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / node graph not set");
     if (ctx->nv != 3) HEMO_FAIL(ctx, HEMO_ESTATE, "the pressure convection term is implemented for triangles only");

@@ -4,9 +4,11 @@
 //
 // Replaces the FFCx tetrahedron `tabulate_tensor` kernels of the forms at
 // src/solvers/stabilized_schur.py:60-123 (reached through `mesh.topology.cell_name()`, e.g.
-// src/scenarios/taylor_green.py:34).  Scope of this first 3-D piece: the batched element tensors
-// (north star, subsystem 1); scattering them into a 4x4-node-block CSR and the 3-D Krylov /
-// multigrid kernels are the follow-up, so there is no 3-D solve yet.
+// src/scenarios/taylor_green.py:34), followed by the exterior-facet terms on triangular facets,
+// the Dirichlet treatment (lifting, zeroed rows / columns, set_bc), the atomic-free gather into the
+// reference's CSR layout and the matrix-vector product on that layout.  The per-thread bodies of
+// everything after the cell kernel live in tet_items.cuh (host-checkable).  The 3-D multigrid
+// preconditioner is the follow-up.
 //
 // One thread per cell.  The rule tables (up to 7^3 collapsed Gauss–Jacobi points per block form,
 // 13.7 kB each) do not fit constant memory and live in global memory: every thread of a warp reads
@@ -14,6 +16,7 @@
 // (alias table from the host) are integrated once.
 #include "hemo_internal.cuh"
 #include "simplex_element.cuh"
+#include "tet_items.cuh"
 
 struct TetRules {
     SimplexRule<3> r[HEMO_NRULES];
@@ -23,6 +26,10 @@ struct TetRules {
 struct hemo_tet_state {
     TetRules* host = nullptr;
     TetRules* dev = nullptr;
+    SimplexFacetRule<3> frule{};     // triangle rule of the exterior-facet integrals (kernel argument)
+    bool have_frule = false;
+    double* dinv = nullptr;          // 9n: inverse 3x3 node-diagonal blocks of A00 (block-Jacobi sweeps of the PC)
+    int dinv_n = 0;
     bool have[HEMO_NRULES] = {false, false, false, false, false, false};
     bool dirty = true;
 };
@@ -199,9 +206,7 @@ extern "C" int hemo_tet_element_tensors(hemo_ctx* ctx, int n_nodes, int n_cells,
 // ---------------------------------------------------------------------------
 // 3-D assembly into the CSR the reference's create_matrix_block builds for P1-P1 tetrahedra
 // (src/solvers/stabilized_schur.py:191-193): global vector [u interleaved (3n) | p (n)], rows in
-// that order, columns ascending.  With B = 4 scalars per node, deg = #neighbours of node i and
-// r0 = nrowptr[i]: row 3i+k starts at 12*r0 + 4*k*deg, row 3n+i at 12*nnz_node + 4*r0; inside a row
-// the u-columns of neighbour t sit at 3t..3t+2 and its p-column at 3*deg + t.
+// that order, columns ascending; layout formulas in tet_items.cuh.
 // Same atomic-free gather as the 2-D path (fixed summation order), 16 scalars per node pair.
 // ---------------------------------------------------------------------------
 int hemo_ensure_elem(hemo_ctx* ctx, size_t ae_count, size_t fe_count);
@@ -227,52 +232,81 @@ __global__ void k_pattern3d(int n, int64_t nnz_node, const int32_t* __restrict__
     }
 }
 
+__global__ void __launch_bounds__(128)
+k_tet_facets(int m, int64_t E, int n, const int32_t* __restrict__ fcells, const int32_t* __restrict__ fmask,
+             hemo_facet_coef co, SimplexFacetRule<3> fr, const int32_t* __restrict__ cells,
+             const double* __restrict__ x, const double* __restrict__ h, const double* __restrict__ sol,
+             const double* __restrict__ un, HemoForm par, bool want_jac, double* __restrict__ Ae,
+             double* __restrict__ Fe) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    tet_facet_item(t, E, n, fcells, fmask, co, fr, cells, x, h, sol, un, par, want_jac, Ae, Fe);
+}
+
+__global__ void __launch_bounds__(128)
+k_tet_facet_flux(int m, int n, const int32_t* __restrict__ fcells, const int32_t* __restrict__ fmask,
+                 const int32_t* __restrict__ cells, const double* __restrict__ x, const double* __restrict__ un,
+                 double* __restrict__ partial) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    partial[t] = tet_flux_item(t, n, fcells, fmask, cells, x, un);
+}
+
+__global__ void __launch_bounds__(128)
+k_tet_lift(int64_t E, int n, const int32_t* __restrict__ cells, const uint8_t* __restrict__ cellflag,
+           const double* __restrict__ dvec, const double* __restrict__ Ae, double* __restrict__ Fe) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= E || !cellflag[c]) return;
+    tet_lift_item(c, E, n, cells, dvec, Ae, Fe);
+}
+
+__global__ void k_tet_lift_vector(int64_t N, const uint8_t* __restrict__ dofflag, const double* __restrict__ x,
+                                  const double* __restrict__ g, double* __restrict__ d) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    d[i] = dofflag[i] ? (g[i] - x[i]) : 0.0;
+}
+
 __global__ void __launch_bounds__(256)
 k_gather_matrix3d(int n, int64_t nnz_node, int64_t E, const int32_t* __restrict__ nrowptr,
-                  const int32_t* __restrict__ rowof, const int32_t* __restrict__ seg_ptr,
-                  const int32_t* __restrict__ seg_src, const double* __restrict__ Ae, double* __restrict__ vals) {
+                  const int32_t* __restrict__ ncol, const int32_t* __restrict__ rowof,
+                  const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_src,
+                  const double* __restrict__ Ae, const uint8_t* __restrict__ dofflag,
+                  const double* __restrict__ dofmult, double* __restrict__ vals) {
     const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nnz_node) return;
-    const int i = rowof[s];
-    double acc[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) acc[k] = 0.0;
-    for (int t = seg_ptr[s]; t < seg_ptr[s + 1]; ++t) {
-        const int src = seg_src[t];
-        const int64_t c = src / 16;
-        const int ab = src - (int)c * 16;
-        const double* p = Ae + (int64_t)ab * 16 * E + c;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) acc[k] += p[k * E];
-    }
-    const int r0 = nrowptr[i];
-    const int deg = nrowptr[i + 1] - r0;
-    const int tpos = (int)(s - r0);
-#pragma unroll
-    for (int ri = 0; ri < 4; ++ri) {
-        const int64_t rs = (ri < 3) ? 12 * (int64_t)r0 + 4 * (int64_t)ri * deg : 12 * nnz_node + 4 * (int64_t)r0;
-        vals[rs + 3 * tpos] = acc[ri * 4 + 0];
-        vals[rs + 3 * tpos + 1] = acc[ri * 4 + 1];
-        vals[rs + 3 * tpos + 2] = acc[ri * 4 + 2];
-        vals[rs + 3 * deg + tpos] = acc[ri * 4 + 3];
-    }
+    tet_gather_matrix_item(s, n, nnz_node, E, nrowptr, ncol, rowof, seg_ptr, seg_src, Ae, dofflag, dofmult, vals);
 }
 
 __global__ void __launch_bounds__(256)
 k_gather_vector3d(int n, int64_t E, const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_src,
-                  const double* __restrict__ Fe, double* __restrict__ b) {
+                  const double* __restrict__ Fe, const uint8_t* __restrict__ dofflag, const double* __restrict__ xk,
+                  const double* __restrict__ g, double* __restrict__ b) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double a[4] = {0, 0, 0, 0};
-    for (int t = seg_ptr[i]; t < seg_ptr[i + 1]; ++t) {
-        const int src = seg_src[t];
-        const int64_t c = src / 4;
-        const int la = src - (int)c * 4;
+    tet_gather_vector_item(i, n, E, seg_ptr, seg_src, Fe, dofflag, xk, g, b);
+}
+
+// y = J x on the 3-D CSR layout: 8 lanes per node (4 rows each), shuffle reduction, lane 0 stores.
+// HBM-bound: 16 values (128 B) + one column index per node pair, four x entries per neighbour.
+__global__ void __launch_bounds__(256)
+k_spmv_node3d(int n, int64_t nnz_node, const int32_t* __restrict__ nrowptr, const int32_t* __restrict__ ncol,
+              const double* __restrict__ vals, const double* __restrict__ xv, double* __restrict__ y) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt >> 3;
+    const int lane = gt & 7;
+    const bool ok = i < n;            // no early return: full-mask shuffles below
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (ok) tet_spmv_item(i, lane, 8, n, nnz_node, nrowptr, ncol, vals, xv, acc);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) a[k] += Fe[(la * 4 + k) * E + c];
+    for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o, 8);
     }
-    b[3 * (int64_t)i] = a[0]; b[3 * (int64_t)i + 1] = a[1]; b[3 * (int64_t)i + 2] = a[2];
-    b[3 * (int64_t)n + i] = a[3];
+    if (ok && lane == 0) {
+        y[3 * (int64_t)i] = acc[0]; y[3 * (int64_t)i + 1] = acc[1]; y[3 * (int64_t)i + 2] = acc[2];
+        y[3 * (int64_t)n + i] = acc[3];
+    }
 }
 
 int hemo_tet_pattern(hemo_ctx* ctx, int64_t* rowptr_dev, int32_t* colind_dev) {
@@ -282,30 +316,161 @@ int hemo_tet_pattern(hemo_ctx* ctx, int64_t* rowptr_dev, int32_t* colind_dev) {
     return 0;
 }
 
-static int tet_cells(hemo_ctx* ctx, const double* x_dev, const double* un_dev) {
+int hemo_tet_set_facet_quadrature(hemo_ctx* ctx, const double* pts, const double* wts, int nq) {
+    if (nq > HEMO_SIMPLEX_MAXFQ) HEMO_FAIL(ctx, HEMO_EINVAL, "too many points for a triangular facet rule");
+    hemo_tet_state* st = tet_state(ctx);
+    simplex_facet_rule_set<3>(st->frule, pts, wts, nq);
+    st->have_frule = true;
+    return 0;
+}
+
+static bool tet_facet_set_active(const HemoFacetSet& fs) {
+    const hemo_facet_coef& c = fs.coef;
+    return fs.m > 0 && (c.a_p != 0.0 || c.pconst != 0.0 || c.a_g != 0.0 || c.a_s != 0.0 || c.a_n != 0.0 || c.a_b != 0.0);
+}
+
+// cell tensors (Jacobian + residual in one pass), then the facet terms of every active set
+static int tet_cells(hemo_ctx* ctx, const double* x_dev, const double* un_dev, bool facet_jac) {
     if (!ctx->cells || !ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / node graph not set");
     int rc = hemo_ensure_elem(ctx, (size_t)256 * ctx->E, (size_t)16 * ctx->E);
     if (rc) return rc;
     const double f3[3] = {ctx->par.f[0], ctx->par.f[1], ctx->fz};
-    return hemo_tet_element_tensors(ctx, ctx->n, ctx->E, ctx->x, ctx->cells, ctx->h, x_dev, un_dev, ctx->uh, f3, ctx->Ae,
-                                    ctx->Fe);
+    if ((rc = hemo_tet_element_tensors(ctx, ctx->n, ctx->E, ctx->x, ctx->cells, ctx->h, x_dev, un_dev, ctx->uh, f3,
+                                       ctx->Ae, ctx->Fe)))
+        return rc;
+    hemo_tet_state* st = tet_state(ctx);
+    for (int s = 0; s < HEMO_MAX_FACET_SETS; ++s) {
+        const HemoFacetSet& fs = ctx->fsets[s];
+        if (!tet_facet_set_active(fs)) continue;
+        if (!st->have_frule) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_set_facet_quadrature not called (triangle rule)");
+        k_tet_facets<<<hemo_grid(fs.m, 128), 128, 0, ctx->stream>>>(fs.m, ctx->E, ctx->n, fs.cells, fs.mask, fs.coef,
+                                                                    st->frule, ctx->cells, ctx->x, ctx->h, x_dev, un_dev,
+                                                                    ctx->par, facet_jac, ctx->Ae, ctx->Fe);
+        HEMO_LAUNCH_CHECK(ctx);
+    }
+    return 0;
 }
 
 int hemo_tet_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const double* un_dev, double* vals_dev) {
-    int rc = tet_cells(ctx, x_dev, un_dev);
+    int rc = tet_cells(ctx, x_dev, un_dev, true);
     if (rc) return rc;
     k_gather_matrix3d<<<hemo_grid(ctx->nnz_node, 256), 256, 0, ctx->stream>>>(
-        ctx->n, ctx->nnz_node, ctx->E, ctx->nrowptr, ctx->rowof, ctx->mseg_ptr, ctx->mseg_src, ctx->Ae, vals_dev);
+        ctx->n, ctx->nnz_node, ctx->E, ctx->nrowptr, ctx->ncol, ctx->rowof, ctx->mseg_ptr, ctx->mseg_src, ctx->Ae,
+        ctx->have_bc ? ctx->dofflag : nullptr, ctx->dofmult, vals_dev);
     HEMO_LAUNCH_CHECK(ctx);
     return 0;
 }
 
-int hemo_tet_assemble_residual(hemo_ctx* ctx, const double* x_dev, const double* un_dev, double* b_dev) {
-    int rc = tet_cells(ctx, x_dev, un_dev);
+int hemo_tet_assemble_residual(hemo_ctx* ctx, const double* x_dev, const double* un_dev, const double* g_dev,
+                               double* b_dev) {
+    if (ctx->have_bc && !g_dev) return HEMO_EINVAL;
+    int rc = tet_cells(ctx, x_dev, un_dev, ctx->have_bc);
     if (rc) return rc;
-    k_gather_vector3d<<<hemo_grid(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->E, ctx->vseg_ptr, ctx->vseg_src,
-                                                                       ctx->Fe, b_dev);
+    cudaStream_t st = ctx->stream;
+    if (ctx->have_bc) {
+        const int64_t N = 4 * (int64_t)ctx->n;
+        k_tet_lift_vector<<<hemo_grid(N, 256), 256, 0, st>>>(N, ctx->dofflag, x_dev, g_dev, ctx->dvec);
+        HEMO_LAUNCH_CHECK(ctx);
+        k_tet_lift<<<hemo_grid(ctx->E, 128), 128, 0, st>>>(ctx->E, ctx->n, ctx->cells, ctx->cellflag, ctx->dvec, ctx->Ae,
+                                                           ctx->Fe);
+        HEMO_LAUNCH_CHECK(ctx);
+    }
+    k_gather_vector3d<<<hemo_grid(ctx->n, 256), 256, 0, st>>>(ctx->n, ctx->E, ctx->vseg_ptr, ctx->vseg_src, ctx->Fe,
+                                                              ctx->have_bc ? ctx->dofflag : nullptr, x_dev, g_dev, b_dev);
     HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int hemo_tet_spmv(hemo_ctx* ctx, const double* vals_dev, const double* x_dev, double* y_dev) {
+    k_spmv_node3d<<<hemo_grid(8 * (int64_t)ctx->n, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->nnz_node, ctx->nrowptr,
+                                                                                ctx->ncol, vals_dev, x_dev, y_dev);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int hemo_tet_facet_flux(hemo_ctx* ctx, const HemoFacetSet& fs, const double* un_dev, double* partial) {
+    k_tet_facet_flux<<<hemo_grid(fs.m, 128), 128, 0, ctx->stream>>>(fs.m, ctx->n, fs.cells, fs.mask, ctx->cells, ctx->x,
+                                                                    un_dev, partial);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+__global__ void k_tet_cell_laplace(int64_t E, const int32_t* __restrict__ cells, const double* __restrict__ x,
+                                   double* __restrict__ Ke, double* __restrict__ Me) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= E) return;
+    tet_laplace_item(c, E, cells, x, Ke, Me);
+}
+
+// element stiffness / lumped mass into Ae[0..16E) / Fe[0..4E) (gathered by the generic scalar kernels)
+int hemo_tet_laplace_mass(hemo_ctx* ctx) {
+    k_tet_cell_laplace<<<hemo_grid(ctx->E, 256), 256, 0, ctx->stream>>>(ctx->E, ctx->cells, ctx->x, ctx->Ae, ctx->Fe);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// 3-D preconditioner kernels (bodies in tet_items.cuh)
+// ---------------------------------------------------------------------------
+__global__ void k_tet_dinv(int n, int64_t nnz_node, const int32_t* __restrict__ nrowptr,
+                           const int32_t* __restrict__ diagslot, const double* __restrict__ vals,
+                           double* __restrict__ dinv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    tet_dinv_item(i, n, nnz_node, nrowptr, diagslot, vals, dinv);
+}
+
+__global__ void k_tet_a01_residual(int n, int64_t nnz_node, const int32_t* __restrict__ nrowptr,
+                                   const int32_t* __restrict__ ncol, const double* __restrict__ vals,
+                                   const double* __restrict__ zp, const double* __restrict__ ru,
+                                   double* __restrict__ tu) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    tet_a01_residual_item(i, n, nnz_node, nrowptr, ncol, vals, zp, ru, tu);
+}
+
+__global__ void k_tet_jacobi(int n, int64_t nnz_node, const int32_t* __restrict__ nrowptr,
+                             const int32_t* __restrict__ ncol, const double* __restrict__ vals,
+                             const double* __restrict__ dinv, double omega, const double* __restrict__ tu,
+                             const double* zin, double* zout) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    tet_jacobi_item(i, n, nnz_node, nrowptr, ncol, vals, dinv, omega, tu, zin, zout);
+}
+
+int hemo_tet_pc_setup(hemo_ctx* ctx, const double* vals_dev) {
+    hemo_tet_state* st = tet_state(ctx);
+    int rc;
+    if (!st->dinv || st->dinv_n != ctx->n) {
+        if ((rc = hemo_alloc(ctx, &st->dinv, (size_t)9 * ctx->n))) return rc;
+        st->dinv_n = ctx->n;
+    }
+    k_tet_dinv<<<hemo_grid(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->nnz_node, ctx->nrowptr, ctx->diagslot,
+                                                                vals_dev, st->dinv);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// t_u = r_u - A01 z_p, then `sweeps` damped block-Jacobi sweeps on A00 z_u = t_u from z_u = 0.
+// tmp: 3n scratch (ping-pong partner of zu); the last sweep always lands in zu.
+int hemo_tet_velocity_solve(hemo_ctx* ctx, const double* vals_dev, const double* ru, const double* zp, double* tu,
+                            double* tmp, double* zu, int sweeps, double omega) {
+    hemo_tet_state* st = tet_state(ctx);
+    if (!st->dinv) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_pc_setup not called");
+    const int n = ctx->n;
+    const int grid = hemo_grid(n, 256);
+    k_tet_a01_residual<<<grid, 256, 0, ctx->stream>>>(n, ctx->nnz_node, ctx->nrowptr, ctx->ncol, vals_dev, zp, ru, tu);
+    HEMO_LAUNCH_CHECK(ctx);
+    if (sweeps < 1) sweeps = 1;
+    // sweep s writes buf[(sweeps - 1 - s) & 1] with buf[0] = zu, so that the final sweep writes zu
+    const double* zin = nullptr;
+    for (int s = 0; s < sweeps; ++s) {
+        double* zout = ((sweeps - 1 - s) & 1) ? tmp : zu;
+        k_tet_jacobi<<<grid, 256, 0, ctx->stream>>>(n, ctx->nnz_node, ctx->nrowptr, ctx->ncol, vals_dev, st->dinv, omega, tu,
+                                                    zin, zout);
+        HEMO_LAUNCH_CHECK(ctx);
+        zin = zout;
+    }
     return 0;
 }
 
@@ -313,6 +478,7 @@ void hemo_tet_free(hemo_ctx* ctx) {
     if (!ctx->tet) return;
     free(ctx->tet->host);
     cudaFree(ctx->tet->dev);
+    cudaFree(ctx->tet->dinv);
     delete ctx->tet;
     ctx->tet = nullptr;
 }

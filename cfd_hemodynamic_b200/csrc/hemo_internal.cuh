@@ -128,7 +128,7 @@ struct hemo_ctx {
 
     // mesh (borrowed)
     int nv = 3;                     // nodes per cell: 3 = P1 triangle, 4 = Q1 quadrilateral (tensor-ordered) | P1 tetrahedron
-    int dim = 2;                    // geometric dimension: 3 only for tetrahedra (assembly into CSR; no 3-D solve yet)
+    int dim = 2;                    // geometric dimension: 3 only for tetrahedra (assembly, Dirichlet rows, SpMV; no 3-D preconditioner yet)
     double fz = 0.0;                // third component of the body force (hemo_set_body_force3)
     const double* x = nullptr;
     const int32_t* cells = nullptr;
@@ -219,6 +219,12 @@ struct hemo_ctx {
         return (code);             \
     } while (0)
 
+// entry points that only exist for the 2-D cell types fail loudly on tetrahedra
+#define HEMO_2D_ONLY(ctx, what)                                                                      \
+    do {                                                                                             \
+        if ((ctx)->dim == 3) HEMO_FAIL(ctx, HEMO_ESTATE, what " is not implemented for tetrahedra yet"); \
+    } while (0)
+
 #define HEMO_LAUNCH_CHECK(ctx)                                       \
     do {                                                             \
         (ctx)->launches++;                                           \
@@ -279,7 +285,15 @@ int hemo_q1_laplace_mass(hemo_ctx* ctx);
 void hemo_tet_free(hemo_ctx* ctx);
 int hemo_tet_pattern(hemo_ctx* ctx, int64_t* rowptr_dev, int32_t* colind_dev);
 int hemo_tet_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const double* un_dev, double* vals_dev);
-int hemo_tet_assemble_residual(hemo_ctx* ctx, const double* x_dev, const double* un_dev, double* b_dev);
+int hemo_tet_assemble_residual(hemo_ctx* ctx, const double* x_dev, const double* un_dev, const double* g_dev,
+                               double* b_dev);
+int hemo_tet_set_facet_quadrature(hemo_ctx* ctx, const double* pts, const double* wts, int nq);
+int hemo_tet_facet_flux(hemo_ctx* ctx, const HemoFacetSet& fs, const double* un_dev, double* partial);
+int hemo_tet_laplace_mass(hemo_ctx* ctx);
+int hemo_tet_pc_setup(hemo_ctx* ctx, const double* vals_dev);
+int hemo_tet_velocity_solve(hemo_ctx* ctx, const double* vals_dev, const double* ru, const double* zp, double* tu,
+                            double* tmp, double* zu, int sweeps, double omega);
+int hemo_tet_spmv(hemo_ctx* ctx, const double* vals_dev, const double* x_dev, double* y_dev);
 // implemented in linalg.cu
 int hemo_ensure_reduce(hemo_ctx* ctx, size_t partial_n, size_t out_n);
 int hemo_dot_dev(hemo_ctx* ctx, int64_t n, const double* x, const double* y, double* out_host);

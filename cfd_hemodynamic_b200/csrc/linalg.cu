@@ -136,6 +136,7 @@ int hemo_spmv_block(hemo_ctx* ctx, int rows, int cols, const double* vals, const
 extern "C" int hemo_spmv(hemo_ctx* ctx, const double* vals_dev, const double* x_dev, double* y_dev) {
     if (!ctx || !vals_dev || !x_dev || !y_dev) return HEMO_EINVAL;
     if (!ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "node graph not set");
+    if (ctx->dim == 3) return hemo_tet_spmv(ctx, vals_dev, x_dev, y_dev);
     const int64_t n = ctx->n;
     return hemo_spmv_block(ctx, 3, 3, vals_dev, x_dev, x_dev + 2 * n, 1.0, nullptr, nullptr, y_dev, y_dev + 2 * n);
 }

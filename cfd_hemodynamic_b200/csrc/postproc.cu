@@ -282,6 +282,7 @@ static int pp_fetch(hemo_ctx* ctx, int count, double* out_host) {
 
 extern "C" int hemo_wall_shear_stress(hemo_ctx* ctx, int set_id, const double* x_dev, double* wss_dev) {
     if (!ctx || set_id < 0 || set_id >= HEMO_MAX_FACET_SETS || !x_dev || !wss_dev) return HEMO_EINVAL;
+    HEMO_2D_ONLY(ctx, "wall shear stress");
     if (!ctx->cells || !ctx->have_par) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / params not set");
     const HemoFacetSet& fs = ctx->fsets[set_id];
     HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(wss_dev, 0, sizeof(double) * 2 * ctx->n, ctx->stream));
@@ -297,6 +298,7 @@ extern "C" int hemo_wall_shear_stress(hemo_ctx* ctx, int set_id, const double* x
 
 extern "C" int hemo_boundary_force(hemo_ctx* ctx, int set_id, const double* x_dev, double* force_host) {
     if (!ctx || set_id < 0 || set_id >= HEMO_MAX_FACET_SETS || !x_dev || !force_host) return HEMO_EINVAL;
+    HEMO_2D_ONLY(ctx, "boundary force");
     if (!ctx->cells || !ctx->have_par) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / params not set");
     const HemoFacetSet& fs = ctx->fsets[set_id];
     force_host[0] = force_host[1] = 0.0;
@@ -332,6 +334,7 @@ extern "C" int hemo_early_stop_norms(hemo_ctx* ctx, int64_t n, const double* u_d
 
 extern "C" int hemo_l2_norm_sq(hemo_ctx* ctx, int bs, const double* f_dev, double* out_host) {
     if (!ctx || !f_dev || !out_host || (bs != 1 && bs != 2)) return HEMO_EINVAL;
+    HEMO_2D_ONLY(ctx, "the L2 norm");
     if (!ctx->cells) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh not set");
     int rc = hemo_ensure_reduce(ctx, (size_t)PP_BLOCKS, 8);
     if (rc) return rc;

@@ -8,11 +8,13 @@
 //     T2_ab = |J| sum_q w_q tau(q) phi_a phi_b ,   L0 = |J| sum_q w_q tau_lsic(q)
 // of each block form's own rule and the (D+1)^2 node blocks follow in closed form.  It is checked
 // on the host against oracle/simplex_oracle.py for D = 2 and D = 3 (tests/test_simplex_host.py,
-// compiled with g++: test infrastructure only).  Not yet wired into libhemo_sm100.so: the 3-D
-// library path also needs 4x4 node blocks in the gather / SpMV / multigrid kernels.
+// compiled with g++: test infrastructure only).  The tetrahedron kernels of assembly_tet.cu
+// instantiate it for D = 3.  `simplex_facet` states the exterior-facet terms
+// (stabilized_schur.py:79, stabilized_schur_pressure_backflow.py:189-217) once for any D.
 #pragma once
 #include <math.h>
 
+#include "../../include/hemo.h"
 #include "hemo_rules.h"
 
 #ifdef __CUDACC__
@@ -301,4 +303,163 @@ HEMO_HD void simplex_jacobian(const SimplexCell<D>& c, const HemoForm& par, cons
     simplex_colsum<D>(Tt, T1, T0pp);
     simplex_moments<D>(c, par, ruu, T2, L0);
     simplex_jacobian_from_moments<D>(c, par, T2, L0, T1up, T1pu, T0pp, ruu.m0, ruu.m2, rup.m1, rpu.m1, emit);
+}
+
+
+// ---------------------------------------------------------------------------
+// Exterior-facet integrals on local facet lf (opposite vertex lf) of a simplex whose geometry and
+// derived fields are set (simplex_geometry + simplex_derive).  Terms and coefficients: FacetSet in
+// oracle/ns_oracle.py (stabilized_schur.py:79; stabilized_schur_pressure_backflow.py:192-217).
+// The facet rule is given in barycentric coordinates of the facet's own vertices (ascending local
+// order); weights sum to the reference facet measure (1 on an interval, 1/2 on a triangle).
+//   res(a, k, value)          adds to F_u[a][k]
+//   jac(a, b, k, ci, value)   adds to dF_u[a][k] / d(U[b][ci]) (ci < D) or / dP[b] (ci = D)
+// ---------------------------------------------------------------------------
+#define HEMO_SIMPLEX_MAXFQ 16
+
+template <int D>
+struct SimplexFacetRule {
+    int nq;
+    double lam[HEMO_SIMPLEX_MAXFQ][D];
+    double w[HEMO_SIMPLEX_MAXFQ];
+};
+
+// pts: nq points on the reference facet ((D-1) coordinates each: s on [0,1]; (s,t) on the triangle)
+template <int D>
+inline void simplex_facet_rule_set(SimplexFacetRule<D>& r, const double* pts, const double* wts, int nq) {
+    r.nq = nq;
+    for (int q = 0; q < nq; ++q) {
+        double s = 0.0;
+        for (int j = 0; j + 1 < D; ++j) { r.lam[q][j + 1] = pts[(D - 1) * q + j]; s += pts[(D - 1) * q + j]; }
+        r.lam[q][0] = 1.0 - s;
+        r.w[q] = wts[q];
+    }
+}
+
+// unit outward normal and physical / reference measure ratio of facet lf: the barycentric
+// coordinate of the opposite vertex decreases towards the facet, so n = -grad phi_lf / |grad phi_lf|,
+// and measure(F) = D |K| |grad phi_lf| with |K| = detJ / D!, reference measure 1 / (D-1)!.
+template <int D>
+HEMO_HD void simplex_facet_normal(const SimplexCell<D>& c, int lf, double nr[D], double& scale) {
+    double g2 = 0.0;
+    for (int i = 0; i < D; ++i) g2 += c.g[lf][i] * c.g[lf][i];
+    const double gn = sqrt(g2);
+    for (int i = 0; i < D; ++i) nr[i] = -c.g[lf][i] / gn;
+    scale = c.detJ * gn;
+}
+
+template <int D, bool WANT_RES, bool WANT_JAC, typename Res, typename Jac>
+HEMO_HD void simplex_facet(const SimplexCell<D>& c, const HemoForm& par, const hemo_facet_coef& co,
+                           const SimplexFacetRule<D>& fr, int lf, Res res, Jac jac) {
+    constexpr int NV = D + 1;
+    const double th = par.theta, mu = par.mu, rho = par.rho;
+    double nr[D], scale;
+    simplex_facet_normal<D>(c, lf, nr, scale);
+    double Pn[D][D];
+    for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) Pn[i][j] = ((i == j) ? 1.0 : 0.0) - nr[i] * nr[j];
+    // facet moments: Ph_a = int phi_a, Ph2_ab = int phi_a phi_b, B_ab = int (u_n.n)_- phi_a phi_b
+    double Ph[NV], Ph2[NV][NV], B[NV][NV];
+    for (int a = 0; a < NV; ++a) {
+        Ph[a] = 0.0;
+        for (int b = 0; b < NV; ++b) { Ph2[a][b] = 0.0; B[a][b] = 0.0; }
+    }
+    for (int q = 0; q < fr.nq; ++q) {
+        double phi[NV];
+        for (int j = 0, v = 0; v < NV; ++v) phi[v] = (v == lf) ? 0.0 : fr.lam[q][j++];
+        const double w = fr.w[q] * scale;
+        double unn = 0.0;
+        for (int k = 0; k < D; ++k) {
+            double u = 0.0;
+            for (int a = 0; a < NV; ++a) u += phi[a] * c.N[a][k];
+            unn += u * nr[k];
+        }
+        const double unm = 0.5 * (unn - fabs(unn));
+        for (int a = 0; a < NV; ++a) {
+            Ph[a] += w * phi[a];
+            for (int b = 0; b < NV; ++b) {
+                Ph2[a][b] += w * phi[a] * phi[b];
+                B[a][b] += w * unm * phi[a] * phi[b];
+            }
+        }
+    }
+    double dn[NV], Png[NV][D];
+    for (int a = 0; a < NV; ++a) {
+        dn[a] = 0.0;
+        for (int i = 0; i < D; ++i) dn[a] += c.g[a][i] * nr[i];
+        for (int k = 0; k < D; ++k) {
+            double v = 0.0;
+            for (int i = 0; i < D; ++i) v += Pn[k][i] * c.g[a][i];
+            Png[a][k] = v;
+        }
+    }
+    const double pen = co.a_n * co.beta_n * mu / c.h;
+    const double bf = co.a_b * co.beta_b * rho;
+    if (WANT_JAC) {
+        for (int a = 0; a < NV; ++a)
+            for (int b = 0; b < NV; ++b)
+                for (int k = 0; k < D; ++k) {
+                    for (int l = 0; l < D; ++l) {
+                        const double dkl = (k == l) ? 1.0 : 0.0;
+                        double v = -th * co.a_g * mu * c.g[b][k] * nr[l] * Ph[a];
+                        v -= th * co.a_s * mu * (c.g[b][k] * nr[l] + dn[b] * dkl) * Ph[a];
+                        v -= th * co.a_n * mu * (Png[b][k] * nr[l] + dn[b] * Pn[k][l]) * Ph[a];
+                        v -= th * co.a_n * mu * (Png[a][l] * nr[k] + dn[a] * Pn[k][l]) * Ph[b];
+                        v += th * pen * Pn[k][l] * Ph2[a][b];
+                        v -= th * bf * B[a][b] * dkl;
+                        jac(a, b, k, l, v);
+                    }
+                    jac(a, b, k, D, co.a_p * nr[k] * Ph2[a][b]);
+                }
+    }
+    if (WANT_RES) {
+        double Gn[D], en[D], enT[D], Mi[D], MiT[D];
+        for (int i = 0; i < D; ++i) {
+            double gn = 0.0, e = 0.0;
+            for (int j = 0; j < D; ++j) { gn += c.G[i][j] * nr[j]; e += 0.5 * (c.G[i][j] + c.G[j][i]) * nr[j]; }
+            Gn[i] = gn; en[i] = e;
+            double m = 0.0;
+            for (int cc = 0; cc < NV; ++cc) m += Ph[cc] * c.M[cc][i];
+            Mi[i] = m;
+        }
+        for (int k = 0; k < D; ++k) {
+            double e = 0.0, m = 0.0;
+            for (int i = 0; i < D; ++i) { e += Pn[k][i] * en[i]; m += Pn[k][i] * Mi[i]; }
+            enT[k] = e; MiT[k] = m;
+        }
+        for (int a = 0; a < NV; ++a) {
+            double pa = 0.0, Ma[D], Ba[D], gM = 0.0;
+            for (int k = 0; k < D; ++k) { Ma[k] = 0.0; Ba[k] = 0.0; gM += c.g[a][k] * MiT[k]; }
+            for (int b = 0; b < NV; ++b) {
+                pa += Ph2[a][b] * c.P[b];
+                for (int k = 0; k < D; ++k) { Ma[k] += Ph2[a][b] * c.M[b][k]; Ba[k] += B[a][b] * c.M[b][k]; }
+            }
+            for (int k = 0; k < D; ++k) {
+                double MaT = 0.0;
+                for (int i = 0; i < D; ++i) MaT += Pn[k][i] * Ma[i];
+                double v = (co.a_p * pa + co.pconst * Ph[a]) * nr[k];
+                v -= co.a_g * mu * Gn[k] * Ph[a];
+                v -= co.a_s * 2.0 * mu * en[k] * Ph[a];
+                v -= co.a_n * 2.0 * mu * enT[k] * Ph[a];
+                v -= co.a_n * mu * (gM * nr[k] + dn[a] * MiT[k]);      // -(2 mu eps(v) n).u_T
+                v += pen * MaT;
+                v -= bf * Ba[k];
+                res(a, k, v);
+            }
+        }
+    }
+}
+
+// Q = int_F u_n . n ds on facet lf (exact for P1: measure times the mean of the facet's nodal values)
+template <int D>
+HEMO_HD double simplex_facet_flux(const SimplexCell<D>& c, int lf) {
+    double nr[D], scale;
+    simplex_facet_normal<D>(c, lf, nr, scale);
+    double q = 0.0;
+    for (int a = 0; a < D + 1; ++a) {
+        if (a == lf) continue;
+        for (int k = 0; k < D; ++k) q += c.N[a][k] * nr[k];
+    }
+    // measure = scale / (D-1)!, mean = sum / D
+    return q * scale / (D == 3 ? 6.0 : 2.0);
 }

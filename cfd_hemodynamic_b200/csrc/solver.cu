@@ -65,13 +65,14 @@ k_extract_a00(int64_t nnz_node, const int32_t* __restrict__ nrowptr, const int32
 // pressure Laplacian with identity rows/cols on Dirichlet pressure dofs
 __global__ void __launch_bounds__(256)
 k_lap_with_bc(int n, int64_t nnz_node, const int32_t* __restrict__ rowof, const int32_t* __restrict__ ncol,
-              const double* __restrict__ lap, const uint8_t* __restrict__ dofflag, areal* __restrict__ out) {
+              const double* __restrict__ lap, const uint8_t* __restrict__ dofflag /* pressure part, n */,
+              areal* __restrict__ out) {
     const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nnz_node) return;
     double v = lap[s];
     if (dofflag) {
         const int i = rowof[s], j = ncol[s];
-        const bool fi = dofflag[2 * (int64_t)n + i] != 0, fj = dofflag[2 * (int64_t)n + j] != 0;
+        const bool fi = dofflag[i] != 0, fj = dofflag[j] != 0;
         if (fi || fj) v = (i == j) ? 1.0 : 0.0;
     }
     out[s] = (areal)v;
@@ -134,17 +135,22 @@ k_node_spmv_scalar(int n, const int32_t* __restrict__ nrowptr, const int32_t* __
 // z_p = (c_m t_p + c_c (N_p q)) / mass + c_L q_p ; Dirichlet pressure dofs: z_p = r_p
 __global__ void k_schur_combine(int n, double cm, double cl, double cc, const double* __restrict__ tp,
                                 const double* __restrict__ mass, const double* __restrict__ qp,
-                                const double* __restrict__ conv, const uint8_t* __restrict__ dofflag,
+                                const double* __restrict__ conv, const uint8_t* __restrict__ dofflag /* pressure part, n */,
                                 const double* __restrict__ rp, double* __restrict__ zp) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double v = cm * tp[i] / mass[i] + cl * qp[i];
     if (conv) v += cc * conv[i] / mass[i];
-    if (dofflag && dofflag[2 * (int64_t)n + i]) v = rp[i];
+    if (dofflag && dofflag[i]) v = rp[i];
     zp[i] = v;
 }
 
 static int pc_build_graph(hemo_ctx* ctx, const double* vals_dev);
+
+// Dirichlet flags of the pressure dofs: the tail of dofflag in the [u (dim n) | p (n)] layout
+static inline const uint8_t* pressure_flags(const hemo_ctx* ctx) {
+    return ctx->have_bc ? ctx->dofflag + (size_t)ctx->dim * ctx->n : nullptr;
+}
 
 extern "C" int hemo_remove_mean_vec(hemo_ctx* ctx, int64_t n, double* x_dev) {
     if (!ctx || !x_dev || n <= 0) return HEMO_EINVAL;
@@ -163,8 +169,7 @@ extern "C" int hemo_amg_setup_scalar(hemo_ctx* ctx, const double* lap_vals_dev, 
     if (!ctx || !lap_vals_dev) return HEMO_EINVAL;
     if (!ctx->amg[1].ready) HEMO_FAIL(ctx, HEMO_ESTATE, "pressure AMG hierarchy not finalized");
     k_lap_with_bc<<<hemo_grid(ctx->nnz_node, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->nnz_node, ctx->rowof, ctx->ncol,
-                                                                          lap_vals_dev,
-                                                                          ctx->have_bc ? ctx->dofflag : nullptr,
+                                                                          lap_vals_dev, pressure_flags(ctx),
                                                                           ctx->amg[1].op[0].val);
     HEMO_LAUNCH_CHECK(ctx);
     return hemo_amg_numeric_shift(ctx, &ctx->amg[1], coarse_shift);
@@ -235,29 +240,36 @@ extern "C" int hemo_set_solver_opts(hemo_ctx* ctx, const hemo_solver_opts* o) {
 extern "C" int hemo_pc_setup(hemo_ctx* ctx, const double* vals_dev, const double* lap_vals_dev,
                              const double* mass_dev) {
     if (!ctx || !vals_dev) return HEMO_EINVAL;
-    if (!ctx->amg[0].ready || !ctx->amg[1].ready) HEMO_FAIL(ctx, HEMO_ESTATE, "AMG hierarchies not finalized");
+    const bool tet = ctx->dim == 3;    // 3-D: block-Jacobi sweeps on A00 instead of the velocity hierarchy
+    if ((!tet && !ctx->amg[0].ready) || !ctx->amg[1].ready) HEMO_FAIL(ctx, HEMO_ESTATE, "AMG hierarchies not finalized");
+    if (tet && (ctx->pc_mask || ctx->external_schur))
+        HEMO_FAIL(ctx, HEMO_ESTATE, "partition masks / external Schur solves are not implemented for tetrahedra yet");
     const int n = ctx->n;
+    const size_t gd = (size_t)ctx->dim;
     cudaStream_t st = ctx->stream;
     int rc;
     if (!ctx->pc_tmp_u) {
-        if ((rc = hemo_alloc(ctx, &ctx->pc_tmp_u, (size_t)2 * n))) return rc;
-        if ((rc = hemo_alloc(ctx, &ctx->pc_tmp_u2, (size_t)2 * n))) return rc;
+        if ((rc = hemo_alloc(ctx, &ctx->pc_tmp_u, gd * n))) return rc;
+        if ((rc = hemo_alloc(ctx, &ctx->pc_tmp_u2, gd * n))) return rc;
         if ((rc = hemo_alloc(ctx, &ctx->pc_tmp_p, (size_t)n))) return rc;
         if ((rc = hemo_alloc(ctx, &ctx->pc_tmp_p2, (size_t)n))) return rc;
-        if ((rc = hemo_alloc(ctx, &ctx->a01, (size_t)ctx->nnz_node))) return rc;
-        if ((rc = hemo_alloc(ctx, &ctx->pc_in, (size_t)3 * n + 32))) return rc;
-        if ((rc = hemo_alloc(ctx, &ctx->pc_out, (size_t)3 * n + 32))) return rc;
+        if (!tet && (rc = hemo_alloc(ctx, &ctx->a01, (size_t)ctx->nnz_node))) return rc;
+        if ((rc = hemo_alloc(ctx, &ctx->pc_in, (gd + 1) * n + 32))) return rc;
+        if ((rc = hemo_alloc(ctx, &ctx->pc_out, (gd + 1) * n + 32))) return rc;
     }
-    k_extract_a00<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(ctx->nnz_node, ctx->nrowptr, ctx->rowof, ctx->ncol,
-                                                                 ctx->pc_mask, vals_dev, ctx->amg[0].op[0].val, ctx->a01);
-    HEMO_LAUNCH_CHECK(ctx);
-    if ((rc = hemo_amg_numeric_shift(ctx, &ctx->amg[0], 0.0))) return rc;
+    if (tet) {
+        if ((rc = hemo_tet_pc_setup(ctx, vals_dev))) return rc;
+    } else {
+        k_extract_a00<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(ctx->nnz_node, ctx->nrowptr, ctx->rowof, ctx->ncol,
+                                                                     ctx->pc_mask, vals_dev, ctx->amg[0].op[0].val, ctx->a01);
+        HEMO_LAUNCH_CHECK(ctx);
+        if ((rc = hemo_amg_numeric_shift(ctx, &ctx->amg[0], 0.0))) return rc;
+    }
     if (mass_dev) ctx->mass = mass_dev;
     if (lap_vals_dev) {
         if (!ctx->mass) return HEMO_EINVAL;
         k_lap_with_bc<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(n, ctx->nnz_node, ctx->rowof, ctx->ncol, lap_vals_dev,
-                                                                     ctx->have_bc ? ctx->dofflag : nullptr,
-                                                                     ctx->amg[1].op[0].val);
+                                                                     pressure_flags(ctx), ctx->amg[1].op[0].val);
         HEMO_LAUNCH_CHECK(ctx);
         if ((rc = hemo_amg_numeric_shift(ctx, &ctx->amg[1], ctx->opts.project_pressure ? 1e-8 : 0.0))) return rc;
     }
@@ -322,9 +334,9 @@ static int pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_
     const int n = ctx->n;
     cudaStream_t st = ctx->stream;
     const double* ru = r_dev;
-    const double* rp = r_dev + 2 * (int64_t)n;
+    const double* rp = r_dev + ctx->dim * (int64_t)n;
     double* zu = z_dev;
-    double* zp = z_dev + 2 * (int64_t)n;
+    double* zp = z_dev + ctx->dim * (int64_t)n;
     double* tp = ctx->pc_tmp_p;
     double* qp = ctx->pc_tmp_p2;
     double* tu = ctx->pc_tmp_u;
@@ -346,11 +358,12 @@ static int pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_
     }
     k_schur_combine<<<hemo_grid(n, 256), 256, 0, st>>>(n, ctx->opts.schur_mass_coef, ctx->opts.schur_lap_coef,
                                                        ctx->npconv_coef, tp, ctx->mass, qp,
-                                                       pcd ? ctx->pc_tmp_u2 : nullptr,
-                                                       ctx->have_bc ? ctx->dofflag : nullptr, rp, zp);
+                                                       pcd ? ctx->pc_tmp_u2 : nullptr, pressure_flags(ctx), rp, zp);
     HEMO_LAUNCH_CHECK(ctx);
     if (ctx->opts.project_pressure && (rc = hemo_remove_mean(ctx, n, zp))) return rc;
     }   // else: z_p was provided by the caller (global pressure solve of the multi-GPU driver)
+    if (ctx->dim == 3)    // t_u = r_u - A01 z_p, then damped block-Jacobi sweeps on A00 (amg_cycles_u * 4 sweeps)
+        return hemo_tet_velocity_solve(ctx, vals_dev, ru, zp, tu, ctx->pc_tmp_u2, zu, 4 * ctx->opts.amg_cycles_u, 2.0 / 3.0);
     // t_u = r_u - A01 z_p
     k_a01_residual<<<hemo_grid((int64_t)n * 4, 256), 256, 0, st>>>(n, ctx->nrowptr, ctx->ncol, ctx->a01, zp, ru, tu);
     HEMO_LAUNCH_CHECK(ctx);
@@ -409,11 +422,11 @@ extern "C" int hemo_pc_apply(hemo_ctx* ctx, const double* vals_dev, const double
     if (!ctx || !vals_dev || !r_dev || !z_dev) return HEMO_EINVAL;
     if (!ctx->mass || !ctx->pc_tmp_u) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_pc_setup not called");
     if (ctx->use_graph && ctx->pc_graph_exec) {
-        const size_t bytes = sizeof(double) * 3 * (size_t)ctx->n;
+        const size_t bytes = sizeof(double) * (size_t)(ctx->dim + 1) * (size_t)ctx->n;
         cudaStream_t st = ctx->stream;
         HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->pc_in, r_dev, bytes, cudaMemcpyDeviceToDevice, st));
         if (ctx->external_schur)
-            HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->pc_out + 2 * (size_t)ctx->n, z_dev + 2 * (size_t)ctx->n,
+            HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->pc_out + (size_t)ctx->dim * ctx->n, z_dev + (size_t)ctx->dim * ctx->n,
                                                  sizeof(double) * ctx->n, cudaMemcpyDeviceToDevice, st));
         HEMO_CHECK_CUDA(ctx, cudaGraphLaunch(ctx->pc_graph_exec, st));
         HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(z_dev, ctx->pc_out, bytes, cudaMemcpyDeviceToDevice, st));
@@ -437,7 +450,7 @@ extern "C" int hemo_fgmres(hemo_ctx* ctx, const double* vals_dev, const double* 
                            int* its_out, double* rel_resid_out) {
     if (!ctx || !vals_dev || !b_dev || !y_dev) return HEMO_EINVAL;
     const int n = ctx->n;
-    const int64_t N = 3 * (int64_t)n;
+    const int64_t N = (int64_t)(ctx->dim + 1) * n;      // [u (dim n) | p (n)]
     const int64_t ldv = (N + 31) / 32 * 32;
     const int m = ctx->opts.restart;
     cudaStream_t st = ctx->stream;
@@ -517,13 +530,18 @@ extern "C" int hemo_fgmres(hemo_ctx* ctx, const double* vals_dev, const double* 
         HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(st));   // red_host is reused below
         if (converged) break;
         // restart: r = b - A y
-        if ((rc = hemo_spmv_block(ctx, 3, 3, vals_dev, y_dev, y_dev + 2 * (int64_t)n, -1.0, b_dev, b_dev + 2 * (int64_t)n,
-                                  w, w + 2 * (int64_t)n)))
+        double sgn = 1.0;
+        if (ctx->dim == 3) {
+            if ((rc = hemo_tet_spmv(ctx, vals_dev, y_dev, w))) return rc;
+            if ((rc = hemo_axpy(ctx, N, -1.0, b_dev, w))) return rc;           // w = A y - b = -r
+            sgn = -1.0;
+        } else if ((rc = hemo_spmv_block(ctx, 3, 3, vals_dev, y_dev, y_dev + 2 * (int64_t)n, -1.0, b_dev,
+                                         b_dev + 2 * (int64_t)n, w, w + 2 * (int64_t)n)))
             return rc;
         if ((rc = hemo_norm2(ctx, N, w, &beta))) return rc;
         res = beta;
         if (beta <= tol) { converged = true; break; }
-        if ((rc = hemo_scale_copy(ctx, N, 1.0 / beta, w, V))) return rc;
+        if ((rc = hemo_scale_copy(ctx, N, sgn / beta, w, V))) return rc;
     }
     if (its_out) *its_out = its;
     if (rel_resid_out) *rel_resid_out = res / bnorm;

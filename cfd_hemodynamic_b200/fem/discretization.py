@@ -44,26 +44,42 @@ def all_exterior_facets(mesh: Mesh) -> np.ndarray:
     return exterior_facet_indices(mesh.topology)
 
 
-def dirichlet_arrays(n_nodes: int, cells: np.ndarray, bcs):
+def pairs_by_cell(pairs: np.ndarray):
+    """Group (cell, local facet) pairs by cell: (cells (m,), mask (m,)), bit lf of mask = facet lf."""
+    pairs = np.asarray(pairs).reshape(-1, 2)
+    if pairs.shape[0] == 0:
+        return np.zeros(0, np.int32), np.zeros(0, np.int32)
+    order = np.argsort(pairs[:, 0], kind="stable")
+    pc = pairs[order, 0]
+    bits = (1 << pairs[order, 1]).astype(np.int32)
+    cells, start = np.unique(pc, return_index=True)
+    return cells.astype(np.int32), np.add.reduceat(bits, start).astype(np.int32)
+
+
+def dirichlet_arrays(n_nodes: int, cells: np.ndarray, bcs, gdim: int = 2):
     """bcs: list of (block 'u'|'p', block dof indices, value array (block-sized)).
-    Returns dofflag (3n uint8), dofmult (3n f64), cellflag (E uint8), g (3n f64).
+    Returns dofflag (N uint8), dofmult (N f64), cellflag (E uint8), g (N f64) with
+    N = (gdim + 1) n in the [u interleaved (gdim n) | p (n)] layout.
     Semantics (3P): diagonal += 1 per DirichletBC containing the
     dof; on shared dofs the last BC in the list provides the value."""
-    N = 3 * n_nodes
+    N = (gdim + 1) * n_nodes
+    nu = gdim * n_nodes
     flag = np.zeros(N, dtype=np.uint8)
     mult = np.zeros(N, dtype=np.float64)
     g = np.zeros(N, dtype=np.float64)
     for block, nodes, values in bcs:
         nodes = np.asarray(nodes, dtype=np.int64)
         if block == "u":
-            d = (2 * nodes[:, None] + np.arange(2)[None, :]).reshape(-1)
+            d = (gdim * nodes[:, None] + np.arange(gdim)[None, :]).reshape(-1)
             vals = np.asarray(values, dtype=np.float64)[d]
         else:
-            d = 2 * n_nodes + nodes
+            d = nu + nodes
             vals = np.asarray(values, dtype=np.float64)[nodes]
         flag[d] = 1
         mult[d] += 1.0
         g[d] = vals
-    nodeflag = (flag[0:2 * n_nodes:2] | flag[1:2 * n_nodes:2] | flag[2 * n_nodes:]).astype(bool)
+    nodeflag = flag[nu:].astype(bool)
+    for k in range(gdim):
+        nodeflag |= flag[k:nu:gdim].astype(bool)
     cellflag = nodeflag[cells].any(axis=1).astype(np.uint8)
     return flag, mult, cellflag, g

@@ -78,7 +78,15 @@ class BlockSchurSolver:
             pmask = np.zeros(n, dtype=bool)
             pmask[np.asarray(p_dirichlet_nodes, dtype=np.int64)] = True
             hemo.set_schur_mask(None)
+        # tetrahedra: the velocity block is handled by block-Jacobi sweeps inside the library
+        # (no 3x3-block hierarchy yet); only the scalar pressure hierarchy is built
+        tet = getattr(hemo, "dim", 2) == 3
+        if tet and schur_mode != "laplace":
+            raise ValueError("tetrahedra: only schur_mode='laplace' is implemented")
         for which, mask, max_coarse in ((0, umask, 80), (1, pmask, 160)):
+            if tet and which == 0:
+                self.levels.append([])
+                continue
             lv = amg_setup.build_hierarchy(L, mask, max_coarse=max_coarse, theta=strength_theta,
                                            smooth=smooth_prolongator, fine_pattern=fine_p if which == 1 else None)
             for l, d in enumerate(lv):

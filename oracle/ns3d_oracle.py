@@ -7,9 +7,10 @@ iteration with sparse LU — what the 3-D CUDA path will be checked against once
 already used for a known-answer test on the Ethier–Steinman solution the reference's
 src/scenarios/taylor_green.py:74-134 compares with (tests/test_ns3d_oracle.py).
 
-On a mesh whose whole boundary carries Dirichlet velocity conditions the exterior-facet term of
-stabilized_schur.py:79 only touches constrained rows, so the cell integrals are the complete form
-there; general 3-D facet terms are not restated yet.
+Exterior-facet terms (stabilized_schur.py:79; stabilized_schur_pressure_backflow.py:189-217) enter
+through `facet_sets` (ns_oracle.FacetSet objects, integrated by simplex_oracle.facet_F on triangular
+facets with `facet_rule`).  On a mesh whose whole boundary carries Dirichlet velocity conditions the
+term of :79 only touches constrained rows, so the Ethier-Steinman test runs without it.
 """
 from __future__ import annotations
 
@@ -53,6 +54,8 @@ class Problem3D:
     f: np.ndarray                     # (3,)
     rules: dict                       # 'Fu','Fp','uu','up','pu','pp' -> (pts, wts) on the reference tetrahedron
     bc_dofs: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))   # global dofs in [u (3n) | p (n)]
+    facet_sets: list = field(default_factory=list)                                # ns_oracle.FacetSet
+    facet_rule: tuple | None = None                                               # (pts (m,2), wts) on the reference triangle
     eps0: float = EPS0
     theta: float = 0.5
     a0: float = 1.0
@@ -85,6 +88,11 @@ def assemble_F_raw(prob, xk, un, uh=None):
     b = np.zeros(prob.ndof, dtype=Fu.dtype)
     np.add.at(b, prob.l2g[:, :12].reshape(-1), Fu.reshape(-1))
     np.add.at(b, prob.l2g[:, 12:].reshape(-1), Fp.reshape(-1))
+    for fs in prob.facet_sets:
+        ce = fs.pairs[:, 0]
+        Ff = S.facet_F(prob.x, c, prob.h, fs.pairs, fs, U[ce], P[ce], Un[ce], prob.facet_rule, prob.rho, prob.mu,
+                       prob.theta)
+        np.add.at(b, prob.l2g[ce, :12].reshape(-1), Ff.reshape(-1))
     return b
 
 
@@ -100,11 +108,42 @@ def assemble_J_raw(prob, xk, un, uh=None):
     Ae[:, :12, 12:] = S.element_J(prob.x, c, prob.h, U, P, Un, prob.rules["up"], **kw)[1].reshape(E, 12, 4)
     Ae[:, 12:, :12] = S.element_J(prob.x, c, prob.h, U, P, Un, prob.rules["pu"], **kw)[2].reshape(E, 4, 12)
     Ae[:, 12:, 12:] = S.element_J(prob.x, c, prob.h, U, P, Un, prob.rules["pp"], **kw)[3]
+    for fs in prob.facet_sets:
+        ce = fs.pairs[:, 0]
+        # (m, 12, 16): columns ordered (U flattened, then P) = the cell's local dof order
+        np.add.at(Ae, (ce, slice(0, 12)), S.facet_J(prob.x, c, prob.h, fs.pairs, fs, Un[ce], prob.facet_rule, prob.rho,
+                                                   prob.mu, prob.theta))
     rows = np.repeat(prob.l2g, 16, axis=1).reshape(-1)
     cols = np.tile(prob.l2g, (1, 16)).reshape(-1)
     A = sp.coo_matrix((Ae.reshape(-1), (rows, cols)), shape=(prob.ndof, prob.ndof)).tocsr()
     A.sort_indices()
     return A
+
+
+def bc_arrays(prob, bc_lists=None):
+    """marker (bool, ndof) and diagonal multiplicity (ndof): `bc_lists` = one dof array per Dirichlet
+    condition (a dof held by k conditions gets k on the diagonal); default: the
+    single list prob.bc_dofs."""
+    lists = [prob.bc_dofs] if bc_lists is None else bc_lists
+    mult = np.zeros(prob.ndof)
+    for dofs in lists:
+        mult[np.asarray(dofs, dtype=np.int64)] += 1.0
+    return mult > 0, mult
+
+
+def assemble_system(prob, xk, un, g, uh=None, bc_lists=None):
+    """(A, b) of assemble_matrix_block / assemble_vector_block + apply_lifting(x0 = x, alpha = -1) +
+    set_bc (stabilized_schur.py:144-175)."""
+    marker, mult = bc_arrays(prob, bc_lists)
+    A_raw = assemble_J_raw(prob, xk, un, uh)
+    b = assemble_F_raw(prob, xk, un, uh)
+    d = np.where(marker, g - xk, 0.0)
+    b = b + A_raw @ d
+    b[marker] = xk[marker] - g[marker]
+    keep = sp.diags((~marker).astype(np.float64))
+    A = (keep @ A_raw @ keep + sp.diags(mult)).tocsr()      # values only: explicit zeros of the FE pattern are dropped
+    A.sort_indices()
+    return A, b
 
 
 def newton_step(prob, x0, un, g, uh=None, rtol=1e-10, max_it=20):

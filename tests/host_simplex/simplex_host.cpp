@@ -72,3 +72,147 @@ void sxh_cells(int dim, int E, int n, const int32_t* cells, const double* x, con
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Exterior-facet routine (any D) and the emulated tetrahedron assembly pipeline: the per-thread
+// items of csrc/tet_items.cuh walked over their index ranges in the order the kernels of
+// assembly_tet.cu are launched.
+// ---------------------------------------------------------------------------
+#include "../../cfd_hemodynamic_b200/csrc/tet_items.cuh"
+
+template <int D>
+static void run_facets(int m, int n, const int32_t* pairs, const int32_t* cells, const double* x, const double* h,
+                       const double* sol, const double* un, const hemo_facet_coef* co, const double* fpts,
+                       const double* fwts, int nq, double* Fu, double* J, double* flux) {
+    constexpr int NV = D + 1, B = D + 1;
+    hemo_form_finalize(g_par);
+    SimplexFacetRule<D> fr;
+    simplex_facet_rule_set<D>(fr, fpts, fwts, nq);
+    for (int t = 0; t < m; ++t) {
+        const int c = pairs[2 * t], lf = pairs[2 * t + 1];
+        SimplexCell<D> cd;
+        double X[NV][D];
+        for (int a = 0; a < NV; ++a) {
+            const int v = cells[NV * (int64_t)c + a];
+            for (int k = 0; k < D; ++k) {
+                X[a][k] = x[D * (int64_t)v + k];
+                cd.U[a][k] = sol[D * (int64_t)v + k];
+                cd.N[a][k] = un[D * (int64_t)v + k];
+                cd.H[a][k] = cd.N[a][k];
+            }
+            cd.P[a] = sol[D * (int64_t)n + v];
+        }
+        for (int k = 0; k < D; ++k) cd.fbody[k] = 0.0;
+        cd.h = h[c];
+        simplex_geometry<D>(cd, X);
+        simplex_derive<D>(cd, g_par);
+        double* fu = Fu + (int64_t)t * NV * D;
+        double* jj = J + (int64_t)t * NV * NV * D * B;
+        simplex_facet<D, true, true>(
+            cd, g_par, *co, fr, lf, [&](int a, int k, double v) { fu[a * D + k] += v; },
+            [&](int a, int b, int k, int ci, double v) { jj[((a * NV + b) * D + k) * B + ci] += v; });
+        flux[t] = simplex_facet_flux<D>(cd, lf);
+    }
+}
+
+extern "C" {
+
+// Fu: [m][NV][D], J: [m][NV][NV][D][D+1] (zero-initialised by the caller), flux: [m]
+void sxh_facets(int dim, int m, int n, const int32_t* pairs, const int32_t* cells, const double* x, const double* h,
+                const double* sol, const double* un, const double* coef8, const double* fpts, const double* fwts, int nq,
+                double* Fu, double* J, double* flux) {
+    hemo_facet_coef co = {coef8[0], coef8[1], coef8[2], coef8[3], coef8[4], coef8[5], coef8[6], coef8[7]};
+    if (dim == 2) run_facets<2>(m, n, pairs, cells, x, h, sol, un, &co, fpts, fwts, nq, Fu, J, flux);
+    else run_facets<3>(m, n, pairs, cells, x, h, sol, un, &co, fpts, fwts, nq, Fu, J, flux);
+}
+
+// Emulated launch sequence of hemo_tet_assemble_jacobian / hemo_tet_assemble_residual / hemo_tet_spmv /
+// hemo_outlet_flux on tetrahedra.  Element buffers SoA as on the device.  dofflag may be null (no
+// Dirichlet conditions).  Outputs: vals (16 nnz_node), b (4n), y = J xv (4n), flux (1).
+void txh_assemble(int E, int n, int64_t nnz_node, const int32_t* cells, const double* x, const double* h,
+                  const double* sol, const double* un, const double* uh, const int32_t* nrowptr, const int32_t* ncol,
+                  const int32_t* rowof, const int32_t* mseg_ptr, const int32_t* mseg_src, const int32_t* vseg_ptr,
+                  const int32_t* vseg_src, int m, const int32_t* fcells, const int32_t* fmask, const double* coef8,
+                  const double* fpts, const double* fwts, int nfq, const uint8_t* dofflag, const double* dofmult,
+                  const uint8_t* cellflag, const double* g, const double* xv, double* Ae, double* Fe, double* vals,
+                  double* b, double* y, double* flux) {
+    hemo_form_finalize(g_par);
+    hemo_facet_coef co = {coef8[0], coef8[1], coef8[2], coef8[3], coef8[4], coef8[5], coef8[6], coef8[7]};
+    SimplexFacetRule<3> fr;
+    simplex_facet_rule_set<3>(fr, fpts, fwts, nfq);
+    // k_tet_cell_tensors (GPU-tested on its own): the same routines into the SoA buffers
+    for (int c = 0; c < E; ++c) {
+        SimplexCell<3> cd;
+        double X[4][3];
+        for (int a = 0; a < 4; ++a) {
+            const int v = cells[4 * (int64_t)c + a];
+            for (int k = 0; k < 3; ++k) {
+                X[a][k] = x[3 * (int64_t)v + k];
+                cd.U[a][k] = sol[3 * (int64_t)v + k];
+                cd.N[a][k] = un[3 * (int64_t)v + k];
+                cd.H[a][k] = uh[3 * (int64_t)v + k];
+            }
+            cd.P[a] = sol[3 * (int64_t)n + v];
+        }
+        for (int k = 0; k < 3; ++k) cd.fbody[k] = g_f[k];
+        cd.h = h[c];
+        simplex_geometry<3>(cd, X);
+        simplex_derive<3>(cd, g_par);
+        double Fu[4][3], Fp[4];
+        simplex_residual<3>(cd, g_par, g_r3.r[0], g_r3.r[1], Fu, Fp);
+        for (int a = 0; a < 4; ++a) {
+            for (int k = 0; k < 3; ++k) Fe[(int64_t)(a * 4 + k) * E + c] = Fu[a][k];
+            Fe[(int64_t)(a * 4 + 3) * E + c] = Fp[a];
+        }
+        simplex_jacobian<3>(cd, g_par, g_r3.r[2], g_r3.r[3], g_r3.r[4], g_r3.r[5],
+                            [&](int a, int bb, int ri, int ci, double v) {
+                                Ae[(int64_t)((a * 4 + bb) * 16 + ri * 4 + ci) * E + c] = v;
+                            });
+    }
+    // k_tet_facets
+    for (int t = 0; t < m; ++t)
+        tet_facet_item(t, E, n, fcells, fmask, co, fr, cells, x, h, sol, un, g_par, true, Ae, Fe);
+    // k_gather_matrix3d
+    for (int64_t s = 0; s < nnz_node; ++s)
+        tet_gather_matrix_item(s, n, nnz_node, E, nrowptr, ncol, rowof, mseg_ptr, mseg_src, Ae, dofflag, dofmult, vals);
+    // k_tet_lift_vector + k_tet_lift
+    if (dofflag) {
+        double* dvec = new double[4 * (int64_t)n];
+        for (int64_t i = 0; i < 4 * (int64_t)n; ++i) dvec[i] = dofflag[i] ? (g[i] - sol[i]) : 0.0;
+        for (int c = 0; c < E; ++c)
+            if (cellflag[c]) tet_lift_item(c, E, n, cells, dvec, Ae, Fe);
+        delete[] dvec;
+    }
+    // k_gather_vector3d
+    for (int i = 0; i < n; ++i) tet_gather_vector_item(i, n, E, vseg_ptr, vseg_src, Fe, dofflag, sol, g, b);
+    // k_spmv_node3d: 8 lanes per node, reduced in shuffle order (pairwise tree over the lanes)
+    for (int i = 0; i < n; ++i) {
+        double part[8][4];
+        for (int lane = 0; lane < 8; ++lane) tet_spmv_item(i, lane, 8, n, nnz_node, nrowptr, ncol, vals, xv, part[lane]);
+        for (int o = 4; o > 0; o >>= 1)
+            for (int lane = 0; lane < o; ++lane)
+                for (int k = 0; k < 4; ++k) part[lane][k] += part[lane + o][k];
+        for (int k = 0; k < 4; ++k) y[tet_dof(n, i, k)] = part[0][k];
+    }
+    // k_tet_facet_flux + k_sum_serial
+    double q = 0.0;
+    for (int t = 0; t < m; ++t) q += tet_flux_item(t, n, fcells, fmask, cells, x, un);
+    flux[0] = q;
+}
+
+// Emulated hemo_tet_pc_setup + hemo_tet_velocity_solve (k_tet_dinv, k_tet_a01_residual, k_tet_jacobi with
+// the library's ping-pong order): zu after `sweeps` damped block-Jacobi sweeps on A00 zu = ru - A01 zp.
+void txh_velocity_solve(int n, int64_t nnz_node, const int32_t* nrowptr, const int32_t* ncol, const int32_t* diagslot,
+                        const double* vals, const double* ru, const double* zp, int sweeps, double omega, double* dinv,
+                        double* tu, double* tmp, double* zu) {
+    for (int i = 0; i < n; ++i) tet_dinv_item(i, n, nnz_node, nrowptr, diagslot, vals, dinv);
+    for (int i = 0; i < n; ++i) tet_a01_residual_item(i, n, nnz_node, nrowptr, ncol, vals, zp, ru, tu);
+    const double* zin = nullptr;
+    for (int s = 0; s < sweeps; ++s) {
+        double* zout = ((sweeps - 1 - s) & 1) ? tmp : zu;
+        for (int i = 0; i < n; ++i) tet_jacobi_item(i, n, nnz_node, nrowptr, ncol, vals, dinv, omega, tu, zin, zout);
+        zin = zout;
+    }
+}
+
+}  // extern "C"

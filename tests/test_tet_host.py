@@ -1,0 +1,246 @@
+"""Host-compiled checks of the 3-D device code that follows the tetrahedron cell kernel
+(csrc/simplex_element.cuh: simplex_facet; csrc/tet_items.cuh: the per-thread bodies of k_tet_facets,
+k_tet_lift, k_gather_matrix3d, k_gather_vector3d, k_spmv_node3d, k_tet_facet_flux) against the oracle.
+The items are walked over their index ranges in kernel-launch order by tests/host_simplex/simplex_host.cpp
+(g++; test infrastructure only, the library never runs them on the CPU).  Tolerance 1e-12."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from cfd_hemodynamic_b200.fem import discretization as D
+from cfd_hemodynamic_b200.fem import quadrature as Q
+from oracle import ns3d_oracle as O3
+from oracle import ns_oracle as O
+from oracle import simplex_oracle as S
+from tests import common as T
+from tests.test_simplex_oracle import FACET_COEFS
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+COEF_KEYS = ("a_p", "pconst", "a_g", "a_s", "a_n", "beta_n", "a_b", "beta_b")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    src = os.path.join(HERE, "host_simplex", "simplex_host.cpp")
+    out_dir = os.path.join(HERE, "host_simplex", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libsimplexhost.so")
+    csrc = os.path.join(HERE, "..", "cfd_hemodynamic_b200", "csrc")
+    deps = [src, os.path.join(HERE, "..", "include", "hemo.h")] + [
+        os.path.join(csrc, f) for f in ("simplex_element.cuh", "tet_items.cuh", "hemo_rules.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src], check=True)
+    L = ctypes.CDLL(so)
+    L.sxh_set_params.argtypes = [ctypes.c_double] * 3 + [ctypes.c_void_p] + [ctypes.c_double] * 3
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _c(a, dt=np.float64):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def _coef8(coef):
+    return _c([coef.get(k, 0.0) for k in COEF_KEYS])
+
+
+def _perturbed_cube(nc, seed=0, amp=0.2):
+    x, cells = O3.unit_cube_tets(nc)
+    rng = np.random.default_rng(seed)
+    interior = (np.abs(x - 0.5) < 0.5 - 1e-12).all(axis=1)
+    x = x.copy()
+    x[interior] += amp / nc * (rng.random((int(interior.sum()), 3)) - 0.5)
+    return x, cells
+
+
+@pytest.mark.parametrize("coef", FACET_COEFS)
+@pytest.mark.parametrize("d", [2, 3])
+def test_facet_routine_matches_oracle(lib, d, coef):
+    if d == 2:
+        prob = T.make_problem(T.perturbed_square(4, 3, seed=2), dt=0.02, rho=1.06, mu=0.035)
+        x, cells = prob.x, prob.cells
+        frule = (np.asarray(prob.facet_rule[0]).reshape(-1, 1), prob.facet_rule[1])
+    else:
+        x, cells = _perturbed_cube(2)
+        frule = S.triangle_facet_rule(4)
+    n = x.shape[0]
+    h = S.cell_diameter(x, cells)
+    pairs = S.exterior_facets(cells)
+    m = len(pairs)
+    rng = np.random.default_rng(3)
+    u, p, un = rng.standard_normal((n, d)), rng.standard_normal(n), rng.standard_normal((n, d))
+    fs = O.FacetSet(pairs=pairs, **coef)
+    f3 = np.zeros(3)
+    for theta in (0.5, 1.0):
+        lib.sxh_set_params(0.02, 1.06, 0.035, _p(f3), O.EPS0, theta, 1.0)
+        nv = d + 1
+        Fu = np.zeros((m, nv, d))
+        J = np.zeros((m, nv, nv, d, d + 1))
+        flux = np.zeros(m)
+        sol = np.concatenate([u.reshape(-1), p])
+        lib.sxh_facets(d, m, n, _p(_c(pairs, np.int32)), _p(_c(cells, np.int32)), _p(_c(x)), _p(_c(h)), _p(sol),
+                       _p(_c(un.reshape(-1))), _p(_coef8(coef)), _p(_c(frule[0])), _p(_c(frule[1])), len(frule[1]),
+                       _p(Fu), _p(J), _p(flux))
+        ce = pairs[:, 0]
+        U, P, Un = u[cells][ce], p[cells][ce], un[cells][ce]
+        ref = S.facet_F(x, cells, h, pairs, fs, U, P, Un, frule, 1.06, 0.035, theta)
+        assert np.abs(Fu - ref).max() < 1e-12 * np.abs(ref).max()
+        Jr = S.facet_J(x, cells, h, pairs, fs, Un, frule, 1.06, 0.035, theta)          # (m, d nv, (d+1) nv)
+        Jh = np.zeros_like(Jr)
+        # J[t, a, b, k, ci] -> row a*d + k, column b*d + ci (ci < d) | d*nv + b (ci = d)
+        Jh[:, :, :d * nv] = J[..., :d].transpose(0, 1, 3, 2, 4).reshape(m, d * nv, d * nv)
+        Jh[:, :, d * nv:] = J[..., d].transpose(0, 1, 3, 2).reshape(m, d * nv, nv)
+        assert np.abs(Jh - Jr).max() < 1e-12 * np.abs(Jr).max()
+        assert abs(flux.sum() - S.outlet_flux(x, cells, pairs, un.reshape(-1))) < 1e-13
+        top = np.array([np.allclose(np.delete(x[cells[c]], lf, axis=0)[:, d - 1], 1.0) for c, lf in pairs])
+        assert abs(flux[top].sum() - S.outlet_flux(x, cells, pairs[top], un.reshape(-1))) < 1e-13
+
+
+def _gather_tables(cells, nrowptr, ncol, n):
+    """What hemo_set_node_graph builds on the device: slot of every (cell, a, b), segments sorted by source."""
+    E, nv = cells.shape
+    rowof = np.repeat(np.arange(n, dtype=np.int32), np.diff(nrowptr))
+    G = sp.csr_matrix((np.arange(len(ncol)) + 1, ncol, nrowptr), shape=(n, n))
+    ii = np.repeat(cells, nv, axis=1).reshape(-1)
+    jj = np.tile(cells, (1, nv)).reshape(-1)
+    slot = np.asarray(G[ii, jj]).reshape(-1).astype(np.int64) - 1
+    assert (slot >= 0).all()
+    src = np.arange(E * nv * nv)
+    order = np.lexsort((src, slot))
+    mseg_src = src[order].astype(np.int32)
+    mseg_ptr = np.concatenate([[0], np.cumsum(np.bincount(slot, minlength=len(ncol)))]).astype(np.int32)
+    vsrc = np.arange(E * nv)
+    vnode = cells.reshape(-1)
+    vorder = np.lexsort((vsrc, vnode))
+    vseg_src = vsrc[vorder].astype(np.int32)
+    vseg_ptr = np.concatenate([[0], np.cumsum(np.bincount(vnode, minlength=n))]).astype(np.int32)
+    return rowof, mseg_ptr, mseg_src, vseg_ptr, vseg_src
+
+
+def _pattern3d(nrowptr, ncol, n):
+    """CSR pattern in the device layout (k_pattern3d)."""
+    nnz_node = len(ncol)
+    rowptr = np.zeros(4 * n + 1, dtype=np.int64)
+    col = np.zeros(16 * nnz_node, dtype=np.int32)
+    for i in range(n):
+        r0, deg = nrowptr[i], nrowptr[i + 1] - nrowptr[i]
+        nb = ncol[r0:r0 + deg]
+        rowc = np.concatenate([(3 * nb[:, None] + np.arange(3)[None]).reshape(-1), 3 * n + nb])
+        for k in range(4):
+            rs = 12 * r0 + 4 * k * deg if k < 3 else 12 * nnz_node + 4 * r0
+            rowptr[3 * i + k if k < 3 else 3 * n + i] = rs
+            col[rs:rs + 4 * deg] = rowc
+    rowptr[4 * n] = 16 * nnz_node
+    return rowptr, col
+
+
+@pytest.mark.parametrize("with_bc", [False, True])
+@pytest.mark.parametrize("coef", [FACET_COEFS[0], FACET_COEFS[3]])
+def test_emulated_tet_assembly_matches_oracle(lib, coef, with_bc):
+    x, cells = _perturbed_cube(3, seed=4)
+    E, n = cells.shape[0], x.shape[0]
+    h = S.cell_diameter(x, cells)
+    rng = np.random.default_rng(11)
+    u, p, un = rng.standard_normal((n, 3)), rng.standard_normal(n), rng.standard_normal((n, 3))
+    f = np.array([0.3, -0.2, 0.1])
+    degs = dict(Fu=6, Fp=5, uu=6, up=5, pu=5, pp=4)          # small rules: the layout, not the quadrature, is under test
+    rules = {k: S.tet_gauss_jacobi(v) for k, v in degs.items()}
+    frule = S.triangle_facet_rule(4)
+    pairs = S.exterior_facets(cells)
+    # facet set: the faces x = 1 and z = 0 (some cells carry two tagged facets)
+    fx = np.array([np.delete(x[cells[c]], lf, axis=0) for c, lf in pairs])                # (m, 3, 3)
+    tagged = np.isclose(fx[:, :, 0], 1.0).all(axis=1) | np.isclose(fx[:, :, 2], 0.0).all(axis=1)
+    fpairs = pairs[tagged]
+    fcells, fmask = D.pairs_by_cell(fpairs)
+    assert (np.bincount(fpairs[:, 0]).max() == 2) and len(fcells) < len(fpairs)
+    # Dirichlet: velocity on x = 0 (one condition) and on y = 0 (a second one: edge dofs get diagonal 2), pressure on x = 1
+    bcs, bc_lists = [], None
+    g = np.zeros(4 * n)
+    if with_bc:
+        gu = rng.standard_normal(3 * n)
+        gp = rng.standard_normal(n)
+        n0 = np.nonzero(np.isclose(x[:, 0], 0.0))[0]
+        n1 = np.nonzero(np.isclose(x[:, 1], 0.0))[0]
+        n2 = np.nonzero(np.isclose(x[:, 0], 1.0))[0]
+        bcs = [("u", n0, gu), ("u", n1, 2.0 * gu), ("p", n2, gp)]
+        udofs = lambda nodes: (3 * nodes[:, None] + np.arange(3)[None]).reshape(-1)
+        bc_lists = [udofs(n0), udofs(n1), 3 * n + n2]
+    flag, mult, cellflag, g = D.dirichlet_arrays(n, cells, bcs, gdim=3)
+    if with_bc:
+        assert mult.max() == 2.0 and cellflag.sum() < E
+    prob = O3.Problem3D(x=x, cells=cells, dt=0.01, rho=1.3, mu=0.02, f=f, rules=rules,
+                        facet_sets=[O.FacetSet(pairs=fpairs, **coef)], facet_rule=frule)
+    sol = np.concatenate([u.reshape(-1), p])
+    A_ref, b_ref = O3.assemble_system(prob, sol, un.reshape(-1), g, bc_lists=bc_lists if with_bc else [])
+    # device-side tables and the emulated launch sequence
+    nrowptr, ncol = D.node_graph(cells, n)
+    rowof, mseg_ptr, mseg_src, vseg_ptr, vseg_src = _gather_tables(cells, nrowptr, ncol, n)
+    nnz_node = len(ncol)
+    for b, k in enumerate(("Fu", "Fp", "uu", "up", "pu", "pp")):
+        pts, wts = rules[k]
+        assert lib.sxh_set_rule(3, b, _p(_c(pts)), _p(_c(wts)), len(wts)) == 0
+    lib.sxh_set_params(0.01, 1.3, 0.02, _p(f), O.EPS0, 0.5, 1.0)
+    Ae, Fe = np.zeros(256 * E), np.zeros(16 * E)
+    vals, bvec, y, flux = np.zeros(16 * nnz_node), np.zeros(4 * n), np.zeros(4 * n), np.zeros(1)
+    xv = rng.standard_normal(4 * n)
+    unf = _c(un.reshape(-1))
+    lib.txh_assemble(E, n, ctypes.c_int64(nnz_node), _p(_c(cells, np.int32)), _p(_c(x)), _p(h), _p(sol), _p(unf), _p(unf),
+                     _p(nrowptr), _p(ncol), _p(_c(rowof, np.int32)), _p(mseg_ptr), _p(mseg_src), _p(vseg_ptr), _p(vseg_src),
+                     len(fcells), _p(fcells), _p(fmask), _p(_coef8(coef)), _p(_c(frule[0])), _p(_c(frule[1])), len(frule[1]),
+                     _p(flag) if with_bc else None, _p(mult), _p(cellflag), _p(g), _p(xv), _p(Ae), _p(Fe), _p(vals), _p(bvec),
+                     _p(y), _p(flux))
+    rowptr, col = _pattern3d(nrowptr, ncol, n)
+    A_dev = sp.csr_matrix((vals, col, rowptr), shape=(4 * n, 4 * n))
+    assert A_dev.has_sorted_indices or np.all(np.diff(col[rowptr[5]:rowptr[6]]) > 0)
+    diff = (A_dev - A_ref).tocoo()
+    assert np.linalg.norm(diff.data) < 1e-12 * np.linalg.norm(A_ref.data)
+    assert np.linalg.norm(bvec - b_ref) < 1e-12 * np.linalg.norm(b_ref)
+    assert np.linalg.norm(y - A_ref @ xv) < 1e-12 * np.linalg.norm(A_ref @ xv)
+    assert abs(flux[0] - S.outlet_flux(x, cells, fpairs, un.reshape(-1))) < 1e-13
+    if with_bc:
+        # Dirichlet rows: unit (or multiplicity) diagonal, x - g on the right-hand side
+        d = np.nonzero(flag)[0]
+        assert np.array_equal(A_dev.diagonal()[d], mult[d]) and np.allclose(bvec[d], sol[d] - g[d], atol=0, rtol=0)
+
+
+@pytest.mark.parametrize("sweeps", [1, 4, 5])
+def test_emulated_tet_velocity_solve(lib, sweeps):
+    """Items of the first 3-D preconditioner: 3x3 node-diagonal inverses of A00, t_u = r_u - A01 z_p and
+    damped block-Jacobi sweeps, on a random matrix stored in the device CSR layout."""
+    x, cells = _perturbed_cube(2, seed=1)
+    n = x.shape[0]
+    nrowptr, ncol = D.node_graph(cells, n)
+    nnz_node = len(ncol)
+    rowptr, col = _pattern3d(nrowptr, ncol, n)
+    rng = np.random.default_rng(2)
+    vals = rng.standard_normal(16 * nnz_node)
+    A = sp.csr_matrix((vals, col, rowptr), shape=(4 * n, 4 * n))
+    A = (A + sp.diags(np.concatenate([8.0 * np.ones(3 * n), np.ones(n)]))).tocsr()      # dominant velocity diagonal
+    A.sort_indices()
+    assert np.array_equal(A.indices, col)
+    vals = np.ascontiguousarray(A.data)
+    rows = np.repeat(np.arange(n), np.diff(nrowptr))
+    diagslot = np.nonzero(rows == ncol)[0].astype(np.int32)
+    ru, zp = rng.standard_normal(3 * n), rng.standard_normal(n)
+    dinv, tu, tmp, zu = np.zeros(9 * n), np.zeros(3 * n), np.zeros(3 * n), np.zeros(3 * n)
+    omega = 2.0 / 3.0
+    lib.txh_velocity_solve(n, ctypes.c_int64(nnz_node), _p(nrowptr), _p(ncol), _p(diagslot), _p(vals), _p(ru), _p(zp), sweeps,
+                           ctypes.c_double(omega), _p(dinv), _p(tu), _p(tmp), _p(zu))
+    A00, A01 = A[:3 * n, :3 * n].toarray(), A[:3 * n, 3 * n:].toarray()
+    Dinv = np.zeros((3 * n, 3 * n))
+    for i in range(n):
+        Dinv[3 * i:3 * i + 3, 3 * i:3 * i + 3] = np.linalg.inv(A00[3 * i:3 * i + 3, 3 * i:3 * i + 3])
+    assert np.abs(dinv.reshape(n, 3, 3) - np.array([Dinv[3 * i:3 * i + 3, 3 * i:3 * i + 3] for i in range(n)])).max() < 1e-12
+    t_ref = ru - A01 @ zp
+    assert np.abs(tu - t_ref).max() < 1e-12 * np.abs(t_ref).max()
+    z = np.zeros(3 * n)
+    for _ in range(sweeps):
+        z = z + omega * Dinv @ (t_ref - A00 @ z)
+    assert np.abs(zu - z).max() < 1e-12 * np.abs(z).max()
