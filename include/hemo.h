@@ -125,7 +125,8 @@ int hemo_get_pattern(hemo_ctx* ctx, int64_t* rowptr_dev, int32_t* colind_dev);
  * Basix rule selected by FFCx at form() (:188-189). */
 int hemo_set_quadrature(hemo_ctx* ctx, int block, const double* pts_host,
                         const double* wts_host, int nq);
-/* Facet rule on [0,1] shared by all exterior-facet integrals. */
+/* Facet rule shared by all exterior-facet integrals: points on [0,1] (2-D cells) or (s, t) pairs on the
+ * reference triangle (tetrahedra). */
 int hemo_set_facet_quadrature(hemo_ctx* ctx, const double* pts_host, const double* wts_host, int nq);
 int hemo_set_params(hemo_ctx* ctx, const hemo_params* p);
 /* Time scheme of the forms: they are evaluated at u_e = theta*u + (1-theta)*u_prev with the time
@@ -166,19 +167,27 @@ int hemo_outlet_flux(hemo_ctx* ctx, int set_id, const double* un_dev, double* q_
  * pressure mass (n doubles) for the Schur-complement approximation. */
 int hemo_assemble_laplace_mass(hemo_ctx* ctx, double* lap_vals_dev, double* mass_dev);
 
-/* ---- tetrahedra: batched element tensors (first 3-D piece) ------------------------------------
+/* ---- tetrahedra ------------------------------------------------------------------------------
  * FFCx tetrahedron kernels of the same forms (src/solvers/stabilized_schur.py:60-123 with
  * `mesh.topology.cell_name() == "tetrahedron"`, e.g. src/scenarios/taylor_green.py:34).  Element
  * tensors only: Ae SoA [(a*4+b)*16 + ri*4+ci][E], Fe SoA [a*4+comp][E] with ri/ci/comp in
- * (u_x, u_y, u_z, p); there is no 3-D scatter / solve yet.  Uses hemo_set_params (dt, rho, mu,
+ * (u_x, u_y, u_z, p) (hemo_tet_element_tensors: the cell kernel alone).  Uses hemo_set_params (dt, rho, mu,
  * eps0; f from f3_host) and hemo_set_time_scheme (theta, a0).  x: 3n, cells: 4E, sol = [u (3n) | p (n)],
  * un / uh: 3n (uh NULL = un).  Rules: points on the reference tetrahedron, weights sum to 1/6,
  * nq <= 343; one per block form like hemo_set_quadrature. */
-/* With hemo_set_cell_type(HEMO_CELL_TETRAHEDRON) (x: 3n doubles, cells: 4E, sol = [u (3n) | p (n)]) the
- * generic entry points hemo_set_mesh, hemo_set_node_graph, hemo_set_quadrature, hemo_matrix_nnz (16 *
- * nnz_node), hemo_get_pattern (4n+1 row pointers), hemo_assemble_jacobian and hemo_assemble_residual
- * assemble the cell integrals into the CSR create_matrix_block builds (:191-193); facet terms,
- * Dirichlet conditions and the solver are not implemented in 3-D yet (HEMO_ESTATE). */
+/* With hemo_set_cell_type(HEMO_CELL_TETRAHEDRON) (x: 3n doubles, cells: 4E, sol = [u (3n) | p (n)], all
+ * dof-sized arrays 4n) the generic entry points work on tetrahedra:
+ *   hemo_set_mesh, hemo_set_node_graph, hemo_set_quadrature, hemo_matrix_nnz (16 * nnz_node),
+ *   hemo_get_pattern (4n+1 row pointers; the CSR create_matrix_block builds, :191-193),
+ *   hemo_set_facet_quadrature (points (s, t) on the reference triangle, nq*2 doubles, weights sum 1/2,
+ *   nq <= 16), hemo_set_facet_set (4-bit mask, local facet i opposite local vertex i), hemo_set_bc,
+ *   hemo_assemble_jacobian / hemo_assemble_residual (cell + exterior-facet integrals, Dirichlet rows and
+ *   columns, lifting, set_bc), hemo_outlet_flux, hemo_spmv, hemo_assemble_laplace_mass,
+ *   hemo_pc_setup / hemo_pc_apply / hemo_fgmres with the first 3-D preconditioner (only the
+ *   scalar pressure hierarchy `which = 1` is needed; the velocity block runs 4 * amg_cycles_u damped
+ *   block-Jacobi sweeps).
+ * Still 2-D only (HEMO_ESTATE on tetrahedra): the post-processing kernels, SELFP / assembled Schur
+ * operators, partition masks. */
 int hemo_set_body_force3(hemo_ctx* ctx, const double* f3_host);
 int hemo_tet_set_quadrature(hemo_ctx* ctx, int block, const double* pts_host, const double* wts_host, int nq);
 int hemo_tet_element_tensors(hemo_ctx* ctx, int n_nodes, int n_cells, const double* x_dev,
