@@ -17,7 +17,7 @@ import numpy as np
 __all__ = [
     "Mesh", "MeshTags", "SerialComm", "meshtags", "locate_entities_boundary",
     "exterior_facet_indices", "create_unit_square", "create_rectangle",
-    "create_mesh",
+    "create_mesh", "create_unit_cube", "create_box",
 ]
 
 
@@ -300,3 +300,34 @@ def _split_grid(nx: int, ny: int, diagonal: str = "right") -> np.ndarray:
 def create_unit_square(comm, nx: int, ny: int, diagonal: str = "right", cell_type: str = "triangle") -> Mesh:
     """Same call shape as `dolfinx.mesh.create_unit_square(comm, nx, ny[, cell_type])`."""
     return create_rectangle((0.0, 0.0), (1.0, 1.0), nx, ny, diagonal, comm, cell_type)
+
+
+def create_box(p0, p1, nx: int, ny: int, nz: int, comm=None) -> Mesh:
+    """Structured tetrahedral mesh of a box: every grid cube is split into the six Kuhn tetrahedra
+    around its main diagonal (conforming across cubes), vertices numbered x fastest.  Same role as
+    `dolfinx.mesh.create_box(..., CellType.tetrahedron)`; DOLFINx's own numbering cannot be reproduced
+    (SURVEY App. A), parity is defined relative to the arrays handed over."""
+    xs = np.linspace(p0[0], p1[0], nx + 1)
+    ys = np.linspace(p0[1], p1[1], ny + 1)
+    zs = np.linspace(p0[2], p1[2], nz + 1)
+    Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+    pts = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    base = np.stack([i.ravel(), j.ravel(), k.ravel()], axis=1)
+    vid = lambda q: (q[:, 2] * (ny + 1) + q[:, 1]) * (nx + 1) + q[:, 0]
+    cells = []
+    for perm in ((0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)):
+        v = [base.copy()]
+        for ax in perm:
+            w = v[-1].copy()
+            w[:, ax] += 1
+            v.append(w)
+        cells.append(np.stack([vid(q) for q in v], axis=1))
+    cells = np.stack(cells, axis=1).reshape(-1, 4).astype(np.int32)     # the six tetrahedra of a cube are consecutive
+    return Mesh(pts, cells, comm)
+
+
+def create_unit_cube(comm, nx: int, ny: int, nz: int) -> Mesh:
+    """Same call shape as `dolfinx.mesh.create_unit_cube(comm, nx, ny, nz)` (tetrahedra; reference
+    src/scenarios/taylor_green.py:34)."""
+    return create_box((0.0, 0.0, 0.0), (1.0, 1.0, 1.0), nx, ny, nz, comm)

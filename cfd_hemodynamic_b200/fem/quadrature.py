@@ -82,6 +82,21 @@ def triangle_gauss_jacobi(degree: int):
     return pts, wts
 
 
+def tetrahedron_rule(degree: int):
+    """Collapsed-coordinate Gauss–Jacobi rule on the reference tetrahedron {x,y,z>=0, x+y+z<=1}
+    (weights sum to 1/6, ((degree + 2) // 2)^3 points, exact to `degree`).  Basix picks a
+    Xiao–Gimbutas scheme with fewer points for these degrees (122 points at degree 12); its tables are
+    not available here, and the rule is a run-time input of the library (`quadrature=` on the solver)."""
+    m = (degree + 2) // 2
+    px, wx = _gauss_jacobi(m, 2.0)
+    py, wy = _gauss_jacobi(m, 1.0)
+    pz, wz = _gauss_jacobi(m, 0.0)
+    X, Y, Z = np.meshgrid(px, py, pz, indexing="ij")
+    WX, WY, WZ = np.meshgrid(wx, wy, wz, indexing="ij")
+    pts = np.stack([X, Y * (1.0 - X), Z * (1.0 - X) * (1.0 - Y)], axis=-1).reshape(-1, 3)
+    return np.ascontiguousarray(pts), np.ascontiguousarray((WX * WY * WZ).reshape(-1))
+
+
 def expand_orbits(centroid_w, s21, s111):
     """Expand D3 orbits to points (x, y) on the reference triangle and weights
     (sum 1/2).  s21: [(w, a)] → barycentric permutations of (a, a, 1-2a);

@@ -41,8 +41,15 @@ class NpyWriter:
 
 def l2_norm_sq(mesh, u: Function) -> float:
     """assemble_scalar(form(inner(u, u) * dx)) for P1 functions (exact)."""
-    x = mesh.geometry.x[:, :2]
     cells = mesh.geometry.dofmap
+    if mesh.topology.cell_name() == "tetrahedron":
+        X = mesh.geometry.x[cells]                             # (E, 4, 3)
+        det = np.abs(np.linalg.det(np.stack([X[:, j + 1] - X[:, 0] for j in range(3)], axis=2)))
+        bs = u.function_space.dofmap.index_map_bs
+        vals = u.x.array.reshape(-1, bs)[cells]                # (E, 4, bs)
+        Mloc = (np.ones((4, 4)) + np.eye(4)) / 120.0           # int phi_a phi_b over the reference tetrahedron
+        return float(np.einsum("e,ab,eak,ebk->", det, Mloc, vals, vals))
+    x = mesh.geometry.x[:, :2]
     X = x[cells]
     if cells.shape[1] == 4:
         # Q1 quadrilaterals: 3 x 3 Gauss points (exact on affine cells)

@@ -135,6 +135,8 @@ class SolverBase(ABC):
             pairs = self._wss_pairs
         except AttributeError:
             return
+        if self.mesh.topology.cell_name() == "tetrahedron":
+            return self._assemble_wss_tetrahedron(pairs)
         x = self.mesh.geometry.x[:, :2]
         cells = self.mesh.geometry.dofmap[pairs[:, 0]]
         lf = pairs[:, 1]
@@ -166,6 +168,30 @@ class SolverBase(ABC):
         out[:] = 0.0
         np.add.at(out, cells[ar, va], 0.5 * Tt)
         np.add.at(out, cells[ar, vb], 0.5 * Tt)
+
+    def _assemble_wss_tetrahedron(self, pairs):
+        """The same traction form on P1 tetrahedra: eps(u) is constant on the cell, the outward normal
+        of local facet lf is -grad(phi_lf) / |grad(phi_lf)|, and (1/|F|) int_F phi_a ds = 1/3 on the
+        three vertices of a triangular facet."""
+        cells = self.mesh.geometry.dofmap[pairs[:, 0]]
+        lf = pairs[:, 1]
+        X = self.mesh.geometry.x[cells]                        # (m, 4, 3)
+        ar = np.arange(cells.shape[0])
+        J = np.stack([X[:, j + 1] - X[:, 0] for j in range(3)], axis=2)
+        ghat = np.vstack([-np.ones((1, 3)), np.eye(3)])
+        dphi = np.einsum("aj,eji->eai", ghat, np.linalg.inv(J))
+        nrm = -dphi[ar, lf]
+        nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+        U = self.u_sol.x.array.reshape(-1, 3)[cells]
+        G = np.einsum("eai,eaj->eij", dphi, U)
+        eps = 0.5 * (G + np.swapaxes(G, 1, 2))
+        T = -2.0 * float(self.mu.value) * np.einsum("eij,ej->ei", eps, nrm)
+        Tt = T - np.einsum("ei,ei->e", T, nrm)[:, None] * nrm
+        out = self.shear_stress.x.array.reshape(-1, 3)
+        out[:] = 0.0
+        for a in range(4):
+            on = lf != a                                        # vertex a belongs to the facet opposite lf
+            np.add.at(out, cells[on, a], Tt[on] / 3.0)
 
     def _assemble_wss_quadrilateral(self, X, cells, lf):
         """Same traction form on Q1 quadrilaterals: grad(u) varies along the facet, so

@@ -43,13 +43,14 @@ SNES_DIVERGED_FNORM_NAN = -4
 
 class StabilizedSchurB200(SolverBase):
     variant = "schur"          # "schur" | "backflow" | "pressure_backflow"
+    _supported_cells = ("triangle", "quadrilateral")
 
     def __init__(self, mesh, dt, rho, mu, f, initial_velocity: Callable | None = None, **kw):
         super().__init__(mesh, dt, rho, mu, f)
         cell = mesh.topology.cell_name()
-        if cell not in ("triangle", "quadrilateral"):
+        if cell not in self._supported_cells:
             raise NotImplementedError(
-                f"cell type {cell}: P1-P1 triangles and Q1-Q1 quadrilaterals are implemented on the device")
+                f"cell type {cell}: {', '.join(self._supported_cells)} cells are implemented on the device for this solver")
         self._quad = cell == "quadrilateral"
         if int(kw.pop("p_grade", 1)) != 1:
             raise NotImplementedError("p_grade != 1: only P1-P1 is implemented on the device")

@@ -1,5 +1,6 @@
 """`--solver stabilized_schur` on B200: SUPG/PSPG/LSIC-stabilised P1–P1
 Navier–Stokes, Newton, FGMRES with a Schur-complement block preconditioner.
+Triangles, quadrilaterals and (through `_stabilized_tet`) tetrahedra.
 
 Drop-in for reference src/solvers/stabilized_schur.py: same module-level
 `Solver` class, same constructor / `setup` / `solveStep` contract, loaded by
@@ -9,10 +10,10 @@ from typing import Callable
 
 import numpy as np
 
-from ._stabilized_common import StabilizedSchurB200
+from ._stabilized_tet import StabilizedSchurTetB200
 
 
-class Solver(StabilizedSchurB200):
+class Solver(StabilizedSchurTetB200):
     MAX_ITER = 20
     variant = "schur"
 

@@ -168,3 +168,53 @@ def test_tet_newton_step_matches_oracle():
     ue = exact_velocity(x, t).reshape(-1)
     assert np.linalg.norm(got[:3 * n] - ue) / np.linalg.norm(ue) < 5e-3
     hemo.close()
+
+
+def test_taylor_green_plugin_matches_oracle(tmp_path):
+    """The reference's 3-D scenario through the plugin API (`Scenario` -> `Solver.setup/solveStep` on
+    tetrahedra, src/scenarios/taylor_green.py) against the oracle's LU Newton: 1e-8 relative L2 after
+    two steps, both sides converged tightly; then the reference time loop itself (`Scenario.solve`,
+    boundary data refreshed after every step, error log against the exact solution)."""
+    from cfd_hemodynamic_b200.fem import quadrature as Q
+    from cfd_hemodynamic_b200.src.scenarios.taylor_green import TaylorGreenSimulation
+    nc, dt, steps, mu = 6, 0.005, 2, 1.0
+    tight = dict(snes_rtol=1e-12, snes_stol=0.0, ksp_rtol=1e-11, ksp_restart=100, amg_cycles_p=2)
+    sc = TaylorGreenSimulation("stabilized_schur", dt, steps * dt, rho=1, mu=mu, n=nc, **tight)
+    s = sc.solver
+    assert s._tet and not s._nullspace           # Dirichlet pressure on the boundary: no constant-pressure mode
+    x = sc.mesh.geometry.x
+    cells = sc.mesh.geometry.dofmap
+    n = x.shape[0]
+    rules = {k: Q.tetrahedron_rule(d) for k, d in dict(Fu=12, Fp=11, uu=12, up=11, pu=11, pp=10).items()}
+    ext = S.exterior_facets(cells)
+    prob = O3.Problem3D(x=x, cells=cells, dt=dt, rho=1.0, mu=mu, f=np.zeros(3), rules=rules,
+                        facet_sets=[O.FacetSet(pairs=ext, a_p=1.0, a_g=1.0)], facet_rule=Q.triangle_rule(2))
+    boundary = np.nonzero((np.abs(x - 0.5) > 0.5 - 1e-12).any(axis=1))[0]
+    prob.bc_dofs = np.concatenate([(3 * boundary[:, None] + np.arange(3)[None, :]).reshape(-1), 3 * n + boundary])
+    un = sc.exact_velocity(0)(x.T).T.reshape(-1)
+    xk = np.concatenate([un, np.zeros(n)])       # the reference starts from p = 0 (p_prev is never interpolated)
+    t = 0.0
+    for _ in range(steps):
+        t += dt
+        sc.update_boundary_conditions(t)
+        s.solveStep()
+        s.u_prev.x.array[:] = s.u_sol.x.array[:]
+        s.p_prev.x.array[:] = s.p_sol.x.array[:]
+        g = np.concatenate([sc.exact_velocity(t)(x.T).T.reshape(-1), sc.exact_pressure(t)(x.T)])
+        xk, _ = O3.newton_step(prob, xk, un, g, rtol=1e-12)
+        un = xk[:3 * n].copy()
+    eu = np.linalg.norm(s.u_sol.x.array - xk[:3 * n]) / np.linalg.norm(xk[:3 * n])
+    ep = np.linalg.norm(s.p_sol.x.array - xk[3 * n:]) / np.linalg.norm(xk[3 * n:])
+    assert eu < 1e-8 and ep < 1e-8, (eu, ep)
+    ue = sc.exact_velocity(t)(x.T).T.reshape(-1)
+    assert np.linalg.norm(s.u_sol.x.array - ue) / np.linalg.norm(ue) < 5e-3
+
+    # the reference loop (default tolerances): runs, logs the error against the exact solution
+    sc2 = TaylorGreenSimulation("stabilized_schur", dt, 3 * dt, rho=1, mu=mu, n=4)
+    sc2.write_output = False
+    out = sc2.solve(str(tmp_path / "tg"))
+    assert sc2.steps_done == 3
+    errs = [float(line.split("error =")[1]) for line in open(f"{out}/err.txt")]
+    assert len(errs) == 4 and errs[0] < 1e-12 and max(errs) < 5e-2
+    norms = open(f"{out}/norms.txt").read()
+    assert "L2 norm of velocity" in norms

@@ -176,3 +176,82 @@ def test_adaptive_plugin_ramp_host_only():
     assert s.target_dt == 0.01 and s.step_count_adapt == 0
     s._set_dt(0.002)
     assert float(s.dt.value) == 0.002
+
+
+# ---- tetrahedra (taylor_green) -------------------------------------------------------------
+def test_unit_cube_mesh_and_tetrahedron_rule():
+    from math import factorial as fa
+    from cfd_hemodynamic_b200.fem import quadrature as Q
+    m = M.create_unit_cube(None, 3, 2, 4)
+    assert m.topology.cell_name() == "tetrahedron" and m.topology.dim == 3 and m.geometry.dim == 3
+    X = m.geometry.x[m.geometry.dofmap]
+    det = np.linalg.det(np.stack([X[:, j + 1] - X[:, 0] for j in range(3)], axis=2))
+    assert m.num_cells == 6 * 24 and abs(np.abs(det).sum() / 6.0 - 1.0) < 1e-14 and np.abs(det).min() > 1e-3
+    ext = M.exterior_facet_indices(m.topology)
+    assert len(ext) == 2 * 2 * (3 * 2 + 2 * 4 + 3 * 4)                  # two triangles per boundary square
+    # conforming: every interior facet is shared by exactly two cells
+    m.topology.create_connectivity(2, 3)
+    assert set(np.unique(m.topology._f2c_count)) == {1, 2}
+    pts, wts = Q.tetrahedron_rule(12)
+    assert len(wts) == 343 and abs(wts.sum() - 1.0 / 6.0) < 1e-15 and (wts > 0).all()
+    for a, b, c in ((12, 0, 0), (0, 12, 0), (0, 0, 12), (4, 4, 4), (5, 3, 1)):
+        exact = fa(a) * fa(b) * fa(c) / fa(a + b + c + 3)
+        assert abs(np.sum(wts * pts[:, 0] ** a * pts[:, 1] ** b * pts[:, 2] ** c) - exact) < 1e-16
+
+
+def test_taylor_green_scenario_tables_host_only():
+    from cfd_hemodynamic_b200.src.scenarios.taylor_green import TaylorGreenSimulation
+    sc = TaylorGreenSimulation("stabilized_schur", 0.005, 0.01, rho=1, mu=1.0, n=3, host_only=True)
+    s = sc.solver
+    n = 4 ** 3
+    assert s.hemo is None and s._tet and s.n == n and s.N == 4 * n
+    assert s.V.dofmap.index_map_bs == 3 and s.u_prev.x.array.shape == (3 * n,)
+    x = sc.mesh.geometry.x
+    # initial velocity = exact solution at t = 0, interleaved per node
+    assert np.allclose(s.u_prev.x.array.reshape(n, 3), sc.exact_velocity(0)(x.T).T, atol=0, rtol=0)
+    boundary = np.nonzero((np.abs(x - 0.5) > 0.5 - 1e-12).any(axis=1))[0]
+    (bu,), (bp,) = s.bcu_d, s.bcp_d
+    assert np.array_equal(bu.block_dofs, boundary) and np.array_equal(bp.block_dofs, boundary)
+    assert len(boundary) == n - 2 ** 3
+    du, _ = bu.dof_indices()
+    assert np.array_equal(du, (3 * boundary[:, None] + np.arange(3)[None]).reshape(-1))
+    # boundary data follow the exact solution in time
+    sc.update_boundary_conditions(0.3)
+    bu.update(); bp.update()
+    assert np.allclose(bu.g.x.array[du], sc.exact_velocity(0.3)(x.T).T.reshape(-1)[du], atol=0, rtol=0)
+    assert np.allclose(bp.g.x.array[boundary], sc.exact_pressure(0.3)(x.T)[boundary], atol=0, rtol=0)
+    # the all-facet term of stabilized_schur.py:79 is registered on every exterior triangle
+    facets, coef = s._facet_tables[0]
+    assert len(facets) == 6 * 2 * 9 and coef == {"a_p": 1.0, "a_g": 1.0}
+    with pytest.raises(NotImplementedError):
+        s.export_tables()
+
+
+def test_host_postprocessing_on_tetrahedra():
+    """l2_norm_sq and the wall-shear-stress vector on P1 tetrahedra (host post-processing of Scenario.solve)."""
+    from cfd_hemodynamic_b200.src.scenario import l2_norm_sq
+    from cfd_hemodynamic_b200.src.scenarios.taylor_green import TaylorGreenSimulation
+    sc = TaylorGreenSimulation("stabilized_schur", 0.005, 0.01, rho=1, mu=0.7, n=2, host_only=True)
+    s = sc.solver
+    x = sc.mesh.geometry.x
+    # int (x + 2y)^2 + z^2 + 1 over the unit cube = 1/3 + 4/3 + 2*1/4*... computed exactly: P1 fields integrate
+    # quadratics exactly with the consistent mass matrix
+    s.u_sol.x.array[:] = np.stack([x[:, 0] + 2 * x[:, 1], x[:, 2], np.ones(len(x))], axis=1).reshape(-1)
+    exact = (1 / 3 + 4 / 3 + 2 * 2 * 0.25) + 1 / 3 + 1.0
+    assert abs(l2_norm_sq(sc.mesh, s.u_sol) - exact) < 1e-13
+    s.p_sol.x.array[:] = x[:, 0] * 0 + 2.0
+    assert abs(l2_norm_sq(sc.mesh, s.p_sol) - 4.0) < 1e-13
+    # shear flow u = (gamma z, 0, 0): traction on the wall z = 0 (n = -e_z) is T = -2 mu eps n = (mu gamma, 0, 0),
+    # purely tangential; every interior node of that face collects (1/3) T from each of its 6 facets... checked
+    # through the sum over the face: sum_i wss_i = (#facets on the face) * T
+    gamma = 1.3
+    s.u_sol.x.array[:] = np.stack([gamma * x[:, 2], 0 * x[:, 0], 0 * x[:, 0]], axis=1).reshape(-1)
+    s.initStressForm()
+    s.assemble_wss()
+    w = s.shear_stress.x.array.reshape(-1, 3)
+    bottom_only = np.isclose(x[:, 2], 0.0) & (np.abs(x[:, :2] - 0.5) < 0.5 - 1e-12).all(axis=1)
+    assert bottom_only.sum() == 1
+    # the single interior node of the bottom face touches 6 or fewer bottom triangles, each giving T / 3
+    T = np.array([0.7 * gamma, 0.0, 0.0])
+    k = np.round(w[bottom_only][0, 0] / (T[0] / 3.0))
+    assert 4 <= k <= 8 and np.allclose(w[bottom_only][0], k * T / 3.0, atol=1e-14)
