@@ -18,6 +18,8 @@
 #include "simplex_element.cuh"
 #include "tet_items.cuh"
 
+enum { TET_JAC_ALL = 0, TET_JAC_FLAGGED = 1, TET_JAC_NONE = 2 };
+
 struct TetRules {
     SimplexRule<3> r[HEMO_NRULES];
     int alias[HEMO_NRULES];          // lowest block id with an identical rule
@@ -43,7 +45,10 @@ __global__ void __launch_bounds__(128)
 k_tet_cell_tensors(int E, int n, const int32_t* __restrict__ cells, const double* __restrict__ x,
                    const double* __restrict__ h, const double* __restrict__ sol, const double* __restrict__ un,
                    const double* __restrict__ uh, HemoForm par, double f0, double f1, double f2,
-                   const TetRules* __restrict__ rules, double* __restrict__ Ae, double* __restrict__ Fe) {
+                   const TetRules* __restrict__ rules, int jac_mode, const uint8_t* __restrict__ jac_cells,
+                   double* __restrict__ Ae, double* __restrict__ Fe) {
+    // jac_mode: TET_JAC_ALL = element Jacobian of every cell, TET_JAC_FLAGGED = only where jac_cells[c] != 0
+    // (residual pass: the lifting needs it on Dirichlet-adjacent cells), TET_JAC_NONE = residual only
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= E) return;
     SimplexCell<3> cd;
@@ -120,6 +125,7 @@ k_tet_cell_tensors(int E, int n, const int32_t* __restrict__ cells, const double
             Fe[(a * 4 + 3) * stride + c] = cd.detJ * rp.m1[a] * cd.divu + acc / par.rho;
         }
     }
+    if (jac_mode == TET_JAC_NONE || (jac_mode == TET_JAC_FLAGGED && !jac_cells[c])) return;
     // ---- Jacobian: rules UU, UP, PU, PP (alias = lowest identical block id among all six)
     {
         double T1up[4], T1pu[4], T1[4], T0, T0pp = 0.0, Lt;
@@ -179,10 +185,10 @@ extern "C" int hemo_tet_set_quadrature(hemo_ctx* ctx, int block, const double* p
     return 0;
 }
 
-extern "C" int hemo_tet_element_tensors(hemo_ctx* ctx, int n_nodes, int n_cells, const double* x_dev,
-                                        const int32_t* cells_dev, const double* h_dev, const double* sol_dev,
-                                        const double* un_dev, const double* uh_dev, const double* f3_host,
-                                        double* Ae_dev, double* Fe_dev) {
+static int tet_launch_cells(hemo_ctx* ctx, int n_nodes, int n_cells, const double* x_dev, const int32_t* cells_dev,
+                            const double* h_dev, const double* sol_dev, const double* un_dev, const double* uh_dev,
+                            const double* f3_host, int jac_mode, const uint8_t* jac_cells, double* Ae_dev,
+                            double* Fe_dev) {
     if (!ctx || n_nodes <= 0 || n_cells <= 0 || !x_dev || !cells_dev || !h_dev || !sol_dev || !un_dev || !f3_host ||
         !Ae_dev || !Fe_dev)
         return HEMO_EINVAL;
@@ -198,9 +204,17 @@ extern "C" int hemo_tet_element_tensors(hemo_ctx* ctx, int n_nodes, int n_cells,
     hemo_form_finalize(ctx->par);
     k_tet_cell_tensors<<<hemo_grid(n_cells, 128), 128, 0, ctx->stream>>>(
         n_cells, n_nodes, cells_dev, x_dev, h_dev, sol_dev, un_dev, uh_dev ? uh_dev : un_dev, ctx->par, f3_host[0],
-        f3_host[1], f3_host[2], st->dev, Ae_dev, Fe_dev);
+        f3_host[1], f3_host[2], st->dev, jac_mode, jac_cells, Ae_dev, Fe_dev);
     HEMO_LAUNCH_CHECK(ctx);
     return 0;
+}
+
+extern "C" int hemo_tet_element_tensors(hemo_ctx* ctx, int n_nodes, int n_cells, const double* x_dev,
+                                        const int32_t* cells_dev, const double* h_dev, const double* sol_dev,
+                                        const double* un_dev, const double* uh_dev, const double* f3_host,
+                                        double* Ae_dev, double* Fe_dev) {
+    return tet_launch_cells(ctx, n_nodes, n_cells, x_dev, cells_dev, h_dev, sol_dev, un_dev, uh_dev, f3_host, TET_JAC_ALL,
+                            nullptr, Ae_dev, Fe_dev);
 }
 
 // ---------------------------------------------------------------------------
@@ -236,10 +250,12 @@ __global__ void __launch_bounds__(128)
 k_tet_facets(int m, int64_t E, int n, const int32_t* __restrict__ fcells, const int32_t* __restrict__ fmask,
              hemo_facet_coef co, SimplexFacetRule<3> fr, const int32_t* __restrict__ cells,
              const double* __restrict__ x, const double* __restrict__ h, const double* __restrict__ sol,
-             const double* __restrict__ un, HemoForm par, bool want_jac, double* __restrict__ Ae,
-             double* __restrict__ Fe) {
+             const double* __restrict__ un, HemoForm par, int jac_mode, const uint8_t* __restrict__ jac_cells,
+             double* __restrict__ Ae, double* __restrict__ Fe) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m) return;
+    // the derivative goes into Ae exactly where the cell kernel of this pass wrote Ae
+    const bool want_jac = jac_mode == TET_JAC_ALL || (jac_mode == TET_JAC_FLAGGED && jac_cells[fcells[t]]);
     tet_facet_item(t, E, n, fcells, fmask, co, fr, cells, x, h, sol, un, par, want_jac, Ae, Fe);
 }
 
@@ -329,14 +345,15 @@ static bool tet_facet_set_active(const HemoFacetSet& fs) {
     return fs.m > 0 && (c.a_p != 0.0 || c.pconst != 0.0 || c.a_g != 0.0 || c.a_s != 0.0 || c.a_n != 0.0 || c.a_b != 0.0);
 }
 
-// cell tensors (Jacobian + residual in one pass), then the facet terms of every active set
-static int tet_cells(hemo_ctx* ctx, const double* x_dev, const double* un_dev, bool facet_jac) {
+// cell tensors (residual, and the Jacobian where jac_mode asks for it), then the facet terms of every active set
+static int tet_cells(hemo_ctx* ctx, const double* x_dev, const double* un_dev, int jac_mode) {
     if (!ctx->cells || !ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / node graph not set");
     int rc = hemo_ensure_elem(ctx, (size_t)256 * ctx->E, (size_t)16 * ctx->E);
     if (rc) return rc;
     const double f3[3] = {ctx->par.f[0], ctx->par.f[1], ctx->fz};
-    if ((rc = hemo_tet_element_tensors(ctx, ctx->n, ctx->E, ctx->x, ctx->cells, ctx->h, x_dev, un_dev, ctx->uh, f3,
-                                       ctx->Ae, ctx->Fe)))
+    if (!ctx->have_par) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_set_params not called");
+    if ((rc = tet_launch_cells(ctx, ctx->n, ctx->E, ctx->x, ctx->cells, ctx->h, x_dev, un_dev, ctx->uh, f3, jac_mode,
+                               ctx->cellflag, ctx->Ae, ctx->Fe)))
         return rc;
     hemo_tet_state* st = tet_state(ctx);
     for (int s = 0; s < HEMO_MAX_FACET_SETS; ++s) {
@@ -345,14 +362,14 @@ static int tet_cells(hemo_ctx* ctx, const double* x_dev, const double* un_dev, b
         if (!st->have_frule) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_set_facet_quadrature not called (triangle rule)");
         k_tet_facets<<<hemo_grid(fs.m, 128), 128, 0, ctx->stream>>>(fs.m, ctx->E, ctx->n, fs.cells, fs.mask, fs.coef,
                                                                     st->frule, ctx->cells, ctx->x, ctx->h, x_dev, un_dev,
-                                                                    ctx->par, facet_jac, ctx->Ae, ctx->Fe);
+                                                                    ctx->par, jac_mode, ctx->cellflag, ctx->Ae, ctx->Fe);
         HEMO_LAUNCH_CHECK(ctx);
     }
     return 0;
 }
 
 int hemo_tet_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const double* un_dev, double* vals_dev) {
-    int rc = tet_cells(ctx, x_dev, un_dev, true);
+    int rc = tet_cells(ctx, x_dev, un_dev, TET_JAC_ALL);
     if (rc) return rc;
     k_gather_matrix3d<<<hemo_grid(ctx->nnz_node, 256), 256, 0, ctx->stream>>>(
         ctx->n, ctx->nnz_node, ctx->E, ctx->nrowptr, ctx->ncol, ctx->rowof, ctx->mseg_ptr, ctx->mseg_src, ctx->Ae,
@@ -364,7 +381,7 @@ int hemo_tet_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const double*
 int hemo_tet_assemble_residual(hemo_ctx* ctx, const double* x_dev, const double* un_dev, const double* g_dev,
                                double* b_dev) {
     if (ctx->have_bc && !g_dev) return HEMO_EINVAL;
-    int rc = tet_cells(ctx, x_dev, un_dev, ctx->have_bc);
+    int rc = tet_cells(ctx, x_dev, un_dev, ctx->have_bc ? TET_JAC_FLAGGED : TET_JAC_NONE);
     if (rc) return rc;
     cudaStream_t st = ctx->stream;
     if (ctx->have_bc) {
