@@ -218,3 +218,35 @@ def test_taylor_green_plugin_matches_oracle(tmp_path):
     assert len(errs) == 4 and errs[0] < 1e-12 and max(errs) < 5e-2
     norms = open(f"{out}/norms.txt").read()
     assert "L2 norm of velocity" in norms
+
+
+def test_golden_tet_case_on_gpu():
+    """The committed 3-D golden vectors (tests/golden/p1tet_small.npz) are reproduced by the CUDA path."""
+    import os
+    from cfd_hemodynamic_b200._lib import Hemo
+    from tests.golden.make_golden_tet import COEF, GOLDEN_TET, bc_values, build_case
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", GOLDEN_TET))
+    prob, fpairs, bcs, u, p, un = build_case()
+    n = prob.n
+    rules = {k: (gold[f"rule_{k}_pts"], gold[f"rule_{k}_wts"]) for k in prob.rules}
+    hemo = Hemo(0)
+    T, keep = _setup(hemo, prob.x, prob.cells, prob.h, rules, (gold["facet_pts"], gold["facet_wts"]),
+                     dict(dt=prob.dt, rho=prob.rho, mu=prob.mu), prob.f)
+    fcells, fmask = D.pairs_by_cell(fpairs)
+    hemo.set_facet_set(0, T(fcells, torch.int32), T(fmask, torch.int32), **COEF)
+    flag, mult, cellflag, g = D.dirichlet_arrays(n, prob.cells, bcs, gdim=3)
+    assert np.array_equal(g, bc_values(n, bcs))
+    hemo.set_bc(T(flag, torch.uint8), T(mult), T(cellflag, torch.uint8))
+    dev = hemo.device
+    xd, und = T(np.concatenate([gold["u"], gold["p"]])), T(gold["un"])
+    vals = torch.zeros(hemo.nnz, dtype=torch.float64, device=dev)
+    b = torch.zeros(4 * n, dtype=torch.float64, device=dev)
+    hemo.assemble_jacobian(xd, und, vals)
+    hemo.assemble_residual(xd, und, T(g), b)
+    rowptr, col = hemo.get_pattern()
+    torch.cuda.synchronize()
+    A_gold = sp.csr_matrix((gold["data"], gold["indices"], gold["indptr"]), shape=(4 * n, 4 * n))
+    A_gpu = sp.csr_matrix((vals.cpu().numpy(), col.cpu().numpy(), rowptr.cpu().numpy()), shape=(4 * n, 4 * n))
+    assert np.linalg.norm((A_gpu - A_gold).tocoo().data) < 1e-12 * np.linalg.norm(gold["data"])
+    assert np.linalg.norm(b.cpu().numpy() - gold["b"]) < 1e-12 * np.linalg.norm(gold["b"])
+    hemo.close()

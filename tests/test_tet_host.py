@@ -141,28 +141,55 @@ def _pattern3d(nrowptr, ncol, n):
     return rowptr, col
 
 
+def _emulate(lib, prob, fpairs, coef, bcs, sol, un, xv, theta=0.5, a0=1.0):
+    """Emulated launch sequence on `prob` (ns3d_oracle.Problem3D): (A in the device CSR layout, b, J xv, flux,
+    Dirichlet tables)."""
+    x, cells = prob.x, prob.cells
+    E, n = cells.shape[0], x.shape[0]
+    fcells, fmask = D.pairs_by_cell(fpairs)
+    flag, mult, cellflag, g = D.dirichlet_arrays(n, cells, bcs, gdim=3)
+    nrowptr, ncol = D.node_graph(cells, n)
+    rowof, mseg_ptr, mseg_src, vseg_ptr, vseg_src = _gather_tables(cells, nrowptr, ncol, n)
+    nnz_node = len(ncol)
+    for b, k in enumerate(("Fu", "Fp", "uu", "up", "pu", "pp")):
+        pts, wts = prob.rules[k]
+        assert lib.sxh_set_rule(3, b, _p(_c(pts)), _p(_c(wts)), len(wts)) == 0
+    f3 = _c(prob.f)
+    lib.sxh_set_params(prob.dt, prob.rho, prob.mu, _p(f3), prob.eps0, theta, a0)
+    Ae, Fe = np.zeros(256 * E), np.zeros(16 * E)
+    vals, bvec, y, flux = np.zeros(16 * nnz_node), np.zeros(4 * n), np.zeros(4 * n), np.zeros(1)
+    unf, solf, xvf, h = _c(un), _c(sol), _c(xv), _c(prob.h)
+    frule = prob.facet_rule
+    with_bc = bool(flag.any())
+    lib.txh_assemble(E, n, ctypes.c_int64(nnz_node), _p(_c(cells, np.int32)), _p(_c(x)), _p(h), _p(solf), _p(unf), _p(unf),
+                     _p(nrowptr), _p(ncol), _p(_c(rowof, np.int32)), _p(mseg_ptr), _p(mseg_src), _p(vseg_ptr), _p(vseg_src),
+                     len(fcells), _p(fcells), _p(fmask), _p(_coef8(coef)), _p(_c(frule[0])), _p(_c(frule[1])), len(frule[1]),
+                     _p(flag) if with_bc else None, _p(mult), _p(cellflag), _p(g), _p(xvf), _p(Ae), _p(Fe), _p(vals), _p(bvec),
+                     _p(y), _p(flux))
+    rowptr, col = _pattern3d(nrowptr, ncol, n)
+    A_dev = sp.csr_matrix((vals, col, rowptr), shape=(4 * n, 4 * n))
+    return A_dev, bvec, y, flux[0], (flag, mult, cellflag, g)
+
+
 @pytest.mark.parametrize("with_bc", [False, True])
 @pytest.mark.parametrize("coef", [FACET_COEFS[0], FACET_COEFS[3]])
 def test_emulated_tet_assembly_matches_oracle(lib, coef, with_bc):
     x, cells = _perturbed_cube(3, seed=4)
     E, n = cells.shape[0], x.shape[0]
-    h = S.cell_diameter(x, cells)
     rng = np.random.default_rng(11)
     u, p, un = rng.standard_normal((n, 3)), rng.standard_normal(n), rng.standard_normal((n, 3))
     f = np.array([0.3, -0.2, 0.1])
     degs = dict(Fu=6, Fp=5, uu=6, up=5, pu=5, pp=4)          # small rules: the layout, not the quadrature, is under test
     rules = {k: S.tet_gauss_jacobi(v) for k, v in degs.items()}
-    frule = S.triangle_facet_rule(4)
     pairs = S.exterior_facets(cells)
     # facet set: the faces x = 1 and z = 0 (some cells carry two tagged facets)
     fx = np.array([np.delete(x[cells[c]], lf, axis=0) for c, lf in pairs])                # (m, 3, 3)
     tagged = np.isclose(fx[:, :, 0], 1.0).all(axis=1) | np.isclose(fx[:, :, 2], 0.0).all(axis=1)
     fpairs = pairs[tagged]
-    fcells, fmask = D.pairs_by_cell(fpairs)
+    fcells, _ = D.pairs_by_cell(fpairs)
     assert (np.bincount(fpairs[:, 0]).max() == 2) and len(fcells) < len(fpairs)
     # Dirichlet: velocity on x = 0 (one condition) and on y = 0 (a second one: edge dofs get diagonal 2), pressure on x = 1
-    bcs, bc_lists = [], None
-    g = np.zeros(4 * n)
+    bcs, bc_lists = [], []
     if with_bc:
         gu = rng.standard_normal(3 * n)
         gp = rng.standard_normal(n)
@@ -172,42 +199,47 @@ def test_emulated_tet_assembly_matches_oracle(lib, coef, with_bc):
         bcs = [("u", n0, gu), ("u", n1, 2.0 * gu), ("p", n2, gp)]
         udofs = lambda nodes: (3 * nodes[:, None] + np.arange(3)[None]).reshape(-1)
         bc_lists = [udofs(n0), udofs(n1), 3 * n + n2]
-    flag, mult, cellflag, g = D.dirichlet_arrays(n, cells, bcs, gdim=3)
+    prob = O3.Problem3D(x=x, cells=cells, dt=0.01, rho=1.3, mu=0.02, f=f, rules=rules,
+                        facet_sets=[O.FacetSet(pairs=fpairs, **coef)], facet_rule=S.triangle_facet_rule(4))
+    sol = np.concatenate([u.reshape(-1), p])
+    xv = rng.standard_normal(4 * n)
+    A_dev, bvec, y, flux, (flag, mult, cellflag, g) = _emulate(lib, prob, fpairs, coef, bcs, sol, un.reshape(-1), xv)
     if with_bc:
         assert mult.max() == 2.0 and cellflag.sum() < E
-    prob = O3.Problem3D(x=x, cells=cells, dt=0.01, rho=1.3, mu=0.02, f=f, rules=rules,
-                        facet_sets=[O.FacetSet(pairs=fpairs, **coef)], facet_rule=frule)
-    sol = np.concatenate([u.reshape(-1), p])
-    A_ref, b_ref = O3.assemble_system(prob, sol, un.reshape(-1), g, bc_lists=bc_lists if with_bc else [])
-    # device-side tables and the emulated launch sequence
-    nrowptr, ncol = D.node_graph(cells, n)
-    rowof, mseg_ptr, mseg_src, vseg_ptr, vseg_src = _gather_tables(cells, nrowptr, ncol, n)
-    nnz_node = len(ncol)
-    for b, k in enumerate(("Fu", "Fp", "uu", "up", "pu", "pp")):
-        pts, wts = rules[k]
-        assert lib.sxh_set_rule(3, b, _p(_c(pts)), _p(_c(wts)), len(wts)) == 0
-    lib.sxh_set_params(0.01, 1.3, 0.02, _p(f), O.EPS0, 0.5, 1.0)
-    Ae, Fe = np.zeros(256 * E), np.zeros(16 * E)
-    vals, bvec, y, flux = np.zeros(16 * nnz_node), np.zeros(4 * n), np.zeros(4 * n), np.zeros(1)
-    xv = rng.standard_normal(4 * n)
-    unf = _c(un.reshape(-1))
-    lib.txh_assemble(E, n, ctypes.c_int64(nnz_node), _p(_c(cells, np.int32)), _p(_c(x)), _p(h), _p(sol), _p(unf), _p(unf),
-                     _p(nrowptr), _p(ncol), _p(_c(rowof, np.int32)), _p(mseg_ptr), _p(mseg_src), _p(vseg_ptr), _p(vseg_src),
-                     len(fcells), _p(fcells), _p(fmask), _p(_coef8(coef)), _p(_c(frule[0])), _p(_c(frule[1])), len(frule[1]),
-                     _p(flag) if with_bc else None, _p(mult), _p(cellflag), _p(g), _p(xv), _p(Ae), _p(Fe), _p(vals), _p(bvec),
-                     _p(y), _p(flux))
-    rowptr, col = _pattern3d(nrowptr, ncol, n)
-    A_dev = sp.csr_matrix((vals, col, rowptr), shape=(4 * n, 4 * n))
-    assert A_dev.has_sorted_indices or np.all(np.diff(col[rowptr[5]:rowptr[6]]) > 0)
+    A_ref, b_ref = O3.assemble_system(prob, sol, un.reshape(-1), g, bc_lists=bc_lists)
     diff = (A_dev - A_ref).tocoo()
     assert np.linalg.norm(diff.data) < 1e-12 * np.linalg.norm(A_ref.data)
     assert np.linalg.norm(bvec - b_ref) < 1e-12 * np.linalg.norm(b_ref)
     assert np.linalg.norm(y - A_ref @ xv) < 1e-12 * np.linalg.norm(A_ref @ xv)
-    assert abs(flux[0] - S.outlet_flux(x, cells, fpairs, un.reshape(-1))) < 1e-13
+    assert abs(flux - S.outlet_flux(x, cells, fpairs, un.reshape(-1))) < 1e-13
     if with_bc:
         # Dirichlet rows: unit (or multiplicity) diagonal, x - g on the right-hand side
         d = np.nonzero(flag)[0]
         assert np.array_equal(A_dev.diagonal()[d], mult[d]) and np.allclose(bvec[d], sol[d] - g[d], atol=0, rtol=0)
+
+
+def test_golden_tet_case_host_emulation(lib):
+    """The committed 3-D golden vectors (tests/golden/make_golden_tet.py) are reproduced by the oracle and
+    by the host-compiled device code."""
+    from tests.golden.make_golden_tet import COEF, GOLDEN_TET, bc_dof_lists, bc_values, build_case
+    gold = np.load(os.path.join(HERE, "golden", GOLDEN_TET))
+    prob, fpairs, bcs, u, p, un = build_case()
+    n = prob.n
+    for k in prob.rules:                       # the committed rules: golden pins arithmetic, not tables
+        prob.rules[k] = (gold[f"rule_{k}_pts"], gold[f"rule_{k}_wts"])
+    prob.facet_rule = (gold["facet_pts"], gold["facet_wts"])
+    assert np.array_equal(gold["cells"], prob.cells) and np.array_equal(gold["x"], prob.x)
+    assert np.array_equal(gold["fpairs"], fpairs)
+    sol = np.concatenate([gold["u"], gold["p"]])
+    A_gold = sp.csr_matrix((gold["data"], gold["indices"], gold["indptr"]), shape=(4 * n, 4 * n))
+    A, b = O3.assemble_system(prob, sol, gold["un"], bc_values(n, bcs), bc_lists=bc_dof_lists(n, bcs))
+    assert np.array_equal(A.indptr, gold["indptr"]) and np.array_equal(A.indices, gold["indices"])
+    assert np.linalg.norm(A.data - gold["data"]) <= 1e-13 * np.linalg.norm(gold["data"])
+    assert np.linalg.norm(b - gold["b"]) <= 1e-13 * np.linalg.norm(gold["b"])
+    A_dev, bvec, _, _, (_, _, _, g) = _emulate(lib, prob, fpairs, COEF, bcs, sol, gold["un"], np.zeros(4 * n))
+    assert np.array_equal(g, bc_values(n, bcs))
+    assert np.linalg.norm((A_dev - A_gold).tocoo().data) < 1e-12 * np.linalg.norm(gold["data"])
+    assert np.linalg.norm(bvec - gold["b"]) < 1e-12 * np.linalg.norm(gold["b"])
 
 
 @pytest.mark.parametrize("sweeps", [1, 4, 5])
