@@ -64,11 +64,13 @@ class Partition:
     """The part of a mesh one rank works on: every cell touching an owned vertex,
     owned vertices first, ghost vertices after; halo plan towards the neighbours."""
 
-    def __init__(self, x, cells, owner, rank: int, overlap: int = 1):
+    def __init__(self, x, cells, owner, rank: int, overlap: int = 1, gdim: int = 2):
         """overlap = number of cell layers around the owned vertices (1 = the minimal ghost
         layer that completes every owned row; more layers widen the subdomain on which the
-        rank-local preconditioner acts — restricted additive Schwarz)."""
+        rank-local preconditioner acts — restricted additive Schwarz).  gdim = velocity
+        components per node (2: triangles / quadrilaterals, 3: tetrahedra)."""
         import numpy as np
+        self.gdim = int(gdim)
         owner = np.asarray(owner)
         cell_owner = owner[cells]                                 # (E, 3)
         mine = (cell_owner == rank).any(axis=1)
@@ -111,7 +113,8 @@ class Partition:
         """Indices into a local [u interleaved | p] vector of all dofs of `nodes`."""
         import numpy as np
         nodes = np.asarray(nodes, dtype=np.int64)
-        return np.concatenate([2 * nodes, 2 * nodes + 1, 2 * self.n_local + nodes])
+        gd = self.gdim
+        return np.concatenate([gd * nodes + k for k in range(gd)] + [gd * self.n_local + nodes])
 
 
 class HaloExchange:
@@ -164,32 +167,35 @@ class HaloExchangeAllGather:
         loc = part.g2l[mine]
         assert (loc >= 0).all() and (loc < part.n_owned).all()
         self.n_mine = len(mine)
-        self.send_idx = torch.as_tensor(part.dof_index(loc).reshape(3, -1).T.reshape(-1).copy(), dtype=torch.int64,
-                                        device=device)          # (node, [ux, uy, p]) order
-        self.sbuf = torch.zeros(3 * self.maxn, dtype=torch.float64, device=device)
-        self.rbuf = torch.zeros(world * 3 * self.maxn, dtype=torch.float64, device=device)
+        gd = part.gdim
+        nb = gd + 1                                              # scalars per node: velocity components + pressure
+        self.nb = nb
+        self.send_idx = torch.as_tensor(part.dof_index(loc).reshape(nb, -1).T.reshape(-1).copy(), dtype=torch.int64,
+                                        device=device)          # (node, [u components, p]) order
+        self.sbuf = torch.zeros(nb * self.maxn, dtype=torch.float64, device=device)
+        self.rbuf = torch.zeros(world * nb * self.maxn, dtype=torch.float64, device=device)
         # where each of my ghost dofs sits in the gathered buffer
         ghosts = part.glob_nodes[part.n_owned:]
-        src = np.empty((len(ghosts), 3), dtype=np.int64)
+        src = np.empty((len(ghosts), nb), dtype=np.int64)
         pos_in_list = {}
         for q in range(world):
             pos_in_list[q] = dict(zip(lists[q].tolist(), range(len(lists[q]))))
         for k, g in enumerate(ghosts.tolist()):
             q = int(owner[g])
             p = pos_in_list[q][g]
-            base = q * 3 * self.maxn + 3 * p
-            src[k] = (base, base + 1, base + 2)
+            base = q * nb * self.maxn + nb * p
+            src[k] = base + np.arange(nb)
         gl = np.arange(part.n_owned, part.n_local)
-        dst = np.stack([2 * gl, 2 * gl + 1, 2 * part.n_local + gl], axis=1)
+        dst = np.stack([gd * gl + k for k in range(gd)] + [gd * part.n_local + gl], axis=1)
         self.src = torch.as_tensor(src.reshape(-1), dtype=torch.int64, device=device)
         self.dst = torch.as_tensor(dst.reshape(-1), dtype=torch.int64, device=device)
-        self.bytes_per_update = 8 * 3 * self.maxn * world
+        self.bytes_per_update = 8 * nb * self.maxn * world
 
     def update(self, v: torch.Tensor):
         if self.src.numel() == 0 and self.n_mine == 0:
             return
         if self.n_mine:
-            self.sbuf[:3 * self.n_mine] = v.index_select(0, self.send_idx)
+            self.sbuf[:self.nb * self.n_mine] = v.index_select(0, self.send_idx)
         dist.all_gather_into_tensor(self.rbuf, self.sbuf, group=self.group)
         if self.src.numel():
             v.index_copy_(0, self.dst, self.rbuf.index_select(0, self.src))

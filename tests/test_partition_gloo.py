@@ -19,25 +19,34 @@ def _worker(rank, world, port, out, cell_type="triangle"):
     from cfd_hemodynamic_b200.parallel import HaloExchange, HaloExchangeAllGather, Partition, slab_partition
     from oracle import ns_oracle as O
     from tests import common as T
-    mesh = T.perturbed_square(9, 6, seed=4, cell_type=cell_type)
-    prob = T.make_problem(mesh)
-    n = prob.n
-    u, p, un = T.smooth_fields(prob.x)
-    A = O.assemble_J_raw(prob, u, p, un).tocsr()
+    gd = 3 if cell_type == "tetrahedron" else 2
+    if gd == 3:
+        # tetrahedra: the oracle's 3-D Jacobian (cell integrals) on a Kuhn-split box
+        from oracle import ns3d_oracle as O3
+        from oracle import simplex_oracle as S
+        x3, cells3 = O3.unit_cube_tets(3)
+        rules = {k: S.tet_gauss_jacobi(d) for k, d in dict(Fu=4, Fp=3, uu=4, up=3, pu=3, pp=2).items()}
+        prob = O3.Problem3D(x=x3, cells=cells3, dt=0.01, rho=1.3, mu=0.02, f=np.zeros(3), rules=rules)
+        n = prob.n
+        rs = np.random.default_rng(5)
+        A = O3.assemble_J_raw(prob, rs.standard_normal(4 * n), rs.standard_normal(3 * n)).tocsr()
+    else:
+        mesh = T.perturbed_square(9, 6, seed=4, cell_type=cell_type)
+        prob = T.make_problem(mesh)
+        n = prob.n
+        u, p, un = T.smooth_fields(prob.x)
+        A = O.assemble_J_raw(prob, u, p, un).tocsr()
     owner = slab_partition(prob.x[:, 0], world)
-    part = Partition(prob.x, prob.cells, owner, rank)
+    part = Partition(prob.x, prob.cells, owner, rank, gdim=gd)
     # local matrix: rows/cols of the local nodes in local [u|p] numbering
     gl = part.glob_nodes
-    gdof = np.concatenate([np.stack([2 * gl, 2 * gl + 1], 1).ravel(), 2 * n + gl])
+    gdof = np.concatenate([np.stack([gd * gl + k for k in range(gd)], 1).ravel(), gd * n + gl])
     Aloc = A[gdof][:, gdof]
     rng = np.random.default_rng(0)
-    xg = rng.standard_normal(3 * n)
+    xg = rng.standard_normal((gd + 1) * n)
     xl = torch.tensor(xg[gdof].copy())
     ghost_dofs = part.dof_index(np.arange(part.n_owned, part.n_local))
-    # local [u|p] layout interleaves u per node: build the same layout for the local vector
-    perm = np.concatenate([np.stack([2 * np.arange(part.n_local), 2 * np.arange(part.n_local) + 1], 1).ravel(),
-                           2 * part.n_local + np.arange(part.n_local)])
-    assert np.array_equal(perm, np.arange(3 * part.n_local))
+    assert np.array_equal(np.sort(part.dof_index(np.arange(part.n_local))), np.arange((gd + 1) * part.n_local))
     xl[torch.as_tensor(ghost_dofs)] = 0.0            # forget ghost values ...
     HaloExchange(part, torch.device("cpu")).update(xl)   # ... and get them back from the owners
     assert np.allclose(xl.numpy(), xg[gdof], rtol=0, atol=0)
@@ -55,7 +64,7 @@ def _worker(rank, world, port, out, cell_type="triangle"):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("cell_type", ["triangle", "quadrilateral"])
+@pytest.mark.parametrize("cell_type", ["triangle", "quadrilateral", "tetrahedron"])
 def test_partition_halo_world2(cell_type):
     sock = socket.socket()
     sock.bind(("127.0.0.1", 0))
@@ -74,4 +83,4 @@ def test_partition_halo_world2(cell_type):
         assert err < 1e-14, err
         assert abs(dsum - dref) < 1e-12 * dref
         assert n_local > n_owned
-    assert res[0][4] + res[1][4] == 70
+    assert res[0][4] + res[1][4] == (64 if cell_type == "tetrahedron" else 70)
