@@ -204,7 +204,7 @@ class Hemo:
     # ---- setup ---------------------------------------------------------
     def set_mesh(self, x2, cells, h):
         """cells: (E, 3) P1 triangles or (E, 4) tensor-ordered Q1 quadrilaterals with x2 (n, 2);
-        (E, 4) P1 tetrahedra with x2 (n, 3) (cell assembly into the CSR only, include/hemo.h)."""
+        (E, 4) P1 tetrahedra with x2 (n, 3) (what works on tetrahedra: include/hemo.h)."""
         if cells.dim() != 2 or cells.shape[1] not in (3, 4) or not cells.is_contiguous():
             raise HemoError("cells must be a contiguous (E, 3) or (E, 4) int32 tensor")
         self.nv = int(cells.shape[1])

@@ -128,7 +128,7 @@ struct hemo_ctx {
 
     // mesh (borrowed)
     int nv = 3;                     // nodes per cell: 3 = P1 triangle, 4 = Q1 quadrilateral (tensor-ordered) | P1 tetrahedron
-    int dim = 2;                    // geometric dimension: 3 only for tetrahedra (assembly, Dirichlet rows, SpMV; no 3-D preconditioner yet)
+    int dim = 2;                    // geometric dimension: 3 only for tetrahedra (include/hemo.h lists what works in 3-D)
     double fz = 0.0;                // third component of the body force (hemo_set_body_force3)
     const double* x = nullptr;
     const int32_t* cells = nullptr;

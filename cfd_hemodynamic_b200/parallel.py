@@ -45,8 +45,8 @@ class TorchComm:
 
 def slab_partition(x_coord, n_parts: int):
     """Contiguous x-slabs with equal vertex counts: returns the
-    owner rank of every vertex.  Used by the partition-invariance tests; the
-    multi-GPU solve itself is replica-parallel in this round."""
+    owner rank of every vertex.  Used by the multi-GPU driver (`distributed_solver.py`,
+    DESIGN.md §7) and the partition-invariance tests."""
     import numpy as np
     order = np.argsort(x_coord, kind="stable")
     owner = np.empty(x_coord.shape[0], dtype=np.int32)
