@@ -1411,9 +1411,13 @@ k_selfp(int64_t nnz2, int64_t nnz_node, const int32_t* __restrict__ rowof2, cons
 
 extern "C" int hemo_pc_set_schur_selfp(hemo_ctx* ctx, const double* vals_dev, double coarse_shift) {
     if (!ctx || !vals_dev) return HEMO_EINVAL;
-    HEMO_2D_ONLY(ctx, "the SELFP Schur approximation");
     HemoAmg& amg = ctx->amg[1];
     if (!amg.ready || !amg.fine_rowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "pressure hierarchy needs the distance-2 fine pattern");
+    if (ctx->dim == 3) {
+        int rc = hemo_tet_selfp(ctx, vals_dev);
+        if (rc) return rc;
+        return hemo_amg_numeric_shift(ctx, &amg, coarse_shift);
+    }
     k_selfp<<<hemo_grid(amg.fine_nnz, 256), 256, 0, ctx->stream>>>(amg.fine_nnz, ctx->nnz_node, amg.fine_rowof, amg.fine_col,
                                                                    ctx->nrowptr, ctx->ncol, ctx->diagslot, vals_dev,
                                                                    amg.op[0].val);

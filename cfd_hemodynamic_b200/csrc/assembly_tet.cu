@@ -455,6 +455,24 @@ __global__ void k_tet_jacobi(int n, int64_t nnz_node, const int32_t* __restrict_
     tet_jacobi_item(i, n, nnz_node, nrowptr, ncol, vals, dinv, omega, tu, zin, zout);
 }
 
+__global__ void __launch_bounds__(256)
+k_tet_selfp(int64_t nnz2, int64_t nnz_node, const int32_t* __restrict__ rowof2, const int32_t* __restrict__ col2,
+            const int32_t* __restrict__ nrowptr, const int32_t* __restrict__ ncol, const int32_t* __restrict__ diagslot,
+            const double* __restrict__ vals, areal* __restrict__ out) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= nnz2) return;
+    tet_selfp_item<areal>(s, nnz_node, rowof2, col2, nrowptr, ncol, diagslot, vals, out);
+}
+
+int hemo_tet_selfp(hemo_ctx* ctx, const double* vals_dev) {
+    HemoAmg& amg = ctx->amg[1];
+    k_tet_selfp<<<hemo_grid(amg.fine_nnz, 256), 256, 0, ctx->stream>>>(amg.fine_nnz, ctx->nnz_node, amg.fine_rowof,
+                                                                       amg.fine_col, ctx->nrowptr, ctx->ncol, ctx->diagslot,
+                                                                       vals_dev, amg.op[0].val);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 int hemo_tet_pc_setup(hemo_ctx* ctx, const double* vals_dev) {
     hemo_tet_state* st = tet_state(ctx);
     int rc;

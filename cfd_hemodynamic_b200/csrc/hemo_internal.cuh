@@ -291,6 +291,7 @@ int hemo_tet_set_facet_quadrature(hemo_ctx* ctx, const double* pts, const double
 int hemo_tet_facet_flux(hemo_ctx* ctx, const HemoFacetSet& fs, const double* un_dev, double* partial);
 int hemo_tet_laplace_mass(hemo_ctx* ctx);
 int hemo_tet_pc_setup(hemo_ctx* ctx, const double* vals_dev);
+int hemo_tet_selfp(hemo_ctx* ctx, const double* vals_dev);
 int hemo_tet_velocity_solve(hemo_ctx* ctx, const double* vals_dev, const double* ru, const double* zp, double* tu,
                             double* tmp, double* zu, int sweeps, double omega);
 int hemo_tet_spmv(hemo_ctx* ctx, const double* vals_dev, const double* x_dev, double* y_dev);

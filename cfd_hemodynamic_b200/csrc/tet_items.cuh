@@ -261,3 +261,46 @@ HEMO_HD void tet_jacobi_item(int i, int n, int64_t nnz_node, const int32_t* nrow
         zout[3 * (int64_t)i + k] = (zin != nullptr ? zin[3 * (int64_t)i + k] : 0.0) + corr;
     }
 }
+
+// position of `key` in the ascending range col[lo, hi), or -1
+HEMO_HD int tet_find_sorted(const int32_t* col, int lo, int hi, int key) {
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const int v = col[mid];
+        if (v == key) return mid;
+        if (v < key) lo = mid + 1; else hi = mid;
+    }
+    return -1;
+}
+
+// SELFP on tetrahedra (the reference's Schur approximation, PETSc `selfp`: stabilized_schur.py:231-235):
+// entry s = (i, j) of Sp = A11 - A10 diag(A00)^-1 A01 on the distance-2 node graph (rowof2 / col2), straight
+// from the monolithic CSR values in the 3-D layout.
+template <typename OutT>
+HEMO_HD void tet_selfp_item(int64_t s, int64_t nnz_node, const int32_t* rowof2, const int32_t* col2,
+                            const int32_t* nrowptr, const int32_t* ncol, const int32_t* diagslot, const double* vals,
+                            OutT* out) {
+    const int i = rowof2[s], j = col2[s];
+    const int r0i = nrowptr[i];
+    const int degi = nrowptr[i + 1] - r0i;
+    const int64_t rpi = 12 * nnz_node + 4 * (int64_t)r0i;              // pressure row of node i
+    double v = 0.0;
+    const int tij = tet_find_sorted(ncol, r0i, r0i + degi, j);
+    if (tij >= 0) v = vals[rpi + 3 * degi + (tij - r0i)];             // A11[i, j]
+    for (int t = 0; t < degi; ++t) {
+        const int k = ncol[r0i + t];
+        const int r0k = nrowptr[k];
+        const int degk = nrowptr[k + 1] - r0k;
+        const int tkj = tet_find_sorted(ncol, r0k, r0k + degk, j);
+        if (tkj < 0) continue;
+        const int tkk = diagslot[k] - r0k;
+        for (int c = 0; c < 3; ++c) {
+            const int64_t ru = 12 * (int64_t)r0k + 4 * (int64_t)c * degk;  // row 3k + c
+            const double a10 = vals[rpi + 3 * t + c];                  // A10[i, (k, c)]
+            const double a01 = vals[ru + 3 * degk + (tkj - r0k)];      // A01[(k, c), j]
+            const double d = vals[ru + 3 * tkk + c];                   // diag(A00)
+            v -= a10 * a01 / d;
+        }
+    }
+    out[s] = (OutT)v;
+}

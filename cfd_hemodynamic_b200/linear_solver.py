@@ -81,8 +81,8 @@ class BlockSchurSolver:
         # tetrahedra: the velocity block is handled by block-Jacobi sweeps inside the library
         # (no 3x3-block hierarchy yet); only the scalar pressure hierarchy is built
         tet = getattr(hemo, "dim", 2) == 3
-        if tet and schur_mode != "laplace":
-            raise ValueError("tetrahedra: only schur_mode='laplace' is implemented")
+        if tet and schur_mode not in ("laplace", "selfp"):
+            raise ValueError("tetrahedra: schur_mode 'laplace' and 'selfp' are implemented")
         for which, mask, max_coarse in ((0, umask, 80), (1, pmask, 160)):
             if tet and which == 0:
                 self.levels.append([])

@@ -215,4 +215,10 @@ void txh_velocity_solve(int n, int64_t nnz_node, const int32_t* nrowptr, const i
     }
 }
 
+// Emulated k_tet_selfp: Sp = A11 - A10 diag(A00)^-1 A01 on the distance-2 pattern (rowof2, col2)
+void txh_selfp(int64_t nnz2, int64_t nnz_node, const int32_t* rowof2, const int32_t* col2, const int32_t* nrowptr,
+               const int32_t* ncol, const int32_t* diagslot, const double* vals, double* out) {
+    for (int64_t s = 0; s < nnz2; ++s) tet_selfp_item<double>(s, nnz_node, rowof2, col2, nrowptr, ncol, diagslot, vals, out);
+}
+
 }  // extern "C"

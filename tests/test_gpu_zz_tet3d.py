@@ -106,7 +106,8 @@ def test_tet_facets_dirichlet_spmv_match_oracle(coef, with_bc):
     hemo.close()
 
 
-def test_tet_newton_step_matches_oracle():
+@pytest.mark.parametrize("schur_mode", ["laplace", "selfp"])
+def test_tet_newton_step_matches_oracle(schur_mode):
     """First 3-D solve through the C-ABI: Newton iterations on the Ethier-Steinman problem of the
     reference's taylor_green scenario (src/scenarios/taylor_green.py:41-58: Dirichlet velocity and
     pressure on the whole boundary) with hemo_fgmres + the 3-D block preconditioner, against the
@@ -129,7 +130,9 @@ def test_tet_newton_step_matches_oracle():
     T, keep = _setup(hemo, x, cells, h, rules, frule, dict(dt=dt, rho=rho, mu=mu), f)
     dev = hemo.device
     nrowptr, ncol = D.node_graph(cells, n)
-    ks = BlockSchurSolver(hemo, nrowptr, ncol, boundary, boundary, dt=dt, rho=rho, mu=mu, rtol=1e-11, amg_cycles_p=2)
+    # "selfp": the reference's Schur approximation (stabilized_schur.py:231-235) formed on the device (k_tet_selfp)
+    ks = BlockSchurSolver(hemo, nrowptr, ncol, boundary, boundary, dt=dt, rho=rho, mu=mu, rtol=1e-11, amg_cycles_p=2,
+                          schur_mode=schur_mode)
     vals = torch.zeros(hemo.nnz, dtype=torch.float64, device=dev)
     bvec = torch.zeros(4 * n, dtype=torch.float64, device=dev)
     y = torch.zeros(4 * n, dtype=torch.float64, device=dev)

@@ -276,3 +276,35 @@ def test_emulated_tet_velocity_solve(lib, sweeps):
     for _ in range(sweeps):
         z = z + omega * Dinv @ (t_ref - A00 @ z)
     assert np.abs(zu - z).max() < 1e-12 * np.abs(z).max()
+
+
+def test_emulated_tet_selfp(lib):
+    """SELFP on tetrahedra (the reference's Schur approximation, stabilized_schur.py:231-235): entries of
+    A11 - A10 diag(A00)^-1 A01 on the distance-2 node graph from the device CSR layout, against SciPy."""
+    x, cells = _perturbed_cube(2, seed=3)
+    n = x.shape[0]
+    nrowptr, ncol = D.node_graph(cells, n)
+    nnz_node = len(ncol)
+    rowptr, col = _pattern3d(nrowptr, ncol, n)
+    rng = np.random.default_rng(8)
+    A = sp.csr_matrix((rng.standard_normal(16 * nnz_node), col, rowptr), shape=(4 * n, 4 * n))
+    A = (A + sp.diags(np.concatenate([5.0 * np.ones(3 * n), np.zeros(n)]))).tocsr()
+    A.sort_indices()
+    assert np.array_equal(A.indices, col)
+    vals = np.ascontiguousarray(A.data)
+    G = sp.csr_matrix((np.ones(nnz_node), ncol, nrowptr), shape=(n, n))
+    G2 = (G @ G).tocsr()
+    G2.sort_indices()
+    rowof2 = np.repeat(np.arange(n, dtype=np.int32), np.diff(G2.indptr))
+    col2 = G2.indices.astype(np.int32)
+    rows = np.repeat(np.arange(n), np.diff(nrowptr))
+    diagslot = np.nonzero(rows == ncol)[0].astype(np.int32)
+    out = np.zeros(G2.nnz)
+    lib.txh_selfp(ctypes.c_int64(G2.nnz), ctypes.c_int64(nnz_node), _p(rowof2), _p(col2), _p(nrowptr), _p(ncol), _p(diagslot),
+                  _p(vals), _p(out))
+    N = 3 * n
+    A00, A01, A10, A11 = A[:N, :N], A[:N, N:], A[N:, :N], A[N:, N:]
+    Sp = (A11 - A10 @ sp.diags(1.0 / A00.diagonal()) @ A01).tocsr()
+    got = sp.csr_matrix((out, col2, G2.indptr), shape=(n, n))
+    d = (got - Sp).tocoo()
+    assert np.abs(d.data).max() < 1e-12 * np.abs(Sp.data).max()
