@@ -8,6 +8,7 @@
 // P1 triangles and Q1 quadrilaterals; reductions are fixed-order (bitwise reproducible).
 #include "hemo_internal.cuh"
 #include "q1_element.cuh"
+#include "tet_items.cuh"
 
 #define PP_THREADS 256
 #define PP_BLOCKS 592     // 4 per SM on 148 SMs
@@ -269,6 +270,30 @@ k_l2_partial(int E, int bs, const int32_t* __restrict__ cells, const double* __r
     if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
+// ---- tetrahedra (bodies in tet_items.cuh) ------------------------------------------------------
+// A boundary vertex of a tetrahedral mesh collects the traction of every tagged facet around it, so
+// unlike in 2-D (two contributions per vertex) the atomic sums depend on the arrival order at
+// round-off level: the wall-shear-stress output is not bitwise reproducible in 3-D.
+__global__ void k_tet_wss(int m, const int32_t* __restrict__ fcells, const int32_t* __restrict__ fmask,
+                          const int32_t* __restrict__ cells, const double* __restrict__ x,
+                          const double* __restrict__ sol, double mu, double* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    tet_wss_item(t, fcells, fmask, cells, x, sol, mu,
+                 [out](int node, int k, double val) { atomicAdd(&out[3 * (int64_t)node + k], val); });
+}
+
+__global__ void __launch_bounds__(PP_THREADS)
+k_tet_l2_partial(int E, int bs, const int32_t* __restrict__ cells, const double* __restrict__ x,
+                 const double* __restrict__ f, double* __restrict__ partial) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < E; c += gridDim.x * blockDim.x)
+        acc += tet_l2_item(c, bs, cells, x, f);
+    acc = pp_block_sum(acc, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -282,13 +307,14 @@ static int pp_fetch(hemo_ctx* ctx, int count, double* out_host) {
 
 extern "C" int hemo_wall_shear_stress(hemo_ctx* ctx, int set_id, const double* x_dev, double* wss_dev) {
     if (!ctx || set_id < 0 || set_id >= HEMO_MAX_FACET_SETS || !x_dev || !wss_dev) return HEMO_EINVAL;
-    HEMO_2D_ONLY(ctx, "wall shear stress");
     if (!ctx->cells || !ctx->have_par) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / params not set");
     const HemoFacetSet& fs = ctx->fsets[set_id];
-    HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(wss_dev, 0, sizeof(double) * 2 * ctx->n, ctx->stream));
+    HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(wss_dev, 0, sizeof(double) * ctx->dim * ctx->n, ctx->stream));
     if (fs.m == 0) return 0;
     const int grid = hemo_grid(fs.m, 128);
-    if (ctx->nv == 4)
+    if (ctx->dim == 3)
+        k_tet_wss<<<grid, 128, 0, ctx->stream>>>(fs.m, fs.cells, fs.mask, ctx->cells, ctx->x, x_dev, ctx->par.mu, wss_dev);
+    else if (ctx->nv == 4)
         k_wss<4><<<grid, 128, 0, ctx->stream>>>(fs.m, ctx->n, fs.cells, fs.mask, ctx->cells, ctx->x, x_dev, ctx->par.mu, wss_dev);
     else
         k_wss<3><<<grid, 128, 0, ctx->stream>>>(fs.m, ctx->n, fs.cells, fs.mask, ctx->cells, ctx->x, x_dev, ctx->par.mu, wss_dev);
@@ -333,14 +359,15 @@ extern "C" int hemo_early_stop_norms(hemo_ctx* ctx, int64_t n, const double* u_d
 }
 
 extern "C" int hemo_l2_norm_sq(hemo_ctx* ctx, int bs, const double* f_dev, double* out_host) {
-    if (!ctx || !f_dev || !out_host || (bs != 1 && bs != 2)) return HEMO_EINVAL;
-    HEMO_2D_ONLY(ctx, "the L2 norm");
+    if (!ctx || !f_dev || !out_host || (bs != 1 && bs != ctx->dim)) return HEMO_EINVAL;
     if (!ctx->cells) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh not set");
     int rc = hemo_ensure_reduce(ctx, (size_t)PP_BLOCKS, 8);
     if (rc) return rc;
     int g = hemo_grid(ctx->E, PP_THREADS);
     if (g > PP_BLOCKS) g = PP_BLOCKS;
-    if (ctx->nv == 4)
+    if (ctx->dim == 3)
+        k_tet_l2_partial<<<g, PP_THREADS, 0, ctx->stream>>>(ctx->E, bs, ctx->cells, ctx->x, f_dev, ctx->red_partial);
+    else if (ctx->nv == 4)
         k_l2_partial<4><<<g, PP_THREADS, 0, ctx->stream>>>(ctx->E, bs, ctx->cells, ctx->x, f_dev, ctx->red_partial);
     else
         k_l2_partial<3><<<g, PP_THREADS, 0, ctx->stream>>>(ctx->E, bs, ctx->cells, ctx->x, f_dev, ctx->red_partial);

@@ -304,3 +304,69 @@ HEMO_HD void tet_selfp_item(int64_t s, int64_t nnz_node, const int32_t* rowof2, 
     }
     out[s] = (OutT)v;
 }
+
+// ---------------------------------------------------------------------------
+// Per-step post-processing on tetrahedra (postproc.cu)
+// ---------------------------------------------------------------------------
+// int_K |f|^2 for a P1 field with bs interleaved components: |J| / 120 * sum_k ((sum_a F_a)^2 + sum_a F_a^2)
+HEMO_HD double tet_l2_item(int c, int bs, const int32_t* cells, const double* x, const double* f) {
+    SimplexCell<3> cd;
+    double X[4][3];
+    int v[4];
+    for (int a = 0; a < 4; ++a) {
+        v[a] = cells[4 * (int64_t)c + a];
+        for (int k = 0; k < 3; ++k) X[a][k] = x[3 * (int64_t)v[a] + k];
+    }
+    simplex_geometry<3>(cd, X);
+    double acc = 0.0;
+    for (int k = 0; k < bs; ++k) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int a = 0; a < 4; ++a) {
+            const double F = f[(int64_t)v[a] * bs + k];
+            s1 += F; s2 += F * F;
+        }
+        acc += s1 * s1 + s2;
+    }
+    return cd.detJ / 120.0 * acc;
+}
+
+// solver.assemble_wss() (src/solverBase.py:144-195) on the tagged facets of boundary cell t:
+// add(node, k, value) receives (1/|F|) int_F phi_i ds * Tt_k = Tt_k / 3 for the three facet vertices,
+// Tt = T - (T.n) n, T = -2 mu eps(u) n (eps constant on a P1 cell).
+template <typename Add>
+HEMO_HD void tet_wss_item(int t, const int32_t* fcells, const int32_t* fmask, const int32_t* cells, const double* x,
+                          const double* sol, double mu, Add add) {
+    const int c = fcells[t];
+    const int mask = fmask[t];
+    SimplexCell<3> cd;
+    double X[4][3], U[4][3];
+    int v[4];
+    for (int a = 0; a < 4; ++a) {
+        v[a] = cells[4 * (int64_t)c + a];
+        for (int k = 0; k < 3; ++k) { X[a][k] = x[3 * (int64_t)v[a] + k]; U[a][k] = sol[3 * (int64_t)v[a] + k]; }
+    }
+    simplex_geometry<3>(cd, X);
+    double G[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double g = 0.0;
+            for (int a = 0; a < 4; ++a) g += cd.g[a][i] * U[a][j];
+            G[i][j] = g;
+        }
+    for (int lf = 0; lf < 4; ++lf) {
+        if (!(mask & (1 << lf))) continue;
+        double nr[3], scale;
+        simplex_facet_normal<3>(cd, lf, nr, scale);
+        double T[3], tn = 0.0;
+        for (int i = 0; i < 3; ++i) {
+            double e = 0.0;
+            for (int j = 0; j < 3; ++j) e += 0.5 * (G[i][j] + G[j][i]) * nr[j];
+            T[i] = -2.0 * mu * e;
+            tn += T[i] * nr[i];
+        }
+        for (int a = 0; a < 4; ++a) {
+            if (a == lf) continue;
+            for (int k = 0; k < 3; ++k) add(v[a], k, (T[k] - tn * nr[k]) / 3.0);
+        }
+    }
+}

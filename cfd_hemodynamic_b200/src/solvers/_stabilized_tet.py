@@ -5,8 +5,8 @@ cube split into tetrahedra).
 `StabilizedSchurTetB200` sits between `StabilizedSchurB200` and the plugin's `Solver`: on triangles
 and quadrilaterals every method defers to the 2-D implementation unchanged; on tetrahedra it
 sequences the same C-ABI calls with the `[u interleaved (3n) | p (n)]` layout.
-Only the plain `stabilized_schur` variant is wired in 3-D; the device post-processing kernels are
-2-D only, so `Scenario.solve` (host post-processing) works and `Scenario.solve_device` does not yet.
+Only the plain `stabilized_schur` variant is wired in 3-D.  Both time loops run: `Scenario.solve` (host
+post-processing) and `Scenario.solve_device` (wall shear stress, early-stop and L2 norms as kernels).
 """
 from __future__ import annotations
 
@@ -19,7 +19,7 @@ from ...fem import discretization as D
 from ...fem import quadrature as Q
 from ...fem.mesh import exterior_facet_indices
 from ...linear_solver import BlockSchurSolver
-from ._stabilized_common import BLOCK_DEGREE, SET_ALL, StabilizedSchurB200
+from ._stabilized_common import BLOCK_DEGREE, SET_ALL, SET_WSS, StabilizedSchurB200
 
 # UFL's degree estimate of the all-facet term p n.v - mu (grad(u) n).v on P1 (stabilized_schur.py:79)
 FACET_DEGREE_TET = 2
@@ -186,6 +186,11 @@ class StabilizedSchurTetB200(StabilizedSchurB200):
         self._torch.cuda.current_stream(self.hemo.device).synchronize()
         self._after_step()
 
+    def step_device(self, shift: bool = True):
+        if self._tet:
+            self._upload_bc_values()         # time-dependent boundary data (taylor_green): boundary-sized, only when changed
+        return super().step_device(shift)
+
     def shift_time_level_device(self):
         if not self._tet:
             return super().shift_time_level_device()
@@ -199,8 +204,21 @@ class StabilizedSchurTetB200(StabilizedSchurB200):
     def initStressForm(self):
         if not self._tet:
             return super().initStressForm()
-        # host traction form only (SolverBase): the device WSS kernel is 2-D
-        return super(StabilizedSchurB200, self).initStressForm()
+        super(StabilizedSchurB200, self).initStressForm()          # host traction form (SolverBase)
+        if self.hemo is not None:
+            self._register_facets(SET_WSS, exterior_facet_indices(self.mesh.topology))
+            self.d_wss = self._torch.zeros(3 * self.n, dtype=self._torch.float64, device=self.hemo.device)
+
+    def l2_norms_device(self):
+        if not self._tet:
+            return super().l2_norms_device()
+        n = self.n
+        return (math.sqrt(self.hemo.l2_norm_sq(self.d_x[:3 * n], 3)), math.sqrt(self.hemo.l2_norm_sq(self.d_x[3 * n:], 1)))
+
+    def boundary_force_device(self, facets):
+        if not self._tet:
+            return super().boundary_force_device(facets)
+        raise NotImplementedError("tetrahedra: the drag / lift integrals are the 2-D forms of dfg_1.py:189-202")
 
     def download_solution(self):
         if not self._tet:
@@ -211,6 +229,8 @@ class StabilizedSchurTetB200(StabilizedSchurB200):
         self._pin["u_residual"].copy_(self.d_f[:3 * n], non_blocking=True)
         self._pin["p_residual"].copy_(self.d_f[3 * n:], non_blocking=True)
         self._pin["u_prev"].copy_(self.d_un, non_blocking=True)
+        if getattr(self, "d_wss", None) is not None and getattr(self, "shear_stress", None) is not None:
+            self.shear_stress.x.array[:] = self.d_wss.cpu().numpy()
         self._torch.cuda.current_stream(self.hemo.device).synchronize()
 
     @property

@@ -221,4 +221,17 @@ void txh_selfp(int64_t nnz2, int64_t nnz_node, const int32_t* rowof2, const int3
     for (int64_t s = 0; s < nnz2; ++s) tet_selfp_item<double>(s, nnz_node, rowof2, col2, nrowptr, ncol, diagslot, vals, out);
 }
 
+// Emulated k_tet_l2_partial / k_tet_wss (post-processing on tetrahedra); wss: 3n, zero-initialised by the caller
+double txh_l2(int E, int bs, const int32_t* cells, const double* x, const double* f) {
+    double acc = 0.0;
+    for (int c = 0; c < E; ++c) acc += tet_l2_item(c, bs, cells, x, f);
+    return acc;
+}
+
+void txh_wss(int m, const int32_t* fcells, const int32_t* fmask, const int32_t* cells, const double* x, const double* sol,
+             double mu, double* wss) {
+    for (int t = 0; t < m; ++t)
+        tet_wss_item(t, fcells, fmask, cells, x, sol, mu, [wss](int node, int k, double v) { wss[3 * (int64_t)node + k] += v; });
+}
+
 }  // extern "C"

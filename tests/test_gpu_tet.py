@@ -154,8 +154,8 @@ def test_tet_csr_assembly_matches_oracle():
     m_ref = np.zeros(n)
     np.add.at(m_ref, cells.reshape(-1), np.repeat(det / 24.0, 4))
     assert np.linalg.norm(mass.cpu().numpy() - m_ref) < 1e-13 * np.linalg.norm(m_ref)
-    # what is not there yet fails loudly: post-processing kernels are 2-D only
+    # what is not there in 3-D fails loudly: the drag / lift integrals are the 2-D DFG forms
     from cfd_hemodynamic_b200._lib import HemoError
     with pytest.raises(HemoError):
-        hemo.l2_norm_sq(T(sol), 1)
+        hemo.boundary_force(0, T(sol))
     hemo.close()

@@ -222,6 +222,18 @@ def test_taylor_green_plugin_matches_oracle(tmp_path):
     norms = open(f"{out}/norms.txt").read()
     assert "L2 norm of velocity" in norms
 
+    # the device-resident loop (wall shear stress, early-stop and L2 norms as kernels) gives the same fields
+    from cfd_hemodynamic_b200.src.scenario import l2_norm_sq
+    sc3 = TaylorGreenSimulation("stabilized_schur", dt, 3 * dt, rho=1, mu=mu, n=4)
+    nsteps, norm_v, norm_p = sc3.solve_device(None, afterStepCallback=sc3.update_boundary_conditions)
+    assert nsteps == 3
+    assert np.array_equal(sc3.solver.u_sol.x.array, sc2.solver.u_sol.x.array)
+    assert np.array_equal(sc3.solver.p_sol.x.array, sc2.solver.p_sol.x.array)
+    assert abs(norm_v - np.sqrt(l2_norm_sq(sc2.mesh, sc2.solver.u_sol))) < 1e-12 * norm_v
+    assert abs(norm_p - np.sqrt(l2_norm_sq(sc2.mesh, sc2.solver.p_sol))) < 1e-12 * norm_p
+    w_host, w_dev = sc2.solver.shear_stress.x.array, sc3.solver.shear_stress.x.array
+    assert np.abs(w_host).max() > 0 and np.abs(w_dev - w_host).max() < 1e-12 * np.abs(w_host).max()
+
 
 def test_golden_tet_case_on_gpu():
     """The committed 3-D golden vectors (tests/golden/p1tet_small.npz) are reproduced by the CUDA path."""

@@ -308,3 +308,32 @@ def test_emulated_tet_selfp(lib):
     got = sp.csr_matrix((out, col2, G2.indptr), shape=(n, n))
     d = (got - Sp).tocoo()
     assert np.abs(d.data).max() < 1e-12 * np.abs(Sp.data).max()
+
+
+def test_emulated_tet_postprocessing(lib):
+    """Device post-processing items on tetrahedra (L2 norm, wall-shear-stress vector) against the host versions
+    `Scenario.solve` uses (src/scenario.py:l2_norm_sq, src/solverBase.py:assemble_wss)."""
+    from cfd_hemodynamic_b200.fem import mesh as M
+    from cfd_hemodynamic_b200.src.scenario import l2_norm_sq
+    from cfd_hemodynamic_b200.src.scenarios.taylor_green import TaylorGreenSimulation
+    sc = TaylorGreenSimulation("stabilized_schur", 0.005, 0.01, rho=1, mu=0.7, n=3, host_only=True)
+    s = sc.solver
+    mesh = sc.mesh
+    x = np.ascontiguousarray(mesh.geometry.x)
+    cells = np.ascontiguousarray(mesh.geometry.dofmap, dtype=np.int32)
+    n, E = x.shape[0], cells.shape[0]
+    rng = np.random.default_rng(6)
+    s.u_sol.x.array[:] = rng.standard_normal(3 * n)
+    s.p_sol.x.array[:] = rng.standard_normal(n)
+    lib.txh_l2.restype = ctypes.c_double
+    lu = lib.txh_l2(E, 3, _p(cells), _p(x), _p(_c(s.u_sol.x.array)))
+    lp = lib.txh_l2(E, 1, _p(cells), _p(x), _p(_c(s.p_sol.x.array)))
+    assert abs(lu - l2_norm_sq(mesh, s.u_sol)) < 1e-13 * lu and abs(lp - l2_norm_sq(mesh, s.p_sol)) < 1e-13 * lp
+    s.initStressForm()
+    s.assemble_wss()
+    fc, fm = D.facet_set_by_cell(mesh, M.exterior_facet_indices(mesh.topology))
+    wss = np.zeros(3 * n)
+    sol = np.concatenate([s.u_sol.x.array, s.p_sol.x.array])
+    lib.txh_wss(len(fc), _p(fc), _p(fm), _p(cells), _p(x), _p(sol), ctypes.c_double(0.7), _p(wss))
+    ref = s.shear_stress.x.array
+    assert np.abs(ref).max() > 0 and np.abs(wss - ref).max() < 1e-13 * np.abs(ref).max()
