@@ -1,0 +1,102 @@
+"""CPU ORACLE — TEST INFRASTRUCTURE ONLY.  **PARITY UNPINNED** (see ns_oracle.py).
+
+GROUNDWORK for SURVEY.md §8(f) rank 4: the cell integrals of the curl-curl ("rotational") formulation of
+src/solvers/stabilized_schur_pressurebc.py:85-160 on P1–P1 simplices (d = 2 triangles, d = 3 tetrahedra),
+FFCx-style (full integrand at every quadrature point):
+
+    F_u(v) = rho (v, (u - u_n)/dt) + mu (curl u_m, curl v) - (p, div v) + rho ((curl u_m x u_m) . v)
+             - rho/2 (u_m . u_m, div v) - rho (v, f)                                   (:126-132)
+           + (tau R, (u_m . grad) v) + tau_lsic rho (div u_m, div v)                   (:152-158)
+    F_p(q) = (q, div u_m) + (1/rho) (tau R, grad q)                                    (:133, :153)
+    R      = rho ((u - u_n)/dt + curl u_m x u_m) + grad p - rho f                      (:143-145)
+
+with u_m = (u + u_n)/2 (:89), tau / tau_lsic as in stabilized_schur.py (:147-157, functions of u_n only).
+In 2-D, curl u is the scalar omega = d_x u_y - d_y u_x and curl u x w = (-omega w_y, omega w_x) (:96-110).
+No CUDA kernel follows this oracle yet; the Jacobian is the complex-step derivative of the residual (exact to
+round-off: the residual is analytic in (U, P), tau depends on u_n only).
+Layout as in simplex_oracle: U, Un (E, d+1, d), P (E, d+1) -> Fu (E, d+1, d), Fp (E, d+1).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .simplex_oracle import _phi, _tau, simplex_geometry
+
+
+def _curl(G, d):
+    """curl of a field with gradient G[e, i, j] = d_i u_j: (E,) in 2-D, (E, 3) in 3-D."""
+    if d == 2:
+        return G[:, 0, 1] - G[:, 1, 0]
+    return np.stack([G[:, 1, 2] - G[:, 2, 1], G[:, 2, 0] - G[:, 0, 2], G[:, 0, 1] - G[:, 1, 0]], axis=1)
+
+
+def _curl_cross(om, w, d):
+    """curl u x w."""
+    if d == 2:
+        return np.stack([-om * w[:, 1], om * w[:, 0]], axis=1)
+    return np.cross(om, w)
+
+
+def element_F(x, cells, h, U, P, Un, rule, dt, rho, mu, f, eps0):
+    det, dphi = simplex_geometry(x, cells)
+    d = x.shape[1]
+    nv = d + 1
+    pts, wts = rule
+    f = np.asarray(f, dtype=np.float64)
+    Um = 0.5 * (U + Un)
+    G = np.einsum("eai,eaj->eij", dphi, Um)
+    gradp = np.einsum("eai,ea->ei", dphi, P)
+    divu = np.einsum("eii->e", G)
+    om = _curl(G, d)
+    # curl of the test functions v = phi_a e_k: gradient d_i v_j = dphi[a, i] delta_jk
+    E = U.shape[0]
+    curl_v = np.zeros((E, nv, d) + (() if d == 2 else (3,)), dtype=np.float64)
+    for a in range(nv):
+        for k in range(d):
+            Gv = np.zeros((E, d, d))
+            Gv[:, :, k] = dphi[:, a, :]
+            curl_v[:, a, k] = _curl(Gv, d)
+    cc = om[:, None, None] * curl_v if d == 2 else np.einsum("ec,eakc->eak", om, curl_v)     # curl u_m . curl v
+    Fu = np.zeros(U.shape, dtype=np.result_type(U, P))
+    Fp = np.zeros(P.shape, dtype=Fu.dtype)
+    for q in range(len(wts)):
+        phi = _phi(pts[q])
+        w = wts[q] * det
+        u = np.einsum("a,eai->ei", phi, U)
+        un = np.einsum("a,eai->ei", phi, Un)
+        um = 0.5 * (u + un)
+        p = np.einsum("a,ea->e", phi, P)
+        tau, tau_l = _tau(un.real, h, dt, rho, mu, eps0)
+        dudt = (u - un) / dt
+        rot = _curl_cross(om, um, d)
+        R = rho * (dudt + rot) + gradp - rho * f[None, :]
+        um_dphi = np.einsum("ei,eai->ea", um, dphi)
+        half_u2 = 0.5 * np.einsum("ei,ei->e", um, um)
+        Fu = Fu + w[:, None, None] * (
+            rho * phi[None, :, None] * (dudt + rot - f[None, :])[:, None, :]
+            + mu * cc
+            - (p + rho * half_u2)[:, None, None] * dphi                   # -(p + rho |u_m|^2 / 2) div v
+            + tau[:, None, None] * um_dphi[:, :, None] * R[:, None, :]
+            + (tau_l * rho * divu)[:, None, None] * dphi)
+        Fp = Fp + w[:, None] * (phi[None, :] * divu[:, None] + (tau / rho)[:, None] * np.einsum("ei,eai->ea", R, dphi))
+    return Fu, Fp
+
+
+def element_J(x, cells, h, U, P, Un, rule_rows_u, rule_rows_p, dt, rho, mu, f, eps0):
+    """(E, (d+1)(d+1), (d+1)(d+1)) derivative of [Fu (rule_rows_u) ; Fp (rule_rows_p)] with respect to
+    [U flattened ; P] by complex steps."""
+    E, nv, d = U.shape
+    nl = (d + 1) * nv
+    J = np.zeros((E, nl, nl))
+    step = 1e-30
+    for j in range(nl):
+        Uc, Pc = U.astype(complex), P.astype(complex)
+        if j < d * nv:
+            Uc[:, j // d, j % d] += 1j * step
+        else:
+            Pc[:, j - d * nv] += 1j * step
+        Fu, _ = element_F(x, cells, h, Uc, Pc, Un, rule_rows_u, dt, rho, mu, f, eps0)
+        _, Fp = element_F(x, cells, h, Uc, Pc, Un, rule_rows_p, dt, rho, mu, f, eps0)
+        J[:, :d * nv, j] = Fu.reshape(E, -1).imag / step
+        J[:, d * nv:, j] = Fp.imag / step
+    return J

@@ -338,3 +338,106 @@ class SimplexForms:
                 vals = self._f(*pt, *U.reshape(-1), *P)
                 out[sl] += w * vals[-1] * np.array(vals[:-1], dtype=out.dtype)[sl]
         return out[:d * nv].reshape(nv, d), out[d * nv:]
+
+
+class CurlCurlForms:
+    """Literal transcription of the cell integrals of src/solvers/stabilized_schur_pressurebc.py:85-160 (curl-curl
+    viscous term, rotational convection) on one P1 simplex, d = 2 or 3: cross-check of `curlcurl_oracle`."""
+
+    def __init__(self, X, Un, h, dt, rho, mu, f, eps0):
+        nv, d = X.shape
+        assert nv == d + 1
+        self.nv, self.d = nv, d
+        xi = sp.symbols(f"xi0:{d}", real=True)
+        phi = [1 - sum(xi)] + list(xi)
+        x = [sum(sp.Float(X[a, i]) * phi[a] for a in range(nv)) for i in range(d)]
+        J = sp.Matrix(d, d, lambda i, j: sp.diff(x[i], xi[j]))
+        detJ = J.det()
+        K = J.inv()
+        R_ = range(d)
+
+        def dx(fn, i):                                    # w.dx(i)
+            return sum(K[j, i] * sp.diff(fn, xi[j]) for j in R_)
+
+        def grad(fn):
+            return [dx(fn, i) for i in R_]
+
+        def nabla_grad(v):
+            return [[dx(v[j], i) for j in R_] for i in R_]
+
+        def div(v):
+            return sum(dx(v[i], i) for i in R_)
+
+        def dot(a, b):
+            return sum(a[i] * b[i] for i in R_)
+
+        if d == 2:                                        # :96-110
+            def _rot(w):
+                return dx(w[1], 0) - dx(w[0], 1)
+
+            def curl_curl_inner(u, v):
+                return _rot(u) * _rot(v)
+
+            def cross_curl_vec(w):
+                om = _rot(w)
+                return [-om * w[1], om * w[0]]
+        else:                                             # :112-122
+            def curl(w):
+                return [dx(w[2], 1) - dx(w[1], 2), dx(w[0], 2) - dx(w[2], 0), dx(w[1], 0) - dx(w[0], 1)]
+
+            def cross(a, b):
+                return [a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]]
+
+            def curl_curl_inner(u, v):
+                return dot(curl(u), curl(v))
+
+            def cross_curl_vec(w):
+                return cross(curl(w), w)
+
+        self.Us = sp.symbols(f"U0:{d * nv}")
+        self.Ps = sp.symbols(f"P0:{nv}")
+        u_sol = [sum(self.Us[d * a + k] * phi[a] for a in range(nv)) for k in R_]
+        p_sol = sum(self.Ps[a] * phi[a] for a in range(nv))
+        u_prev = [sum(sp.Float(Un[a, k]) * phi[a] for a in range(nv)) for k in R_]
+        dt_, rho_, mu_, h_ = sp.Float(dt), sp.Float(rho), sp.Float(mu), sp.Float(h)
+        fvec = [sp.Float(v) for v in f]
+        u_mid = [(u_sol[k] + u_prev[k]) / 2 for k in R_]                               # :89
+        vnorm = sp.sqrt(dot(u_prev, u_prev))                                           # :141
+        Rs = [rho_ * ((u_sol[k] - u_prev[k]) / dt_ + cross_curl_vec(u_mid)[k]) for k in R_]    # :143-144
+        gp = grad(p_sol)
+        Rs = [Rs[k] + gp[k] - rho_ * fvec[k] for k in R_]                              # :145
+        eps = sp.Float(eps0)
+        tau1 = h_ / sp.Piecewise((2 * vnorm, 2 * vnorm >= eps), (eps, True))           # :148
+        tau = (1 / tau1 ** 2 + 1 / (dt_ / 2) ** 2 + 1 / ((h_ * h_) / (4 * (mu_ / rho_))) ** 2) ** sp.Rational(-1, 2)
+        Re = (vnorm * h_) / (2 * (mu_ / rho_))                                         # :155
+        z = sp.Piecewise((Re / 3, Re <= 3), (1, True))
+        tau_lsic = (vnorm * h_ * z) / 2                                                # :157
+        integrands = []
+        for a in range(nv):
+            for k in R_:
+                v = [phi[a] if i == k else sp.Integer(0) for i in R_]
+                Fv = rho_ * dot(v, [(u_sol[i] - u_prev[i]) / dt_ for i in R_])         # :126
+                Fv += mu_ * curl_curl_inner(u_mid, v)                                  # :127
+                Fv -= p_sol * div(v)                                                   # :128
+                Fv += rho_ * dot(cross_curl_vec(u_mid), v)                             # :129
+                Fv -= rho_ * sp.Rational(1, 2) * dot(u_mid, u_mid) * div(v)            # :130
+                Fv -= rho_ * dot(v, fvec)                                              # :131
+                ngv = nabla_grad(v)
+                Fv += dot([tau * r for r in Rs], [sum(u_mid[i] * ngv[i][j] for i in R_) for j in R_])   # :152
+                Fv += tau_lsic * div(u_mid) * rho_ * div(v)                            # :158
+                integrands.append(Fv)
+        for a in range(nv):
+            q = phi[a]
+            integrands.append(q * div(u_mid) + (1 / rho_) * dot([tau * r for r in Rs], grad(q)))        # :132, :153
+        args = tuple(xi) + tuple(self.Us) + tuple(self.Ps)
+        self._f = sp.lambdify(args, integrands + [sp.Abs(detJ)], modules="numpy", cse=True)
+
+    def cell_residual(self, U, P, rule_u, rule_p):
+        nv, d = self.nv, self.d
+        out = np.zeros((d + 1) * nv, dtype=np.result_type(U, P))
+        for rule, sl in ((rule_u, slice(0, d * nv)), (rule_p, slice(d * nv, (d + 1) * nv))):
+            pts, wts = rule
+            for pt, w in zip(pts, wts):
+                vals = self._f(*np.atleast_1d(pt), *U.reshape(-1), *P)
+                out[sl] += w * vals[-1] * np.array(vals[:-1], dtype=out.dtype)[sl]
+        return out[:d * nv].reshape(nv, d), out[d * nv:]
