@@ -1,0 +1,138 @@
+// GROUNDWORK: dimension-generic P1–P1 simplex element routine of the curl-curl /
+// rotational formulation of src/solvers/stabilized_schur_pressurebc.py:85-160 (and the `vascularbc` family
+// built on it).  Not wired into libhemo_sm100.so yet: checked on the host against oracle/curlcurl_oracle.py
+// (tests/test_curlcurl_host.py, compiled with g++: test infrastructure only).
+//
+// With G_ij = d_i u_mj and the antisymmetric W_ij = G_ij - G_ji both curl expressions of the form are
+// dimension-independent:
+//     (curl u_m x w)_k = sum_i w_i W_ik ,      curl u_m . curl(phi_a e_k) = sum_i W_ik d_i phi_a
+// (2-D: W_01 = omega, :96-110; 3-D: W_ij = eps_ijc omega_c, :112-122).  On an affine P1 cell W, div u_m and
+// grad p are constant; u, u_n, p and tau vary with the quadrature point, so the integrand is evaluated
+// at every point of the block form's rule (FFCx-style; a moment factorisation like simplex_element.cuh
+// is the optimisation to do when this becomes a kernel).
+//
+//   F_u[a][k] = int rho phi_a (dudt + rot - f)_k + mu sum_i W_ik d_i phi_a - (p + rho |u_m|^2 / 2) d_k phi_a
+//                   + tau (u_m . grad phi_a) R_k + tau_lsic rho div(u_m) d_k phi_a
+//   F_p[a]    = int phi_a div(u_m) + (tau / rho) R . grad phi_a
+//   R = rho (dudt + rot) + grad p - rho f,  dudt = (u - u_n) / dt,  rot = curl u_m x u_m,  u_m = (u + u_n) / 2
+#pragma once
+#include "simplex_element.cuh"
+
+// Residual and Jacobian of one cell with one rule.  `c` needs g, detJ, U, N, P, h, fbody
+// (simplex_geometry + nodal values; simplex_derive is not used).  Outputs are ADDED:
+//   Fu[a][k], Fp[a];  J[r][s] with r, s in the cell-local order (a*D + k for velocity, D*NV + a for pressure).
+// rows_u / rows_p select which rows this rule integrates (each block form has its own rule).
+template <int D>
+HEMO_HD void curlcurl_cell(const SimplexCell<D>& c, const HemoForm& par, const SimplexRule<D>& r, bool rows_u,
+                           bool rows_p, bool want_jac, double Fu[D + 1][D], double Fp[D + 1],
+                           double* J /* [(D+1)^2][(D+1)^2] or nullptr */) {
+    constexpr int NV = D + 1, NL = (D + 1) * (D + 1), PO = D * NV;
+    const double rho = par.rho, mu = par.mu, idt = 1.0 / par.dt, th = 0.5;
+    double G[D][D], W[D][D], gp[D], divu = 0.0;
+    for (int i = 0; i < D; ++i) {
+        for (int j = 0; j < D; ++j) {
+            double v = 0.0;
+            for (int a = 0; a < NV; ++a) v += c.g[a][i] * 0.5 * (c.U[a][j] + c.N[a][j]);
+            G[i][j] = v;
+        }
+        double v = 0.0;
+        for (int a = 0; a < NV; ++a) v += c.g[a][i] * c.P[a];
+        gp[i] = v;
+    }
+    for (int i = 0; i < D; ++i) {
+        divu += G[i][i];
+        for (int j = 0; j < D; ++j) W[i][j] = G[i][j] - G[j][i];
+    }
+    double gg[NV][NV];
+    for (int a = 0; a < NV; ++a)
+        for (int b = 0; b < NV; ++b) {
+            double v = 0.0;
+            for (int i = 0; i < D; ++i) v += c.g[a][i] * c.g[b][i];
+            gg[a][b] = v;
+        }
+    const double h = c.h, nu = mu / rho;
+    for (int q = 0; q < r.nq; ++q) {
+        const double* phi = r.phi[q];
+        const double w = r.w[q] * c.detJ;
+        double u[D], un[D], um[D], p = 0.0, v2 = 0.0, um2 = 0.0;
+        for (int k = 0; k < D; ++k) {
+            double a1 = 0.0, a2 = 0.0;
+            for (int a = 0; a < NV; ++a) { a1 += phi[a] * c.U[a][k]; a2 += phi[a] * c.N[a][k]; }
+            u[k] = a1; un[k] = a2; um[k] = 0.5 * (a1 + a2);
+            v2 += a2 * a2; um2 += um[k] * um[k];
+        }
+        for (int a = 0; a < NV; ++a) p += phi[a] * c.P[a];
+        // tau_supg, tau_lsic (functions of u_n only; stabilized_schur_pressurebc.py:147-157)
+        const double vn = sqrt(v2);
+        const double two_v = 2.0 * vn;
+        const double t1 = h / (two_v >= par.eps0 ? two_v : par.eps0);
+        const double t2 = par.dt / 2.0, t3 = h * h / (4.0 * nu);
+        const double tau = 1.0 / sqrt(1.0 / (t1 * t1) + 1.0 / (t2 * t2) + 1.0 / (t3 * t3));
+        const double Re = vn * h / (2.0 * nu);
+        const double tl = 0.5 * vn * h * (Re <= 3.0 ? Re / 3.0 : 1.0);
+        double rot[D], R[D], acc[D], s[NV];
+        for (int k = 0; k < D; ++k) {
+            double v = 0.0;
+            for (int i = 0; i < D; ++i) v += um[i] * W[i][k];
+            rot[k] = v;
+            acc[k] = (u[k] - un[k]) * idt + v - c.fbody[k];
+            R[k] = rho * acc[k] + gp[k];
+        }
+        for (int a = 0; a < NV; ++a) {
+            double v = 0.0;
+            for (int i = 0; i < D; ++i) v += um[i] * c.g[a][i];
+            s[a] = v;                                         // u_m . grad phi_a
+        }
+        const double bern = p + 0.5 * rho * um2;
+        for (int a = 0; a < NV; ++a) {
+            if (rows_u)
+                for (int k = 0; k < D; ++k) {
+                    double cc = 0.0;
+                    for (int i = 0; i < D; ++i) cc += W[i][k] * c.g[a][i];
+                    Fu[a][k] += w * (rho * phi[a] * acc[k] + mu * cc - bern * c.g[a][k] + tau * s[a] * R[k] +
+                                     tl * rho * divu * c.g[a][k]);
+                }
+            if (rows_p) {
+                double rg = 0.0;
+                for (int i = 0; i < D; ++i) rg += R[i] * c.g[a][i];
+                Fp[a] += w * (phi[a] * divu + tau / rho * rg);
+            }
+        }
+        if (!want_jac) continue;
+        for (int b = 0; b < NV; ++b) {
+            // d rot_k / dU[b][l] = th (phi_b W_lk + s_b delta_kl - g_b[k] um_l);  dR_k/dU[b][l] = rho (phi_b/dt delta_kl + d rot)
+            double dR[D][D];                                  // [k][l]
+            for (int k = 0; k < D; ++k)
+                for (int l = 0; l < D; ++l) {
+                    const double dkl = (k == l) ? 1.0 : 0.0;
+                    const double drot = th * (phi[b] * W[l][k] + s[b] * dkl - c.g[b][k] * um[l]);
+                    dR[k][l] = rho * (phi[b] * idt * dkl + drot);
+                }
+            for (int a = 0; a < NV; ++a) {
+                if (rows_u)
+                    for (int k = 0; k < D; ++k) {
+                        const int row = a * D + k;
+                        for (int l = 0; l < D; ++l) {
+                            const double dkl = (k == l) ? 1.0 : 0.0;
+                            double v = phi[a] * dR[k][l];                                         // rho phi_a d(acc_k)
+                            v += mu * th * (gg[a][b] * dkl - c.g[b][k] * c.g[a][l]);              // curl-curl
+                            v -= rho * th * um[l] * phi[b] * c.g[a][k];                           // -rho/2 |u_m|^2 div v
+                            v += tau * (th * phi[b] * c.g[a][l] * R[k] + s[a] * dR[k][l]);        // SUPG
+                            v += tl * rho * th * c.g[b][l] * c.g[a][k];                           // LSIC
+                            J[row * NL + b * D + l] += w * v;
+                        }
+                        J[row * NL + PO + b] += w * (-phi[b] * c.g[a][k] + tau * s[a] * c.g[b][k]);   // J_up
+                    }
+                if (rows_p) {
+                    const int row = PO + a;
+                    for (int l = 0; l < D; ++l) {
+                        double v = phi[a] * th * c.g[b][l];
+                        for (int i = 0; i < D; ++i) v += tau / rho * dR[i][l] * c.g[a][i];
+                        J[row * NL + b * D + l] += w * v;                                          // J_pu
+                    }
+                    J[row * NL + PO + b] += w * tau / rho * gg[a][b];                              // J_pp
+                }
+            }
+        }
+    }
+}

@@ -235,3 +235,54 @@ void txh_wss(int m, const int32_t* fcells, const int32_t* fmask, const int32_t* 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Curl-curl / rotational formulation (csrc/curlcurl_element.cuh): residual with the rules of blocks 0 (F_u rows)
+// and 1 (F_p rows), Jacobian rows with the rules of blocks 2 (velocity rows) and 4 (pressure rows).
+// ---------------------------------------------------------------------------
+#include "../../cfd_hemodynamic_b200/csrc/curlcurl_element.cuh"
+
+template <int D>
+static void run_curlcurl(Rules<D>& R, int E, int n, const int32_t* cells, const double* x, const double* h,
+                         const double* sol, const double* un, double* Fe, double* Je) {
+    constexpr int NV = D + 1, NL = NV * NV;
+    hemo_form_finalize(g_par);
+    for (int c = 0; c < E; ++c) {
+        SimplexCell<D> cd;
+        double X[NV][D];
+        for (int a = 0; a < NV; ++a) {
+            const int v = cells[NV * (int64_t)c + a];
+            for (int k = 0; k < D; ++k) {
+                X[a][k] = x[D * (int64_t)v + k];
+                cd.U[a][k] = sol[D * (int64_t)v + k];
+                cd.N[a][k] = un[D * (int64_t)v + k];
+            }
+            cd.P[a] = sol[D * (int64_t)n + v];
+        }
+        for (int k = 0; k < D; ++k) cd.fbody[k] = g_f[k];
+        cd.h = h[c];
+        simplex_geometry<D>(cd, X);
+        double Fu[NV][D] = {}, Fp[NV] = {}, Fu2[NV][D] = {}, Fp2[NV] = {};
+        double* J = Je + (int64_t)c * NL * NL;
+        curlcurl_cell<D>(cd, g_par, R.r[0], true, false, false, Fu, Fp, nullptr);
+        curlcurl_cell<D>(cd, g_par, R.r[1], false, true, false, Fu, Fp, nullptr);
+        curlcurl_cell<D>(cd, g_par, R.r[2], true, false, true, Fu2, Fp2, J);
+        curlcurl_cell<D>(cd, g_par, R.r[4], false, true, true, Fu2, Fp2, J);
+        double* F = Fe + (int64_t)c * NL;
+        for (int a = 0; a < NV; ++a) {
+            for (int k = 0; k < D; ++k) F[a * D + k] = Fu[a][k];
+            F[D * NV + a] = Fp[a];
+        }
+    }
+}
+
+extern "C" {
+
+// Fe: [E][(D+1)^2] (velocity rows a*D + k, then pressure rows), Je: [E][(D+1)^2][(D+1)^2], zero-initialised
+void cch_cells(int dim, int E, int n, const int32_t* cells, const double* x, const double* h, const double* sol,
+               const double* un, double* Fe, double* Je) {
+    if (dim == 2) run_curlcurl<2>(g_r2, E, n, cells, x, h, sol, un, Fe, Je);
+    else run_curlcurl<3>(g_r3, E, n, cells, x, h, sol, un, Fe, Je);
+}
+
+}  // extern "C"

@@ -22,7 +22,7 @@ def lib():
     out_dir = os.path.join(HERE, "host_simplex", "_build")
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libsimplexhost.so")
-    deps = [src] + [os.path.join(HERE, "..", "cfd_hemodynamic_b200", "csrc", f) for f in ("simplex_element.cuh", "hemo_rules.h")]
+    deps = [src] + [os.path.join(HERE, "..", "cfd_hemodynamic_b200", "csrc", f) for f in ("simplex_element.cuh", "tet_items.cuh", "curlcurl_element.cuh", "hemo_rules.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src], check=True)
     L = ctypes.CDLL(so)

@@ -31,7 +31,7 @@ def lib():
     so = os.path.join(out_dir, "libsimplexhost.so")
     csrc = os.path.join(HERE, "..", "cfd_hemodynamic_b200", "csrc")
     deps = [src, os.path.join(HERE, "..", "include", "hemo.h")] + [
-        os.path.join(csrc, f) for f in ("simplex_element.cuh", "tet_items.cuh", "hemo_rules.h")]
+        os.path.join(csrc, f) for f in ("simplex_element.cuh", "tet_items.cuh", "curlcurl_element.cuh", "hemo_rules.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src], check=True)
     L = ctypes.CDLL(so)
