@@ -136,3 +136,91 @@ HEMO_HD void curlcurl_cell(const SimplexCell<D>& c, const HemoForm& par, const S
         }
     }
 }
+
+// Exterior-facet terms of stabilized_schur_pressurebc.setup (:189-201) on local facet lf: weak pressure
+// pconst (n.v) and the Nitsche terms for u_T = 0 written with curl x n,
+//     a_n [ -mu (curl u_m x n).v_T - mu (curl v x n).u_T + (beta_n mu / h) u_T.v_T ],   (curl w x n)_k = sum_i n_i W_ik(w).
+// Uses co.pconst, co.a_n, co.beta_n.  res(a, k, value) adds to F_u[a][k]; jac(a, b, k, l, value) to
+// dF_u[a][k] / dU[b][l] (no pressure dependence).  `c` needs g, detJ, U, N, h.
+template <int D, bool WANT_RES, bool WANT_JAC, typename Res, typename Jac>
+HEMO_HD void curlcurl_facet(const SimplexCell<D>& c, const HemoForm& par, const hemo_facet_coef& co,
+                            const SimplexFacetRule<D>& fr, int lf, Res res, Jac jac) {
+    constexpr int NV = D + 1;
+    const double mu = par.mu, th = 0.5;
+    double nr[D], scale;
+    simplex_facet_normal<D>(c, lf, nr, scale);
+    double Pn[D][D];
+    for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) Pn[i][j] = ((i == j) ? 1.0 : 0.0) - nr[i] * nr[j];
+    double Ph[NV], Ph2[NV][NV];
+    for (int a = 0; a < NV; ++a) {
+        Ph[a] = 0.0;
+        for (int b = 0; b < NV; ++b) Ph2[a][b] = 0.0;
+    }
+    for (int q = 0; q < fr.nq; ++q) {
+        double phi[NV];
+        for (int j = 0, v = 0; v < NV; ++v) phi[v] = (v == lf) ? 0.0 : fr.lam[q][j++];
+        const double w = fr.w[q] * scale;
+        for (int a = 0; a < NV; ++a) {
+            Ph[a] += w * phi[a];
+            for (int b = 0; b < NV; ++b) Ph2[a][b] += w * phi[a] * phi[b];
+        }
+    }
+    double M[NV][D], dn[NV], Png[NV][D];
+    for (int a = 0; a < NV; ++a) {
+        dn[a] = 0.0;
+        for (int i = 0; i < D; ++i) { M[a][i] = 0.5 * (c.U[a][i] + c.N[a][i]); dn[a] += c.g[a][i] * nr[i]; }
+        for (int k = 0; k < D; ++k) {
+            double v = 0.0;
+            for (int i = 0; i < D; ++i) v += Pn[k][i] * c.g[a][i];
+            Png[a][k] = v;
+        }
+    }
+    const double pen = co.a_n * co.beta_n * mu / c.h;
+    if (WANT_RES) {
+        double Wn[D], WnT[D], Mi[D], MiT[D];
+        for (int k = 0; k < D; ++k) {
+            double v = 0.0;                                   // (curl u_m x n)_k = sum_i n_i (G_ik - G_ki)
+            for (int i = 0; i < D; ++i)
+                for (int a = 0; a < NV; ++a) v += nr[i] * (c.g[a][i] * M[a][k] - c.g[a][k] * M[a][i]);
+            Wn[k] = v;
+            double m = 0.0;
+            for (int a = 0; a < NV; ++a) m += Ph[a] * M[a][k];
+            Mi[k] = m;
+        }
+        for (int k = 0; k < D; ++k) {
+            double v = 0.0, m = 0.0;
+            for (int j = 0; j < D; ++j) { v += Wn[j] * Pn[j][k]; m += Pn[k][j] * Mi[j]; }
+            WnT[k] = v; MiT[k] = m;
+        }
+        for (int a = 0; a < NV; ++a) {
+            double gM = 0.0, Ma[D];
+            for (int k = 0; k < D; ++k) {
+                gM += c.g[a][k] * MiT[k];
+                double m = 0.0;
+                for (int b = 0; b < NV; ++b) m += Ph2[a][b] * M[b][k];
+                Ma[k] = m;
+            }
+            for (int k = 0; k < D; ++k) {
+                double MaT = 0.0;
+                for (int i = 0; i < D; ++i) MaT += Pn[k][i] * Ma[i];
+                double v = co.pconst * Ph[a] * nr[k];
+                v -= co.a_n * mu * Ph[a] * WnT[k];
+                v -= co.a_n * mu * (dn[a] * MiT[k] - gM * nr[k]);
+                v += pen * MaT;
+                res(a, k, v);
+            }
+        }
+    }
+    if (WANT_JAC) {
+        for (int a = 0; a < NV; ++a)
+            for (int b = 0; b < NV; ++b)
+                for (int k = 0; k < D; ++k)
+                    for (int l = 0; l < D; ++l) {
+                        double v = -co.a_n * mu * th * Ph[a] * (dn[b] * Pn[l][k] - Png[b][k] * nr[l]);
+                        v -= co.a_n * mu * th * Ph[b] * (dn[a] * Pn[k][l] - Png[a][l] * nr[k]);
+                        v += th * pen * Pn[k][l] * Ph2[a][b];
+                        jac(a, b, k, l, v);
+                    }
+    }
+}

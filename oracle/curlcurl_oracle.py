@@ -100,3 +100,41 @@ def element_J(x, cells, h, U, P, Un, rule_rows_u, rule_rows_p, dt, rho, mu, f, e
         J[:, :d * nv, j] = Fu.reshape(E, -1).imag / step
         J[:, d * nv:, j] = Fp.imag / step
     return J
+
+
+# --------------------------------------------------------------------------
+# exterior-facet terms of stabilized_schur_pressurebc.setup (:189-205): weak pressure p_c (n.v) and the
+# Nitsche terms for u_T = 0 written with curl x n,
+#     pconst (n.v) + a_n [ -mu (curl u_m x n).v_T - mu (curl v x n).u_T + (beta_n mu / h) u_T.v_T ]
+# (the reference passes p_inlet / 2 and p_outlet / 2 as p_c, :63-64).  (curl w x n)_k = sum_i n_i W_ik(w).
+# --------------------------------------------------------------------------
+def facet_F(x, cells, h, pairs, coef, U, P, Un, facet_rule, mu):
+    """Fu (m, d+1, d) of one facet set; `coef` has pconst, a_n, beta_n.  Independent of P."""
+    from .simplex_oracle import _facet_phi, facet_geometry
+    d = x.shape[1]
+    _, dphi_all = simplex_geometry(x, cells)
+    dphi = dphi_all[pairs[:, 0]]
+    hh = h[pairs[:, 0]]
+    nrm, scale = facet_geometry(x, cells, pairs)
+    Um = 0.5 * (U + Un)
+    G = np.einsum("eai,eaj->eij", dphi, Um)
+    W = G - np.swapaxes(G, 1, 2)
+    Wn = np.einsum("ei,eik->ek", nrm, W)                   # curl u_m x n
+    Pn = np.eye(d)[None] - nrm[:, :, None] * nrm[:, None, :]
+    dn = np.einsum("eai,ei->ea", dphi, nrm)
+    Fu = np.zeros(U.shape, dtype=np.result_type(U, P))
+    pts, wts = facet_rule
+    for q in range(len(wts)):
+        phi = _facet_phi(d, pairs[:, 1], pts[q])
+        w = wts[q] * scale
+        um = np.einsum("ea,eai->ei", phi, Um)
+        uT = np.einsum("eij,ej->ei", Pn, um)
+        val = coef.pconst * phi[:, :, None] * nrm[:, None, :]
+        WnT = np.einsum("ej,ejk->ek", Wn, Pn)
+        val = val - coef.a_n * mu * phi[:, :, None] * WnT[:, None, :]
+        # (curl v x n)_j for v = phi_a e_k: dn_a delta_jk - d_j phi_a n_k   (phi-independent: v enters through its gradient)
+        g_uT = np.einsum("eai,ei->ea", dphi, uT)
+        val = val - coef.a_n * mu * (dn[:, :, None] * uT[:, None, :] - g_uT[:, :, None] * nrm[:, None, :])
+        val = val + coef.a_n * (coef.beta_n * mu / hh)[:, None, None] * phi[:, :, None] * uT[:, None, :]
+        Fu = Fu + w[:, None, None] * val
+    return Fu

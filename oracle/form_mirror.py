@@ -431,6 +431,42 @@ class CurlCurlForms:
             integrands.append(q * div(u_mid) + (1 / rho_) * dot([tau * r for r in Rs], grad(q)))        # :132, :153
         args = tuple(xi) + tuple(self.Us) + tuple(self.Ps)
         self._f = sp.lambdify(args, integrands + [sp.Abs(detJ)], modules="numpy", cse=True)
+        self._args, self._phi, self._u_mid, self._mu, self._h = args, phi, u_mid, mu_, h_
+        if d == 2:                                        # _cross_curl_n, :105-107 / :121-122
+            self._cross_curl_n = lambda w, n: [-_rot(w) * n[1], _rot(w) * n[0]]
+        else:
+            self._cross_curl_n = lambda w, n: cross(curl(w), n)
+
+    def facet_residual(self, U, P, lf, nrm, scale, rule, pconst=0.0, a_n=0.0, beta_n=0.0):
+        """Fu (nv, d) of the ds terms of stabilized_schur_pressurebc.setup on local facet `lf`: p_c dot(v, n)
+        (:189-190) and the Nitsche terms (:193-201)."""
+        nv, d = self.nv, self.d
+        R_ = range(d)
+        n = [sp.Float(v) for v in nrm]
+        u, mu_, h_ = self._u_mid, self._mu, self._h
+        dot = lambda a, b: sum(a[i] * b[i] for i in R_)
+        u_T = [u[i] - dot(u, n) * n[i] for i in R_]                                    # :195
+        exprs = []
+        for a in range(nv):
+            for k in R_:
+                v = [self._phi[a] if i == k else sp.Integer(0) for i in R_]
+                v_T = [v[i] - dot(v, n) * n[i] for i in R_]                            # :196
+                e = pconst * dot(v, n)                                                 # :189-190
+                e += a_n * (-mu_ * dot(self._cross_curl_n(u, n), v_T)                  # :199
+                            - mu_ * dot(self._cross_curl_n(v, n), u_T)                 # :200
+                            + (beta_n * mu_ / h_) * dot(u_T, v_T))                     # :201
+                exprs.append(e)
+        fn = sp.lambdify(self._args, exprs, modules="numpy", cse=True)
+        ref = np.vstack([np.zeros((1, d)), np.eye(d)])
+        fverts = [v for v in range(nv) if v != lf]
+        out = np.zeros(d * nv, dtype=np.result_type(U, P))
+        pts, wts = rule
+        for pt, w in zip(pts, wts):
+            pt = np.atleast_1d(pt)
+            lam = np.concatenate([[1.0 - pt.sum()], pt])
+            xi = sum(lam[j] * ref[fverts[j]] for j in range(d))
+            out += w * scale * np.array(fn(*xi, *U.reshape(-1), *P), dtype=out.dtype)
+        return out.reshape(nv, d)
 
     def cell_residual(self, U, P, rule_u, rule_p):
         nv, d = self.nv, self.d

@@ -286,3 +286,46 @@ void cch_cells(int dim, int E, int n, const int32_t* cells, const double* x, con
 }
 
 }  // extern "C"
+
+template <int D>
+static void run_curlcurl_facets(int m, int n, const int32_t* pairs, const int32_t* cells, const double* x, const double* h,
+                                const double* sol, const double* un, const hemo_facet_coef* co, const double* fpts,
+                                const double* fwts, int nq, double* Fu, double* J) {
+    constexpr int NV = D + 1;
+    hemo_form_finalize(g_par);
+    SimplexFacetRule<D> fr;
+    simplex_facet_rule_set<D>(fr, fpts, fwts, nq);
+    for (int t = 0; t < m; ++t) {
+        const int c = pairs[2 * t], lf = pairs[2 * t + 1];
+        SimplexCell<D> cd;
+        double X[NV][D];
+        for (int a = 0; a < NV; ++a) {
+            const int v = cells[NV * (int64_t)c + a];
+            for (int k = 0; k < D; ++k) {
+                X[a][k] = x[D * (int64_t)v + k];
+                cd.U[a][k] = sol[D * (int64_t)v + k];
+                cd.N[a][k] = un[D * (int64_t)v + k];
+            }
+        }
+        cd.h = h[c];
+        simplex_geometry<D>(cd, X);
+        double* fu = Fu + (int64_t)t * NV * D;
+        double* jj = J + (int64_t)t * NV * NV * D * D;
+        curlcurl_facet<D, true, true>(
+            cd, g_par, *co, fr, lf, [&](int a, int k, double v) { fu[a * D + k] += v; },
+            [&](int a, int b, int k, int l, double v) { jj[((a * NV + b) * D + k) * D + l] += v; });
+    }
+}
+
+extern "C" {
+
+// Fu: [m][NV][D], J: [m][NV][NV][D][D] (zero-initialised by the caller)
+void cch_facets(int dim, int m, int n, const int32_t* pairs, const int32_t* cells, const double* x, const double* h,
+                const double* sol, const double* un, const double* coef8, const double* fpts, const double* fwts, int nq,
+                double* Fu, double* J) {
+    hemo_facet_coef co = {coef8[0], coef8[1], coef8[2], coef8[3], coef8[4], coef8[5], coef8[6], coef8[7]};
+    if (dim == 2) run_curlcurl_facets<2>(m, n, pairs, cells, x, h, sol, un, &co, fpts, fwts, nq, Fu, J);
+    else run_curlcurl_facets<3>(m, n, pairs, cells, x, h, sol, un, &co, fpts, fwts, nq, Fu, J);
+}
+
+}  // extern "C"

@@ -48,3 +48,46 @@ def test_curlcurl_routine_matches_oracle(lib, d):  # noqa: F811
     assert np.abs(Fe - F_ref).max() < 1e-12 * np.abs(F_ref).max()
     J_ref = C.element_J(x, cells, h, U, P, Un, rules[2], rules[4], **kw)
     assert np.abs(Je - J_ref).max() < 1e-11 * np.abs(J_ref).max()
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_curlcurl_facet_routine_matches_oracle(lib, d):  # noqa: F811
+    """curlcurl_facet<D>: weak pressure + curl-form Nitsche terms (stabilized_schur_pressurebc.py:189-201) on
+    every exterior facet of a small mesh; the Jacobian is checked against unit-vector differences of the
+    (affine) oracle residual."""
+    from types import SimpleNamespace
+    from tests.test_tet_host import _coef8, _perturbed_cube
+    from tests import common as T
+    if d == 2:
+        prob = T.make_problem(T.perturbed_square(3, 3, seed=5))
+        x, cells = prob.x, prob.cells
+        g3 = Q.interval_gauss(3)
+        frule = (np.asarray(g3[0]).reshape(-1, 1), g3[1])
+    else:
+        x, cells = _perturbed_cube(2, seed=5)
+        frule = S.triangle_facet_rule(4)
+    n, nv = x.shape[0], d + 1
+    h = S.cell_diameter(x, cells)
+    pairs = S.exterior_facets(cells)
+    m = len(pairs)
+    rng = np.random.default_rng(19)
+    u, p, un = rng.standard_normal((n, d)), rng.standard_normal(n), rng.standard_normal((n, d))
+    coef = dict(pconst=3.7, a_n=1.0, beta_n=100.0)
+    lib.sxh_set_params(0.02, 1.06, 0.035, _p(np.zeros(3)), O.EPS0, 0.5, 1.0)
+    Fu, J = np.zeros((m, nv, d)), np.zeros((m, nv, nv, d, d))
+    sol = np.concatenate([u.reshape(-1), p])
+    c = lambda a, dt=np.float64: np.ascontiguousarray(a, dtype=dt)
+    lib.cch_facets(d, m, n, _p(c(pairs, np.int32)), _p(c(cells, np.int32)), _p(c(x)), _p(c(h)), _p(sol), _p(c(un.reshape(-1))),
+                   _p(_coef8(coef)), _p(c(frule[0])), _p(c(frule[1])), len(frule[1]), _p(Fu), _p(J))
+    ns = SimpleNamespace(**coef)
+    ce = pairs[:, 0]
+    U, P, Un = u[cells][ce], p[cells][ce], un[cells][ce]
+    ref = C.facet_F(x, cells, h, pairs, ns, U, P, Un, frule, 0.035)
+    assert np.abs(Fu - ref).max() < 1e-12 * np.abs(ref).max()
+    F0 = C.facet_F(x, cells, h, pairs, ns, np.zeros_like(U), P, Un, frule, 0.035)
+    for b in range(nv):
+        for l in range(d):
+            E1 = np.zeros_like(U)
+            E1[:, b, l] = 1.0
+            dF = C.facet_F(x, cells, h, pairs, ns, E1, P, Un, frule, 0.035) - F0       # (m, a, k)
+            assert np.abs(J[:, :, b, :, l] - dF).max() < 1e-12 * max(np.abs(dF).max(), 1.0)

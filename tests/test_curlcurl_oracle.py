@@ -77,3 +77,23 @@ def test_constant_and_hydrostatic_known_answers(d):
     assert np.abs(Fp).max() < 1e-14                                           # R = 0, div u = 0
     # F_u[a] = -int p grad(phi_a) - rho f int phi_a ; summed over a: -rho f |K| (grad of the partition of unity is 0)
     assert np.abs(Fu[0].sum(axis=0) + PAR["rho"] * fvec * vol).max() < 1e-14
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_curlcurl_facet_terms_match_form_text(d):
+    """Weak pressure + Nitsche terms of stabilized_schur_pressurebc.setup (:189-201) on every local facet."""
+    from types import SimpleNamespace
+    X, _ = _cell(d)
+    cells = np.arange(d + 1, dtype=np.int32)[None, :]
+    h = S.cell_diameter(X, cells)
+    rng = np.random.default_rng(11 + d)
+    U, P, Un = rng.standard_normal((d + 1, d)), rng.standard_normal(d + 1), rng.standard_normal((d + 1, d))
+    cf = CurlCurlForms(X, Un, float(h[0]), f=(0.0,) * d, **PAR)
+    frule = (np.asarray(Q.interval_gauss(3)[0]).reshape(-1, 1), Q.interval_gauss(3)[1]) if d == 2 else S.triangle_facet_rule(4)
+    coef = SimpleNamespace(pconst=3.7, a_n=1.0, beta_n=100.0)
+    for lf in range(d + 1):
+        pairs = np.array([[0, lf]], dtype=np.int32)
+        nrm, scale = S.facet_geometry(X, cells, pairs)
+        got = C.facet_F(X, cells, h, pairs, coef, U[None], P[None], Un[None], frule, PAR["mu"])[0]
+        ref = cf.facet_residual(U, P, lf, nrm[0], float(scale[0]), frule, pconst=3.7, a_n=1.0, beta_n=100.0)
+        assert np.abs(got - ref).max() < 1e-12 * np.abs(ref).max()
