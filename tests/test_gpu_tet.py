@@ -141,21 +141,4 @@ def test_tet_csr_assembly_matches_oracle():
     np.add.at(b_ref, l2g[:, :12].reshape(-1), Fu.reshape(-1))
     np.add.at(b_ref, l2g[:, 12:].reshape(-1), Fp.reshape(-1))
     assert np.linalg.norm(bvec.cpu().numpy() - b_ref) < 1e-12 * np.linalg.norm(b_ref)
-    # operators of the Schur-complement approximation: P1 stiffness and lumped mass on tetrahedra
-    lap, mass = hemo.assemble_laplace_mass()
-    torch.cuda.synchronize()
-    det, dphi = S.simplex_geometry(x, cells)
-    Ke = (det / 6.0)[:, None, None] * np.einsum("eai,ebi->eab", dphi, dphi)
-    L_ref = sp.coo_matrix((Ke.reshape(-1), (np.repeat(c64, 4, axis=1).reshape(-1), np.tile(c64, (1, 4)).reshape(-1))),
-                          shape=(n, n)).tocsr()
-    L_ref.sort_indices()
-    assert np.array_equal(L_ref.indices, ncol) and np.array_equal(L_ref.indptr, nrowptr)
-    assert np.linalg.norm(lap.cpu().numpy() - L_ref.data) < 1e-12 * np.linalg.norm(L_ref.data)
-    m_ref = np.zeros(n)
-    np.add.at(m_ref, cells.reshape(-1), np.repeat(det / 24.0, 4))
-    assert np.linalg.norm(mass.cpu().numpy() - m_ref) < 1e-13 * np.linalg.norm(m_ref)
-    # what is not there in 3-D fails loudly: the drag / lift integrals are the 2-D DFG forms
-    from cfd_hemodynamic_b200._lib import HemoError
-    with pytest.raises(HemoError):
-        hemo.boundary_force(0, T(sol))
     hemo.close()

@@ -266,3 +266,40 @@ def test_golden_tet_case_on_gpu():
     assert np.linalg.norm((A_gpu - A_gold).tocoo().data) < 1e-12 * np.linalg.norm(gold["data"])
     assert np.linalg.norm(b.cpu().numpy() - gold["b"]) < 1e-12 * np.linalg.norm(gold["b"])
     hemo.close()
+
+
+def test_tet_schur_operators_and_loud_failures():
+    """P1 stiffness and lumped mass on tetrahedra (operators of the Schur-complement approximation) against
+    numpy; the L2 norm kernel; entry points that do not exist in 3-D fail loudly."""
+    from cfd_hemodynamic_b200._lib import Hemo, HemoError
+    x, cells = _perturbed_cube(3, seed=2)
+    n = x.shape[0]
+    h = S.cell_diameter(x, cells)
+    rules = {k: S.tet_gauss_jacobi(d) for k, d in dict(Fu=4, Fp=3, uu=4, up=3, pu=3, pp=2).items()}
+    hemo = Hemo(0)
+    T, keep = _setup(hemo, x, cells, h, rules, S.triangle_facet_rule(2), dict(dt=0.01, rho=1.3, mu=0.02), np.zeros(3))
+    nrowptr, ncol = D.node_graph(cells, n)
+    lap, mass = hemo.assemble_laplace_mass()
+    torch.cuda.synchronize()
+    det, dphi = S.simplex_geometry(x, cells)
+    Ke = (det / 6.0)[:, None, None] * np.einsum("eai,ebi->eab", dphi, dphi)
+    c64 = cells.astype(np.int64)
+    L_ref = sp.coo_matrix((Ke.reshape(-1), (np.repeat(c64, 4, axis=1).reshape(-1), np.tile(c64, (1, 4)).reshape(-1))),
+                          shape=(n, n)).tocsr()
+    L_ref.sort_indices()
+    assert np.array_equal(L_ref.indices, ncol) and np.array_equal(L_ref.indptr, nrowptr)
+    assert np.linalg.norm(lap.cpu().numpy() - L_ref.data) < 1e-12 * np.linalg.norm(L_ref.data)
+    m_ref = np.zeros(n)
+    np.add.at(m_ref, cells.reshape(-1), np.repeat(det / 24.0, 4))
+    assert np.linalg.norm(mass.cpu().numpy() - m_ref) < 1e-13 * np.linalg.norm(m_ref)
+    # L2 norm of a P1 vector field: int |(x + 2y, z, 1)|^2 over the unit cube (exact for the consistent mass matrix)
+    u = np.stack([x[:, 0] + 2 * x[:, 1], x[:, 2], np.ones(n)], axis=1).reshape(-1)
+    exact = (1 / 3 + 4 / 3 + 1.0) + 1 / 3 + 1.0
+    assert abs(hemo.l2_norm_sq(T(u), 3) - exact) < 1e-12
+    assert abs(hemo.l2_norm_sq(T(np.full(n, 2.0)), 1) - 4.0) < 1e-12
+    # the drag / lift integrals are the 2-D DFG forms; the assembled Schur operator is triangles-only
+    with pytest.raises(HemoError):
+        hemo.boundary_force(0, T(np.zeros(4 * n)))
+    with pytest.raises(HemoError):
+        hemo.l2_norm_sq(T(u), 2)
+    hemo.close()
