@@ -77,7 +77,9 @@ struct SimplexCell {
 template <int D>
 HEMO_HD void simplex_geometry(SimplexCell<D>& c, const double X[D + 1][D]) {
     double J[D][D], K[D][D];
+    #pragma unroll
     for (int i = 0; i < D; ++i)
+        #pragma unroll
         for (int j = 0; j < D; ++j) J[i][j] = X[j + 1][i] - X[0][i];
     double det;
     if constexpr (D == 2) {
@@ -87,18 +89,24 @@ HEMO_HD void simplex_geometry(SimplexCell<D>& c, const double X[D + 1][D]) {
     } else {
         // cofactors (indices modulo 3)
         double C[3][3];
+        #pragma unroll
         for (int i = 0; i < 3; ++i)
+            #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
                 C[i][j] = J[i1][j1] * J[i2][j2] - J[i1][j2] * J[i2][j1];
             }
         det = J[0][0] * C[0][0] + J[0][1] * C[0][1] + J[0][2] * C[0][2];
+        #pragma unroll
         for (int i = 0; i < 3; ++i)
+            #pragma unroll
             for (int j = 0; j < 3; ++j) K[i][j] = C[j][i] / det;       // inverse = adj / det
     }
     // grad phi_a = K^T ghat_a, ghat_0 = -(1,..,1), ghat_{j+1} = e_j
+    #pragma unroll
     for (int i = 0; i < D; ++i) {
         double s0 = 0.0;
+        #pragma unroll
         for (int j = 0; j < D; ++j) { c.g[j + 1][i] = K[j][i]; s0 += K[j][i]; }
         c.g[0][i] = -s0;
     }
@@ -109,28 +117,40 @@ template <int D>
 HEMO_HD void simplex_derive(SimplexCell<D>& c, const HemoForm& par) {
     constexpr int NV = D + 1;
     const double th = par.theta;
+    #pragma unroll
     for (int a = 0; a < NV; ++a)
+        #pragma unroll
         for (int k = 0; k < D; ++k) c.M[a][k] = th * c.U[a][k] + (1.0 - th) * c.N[a][k];
+    #pragma unroll
     for (int i = 0; i < D; ++i) {
+        #pragma unroll
         for (int j = 0; j < D; ++j) {
             double v = 0.0;
+            #pragma unroll
             for (int a = 0; a < NV; ++a) v += c.g[a][i] * c.M[a][j];
             c.G[i][j] = v;
         }
         double v = 0.0;
+        #pragma unroll
         for (int a = 0; a < NV; ++a) v += c.g[a][i] * c.P[a];
         c.gp[i] = v;
     }
     c.divu = 0.0;
+    #pragma unroll
     for (int i = 0; i < D; ++i) c.divu += c.G[i][i];
+    #pragma unroll
     for (int cc = 0; cc < NV; ++cc) {
+        #pragma unroll
         for (int a = 0; a < NV; ++a) {
             double v = 0.0;
+            #pragma unroll
             for (int i = 0; i < D; ++i) v += c.M[cc][i] * c.g[a][i];
             c.s[cc][a] = v;
         }
+        #pragma unroll
         for (int k = 0; k < D; ++k) {
             double conv = 0.0;
+            #pragma unroll
             for (int i = 0; i < D; ++i) conv += c.M[cc][i] * c.G[i][k];
             c.A[cc][k] = (par.a0 * c.U[cc][k] - c.H[cc][k]) * par.inv_dt + conv - c.fbody[k];
             c.R[cc][k] = par.rho * c.A[cc][k] + c.gp[k];
@@ -149,13 +169,17 @@ HEMO_HD void simplex_moments(const SimplexCell<D>& c, const HemoForm& par, const
     const double c23 = t2inv * t2inv + t3inv * t3inv;
     const double eps2 = par.eps0 * par.eps0;
     const double re_fac = h / (2.0 * par.nu);
+    #pragma unroll
     for (int a = 0; a < NV; ++a)
+        #pragma unroll
         for (int b = 0; b < NV; ++b) T2[a][b] = 0.0;
     L0 = 0.0;
     for (int q = 0; q < r.nq; ++q) {
         double v2 = 0.0;
+        #pragma unroll
         for (int k = 0; k < D; ++k) {
             double u = 0.0;
+            #pragma unroll
             for (int a = 0; a < NV; ++a) u += r.phi[q][a] * c.N[a][k];
             v2 += u * u;
         }
@@ -165,11 +189,15 @@ HEMO_HD void simplex_moments(const SimplexCell<D>& c, const HemoForm& par, const
         const double Re = v * re_fac;
         const double z = (Re <= 3.0) ? Re / 3.0 : 1.0;
         const double wt = r.w[q] * tau;
+        #pragma unroll
         for (int a = 0; a < NV; ++a)
+            #pragma unroll
             for (int b = a; b < NV; ++b) T2[a][b] += wt * r.phi[q][a] * r.phi[q][b];
         L0 += r.w[q] * (0.5 * v * h * z);
     }
+    #pragma unroll
     for (int a = 0; a < NV; ++a)
+        #pragma unroll
         for (int b = a; b < NV; ++b) { T2[a][b] *= c.detJ; T2[b][a] = T2[a][b]; }
     L0 *= c.detJ;
 }
@@ -183,34 +211,46 @@ HEMO_HD void simplex_residual(const SimplexCell<D>& c, const HemoForm& par, cons
     double T2[NV][NV], L0, T2p[NV][NV], L0p, T1p[NV];
     simplex_moments<D>(c, par, ru, T2, L0);
     simplex_moments<D>(c, par, rp, T2p, L0p);
+    #pragma unroll
     for (int d = 0; d < NV; ++d) {
         T1p[d] = 0.0;
+        #pragma unroll
         for (int cc = 0; cc < NV; ++cc) T1p[d] += T2p[cc][d];
     }
     const double m0 = ru.m0 * c.detJ;
     double pbar = 0.0;
+    #pragma unroll
     for (int b = 0; b < NV; ++b) pbar += ru.m1[b] * c.P[b];
     pbar *= c.detJ;
+    #pragma unroll
     for (int a = 0; a < NV; ++a) {
         double Wd[NV];
+        #pragma unroll
         for (int d = 0; d < NV; ++d) {
             double v = 0.0;
+            #pragma unroll
             for (int cc = 0; cc < NV; ++cc) v += T2[cc][d] * c.s[cc][a];
             Wd[d] = v;
         }
+        #pragma unroll
         for (int k = 0; k < D; ++k) {
             double v = 0.0;
+            #pragma unroll
             for (int cc = 0; cc < NV; ++cc) v += rho * c.detJ * ru.m2[a][cc] * c.A[cc][k];
             double sg = 0.0;                                  // g_a . (2 mu eps)_{.k}
+            #pragma unroll
             for (int i = 0; i < D; ++i) sg += c.g[a][i] * mu * (c.G[i][k] + c.G[k][i]);
             v += m0 * sg - c.g[a][k] * pbar;
+            #pragma unroll
             for (int d = 0; d < NV; ++d) v += Wd[d] * c.R[d][k];
             v += L0 * rho * c.divu * c.g[a][k];
             Fu[a][k] = v;
         }
         double acc = 0.0;
+        #pragma unroll
         for (int d = 0; d < NV; ++d) {
             double rg = 0.0;
+            #pragma unroll
             for (int i = 0; i < D; ++i) rg += c.R[d][i] * c.g[a][i];
             acc += T1p[d] * rg;
         }
@@ -230,37 +270,51 @@ HEMO_HD void simplex_jacobian_from_moments(const SimplexCell<D>& c, const HemoFo
     const double rho = par.rho, mu = par.mu, idt = par.a0_dt, th = par.theta;
     const double m0 = m0uu * c.detJ;
     double RT[NV][D], Y[NV], V[NV];
+    #pragma unroll
     for (int b = 0; b < NV; ++b) {
+        #pragma unroll
         for (int k = 0; k < D; ++k) {
             double v = 0.0;
+            #pragma unroll
             for (int d = 0; d < NV; ++d) v += T2[d][b] * c.R[d][k];
             RT[b][k] = v;
         }
         double y = 0.0, vv = 0.0;
+        #pragma unroll
         for (int d = 0; d < NV; ++d) { y += T1pu[d] * c.s[d][b]; vv += T1up[d] * c.s[d][b]; }
         Y[b] = y; V[b] = vv;
     }
+    #pragma unroll
     for (int a = 0; a < NV; ++a) {
         double TS[NV], Gga[D];
+        #pragma unroll
         for (int cc = 0; cc < NV; ++cc) {
             double v = 0.0;
+            #pragma unroll
             for (int d = 0; d < NV; ++d) v += T2[cc][d] * c.s[d][a];
             TS[cc] = v;
         }
+        #pragma unroll
         for (int l = 0; l < D; ++l) {
             double v = 0.0;
+            #pragma unroll
             for (int k = 0; k < D; ++k) v += c.G[l][k] * c.g[a][k];
             Gga[l] = v;
         }
+        #pragma unroll
         for (int b = 0; b < NV; ++b) {
             const double m2ab = c.detJ * m2uu[a][b];
             double gab = 0.0, Zab = 0.0, Qab = 0.0;
+            #pragma unroll
             for (int i = 0; i < D; ++i) gab += c.g[a][i] * c.g[b][i];
             const double Wab = TS[b];
+            #pragma unroll
             for (int d = 0; d < NV; ++d) { Zab += TS[d] * c.s[d][b]; Qab += c.detJ * m2uu[a][d] * c.s[d][b]; }
             const double diag = rho * m2ab * idt + th * rho * Qab + th * mu * m0 * gab + rho * Wab * idt + th * rho * Zab;
             const double cG = th * rho * (m2ab + Wab);
+            #pragma unroll
             for (int k = 0; k < D; ++k)
+                #pragma unroll
                 for (int l = 0; l < D; ++l) {
                     double v = cG * c.G[l][k] + th * mu * m0 * c.g[a][l] * c.g[b][k] + th * c.g[a][l] * RT[b][k] +
                                th * L0 * rho * c.g[a][k] * c.g[b][l];
@@ -268,6 +322,7 @@ HEMO_HD void simplex_jacobian_from_moments(const SimplexCell<D>& c, const HemoFo
                     emit(a, b, k, l, v);
                 }
             const double m1b_up = c.detJ * m1up[b], m1a_pu = c.detJ * m1pu[a];
+            #pragma unroll
             for (int k = 0; k < D; ++k) {
                 emit(a, b, k, D, -m1b_up * c.g[a][k] + c.g[b][k] * V[a]);                                        // J_up
                 emit(a, b, D, k, th * m1a_pu * c.g[b][k] + c.g[a][k] * (T1pu[b] * idt + th * Y[b]) + th * T1pu[b] * Gga[k]);   // J_pu
@@ -281,8 +336,10 @@ HEMO_HD void simplex_jacobian_from_moments(const SimplexCell<D>& c, const HemoFo
 template <int D>
 HEMO_HD void simplex_colsum(const double T[D + 1][D + 1], double T1[D + 1], double& T0) {
     T0 = 0.0;
+    #pragma unroll
     for (int d = 0; d < D + 1; ++d) {
         T1[d] = 0.0;
+        #pragma unroll
         for (int cc = 0; cc < D + 1; ++cc) T1[d] += T[cc][d];
         T0 += T1[d];
     }
