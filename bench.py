@@ -3,19 +3,26 @@
 DOF-timesteps/s; assembly cells/s and nnz/s are reported beside it).
 
   python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
-  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the reference's solver configuration
+                                                           # restated in C + OpenMP on all host cores
                                                            # (DOLFINx/PETSc cannot be installed)
 
-A "step" is one time step (`Solver.solveStep`) of the workload: Newton with
-Jacobian + residual assemblies and a preconditioned FGMRES solve per
-iteration.  `value` is measured with everything resident in HBM
-(`Solver.step_device`), `e2e` through the reference-facing plugin API with host
-buffers (`Solver.solveStep` + the host-side u_prev <- u_sol shift the
-reference's time loop performs, src/scenario.py:306-307).
+A "step" is one time step (`Solver.solveStep`) of the workload: Newton with Jacobian + residual assemblies and a
+preconditioned FGMRES solve per iteration.  `value` is measured with everything resident in HBM
+(`Solver.step_device`), `e2e` through the reference-facing plugin API with host buffers (`Solver.solveStep` + the
+host-side u_prev <- u_sol shift the reference's time loop performs, src/scenario.py:306-307).
+
+Both arms run the SAME mesh, parameters and time steps (W warm-up steps, then K timed ones): the default workload
+is BASELINE config 2 (lid_driven2D, `--solver stabilized_schur`) at the largest size at which the reference's own
+algorithm — FGMRES(200) + fieldsplit Schur FULL/SELFP + GMRES(30)/ASM-ILU(0) sub-solves,
+src/solvers/stabilized_schur.py:226-275 — finishes W + K steps on the GPU box's host cores within the driver's time
+limit (it needs minutes per step at 1 M cells).  The larger configurations (1 M-cell lid cavity, the 16 M-cell
+stenosis mesh of the north star) are measured in the same run on the GPU arm and reported under `other_workloads`.
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import math
 import os
@@ -30,7 +37,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # BASELINE.json configs[1]: lid_driven2D on a refined structured mesh (~1M cells)
+    # BASELINE.json configs[1]: lid_driven2D on a refined structured mesh; nx = 707 is the ~1 M-cell size,
+    # nx = 384 the largest one the CPU arm finishes in the driver's time limit (see module docstring)
+    "lid_driven2D_nx384": dict(scenario="lid_driven2D", nx=384, mu=0.01, rho=1.0, dt=0.01),
     "lid_driven2D_nx707": dict(scenario="lid_driven2D", nx=707, mu=0.01, rho=1.0, dt=0.01),
     "lid_driven2D_nx1414": dict(scenario="lid_driven2D", nx=1414, mu=0.01, rho=1.0, dt=0.01),
     "lid_driven2D_nx2828": dict(scenario="lid_driven2D", nx=2828, mu=0.01, rho=1.0, dt=0.01),
@@ -39,6 +48,8 @@ WORKLOADS = {
     "stenosis_backflow_1m": dict(scenario="stenosis_mesh_variable", res=0.03, dt=1e-3, v_max=100.0),
     "stenosis_backflow_4m": dict(scenario="stenosis_mesh_variable", res=0.015, dt=1e-3, v_max=100.0),
     "stenosis_pressure_4m": dict(scenario="stenosis_pressure", res=0.015, dt=1e-3, p_inlet=80.0, R_resistance=10.0),
+    "stenosis_pressure_structured_1m": dict(scenario="stenosis_pressure_structured", res=0.03, dt=1e-3,
+                                            p_inlet=80.0, R_resistance=10.0),
     "stenosis_pressure_structured_16m": dict(scenario="stenosis_pressure_structured", res=0.0075, dt=1e-3,
                                              p_inlet=80.0, R_resistance=10.0),
     # the same transfinite grid with the reference's recombined Q1 cells
@@ -49,7 +60,10 @@ WORKLOADS = {
     "stenosis_pressure_structured_q1_8m": dict(scenario="stenosis_pressure_structured", res=0.0075, dt=1e-3,
                                                p_inlet=80.0, R_resistance=10.0, cell_type="quadrilateral"),
 }
-CPU_SAMPLE_NX = 128  # bounded CPU sample of the same workload (same physics, coarser mesh)
+DEFAULT_WORKLOAD = "lid_driven2D_nx384"
+# measured on the GPU arm in the same run (N = 1, default workload only): (name, warm-up, steps)
+EXTRA_WORKLOADS = [("lid_driven2D_nx707", 3, 10), ("stenosis_pressure_structured_16m", 2, 4)]
+CPU_BUDGET_S = 1500.0        # the CPU arm stops taking new steps beyond this (driver limit: 1800 s per arm)
 
 PROF_CLASSES = {0: "spmv_node(J)", 1: "cell_jacobian", 2: "gather_matrix", 3: "cell_residual",
                 4: "cheb_step<2>(A00,l0)", 5: "cheb_step<1>(Lp,l0)", 6: "mdot", 7: "maxpy_norm",
@@ -125,77 +139,281 @@ def build_scenario(w, **solver_kw):
                                                 cell_type=w.get("cell_type", "triangle"), **solver_kw)
 
 
-def oracle_steps(w, nx, steps):
-    """The CPU port (oracle/ns_oracle.py): same scenario, Newton + sparse LU, `steps`
-    time steps at mesh size nx.  Returns (ndof, seconds)."""
-    from cfd_hemodynamic_b200.fem import mesh as M
-    from oracle import ns_oracle as O
-    from tests import common as T
-    mesh = M.create_unit_square(None, nx, nx)
-    prob = T.make_problem(mesh, dt=w["dt"], rho=w["rho"], mu=w["mu"], f=(0.0, 0.0))
-    x = prob.x
-    n = prob.n
-    ext = M.exterior_facet_indices(mesh.topology)
-    prob.facet_sets = [O.FacetSet(pairs=mesh.topology.facet_cell_pairs(ext), a_p=1.0, a_g=1.0)]
-    walls = np.nonzero(np.isclose(x[:, 0], 0) | np.isclose(x[:, 0], 1) | np.isclose(x[:, 1], 0))[0]
-    lidf = M.locate_entities_boundary(mesh, 1, lambda X: np.isclose(X[1], 1.0) & (X[0] > 1e-10) & (X[0] < 1 - 1e-10))
-    lid = np.unique(mesh.topology.facet_vertices[lidf])
-    g1 = np.zeros(2 * n)
-    g1[0::2] = 1.0
-    prob.bcs = T.oracle_bcs(prob, [("u", walls, np.zeros(2 * n)), ("u", lid, g1)])
-    from oracle.c_oracle import FastAssembler
-    asm = FastAssembler(prob)            # C cell kernels, OpenMP over all host cores
-    xk = np.zeros(3 * n)
-    un = np.zeros(2 * n)
+def workload_config(name, sc):
+    """The part of the JSON line both arms must agree on: what was solved."""
+    s = sc.solver
+    cells = s._cells_host
+    n = s.n
+    nv = int(cells.shape[1])
+    return {"workload": name, "solver": sc.solver_name, "cell_type": s.mesh.topology.cell_name(),
+            "cells": int(cells.shape[0]), "dofs": int(3 * n), "dt": float(s.dt.value), "mu": float(s.mu.value),
+            "rho": float(s.rho.value),
+            "tolerances": {"snes_rtol": s.snes_rtol, "snes_stol": s.snes_stol, "ksp_rtol": s.ksp_rtol},
+            "l2": "inputs larger than L2: Jacobian values + element buffer %.0f MB vs 126 MB L2"
+                  % ((8 * 9 * 7.0 * n + 72 * nv * nv * cells.shape[0]) / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm
+# ------------------------------------------------------------------------------------------------------
+def cpu_steps(name, n_warm, n_steps, budget_s, nranks=None):
+    """The reference's solver configuration restated on host cores (oracle/cpu_reference.CReferenceSolver:
+    C + OpenMP, one thread per `mpirun` rank) marching the same scenario.  Returns a dict."""
+    from oracle.workload import CpuMarcher
+    w = WORKLOADS[name]
+    with contextlib.redirect_stdout(sys.stderr):
+        sc = build_scenario(w, host_only=True)
+    cores = int(nranks or os.cpu_count() or 1)
+    t_setup = time.perf_counter()
+    m = CpuMarcher(sc, solver="reference", nranks=cores)
+    t_setup = time.perf_counter() - t_setup
+    t_begin = time.perf_counter()
+    for _ in range(n_warm):
+        m.step()
+    done = 0
     t0 = time.perf_counter()
-    for _ in range(steps):
-        xk = O.remove_nullspace(prob, xk)
-        xk, its, reason = O.newton_solve(prob, xk, un, asm=asm)
-        un = xk[:2 * n].copy()
-    return 3 * n, time.perf_counter() - t0
+    for _ in range(n_steps):
+        m.step()
+        done += 1
+        if time.perf_counter() - t_begin > budget_s:
+            break
+    secs = time.perf_counter() - t0
+    st = m.ref.stats()
+    return dict(config=workload_config(name, sc), ndof=3 * m.n, steps=done, seconds=secs, cores=cores,
+                newton_its=m.ref.newton_its, outer_its=st["outer_its"], inner_its=st["inner_its"],
+                timers=dict(m.ref.timers), setup_s=t_setup, total_steps=n_warm + done)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w = WORKLOADS[args.workload]
-    if w["scenario"] != "lid_driven2D":
-        w = WORKLOADS["lid_driven2D_nx707"]      # the CPU arm is only wired for the default workload
-    cores = os.cpu_count() or 1
-    for _ in range(min(args.warmup, 1)):
-        oracle_steps(w, 16, 1)
-    steps = max(1, args.steps)
-    # bounded sample: the mesh is sized so that K steps finish within a few minutes
-    # (sparse-LU Newton: ~30 s per step at nx=128, ~4 s at 64, ~1.5 s at 40, < 1 s at 32)
-    sample_nx = 128 if steps <= 4 else 64 if steps <= 20 else 40 if steps <= 80 else 32
-    ndof, secs = oracle_steps(w, sample_nx, steps)
-    val = ndof * steps / secs
+    name = args.workload
+    if WORKLOADS[name]["scenario"] != "lid_driven2D":
+        raise SystemExit("bench.py --impl reference: the CPU arm (asm/ilu(0) sub-solves, stabilized_schur.py:256-267) is "
+                         "wired for the lid_driven2D workloads; the hemodynamic variants ask for `lu` sub-solves "
+                         "(stabilized_schur_pressure_backflow.py:284-288)")
+    W = max(0, args.warmup)
+    K = max(1, args.steps)
+    r = cpu_steps(name, W, K, CPU_BUDGET_S)
+    val = r["ndof"] * r["steps"] / r["seconds"]
+    sample = (f"{r['steps']} timed time step(s) after {W} warm-up step(s) of {name} ({r['ndof']} DOFs), the same mesh and "
+              f"steps as the GPU arm; FGMRES(200) + fieldsplit Schur FULL/SELFP + GMRES(30)/ASM-ILU(0) "
+              f"(stabilized_schur.py:226-275) restated in C + OpenMP, {r['cores']} threads = {r['cores']} ASM blocks; "
+              f"{r['newton_its']} Newton, {r['outer_its']} outer and {r['inner_its']} inner Krylov iterations in "
+              f"{r['total_steps']} steps; assembly {r['timers']['assembly']:.1f} s, PCSetUp {r['timers']['pc_setup']:.1f} s, "
+              f"KSPSolve {r['timers']['ksp']:.1f} s")
     line = {
         "impl": "reference", "metric": "DOF-timesteps/s", "value": val, "unit": "DOF-timesteps/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / steps,
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": W, "ms_per_step": 1e3 * r["seconds"] / r["steps"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "solver": "stabilized_schur",
-                   "note": "DOLFINx/PETSc are not installable in this image; CPU arm = oracle port "
-                           "(C/OpenMP element kernels + SciPy SuperLU Newton) on a bounded sample of the workload"},
-        "cpu_baseline": {"value": val, "unit": "DOF-timesteps/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} time step(s) of {w['scenario']} at nx={sample_nx} "
-                                   f"({ndof} DOFs); assembly on all cores (OpenMP), sparse LU single-threaded"},
+        "config": r["config"],
+        "note": "DOLFINx/PETSc are not installable in this image (no wheels, no MPI): the CPU arm is the reference's "
+                "solver configuration restated in C + OpenMP on all host cores (oracle/c/ref_ksp.c, "
+                "oracle/c/p1tri_cells.c), parity unpinned against PETSc itself",
+        "cpu_baseline": {"value": val, "unit": "DOF-timesteps/s", "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "DOF-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def run_distributed(args, w, W, K, world, rank, local_rank):
-    """N > 1: ONE mesh partitioned over the GPUs (vertex-owned x-slabs + overlap, halo exchange
-    and Krylov allreduces over NCCL).  Weak scaling: the per-GPU cell count is held at the
-    single-GPU workload's, so the global mesh is nx*sqrt(N) squared."""
-    import contextlib
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def hierarchy_bytes(s):
+    """Algorithmic bytes of one preconditioner application from the level sizes (fp32 hierarchy storage):
+    per level and cycle, the operator is read by 1 (pre, from zero) + 1 (residual) + 2 (post) sweeps and the
+    transfer operators once each."""
+    lin = s.linear
+    out = 0.0
+    n0 = s.n
+    for which, bs in ((0, 2), (1, 1)):
+        lv = lin.levels[which] if which < len(lin.levels) else []
+        if not lv:
+            continue
+        nn = n0
+        nnz = s.hemo.nnz_node if not (which == 1 and lin.schur_mode == "selfp") else lv[0]["AP"].shape[0] * 19
+        cyc = lin.opts["amg_cycles_u"] if which == 0 else lin.opts["amg_cycles_p"]
+        for d in lv:
+            op = nnz * (4 * bs * bs + 4) + nn * (4 + 4 * bs * 7)
+            tr = 2 * d["P"].nnz * (8 + 4) + 2 * nn * 4 * bs
+            out += cyc * (3 * op + tr)
+            nnz = d["C"].nnz
+            nn = d["P"].shape[1]
+    return out
+
+
+def measure_workload(name, W, K, local_rank, want_e2e=True, want_prof=True, solver_kw=None):
+    import torch
+    w = WORKLOADS[name]
+    t_build = time.perf_counter()
+    with contextlib.redirect_stdout(sys.stderr):       # stdout carries exactly one JSON line
+        sc = build_scenario(w, device=local_rank, **(solver_kw or {}))
+    t_build = time.perf_counter() - t_build
+    s = sc.solver
+    hemo = s.hemo
+    ndof = s.N
+    E = s._cells_host.shape[0]
+    nnz = hemo.nnz
+    dev = hemo.device
+    n = s.n
+    nnz_node = hemo.nnz_node
+    nv = int(s._cells_host.shape[1])
+
+    # ---- device-resident timed region --------------------------------------
+    for _ in range(W):
+        s.step_device()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = hemo.launches
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    newton = ksp = 0
+    e0.record()
+    for _ in range(K):
+        s.step_device()
+        newton += s.its_snes
+        ksp += s.its_ksp
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    launches = hemo.launches - launches0
+    clocks = sampler.stop()
+    out = dict(config=workload_config(name, sc), value=ndof * K / (ms * 1e-3), ms_per_step=ms / K, steps=K, warmup=W,
+               newton_its_per_step=newton / K, fgmres_its_per_step=ksp / K, gpu_launches=launches, clocks=clocks,
+               nnz=nnz, build_s=t_build)
+
+    # ---- per-kernel-class CUDA-event times: the timed region above replays whole FGMRES iterations as CUDA graphs,
+    # whose kernels carry no event pairs; two extra steps with direct launches (same kernels, same data) time the
+    # classes with the library's event pairs and their shares are scaled to the timed region -------------------
+    prof = None
+    if want_prof:
+        hemo.use_graph(False)
+        s.step_device()
+        hemo.prof_enable(True)
+        g0 = torch.cuda.Event(enable_timing=True)
+        g1 = torch.cuda.Event(enable_timing=True)
+        g0.record()
+        kp = 0
+        for _ in range(2):
+            s.step_device()
+            kp += s.its_ksp
+        g1.record()
+        torch.cuda.synchronize(dev)
+        ms_nograph = g0.elapsed_time(g1)
+        prof = {c: hemo.prof_get(c) for c in PROF_CLASSES}
+        hemo.prof_enable(False)
+        hemo.use_graph(True)
+        s.step_device()          # re-captures the graphs
+        out["ms_per_step_direct_launches"] = ms_nograph / 2
+
+    # ---- isolated assembly timings (cells/s, nnz/s) ------------------------------
+    def time_fn(fn, reps=5):
+        fn()
+        torch.cuda.synchronize(dev)
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps
+
+    jac_ms = time_fn(lambda: hemo.assemble_jacobian(s.d_x, s.d_un, s.d_vals))
+    res_ms = time_fn(lambda: hemo.assemble_residual(s.d_x, s.d_un, s.d_bcval, s.d_g))
+    out["assembly"] = {"jacobian_cells_per_s": E / (jac_ms * 1e-3), "jacobian_nnz_per_s": nnz / (jac_ms * 1e-3),
+                       "residual_cells_per_s": E / (res_ms * 1e-3), "jacobian_ms": jac_ms, "residual_ms": res_ms}
+
+    # ---- end to end through the plugin API (host buffers) ------------------------
+    if want_e2e:
+        for _ in range(2):
+            s.solveStep()
+            s.u_prev.x.array[:] = s.u_sol.x.array[:]
+            s.p_prev.x.array[:] = s.p_sol.x.array[:]
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(K):
+            s.solveStep()
+            s.u_prev.x.array[:] = s.u_sol.x.array[:]
+            s.p_prev.x.array[:] = s.p_sol.x.array[:]
+        torch.cuda.synchronize(dev)
+        out["e2e"] = {"value": ndof * K / (time.perf_counter() - t0), "unit": "DOF-timesteps/s",
+                      "h2d_bytes_per_step": s.h2d_bytes_per_step, "d2h_bytes_per_step": s.d2h_bytes_per_step}
+
+    # ---- roofline ---------------------------------------------------------------------
+    peak, peak_kind = measured_peaks()
+    ae_bytes = 72 * nv * nv * E
+    its_per_solve = max(ksp / max(newton, 1), 1.0)
+    kavg = 0.5 * its_per_solve + 1.0                       # average number of basis vectors per Gram-Schmidt pass
+    alg_bytes = {
+        0: 76 * nnz_node + 52 * n + 24 * n,               # J values + node cols + rowptr + x + y (+ the Z_j copy)
+        1: 4 * nv * E + 8 * E + 56 * n + ae_bytes,        # cells, h, nodal gathers, element matrices out
+        2: ae_bytes + 4 * nv * nv * E + 12 * nnz_node + 72 * nnz_node,
+        3: 4 * nv * E + 8 * E + 56 * n + 24 * nv * E,
+        4: 20 * nnz_node + 4 * n + 56 * n,                # A00 BSR2 fp32 values + cols + rowptr + 7 fp32 vectors of 2n
+        5: 8 * nnz_node + 4 * n + 28 * n,
+        6: 8 * ndof * (kavg + 1),                          # V_0..V_j and w read once
+        7: 8 * ndof * (kavg + 2),                          # V_0..V_j read, w read + written
+        8: None,
+    }
+    if prof is not None:
+        scale = (ms / K) / (ms_nograph / 2) if ms_nograph > 0 else 1.0
+        classes = {}
+        for c, (t, cnt) in prof.items():
+            if cnt == 0:
+                continue
+            avg_us = 1e3 * t / cnt
+            gbps = alg_bytes[c] / (avg_us * 1e-6) / 1e9 if alg_bytes.get(c) else None
+            classes[PROF_CLASSES[c]] = {"avg_us": avg_us, "launches_per_step": cnt / 2, "share_of_step": t / ms_nograph,
+                                        "GBps": gbps, "frac_of_hbm_peak": gbps / peak if gbps else None}
+        hbm = [c for c in (0, 2, 4, 5, 6, 7) if prof[c][1] > 0]
+        dom = max(hbm, key=lambda c: prof[c][0], default=0)
+        dms, dcnt = prof[dom]
+        achieved = alg_bytes[dom] / (dms / dcnt * 1e-3) / 1e9 if dcnt else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("workload") == name:
+                traffic = tj.get("dram_bytes_per_launch", {}).get(PROF_CLASSES[dom])
+        # whole step: algorithmic bytes of everything executed / step time
+        step_bytes = (ksp / K) * (alg_bytes[0] + alg_bytes[6] + alg_bytes[7] + hierarchy_bytes(s) + 16 * ndof) \
+            + (newton / K) * (alg_bytes[1] + alg_bytes[2]) + (newton / K + 1) * alg_bytes[3]
+        out["roofline"] = {
+            "bound": "hbm", "kernel": PROF_CLASSES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind, "launches_timed": dcnt,
+            "avg_us": 1e3 * dms / max(dcnt, 1), "share_of_step": dms / ms_nograph,
+            "how": "CUDA-event pairs around every launch of the class (library side, on the solver's stream) during two "
+                   "extra time steps with direct launches; the timed region itself replays CUDA graphs",
+            "whole_step": {"algorithmic_bytes": step_bytes, "GBps": step_bytes / (ms / K * 1e-3) / 1e9,
+                           "frac": step_bytes / (ms / K * 1e-3) / 1e9 / peak},
+            "fp64_bound": {"kernels": ["cell_jacobian", "cell_residual"],
+                           "cell_jacobian_Gcells_per_s": E / max(prof[1][0] / max(prof[1][1], 1), 1e-9) / 1e6,
+                           "cell_residual_Gcells_per_s": E / max(prof[3][0] / max(prof[3][1], 1), 1e-9) / 1e6},
+            "classes": classes, "graph_vs_direct_scale": scale}
+    out["precision"] = ("outer FGMRES, Jacobian, residuals, reductions: fp64; multigrid hierarchy storage (operators, "
+                        "smoother vectors, A01 copy): fp32 with fp64 accumulation (preconditioner only)")
+    # free the device before the next workload
+    sc.solver.hemo.close()
+    del sc, s
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_distributed(args, name, W, K, world, rank, local_rank):
+    """N > 1: ONE mesh partitioned over the GPUs (vertex-owned x-slabs), halo exchange and Krylov allreduces with
+    NCCL inside the library.  Weak scaling: the per-GPU cell count is held at the single-GPU workload's, so the
+    global mesh is nx*sqrt(N) squared."""
     import torch
     import torch.distributed as dist
     from cfd_hemodynamic_b200.distributed_solver import DistributedStabilizedSchur
     from cfd_hemodynamic_b200.parallel import slab_partition
     from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation
+    w = WORKLOADS[name]
     nx = int(round(w["nx"] * math.sqrt(world)))
     with contextlib.redirect_stdout(sys.stderr):
         sc = LidDriven2DSimulation("stabilized_schur", w["dt"], 1.0, rho=w["rho"], mu=w["mu"], nx=nx, host_only=True)
@@ -216,7 +434,7 @@ def run_distributed(args, w, W, K, world, rank, local_rank):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = ds.hemo.launches + ds.hemo_p.launches
+    l0 = ds.launches()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     newton = ksp = 0
@@ -230,11 +448,11 @@ def run_distributed(args, w, W, K, world, rank, local_rank):
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    launches = torch.tensor([float(ds.hemo.launches + ds.hemo_p.launches - l0)], dtype=torch.float64, device=dev)
+    launches = torch.tensor([float(ds.launches() - l0)], dtype=torch.float64, device=dev)
     dist.all_reduce(launches)
     clocks = sampler.stop()
     # e2e: owned values are pulled to pinned host memory and u_prev pushed back every step
-    no, nl = ds.part.n_owned, ds.n
+    nl = ds.n
     host = torch.empty(3 * nl, dtype=torch.float64).pin_memory()
     hun = torch.empty(2 * nl, dtype=torch.float64).pin_memory()
     barrier()
@@ -247,21 +465,20 @@ def run_distributed(args, w, W, K, world, rank, local_rank):
     barrier()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    info = ds.comm_summary()
     if rank == 0:
         peak, peak_kind = measured_peaks()
         line = {
             "metric": "DOF-timesteps/s", "value": ndof * K / (ms * 1e-3), "unit": "DOF-timesteps/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "solver": "stabilized_schur", "cells": E, "dofs": ndof,
+            "config": {"workload": name, "solver": "stabilized_schur", "cell_type": "triangle", "cells": E, "dofs": ndof,
                        "global_nx": nx, "cells_per_gpu": E // world, "dt": w["dt"], "mu": w["mu"], "rho": w["rho"],
-                       "newton_its_per_step": newton / K, "fgmres_its_per_step": ksp / K,
-                       "parallelism": f"domain decomposition: {world} vertex-owned x-slabs, overlap {ds.overlap} cell "
-                                      f"layers, all-gather halo ({ds.halo.bytes_per_update} B/update), "
-                                      f"replicated global pressure V-cycle, NCCL allreduce for Krylov/Newton reductions",
                        "l2": "inputs larger than L2 (per-GPU matrix %.0f MB vs 126 MB L2)" % (8 * ds.hemo.nnz / 1e6)},
+            "solve": {"newton_its_per_step": newton / K, "fgmres_its_per_step": ksp / K},
+            "parallelism": info,
             "e2e": {"value": ndof * K / float(te.item()), "unit": "DOF-timesteps/s",
-                    "h2d_bytes_per_step": world * 8 * 2 * nl, "d2h_bytes_per_step": world * 8 * 5 * nl},
+                    "h2d_bytes_per_step": world * 8 * 2 * nl, "d2h_bytes_per_step": world * 8 * 3 * nl},
             "gpu_launches": int(launches.item()), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "see the N=1 line (same kernels per partition)", "achieved": None,
                          "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_kind},
@@ -277,9 +494,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="lid_driven2D_nx707", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the larger GPU-only workloads")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -297,180 +515,48 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     W = max(3, args.warmup)
     K = max(1, args.steps)
-    w = WORKLOADS[args.workload]
+    name = args.workload
 
-    import contextlib
     if world > 1:
-        run_distributed(args, w, W, K, world, rank, local_rank)
+        run_distributed(args, name if WORKLOADS[name]["scenario"] == "lid_driven2D" else "lid_driven2D_nx707", W, K,
+                        world, rank, local_rank)
         return
-    with contextlib.redirect_stdout(sys.stderr):       # stdout carries exactly one JSON line
-        sc = build_scenario(w, device=local_rank)
-    s = sc.solver
-    hemo = s.hemo
-    ndof = s.N
-    E = s._cells_host.shape[0]
-    nnz = hemo.nnz
-    dev = hemo.device
 
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize(dev)
+    r = measure_workload(name, W, K, local_rank, want_e2e=not args.no_e2e)
+    others = {}
+    if name == DEFAULT_WORKLOAD and not args.no_extra:
+        for ename, ew, ek in EXTRA_WORKLOADS:
+            t0 = time.perf_counter()
+            try:
+                o = measure_workload(ename, ew, ek, local_rank, want_e2e=True, want_prof=True)
+                o["wall_s"] = time.perf_counter() - t0
+                o["cpu_arm"] = ("not run: the reference's algorithm needs minutes per time step on the host cores at this "
+                                "size (measured 230 s for one step of lid_driven2D_nx707 on 8 cores)")
+                others[ename] = o
+            except Exception as exc:                        # a failed extra workload must not void the main line
+                others[ename] = {"error": f"{type(exc).__name__}: {exc}"}
 
-    # ---- device-resident timed region --------------------------------------
-    for _ in range(W):
-        s.step_device()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    hemo.prof_enable(True)
-    launches0 = hemo.launches
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    newton = ksp = 0
-    e0.record()
-    for _ in range(K):
-        s.step_device()
-        newton += s.its_snes
-        ksp += s.its_ksp
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = hemo.launches - launches0
-    prof = {c: hemo.prof_get(c) for c in PROF_CLASSES}
-    hemo.prof_enable(False)
-    clocks = sampler.stop()
-    # The preconditioner replays as a CUDA graph, so its kernels carry no event pairs in the
-    # timed region above.  Two extra steps with direct launches (same kernels, same data) time
-    # them with the same CUDA-event mechanism; their share is scaled to the timed region.
-    hemo.use_graph(False)
-    s.step_device()
-    hemo.prof_enable(True)
-    g0 = torch.cuda.Event(enable_timing=True)
-    g1 = torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for _ in range(2):
-        s.step_device()
-    g1.record()
-    torch.cuda.synchronize(dev)
-    ms_nograph = g0.elapsed_time(g1)
-    for c in (4, 5):
-        t, k = hemo.prof_get(c)
-        prof[c] = (t * (ms / ms_nograph) if ms_nograph > 0 else t, int(round(k * K / 2)))
-    hemo.prof_enable(False)
-    hemo.use_graph(True)
-    s.step_device()          # re-captures the graph
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms = float(t_ms.item())
-    value = world * ndof * K / (ms * 1e-3)
-
-    # ---- isolated assembly timings (cells/s, nnz/s) ------------------------------
-    def time_fn(fn, reps=5):
-        fn()
-        torch.cuda.synchronize(dev)
-        a = torch.cuda.Event(enable_timing=True)
-        b = torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            fn()
-        b.record()
-        torch.cuda.synchronize(dev)
-        return a.elapsed_time(b) / reps
-
-    jac_ms = time_fn(lambda: hemo.assemble_jacobian(s.d_x, s.d_un, s.d_vals))
-    res_ms = time_fn(lambda: hemo.assemble_residual(s.d_x, s.d_un, s.d_bcval, s.d_g))
-
-    # ---- end to end through the plugin API (host buffers) ------------------------
-    e2e = None
-    if not args.no_e2e:
-        for _ in range(2):
-            s.solveStep()
-            s.u_prev.x.array[:] = s.u_sol.x.array[:]
-            s.p_prev.x.array[:] = s.p_sol.x.array[:]
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            s.solveStep()
-            s.u_prev.x.array[:] = s.u_sol.x.array[:]
-            s.p_prev.x.array[:] = s.p_sol.x.array[:]
-        barrier()
-        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * ndof * K / float(t_e2e.item()), "unit": "DOF-timesteps/s",
-               "h2d_bytes_per_step": s.h2d_bytes_per_step, "d2h_bytes_per_step": s.d2h_bytes_per_step}
-
-    # ---- roofline of the dominant kernel -------------------------------------------
-    n = s.n
-    nnz_node = hemo.nnz_node
-    nv = int(s._cells_host.shape[1])                      # 3: P1 triangles, 4: Q1 quadrilaterals
-    ae_bytes = 72 * nv * nv * E                           # element matrices, 9 doubles per node pair
-    alg_bytes = {
-        0: 76 * nnz_node + 52 * n,                        # J values + node cols + rowptr + x + y
-        1: 4 * nv * E + 8 * E + 56 * n + ae_bytes,        # cells, h, nodal gathers, element matrices out
-        2: ae_bytes + 4 * nv * nv * E + 12 * nnz_node + 72 * nnz_node,
-        3: 4 * nv * E + 8 * E + 56 * n + 24 * nv * E,
-        4: 20 * nnz_node + 4 * n + 56 * n,                # A00 BSR2 fp32 values + cols + rowptr + 7 fp32 vectors of 2n
-        5: 8 * nnz_node + 4 * n + 28 * n,
-        6: None, 7: None,
-        8: None,
-    }
-    peak, peak_kind = measured_peaks()
-    # the cell kernels are FP64-pipe bound at the reference quadrature (on Q1 cells by two
-    # orders of magnitude): the HBM roofline line is chosen among the bandwidth-bound kernel classes
-    hbm_classes = (0, 2, 4, 5)
-    dom = max((c for c in hbm_classes if prof[c][1] > 0 and alg_bytes[c]), key=lambda c: prof[c][0], default=0)
-    dms, dcnt = prof[dom]
-    achieved = alg_bytes[dom] / (dms / dcnt * 1e-3) / 1e9 if dcnt else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        if tj.get("workload") == args.workload:
-            traffic = tj.get("dram_bytes_per_launch", {}).get(PROF_CLASSES[dom])
-    roofline = {"bound": "hbm", "kernel": PROF_CLASSES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
-                "launches_timed": dcnt, "avg_us": 1e3 * dms / max(dcnt, 1),
-                "share_of_step": dms / ms,
-                "fp64_bound": {"kernels": ["cell_jacobian", "cell_residual"],
-                               "evidence": "ncu sm__pipe_fp64_cycles_active: 75 % (Q1 J_uu work items, "
-                                           "profiles/r01_q1_ncu_full_cell_kernels.csv); DRAM <= 10 %"},
-                "other_kernels": {PROF_CLASSES[c]: {"ms_total": prof[c][0], "launches": prof[c][1],
-                                                    "GBps": (alg_bytes[c] / (prof[c][0] / prof[c][1] * 1e-3) / 1e9
-                                                             if alg_bytes[c] and prof[c][1] else None)}
-                                  for c in prof if c != dom}}
-
-    # ---- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample --------
+    # ---- CPU baseline: the reference's algorithm on the host cores, one time step of the SAME mesh ----------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and w["scenario"] == "lid_driven2D":
-        cdof, csecs = oracle_steps(w, CPU_SAMPLE_NX, 1)
-        cpu = {"value": cdof / csecs, "unit": "DOF-timesteps/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"1 time step of {w['scenario']} at nx={CPU_SAMPLE_NX} ({cdof} DOFs) with the numpy/SciPy "
-                         f"oracle port: C/OpenMP cell kernels on all cores + SciPy SuperLU Newton ({csecs:.1f} s); "
-                         f"DOLFINx/PETSc not installable here"}
+    if not args.no_cpu_baseline and WORKLOADS[name]["scenario"] == "lid_driven2D":
+        c = cpu_steps(name, 0, 1, 120.0)
+        cpu = {"value": c["ndof"] * c["steps"] / c["seconds"], "unit": "DOF-timesteps/s", "cores": c["cores"], "kind": "port",
+               "sample": f"the first time step of {name} ({c['ndof']} DOFs, the same mesh) with the reference's solver "
+                         f"configuration restated in C + OpenMP (FGMRES(200) + fieldsplit Schur FULL/SELFP + "
+                         f"GMRES(30)/ASM-ILU(0), {c['cores']} threads): {c['seconds']:.1f} s, {c['newton_its']} Newton / "
+                         f"{c['outer_its']} outer / {c['inner_its']} inner iterations; DOLFINx/PETSc not installable here"}
 
-    if rank == 0:
-        line = {
-            "metric": "DOF-timesteps/s", "value": value, "unit": "DOF-timesteps/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "solver": sc.solver_name, "cells": E, "dofs": ndof,
-                       "nnz": nnz, "dt": w["dt"], "mu": float(s.mu.value), "rho": float(s.rho.value),
-                       "newton_its_per_step": newton / K, "fgmres_its_per_step": ksp / K,
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (one mesh per GPU)",
-                       "l2": "inputs larger than L2 (matrix %.0f MB, element buffer %.0f MB vs 126 MB L2)"
-                             % (8 * nnz / 1e6, 72 * int(s._cells_host.shape[1]) ** 2 * E / 1e6),
-                       "cell_type": s.mesh.topology.cell_name()},
-            "assembly": {"jacobian_cells_per_s": world * E / (jac_ms * 1e-3), "jacobian_nnz_per_s": world * nnz / (jac_ms * 1e-3),
-                         "residual_cells_per_s": world * E / (res_ms * 1e-3), "jacobian_ms": jac_ms, "residual_ms": res_ms},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        }
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    line = {
+        "metric": "DOF-timesteps/s", "value": r["value"], "unit": "DOF-timesteps/s", "n_gpus": 1, "steps": K,
+        "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": r["config"],
+        "solve": {"newton_its_per_step": r["newton_its_per_step"], "fgmres_its_per_step": r["fgmres_its_per_step"],
+                  "nnz": r["nnz"], "ms_per_step_direct_launches": r.get("ms_per_step_direct_launches")},
+        "parallelism": "1 GPU", "precision": r["precision"],
+        "assembly": r["assembly"], "e2e": r.get("e2e"), "gpu_launches": r["gpu_launches"], "clocks": r["clocks"],
+        "roofline": r.get("roofline"), "cpu_baseline": cpu, "other_workloads": others,
+    }
+    print(json.dumps(line))
 
 
 if __name__ == "__main__":

@@ -106,6 +106,14 @@ SYMBOLS = {
     "hemo_amg_get_level_values": (_I, [_VP, _I, _I, _VP, _L]),
     "hemo_pc_apply": (_I, [_VP, _VP, _VP, _VP]),
     "hemo_fgmres": (_I, [_VP, _VP, _VP, _VP, C.POINTER(_I), C.POINTER(_D)]),
+    "hemo_comm_unique_id": (_I, [C.c_char_p]),
+    "hemo_comm_init": (_I, [_VP, C.c_char_p, _I, _I]),
+    "hemo_comm_info": (_I, [_VP, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L), C.POINTER(_L)]),
+    "hemo_comm_set_partition": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _I]),
+    "hemo_comm_halo_update": (_I, [_VP, _VP]),
+    "hemo_comm_allreduce": (_I, [_VP, _VP, _I]),
+    "hemo_global_dot": (_I, [_VP, _VP, _VP, C.POINTER(_D)]),
+    "hemo_set_poll_interval": (_I, [_VP, _I]),
 }
 
 _lib = None
@@ -446,6 +454,49 @@ class Hemo:
 
     def pc_apply(self, vals, r, z):
         self._check(self.lib.hemo_pc_apply(self._ctx, _ptr(vals), _ptr(r), _ptr(z)), "hemo_pc_apply")
+
+    # ---- multi-GPU: NCCL inside the library ---------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = load_library().hemo_comm_unique_id(buf)
+        if rc:
+            raise HemoError("hemo_comm_unique_id failed (NCCL not loadable)")
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, nranks: int):
+        self._check(self.lib.hemo_comm_init(self._ctx, C.c_char_p(uid), int(rank), int(nranks)), "hemo_comm_init")
+
+    def comm_info(self):
+        r, n, v = C.c_int(), C.c_int(), C.c_int()
+        h, a = C.c_int64(), C.c_int64()
+        self._check(self.lib.hemo_comm_info(self._ctx, C.byref(r), C.byref(n), C.byref(v), C.byref(h), C.byref(a)),
+                    "hemo_comm_info")
+        return dict(rank=r.value, nranks=n.value, nccl_version=v.value, halo_updates=h.value, allreduces=a.value)
+
+    def comm_set_partition(self, n_owned, peers, send_ptr, send_nodes, recv_ptr, ras_overlap=False):
+        peers = np.ascontiguousarray(peers, dtype=np.int32)
+        send_ptr = np.ascontiguousarray(send_ptr, dtype=np.int32)
+        send_nodes = np.ascontiguousarray(send_nodes, dtype=np.int32)
+        recv_ptr = np.ascontiguousarray(recv_ptr, dtype=np.int32)
+        hp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._check(self.lib.hemo_comm_set_partition(self._ctx, int(n_owned), int(peers.shape[0]), hp(peers), hp(send_ptr),
+                                                     hp(send_nodes), hp(recv_ptr), int(bool(ras_overlap))),
+                    "hemo_comm_set_partition")
+
+    def halo_update(self, v):
+        self._check(self.lib.hemo_comm_halo_update(self._ctx, _ptr(v)), "hemo_comm_halo_update")
+
+    def allreduce(self, buf):
+        self._check(self.lib.hemo_comm_allreduce(self._ctx, _ptr(buf), buf.numel()), "hemo_comm_allreduce")
+
+    def global_dot(self, x, y) -> float:
+        out = C.c_double()
+        self._check(self.lib.hemo_global_dot(self._ctx, _ptr(x), _ptr(y), C.byref(out)), "hemo_global_dot")
+        return out.value
+
+    def set_poll_interval(self, every: int):
+        self._check(self.lib.hemo_set_poll_interval(self._ctx, int(every)), "hemo_set_poll_interval")
 
     def fgmres(self, vals, b, y):
         its = C.c_int()

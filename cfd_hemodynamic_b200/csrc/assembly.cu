@@ -913,13 +913,8 @@ extern "C" int hemo_set_cell_type(hemo_ctx* ctx, int cell_type) {
         fs.m = 0;
     }
     ctx->have_bc = false;
-    ctx->amg[0].ready = ctx->amg[1].ready = false;
-    // preconditioner work vectors are sized by (dim, n): reallocated by the next hemo_pc_setup
-    cudaFree(ctx->pc_tmp_u); cudaFree(ctx->pc_tmp_u2); cudaFree(ctx->pc_tmp_p); cudaFree(ctx->pc_tmp_p2);
-    cudaFree(ctx->pc_in); cudaFree(ctx->pc_out); cudaFree(ctx->a01);
-    ctx->pc_tmp_u = ctx->pc_tmp_u2 = ctx->pc_tmp_p = ctx->pc_tmp_p2 = ctx->pc_in = ctx->pc_out = nullptr;
-    ctx->a01 = nullptr;
-    if (ctx->pc_graph_exec) { cudaGraphExecDestroy(ctx->pc_graph_exec); ctx->pc_graph_exec = nullptr; }
+    // solver buffers and captured graphs are sized by (dim, n): reallocated by the next hemo_pc_setup / hemo_fgmres
+    hemo_drop_solver_state(ctx);
     return 0;
 }
 
@@ -930,6 +925,19 @@ extern "C" int hemo_set_mesh(hemo_ctx* ctx, const double* x_dev, int n_nodes, co
     const int64_t nv2 = (int64_t)ctx->nv * ctx->nv;
     if ((int64_t)n_cells * 9 * nv2 >= ((int64_t)1 << 40)) HEMO_FAIL(ctx, HEMO_EINVAL, "mesh too large");
     if ((int64_t)n_cells * nv2 >= ((int64_t)1 << 31)) HEMO_FAIL(ctx, HEMO_EINVAL, "n_cells*nv^2 exceeds int32 gather index");
+    if (ctx->n != n_nodes || ctx->E != n_cells) {
+        // a context re-used with another mesh: nothing sized by the old one may survive (Krylov basis,
+        // preconditioner vectors, captured graphs, node-graph tables, Dirichlet flags, facet sets)
+        hemo_drop_solver_state(ctx);
+        ctx->nrowptr = nullptr; ctx->ncol = nullptr; ctx->nnz_node = 0;
+        ctx->have_bc = false;
+        for (int s = 0; s < HEMO_MAX_FACET_SETS; ++s) {
+            HemoFacetSet& fs = ctx->fsets[s];
+            cudaFree(fs.cells); cudaFree(fs.mask);
+            fs.cells = fs.mask = nullptr;
+            fs.m = 0;
+        }
+    }
     ctx->x = x_dev; ctx->cells = cells_dev; ctx->h = h_dev;
     ctx->n = n_nodes; ctx->E = n_cells;
     int rc;

@@ -117,6 +117,28 @@ struct HemoProf {
 };
 
 struct hemo_tet_state;      // assembly_tet.cu
+struct HemoComm;            // comm.cu (NCCL communicator + halo plan of a mesh partition)
+
+// device-resident FGMRES (krylov.cu)
+struct HemoKrylov {
+    int m = 0;                      // restart the buffers are sized for
+    int64_t ldv = 0;                // leading dimension of the basis
+    double* H = nullptr;            // (m+1) x m Hessenberg / triangular factor, column-major
+    double* small = nullptr;        // cs, sn, g, ycoef, hcol, scale: 6 x (m+2)
+    double* partial = nullptr;      // per-block partial sums of the multi-dot
+    double* state = nullptr;        // FgState + scalars (64 doubles)
+    double* state_host = nullptr;   // pinned copy
+    int last_its = 0;               // iterations of the previous solve (first poll)
+    int poll_every = 2;
+    int64_t polls = 0;
+    // owned entries of a local vector (multi-GPU): [0, seg_len0) and [seg_off1, seg_off1 + seg_len1); 0 = all
+    int64_t seg_len0 = 0, seg_off1 = 0, seg_len1 = 0;
+    // CUDA graph of one iteration
+    cudaGraphExec_t iter_exec = nullptr;
+    bool iter_valid = false;
+    const double* iter_vals = nullptr;
+    int64_t iter_nodes = 0;
+};
 
 struct hemo_ctx {
     HemoProf prof;
@@ -190,6 +212,7 @@ struct hemo_ctx {
     cudaGraph_t pc_graph = nullptr;
     cudaGraphExec_t pc_graph_exec = nullptr;
     int64_t pc_graph_nodes = 0;
+    bool pc_graph_dirty = true;     // re-captured lazily by the next hemo_pc_apply (hemo_fgmres captures whole iterations)
     bool capturing = false;
     int use_graph = 1;
     double* pc_in = nullptr;        // 3n (padded) staging of the graph's input / output
@@ -202,6 +225,10 @@ struct hemo_ctx {
     double* kry_Z = nullptr;        // restart*N
     double* kry_w = nullptr;        // N
     int kry_restart = 0;
+    HemoKrylov kry;
+    // multi-GPU (comm.cu): null = single GPU
+    HemoComm* comm = nullptr;
+    int comm_ras_overlap = 0;       // 1: the preconditioner input needs valid ghost values (overlapping Schwarz)
 };
 
 #define HEMO_CHECK_CUDA(ctx, expr)                                                     \
@@ -297,9 +324,21 @@ int hemo_tet_velocity_solve(hemo_ctx* ctx, const double* vals_dev, const double*
 int hemo_tet_spmv(hemo_ctx* ctx, const double* vals_dev, const double* x_dev, double* y_dev);
 // implemented in linalg.cu
 int hemo_ensure_reduce(hemo_ctx* ctx, size_t partial_n, size_t out_n);
+// Drops everything sized by (dim, n, nnz_node) in the solver part of the context: Krylov basis,
+// preconditioner work vectors, the compact A01 copy and every captured CUDA graph (their nodes
+// hold raw pointers).  Called when the mesh or the cell type changes; the next hemo_pc_setup /
+// hemo_fgmres reallocates.
+void hemo_drop_solver_state(hemo_ctx* ctx);
 int hemo_dot_dev(hemo_ctx* ctx, int64_t n, const double* x, const double* y, double* out_host);
 int hemo_bsr_spmv(hemo_ctx* ctx, int bs, int n, const int32_t* rowptr, const int32_t* col,
                   const areal* val, const areal* x, areal* y);
+// implemented in krylov.cu
+void hemo_krylov_free(hemo_ctx* ctx);
+void hemo_krylov_invalidate(hemo_ctx* ctx);
+// implemented in comm.cu
+int hemo_comm_halo(hemo_ctx* ctx, double* v_dev);                 // forward ghost update of a local [u | p] vector
+int hemo_comm_allreduce_j(hemo_ctx* ctx, double* buf_dev, int count);   // in-place sum over the ranks (device buffer)
+void hemo_comm_free(hemo_ctx* ctx);
 // implemented in amg.cu
 int hemo_amg_numeric(hemo_ctx* ctx, HemoAmg* amg);
 int hemo_amg_vcycle(hemo_ctx* ctx, HemoAmg* amg, const double* b, double* x, int ncycles);

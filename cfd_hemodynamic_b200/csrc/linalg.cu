@@ -13,13 +13,40 @@
 #define RED_BLOCKS 1184   // 148 SMs * 8
 #define RED_THREADS 256
 
+// Captured CUDA graphs (preconditioner application, V-cycle) hold the raw addresses of these
+// buffers in their kernel nodes.  The scratch is therefore allocated once at the size of the largest
+// request any entry point makes (restart <= 400: RED_BLOCKS * (400 + 4) partial sums, 1024 results);
+// should a larger request ever arrive, every captured graph is dropped before the buffers move.
+static void drop_graphs(hemo_ctx* ctx) {
+    hemo_krylov_invalidate(ctx);
+    if (ctx->pc_graph_exec) { cudaGraphExecDestroy(ctx->pc_graph_exec); ctx->pc_graph_exec = nullptr; }
+    if (ctx->pc_graph) { cudaGraphDestroy(ctx->pc_graph); ctx->pc_graph = nullptr; }
+    ctx->pc_graph_dirty = true;
+    for (int w = 0; w < 2; ++w) {
+        HemoAmg& a = ctx->amg[w];
+        if (a.apply_exec) { cudaGraphExecDestroy(a.apply_exec); a.apply_exec = nullptr; }
+        a.apply_valid = false;
+    }
+}
+
 int hemo_ensure_reduce(hemo_ctx* ctx, size_t partial_n, size_t out_n) {
+    const size_t min_partial = (size_t)RED_BLOCKS * 404, min_out = 1024;
+    if (partial_n < min_partial) partial_n = min_partial;
+    if (out_n < min_out) out_n = min_out;
     if (partial_n > ctx->red_partial_n) {
+        if (ctx->red_partial) {
+            HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            drop_graphs(ctx);
+        }
         int rc = hemo_alloc(ctx, &ctx->red_partial, partial_n);
         if (rc) return rc;
         ctx->red_partial_n = partial_n;
     }
     if (out_n > ctx->red_out_n) {
+        if (ctx->red_out) {
+            HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            drop_graphs(ctx);
+        }
         int rc = hemo_alloc(ctx, &ctx->red_out, out_n);
         if (rc) return rc;
         if (ctx->red_host) cudaFreeHost(ctx->red_host);
@@ -27,6 +54,25 @@ int hemo_ensure_reduce(hemo_ctx* ctx, size_t partial_n, size_t out_n) {
         ctx->red_out_n = out_n;
     }
     return 0;
+}
+
+void hemo_drop_solver_state(hemo_ctx* ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    drop_graphs(ctx);
+    cudaFree(ctx->pc_tmp_u); cudaFree(ctx->pc_tmp_u2); cudaFree(ctx->pc_tmp_p); cudaFree(ctx->pc_tmp_p2);
+    cudaFree(ctx->pc_in); cudaFree(ctx->pc_out); cudaFree(ctx->a01);
+    ctx->pc_tmp_u = ctx->pc_tmp_u2 = ctx->pc_tmp_p = ctx->pc_tmp_p2 = ctx->pc_in = ctx->pc_out = nullptr;
+    ctx->a01 = nullptr;
+    cudaFree(ctx->kry_V); cudaFree(ctx->kry_Z); cudaFree(ctx->kry_w);
+    ctx->kry_V = ctx->kry_Z = ctx->kry_w = nullptr;
+    ctx->kry_restart = 0;
+    hemo_krylov_invalidate(ctx);
+    ctx->kry.m = 0; ctx->kry.last_its = 0;
+    cudaFree(ctx->pc_mask); cudaFree(ctx->schur_mask); cudaFree(ctx->schur_tmp); cudaFree(ctx->npconv);
+    ctx->pc_mask = ctx->schur_mask = nullptr; ctx->schur_tmp = nullptr; ctx->npconv = nullptr;
+    ctx->npconv_coef = 0.0;
+    ctx->mass = nullptr;
+    ctx->amg[0].ready = ctx->amg[1].ready = false;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -306,6 +352,41 @@ int hemo_dot_dev(hemo_ctx* ctx, int64_t n, const double* x, const double* y, dou
 extern "C" int hemo_dot(hemo_ctx* ctx, int64_t n, const double* x_dev, const double* y_dev, double* out_host) {
     if (!ctx || !x_dev || !y_dev || !out_host || n < 0) return HEMO_EINVAL;
     return hemo_dot_dev(ctx, n, x_dev, y_dev, out_host);
+}
+
+// dot product over the owned entries of two local [u | p] vectors, summed over the ranks (VecDot under MPI)
+__global__ void __launch_bounds__(RED_THREADS)
+k_dot_seg_partial(int64_t len0, int64_t off1, int64_t len1, const double* __restrict__ x, const double* __restrict__ y,
+                  double* __restrict__ partial) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    const int64_t n = len0 + len1;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = i < len0 ? i : i - len0 + off1;
+        acc = fma(x[q], y[q], acc);
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+extern "C" int hemo_global_dot(hemo_ctx* ctx, const double* x_dev, const double* y_dev, double* out_host) {
+    if (!ctx || !x_dev || !y_dev || !out_host) return HEMO_EINVAL;
+    if (!ctx->cells) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh not set");
+    const int64_t N = (int64_t)(ctx->dim + 1) * ctx->n;
+    if (!ctx->comm || ctx->kry.seg_len0 == 0) return hemo_dot_dev(ctx, N, x_dev, y_dev, out_host);
+    int rc = hemo_ensure_reduce(ctx, RED_BLOCKS * 8, 512);
+    if (rc) return rc;
+    const HemoKrylov& K = ctx->kry;
+    const int g = grid_for(K.seg_len0 + K.seg_len1);
+    k_dot_seg_partial<<<g, RED_THREADS, 0, ctx->stream>>>(K.seg_len0, K.seg_off1, K.seg_len1, x_dev, y_dev, ctx->red_partial);
+    HEMO_LAUNCH_CHECK(ctx);
+    k_reduce_final<<<1, RED_THREADS, 0, ctx->stream>>>(g, ctx->red_partial, ctx->red_out + 502, -1);
+    HEMO_LAUNCH_CHECK(ctx);
+    if ((rc = hemo_comm_allreduce_j(ctx, ctx->red_out + 502, 1))) return rc;
+    HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->red_host + 502, ctx->red_out + 502, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out_host = ctx->red_host[502];
+    return 0;
 }
 
 extern "C" int hemo_norm2(hemo_ctx* ctx, int64_t n, const double* x_dev, double* out_host) {

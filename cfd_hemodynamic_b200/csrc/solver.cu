@@ -146,6 +146,7 @@ __global__ void k_schur_combine(int n, double cm, double cl, double cc, const do
 }
 
 static int pc_build_graph(hemo_ctx* ctx, const double* vals_dev);
+int hemo_pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_dev, double* z_dev);
 
 // Dirichlet flags of the pressure dofs: the tail of dofflag in the [u (dim n) | p (n)] layout
 static inline const uint8_t* pressure_flags(const hemo_ctx* ctx) {
@@ -274,7 +275,9 @@ extern "C" int hemo_pc_setup(hemo_ctx* ctx, const double* vals_dev, const double
         if ((rc = hemo_amg_numeric_shift(ctx, &ctx->amg[1], ctx->opts.project_pressure ? 1e-8 : 0.0))) return rc;
     }
     if (!ctx->mass) HEMO_FAIL(ctx, HEMO_ESTATE, "first hemo_pc_setup call needs lap_vals and mass");
-    return pc_build_graph(ctx, vals_dev);
+    hemo_krylov_invalidate(ctx);     // smoother coefficients are baked into the captured iteration
+    ctx->pc_graph_dirty = true;      // ... and into the stand-alone preconditioner graph (re-captured on demand)
+    return 0;
 }
 
 extern "C" int hemo_amg_apply(hemo_ctx* ctx, int which, const double* b_dev, double* x_dev, int ncycles) {
@@ -330,7 +333,7 @@ extern "C" int hemo_amg_get_level_values(hemo_ctx* ctx, int which, int level, do
     return 0;
 }
 
-static int pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_dev, double* z_dev) {
+int hemo_pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_dev, double* z_dev) {
     const int n = ctx->n;
     cudaStream_t st = ctx->stream;
     const double* ru = r_dev;
@@ -393,7 +396,7 @@ static int pc_build_graph(hemo_ctx* ctx, const double* vals_dev) {
         ctx->use_graph = 0;            // capture unsupported here: fall back to direct launches
         return 0;
     }
-    rc = pc_apply_body(ctx, vals_dev, ctx->pc_in, ctx->pc_out);
+    rc = hemo_pc_apply_body(ctx, vals_dev, ctx->pc_in, ctx->pc_out);
     cudaGraph_t g = nullptr;
     e = cudaStreamEndCapture(st, &g);
     ctx->capturing = false;
@@ -421,7 +424,12 @@ static int pc_build_graph(hemo_ctx* ctx, const double* vals_dev) {
 extern "C" int hemo_pc_apply(hemo_ctx* ctx, const double* vals_dev, const double* r_dev, double* z_dev) {
     if (!ctx || !vals_dev || !r_dev || !z_dev) return HEMO_EINVAL;
     if (!ctx->mass || !ctx->pc_tmp_u) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_pc_setup not called");
-    if (ctx->use_graph && ctx->pc_graph_exec) {
+    if (ctx->use_graph && ctx->stream != 0 && ctx->pc_graph_dirty) {
+        int rc = pc_build_graph(ctx, vals_dev);
+        if (rc) return rc;
+        ctx->pc_graph_dirty = false;
+    }
+    if (ctx->use_graph && ctx->pc_graph_exec && ctx->stream != 0) {
         const size_t bytes = sizeof(double) * (size_t)(ctx->dim + 1) * (size_t)ctx->n;
         cudaStream_t st = ctx->stream;
         HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->pc_in, r_dev, bytes, cudaMemcpyDeviceToDevice, st));
@@ -433,120 +441,7 @@ extern "C" int hemo_pc_apply(hemo_ctx* ctx, const double* vals_dev, const double
         ctx->launches += ctx->pc_graph_nodes;
         return 0;
     }
-    return pc_apply_body(ctx, vals_dev, r_dev, z_dev);
-}
-
-static int ensure_krylov(hemo_ctx* ctx, int restart, int64_t ldv) {
-    if (ctx->kry_restart >= restart && ctx->kry_V) return 0;
-    int rc;
-    if ((rc = hemo_alloc(ctx, &ctx->kry_V, (size_t)(restart + 1) * ldv))) return rc;
-    if ((rc = hemo_alloc(ctx, &ctx->kry_Z, (size_t)restart * ldv))) return rc;
-    if ((rc = hemo_alloc(ctx, &ctx->kry_w, (size_t)ldv + 512))) return rc;
-    ctx->kry_restart = restart;
-    return 0;
-}
-
-extern "C" int hemo_fgmres(hemo_ctx* ctx, const double* vals_dev, const double* b_dev, double* y_dev,
-                           int* its_out, double* rel_resid_out) {
-    if (!ctx || !vals_dev || !b_dev || !y_dev) return HEMO_EINVAL;
-    const int n = ctx->n;
-    const int64_t N = (int64_t)(ctx->dim + 1) * n;      // [u (dim n) | p (n)]
-    const int64_t ldv = (N + 31) / 32 * 32;
-    const int m = ctx->opts.restart;
-    cudaStream_t st = ctx->stream;
-    int rc;
-    if ((rc = ensure_krylov(ctx, m, ldv))) return rc;
-    if ((rc = hemo_ensure_reduce(ctx, (size_t)1184 * (m + 3), 512))) return rc;
-    double* V = ctx->kry_V;
-    double* Z = ctx->kry_Z;
-    double* w = ctx->kry_w;
-    double* coef_dev = ctx->kry_w + ldv;   // m+1 doubles of device scratch for the update coefficients
-    std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), hcol(m + 2), yk(m);
-
-    HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(y_dev, 0, sizeof(double) * N, st));
-    double bnorm = 0.0;
-    if ((rc = hemo_norm2(ctx, N, b_dev, &bnorm))) return rc;
-    int its = 0;
-    double res = bnorm;
-    const double tol = fmax(ctx->opts.rtol * bnorm, ctx->opts.atol);
-    if (bnorm == 0.0 || bnorm <= ctx->opts.atol) {
-        if (its_out) *its_out = 0;
-        if (rel_resid_out) *rel_resid_out = 0.0;
-        return 0;
-    }
-    bool converged = false;
-    double beta = bnorm;
-    // r0 = b (zero initial guess)
-    if ((rc = hemo_scale_copy(ctx, N, 1.0 / beta, b_dev, V))) return rc;
-    while (!converged && its < ctx->opts.max_it) {
-        for (int i = 0; i <= m; ++i) g[i] = 0.0;
-        g[0] = beta;
-        int j = 0;
-        for (; j < m && its < ctx->opts.max_it; ++j) {
-            double* vj = V + (int64_t)j * ldv;
-            double* zj = Z + (int64_t)j * ldv;
-            if ((rc = hemo_pc_apply(ctx, vals_dev, vj, zj))) return rc;
-            HEMO_PROF_BEGIN(ctx, HEMO_PROF_SPMV);
-            if ((rc = hemo_spmv(ctx, vals_dev, zj, w))) return rc;
-            HEMO_PROF_END(ctx, HEMO_PROF_SPMV);
-            // classical Gram–Schmidt (PETSc default: no refinement)
-            if ((rc = hemo_mdot(ctx, N, j + 1, V, ldv, w, hcol.data()))) return rc;
-            double hn = 0.0;
-            if ((rc = hemo_maxpy(ctx, N, j + 1, V, ldv, ctx->red_out, -1.0, w, &hn))) return rc;
-            for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = hcol[i];
-            H[(size_t)(j + 1) * m + j] = hn;
-            if (hn > 0.0) {
-                if ((rc = hemo_scale_copy(ctx, N, 1.0 / hn, w, V + (int64_t)(j + 1) * ldv))) return rc;
-            }
-            // Givens rotations
-            for (int i = 0; i < j; ++i) {
-                const double a = H[(size_t)i * m + j], b2 = H[(size_t)(i + 1) * m + j];
-                H[(size_t)i * m + j] = cs[i] * a + sn[i] * b2;
-                H[(size_t)(i + 1) * m + j] = -sn[i] * a + cs[i] * b2;
-            }
-            const double a = H[(size_t)j * m + j], b2 = H[(size_t)(j + 1) * m + j];
-            const double d = hypot(a, b2);
-            cs[j] = (d > 0.0) ? a / d : 1.0;
-            sn[j] = (d > 0.0) ? b2 / d : 0.0;
-            H[(size_t)j * m + j] = d;
-            H[(size_t)(j + 1) * m + j] = 0.0;
-            g[j + 1] = -sn[j] * g[j];
-            g[j] = cs[j] * g[j];
-            ++its;
-            res = fabs(g[j + 1]);
-            if (!isfinite(res)) HEMO_FAIL(ctx, HEMO_DIVERGED, "FGMRES residual is not finite");
-            if (res <= tol || hn == 0.0) { converged = true; ++j; break; }
-        }
-        // y += Z_k * (H_k^-1 g_k)
-        const int k = j;
-        for (int i = k - 1; i >= 0; --i) {
-            double s = g[i];
-            for (int l = i + 1; l < k; ++l) s -= H[(size_t)i * m + l] * yk[l];
-            yk[i] = s / H[(size_t)i * m + i];
-        }
-        for (int i = 0; i < k; ++i) ctx->red_host[i] = yk[i];
-        HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(coef_dev, ctx->red_host, sizeof(double) * k, cudaMemcpyHostToDevice, st));
-        if ((rc = hemo_maxpy(ctx, N, k, Z, ldv, coef_dev, 1.0, y_dev, nullptr))) return rc;
-        HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(st));   // red_host is reused below
-        if (converged) break;
-        // restart: r = b - A y
-        double sgn = 1.0;
-        if (ctx->dim == 3) {
-            if ((rc = hemo_tet_spmv(ctx, vals_dev, y_dev, w))) return rc;
-            if ((rc = hemo_axpy(ctx, N, -1.0, b_dev, w))) return rc;           // w = A y - b = -r
-            sgn = -1.0;
-        } else if ((rc = hemo_spmv_block(ctx, 3, 3, vals_dev, y_dev, y_dev + 2 * (int64_t)n, -1.0, b_dev,
-                                         b_dev + 2 * (int64_t)n, w, w + 2 * (int64_t)n)))
-            return rc;
-        if ((rc = hemo_norm2(ctx, N, w, &beta))) return rc;
-        res = beta;
-        if (beta <= tol) { converged = true; break; }
-        if ((rc = hemo_scale_copy(ctx, N, sgn / beta, w, V))) return rc;
-    }
-    if (its_out) *its_out = its;
-    if (rel_resid_out) *rel_resid_out = res / bnorm;
-    if (!converged) HEMO_FAIL(ctx, HEMO_DIVERGED, "FGMRES reached max_it without converging");
-    return 0;
+    return hemo_pc_apply_body(ctx, vals_dev, r_dev, z_dev);
 }
 
 // ---------------------------------------------------------------------------
@@ -593,6 +488,8 @@ extern "C" int hemo_ctx_destroy(hemo_ctx* ctx) {
     cudaFree(ctx->pc_in); cudaFree(ctx->pc_out); cudaFree(ctx->pc_mask); cudaFree(ctx->kry_coef); cudaFree(ctx->a01);
     cudaFree(ctx->pc_tmp_u); cudaFree(ctx->pc_tmp_u2); cudaFree(ctx->pc_tmp_p); cudaFree(ctx->pc_tmp_p2);
     cudaFree(ctx->kry_V); cudaFree(ctx->kry_Z); cudaFree(ctx->kry_w);
+    hemo_krylov_free(ctx);
+    hemo_comm_free(ctx);
     delete ctx;
     return 0;
 }

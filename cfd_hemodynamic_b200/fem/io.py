@@ -156,12 +156,17 @@ def read_from_msh(path, comm=None, rank: int = 0, gdim: int = 3):
         fv = np.concatenate([renum(b) for _, b in fgroups])
         fvals = np.concatenate([np.full(len(b), p, dtype=np.int32) for p, b in fgroups])
         nfv = fv.shape[1]
-        nv = np.int64(mesh.num_vertices)
-        key = lambda a: np.sort(a, axis=1).astype(np.int64) @ (nv ** np.arange(nfv - 1, -1, -1, dtype=np.int64))
-        mesh_keys = key(mesh.topology.facet_vertices)
-        order = np.argsort(mesh_keys)
-        pos = np.searchsorted(mesh_keys[order], key(fv))
-        if (pos >= len(order)).any() or (mesh_keys[order][np.minimum(pos, len(order) - 1)] != key(fv)).any():
+        # match by the sorted vertex tuples themselves (lexicographic rows): a packed integer key would
+        # wrap beyond 2^63 for triangular facets of meshes with more than ~2.1 M vertices
+        mv = np.sort(mesh.topology.facet_vertices, axis=1).astype(np.int64)
+        tv = np.sort(fv, axis=1).astype(np.int64)
+        both = np.concatenate([mv, tv])
+        _, inv = np.unique(both, axis=0, return_inverse=True)
+        inv = np.asarray(inv).reshape(-1)
+        mesh_keys, tag_keys = inv[:len(mv)], inv[len(mv):]
+        order = np.argsort(mesh_keys, kind="stable")
+        pos = np.searchsorted(mesh_keys[order], tag_keys)
+        if (pos >= len(order)).any() or (mesh_keys[order][np.minimum(pos, len(order) - 1)] != tag_keys).any():
             raise ValueError(f"{path}: a tagged facet is not a facet of any cell")
         facet_tags = meshtags(mesh, tdim - 1, order[pos].astype(np.int32), fvals)
     else:

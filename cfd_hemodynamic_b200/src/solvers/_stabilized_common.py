@@ -369,6 +369,9 @@ class StabilizedSchurB200(SolverBase):
         return None
 
     def _solve_on_device(self):
+        # bc.update() for every bc + refresh of the Dirichlet values (stabilized_schur.py:170): in the
+        # host loop and in the device-resident loop alike (boundary-sized, uploads only on change)
+        self._upload_bc_values()
         self._remove_pressure_mean()
         self._update_facet_coefs()
         self._prepare_time_scheme()
@@ -385,7 +388,6 @@ class StabilizedSchurB200(SolverBase):
         n = self.n
         # the host owns the time-level shift (scenario.py:306-307)
         self.d_un.copy_(self._pin["u_prev"], non_blocking=True)
-        self._upload_bc_values()
         self._solve_on_device()
         self._pin["u_sol"].copy_(self.d_x[:2 * n], non_blocking=True)
         self._pin["p_sol"].copy_(self.d_x[2 * n:], non_blocking=True)

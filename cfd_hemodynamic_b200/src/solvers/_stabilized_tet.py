@@ -177,19 +177,13 @@ class StabilizedSchurTetB200(StabilizedSchurB200):
             return super().solveStep()
         n = self.n
         self.d_un.copy_(self._pin["u_prev"], non_blocking=True)
-        self._upload_bc_values()
-        self._solve_on_device()
+        self._solve_on_device()              # refreshes the Dirichlet values first (bc.update(), stabilized_schur.py:170)
         self._pin["u_sol"].copy_(self.d_x[:3 * n], non_blocking=True)
         self._pin["p_sol"].copy_(self.d_x[3 * n:], non_blocking=True)
         self._pin["u_residual"].copy_(self.d_f[:3 * n], non_blocking=True)
         self._pin["p_residual"].copy_(self.d_f[3 * n:], non_blocking=True)
         self._torch.cuda.current_stream(self.hemo.device).synchronize()
         self._after_step()
-
-    def step_device(self, shift: bool = True):
-        if self._tet:
-            self._upload_bc_values()         # time-dependent boundary data (taylor_green): boundary-sized, only when changed
-        return super().step_device(shift)
 
     def shift_time_level_device(self):
         if not self._tet:

@@ -279,6 +279,38 @@ int hemo_vec_maxpy(hemo_ctx* ctx, int64_t n, int k, const double* V_dev, int64_t
                    const double* coef_host, double sign, double* w_dev, double* normsq_host);
 int hemo_vec_scale(hemo_ctx* ctx, int64_t n, double a, const double* x_dev, double* y_dev);
 
+/* ---- multi-GPU inside the library: one mesh partition per GPU, NCCL over NVLink ------------------
+ * What PETSc/MPI does for the reference under `mpirun -n N`: after hemo_comm_init and
+ * hemo_comm_set_partition, hemo_fgmres runs the distributed Krylov iteration itself — forward ghost
+ * update of the search direction before the operator (ghostUpdate(INSERT, FORWARD),
+ * src/solvers/stabilized_schur.py:137-142,168), one ncclAllReduce for the Gram-Schmidt coefficients and
+ * one for the norm per iteration (VecMDot / VecNorm), Givens rotations and the convergence flag on the
+ * device — captured in the same per-iteration CUDA graph as on one GPU.
+ * Local numbering: owned nodes first, then ghost nodes grouped by owner rank in the order of `peers`.
+ * hemo_comm_unique_id: ncclGetUniqueId on rank 0 (128 bytes, broadcast by the caller, e.g. through the
+ * torch.distributed store).  NCCL is dlopen'ed (libnccl.so.2), the single-GPU path does not need it. */
+int hemo_comm_unique_id(char* out128);
+int hemo_comm_init(hemo_ctx* ctx, const char* uid128, int rank, int nranks);
+int hemo_comm_info(hemo_ctx* ctx, int* rank, int* nranks, int* nccl_version, int64_t* halo_updates,
+                   int64_t* allreduces);
+/* Halo plan (host arrays): for neighbour k = peers[k], the owned local nodes send_nodes[send_ptr[k] ..
+ * send_ptr[k+1]) are sent, and its values arrive in the ghost nodes n_owned + recv_ptr[k] .. n_owned +
+ * recv_ptr[k+1]) — both sides list the nodes in ascending global id.  ras_overlap = 1: the preconditioner
+ * input gets a ghost update too (overlapping restricted additive Schwarz, PCASM-like, :256-267). */
+int hemo_comm_set_partition(hemo_ctx* ctx, int n_owned, int nneigh, const int32_t* peers_host,
+                            const int32_t* send_ptr_host, const int32_t* send_nodes_host,
+                            const int32_t* recv_ptr_host, int ras_overlap);
+/* x.ghostUpdate(INSERT, FORWARD) of a local [u | p] vector (device). */
+int hemo_comm_halo_update(hemo_ctx* ctx, double* v_dev);
+/* comm.allreduce(SUM) of `count` doubles in place on the device (asynchronous on the stream). */
+int hemo_comm_allreduce(hemo_ctx* ctx, double* buf_dev, int count);
+/* VecDot of two local [u | p] vectors over the owned entries, summed over the ranks (plain dot
+ * product without a communicator); synchronises the stream. */
+int hemo_global_dot(hemo_ctx* ctx, const double* x_dev, const double* y_dev, double* out_host);
+/* Iterations between two looks at the device-side convergence flag of hemo_fgmres once the iteration
+ * count of the previous solve has been reached (default 2). */
+int hemo_set_poll_interval(hemo_ctx* ctx, int every);
+
 /* 1 (default): hemo_pc_setup captures one preconditioner application as a CUDA
  * graph (needs a non-default stream) and hemo_pc_apply replays it; 0: direct launches. */
 int hemo_use_graph(hemo_ctx* ctx, int on);
@@ -307,7 +339,10 @@ int hemo_pc_set_convection(hemo_ctx* ctx, const double* x_dev, const double* un_
 /* z = M^{-1} r (one application of the block preconditioner). */
 int hemo_pc_apply(hemo_ctx* ctx, const double* vals_dev, const double* r_dev, double* z_dev);
 /* KSPSolve: right-preconditioned FGMRES(restart) on J y = b with zero initial
- * guess (:226-229,272-273).  its_out/resid_out on host. */
+ * guess (:226-229,272-273).  Device-resident: Hessenberg column, Givens rotations, residual estimate and
+ * convergence flag live on the device, one iteration replays as one CUDA graph (non-default stream), the
+ * host looks at the flag when the iteration count of the previous solve is reached.  its_out/resid_out on
+ * host.  With a communicator (hemo_comm_init) b and y are local vectors; y returns with valid ghosts. */
 int hemo_fgmres(hemo_ctx* ctx, const double* vals_dev, const double* b_dev, double* y_dev,
                 int* its_out, double* rel_resid_out);
 

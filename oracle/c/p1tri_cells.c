@@ -69,7 +69,7 @@ static void eval_point(point_t* q, const cell_t* c, double xi, double eta, doubl
     const double t1 = c->h / (two_v >= eps0 ? two_v : eps0);
     const double t2 = dt / 2.0;
     const double t3 = (c->h * c->h) / (4.0 * nu);
-    q->tau = pow(1.0 / (t1 * t1) + 1.0 / (t2 * t2) + 1.0 / (t3 * t3), -0.5);
+    q->tau = 1.0 / sqrt(1.0 / (t1 * t1) + 1.0 / (t2 * t2) + 1.0 / (t3 * t3));   /* (...)**(-0.5), :100-108 */
     const double Re = (vnorm * c->h) / (2.0 * nu);
     const double z = (Re <= 3.0) ? Re / 3.0 : 1.0;
     q->tau_l = (vnorm * c->h * z) / 2.0;
@@ -113,35 +113,50 @@ void hemo_ref_cells(int E, const double* x, const int* cells, const double* h, c
             double dd[3][3];
             for (int a = 0; a < 3; ++a)
                 for (int b = 0; b < 3; ++b) dd[a][b] = c.g[a][0] * c.g[b][0] + c.g[a][1] * c.g[b][1];
-            for (int r = 2; r <= 5; ++r) {
-                for (int iq = 0; iq < nq[r]; ++iq) {
-                    eval_point(&q, &c, pts[r][2 * iq], pts[r][2 * iq + 1], wts[r][iq], dt, rho, mu, f, eps0);
-                    for (int a = 0; a < 3; ++a)
-                        for (int b = 0; b < 3; ++b) {
-                            if (r == 5) { A[(6 + a) * 9 + 6 + b] += q.w * q.tau / rho * dd[a][b]; continue; }
-                            if (r == 3) {
-                                for (int k = 0; k < 2; ++k)
-                                    A[(2 * a + k) * 9 + 6 + b] += q.w * (-q.phi[b] * c.g[a][k] + q.tau * q.umd[a] * c.g[b][k]);
-                                continue;
-                            }
+            /* one loop nest per block form (each has its own rule, stabilized_schur.py:188-189); point-only
+             * factors are hoisted out of the (a, b) loops the way FFCx hoists them */
+            for (int iq = 0; iq < nq[2]; ++iq) {               /* J_uu */
+                eval_point(&q, &c, pts[2][2 * iq], pts[2][2 * iq + 1], wts[2][iq], dt, rho, mu, f, eps0);
+                for (int b = 0; b < 3; ++b) {
+                    const double s = rho * (q.phi[b] / dt + 0.5 * q.umd[b]);
+                    double dR[2][2];                           /* dR[l][k] = d R_k / d u_(b,l) */
+                    for (int l = 0; l < 2; ++l)
+                        for (int k = 0; k < 2; ++k) dR[l][k] = s * (k == l) + 0.5 * rho * q.phi[b] * c.G[l][k];
+                    for (int a = 0; a < 3; ++a) {
+                        const double ta = q.phi[a] + q.tau * q.umd[a];
+                        for (int k = 0; k < 2; ++k)
                             for (int l = 0; l < 2; ++l) {
-                                double dR[2];
-                                for (int k = 0; k < 2; ++k)
-                                    dR[k] = rho * ((q.phi[b] / dt + 0.5 * q.umd[b]) * (k == l) + 0.5 * q.phi[b] * c.G[l][k]);
-                                if (r == 4) {
-                                    A[(6 + a) * 9 + 2 * b + l] += q.w * (0.5 * q.phi[a] * c.g[b][l] +
-                                        (q.tau / rho) * (dR[0] * c.g[a][0] + dR[1] * c.g[a][1]));
-                                } else {                     /* r == 2: J_uu */
-                                    for (int k = 0; k < 2; ++k) {
-                                        const double visc = 0.5 * mu * (dd[a][b] * (k == l) + c.g[a][l] * c.g[b][k]);
-                                        A[(2 * a + k) * 9 + 2 * b + l] += q.w * (q.phi[a] * dR[k] + visc +
-                                            q.tau * (q.umd[a] * dR[k] + 0.5 * q.R[k] * q.phi[b] * c.g[a][l]) +
-                                            0.5 * q.tau_l * rho * c.g[a][k] * c.g[b][l]);
-                                    }
-                                }
+                                const double visc = 0.5 * mu * (dd[a][b] * (k == l) + c.g[a][l] * c.g[b][k]);
+                                A[(2 * a + k) * 9 + 2 * b + l] += q.w * (ta * dR[l][k] + visc +
+                                    0.5 * q.tau * q.R[k] * q.phi[b] * c.g[a][l] + 0.5 * q.tau_l * rho * c.g[a][k] * c.g[b][l]);
                             }
-                        }
+                    }
                 }
+            }
+            for (int iq = 0; iq < nq[3]; ++iq) {               /* J_up */
+                eval_point(&q, &c, pts[3][2 * iq], pts[3][2 * iq + 1], wts[3][iq], dt, rho, mu, f, eps0);
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b)
+                        for (int k = 0; k < 2; ++k)
+                            A[(2 * a + k) * 9 + 6 + b] += q.w * (-q.phi[b] * c.g[a][k] + q.tau * q.umd[a] * c.g[b][k]);
+            }
+            for (int iq = 0; iq < nq[4]; ++iq) {               /* J_pu */
+                eval_point(&q, &c, pts[4][2 * iq], pts[4][2 * iq + 1], wts[4][iq], dt, rho, mu, f, eps0);
+                for (int b = 0; b < 3; ++b) {
+                    const double s = rho * (q.phi[b] / dt + 0.5 * q.umd[b]);
+                    for (int l = 0; l < 2; ++l) {
+                        const double dR0 = s * (l == 0) + 0.5 * rho * q.phi[b] * c.G[l][0];
+                        const double dR1 = s * (l == 1) + 0.5 * rho * q.phi[b] * c.G[l][1];
+                        for (int a = 0; a < 3; ++a)
+                            A[(6 + a) * 9 + 2 * b + l] += q.w * (0.5 * q.phi[a] * c.g[b][l] +
+                                (q.tau / rho) * (dR0 * c.g[a][0] + dR1 * c.g[a][1]));
+                    }
+                }
+            }
+            for (int iq = 0; iq < nq[5]; ++iq) {               /* J_pp */
+                eval_point(&q, &c, pts[5][2 * iq], pts[5][2 * iq + 1], wts[5][iq], dt, rho, mu, f, eps0);
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b) A[(6 + a) * 9 + 6 + b] += q.w * q.tau / rho * dd[a][b];
             }
         }
     }

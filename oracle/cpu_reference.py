@@ -152,3 +152,194 @@ class ReferenceLikeSolver:
     def step(self, x, un):
         x = O.remove_nullspace(self.prob, x)
         return self.newton(x, un)
+
+
+# =====================================================================================================
+# The same configuration on all host cores: C + OpenMP (oracle/c/ref_ksp.c), one thread per "MPI rank".
+# This is what bench.py times as the CPU arm (`--impl reference`, `cpu_baseline`).
+# =====================================================================================================
+import ctypes as _C
+import os as _os
+
+from . import build_c as _build_c
+from . import c_oracle as _CO
+
+_ksp_lib = None
+
+
+def _ksp():
+    global _ksp_lib
+    if _ksp_lib is None:
+        L = _C.CDLL(_build_c.build(which="ksp"))
+        L.refksp_create.restype = _C.c_void_p
+        L.refksp_create.argtypes = [_C.c_int, _C.c_int, _C.c_int, _C.c_int]
+        L.refksp_destroy.argtypes = [_C.c_void_p]
+        L.refksp_set_inner.argtypes = [_C.c_void_p, _C.c_int, _C.c_int, _C.c_double]
+        L.refksp_set_nullspace.argtypes = [_C.c_void_p, _C.c_int]
+        L.refksp_stats.argtypes = [_C.c_void_p, _C.c_void_p]
+        L.refksp_setup.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p]
+        L.refksp_solve.restype = _C.c_int
+        L.refksp_solve.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_double, _C.c_int, _C.c_void_p, _C.c_void_p]
+        L.ref_insert_matrix.argtypes = [_C.c_int64, _C.c_int, _C.c_void_p, _C.c_void_p, _C.c_int64, _C.c_void_p, _C.c_int]
+        L.ref_insert_vector.argtypes = [_C.c_int64, _C.c_int, _C.c_void_p, _C.c_void_p, _C.c_int64, _C.c_void_p, _C.c_int]
+        L.ref_cell_positions.argtypes = [_C.c_int64, _C.c_int, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_int]
+        _ksp_lib = L
+    return _ksp_lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_C.c_void_p)
+
+
+def block_pattern(nrowptr, ncol):
+    """CSR pattern create_matrix_block builds for [u interleaved (2n) | p (n)] from the sorted node graph
+    (stabilized_schur.py:191): every row of node i holds (2j, 2j+1) for its neighbours j, then 2n + j."""
+    nrowptr = np.asarray(nrowptr, dtype=np.int64)
+    ncol = np.asarray(ncol, dtype=np.int64)
+    n = nrowptr.shape[0] - 1
+    deg = np.diff(nrowptr)
+    nnz_node = int(nrowptr[-1])
+    rowlen = np.empty(3 * n, dtype=np.int64)
+    rowlen[0:2 * n:2] = 3 * deg
+    rowlen[1:2 * n:2] = 3 * deg
+    rowlen[2 * n:] = 3 * deg
+    rowptr = np.zeros(3 * n + 1, dtype=np.int64)
+    np.cumsum(rowlen, out=rowptr[1:])
+    colind = np.empty(9 * nnz_node, dtype=np.int32)
+    rows = np.repeat(np.arange(n, dtype=np.int64), deg)
+    t = np.arange(nnz_node, dtype=np.int64) - nrowptr[rows]
+    d = deg[rows]
+    for base in (6 * nrowptr[rows], 6 * nrowptr[rows] + 3 * d, 6 * nnz_node + 3 * nrowptr[rows]):
+        colind[base + 2 * t] = 2 * ncol
+        colind[base + 2 * t + 1] = 2 * ncol + 1
+        colind[base + 2 * d + t] = 2 * n + ncol
+    return rowptr, colind
+
+
+class CReferenceSolver:
+    """SNES newtonls + bt (oracle/ns_oracle.newton_solve) around the C restatement of
+    KSP fgmres(200) / fieldsplit Schur FULL + SELFP / gmres(30)+asm-ilu0 / preonly+asm-ilu0
+    (/root/reference/src/solvers/stabilized_schur.py:202-275).  P1 triangles.  `nranks` threads stand for the
+    MPI ranks of `mpirun -n nranks` (default: all cores).  The hemodynamic variants that ask for `lu` sub-solvers
+    (stabilized_schur_pressure_backflow.py:284-288) get the same asm/ilu(0) blocks here: PETSc's `lu` is sequential
+    (a parallel run needs an external package), and ILU(0) is the cheaper choice for the CPU arm."""
+
+    def __init__(self, prob: O.Problem, nranks: int | None = None, nullspace: bool | None = None,
+                 ksp_rtol: float = 1e-5, ksp_max_it: int = 1000, restart: int = 200, node_graph=None):
+        from cfd_hemodynamic_b200.fem import discretization as D
+        L = _ksp()
+        self.prob = prob
+        self.nranks = int(nranks or (_os.cpu_count() or 1))
+        n = prob.n
+        self.n = n
+        if prob.cells.shape[1] != 3:
+            raise NotImplementedError("the CPU arm is written for P1 triangles")
+        nrowptr, ncol = node_graph if node_graph is not None else D.node_graph(prob.cells, n)
+        self.rowptr, self.colind = block_pattern(nrowptr, ncol)
+        self.nnz = int(self.rowptr[-1])
+        self.vals = np.zeros(self.nnz)
+        self.l2g = np.ascontiguousarray(O.local_to_global(prob), dtype=np.int64)
+        E = prob.cells.shape[0]
+        self.pos = np.empty((E, 9, 9), dtype=np.int32)
+        L.ref_cell_positions(E, 9, _ptr(self.l2g), _ptr(self.rowptr), _ptr(self.colind), _ptr(self.pos), self.nranks)
+        assert (self.pos >= 0).all()
+        self.marker, self.g, self.mult = O.bc_arrays(prob)
+        if self.marker.any():
+            md = np.nonzero(self.marker)[0]
+            rows = np.concatenate([np.arange(self.rowptr[r], self.rowptr[r + 1]) for r in md])
+            cols = np.nonzero(self.marker[self.colind])[0]
+            self.zero_idx = np.unique(np.concatenate([rows, cols]))
+            self.diag_idx = np.array([self.rowptr[r] + np.searchsorted(self.colind[self.rowptr[r]:self.rowptr[r + 1]], r)
+                                      for r in md], dtype=np.int64)
+            self.diag_val = self.mult[md]
+        self.ksp = L.refksp_create(2 * n, n, self.nranks, restart)
+        self.ksp_rtol, self.ksp_max_it = ksp_rtol, ksp_max_it
+        self._nullspace = nullspace
+        self.timers = {"assembly": 0.0, "pc_setup": 0.0, "ksp": 0.0}
+        self.lin_its = 0
+        self.newton_its = 0
+
+    def close(self):
+        if self.ksp:
+            _ksp().refksp_destroy(self.ksp)
+            self.ksp = None
+
+    # --- assembly: C cell kernels on all cores, threaded insertion into the fixed pattern ---------
+    def J_raw_vals(self, u, p, un, out):
+        prob = self.prob
+        Ae, _ = _CO.element_tensors(prob, u, p, un, True, False)
+        _ksp().ref_insert_matrix(Ae.shape[0], 9, _ptr(Ae), _ptr(self.pos), self.nnz, _ptr(out), self.nranks)
+        for fs in prob.facet_sets:
+            ce = fs.pairs[:, 0]
+            Af = O.facet_matrices(prob, fs, un)                       # (m, 6, 9), boundary-sized
+            np.add.at(out, self.pos[ce][:, :6, :].reshape(-1), Af.reshape(-1))
+        return out
+
+    def J(self, u, p, un):
+        t0 = time.perf_counter()
+        self.J_raw_vals(u, p, un, self.vals)
+        if self.marker.any():
+            self.vals[self.zero_idx] = 0.0
+            self.vals[self.diag_idx] = self.diag_val
+        self.timers["assembly"] += time.perf_counter() - t0
+        A = sp.csr_matrix((self.vals, self.colind, self.rowptr), shape=(3 * self.n, 3 * self.n), copy=False)
+        return A
+
+    def F(self, x, un):
+        t0 = time.perf_counter()
+        prob = self.prob
+        n = self.n
+        u, p = x[:2 * n], x[2 * n:]
+        _, Fe = _CO.element_tensors(prob, u, p, un, False, True)
+        b = np.empty(3 * n)
+        _ksp().ref_insert_vector(Fe.shape[0], 9, _ptr(Fe), _ptr(self.l2g), 3 * n, _ptr(b), self.nranks)
+        if prob.facet_sets:
+            U, P, Un = O._gather(prob, u, p, un)
+            for fs in prob.facet_sets:
+                ce = fs.pairs[:, 0]
+                Fu_f = O.facet_F(prob, fs, U[ce], P[ce], Un[ce])
+                np.add.at(b, self.l2g[ce][:, :6].reshape(-1), Fu_f.reshape(-1))
+        if self.marker.any():
+            d = np.where(self.marker, self.g - x, 0.0)
+            if np.any(d != 0.0):
+                tmp = np.zeros(self.nnz)
+                self.J_raw_vals(u, p, un, tmp)
+                b = b + sp.csr_matrix((tmp, self.colind, self.rowptr), shape=(3 * n, 3 * n)) @ d
+            b[self.marker] = x[self.marker] - self.g[self.marker]
+        self.timers["assembly"] += time.perf_counter() - t0
+        return b
+
+    # --- KSPSolve -----------------------------------------------------------------------------------
+    def linear_solve(self, A, f):
+        L = _ksp()
+        if self._nullspace is None:
+            self._nullspace = bool(O.has_constant_pressure_nullspace(self.prob, A))
+        L.refksp_set_nullspace(self.ksp, int(self._nullspace))
+        t0 = time.perf_counter()
+        L.refksp_setup(self.ksp, _ptr(self.rowptr), _ptr(self.colind), _ptr(self.vals))
+        t1 = time.perf_counter()
+        y = np.empty(3 * self.n)
+        its = _C.c_int(0)
+        rel = _C.c_double(0.0)
+        f = np.ascontiguousarray(f)
+        rc = L.refksp_solve(self.ksp, _ptr(f), _ptr(y), self.ksp_rtol, self.ksp_max_it, _C.byref(its), _C.byref(rel))
+        self.timers["pc_setup"] += t1 - t0
+        self.timers["ksp"] += time.perf_counter() - t1
+        self.lin_its += its.value
+        if rc != 0:
+            raise RuntimeError(f"reference KSP did not converge in {its.value} iterations (rel. residual {rel.value:.2e})")
+        return y
+
+    def stats(self):
+        out = np.zeros(3, dtype=np.int64)
+        _ksp().refksp_stats(self.ksp, _ptr(out))
+        return dict(outer_its=int(out[0]), inner_its=int(out[1]), inner_solves=int(out[2]))
+
+    def step(self, x, un, rtol=1e-8, stol=1e-8):
+        """solveStep (stabilized_schur.py:313-334): nullsp.remove(x_n) then SNES.solve."""
+        x = O.remove_nullspace(self.prob, x)
+        x, its, reason = O.newton_solve(self.prob, x, un, rtol=rtol, stol=stol, asm=self, linear_solve=self.linear_solve)
+        self.newton_its += its
+        if reason < 0:
+            raise RuntimeError(f"Did not converge, reason: {reason}.")
+        return x

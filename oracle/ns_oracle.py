@@ -263,8 +263,7 @@ def facet_F(prob, fs: FacetSet, U, P, Un):
     cells = prob.cells[fs.pairs[:, 0]]
     lf = fs.pairs[:, 1]
     X = prob.x[cells]                                   # (m,3,2)
-    det, dphi_all = cell_geometry(prob.x, prob.cells)
-    dphi = dphi_all[fs.pairs[:, 0]]
+    _, dphi = cell_geometry(prob.x, cells)               # boundary cells only
     h = prob.h[fs.pairs[:, 0]]
     m = cells.shape[0]
     ar = np.arange(m)
@@ -537,10 +536,12 @@ def has_constant_pressure_nullspace(prob, A, tol=1e-8):
 
 
 def newton_solve(prob, x0, un, rtol=1e-8, atol=1e-50, stol=1e-8, max_it=100,
-                 verbose=False, asm=None):
+                 verbose=False, asm=None, linear_solve=None):
     """One SNES.solve (stabilized_schur.py:321) with an exact (sparse LU)
     linear solve.  Returns (x, iterations, reason>0 converged).  `asm`: optional
-    assembler object with J(u, p, un) / F(x, un) (oracle/c_oracle.FastAssembler)."""
+    assembler object with J(u, p, un) / F(x, un) (oracle/c_oracle.FastAssembler).
+    `linear_solve(A, f) -> y`: optional replacement of the sparse-LU solve (oracle/cpu_reference.py
+    plugs in the restated FGMRES + fieldsplit configuration of the reference)."""
     n = prob.n
     x = x0.copy()
     _F = (lambda xx: asm.F(xx, un)) if asm is not None else (lambda xx: assemble_F(prob, xx, un))
@@ -555,8 +556,10 @@ def newton_solve(prob, x0, un, rtol=1e-8, atol=1e-50, stol=1e-8, max_it=100,
         return x, 0, 2
     for it in range(max_it):
         A = _J(x)
-        singular = has_constant_pressure_nullspace(prob, A)
-        if singular:
+        singular = linear_solve is None and has_constant_pressure_nullspace(prob, A)
+        if linear_solve is not None:
+            y = linear_solve(A, f)
+        elif singular:
             # pin through a bordered system: solve in the orthogonal complement
             e = np.zeros(prob.ndof); e[2 * n:] = 1.0 / np.sqrt(n)
             B = sp.bmat([[A, sp.csr_matrix(e[:, None])], [sp.csr_matrix(e[None, :]), None]]).tocsc()
