@@ -110,6 +110,8 @@ SYMBOLS = {
     "hemo_comm_init": (_I, [_VP, C.c_char_p, _I, _I]),
     "hemo_comm_info": (_I, [_VP, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L), C.POINTER(_L)]),
     "hemo_comm_set_partition": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _I]),
+    "hemo_set_graph": (_I, [_VP, _I, _VP, _VP, _L]),
+    "hemo_pc_set_coarse_pressure": (_I, [_VP, _VP, _I] + [_VP] * 6 + [_I]),
     "hemo_comm_halo_update": (_I, [_VP, _VP]),
     "hemo_comm_allreduce": (_I, [_VP, _VP, _I]),
     "hemo_global_dot": (_I, [_VP, _VP, _VP, C.POINTER(_D)]),
@@ -483,6 +485,27 @@ class Hemo:
         self._check(self.lib.hemo_comm_set_partition(self._ctx, int(n_owned), int(peers.shape[0]), hp(peers), hp(send_ptr),
                                                      hp(send_nodes), hp(recv_ptr), int(bool(ras_overlap))),
                     "hemo_comm_set_partition")
+
+    def set_graph(self, rowptr, col):
+        """Mesh-less context carrying a scalar operator on the graph (rowptr, col) (device int32 tensors, kept alive)."""
+        self._keep["graph"] = (rowptr, col)
+        self.n = int(rowptr.numel() - 1)
+        self.nnz_node = int(col.numel())
+        self._check(self.lib.hemo_set_graph(self._ctx, self.n, _ptr(rowptr), _ptr(col), self.nnz_node), "hemo_set_graph")
+
+    def pc_set_coarse_pressure(self, coarse, P0, R0, cycles=1):
+        """coarse: Hemo context with the replicated coarse hierarchy (None removes); P0 / R0: scipy CSR."""
+        if coarse is None:
+            self._check(self.lib.hemo_pc_set_coarse_pressure(self._ctx, None, 0, *([None] * 6), 1), "hemo_pc_set_coarse_pressure")
+            return
+        arrs = []
+        for A in (P0, R0):
+            arrs += [np.ascontiguousarray(A.indptr, dtype=np.int32), np.ascontiguousarray(A.indices, dtype=np.int32),
+                     np.ascontiguousarray(A.data, dtype=np.float64)]
+        hp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._coarse = coarse
+        self._check(self.lib.hemo_pc_set_coarse_pressure(self._ctx, coarse._ctx, int(P0.shape[1]), *[hp(a) for a in arrs],
+                                                         int(cycles)), "hemo_pc_set_coarse_pressure")
 
     def halo_update(self, v):
         self._check(self.lib.hemo_comm_halo_update(self._ctx, _ptr(v)), "hemo_comm_halo_update")

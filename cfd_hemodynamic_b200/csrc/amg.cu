@@ -10,6 +10,7 @@
 // mesh graph and are built once by the host; what runs here every Newton
 // iteration is the numeric Galerkin product R*A*P on fixed patterns, the
 // smoother set-up, and the cycles.
+#include <cooperative_groups.h>
 #include <cub/device/device_scan.cuh>
 
 #include "hemo_internal.cuh"
@@ -439,15 +440,34 @@ k_transfer(int nrows, const int32_t* __restrict__ rowptr, const int32_t* __restr
 }
 
 // ---------------------------------------------------------------------------
-// fused coarse V-cycle: all levels with n <= HEMO_FUSE_MAX_NODES run inside one
-// CTA (phases separated by __syncthreads), replacing ~10 launches per level.
+// fused coarse V-cycle: every level from `fuse_level` down runs inside ONE kernel, phases separated by a
+// barrier, replacing ~7 launches per level.  Two scopes share the code:
+//   GridScope — a persistent cooperative grid (one CTA per SM, cooperative_groups grid.sync between phases):
+//               the levels below the finest are a few thousand rows each, far too small to fill the GPU from
+//               separate launches (each costs 5-10 us of launch + drain), but still too large for one CTA;
+//   CtaScope  — one CTA with __syncthreads (fallback when a cooperative launch is not possible).
 // ---------------------------------------------------------------------------
-// Row loops of the fused kernel: 8 lanes cooperate on one block row (coarse Galerkin rows hold
-// 20-60 blocks; a thread-serial walk makes every phase a ~50-deep dependent load chain).  All
-// lanes of a warp execute the same number of outer iterations, so full-mask shuffles are legal.
-template <int BS, typename Epi>
-__device__ __forceinline__ void rows_matvec(const HemoCoarseLevel& L, const areal* __restrict__ x, Epi epi) {
-    const int lane = threadIdx.x & 7, group = threadIdx.x >> 3, ngroups = blockDim.x >> 3;
+namespace cg = cooperative_groups;
+
+struct CtaScope {
+    __device__ __forceinline__ int tid() const { return threadIdx.x; }
+    __device__ __forceinline__ int nthreads() const { return blockDim.x; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+struct GridScope {
+    cg::grid_group g;
+    __device__ __forceinline__ GridScope() : g(cg::this_grid()) {}
+    __device__ __forceinline__ int tid() const { return blockIdx.x * blockDim.x + threadIdx.x; }
+    __device__ __forceinline__ int nthreads() const { return gridDim.x * blockDim.x; }
+    __device__ __forceinline__ void sync() const { g.sync(); }
+};
+
+// Row loops: 8 lanes cooperate on one block row (coarse Galerkin rows hold 20-60 blocks; a thread-serial
+// walk makes every phase a ~50-deep dependent load chain).  All lanes of a warp execute the same number of
+// outer iterations, so full-mask shuffles are legal.
+template <int BS, typename Scope, typename Epi>
+__device__ __forceinline__ void rows_matvec(const Scope& sc, const HemoCoarseLevel& L, const areal* __restrict__ x, Epi epi) {
+    const int lane = sc.tid() & 7, group = sc.tid() >> 3, ngroups = sc.nthreads() >> 3;
     for (int base = 0; base < L.n; base += ngroups) {
         const int i = base + group;
         const bool ok = i < L.n;
@@ -476,10 +496,11 @@ __device__ __forceinline__ void rows_matvec(const HemoCoarseLevel& L, const area
 }
 
 // y-rows of a transfer operator (CSR with fp64 weights) applied to a BS-component vector
-template <int BS, typename Epi>
-__device__ __forceinline__ void rows_transfer(int nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                              const double* __restrict__ w, const areal* __restrict__ x, Epi epi) {
-    const int lane = threadIdx.x & 7, group = threadIdx.x >> 3, ngroups = blockDim.x >> 3;
+template <int BS, typename Scope, typename Epi>
+__device__ __forceinline__ void rows_transfer(const Scope& sc, int nrows, const int32_t* __restrict__ rowptr,
+                                              const int32_t* __restrict__ col, const double* __restrict__ w,
+                                              const areal* __restrict__ x, Epi epi) {
+    const int lane = sc.tid() & 7, group = sc.tid() >> 3, ngroups = sc.nthreads() >> 3;
     for (int base = 0; base < nrows; base += ngroups) {
         const int i = base + group;
         const bool ok = i < nrows;
@@ -505,10 +526,10 @@ __device__ __forceinline__ void rows_transfer(int nrows, const int32_t* __restri
     }
 }
 
-template <int BS>
-__device__ void fused_smooth(const HemoCoarseLevel& L, const areal* __restrict__ b, areal* __restrict__ x,
+template <int BS, typename Scope>
+__device__ void fused_smooth(const Scope& sc, const HemoCoarseLevel& L, const areal* __restrict__ b, areal* __restrict__ x,
                              bool x_is_zero, int degree, double ratio) {
-    const int tid = threadIdx.x, T = blockDim.x;
+    const int tid = sc.tid(), T = sc.nthreads();
     const int N = L.n * BS;
     const double lmax = *L.lmax, lmin = lmax / ratio;
     const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
@@ -523,7 +544,7 @@ __device__ void fused_smooth(const HemoCoarseLevel& L, const areal* __restrict__
             x[q] = (areal)(rv / theta);
         }
     } else {
-        rows_matvec<BS>(L, x, [&](int i, const double* acc) {
+        rows_matvec<BS>(sc, L, x, [&](int i, const double* acc) {
 #pragma unroll
             for (int k = 0; k < BS; ++k) {
                 const int q = i * BS + k;
@@ -533,7 +554,7 @@ __device__ void fused_smooth(const HemoCoarseLevel& L, const areal* __restrict__
             }
         });
     }
-    __syncthreads();
+    sc.sync();
     bool pending = !x_is_zero;
     for (int s = 1; s < degree; ++s) {
         const double rho_new = 1.0 / (2.0 * sigma - rho);
@@ -541,7 +562,7 @@ __device__ void fused_smooth(const HemoCoarseLevel& L, const areal* __restrict__
         const areal* dcur = dold;
         areal* dnext = dnew;
         const bool add_old = pending;
-        rows_matvec<BS>(L, dcur, [&](int i, const double* acc) {
+        rows_matvec<BS>(sc, L, dcur, [&](int i, const double* acc) {
 #pragma unroll
             for (int k = 0; k < BS; ++k) {
                 const int q = i * BS + k;
@@ -552,39 +573,40 @@ __device__ void fused_smooth(const HemoCoarseLevel& L, const areal* __restrict__
                 x[q] = (areal)((double)x[q] + (add_old ? (dv + (double)dcur[q]) : dv));
             }
         });
-        __syncthreads();
+        sc.sync();
         pending = false;
         areal* t = dold; dold = dnew; dnew = t;
         rho = rho_new;
     }
     if (pending) {
         for (int q = tid; q < N; q += T) x[q] = (areal)((double)x[q] + (double)dold[q]);
-        __syncthreads();
+        sc.sync();
     }
 }
 
-template <int BS>
-__global__ void __launch_bounds__(1024)
-k_coarse_vcycle(const HemoCoarseLevel* __restrict__ desc, int nl, const areal* __restrict__ b0, areal* __restrict__ x0,
-                int degree, double ratio, const double* __restrict__ dense_inv, int dense_n) {
-    const int tid = threadIdx.x, T = blockDim.x;
+template <int BS, typename Scope>
+__device__ void coarse_vcycle_body(const Scope& sc, const HemoCoarseLevel* __restrict__ desc, int nl,
+                                   const areal* __restrict__ b0, areal* __restrict__ x0, int degree_pre, int degree,
+                                   double ratio, const double* __restrict__ dense_inv, int dense_n) {
+    const int tid = sc.tid(), T = sc.nthreads();
     // down sweep
     for (int l = 0; l + 1 < nl; ++l) {
         const HemoCoarseLevel L = desc[l];
         const areal* b = (l == 0) ? b0 : L.b;
         areal* x = (l == 0) ? x0 : L.x;
-        fused_smooth<BS>(L, b, x, true, degree, ratio);
-        rows_matvec<BS>(L, x, [&](int i, const double* acc) {
+        // the levels small enough for one CTA keep the stronger pre-smoother they have always had
+        fused_smooth<BS>(sc, L, b, x, true, L.n <= HEMO_FUSE_MAX_NODES ? degree : degree_pre, ratio);
+        rows_matvec<BS>(sc, L, x, [&](int i, const double* acc) {
 #pragma unroll
             for (int k = 0; k < BS; ++k) L.r[i * BS + k] = (areal)((double)b[i * BS + k] - acc[k]);
         });
-        __syncthreads();
+        sc.sync();
         areal* bc = desc[l + 1].b;
-        rows_transfer<BS>(L.nc, L.r_rowptr, L.r_col, L.r_val, L.r, [&](int I, const double* acc) {
+        rows_transfer<BS>(sc, L.nc, L.r_rowptr, L.r_col, L.r_val, L.r, [&](int I, const double* acc) {
 #pragma unroll
             for (int k = 0; k < BS; ++k) bc[I * BS + k] = (areal)acc[k];
         });
-        __syncthreads();
+        sc.sync();
     }
     // coarsest: dense inverse, 8 lanes per row
     {
@@ -602,7 +624,7 @@ k_coarse_vcycle(const HemoCoarseLevel* __restrict__ desc, int nl, const areal* _
             acc += __shfl_xor_sync(0xffffffffu, acc, 4, 8);
             if (ok && lane == 0) x[row] = (areal)acc;
         }
-        __syncthreads();
+        sc.sync();
     }
     // up sweep
     for (int l = nl - 2; l >= 0; --l) {
@@ -610,13 +632,29 @@ k_coarse_vcycle(const HemoCoarseLevel* __restrict__ desc, int nl, const areal* _
         const areal* b = (l == 0) ? b0 : L.b;
         areal* x = (l == 0) ? x0 : L.x;
         const areal* xc = desc[l + 1].x;
-        rows_transfer<BS>(L.n, L.p_rowptr, L.p_col, L.p_val, xc, [&](int i, const double* acc) {
+        rows_transfer<BS>(sc, L.n, L.p_rowptr, L.p_col, L.p_val, xc, [&](int i, const double* acc) {
 #pragma unroll
             for (int k = 0; k < BS; ++k) x[i * BS + k] = (areal)((double)x[i * BS + k] + acc[k]);
         });
-        __syncthreads();
-        fused_smooth<BS>(L, b, x, false, degree, ratio);
+        sc.sync();
+        fused_smooth<BS>(sc, L, b, x, false, degree, ratio);
     }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(1024)
+k_coarse_vcycle(const HemoCoarseLevel* __restrict__ desc, int nl, const areal* __restrict__ b0, areal* __restrict__ x0,
+                int degree_pre, int degree, double ratio, const double* __restrict__ dense_inv, int dense_n) {
+    CtaScope sc;
+    coarse_vcycle_body<BS>(sc, desc, nl, b0, x0, degree_pre, degree, ratio, dense_inv, dense_n);
+}
+
+template <int BS>
+__global__ void __launch_bounds__(512)
+k_coarse_vcycle_grid(const HemoCoarseLevel* __restrict__ desc, int nl, const areal* __restrict__ b0, areal* __restrict__ x0,
+                     int degree_pre, int degree, double ratio, const double* __restrict__ dense_inv, int dense_n) {
+    GridScope sc;
+    coarse_vcycle_body<BS>(sc, desc, nl, b0, x0, degree_pre, degree, ratio, dense_inv, dense_n);
 }
 
 // ---------------------------------------------------------------------------
@@ -717,7 +755,8 @@ void hemo_amg_free(HemoAmg* amg) {
     cudaFree(amg->fine_rowptr); cudaFree(amg->fine_col); cudaFree(amg->fine_rowof);
     amg->fine_rowptr = amg->fine_col = amg->fine_rowof = nullptr; amg->fine_nnz = 0;
     cudaFree(amg->dense_inv); cudaFree(amg->dense_work); cudaFree(amg->fuse_desc); cudaFree(amg->lmax_dev);
-    amg->fuse_desc = nullptr; amg->lmax_dev = nullptr; amg->fuse_level = -1;
+    amg->fuse_desc = nullptr; amg->lmax_dev = nullptr; amg->fuse_level = amg->fuse_level_grid = amg->fuse_base = -1;
+    amg->grid_blocks = 0;
     amg->dense_inv = amg->dense_work = nullptr;
     amg->nlev = 0;
     amg->ready = false;
@@ -831,13 +870,34 @@ extern "C" int hemo_amg_finalize(hemo_ctx* ctx, int which, int n_levels) {
                                      L.c_col, L.nnz_c, &L.c_seg_ptr, &L.c_seg_src))) return rc;
         }
     }
-    // levels small enough for the single-CTA fused cycle
-    amg.fuse_level = -1;
+    // levels handled by the fused kernels: from `fuse_level_grid` down by the cooperative persistent grid, from
+    // `fuse_level` (<= HEMO_FUSE_MAX_NODES nodes) down by one CTA when a cooperative launch is not possible
+    amg.fuse_level = amg.fuse_level_grid = -1;
     for (int l = 0; l < n_levels; ++l)
         if (amg.op[l].n <= HEMO_FUSE_MAX_NODES) { amg.fuse_level = l; break; }
-    if (amg.fuse_level >= 0) {
+    {
+        int coop = 0, sms = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        const char* env = getenv("HEMO_GRID_FUSE_MAX");
+        const int cap = env ? atoi(env) : HEMO_GRID_FUSE_MAX_NODES;
+        amg.grid_blocks = 0;
+        if (coop && sms > 0 && cap > 0) {
+            int occ = 0;
+            if (bs == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_coarse_vcycle_grid<2>, 512, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_coarse_vcycle_grid<1>, 512, 0);
+            if (occ >= 1) {
+                amg.grid_blocks = sms;
+                for (int l = 1; l < n_levels; ++l)
+                    if (amg.op[l].n <= cap) { amg.fuse_level_grid = l; break; }
+            }
+        }
+        cudaGetLastError();
+    }
+    amg.fuse_base = amg.fuse_level_grid >= 0 ? amg.fuse_level_grid : amg.fuse_level;
+    if (amg.fuse_base >= 0) {
         std::vector<HemoCoarseLevel> d;
-        for (int l = amg.fuse_level; l < n_levels; ++l) {
+        for (int l = amg.fuse_base; l < n_levels; ++l) {
             const HemoAmgOp& o = amg.op[l];
             HemoCoarseLevel c{};
             c.n = o.n; c.rowptr = o.rowptr; c.col = o.col; c.val = o.val; c.dinv = o.dinv;
@@ -979,10 +1039,28 @@ static int vcycle_t(hemo_ctx* ctx, HemoAmg* amg, int l, const areal* b, areal* x
     const int degree = ctx->opts.cheb_degree > 0 ? ctx->opts.cheb_degree : 2;
     const int degree_pre = ctx->opts.cheb_degree_pre > 0 ? ctx->opts.cheb_degree_pre : degree;
     const double ratio = ctx->opts.cheb_ratio > 1.0 ? ctx->opts.cheb_ratio : 4.0;
+    if (l == amg->fuse_level_grid && amg->grid_blocks > 0) {
+        // every remaining level inside one persistent cooperative kernel
+        const HemoCoarseLevel* desc = amg->fuse_desc + (l - amg->fuse_base);
+        int nl = amg->nlev - l, dp = degree_pre, dg = degree, dn = amg->dense_n;
+        double rt = ratio;
+        const double* dinv = amg->dense_inv;
+        void* args[] = {(void*)&desc, (void*)&nl, (void*)&b, (void*)&x, (void*)&dp, (void*)&dg, (void*)&rt, (void*)&dinv, (void*)&dn};
+        const void* fn = (BS == 2) ? (const void*)k_coarse_vcycle_grid<2> : (const void*)k_coarse_vcycle_grid<1>;
+        cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(amg->grid_blocks), dim3(512), args, 0, st);
+        if (e == cudaSuccess) {
+            ctx->launches++;
+            return 0;
+        }
+        cudaGetLastError();
+        // not available here (or not capturable): per-level kernels + the one-CTA tail from now on
+        ctx->amg[0].grid_blocks = ctx->amg[1].grid_blocks = 0;
+        if (ctx->capturing) HEMO_FAIL(ctx, HEMO_ERETRY, "cooperative launch not capturable: capture is repeated without it");
+    }
     if (l == amg->fuse_level) {
         // every remaining level fits one CTA
-        k_coarse_vcycle<BS><<<1, 1024, 0, st>>>(amg->fuse_desc, amg->nlev - l, b, x, degree, ratio, amg->dense_inv,
-                                                amg->dense_n);
+        k_coarse_vcycle<BS><<<1, 1024, 0, st>>>(amg->fuse_desc + (l - amg->fuse_base), amg->nlev - l, b, x, degree_pre, degree, ratio,
+                                                amg->dense_inv, amg->dense_n);
         HEMO_LAUNCH_CHECK(ctx);
         return 0;
     }

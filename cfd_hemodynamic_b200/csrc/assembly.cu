@@ -950,6 +950,24 @@ extern "C" int hemo_set_mesh(hemo_ctx* ctx, const double* x_dev, int n_nodes, co
     return 0;
 }
 
+// A context that only carries a scalar operator on an abstract graph (no mesh): the replicated coarse space of the
+// multi-GPU pressure preconditioner.  Only the pressure-hierarchy entry points work on it.
+extern "C" int hemo_set_graph(hemo_ctx* ctx, int n, const int32_t* rowptr_dev, const int32_t* col_dev, int64_t nnz) {
+    if (!ctx || n <= 0 || !rowptr_dev || !col_dev || nnz <= 0 || nnz >= ((int64_t)1 << 31)) return HEMO_EINVAL;
+    if (ctx->n != n) hemo_drop_solver_state(ctx);
+    ctx->x = nullptr; ctx->cells = nullptr; ctx->h = nullptr; ctx->E = 0;
+    ctx->n = n;
+    ctx->nrowptr = rowptr_dev; ctx->ncol = col_dev; ctx->nnz_node = nnz;
+    ctx->have_bc = false;
+    int rc;
+    if ((rc = hemo_alloc(ctx, &ctx->rowof, (size_t)nnz))) return rc;
+    if ((rc = hemo_alloc(ctx, &ctx->diagslot, (size_t)n))) return rc;
+    HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->diagslot, 0xff, sizeof(int32_t) * n, ctx->stream));
+    k_rowof<<<hemo_grid(n, 256), 256, 0, ctx->stream>>>(n, rowptr_dev, ctx->rowof, col_dev, ctx->diagslot);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 extern "C" int hemo_set_node_graph(hemo_ctx* ctx, const int32_t* nrowptr_dev, const int32_t* ncol_dev,
                                    int64_t nnz_node) {
     if (!ctx || !nrowptr_dev || !ncol_dev || nnz_node <= 0) return HEMO_EINVAL;

@@ -28,6 +28,8 @@ typedef float areal;
 typedef float2 areal2;
 #endif
 
+#define HEMO_ERETRY (-3)      // internal: a stream capture has to be repeated (never returned through the C ABI)
+
 struct HemoRule {
     int nq;
     int alias;                // lowest block id with an identical rule
@@ -80,6 +82,10 @@ struct HemoCoarseLevel {
 };
 
 #define HEMO_FUSE_MAX_NODES 256    // levels at or below this size run inside one CTA
+// Levels (below the finest) at or below this size run inside the cooperative persistent-grid kernel.  0 = off, the
+// default: measured on a B200 (lid cavity 707^2) the grid.sync between the ~40 phases costs more than the graph-
+// scheduled per-level launches it replaces (36.9 vs 29.7 ms per time step); HEMO_GRID_FUSE_MAX=<nodes> turns it on.
+#define HEMO_GRID_FUSE_MAX_NODES 0
 
 struct HemoAmg {
     // cached CUDA graph of hemo_amg_apply(b, x, ncycles) (replicated global pressure solve)
@@ -92,7 +98,10 @@ struct HemoAmg {
     // optional level-0 pattern that differs from the mesh node graph (SELFP: distance-2 graph)
     int32_t *fine_rowptr = nullptr, *fine_col = nullptr, *fine_rowof = nullptr;
     int64_t fine_nnz = 0;
-    int fuse_level = -1;           // first level handled by the fused kernel (-1: none)
+    int fuse_level = -1;           // first level handled by the one-CTA fused kernel (-1: none)
+    int fuse_level_grid = -1;      // first level handled by the cooperative persistent-grid kernel (-1: none)
+    int fuse_base = -1;            // level of fuse_desc[0]
+    int grid_blocks = 0;           // CTAs of the cooperative kernel (one per SM); 0: cooperative launch unavailable
     HemoCoarseLevel* fuse_desc = nullptr;   // device array, one per level from fuse_level
     double* lmax_dev = nullptr;    // HEMO_MAX_LEVELS Gershgorin bounds kept on the device
     int bs = 1;
@@ -129,7 +138,7 @@ struct HemoKrylov {
     double* state = nullptr;        // FgState + scalars (64 doubles)
     double* state_host = nullptr;   // pinned copy
     int last_its = 0;               // iterations of the previous solve (first poll)
-    int poll_every = 2;
+    int poll_every = 1;
     int64_t polls = 0;
     // owned entries of a local vector (multi-GPU): [0, seg_len0) and [seg_off1, seg_off1 + seg_len1); 0 = all
     int64_t seg_len0 = 0, seg_off1 = 0, seg_len1 = 0;
@@ -227,6 +236,14 @@ struct hemo_ctx {
     int kry_restart = 0;
     HemoKrylov kry;
     // multi-GPU (comm.cu): null = single GPU
+    // coarse space of the two-level Schwarz pressure solve (hemo_pc_set_coarse_pressure): replicated hierarchy in
+    // another context, P0 rows of the local nodes, R0 = P0^T restricted to the owned nodes
+    hemo_ctx* coarse_ctx = nullptr;
+    int coarse_n = 0;
+    int32_t *cp_rowptr = nullptr, *cp_col = nullptr; double* cp_val = nullptr;     // P0: n x coarse_n
+    int32_t *cr_rowptr = nullptr, *cr_col = nullptr; double* cr_val = nullptr;     // R0: coarse_n x n (owned columns)
+    double *coarse_rhs = nullptr, *coarse_sol = nullptr;
+    int coarse_cycles = 1;
     HemoComm* comm = nullptr;
     int comm_ras_overlap = 0;       // 1: the preconditioner input needs valid ghost values (overlapping Schwarz)
 };

@@ -196,21 +196,24 @@ k_fg_store(const FgState* __restrict__ st, int64_t n, const double* __restrict__
     }
 }
 
-// h_i = s_i (V_i . w), i <= j  (VecMDot): w tile held in registers, V streamed once; the last block sums the
-// per-block partials in a fixed order (bitwise reproducible)
+// h_i = s_i (V_i . w), i <= j  (VecMDot): the w tile is held in registers and V streamed once, four basis vectors
+// in flight per pass; partial sums go warp -> per-warp shared accumulators (no block barrier inside the loop) ->
+// one partial per block and vector.  k_fg_mdot_final sums the partials in a fixed order (bitwise reproducible).
+template <bool SEG>
 __global__ void __launch_bounds__(FG_THREADS)
-k_fg_mdot(FgState* st, FgSeg seg, const double* __restrict__ V, int64_t ldv, const double* __restrict__ scale,
-          double* __restrict__ partial /*[m+1][gridDim.x]*/, double* __restrict__ hcol) {
-    __shared__ double sh[32];
-    extern __shared__ double acc_sh[];
+k_fg_mdot(const FgState* __restrict__ st, FgSeg seg, const double* __restrict__ V, int64_t ldv,
+          double* __restrict__ partial /*[m+1][gridDim.x]*/, int kpad) {
+    extern __shared__ double acc_sh[];       // (FG_THREADS / 32) x kpad
     if (st->converged || st->cycle_full) return;
     const int j = st->j, k = j + 1;
     const double* w = V + (int64_t)k * ldv;
     const int64_t n = seg.len0 + seg.len1;
     const int64_t tile = (int64_t)FG_THREADS * FG_TILE;
     const int64_t ntiles = (n + tile - 1) / tile;
-    for (int i = threadIdx.x; i < k; i += blockDim.x) acc_sh[i] = 0.0;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = FG_THREADS / 32;
+    for (int i = threadIdx.x; i < nw * kpad; i += blockDim.x) acc_sh[i] = 0.0;
     __syncthreads();
+    double* acc = acc_sh + wid * kpad;
     for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
         const int64_t base = tl * tile + threadIdx.x;
         double wr[FG_TILE];
@@ -218,61 +221,107 @@ k_fg_mdot(FgState* st, FgSeg seg, const double* __restrict__ V, int64_t ldv, con
 #pragma unroll
         for (int e = 0; e < FG_TILE; ++e) {
             const int64_t idx = base + (int64_t)e * FG_THREADS;
-            qi[e] = idx < n ? seg_index(seg, idx) : -1;
-            wr[e] = idx < n ? w[qi[e]] : 0.0;
+            const bool ok = idx < n;
+            qi[e] = ok ? (SEG ? seg_index(seg, idx) : idx) : 0;
+            wr[e] = ok ? w[qi[e]] : 0.0;          // out-of-range lanes multiply entry 0 by zero
         }
-        for (int i = 0; i < k; ++i) {
-            const double* Vi = V + (int64_t)i * ldv;
-            double a = 0.0;
+        for (int i = 0; i < k; i += 4) {
+            const double* V0 = V + (int64_t)i * ldv;
+            const double* V1 = V + (int64_t)min(i + 1, k - 1) * ldv;
+            const double* V2 = V + (int64_t)min(i + 2, k - 1) * ldv;
+            const double* V3 = V + (int64_t)min(i + 3, k - 1) * ldv;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-            for (int e = 0; e < FG_TILE; ++e)
-                if (qi[e] >= 0) a = fma(Vi[qi[e]], wr[e], a);
-            a = fg_block_sum(a, sh);
-            if (threadIdx.x == 0) acc_sh[i] += a;
+            for (int e = 0; e < FG_TILE; ++e) {
+                a0 = fma(V0[qi[e]], wr[e], a0);
+                a1 = fma(V1[qi[e]], wr[e], a1);
+                a2 = fma(V2[qi[e]], wr[e], a2);
+                a3 = fma(V3[qi[e]], wr[e], a3);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a0 += __shfl_down_sync(0xffffffffu, a0, o);
+                a1 += __shfl_down_sync(0xffffffffu, a1, o);
+                a2 += __shfl_down_sync(0xffffffffu, a2, o);
+                a3 += __shfl_down_sync(0xffffffffu, a3, o);
+            }
+            if (lane == 0) {
+                acc[i] += a0;
+                if (i + 1 < k) acc[i + 1] += a1;
+                if (i + 2 < k) acc[i + 2] += a2;
+                if (i + 3 < k) acc[i + 3] += a3;
+            }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < k; i += blockDim.x) partial[(int64_t)i * gridDim.x + blockIdx.x] = acc_sh[i];
-    if (!fg_last_block(&st->ticket_mdot)) return;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int i = wid; i < k; i += nw) {
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
         double s = 0.0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) s += partial[(int64_t)i * gridDim.x + b];
-        s = fg_warp_sum(s);
-        if (lane == 0) hcol[i] = scale[i] * s;
+#pragma unroll
+        for (int q = 0; q < nw; ++q) s += acc_sh[q * kpad + i];
+        partial[(int64_t)i * gridDim.x + blockIdx.x] = s;
     }
 }
 
-// Givens update of column j from h (hcol[0..j]) and hn: one thread
+// one block per basis vector (blocks beyond the current column leave at once: the grid is fixed for the graph)
+__global__ void __launch_bounds__(128)
+k_fg_mdot_final(const FgState* __restrict__ st, int nblk, const double* __restrict__ partial,
+                const double* __restrict__ scale, double* __restrict__ hcol) {
+    __shared__ double sh[32];
+    if (st->converged || st->cycle_full) return;
+    const int i = blockIdx.x;
+    if (i > st->j) return;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) s += partial[(int64_t)i * nblk + b];
+    s = fg_block_sum(s, sh);
+    if (threadIdx.x == 0) hcol[i] = scale[i] * s;
+}
+
+// Givens update of column j from h (hcol[0..j]) and hn.  Called by a whole block: the previous rotations and the
+// column are staged in shared memory by all threads (one coalesced pass), then thread 0 runs the dependent chain out
+// of shared memory (a chain of global loads would cost one L2 round trip per rotation).
 __device__ void fg_givens(FgState* st, int m, const double* __restrict__ hcol, double hn, double* __restrict__ H,
                           double* __restrict__ cs, double* __restrict__ sn, double* __restrict__ g,
-                          double* __restrict__ scale) {
+                          double* __restrict__ scale, double* __restrict__ smem /* 3 (m + 2) */) {
     const int j = st->j;
-    double* Hj = H + (int64_t)j * (m + 1);
-    for (int i = 0; i <= j; ++i) Hj[i] = hcol[i];
-    Hj[j + 1] = hn;
-    for (int i = 0; i < j; ++i) {
-        const double a = Hj[i], b = Hj[i + 1];
-        Hj[i] = cs[i] * a + sn[i] * b;
-        Hj[i + 1] = -sn[i] * a + cs[i] * b;
+    double* hs = smem;
+    double* cs_s = smem + (m + 2);
+    double* sn_s = smem + 2 * (m + 2);
+    for (int i = threadIdx.x; i <= j; i += blockDim.x) {
+        hs[i] = hcol[i];
+        if (i < j) { cs_s[i] = cs[i]; sn_s[i] = sn[i]; }
     }
-    const double a = Hj[j], b = Hj[j + 1];
-    const double d = hypot(a, b);
-    cs[j] = d > 0.0 ? a / d : 1.0;
-    sn[j] = d > 0.0 ? b / d : 0.0;
-    Hj[j] = d;
-    Hj[j + 1] = 0.0;
-    g[j + 1] = -sn[j] * g[j];
-    g[j] = cs[j] * g[j];
-    const double res = fabs(g[j + 1]);
-    st->res = res;
-    st->its += 1;
-    scale[j + 1] = hn > 0.0 ? 1.0 / hn : 0.0;
-    if (!isfinite(res)) st->converged = -1;
-    else if (res <= st->tol) st->converged = 1;
-    else if (hn == 0.0) st->converged = 2;
-    st->j = j + 1;
-    if (j + 1 >= m) st->cycle_full = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        hs[j + 1] = hn;
+        for (int i = 0; i < j; ++i) {
+            const double a = hs[i], b = hs[i + 1];
+            hs[i] = cs_s[i] * a + sn_s[i] * b;
+            hs[i + 1] = -sn_s[i] * a + cs_s[i] * b;
+        }
+        const double a = hs[j], b = hs[j + 1];
+        const double d = hypot(a, b);
+        const double c = d > 0.0 ? a / d : 1.0, sgn = d > 0.0 ? b / d : 0.0;
+        cs[j] = c;
+        sn[j] = sgn;
+        hs[j] = d;
+        hs[j + 1] = 0.0;
+        const double gj = g[j];
+        g[j + 1] = -sgn * gj;
+        g[j] = c * gj;
+        const double res = fabs(sgn * gj);
+        st->res = res;
+        st->its += 1;
+        scale[j + 1] = hn > 0.0 ? 1.0 / hn : 0.0;
+        if (!isfinite(res)) st->converged = -1;
+        else if (res <= st->tol) st->converged = 1;
+        else if (hn == 0.0) st->converged = 2;
+        if (j + 1 >= m) st->cycle_full = 1;
+    }
+    __syncthreads();
+    double* Hj = H + (int64_t)j * (m + 1);
+    for (int i = threadIdx.x; i <= j + 1; i += blockDim.x) Hj[i] = hs[i];
+    __syncthreads();
+    if (threadIdx.x == 0) st->j = j + 1;
 }
 
 // w -= sum_i (s_i h_i) V_i ; ||w||^2 ; (single GPU) Givens by the last block
@@ -299,22 +348,25 @@ k_fg_maxpy(FgState* st, FgSeg seg, double* __restrict__ V, int64_t ldv, const do
     nrm = fg_block_sum(nrm, sh);
     if (threadIdx.x == 0) partial[blockIdx.x] = nrm;
     if (!fg_last_block(&st->ticket_maxpy)) return;
+    __shared__ double total;
     double s = 0.0;
     for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s += partial[b];
     s = fg_block_sum(s, sh);
     if (threadIdx.x == 0) {
         normsq_out[0] = s;
-        if (do_givens) fg_givens(st, m, hcol, sqrt(fmax(s, 0.0)), H, cs, sn, g, scale);
+        total = s;
     }
+    __syncthreads();
+    if (do_givens) fg_givens(st, m, hcol, sqrt(fmax(total, 0.0)), H, cs, sn, g, scale, hsh);
 }
 
 // multi-GPU: Givens after the norm has been summed over the ranks
 __global__ void k_fg_givens(FgState* st, int m, const double* __restrict__ hcol, const double* __restrict__ normsq,
                             double* __restrict__ H, double* __restrict__ cs, double* __restrict__ sn,
                             double* __restrict__ g, double* __restrict__ scale) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    extern __shared__ double gsh[];
     if (st->converged || st->cycle_full) return;
-    fg_givens(st, m, hcol, sqrt(fmax(normsq[0], 0.0)), H, cs, sn, g, scale);
+    fg_givens(st, m, hcol, sqrt(fmax(normsq[0], 0.0)), H, cs, sn, g, scale, gsh);
 }
 
 // ---- end of a cycle: y += Z_k (H_k^-1 g_k) ------------------------------------------------------------------------
@@ -368,6 +420,9 @@ static int fg_ensure(hemo_ctx* ctx, int m, int64_t ldv) {
         if ((rc = hemo_alloc(ctx, &ctx->kry_V, (size_t)(m + 1) * ldv))) return rc;
         if ((rc = hemo_alloc(ctx, &ctx->kry_Z, (size_t)m * ldv))) return rc;
         if ((rc = hemo_alloc(ctx, &ctx->kry_w, (size_t)ldv + 512))) return rc;
+        // ghost entries of the basis are never written by the owned-entry kernels: start from defined values
+        HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->kry_V, 0, sizeof(double) * (size_t)(m + 1) * ldv, ctx->stream));
+        HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->kry_Z, 0, sizeof(double) * (size_t)m * ldv, ctx->stream));
         if ((rc = hemo_alloc(ctx, &K.H, (size_t)(m + 1) * m))) return rc;
         if ((rc = hemo_alloc(ctx, &K.small, (size_t)6 * (m + 2)))) return rc;
         if ((rc = hemo_alloc(ctx, &K.partial, (size_t)FG_BLOCKS * (m + 2)))) return rc;
@@ -445,20 +500,27 @@ static int fg_iteration_body(hemo_ctx* ctx, const double* vals_dev) {
     HEMO_PROF_END(ctx, HEMO_PROF_SPMV);
     const int64_t nown = seg.len0 + seg.len1;
     HEMO_PROF_BEGIN(ctx, HEMO_PROF_MDOT);
-    k_fg_mdot<<<fg_grid(nown, FG_TILE), FG_THREADS, sizeof(double) * (m + 2), st>>>(p.st, seg, ctx->kry_V, ldv, p.scale, K.partial,
-                                                                                    p.hcol);
-    HEMO_LAUNCH_CHECK(ctx);
+    {
+        const int kpad = m + 4;
+        const int gm = fg_grid(nown, FG_TILE);
+        const size_t smem = sizeof(double) * (FG_THREADS / 32) * kpad;
+        if (seg.len1 > 0) k_fg_mdot<true><<<gm, FG_THREADS, smem, st>>>(p.st, seg, ctx->kry_V, ldv, K.partial, kpad);
+        else k_fg_mdot<false><<<gm, FG_THREADS, smem, st>>>(p.st, seg, ctx->kry_V, ldv, K.partial, kpad);
+        HEMO_LAUNCH_CHECK(ctx);
+        k_fg_mdot_final<<<m, 128, 0, st>>>(p.st, gm, K.partial, p.scale, p.hcol);
+        HEMO_LAUNCH_CHECK(ctx);
+    }
     HEMO_PROF_END(ctx, HEMO_PROF_MDOT);
     if (ctx->comm && (rc = hemo_comm_allreduce_j(ctx, p.hcol, m + 1))) return rc;
     HEMO_PROF_BEGIN(ctx, HEMO_PROF_MAXPY);
-    k_fg_maxpy<<<fg_grid(nown, 1), FG_THREADS, sizeof(double) * (m + 2), st>>>(p.st, seg, ctx->kry_V, ldv, p.hcol, m, K.partial,
+    k_fg_maxpy<<<fg_grid(nown, 1), FG_THREADS, sizeof(double) * 3 * (m + 2), st>>>(p.st, seg, ctx->kry_V, ldv, p.hcol, m, K.partial,
                                                                                p.normsq, ctx->comm ? 0 : 1, p.H, p.cs, p.sn, p.g,
                                                                                p.scale);
     HEMO_LAUNCH_CHECK(ctx);
     HEMO_PROF_END(ctx, HEMO_PROF_MAXPY);
     if (ctx->comm) {
         if ((rc = hemo_comm_allreduce_j(ctx, p.normsq, 1))) return rc;
-        k_fg_givens<<<1, 32, 0, st>>>(p.st, m, p.hcol, p.normsq, p.H, p.cs, p.sn, p.g, p.scale);
+        k_fg_givens<<<1, 64, sizeof(double) * 3 * (m + 2), st>>>(p.st, m, p.hcol, p.normsq, p.H, p.cs, p.sn, p.g, p.scale);
         HEMO_LAUNCH_CHECK(ctx);
     }
     return 0;
@@ -492,6 +554,7 @@ static int fg_iteration(hemo_ctx* ctx, const double* vals_dev) {
     if (rc != 0 || e != cudaSuccess || !g) {
         cudaGetLastError();
         if (g) cudaGraphDestroy(g);
+        if (rc == HEMO_ERETRY) return fg_iteration(ctx, vals_dev);     // captured again without the cooperative kernel
         if (rc) return rc;
         ctx->use_graph = 0;
         return fg_iteration_body(ctx, vals_dev);
@@ -565,7 +628,7 @@ extern "C" int hemo_fgmres(hemo_ctx* ctx, const double* vals_dev, const double* 
             if (queued >= next_poll) {
                 if ((rc = fg_poll(ctx, &hs))) return rc;
                 if (hs.converged) { done = true; break; }
-                next_poll = queued + (K.poll_every > 0 ? K.poll_every : 2);
+                next_poll = queued + (K.poll_every > 0 ? K.poll_every : 1);
             }
         }
         // y += Z_k (H_k^-1 g_k) with k = columns completed in this cycle (device value)

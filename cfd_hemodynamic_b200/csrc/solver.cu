@@ -146,6 +146,91 @@ __global__ void k_schur_combine(int n, double cm, double cl, double cc, const do
 }
 
 static int pc_build_graph(hemo_ctx* ctx, const double* vals_dev);
+
+// y (+)= A x for a CSR matrix with fp64 values on fp64 vectors, 4 lanes per row (coarse-space transfers)
+template <bool ADD>
+__global__ void __launch_bounds__(256)
+k_csr_apply_d(int nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+              const double* __restrict__ x, double scale, double* __restrict__ y) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt >> 2, lane = gt & 3;
+    const bool ok = i < nrows;
+    const int r0 = ok ? rowptr[i] : 0, r1 = ok ? rowptr[i + 1] : 0;
+    double a = 0.0;
+    for (int t = r0 + lane; t < r1; t += 4) a = fma(val[t], x[col[t]], a);
+    a += __shfl_xor_sync(0xffffffffu, a, 1, 4);
+    a += __shfl_xor_sync(0xffffffffu, a, 2, 4);
+    if (ok && lane == 0) y[i] = ADD ? y[i] + scale * a : scale * a;
+}
+
+// Two-level Schwarz for the pressure operator of the Schur approximation on a partitioned mesh: the rank-local
+// V-cycle sees only its subdomain, so the global low modes come from a coarse space — the level-k operator of the
+// global pressure hierarchy, replicated on every rank (a few 10^4 unknowns).  P0 / R0 are host CSR arrays (copied).
+extern "C" int hemo_pc_set_coarse_pressure(hemo_ctx* ctx, hemo_ctx* coarse_ctx, int coarse_n, const int32_t* p_rowptr,
+                                           const int32_t* p_col, const double* p_val, const int32_t* r_rowptr,
+                                           const int32_t* r_col, const double* r_val, int cycles) {
+    if (!ctx) return HEMO_EINVAL;
+    cudaFree(ctx->cp_rowptr); cudaFree(ctx->cp_col); cudaFree(ctx->cp_val);
+    cudaFree(ctx->cr_rowptr); cudaFree(ctx->cr_col); cudaFree(ctx->cr_val);
+    cudaFree(ctx->coarse_rhs); cudaFree(ctx->coarse_sol);
+    ctx->cp_rowptr = ctx->cp_col = ctx->cr_rowptr = ctx->cr_col = nullptr;
+    ctx->cp_val = ctx->cr_val = ctx->coarse_rhs = ctx->coarse_sol = nullptr;
+    ctx->coarse_ctx = nullptr;
+    ctx->coarse_n = 0;
+    hemo_krylov_invalidate(ctx);
+    ctx->pc_graph_dirty = true;
+    if (!coarse_ctx) return 0;
+    if (coarse_n <= 0 || !p_rowptr || !p_col || !p_val || !r_rowptr || !r_col || !r_val) return HEMO_EINVAL;
+    if (!ctx->cells) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_set_mesh must precede hemo_pc_set_coarse_pressure");
+    if (coarse_ctx->n != coarse_n || !coarse_ctx->amg[1].ready)
+        HEMO_FAIL(ctx, HEMO_ESTATE, "coarse context: graph / pressure hierarchy not set up");
+    const int n = ctx->n;
+    int rc;
+    if ((rc = hemo_upload(ctx, &ctx->cp_rowptr, p_rowptr, (size_t)n + 1, false))) return rc;
+    if ((rc = hemo_upload(ctx, &ctx->cp_col, p_col, (size_t)p_rowptr[n], false))) return rc;
+    if ((rc = hemo_upload(ctx, &ctx->cp_val, p_val, (size_t)p_rowptr[n], false))) return rc;
+    if ((rc = hemo_upload(ctx, &ctx->cr_rowptr, r_rowptr, (size_t)coarse_n + 1, false))) return rc;
+    if ((rc = hemo_upload(ctx, &ctx->cr_col, r_col, (size_t)r_rowptr[coarse_n], false))) return rc;
+    if ((rc = hemo_upload(ctx, &ctx->cr_val, r_val, (size_t)r_rowptr[coarse_n], false))) return rc;
+    if ((rc = hemo_alloc(ctx, &ctx->coarse_rhs, (size_t)coarse_n))) return rc;
+    if ((rc = hemo_alloc(ctx, &ctx->coarse_sol, (size_t)coarse_n))) return rc;
+    HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->coarse_ctx = coarse_ctx;
+    ctx->coarse_n = coarse_n;
+    ctx->coarse_cycles = cycles > 0 ? cycles : 1;
+    return 0;
+}
+
+// q += P0 Ac^-1 sum_ranks(R0 t): the additive coarse correction
+static int coarse_pressure_correction(hemo_ctx* ctx, const double* t_dev, double* q_dev) {
+    hemo_ctx* cc = ctx->coarse_ctx;
+    const int nc = ctx->coarse_n, n = ctx->n;
+    cudaStream_t st = ctx->stream;
+    int rc;
+    k_csr_apply_d<false><<<hemo_grid((int64_t)nc * 4, 256), 256, 0, st>>>(nc, ctx->cr_rowptr, ctx->cr_col, ctx->cr_val, t_dev, 1.0,
+                                                                         ctx->coarse_rhs);
+    HEMO_LAUNCH_CHECK(ctx);
+    if ((rc = hemo_comm_allreduce_j(ctx, ctx->coarse_rhs, nc))) return rc;
+    // the replicated hierarchy lives in its own context: run it on this stream (and inside this capture)
+    cudaStream_t saved = cc->stream;
+    const bool saved_cap = cc->capturing;
+    const int64_t before = cc->launches;
+    cc->stream = st;
+    cc->capturing = ctx->capturing;
+    cc->opts.cheb_degree = ctx->opts.cheb_degree;
+    cc->opts.cheb_degree_pre = ctx->opts.cheb_degree_pre;
+    cc->opts.cheb_ratio = ctx->opts.cheb_ratio;
+    if (ctx->opts.project_pressure && (rc = hemo_remove_mean(ctx, nc, ctx->coarse_rhs))) return rc;
+    rc = hemo_amg_vcycle(cc, &cc->amg[1], ctx->coarse_rhs, ctx->coarse_sol, ctx->coarse_cycles);
+    ctx->launches += cc->launches - before;
+    cc->stream = saved;
+    cc->capturing = saved_cap;
+    if (rc) { ctx->err = cc->err; return rc; }
+    k_csr_apply_d<true><<<hemo_grid((int64_t)n * 4, 256), 256, 0, st>>>(n, ctx->cp_rowptr, ctx->cp_col, ctx->cp_val, ctx->coarse_sol,
+                                                                       1.0, q_dev);
+    HEMO_LAUNCH_CHECK(ctx);
+    return 0;
+}
 int hemo_pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_dev, double* z_dev);
 
 // Dirichlet flags of the pressure dofs: the tail of dofflag in the [u (dim n) | p (n)] layout
@@ -310,7 +395,7 @@ extern "C" int hemo_amg_apply(hemo_ctx* ctx, int which, const double* b_dev, dou
     if (rc != 0 || e != cudaSuccess || !g) {
         cudaGetLastError();
         if (g) cudaGraphDestroy(g);
-        if (rc) return rc;
+        if (rc && rc != HEMO_ERETRY) return rc;
         return hemo_amg_vcycle(ctx, &amg, b_dev, x_dev, ncycles);
     }
     if (amg.apply_exec) { cudaGraphExecDestroy(amg.apply_exec); amg.apply_exec = nullptr; }
@@ -352,6 +437,7 @@ int hemo_pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_de
     }
     if (ctx->opts.project_pressure && (rc = hemo_remove_mean(ctx, n, tp))) return rc;
     if ((rc = hemo_amg_vcycle(ctx, &ctx->amg[1], tp, qp, ctx->opts.amg_cycles_p))) return rc;
+    if (ctx->coarse_ctx && (rc = coarse_pressure_correction(ctx, tp, qp))) return rc;
     const bool pcd = ctx->npconv_coef != 0.0 && ctx->npconv;
     if (pcd) {
         // pressure convection-diffusion term: S^-1 ~ 2 Mp^-1 Fp Lp^-1 with Fp = rho/dt Mp + rho/2 Np + mu/2 Lp
@@ -405,6 +491,7 @@ static int pc_build_graph(hemo_ctx* ctx, const double* vals_dev) {
     if (rc != 0 || e != cudaSuccess || !g) {
         cudaGetLastError();
         if (g) cudaGraphDestroy(g);
+        if (rc == HEMO_ERETRY) return pc_build_graph(ctx, vals_dev);
         ctx->use_graph = 0;
         if (rc) return rc;
         return 0;
@@ -488,6 +575,9 @@ extern "C" int hemo_ctx_destroy(hemo_ctx* ctx) {
     cudaFree(ctx->pc_in); cudaFree(ctx->pc_out); cudaFree(ctx->pc_mask); cudaFree(ctx->kry_coef); cudaFree(ctx->a01);
     cudaFree(ctx->pc_tmp_u); cudaFree(ctx->pc_tmp_u2); cudaFree(ctx->pc_tmp_p); cudaFree(ctx->pc_tmp_p2);
     cudaFree(ctx->kry_V); cudaFree(ctx->kry_Z); cudaFree(ctx->kry_w);
+    cudaFree(ctx->cp_rowptr); cudaFree(ctx->cp_col); cudaFree(ctx->cp_val);
+    cudaFree(ctx->cr_rowptr); cudaFree(ctx->cr_col); cudaFree(ctx->cr_val);
+    cudaFree(ctx->coarse_rhs); cudaFree(ctx->coarse_sol);
     hemo_krylov_free(ctx);
     hemo_comm_free(ctx);
     delete ctx;

@@ -84,6 +84,9 @@ class Partition:
         nodes = np.unique(lc)
         owned = nodes[owner[nodes] == rank]
         ghosts = nodes[owner[nodes] != rank]
+        # ghosts grouped by owner rank (ascending), ascending global id inside a group: every neighbour's values
+        # then land in one contiguous slice of a local vector (the library's halo plan, hemo_comm_set_partition)
+        ghosts = ghosts[np.lexsort((ghosts, owner[ghosts]))]
         self.glob_nodes = np.concatenate([owned, ghosts])
         self.n_owned = int(owned.shape[0])
         self.n_local = int(self.glob_nodes.shape[0])
@@ -199,3 +202,34 @@ class HaloExchangeAllGather:
         dist.all_gather_into_tensor(self.rbuf, self.sbuf, group=self.group)
         if self.src.numel():
             v.index_copy_(0, self.dst, self.rbuf.index_select(0, self.src))
+
+
+def library_halo_plan(part: Partition, owner, group=None):
+    """Halo plan in the form hemo_comm_set_partition takes: (peers, send_ptr, send_nodes, recv_ptr).
+    Ghosts of `part` are grouped by owner rank, so neighbour k's values arrive in the local nodes
+    n_owned + recv_ptr[k] .. n_owned + recv_ptr[k+1]; what each neighbour wants from this rank is learnt from an
+    all-gather of the ghost lists (every rank lists its ghosts in the same (owner, global id) order the receiver
+    stores them in)."""
+    import numpy as np
+    owner = np.asarray(owner)
+    world = dist.get_world_size(group)
+    ghosts = part.glob_nodes[part.n_owned:]
+    lists = [None] * world
+    dist.all_gather_object(lists, ghosts, group=group)
+    gown = owner[ghosts]
+    peers = sorted(set(int(q) for q in np.unique(gown)) | set(q for q in range(world)
+                                                              if q != part.rank and (owner[np.asarray(lists[q], dtype=np.int64)] == part.rank).any()))
+    send_ptr, recv_ptr, send_nodes = [0], [0], []
+    for q in peers:
+        want = np.asarray(lists[q], dtype=np.int64)
+        want = want[owner[want] == part.rank]                  # already in q's storage order
+        loc = part.g2l[want]
+        assert (loc >= 0).all() and (loc < part.n_owned).all()
+        send_nodes.append(loc.astype(np.int32))
+        send_ptr.append(send_ptr[-1] + len(loc))
+        recv_ptr.append(recv_ptr[-1] + int((gown == q).sum()))
+    # the receive slices must tile the ghost range in order: ghosts are sorted by owner, peers ascending
+    assert recv_ptr[-1] == len(ghosts)
+    send_nodes = np.concatenate(send_nodes) if send_nodes else np.zeros(0, np.int32)
+    return (np.asarray(peers, dtype=np.int32), np.asarray(send_ptr, dtype=np.int32), send_nodes.astype(np.int32),
+            np.asarray(recv_ptr, dtype=np.int32))

@@ -300,6 +300,17 @@ int hemo_comm_info(hemo_ctx* ctx, int* rank, int* nranks, int* nccl_version, int
 int hemo_comm_set_partition(hemo_ctx* ctx, int n_owned, int nneigh, const int32_t* peers_host,
                             const int32_t* send_ptr_host, const int32_t* send_nodes_host,
                             const int32_t* recv_ptr_host, int ras_overlap);
+/* A context that carries only a scalar operator on an abstract graph (CSR, device, borrowed) — the replicated
+ * coarse space below; only hemo_amg_set_level / hemo_amg_finalize / hemo_amg_setup_scalar / hemo_amg_apply work on it. */
+int hemo_set_graph(hemo_ctx* ctx, int n, const int32_t* rowptr_dev, const int32_t* col_dev, int64_t nnz);
+/* Two-level Schwarz for the pressure operator of the Schur approximation on a partitioned mesh (what PCASM lacks and
+ * the reason its iteration count grows with the rank count, src/solvers/stabilized_schur.py:256-267): the rank-local
+ * V-cycle is complemented by  P0 Ac^-1 sum_ranks(R0 r)  with Ac the level-k operator of the global pressure hierarchy,
+ * replicated in `coarse_ctx` (hemo_set_graph + hierarchy).  P0: n x coarse_n (rows of the local nodes), R0: coarse_n x n
+ * with the owned columns only; host CSR arrays, copied.  coarse_ctx = NULL removes the correction. */
+int hemo_pc_set_coarse_pressure(hemo_ctx* ctx, hemo_ctx* coarse_ctx, int coarse_n, const int32_t* p_rowptr,
+                                const int32_t* p_col, const double* p_val, const int32_t* r_rowptr,
+                                const int32_t* r_col, const double* r_val, int cycles);
 /* x.ghostUpdate(INSERT, FORWARD) of a local [u | p] vector (device). */
 int hemo_comm_halo_update(hemo_ctx* ctx, double* v_dev);
 /* comm.allreduce(SUM) of `count` doubles in place on the device (asynchronous on the stream). */
@@ -308,7 +319,7 @@ int hemo_comm_allreduce(hemo_ctx* ctx, double* buf_dev, int count);
  * product without a communicator); synchronises the stream. */
 int hemo_global_dot(hemo_ctx* ctx, const double* x_dev, const double* y_dev, double* out_host);
 /* Iterations between two looks at the device-side convergence flag of hemo_fgmres once the iteration
- * count of the previous solve has been reached (default 2). */
+ * count of the previous solve has been reached (default 1). */
 int hemo_set_poll_interval(hemo_ctx* ctx, int every);
 
 /* 1 (default): hemo_pc_setup captures one preconditioner application as a CUDA

@@ -57,6 +57,37 @@ def _worker(rank, world, port, out, cell_type="triangle"):
     owned_dofs = part.dof_index(np.arange(part.n_owned))
     y_ref = (A @ xg)[gdof][owned_dofs]
     err = np.abs(yl[owned_dofs] - y_ref).max() / np.abs(y_ref).max()
+    # the halo plan handed to the library (hemo_comm_set_partition), emulated with P2P on the CPU: pack the send
+    # nodes per neighbour as [u (gd each) | p], receive straight into the contiguous ghost slices; with an overlap of
+    # several cell layers as well (restricted additive Schwarz)
+    from cfd_hemodynamic_b200.parallel import library_halo_plan
+    for ov in (1, 3):
+        part2 = Partition(prob.x, prob.cells, owner, rank, overlap=ov, gdim=gd)
+        peers, send_ptr, send_nodes, recv_ptr = library_halo_plan(part2, owner)
+        gl2 = part2.glob_nodes
+        gdof2 = np.concatenate([np.stack([gd * gl2 + k for k in range(gd)], 1).ravel(), gd * n + gl2])
+        v = torch.tensor(xg[gdof2].copy())
+        nl2, no2 = part2.n_local, part2.n_owned
+        v[gd * no2:gd * nl2] = 0.0
+        v[gd * nl2 + no2:] = 0.0
+        ops, bufs = [], []
+        for k, q in enumerate(peers.tolist()):
+            sn = torch.as_tensor(send_nodes[send_ptr[k]:send_ptr[k + 1]].astype(np.int64))
+            su = torch.stack([v[gd * sn + c] for c in range(gd)], 1).reshape(-1).contiguous()
+            spp = v[gd * nl2 + sn].contiguous()
+            g0, g1 = no2 + int(recv_ptr[k]), no2 + int(recv_ptr[k + 1])
+            ru = torch.empty(gd * (g1 - g0), dtype=torch.float64)
+            rp = torch.empty(g1 - g0, dtype=torch.float64)
+            bufs.append((g0, g1, ru, rp))
+            for t_, fn in ((su, dist.isend), (spp, dist.isend), (ru, dist.irecv), (rp, dist.irecv)):
+                if t_.numel():
+                    ops.append(dist.P2POp(fn, t_, q))
+        for w_ in dist.batch_isend_irecv(ops):
+            w_.wait()
+        for g0, g1, ru, rp in bufs:
+            v[gd * g0:gd * g1] = ru
+            v[gd * nl2 + g0:gd * nl2 + g1] = rp
+        assert np.array_equal(v.numpy(), xg[gdof2]), f"library halo plan, overlap {ov}"
     # distributed dot = allreduce of owned parts
     t = torch.tensor([float(xg[gdof][owned_dofs] @ xg[gdof][owned_dofs])], dtype=torch.float64)
     dist.all_reduce(t)

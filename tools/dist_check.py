@@ -41,7 +41,9 @@ with contextlib.redirect_stdout(sys.stderr):
 tables = sc.solver.export_tables()
 owner = slab_partition(tables["x"][:, 0], world)
 ds = DistributedStabilizedSchur(tables, owner, lr, verbose=bool(os.environ.get('DIST_VERBOSE')),
-                                overlap=int(os.environ['DIST_OVERLAP']) if os.environ.get('DIST_OVERLAP') else None)
+                                overlap=int(os.environ['DIST_OVERLAP']) if os.environ.get('DIST_OVERLAP') else None,
+                                coarse_pressure=not os.environ.get('DIST_NO_COARSE'),
+                                coarse_level=int(os.environ.get('DIST_COARSE_LEVEL', '2')))
 torch.cuda.synchronize(); dist.barrier()
 t0 = time.time()
 its = []
@@ -51,10 +53,8 @@ for k in range(steps):
 torch.cuda.synchronize(); dist.barrier()
 dt = (time.time() - t0) / steps
 u, p = ds.gather_solution()
-if rank == 0 and ds.timers:
-    print("section seconds:", {k: round(v, 3) for k, v in ds.timers.items()}, "its", sum(i[1] for i in its))
 if rank == 0:
-    print(f"distributed: world {world} nx {nx} ms/step {1e3*dt:.1f} its {its} owned {ds.part.n_owned} local {ds.part.n_local} halo bytes {ds.halo.bytes_per_update}")
+    print(f"distributed: world {world} nx {nx} ms/step {1e3*dt:.1f} its {its} {ds.comm_summary()}")
     if nx <= 128:
         with contextlib.redirect_stdout(sys.stderr):
             ref = make(False, device=lr, **tight)
