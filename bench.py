@@ -216,7 +216,7 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": "DOF-timesteps/s", "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "DOF-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -468,6 +468,30 @@ def run_distributed(args, name, W, K, world, rank, local_rank):
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     dist.all_reduce(te, op=dist.ReduceOp.MAX)
     info = ds.comm_summary()
+    # per-phase CUDA-event times (library side) from two extra steps with direct launches: the timed region replays
+    # CUDA graphs; a rank's halo / allreduce time includes waiting for its peers
+    ds.hemo.use_graph(False)
+    ds.step_device()
+    ds.hemo.prof_enable(True)
+    g0 = torch.cuda.Event(enable_timing=True)
+    g1 = torch.cuda.Event(enable_timing=True)
+    g0.record()
+    kp = 0
+    for _ in range(2):
+        ds.step_device()
+        kp += ds.its_ksp
+    g1.record()
+    torch.cuda.synchronize(dev)
+    names = {0: "spmv", 6: "mdot", 7: "maxpy_norm", 9: "halo", 10: "allreduce", 11: "pressure_coarse_space", 12: "preconditioner"}
+    phases = {}
+    for c, nm in names.items():
+        t_c, cnt = ds.hemo.prof_get(c)
+        phases[nm] = {"ms_per_iteration": t_c / max(kp, 1), "launches_per_iteration": cnt / max(kp, 1)}
+    phases["direct_launch_ms_per_iteration"] = g0.elapsed_time(g1) / max(kp, 1)
+    phases["graph_ms_per_iteration"] = ms / max(ksp, 1)
+    ds.hemo.prof_enable(False)
+    ds.hemo.use_graph(True)
+    info["phases_rank0"] = phases
     if rank == 0:
         peak, peak_kind = measured_peaks()
         line = {
@@ -486,8 +510,27 @@ def run_distributed(args, name, W, K, world, rank, local_rank):
                          "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_kind},
             "cpu_baseline": None,
         }
-        print(json.dumps(line))
+        emit(line)
     dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """stdout must carry exactly one JSON line: C-level writers (the NCCL version banner, library diagnostics) and
+    stray prints are sent to stderr for the whole run; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
@@ -501,6 +544,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the larger GPU-only workloads")
     args = ap.parse_args()
+    _guard_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -558,7 +602,7 @@ def main():
         "assembly": r["assembly"], "e2e": r.get("e2e"), "gpu_launches": r["gpu_launches"], "clocks": r["clocks"],
         "roofline": r.get("roofline"), "cpu_baseline": cpu, "other_workloads": others,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 if __name__ == "__main__":

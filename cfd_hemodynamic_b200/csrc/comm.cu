@@ -196,6 +196,7 @@ int hemo_comm_halo(hemo_ctx* ctx, double* v) {
     const int64_t n = ctx->n;
     const int total = c->send_ptr[c->nneigh];
     cudaStream_t st = ctx->stream;
+    HEMO_PROF_BEGIN(ctx, HEMO_PROF_HALO);
     if (total > 0) {
         k_halo_pack<<<hemo_grid(total, 256), 256, 0, st>>>(total, dim, n, c->send_nodes, nullptr, v, c->sendbuf);
         HEMO_LAUNCH_CHECK(ctx);
@@ -214,6 +215,7 @@ int hemo_comm_halo(hemo_ctx* ctx, double* v) {
         }
     }
     HEMO_CHECK_NCCL(ctx, g_nccl.GroupEnd());
+    HEMO_PROF_END(ctx, HEMO_PROF_HALO);
     if (!ctx->capturing) c->halo_updates++;
     ctx->launches++;
     return 0;
@@ -222,7 +224,9 @@ int hemo_comm_halo(hemo_ctx* ctx, double* v) {
 int hemo_comm_allreduce_j(hemo_ctx* ctx, double* buf, int count) {
     HemoComm* c = ctx->comm;
     if (!c || c->nranks == 1) return 0;
+    HEMO_PROF_BEGIN(ctx, HEMO_PROF_ALLREDUCE);
     HEMO_CHECK_NCCL(ctx, g_nccl.AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclSum, c->comm, ctx->stream));
+    HEMO_PROF_END(ctx, HEMO_PROF_ALLREDUCE);
     if (!ctx->capturing) c->allreduces++;
     ctx->launches++;
     return 0;

@@ -117,7 +117,8 @@ struct HemoAmg {
 // kernel classes timed by the optional CUDA-event profiler (hemo_prof_*)
 enum { HEMO_PROF_SPMV = 0, HEMO_PROF_CELL_JAC = 1, HEMO_PROF_GATHER_MAT = 2, HEMO_PROF_CELL_RES = 3,
        HEMO_PROF_CHEB_U0 = 4, HEMO_PROF_CHEB_P0 = 5, HEMO_PROF_MDOT = 6, HEMO_PROF_MAXPY = 7,
-       HEMO_PROF_RAP = 8, HEMO_PROF_NCLASS = 9 };
+       HEMO_PROF_RAP = 8, HEMO_PROF_HALO = 9, HEMO_PROF_ALLREDUCE = 10, HEMO_PROF_COARSE = 11, HEMO_PROF_PC = 12,
+       HEMO_PROF_NCLASS = 13 };
 
 struct HemoProf {
     bool on = false;
@@ -244,6 +245,8 @@ struct hemo_ctx {
     int32_t *cr_rowptr = nullptr, *cr_col = nullptr; double* cr_val = nullptr;     // R0: coarse_n x n (owned columns)
     double *coarse_rhs = nullptr, *coarse_sol = nullptr;
     int coarse_cycles = 1;
+    cudaStream_t side_stream = nullptr;   // the coarse-space branch runs beside the local V-cycle (fork / join by events)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     HemoComm* comm = nullptr;
     int comm_ras_overlap = 0;       // 1: the preconditioner input needs valid ghost values (overlapping Schwarz)
 };

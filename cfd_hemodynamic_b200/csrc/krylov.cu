@@ -41,6 +41,7 @@ struct FgSeg {
     int64_t len0, off1, len1;
 };
 __device__ __forceinline__ int64_t seg_index(const FgSeg& s, int64_t i) { return i < s.len0 ? i : i - s.len0 + s.off1; }
+__device__ __forceinline__ bool seg_owned(const FgSeg& s, int64_t q) { return q < s.len0 || (q >= s.off1 && q < s.off1 + s.len1); }
 
 __device__ __forceinline__ double fg_warp_sum(double v) {
 #pragma unroll
@@ -79,18 +80,17 @@ __device__ __forceinline__ bool fg_last_block(unsigned int* ticket) {
 // ---- start of a solve / of a restart cycle ------------------------------------------------------------------------
 // V_0 = r (unnormalised), partial ||r||^2
 __global__ void __launch_bounds__(FG_THREADS)
-k_fg_start(FgState* st, FgSeg seg, const double* __restrict__ r, double* __restrict__ V0, double* __restrict__ partial,
-           double* __restrict__ out, int first, double rtol, double atol, double* __restrict__ g, double* __restrict__ scale,
-           int reduce_here) {
+k_fg_start(FgState* st, FgSeg seg, int64_t nloc, const double* __restrict__ r, double* __restrict__ V0,
+           double* __restrict__ partial, double* __restrict__ out, int first) {
     __shared__ double sh[32];
     if (!first && st->converged) return;
-    const int64_t n = seg.len0 + seg.len1;
+    // every local entry is kept (the rows of the overlap region are complete: their values equal the owners' up to
+    // rounding, so the overlapping Schwarz preconditioner needs no ghost update of its input); owned entries are reduced
     double acc = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t q = seg_index(seg, i);
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nloc; q += (int64_t)gridDim.x * blockDim.x) {
         const double v = r[q];
         V0[q] = v;
-        acc = fma(v, v, acc);
+        if (seg_owned(seg, q)) acc = fma(v, v, acc);
     }
     acc = fg_block_sum(acc, sh);
     if (threadIdx.x == 0) partial[blockIdx.x] = acc;
@@ -99,7 +99,6 @@ k_fg_start(FgState* st, FgSeg seg, const double* __restrict__ r, double* __restr
     for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s += partial[b];
     s = fg_block_sum(s, sh);
     if (threadIdx.x == 0) out[0] = s;     // local ||r||^2 (summed over ranks before k_fg_begin_cycle)
-    (void)first; (void)rtol; (void)atol; (void)g; (void)scale; (void)reduce_here;
 }
 
 __global__ void k_fg_begin_cycle(FgState* st, const double* __restrict__ normsq, int first, double rtol, double atol,
@@ -326,7 +325,7 @@ __device__ void fg_givens(FgState* st, int m, const double* __restrict__ hcol, d
 
 // w -= sum_i (s_i h_i) V_i ; ||w||^2 ; (single GPU) Givens by the last block
 __global__ void __launch_bounds__(FG_THREADS)
-k_fg_maxpy(FgState* st, FgSeg seg, double* __restrict__ V, int64_t ldv, const double* __restrict__ hcol, int m,
+k_fg_maxpy(FgState* st, FgSeg seg, int64_t nloc, double* __restrict__ V, int64_t ldv, const double* __restrict__ hcol, int m,
            double* __restrict__ partial, double* __restrict__ normsq_out, int do_givens, double* __restrict__ H,
            double* __restrict__ cs, double* __restrict__ sn, double* __restrict__ g, double* __restrict__ scale) {
     __shared__ double sh[32];
@@ -336,14 +335,12 @@ k_fg_maxpy(FgState* st, FgSeg seg, double* __restrict__ V, int64_t ldv, const do
     double* w = V + (int64_t)k * ldv;
     for (int i = threadIdx.x; i < k; i += blockDim.x) hsh[i] = hcol[i] * scale[i];
     __syncthreads();
-    const int64_t n = seg.len0 + seg.len1;
     double nrm = 0.0;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t q = seg_index(seg, idx);
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nloc; q += (int64_t)gridDim.x * blockDim.x) {
         double acc = w[q];
         for (int i = 0; i < k; ++i) acc = fma(-hsh[i], V[(int64_t)i * ldv + q], acc);
         w[q] = acc;
-        nrm = fma(acc, acc, nrm);
+        if (seg_owned(seg, q)) nrm = fma(acc, acc, nrm);
     }
     nrm = fg_block_sum(nrm, sh);
     if (threadIdx.x == 0) partial[blockIdx.x] = nrm;
@@ -486,7 +483,9 @@ static int fg_iteration_body(hemo_ctx* ctx, const double* vals_dev) {
     k_fg_load<<<fg_grid(N, 4), FG_THREADS, 0, st>>>(p.st, N, ctx->kry_V, ldv, p.scale, ctx->pc_in);
     HEMO_LAUNCH_CHECK(ctx);
     if (ctx->comm && ctx->comm_ras_overlap && (rc = hemo_comm_halo(ctx, ctx->pc_in))) return rc;
+    HEMO_PROF_BEGIN(ctx, HEMO_PROF_PC);
     if ((rc = hemo_pc_apply_body(ctx, vals_dev, ctx->pc_in, ctx->pc_out))) return rc;
+    HEMO_PROF_END(ctx, HEMO_PROF_PC);
     if (ctx->comm && (rc = hemo_comm_halo(ctx, ctx->pc_out))) return rc;
     HEMO_PROF_BEGIN(ctx, HEMO_PROF_SPMV);
     if (ctx->dim == 3) {
@@ -513,7 +512,7 @@ static int fg_iteration_body(hemo_ctx* ctx, const double* vals_dev) {
     HEMO_PROF_END(ctx, HEMO_PROF_MDOT);
     if (ctx->comm && (rc = hemo_comm_allreduce_j(ctx, p.hcol, m + 1))) return rc;
     HEMO_PROF_BEGIN(ctx, HEMO_PROF_MAXPY);
-    k_fg_maxpy<<<fg_grid(nown, 1), FG_THREADS, sizeof(double) * 3 * (m + 2), st>>>(p.st, seg, ctx->kry_V, ldv, p.hcol, m, K.partial,
+    k_fg_maxpy<<<fg_grid(N, 1), FG_THREADS, sizeof(double) * 3 * (m + 2), st>>>(p.st, seg, N, ctx->kry_V, ldv, p.hcol, m, K.partial,
                                                                                p.normsq, ctx->comm ? 0 : 1, p.H, p.cs, p.sn, p.g,
                                                                                p.scale);
     HEMO_LAUNCH_CHECK(ctx);
@@ -608,7 +607,7 @@ extern "C" int hemo_fgmres(hemo_ctx* ctx, const double* vals_dev, const double* 
     const FgSeg seg = {K.seg_len0 ? K.seg_len0 : N, K.seg_off1, K.seg_len0 ? K.seg_len1 : 0};
     const int64_t nown = seg.len0 + seg.len1;
     HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(y_dev, 0, sizeof(double) * N, st));
-    k_fg_start<<<fg_grid(nown, 4), FG_THREADS, 0, st>>>(p.st, seg, b_dev, ctx->kry_V, K.partial, p.normsq, 1, 0, 0, p.g, p.scale, 0);
+    k_fg_start<<<fg_grid(N, 4), FG_THREADS, 0, st>>>(p.st, seg, N, b_dev, ctx->kry_V, K.partial, p.normsq, 1);
     HEMO_LAUNCH_CHECK(ctx);
     if (ctx->comm && (rc = hemo_comm_allreduce_j(ctx, p.normsq, 1))) return rc;
     k_fg_begin_cycle<<<1, 32, 0, st>>>(p.st, p.normsq, 1, ctx->opts.rtol, ctx->opts.atol, p.g, p.scale, m);
@@ -644,8 +643,7 @@ extern "C" int hemo_fgmres(hemo_ctx* ctx, const double* vals_dev, const double* 
         if ((rc = hemo_spmv(ctx, vals_dev, y_dev, ctx->kry_w))) return rc;
         k_fg_residual<<<fg_grid(N, 4), FG_THREADS, 0, st>>>(p.st, N, b_dev, ctx->kry_w, ctx->kry_w);
         HEMO_LAUNCH_CHECK(ctx);
-        k_fg_start<<<fg_grid(nown, 4), FG_THREADS, 0, st>>>(p.st, seg, ctx->kry_w, ctx->kry_V, K.partial, p.normsq, 0, 0, 0, p.g,
-                                                          p.scale, 0);
+        k_fg_start<<<fg_grid(N, 4), FG_THREADS, 0, st>>>(p.st, seg, N, ctx->kry_w, ctx->kry_V, K.partial, p.normsq, 0);
         HEMO_LAUNCH_CHECK(ctx);
         if (ctx->comm && (rc = hemo_comm_allreduce_j(ctx, p.normsq, 1))) return rc;
         k_fg_begin_cycle<<<1, 32, 0, st>>>(p.st, p.normsq, 0, ctx->opts.rtol, ctx->opts.atol, p.g, p.scale, m);

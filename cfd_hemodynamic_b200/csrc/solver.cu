@@ -201,37 +201,58 @@ extern "C" int hemo_pc_set_coarse_pressure(hemo_ctx* ctx, hemo_ctx* coarse_ctx, 
     return 0;
 }
 
-// q += P0 Ac^-1 sum_ranks(R0 t): the additive coarse correction
-static int coarse_pressure_correction(hemo_ctx* ctx, const double* t_dev, double* q_dev) {
+// The additive coarse correction q += P0 Ac^-1 sum_ranks(R0 t) in two halves: the branch (restriction, allreduce,
+// replicated coarse V-cycle) is enqueued on a side stream forked from the solver's stream, so it runs beside the
+// rank-local V-cycle (and its allreduce latency hides behind it); the join adds the prolongated correction.
+// Fork / join are event dependencies, which stream capture records as graph edges.
+static int coarse_pressure_fork(hemo_ctx* ctx, const double* t_dev) {
     hemo_ctx* cc = ctx->coarse_ctx;
-    const int nc = ctx->coarse_n, n = ctx->n;
+    const int nc = ctx->coarse_n;
+    int rc = 0;
+    if (!ctx->side_stream) {
+        HEMO_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+        HEMO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        HEMO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    cudaStream_t main_st = ctx->stream, side = ctx->side_stream;
+    HEMO_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main_st));
+    HEMO_CHECK_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_fork, 0));
+    ctx->stream = side;                       // everything below is enqueued on the side stream
+    do {
+        k_csr_apply_d<false><<<hemo_grid((int64_t)nc * 4, 256), 256, 0, side>>>(nc, ctx->cr_rowptr, ctx->cr_col, ctx->cr_val, t_dev,
+                                                                               1.0, ctx->coarse_rhs);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) { rc = HEMO_ESTATE; ctx->err = "coarse restriction launch failed"; break; }
+        if ((rc = hemo_comm_allreduce_j(ctx, ctx->coarse_rhs, nc))) break;
+        cudaStream_t saved = cc->stream;
+        const bool saved_cap = cc->capturing;
+        const int64_t before = cc->launches;
+        cc->stream = side;
+        cc->capturing = ctx->capturing;
+        cc->opts.cheb_degree = ctx->opts.cheb_degree;
+        cc->opts.cheb_degree_pre = ctx->opts.cheb_degree_pre;
+        cc->opts.cheb_ratio = ctx->opts.cheb_ratio;
+        rc = hemo_amg_vcycle(cc, &cc->amg[1], ctx->coarse_rhs, ctx->coarse_sol, ctx->coarse_cycles);
+        ctx->launches += cc->launches - before;
+        cc->stream = saved;
+        cc->capturing = saved_cap;
+        if (rc) ctx->err = cc->err;
+    } while (0);
+    ctx->stream = main_st;
+    if (rc) return rc;
+    HEMO_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_join, side));
+    return 0;
+}
+
+static int coarse_pressure_join(hemo_ctx* ctx, double* q_dev) {
+    const int n = ctx->n;
     cudaStream_t st = ctx->stream;
-    int rc;
-    k_csr_apply_d<false><<<hemo_grid((int64_t)nc * 4, 256), 256, 0, st>>>(nc, ctx->cr_rowptr, ctx->cr_col, ctx->cr_val, t_dev, 1.0,
-                                                                         ctx->coarse_rhs);
-    HEMO_LAUNCH_CHECK(ctx);
-    if ((rc = hemo_comm_allreduce_j(ctx, ctx->coarse_rhs, nc))) return rc;
-    // the replicated hierarchy lives in its own context: run it on this stream (and inside this capture)
-    cudaStream_t saved = cc->stream;
-    const bool saved_cap = cc->capturing;
-    const int64_t before = cc->launches;
-    cc->stream = st;
-    cc->capturing = ctx->capturing;
-    cc->opts.cheb_degree = ctx->opts.cheb_degree;
-    cc->opts.cheb_degree_pre = ctx->opts.cheb_degree_pre;
-    cc->opts.cheb_ratio = ctx->opts.cheb_ratio;
-    if (ctx->opts.project_pressure && (rc = hemo_remove_mean(ctx, nc, ctx->coarse_rhs))) return rc;
-    rc = hemo_amg_vcycle(cc, &cc->amg[1], ctx->coarse_rhs, ctx->coarse_sol, ctx->coarse_cycles);
-    ctx->launches += cc->launches - before;
-    cc->stream = saved;
-    cc->capturing = saved_cap;
-    if (rc) { ctx->err = cc->err; return rc; }
+    HEMO_CHECK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     k_csr_apply_d<true><<<hemo_grid((int64_t)n * 4, 256), 256, 0, st>>>(n, ctx->cp_rowptr, ctx->cp_col, ctx->cp_val, ctx->coarse_sol,
                                                                        1.0, q_dev);
     HEMO_LAUNCH_CHECK(ctx);
     return 0;
 }
-int hemo_pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_dev, double* z_dev);
 
 // Dirichlet flags of the pressure dofs: the tail of dofflag in the [u (dim n) | p (n)] layout
 static inline const uint8_t* pressure_flags(const hemo_ctx* ctx) {
@@ -436,8 +457,13 @@ int hemo_pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_de
         HEMO_LAUNCH_CHECK(ctx);
     }
     if (ctx->opts.project_pressure && (rc = hemo_remove_mean(ctx, n, tp))) return rc;
+    if (ctx->coarse_ctx && (rc = coarse_pressure_fork(ctx, tp))) return rc;
     if ((rc = hemo_amg_vcycle(ctx, &ctx->amg[1], tp, qp, ctx->opts.amg_cycles_p))) return rc;
-    if (ctx->coarse_ctx && (rc = coarse_pressure_correction(ctx, tp, qp))) return rc;
+    if (ctx->coarse_ctx) {
+        HEMO_PROF_BEGIN(ctx, HEMO_PROF_COARSE);          // what is left on the critical path: the join
+        if ((rc = coarse_pressure_join(ctx, qp))) return rc;
+        HEMO_PROF_END(ctx, HEMO_PROF_COARSE);
+    }
     const bool pcd = ctx->npconv_coef != 0.0 && ctx->npconv;
     if (pcd) {
         // pressure convection-diffusion term: S^-1 ~ 2 Mp^-1 Fp Lp^-1 with Fp = rho/dt Mp + rho/2 Np + mu/2 Lp
@@ -578,6 +604,9 @@ extern "C" int hemo_ctx_destroy(hemo_ctx* ctx) {
     cudaFree(ctx->cp_rowptr); cudaFree(ctx->cp_col); cudaFree(ctx->cp_val);
     cudaFree(ctx->cr_rowptr); cudaFree(ctx->cr_col); cudaFree(ctx->cr_val);
     cudaFree(ctx->coarse_rhs); cudaFree(ctx->coarse_sol);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     hemo_krylov_free(ctx);
     hemo_comm_free(ctx);
     delete ctx;

@@ -141,7 +141,9 @@ class DistributedStabilizedSchur:
         if self.world > 1:
             hemo.comm_init(_broadcast_nccl_id(self.rank, group), self.rank, self.world)
             peers, send_ptr, send_nodes, recv_ptr = library_halo_plan(part, owner, group)
-            hemo.comm_set_partition(part.n_owned, peers, send_ptr, send_nodes, recv_ptr, ras_overlap=self.overlap > 1)
+            # no ghost update of the preconditioner input: the Krylov vectors stay valid on the overlap (complete rows)
+            hemo.comm_set_partition(part.n_owned, peers, send_ptr, send_nodes, recv_ptr,
+                                    ras_overlap=bool(os.environ.get("HEMO_DIST_HALO_PC_INPUT")))
             self.halo_bytes_per_update = int(8 * 3 * (send_ptr[-1] + recv_ptr[-1]))
             self.n_neighbours = int(len(peers))
         else:

@@ -91,7 +91,8 @@ int64_t hemo_launch_count(hemo_ctx* ctx);
 /* Optional CUDA-event timing of selected kernel classes on the context's
  * stream (bench.py roofline): 0 SpMV(J), 1 cell Jacobian, 2 matrix gather,
  * 3 cell residual, 4 Chebyshev step A00 level 0, 5 Chebyshev step Lp level 0,
- * 6 multi-dot, 7 multi-axpy+norm, 8 Galerkin R*AP level 0.  enable(on) resets
+ * 6 multi-dot, 7 multi-axpy+norm, 8 Galerkin R*AP level 0, 9 halo exchange, 10 allreduce, 11 coarse-space pressure
+ * correction, 12 whole preconditioner application (nested classes overlap).  enable(on) resets
  * the counters; get() synchronises the stream. */
 int hemo_prof_enable(hemo_ctx* ctx, int on);
 int hemo_prof_get(hemo_ctx* ctx, int kernel_class, double* ms_total, int64_t* launches);
