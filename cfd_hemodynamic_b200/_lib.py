@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libhemo_sm100.so")
 
 HEMO_DIVERGED = -100
 Q_FU, Q_FP, Q_UU, Q_UP, Q_PU, Q_PP = range(6)
-CELL_TRIANGLE, CELL_QUADRILATERAL, CELL_TETRAHEDRON = 0, 1, 2
+CELL_TRIANGLE, CELL_QUADRILATERAL, CELL_TETRAHEDRON, CELL_TRIANGLE_P2 = 0, 1, 2, 3
 
 
 class HemoError(RuntimeError):
@@ -215,13 +215,13 @@ class Hemo:
     def set_mesh(self, x2, cells, h):
         """cells: (E, 3) P1 triangles or (E, 4) tensor-ordered Q1 quadrilaterals with x2 (n, 2);
         (E, 4) P1 tetrahedra with x2 (n, 3) (what works on tetrahedra: include/hemo.h)."""
-        if cells.dim() != 2 or cells.shape[1] not in (3, 4) or not cells.is_contiguous():
-            raise HemoError("cells must be a contiguous (E, 3) or (E, 4) int32 tensor")
+        if cells.dim() != 2 or cells.shape[1] not in (3, 4, 6) or not cells.is_contiguous():
+            raise HemoError("cells must be a contiguous (E, 3), (E, 4) or (E, 6: P2 triangles) int32 tensor")
         self.nv = int(cells.shape[1])
         self.dim = int(x2.shape[1]) if x2.dim() == 2 else 2
         if self.dim == 3 and self.nv != 4:
             raise HemoError("3-D meshes must be tetrahedral: cells (E, 4)")
-        ctype = CELL_TETRAHEDRON if self.dim == 3 else (CELL_QUADRILATERAL if self.nv == 4 else CELL_TRIANGLE)
+        ctype = CELL_TETRAHEDRON if self.dim == 3 else {3: CELL_TRIANGLE, 4: CELL_QUADRILATERAL, 6: CELL_TRIANGLE_P2}[self.nv]
         self._check(self.lib.hemo_set_cell_type(self._ctx, ctype), "hemo_set_cell_type")
         self._keep.update(x=x2, cells=cells, h=h)
         self.n = x2.shape[0]

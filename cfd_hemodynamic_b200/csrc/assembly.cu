@@ -893,9 +893,9 @@ static int upload_constants(hemo_ctx* ctx) {
 
 extern "C" int hemo_set_cell_type(hemo_ctx* ctx, int cell_type) {
     if (!ctx || (cell_type != HEMO_CELL_TRIANGLE && cell_type != HEMO_CELL_QUADRILATERAL &&
-                 cell_type != HEMO_CELL_TETRAHEDRON))
+                 cell_type != HEMO_CELL_TETRAHEDRON && cell_type != HEMO_CELL_TRIANGLE_P2))
         return HEMO_EINVAL;
-    const int nv = (cell_type == HEMO_CELL_TRIANGLE) ? 3 : 4;
+    const int nv = (cell_type == HEMO_CELL_TRIANGLE) ? 3 : (cell_type == HEMO_CELL_TRIANGLE_P2 ? 6 : 4);
     const int dim = (cell_type == HEMO_CELL_TETRAHEDRON) ? 3 : 2;
     if (nv == ctx->nv && dim == ctx->dim) return 0;
     // a different cell type invalidates the mesh, the node graph tables and the rules
@@ -1065,6 +1065,7 @@ extern "C" int hemo_set_quadrature(hemo_ctx* ctx, int block, const double* pts, 
     if (!ctx || block < 0 || block >= HEMO_NRULES || !pts || !wts || nq <= 0) return HEMO_EINVAL;
     if (ctx->dim == 3) return hemo_tet_set_quadrature(ctx, block, pts, wts, nq);
     if (ctx->nv == 4) return set_quadrature_quad(ctx, block, pts, wts, nq);
+    if (ctx->nv == 6) return hemo_p2_set_quadrature(ctx, block, pts, wts, nq);
     if (nq > HEMO_MAXQ) return HEMO_EINVAL;
     HemoRule& r = ctx->rules[block];
     r.nq = nq;
@@ -1226,6 +1227,8 @@ extern "C" int hemo_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const 
     HEMO_PROF_BEGIN(ctx, HEMO_PROF_CELL_JAC);
     if (nv == 4) {
         if ((rc = hemo_q1_cell_jacobian(ctx, x_dev, un_dev))) return rc;
+    } else if (nv == 6) {
+        if ((rc = hemo_p2_cell_jacobian(ctx, x_dev, un_dev))) return rc;
     } else {
         k_cell_jacobian<<<hemo_grid(E, 128), 128, 0, st>>>(E, n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, uh, ctx->Ae);
         HEMO_LAUNCH_CHECK(ctx);
@@ -1236,6 +1239,10 @@ extern "C" int hemo_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const 
         if (!facet_set_active(fs)) continue;
         if (nv == 4) {
             if ((rc = hemo_q1_facets(ctx, 1, fs, x_dev, un_dev, nullptr))) return rc;
+            continue;
+        }
+        if (nv == 6) {
+            if ((rc = hemo_p2_facets(ctx, 1, fs, x_dev, un_dev, nullptr))) return rc;
             continue;
         }
         k_facets<1><<<hemo_grid(fs.m, 128), 128, 0, st>>>(fs.m, E, n, fs.cells, fs.mask, fs.coef, ctx->cells, ctx->x,
@@ -1270,6 +1277,8 @@ extern "C" int hemo_assemble_residual(hemo_ctx* ctx, const double* x_dev, const 
     HEMO_PROF_BEGIN(ctx, HEMO_PROF_CELL_RES);
     if (nv == 4) {
         if ((rc = hemo_q1_cell_residual(ctx, x_dev, un_dev, cf))) return rc;
+    } else if (nv == 6) {
+        if ((rc = hemo_p2_cell_residual(ctx, x_dev, un_dev, cf))) return rc;
     } else {
         k_cell_residual<<<hemo_grid(E, 128), 128, 0, st>>>(E, n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, uh, cf, ctx->dvec, ctx->Fe);
         HEMO_LAUNCH_CHECK(ctx);
@@ -1280,6 +1289,10 @@ extern "C" int hemo_assemble_residual(hemo_ctx* ctx, const double* x_dev, const 
         if (!facet_set_active(fs)) continue;
         if (nv == 4) {
             if ((rc = hemo_q1_facets(ctx, 0, fs, x_dev, un_dev, cf))) return rc;
+            continue;
+        }
+        if (nv == 6) {
+            if ((rc = hemo_p2_facets(ctx, 0, fs, x_dev, un_dev, cf))) return rc;
             continue;
         }
         k_facets<0><<<hemo_grid(fs.m, 128), 128, 0, st>>>(fs.m, E, n, fs.cells, fs.mask, fs.coef, ctx->cells, ctx->x,
@@ -1303,6 +1316,8 @@ extern "C" int hemo_outlet_flux(hemo_ctx* ctx, int set_id, const double* un_dev,
         if ((rc = hemo_tet_facet_flux(ctx, fs, un_dev, ctx->red_partial))) return rc;
     } else if (ctx->nv == 4) {
         if ((rc = hemo_q1_facet_flux(ctx, fs, un_dev, ctx->red_partial))) return rc;
+    } else if (ctx->nv == 6) {
+        if ((rc = hemo_p2_facet_flux(ctx, fs, un_dev, ctx->red_partial))) return rc;
     } else {
         k_facet_flux<<<hemo_grid(fs.m, 128), 128, 0, st>>>(fs.m, fs.cells, fs.mask, ctx->cells, ctx->x, un_dev, ctx->red_partial);
         HEMO_LAUNCH_CHECK(ctx);
@@ -1327,6 +1342,8 @@ extern "C" int hemo_assemble_laplace_mass(hemo_ctx* ctx, double* lap_vals_dev, d
         if ((rc = hemo_tet_laplace_mass(ctx))) return rc;
     } else if (nv == 4) {
         if ((rc = hemo_q1_laplace_mass(ctx))) return rc;
+    } else if (nv == 6) {
+        if ((rc = hemo_p2_laplace_mass(ctx))) return rc;
     } else {
         k_cell_laplace<<<hemo_grid(E, 256), 256, 0, st>>>(E, ctx->cells, ctx->x, ctx->Ae, ctx->Fe);
         HEMO_LAUNCH_CHECK(ctx);

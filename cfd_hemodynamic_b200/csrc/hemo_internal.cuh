@@ -159,7 +159,8 @@ struct hemo_ctx {
     int64_t launches = 0;
 
     // mesh (borrowed)
-    int nv = 3;                     // nodes per cell: 3 = P1 triangle, 4 = Q1 quadrilateral (tensor-ordered) | P1 tetrahedron
+    int nv = 3;                     // nodes per cell: 3 = P1 triangle, 4 = Q1 quadrilateral (tensor-ordered) | P1 tetrahedron,
+                                    // 6 = P2 triangle (3 vertex + 3 edge nodes)
     int dim = 2;                    // geometric dimension: 3 only for tetrahedra (include/hemo.h lists what works in 3-D)
     double fz = 0.0;                // third component of the body force (hemo_set_body_force3)
     const double* x = nullptr;
@@ -192,6 +193,7 @@ struct hemo_ctx {
     bool rules_dirty = true;
     HemoQuadRule* qrules = nullptr; // HEMO_NRULES host-side rules of the quadrilateral path (allocated on first use)
     bool qrules_dirty = true;
+    void* p2rules = nullptr;        // HEMO_NRULES host-side HemoP2Rule tables of the P2 triangle path (allocated on first use)
     HemoFacetRule frule{};
     HemoFacetSet fsets[HEMO_MAX_FACET_SETS];
     uint8_t* dofflag = nullptr;
@@ -328,6 +330,14 @@ int hemo_q1_facets(hemo_ctx* ctx, int mode, const HemoFacetSet& fs, const double
                    const uint8_t* cellflag);
 int hemo_q1_facet_flux(hemo_ctx* ctx, const HemoFacetSet& fs, const double* un_dev, double* partial);
 int hemo_q1_laplace_mass(hemo_ctx* ctx);
+// implemented in assembly_p2.cu (P2-P2 triangle cell / facet kernels, nv = 6)
+int hemo_p2_set_quadrature(hemo_ctx* ctx, int block, const double* pts, const double* wts, int nq);
+int hemo_p2_cell_jacobian(hemo_ctx* ctx, const double* x_dev, const double* un_dev);
+int hemo_p2_cell_residual(hemo_ctx* ctx, const double* x_dev, const double* un_dev, const uint8_t* cellflag);
+int hemo_p2_facets(hemo_ctx* ctx, int mode, const HemoFacetSet& fs, const double* x_dev, const double* un_dev,
+                   const uint8_t* cellflag);
+int hemo_p2_facet_flux(hemo_ctx* ctx, const HemoFacetSet& fs, const double* un_dev, double* partial);
+int hemo_p2_laplace_mass(hemo_ctx* ctx);
 // implemented in assembly_tet.cu
 void hemo_tet_free(hemo_ctx* ctx);
 int hemo_tet_pattern(hemo_ctx* ctx, int64_t* rowptr_dev, int32_t* colind_dev);

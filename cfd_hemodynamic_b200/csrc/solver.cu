@@ -597,6 +597,7 @@ extern "C" int hemo_ctx_destroy(hemo_ctx* ctx) {
     if (ctx->pc_graph) cudaGraphDestroy(ctx->pc_graph);
     cudaFree(ctx->npconv); cudaFree(ctx->schur_mask); cudaFree(ctx->schur_tmp);
     free(ctx->qrules);
+    free(ctx->p2rules);
     hemo_tet_free(ctx);
     cudaFree(ctx->pc_in); cudaFree(ctx->pc_out); cudaFree(ctx->pc_mask); cudaFree(ctx->kry_coef); cudaFree(ctx->a01);
     cudaFree(ctx->pc_tmp_u); cudaFree(ctx->pc_tmp_u2); cudaFree(ctx->pc_tmp_p); cudaFree(ctx->pc_tmp_p2);

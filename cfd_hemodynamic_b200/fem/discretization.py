@@ -83,3 +83,18 @@ def dirichlet_arrays(n_nodes: int, cells: np.ndarray, bcs, gdim: int = 2):
         nodeflag |= flag[k:nu:gdim].astype(bool)
     cellflag = nodeflag[cells].any(axis=1).astype(np.uint8)
     return flag, mult, cellflag, g
+
+
+def p2_nodes(mesh: Mesh):
+    """Node set and cell table of the P2 Lagrange space on a triangle mesh (3P: Basix / DOLFINx dof layout):
+    one node per vertex, then one per edge (= facet in 2-D) at its mid-point; a cell lists its three vertex nodes and
+    then the nodes of the edges opposite local vertices 0, 1, 2.  Returns (x (Nv + Ne, 2), cells6 (E, 6) int32)."""
+    if mesh.topology.cell_name() != "triangle":
+        raise NotImplementedError("P2 node layout is implemented for triangles")
+    x = mesh.geometry.x[:, :2]
+    nv = x.shape[0]
+    fv = mesh.topology.facet_vertices
+    xe = 0.5 * (x[fv[:, 0]] + x[fv[:, 1]])
+    c2f = mesh.topology.cell_facets
+    cells6 = np.hstack([mesh.geometry.dofmap, nv + c2f]).astype(np.int32)
+    return np.ascontiguousarray(np.vstack([x, xe])), np.ascontiguousarray(cells6)

@@ -6,8 +6,9 @@ src/boundaryCondition.py:33-52 (`locate_dofs_topological`, `dirichletbc`,
 `Function.interpolate`), src/scenario.py:151-159 (`dofmap.index_map.size_global`,
 `index_map_bs`), src/scenario.py:306-307 (`Function.x.array`).
 
-Only Lagrange P1 on simplices is generated here (one dof per vertex, dof
-index == vertex index).  A blocked space shares the scalar dofmap and
+Lagrange P1 (one dof per vertex, dof index == vertex index) on every cell type and P2 on triangles
+(vertex dofs, then one dof per edge at its mid-point; cell order: vertices 0, 1, 2, then the edges
+opposite them — the Basix layout).  A blocked space shares the scalar dofmap and
 stores values interleaved (`bs*node + comp`), like DOLFINx.
 """
 from __future__ import annotations
@@ -38,16 +39,21 @@ class _DofMap:
 class FunctionSpace:
     def __init__(self, mesh: Mesh, family: str = "Lagrange", degree: int = 1,
                  shape: tuple | None = None):
-        if degree != 1:
-            raise NotImplementedError(
-                "only P1 spaces are generated by the standalone host shim "
-                "(P2 is a SURVEY §8(f)/north_star follow-up)")
+        if degree not in (1, 2) or (degree == 2 and mesh.topology.cell_name() != "triangle"):
+            raise NotImplementedError("the standalone host shim generates P1 spaces and P2 spaces on triangles")
         self.mesh = mesh
         self.family = family
         self.degree = degree
         self.shape = tuple(shape) if shape else ()
         bs = int(np.prod(self.shape)) if self.shape else 1
-        self.dofmap = _DofMap(mesh.geometry.dofmap, mesh.geometry.x.shape[0], bs)
+        if degree == 1:
+            self._x = mesh.geometry.x
+            self.dofmap = _DofMap(mesh.geometry.dofmap, mesh.geometry.x.shape[0], bs)
+        else:
+            from .discretization import p2_nodes
+            x2, cells6 = p2_nodes(mesh)
+            self._x = np.hstack([x2, np.zeros((x2.shape[0], 1))])
+            self.dofmap = _DofMap(cells6, x2.shape[0], bs)
         self.value_size = bs
 
     @property
@@ -55,7 +61,7 @@ class FunctionSpace:
         return self.dofmap.index_map.size_local
 
     def tabulate_dof_coordinates(self) -> np.ndarray:
-        return self.mesh.geometry.x
+        return self._x
 
 
 def functionspace(mesh: Mesh, element) -> FunctionSpace:
@@ -157,8 +163,12 @@ def locate_dofs_topological(V: FunctionSpace, entity_dim: int, entities) -> np.n
     src/boundaryCondition.py:36."""
     topo = V.mesh.topology
     assert entity_dim == topo.dim - 1, "only facet entities are used by the scenarios"
-    fv = topo.facet_vertices[np.asarray(entities, dtype=np.int64)]
-    return np.unique(fv.reshape(-1)).astype(np.int32)
+    entities = np.asarray(entities, dtype=np.int64)
+    fv = topo.facet_vertices[entities]
+    dofs = fv.reshape(-1)
+    if getattr(V, "degree", 1) == 2:         # P2 triangles: plus the dof of the facet's own edge
+        dofs = np.concatenate([dofs, V.mesh.geometry.x.shape[0] + entities])
+    return np.unique(dofs).astype(np.int32)
 
 
 def locate_dofs_geometrical(V: FunctionSpace, marker) -> np.ndarray:

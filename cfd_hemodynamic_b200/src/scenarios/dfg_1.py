@@ -103,6 +103,12 @@ class DFG1Benchmark(Scenario):
         FL = float(np.sum(-length * (self.mu * dut_dn * n[:, 0] + pbar * n[:, 1])))
         return 500 * FD, 500 * FL
 
+    def drag_lift_consistent(self):
+        """Cd, Cl from the consistent nodal forces on the cylinder (`Solver.consistent_boundary_force`), times 500."""
+        nodes = np.unique(self.mesh.topology.facet_vertices[self._ft.find(self.obstacle_marker)])
+        fx, fy = self.solver.consistent_boundary_force(nodes)
+        return 500 * fx, 500 * fy
+
     def drag_lift_device(self):
         """Same integrals evaluated by `hemo_boundary_force` from the device state (no D2H of the fields)."""
         fd, fl = self.solver.boundary_force_device(self._ft.find(self.obstacle_marker))

@@ -29,6 +29,9 @@ BLOCK_DEGREE = {Q_FU: 12, Q_FP: 11, Q_UU: 12, Q_UP: 11, Q_PU: 11, Q_PP: 10}
 # Q1 quadrilaterals: Q1 counts as degree 2 and derivatives keep the degree:
 # tau(14) R(4) (u_m.grad v)(4) = 22, PSPG/J_up/J_pu 20, J_pp 18 -> 12x12 / 11x11 / 10x10 Gauss points
 BLOCK_DEGREE_QUAD = {Q_FU: 22, Q_FP: 20, Q_UU: 22, Q_UP: 20, Q_PU: 20, Q_PP: 18}
+# P2-P2 triangles (p_grade = 2): tau(14) R(3) (u_m.grad v)(3) = 20, PSPG / J_up / J_pu 18, J_pp 16; facet terms 6
+BLOCK_DEGREE_P2 = {Q_FU: 20, Q_FP: 18, Q_UU: 20, Q_UP: 18, Q_PU: 18, Q_PP: 16}
+FACET_POINTS_P2 = 4
 
 # facet-set slots in the library (SET_WSS: all exterior facets with zero coefficients, only tagged
 # for the device post-processing kernels)
@@ -52,10 +55,15 @@ class StabilizedSchurB200(SolverBase):
             raise NotImplementedError(
                 f"cell type {cell}: {', '.join(self._supported_cells)} cells are implemented on the device for this solver")
         self._quad = cell == "quadrilateral"
-        if int(kw.pop("p_grade", 1)) != 1:
-            raise NotImplementedError("p_grade != 1: only P1-P1 is implemented on the device")
-        super().initVelocitySpace("Lagrange", cell, 1, shape=(mesh.geometry.dim,))
-        super().initPressureSpace("Lagrange", cell, 1)
+        # p_grade: Lagrange degree of BOTH spaces (stabilized_schur_pressure_backflow.py:71,102-106;
+        # stabilized_schur_backflow.py:63,85-87); 2 = P2-P2 on triangles, "nodes" are then the P2 dof points
+        self.p_grade = int(kw.pop("p_grade", 1))
+        if self.p_grade not in (1, 2) or (self.p_grade == 2 and cell != "triangle"):
+            raise NotImplementedError(f"p_grade = {self.p_grade} on {cell} cells: P1-P1 on every supported cell type and "
+                                      "P2-P2 on triangles are implemented on the device")
+        self._p2 = self.p_grade == 2
+        super().initVelocitySpace("Lagrange", cell, self.p_grade, shape=(mesh.geometry.dim,))
+        super().initPressureSpace("Lagrange", cell, self.p_grade)
         if initial_velocity:
             self.u_prev.interpolate(initial_velocity)
 
@@ -95,9 +103,9 @@ class StabilizedSchurB200(SolverBase):
         self.reason = 0
         self.hemo = None
         if self._host_only:
-            self.n = mesh.geometry.x.shape[0]
+            self._cells_host = np.ascontiguousarray(self.V.dofmap.list, dtype=np.int32)
+            self.n = self.V.num_nodes
             self.N = 3 * self.n
-            self._cells_host = np.ascontiguousarray(mesh.geometry.dofmap, dtype=np.int32)
             if self.variant == "schur":
                 self._register_facets(SET_ALL, exterior_facet_indices(mesh.topology), a_p=1.0, a_g=1.0)
         else:
@@ -110,8 +118,9 @@ class StabilizedSchurB200(SolverBase):
         self.hemo = Hemo(self._device_index)
         dev = self.hemo.device
         mesh = self.mesh
-        x = np.ascontiguousarray(mesh.geometry.x[:, :2])
-        cells = np.ascontiguousarray(mesh.geometry.dofmap, dtype=np.int32)
+        # nodes = dof points of the (equal-order) spaces: the mesh vertices for P1 / Q1, vertices + edge mid-points for P2
+        x = np.ascontiguousarray(self.V.tabulate_dof_coordinates()[:, :2])
+        cells = np.ascontiguousarray(self.V.dofmap.list, dtype=np.int32)
         self.n = n = x.shape[0]
         self.N = 3 * n
         E = cells.shape[0]
@@ -121,13 +130,13 @@ class StabilizedSchurB200(SolverBase):
                            torch.from_numpy(np.ascontiguousarray(h)).to(dev))
         self._nrowptr, self._ncol = D.node_graph(cells, n)
         self.hemo.set_node_graph(torch.from_numpy(self._nrowptr).to(dev), torch.from_numpy(self._ncol).to(dev))
-        for block, deg in (BLOCK_DEGREE_QUAD if self._quad else BLOCK_DEGREE).items():
+        for block, deg in (BLOCK_DEGREE_QUAD if self._quad else BLOCK_DEGREE_P2 if self._p2 else BLOCK_DEGREE).items():
             if self._rules:
                 pts, wts = self._rules[block]
             else:
                 pts, wts = Q.quadrilateral_rule(deg) if self._quad else Q.triangle_rule(deg)
             self.hemo.set_quadrature(block, pts, wts)
-        self.hemo.set_facet_quadrature(*Q.interval_gauss(Q.FACET_POINTS_QUAD if self._quad else 2))
+        self.hemo.set_facet_quadrature(*Q.interval_gauss(Q.FACET_POINTS_QUAD if self._quad else FACET_POINTS_P2 if self._p2 else 2))
         eps0 = float(np.finfo(np.float64).resolution)
         fval = np.asarray(self.f.value, dtype=np.float64).reshape(-1)
         self.hemo.set_params(float(self.dt.value), float(self.rho.value), float(self.mu.value), fval[:2], eps0)
@@ -172,7 +181,7 @@ class StabilizedSchurB200(SolverBase):
         objects in list order, facet sets as (cell, local facet) pairs with coefficients."""
         topo = self.mesh.topology
         return dict(
-            x=np.ascontiguousarray(self.mesh.geometry.x[:, :2]), cells=self._cells_host,
+            x=np.ascontiguousarray(self.V.tabulate_dof_coordinates()[:, :2]), cells=self._cells_host,
             bcs=[("u", bc.block_dofs.copy(), bc.g.x.array.copy()) for bc in self.bcu_d]
                 + [("p", bc.block_dofs.copy(), bc.g.x.array.copy()) for bc in self.bcp_d],
             facet_sets={sid: (topo.facet_cell_pairs(f), c) for sid, (f, c) in self._facet_tables.items()},
@@ -239,9 +248,10 @@ class StabilizedSchurB200(SolverBase):
         self._g_host = g
         self._g_last = None
         if flag.any():
-            self.hemo.set_bc(torch.from_numpy(flag).to(dev), torch.from_numpy(mult).to(dev),
-                             torch.from_numpy(cellflag).to(dev))
+            self._bc_dev = (torch.from_numpy(flag).to(dev), torch.from_numpy(mult).to(dev), torch.from_numpy(cellflag).to(dev))
+            self.hemo.set_bc(*self._bc_dev)
         else:
+            self._bc_dev = None
             self.hemo.set_bc(None, None, None)
         self._has_bc = bool(flag.any())
         self._upload_bc_values()
@@ -262,6 +272,8 @@ class StabilizedSchurB200(SolverBase):
             # Dirichlet-like pressure condition wherever the velocity is free on the boundary
             ext = exterior_facet_indices(self.mesh.topology)
             bnodes = np.unique(self.mesh.topology.facet_vertices[ext])
+            if self._p2:                     # plus the edge nodes of the boundary facets
+                bnodes = np.union1d(bnodes, self.mesh.geometry.x.shape[0] + ext)
             p_open = np.setdiff1d(bnodes, u_nodes)
         self._nullspace = self._test_nullspace()
         self.linear = BlockSchurSolver(
@@ -414,6 +426,8 @@ class StabilizedSchurB200(SolverBase):
         """Reference :144-174; additionally tags the exterior facets on the device so that
         `assemble_wss_device` can run without host work."""
         super().initStressForm()
+        if self._p2:
+            return                            # the device post-processing kernels are P1 / Q1 (include/hemo.h)
         if self.hemo is not None:
             self._register_facets(SET_WSS, exterior_facet_indices(self.mesh.topology))
             self.d_wss = self._torch.zeros(2 * self.n, dtype=self._torch.float64, device=self.hemo.device)
@@ -434,6 +448,32 @@ class StabilizedSchurB200(SolverBase):
             self._register_facets(SET_FORCE, facets)
             self._force_key = key
         return self.hemo.boundary_force(SET_FORCE, self.d_x)
+
+    def consistent_boundary_force(self, nodes):
+        """Force the fluid exerts on the boundary nodes `nodes`, from the momentum residual itself (consistent nodal
+        forces): minus the sum of the rows of the raw residual (no Dirichlet treatment, no all-facet boundary term, time
+        level u = u_prev) at those nodes.  With v = 1 on the body and the discrete equations satisfied elsewhere this is
+        int (sigma n) ds tested with the finite-element extension of v — it converges at twice the rate of the
+        boundary-gradient formula the reference's post-processing uses (src/scenarios/dfg_1.py:183-202) and serves as an
+        independent anchor on the literature values (tests/test_gpu_literature.py)."""
+        torch = self._torch
+        hemo = self.hemo
+        n = self.n
+        saved = {sid: dict(c) for sid, (f, c) in self._facet_tables.items()}
+        for sid in saved:
+            hemo.set_facet_coef(sid)                       # all coefficients zero: cell integrals only
+        hemo.set_bc(None, None, None)
+        un_saved = self.d_un.clone()
+        self.d_un.copy_(self.d_x[:2 * n])                   # steady state: (u - u_prev)/dt = 0, u_mid = u
+        hemo.assemble_residual(self.d_x, self.d_un, None, self.d_t)
+        self.d_un.copy_(un_saved)
+        for sid, c in saved.items():
+            hemo.set_facet_coef(sid, **c)
+        if self._bc_dev is not None:
+            hemo.set_bc(*self._bc_dev)
+        idx = torch.as_tensor(np.asarray(nodes, dtype=np.int64), device=hemo.device)
+        r = self.d_t[:2 * n].reshape(-1, 2).index_select(0, idx).sum(dim=0).cpu().numpy()
+        return -float(r[0]), -float(r[1])
 
     def l2_norms_device(self):
         """sqrt(int |u|^2), sqrt(int p^2) of the final state (scenario.py:315-324)."""

@@ -104,7 +104,13 @@ int hemo_prof_get(hemo_ctx* ctx, int kernel_class, double* ms_total, int64_t* la
  * before hemo_set_mesh; changing the type drops the mesh, the node graph and the quadrature
  * rules set earlier (rules belong to a cell type: triangle rules have weights summing to 1/2,
  * quadrilateral rules live on [0,1]^2 and sum to 1). */
-enum { HEMO_CELL_TRIANGLE = 0, HEMO_CELL_QUADRILATERAL = 1, HEMO_CELL_TETRAHEDRON = 2 };
+/* HEMO_CELL_TRIANGLE_P2: P2-P2 triangles, `p_grade = 2` of src/solvers/stabilized_schur_pressure_backflow.py:71,102-106 and
+ * stabilized_schur_backflow.py:63,85-87.  "Nodes" are then the P2 dof points: cells are n_cells*6 int32 (three vertex nodes,
+ * then the nodes of the edges opposite local vertices 0, 1, 2 — the Basix dof order), x holds the coordinates of all nodes
+ * (the affine geometry is read from the vertex nodes), every nodal array / the node graph / the CSR layout works as for P1
+ * with one (u_x, u_y, p) triple per node; rules: points on the reference triangle, weights sum to 1/2, nq <= 128;
+ * facet rule on [0,1], nq <= 8.  The per-step post-processing kernels are P1 / Q1 only. */
+enum { HEMO_CELL_TRIANGLE = 0, HEMO_CELL_QUADRILATERAL = 1, HEMO_CELL_TETRAHEDRON = 2, HEMO_CELL_TRIANGLE_P2 = 3 };
 int hemo_set_cell_type(hemo_ctx* ctx, int cell_type);
 /* mesh.geometry.x / .dofmap / mesh.h (src/solvers/stabilized_schur.py:55-58,83-88).
  * x: n_nodes*2 doubles, cells: n_cells*(3|4) int32, h: n_cells doubles; borrowed. */

@@ -323,6 +323,9 @@ def outlet_flux(prob, pairs, Un_nodal):
     if prob.cells.shape[1] == 4:
         from . import q1_oracle
         return q1_oracle.outlet_flux(prob, pairs, Un_nodal)
+    if prob.cells.shape[1] == 6:
+        from . import pk_oracle
+        return pk_oracle.outlet_flux(prob, pairs, Un_nodal)
     cells = prob.cells[pairs[:, 0]]
     lf = pairs[:, 1]
     X = prob.x[cells]
@@ -357,6 +360,9 @@ def _kernels(prob):
     if prob.cells.shape[1] == 4:
         from . import q1_oracle
         return q1_oracle
+    if prob.cells.shape[1] == 6:          # P2-P2 triangles (3 vertex + 3 edge nodes per cell)
+        from . import pk_oracle
+        return pk_oracle
     import sys
     return sys.modules[__name__]
 

@@ -32,11 +32,15 @@ def problem_from_solver(s, facet_tags=None, tags=None, rules=None):
         deg = ({"Fu": 22, "Fp": 20, "uu": 22, "up": 20, "pu": 20, "pp": 18} if quad
                else {"Fu": 12, "Fp": 11, "uu": 12, "up": 11, "pu": 11, "pp": 10})
         rules = {k: (Q.quadrilateral_rule(d) if quad else Q.triangle_rule(d)) for k, d in deg.items()}
-    cells = mesh.geometry.dofmap
+    p2 = getattr(s, "p_grade", 1) == 2
+    cells = np.ascontiguousarray(s.V.dofmap.list)            # P2: three vertex nodes + three edge nodes per cell
+    xn = s.V.tabulate_dof_coordinates()[:, :2].copy()
+    if p2:
+        rules = {k: Q.triangle_rule(d) for k, d in {"Fu": 20, "Fp": 18, "uu": 20, "up": 18, "pu": 18, "pp": 16}.items()}
     fval = np.asarray(s.f.value, dtype=float).reshape(-1)[:2]
-    prob = O.Problem(x=mesh.geometry.x[:, :2].copy(), cells=cells, h=mesh.h(2, np.arange(cells.shape[0])),
+    prob = O.Problem(x=xn, cells=cells, h=mesh.h(2, np.arange(cells.shape[0])),
                      dt=float(s.dt.value), rho=float(s.rho.value), mu=float(s.mu.value), f=fval, rules=rules,
-                     facet_rule=Q.interval_gauss(Q.FACET_POINTS_QUAD if quad else 2))
+                     facet_rule=Q.interval_gauss(Q.FACET_POINTS_QUAD if quad else 4 if p2 else 2))
     bcs = [("u", bc.block_dofs, bc.g.x.array.copy()) for bc in s.bcu_d]
     bcs += [("p", bc.block_dofs, bc.g.x.array.copy()) for bc in s.bcp_d]
     prob.bcs = oracle_bcs(bcs)

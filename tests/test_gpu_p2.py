@@ -1,0 +1,99 @@
+"""P2-P2 triangles (`p_grade = 2`, reference stabilized_schur_pressure_backflow.py:71,102-106) on the GPU, through the C-ABI:
+pattern bit-exact, Jacobian / residual (cells + every facet term + Dirichlet rows / lifting / set_bc) <= 1e-12 against
+oracle/pk_oracle.py, and the plugin-level solve of the pressure-driven stenosis <= 1e-8 against the oracle's LU Newton."""
+import numpy as np
+import pytest
+
+from tests import common as T
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TIGHT = dict(snes_rtol=1e-12, snes_stol=0.0, ksp_rtol=1e-11, ksp_restart=150)
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _p2_case(seed=4):
+    from cfd_hemodynamic_b200.fem import discretization as D
+    from cfd_hemodynamic_b200.fem import mesh as M
+    from cfd_hemodynamic_b200.fem import quadrature as Q
+    from oracle import ns_oracle as O
+    from oracle import pk_oracle as PK
+    mesh = T.perturbed_square(5, 4, seed=seed)
+    x, cells6 = D.p2_nodes(mesh)
+    deg = {"Fu": 20, "Fp": 18, "uu": 20, "up": 18, "pu": 18, "pp": 16}
+    prob = O.Problem(x=x, cells=cells6, h=PK.cell_diameter(x, cells6), dt=0.01, rho=1.3, mu=0.02, f=np.array([0.3, -0.2]),
+                     rules={k: Q.triangle_rule(d) for k, d in deg.items()}, facet_rule=Q.interval_gauss(4))
+    ext = M.exterior_facet_indices(mesh.topology)
+    xm = x[mesh.topology.facet_vertices[ext]].mean(axis=1)
+    left = ext[xm[:, 0] < 1e-9]
+    right = ext[xm[:, 0] > 1 - 1e-9]
+    walls = ext[(xm[:, 1] < 1e-9) | (xm[:, 1] > 1 - 1e-9)]
+    fsets = [(left, dict(pconst=0.4, a_n=1.0, beta_n=50.0)), (right, dict(pconst=0.1, a_s=1.0, a_b=1.0, beta_b=0.2))]
+    prob.facet_sets = [O.FacetSet(pairs=mesh.topology.facet_cell_pairs(f), **c) for f, c in fsets]
+    nv = mesh.geometry.x.shape[0]
+    wall_nodes = np.union1d(np.unique(mesh.topology.facet_vertices[walls]), nv + walls)
+    g = np.zeros(2 * prob.n)
+    g[0::2] = 0.05 * np.sin(3 * x[:, 0])
+    corner = np.array([0], dtype=np.int64)
+    bcs = [("u", wall_nodes, g), ("u", corner, np.zeros(2 * prob.n)), ("p", np.array([nv - 1]), np.full(prob.n, 0.3))]
+    prob.bcs = T.oracle_bcs(prob, bcs)
+    return mesh, prob, fsets, bcs
+
+
+def test_p2_assembly_matches_oracle():
+    from cfd_hemodynamic_b200._lib import Hemo
+    from oracle import ns_oracle as O
+    mesh, prob, fsets, bcs = _p2_case()
+    n = prob.n
+    hemo = Hemo(0)
+    g, _ = T.setup_gpu(hemo, mesh, prob, fsets, bcs)
+    dev = hemo.device
+    u, p, un = T.smooth_fields(prob.x)
+    xd = torch.tensor(np.concatenate([u, p]), device=dev)
+    und = torch.tensor(un, device=dev)
+    vals = torch.zeros(hemo.nnz, dtype=torch.float64, device=dev)
+    b = torch.zeros(3 * n, dtype=torch.float64, device=dev)
+    hemo.assemble_jacobian(xd, und, vals)
+    hemo.assemble_residual(xd, und, g, b)
+    rowptr, col = hemo.get_pattern()
+    rp, ci = O.sparsity_pattern(prob)
+    assert np.array_equal(rowptr.cpu().numpy(), rp) and np.array_equal(col.cpu().numpy(), ci)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((vals.cpu().numpy(), ci, rp), shape=(3 * n, 3 * n))
+    A_ref = O.assemble_J(prob, u, p, un)
+    assert np.linalg.norm((A - A_ref).toarray()) <= 1e-12 * np.linalg.norm(A_ref.data)
+    b_ref = O.assemble_F(prob, np.concatenate([u, p]), un)
+    assert _rel(b.cpu().numpy(), b_ref) < 1e-12
+    # multiplicity 2 on the corner dof shared by two velocity conditions
+    d = A.diagonal()
+    assert d[0] == 2.0 and d[1] == 2.0
+    q_ref = O.outlet_flux(prob, prob.facet_sets[1].pairs, un)
+    assert abs(hemo.outlet_flux(1, und) - q_ref) <= 1e-12 * max(1.0, abs(q_ref))
+    hemo.close()
+
+
+@pytest.mark.parametrize("double_setup", [False, True])
+def test_p2_pressure_backflow_plugin_matches_oracle(double_setup):
+    from cfd_hemodynamic_b200.src.scenarios.stenosis_pressure_structured import StenosisPressureStructuredSimulation
+    from oracle.workload import CpuMarcher
+    sc = StenosisPressureStructuredSimulation("stabilized_schur_pressure_backflow", 0.005, 0.02, grade="moderate",
+                                              cell_type="triangle", p_inlet=2.0, R_resistance=50.0, res=0.8, L=20.0,
+                                              x_position_stenosis=8.0, p_grade=2, **TIGHT)
+    if double_setup:
+        sc.setup()
+    s = sc.solver
+    assert s.p_grade == 2 and s._cells_host.shape[1] == 6 and s.n == s.mesh.geometry.x.shape[0] + s.mesh.topology.facet_vertices.shape[0]
+    m = CpuMarcher(sc, solver="lu", rtol=1e-12, stol=0.0)
+    n = s.n
+    for _ in range(3):
+        s.solveStep()
+        s.u_prev.x.array[:] = s.u_sol.x.array[:]
+        s.p_prev.x.array[:] = s.p_sol.x.array[:]
+        m.step()
+    assert abs(s._p_c - m.outlet["pc"]) <= 1e-9 * max(1.0, abs(m.outlet["pc"]))
+    assert _rel(s.u_sol.x.array, m.x[:2 * n]) < 1e-8
+    assert _rel(s.p_sol.x.array, m.x[2 * n:]) < 1e-8

@@ -25,9 +25,10 @@ while t < T:
     if i % 100 == 0 or t >= T:
         cd, cl = sc.drag_lift()
         dp = sc.pressure_difference()
+        cdc, clc = sc.drag_lift_consistent()
         rel = np.abs(s.u_sol.x.array - s.u_prev.x.array).max() / max(np.abs(s.u_sol.x.array).max(), 1e-12) / dt
-        hist.append((round(t, 3), cd, cl, dp))
-        print(f"t={t:6.2f} Cd={cd:.5f} Cl={cl:.6f} dp={dp:.6f} du/dt_rel={rel:.2e} its=({s.its_snes},{s.its_ksp}) wall={time.time()-t0:.1f}s")
+        hist.append((round(t, 3), cd, cl, dp, cdc, clc))
+        print(f"t={t:6.2f} Cd={cd:.5f} Cl={cl:.6f} dp={dp:.6f} consistent Cd={cdc:.5f} Cl={clc:.6f} du/dt_rel={rel:.2e} its=({s.its_snes},{s.its_ksp}) wall={time.time()-t0:.1f}s")
     s.u_prev.x.array[:] = s.u_sol.x.array[:]
     s.p_prev.x.array[:] = s.p_sol.x.array[:]
 print(json.dumps({"refine": refine, "cells": int(s._cells_host.shape[0]), "final": hist[-1]}))
