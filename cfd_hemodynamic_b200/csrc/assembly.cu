@@ -1146,6 +1146,7 @@ extern "C" int hemo_set_body_force3(hemo_ctx* ctx, const double* f3_host) {
 
 extern "C" int hemo_set_facet_set(hemo_ctx* ctx, int set_id, const int32_t* cells_dev, const int32_t* mask_dev,
                                   int m, const hemo_facet_coef* coef) {
+    if (ctx) ctx->fset_version++;
     if (!ctx || set_id < 0 || set_id >= HEMO_MAX_FACET_SETS || m < 0) return HEMO_EINVAL;
     HemoFacetSet& fs = ctx->fsets[set_id];
     if (fs.cells) { cudaFree(fs.cells); fs.cells = nullptr; }

@@ -42,10 +42,12 @@ __device__ __forceinline__ void p2_load(P2Cell& cd, int c, const int32_t* __rest
     p2_prepare(cd, c_p2par);
 }
 
+// one pass (rule `rule`, block forms MASK) of the Jacobian: blockIdx.y = test node
+template <int MASK>
 __global__ void __launch_bounds__(128)
-k_p2_cell_jacobian(int E, int n, const int32_t* __restrict__ cells, const double* __restrict__ x, const double* __restrict__ h,
-                   const double* __restrict__ sol, const double* __restrict__ un, const double* __restrict__ uh,
-                   double* __restrict__ Ae) {
+k_p2_cell_jacobian(int E, int n, int rule, const int32_t* __restrict__ cells, const double* __restrict__ x,
+                   const double* __restrict__ h, const double* __restrict__ sol, const double* __restrict__ un,
+                   const double* __restrict__ uh, double* __restrict__ Ae) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= E) return;
     const int a = blockIdx.y;               // test node of this work item
@@ -54,7 +56,7 @@ k_p2_cell_jacobian(int E, int n, const int32_t* __restrict__ cells, const double
     p2_load(cd, c, cells, x, h, sol, un, uh, n, v);
     double* out = Ae + c;
     const int64_t stride = E;
-    p2_cell_jacobian_rows(cd, c_p2par, c_p2rules, a, [&](int slot, double val) { out[slot * stride] = val; });
+    p2_jac_pass_node<MASK>(cd, c_p2par, c_p2rules[rule], a, [&](int slot, double val) { out[slot * stride] = val; });
 }
 
 // lifting of a boundary-adjacent cell: Fe += Ae (g - x), out of line (it recomputes the Jacobian rows)
@@ -77,10 +79,15 @@ __device__ __noinline__ void p2_lift_device(int c, int E, int n, const int32_t* 
     const int64_t stride = E;
     for (int a = 0; a < 6; ++a) {
         double F[3] = {0.0, 0.0, 0.0};
-        p2_cell_jacobian_rows(cd, c_p2par, c_p2rules, a, [&](int slot, double val) {
+        auto acc = [&](int slot, double val) {
             const int r = slot % 9, b = (slot / 9) % 6;
             F[r / 3] += val * dl[b][r % 3];
-        });
+        };
+        // block by block (boundary-adjacent cells only: register pressure matters more than the repeated point set-up)
+        p2_jac_pass_node<P2_UU>(cd, c_p2par, c_p2rules[HEMO_Q_UU], a, acc);
+        p2_jac_pass_node<P2_UP>(cd, c_p2par, c_p2rules[HEMO_Q_UP], a, acc);
+        p2_jac_pass_node<P2_PU>(cd, c_p2par, c_p2rules[HEMO_Q_PU], a, acc);
+        p2_jac_pass_node<P2_PP>(cd, c_p2par, c_p2rules[HEMO_Q_PP], a, acc);
         Fe[(a * 3 + 0) * stride + c] += F[0];
         Fe[(a * 3 + 1) * stride + c] += F[1];
         Fe[(a * 3 + 2) * stride + c] += F[2];
@@ -236,9 +243,23 @@ int hemo_p2_cell_jacobian(hemo_ctx* ctx, const double* x_dev, const double* un_d
     if (rc) return rc;
     const int E = ctx->E;
     const double* uh = ctx->uh ? ctx->uh : un_dev;
-    k_p2_cell_jacobian<<<dim3(hemo_grid(E, 128), 6), 128, 0, ctx->stream>>>(E, ctx->n, ctx->cells, ctx->x, ctx->h, x_dev, un_dev,
-                                                                            uh, ctx->Ae);
-    HEMO_LAUNCH_CHECK(ctx);
+    int passes[4][2];
+    const int np = hemo_p2_jacobian_passes((const HemoP2Rule*)ctx->p2rules, passes);
+    const dim3 grid(hemo_grid(E, 128), 6);
+    for (int i = 0; i < np; ++i) {
+        const int r = passes[i][0];
+#define P2_LAUNCH(M) k_p2_cell_jacobian<M><<<grid, 128, 0, ctx->stream>>>(E, ctx->n, r, ctx->cells, ctx->x, ctx->h, x_dev, un_dev, uh, ctx->Ae)
+        switch (passes[i][1]) {
+            case P2_UU: P2_LAUNCH(P2_UU); break;
+            case P2_UP: P2_LAUNCH(P2_UP); break;
+            case P2_PU: P2_LAUNCH(P2_PU); break;
+            case P2_PP: P2_LAUNCH(P2_PP); break;
+            case (P2_UP | P2_PU): P2_LAUNCH((P2_UP | P2_PU)); break;
+            default: P2_LAUNCH(15); break;
+        }
+#undef P2_LAUNCH
+        HEMO_LAUNCH_CHECK(ctx);
+    }
     return 0;
 }
 

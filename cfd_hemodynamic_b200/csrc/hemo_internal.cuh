@@ -196,6 +196,9 @@ struct hemo_ctx {
     void* p2rules = nullptr;        // HEMO_NRULES host-side HemoP2Rule tables of the P2 triangle path (allocated on first use)
     HemoFacetRule frule{};
     HemoFacetSet fsets[HEMO_MAX_FACET_SETS];
+    int64_t fset_version = 0;        // bumped by every hemo_set_facet_set (caches keyed on a set's cells check it)
+    // deterministic 3-D wall-shear-stress gather (postproc.cu): cell -> index in the tagged set, per-cell contributions
+    int32_t* wss_cell2t = nullptr; double* wss_tmp = nullptr; int wss_set = -1; int64_t wss_version = -1;
     uint8_t* dofflag = nullptr;
     double* dofmult = nullptr;
     uint8_t* cellflag = nullptr;

@@ -245,100 +245,135 @@ HEMO_HD void p2_cell_residual(const P2Cell& c, const HemoForm& par, const HemoP2
 // ---- Jacobian rows of one test node -------------------------------------------------------------------------------
 // dR_k / dU_(b,l) = rho [ (a0 phi_b / dt + th um.g_b) d_kl + th phi_b G[l][k] ] - th mu [ lap_b d_kl + H_b[k][l] ]
 // emit(slot, value) with slot = (a*6+b)*9 + ri*3 + ci.
-template <int a, typename Emit>
-HEMO_HD void p2_cell_jacobian_rows_t(const P2Cell& c, const HemoForm& par, const HemoP2Rule* rules, Emit emit) {
+// One pass integrates the block forms in MASK (bit 0 J_uu, 1 J_up, 2 J_pu, 3 J_pp) with one rule; test node and mask
+// are compile-time constants, so every accumulator index is static (registers, no stack) and only the accumulators of
+// the blocks in the pass exist.
+#define P2_UU 1
+#define P2_UP 2
+#define P2_PU 4
+#define P2_PP 8
+
+template <int a, int MASK, typename Emit>
+HEMO_HD void p2_jac_pass(const P2Cell& c, const HemoForm& par, const HemoP2Rule& ru, Emit emit) {
     const double th = par.theta, rho = par.rho, mu = par.mu;
-    // group the block forms by identical rules (aliases) so that a shared rule is integrated once
-    bool done[6] = {true, true, false, false, false, false};
-    for (int r0 = HEMO_Q_UU; r0 <= HEMO_Q_PP; ++r0) {
-        if (done[r0]) continue;
-        bool in[6] = {false, false, false, false, false, false};
-        for (int r = r0; r <= HEMO_Q_PP; ++r)
-            if (!done[r] && (r == r0 || rules[r].alias == r0 || rules[r].alias == rules[r0].alias)) { in[r] = true; done[r] = true; }
-        const HemoP2Rule& ru = rules[r0];
-        double uu[6][2][2], up[6][2], pu[6][2], pp[6];
+    double uu[(MASK & P2_UU) ? 6 : 1][2][2], up[(MASK & P2_UP) ? 6 : 1][2], pu[(MASK & P2_PU) ? 6 : 1][2], pp[(MASK & P2_PP) ? 6 : 1];
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+        if (MASK & P2_UU) uu[b][0][0] = uu[b][0][1] = uu[b][1][0] = uu[b][1][1] = 0.0;
+        if (MASK & P2_UP) up[b][0] = up[b][1] = 0.0;
+        if (MASK & P2_PU) pu[b][0] = pu[b][1] = 0.0;
+        if (MASK & P2_PP) pp[b] = 0.0;
+    }
+    for (int q = 0; q < ru.nq; ++q) {
+        P2Point s;
+        p2_point(c, par, ru.pt[q][0], ru.pt[q][1], s);
+        const double w = ru.pt[q][2] * c.adet;
+        const double pa = s.phi[a], ga0 = s.g[a][0], ga1 = s.g[a][1], sa = s.umg[a];
+        const double ta = pa + s.tau * sa;                 // Galerkin + SUPG weight of the rho part of dR
+        const double gak[2] = {ga0, ga1};
 #pragma unroll
         for (int b = 0; b < 6; ++b) {
-            uu[b][0][0] = uu[b][0][1] = uu[b][1][0] = uu[b][1][1] = 0.0;
-            up[b][0] = up[b][1] = pu[b][0] = pu[b][1] = 0.0;
-            pp[b] = 0.0;
-        }
-        for (int q = 0; q < ru.nq; ++q) {
-            P2Point s;
-            p2_point(c, par, ru.pt[q][0], ru.pt[q][1], s);
-            const double w = ru.pt[q][2] * c.adet;
-            const double pa = s.phi[a], ga0 = s.g[a][0], ga1 = s.g[a][1], sa = s.umg[a];
-            const double ta = pa + s.tau * sa;                 // Galerkin + SUPG weight of the rho part of dR
+            const double pb = s.phi[b], gb0 = s.g[b][0], gb1 = s.g[b][1];
+            const double gbk[2] = {gb0, gb1};
+            const double cb = rho * (par.a0_dt * pb + th * s.umg[b]);
+            const double hb = th * rho * pb;
+            const double vb = th * mu;
+            const double Hb[2][2] = {{c.hess[b][0], c.hess[b][1]}, {c.hess[b][1], c.hess[b][2]}};
+            if (MASK & P2_UU) {
+                const double dd = ga0 * gb0 + ga1 * gb1;
 #pragma unroll
-            for (int b = 0; b < 6; ++b) {
-                const double pb = s.phi[b], gb0 = s.g[b][0], gb1 = s.g[b][1];
-                if (in[HEMO_Q_UU]) {
-                    const double cb = rho * (par.a0_dt * pb + th * s.umg[b]);
-                    const double hb = th * rho * pb;
-                    const double dd = ga0 * gb0 + ga1 * gb1;
-                    const double vb = th * mu;
-                    const double gak[2] = {ga0, ga1}, gbk[2] = {gb0, gb1};
-                    const double Hb[2][2] = {{c.hess[b][0], c.hess[b][1]}, {c.hess[b][1], c.hess[b][2]}};
-#pragma unroll
-                    for (int k = 0; k < 2; ++k)
-#pragma unroll
-                        for (int l = 0; l < 2; ++l) {
-                            const double dkl = (k == l) ? 1.0 : 0.0;
-                            const double C = cb * dkl + hb * s.G[l][k];                 // rho part of dR_k/dU_bl
-                            const double V = vb * (c.lapb[b] * dkl + Hb[k][l]);         // viscous strong part
-                            uu[b][k][l] += w * (ta * C - s.tau * sa * V + vb * (dd * dkl + gak[l] * gbk[k]) +
-                                                th * s.tau * s.R[k] * pb * gak[l] + th * s.taul * rho * gak[k] * gbk[l]);
-                        }
-                }
-                if (in[HEMO_Q_UP]) {
-                    up[b][0] += w * (-pb * ga0 + s.tau * sa * gb0);
-                    up[b][1] += w * (-pb * ga1 + s.tau * sa * gb1);
-                }
-                if (in[HEMO_Q_PU]) {
-                    const double cb = rho * (par.a0_dt * pb + th * s.umg[b]);
-                    const double hb = th * rho * pb;
-                    const double vb = th * mu;
-                    const double Hb[2][2] = {{c.hess[b][0], c.hess[b][1]}, {c.hess[b][1], c.hess[b][2]}};
-                    const double gak[2] = {ga0, ga1}, gbl[2] = {gb0, gb1};
+                for (int k = 0; k < 2; ++k)
 #pragma unroll
                     for (int l = 0; l < 2; ++l) {
-                        double t = 0.0;
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const double dkl = (k == l) ? 1.0 : 0.0;
-                            t += (cb * dkl + hb * s.G[l][k] - vb * (c.lapb[b] * dkl + Hb[k][l])) * gak[k];
-                        }
-                        pu[b][l] += w * (th * pa * gbl[l] + s.tau * par.inv_rho * t);
+                        const double dkl = (k == l) ? 1.0 : 0.0;
+                        const double C = cb * dkl + hb * s.G[l][k];                 // rho part of dR_k/dU_bl
+                        const double V = vb * (c.lapb[b] * dkl + Hb[k][l]);         // viscous strong part
+                        uu[b][k][l] += w * (ta * C - s.tau * sa * V + vb * (dd * dkl + gak[l] * gbk[k]) +
+                                            th * s.tau * s.R[k] * pb * gak[l] + th * s.taul * rho * gak[k] * gbk[l]);
                     }
-                }
-                if (in[HEMO_Q_PP]) pp[b] += w * s.tau * par.inv_rho * (ga0 * gb0 + ga1 * gb1);
             }
-        }
+            if (MASK & P2_UP) {
+                up[b][0] += w * (-pb * ga0 + s.tau * sa * gb0);
+                up[b][1] += w * (-pb * ga1 + s.tau * sa * gb1);
+            }
+            if (MASK & P2_PU) {
 #pragma unroll
-        for (int b = 0; b < 6; ++b) {
-            const int base = (a * 6 + b) * 9;
-            if (in[HEMO_Q_UU]) {
-                emit(base + 0, uu[b][0][0]); emit(base + 1, uu[b][0][1]);
-                emit(base + 3, uu[b][1][0]); emit(base + 4, uu[b][1][1]);
+                for (int l = 0; l < 2; ++l) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const double dkl = (k == l) ? 1.0 : 0.0;
+                        t += (cb * dkl + hb * s.G[l][k] - vb * (c.lapb[b] * dkl + Hb[k][l])) * gak[k];
+                    }
+                    pu[b][l] += w * (th * pa * gbk[l] + s.tau * par.inv_rho * t);
+                }
             }
-            if (in[HEMO_Q_UP]) { emit(base + 2, up[b][0]); emit(base + 5, up[b][1]); }
-            if (in[HEMO_Q_PU]) { emit(base + 6, pu[b][0]); emit(base + 7, pu[b][1]); }
-            if (in[HEMO_Q_PP]) emit(base + 8, pp[b]);
+            if (MASK & P2_PP) pp[b] += w * s.tau * par.inv_rho * (ga0 * gb0 + ga1 * gb1);
         }
+    }
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+        const int base = (a * 6 + b) * 9;
+        if (MASK & P2_UU) {
+            emit(base + 0, uu[b][0][0]); emit(base + 1, uu[b][0][1]);
+            emit(base + 3, uu[b][1][0]); emit(base + 4, uu[b][1][1]);
+        }
+        if (MASK & P2_UP) { emit(base + 2, up[b][0]); emit(base + 5, up[b][1]); }
+        if (MASK & P2_PU) { emit(base + 6, pu[b][0]); emit(base + 7, pu[b][1]); }
+        if (MASK & P2_PP) emit(base + 8, pp[b]);
     }
 }
 
-// run-time test node: one instantiation per node keeps every array index a compile-time constant (registers, no stack)
-template <typename Emit>
-HEMO_HD void p2_cell_jacobian_rows(const P2Cell& c, const HemoForm& par, const HemoP2Rule* rules, int a, Emit emit) {
+// run-time test node
+template <int MASK, typename Emit>
+HEMO_HD void p2_jac_pass_node(const P2Cell& c, const HemoForm& par, const HemoP2Rule& ru, int a, Emit emit) {
     switch (a) {
-        case 0: p2_cell_jacobian_rows_t<0>(c, par, rules, emit); break;
-        case 1: p2_cell_jacobian_rows_t<1>(c, par, rules, emit); break;
-        case 2: p2_cell_jacobian_rows_t<2>(c, par, rules, emit); break;
-        case 3: p2_cell_jacobian_rows_t<3>(c, par, rules, emit); break;
-        case 4: p2_cell_jacobian_rows_t<4>(c, par, rules, emit); break;
-        default: p2_cell_jacobian_rows_t<5>(c, par, rules, emit); break;
+        case 0: p2_jac_pass<0, MASK>(c, par, ru, emit); break;
+        case 1: p2_jac_pass<1, MASK>(c, par, ru, emit); break;
+        case 2: p2_jac_pass<2, MASK>(c, par, ru, emit); break;
+        case 3: p2_jac_pass<3, MASK>(c, par, ru, emit); break;
+        case 4: p2_jac_pass<4, MASK>(c, par, ru, emit); break;
+        default: p2_jac_pass<5, MASK>(c, par, ru, emit); break;
     }
+}
+
+// Passes of the Jacobian: block forms with identical rules (aliases) are integrated together when the combination is
+// one of the fused ones (J_up + J_pu; all four), otherwise block by block.  passes[i] = (rule id, mask); returns count.
+static inline int hemo_p2_jacobian_passes(const HemoP2Rule* rules, int passes[4][2]) {
+    bool done[6] = {true, true, false, false, false, false};
+    int np = 0;
+    for (int r0 = HEMO_Q_UU; r0 <= HEMO_Q_PP; ++r0) {
+        if (done[r0]) continue;
+        int mask = 0;
+        for (int r = r0; r <= HEMO_Q_PP; ++r)
+            if (!done[r] && (r == r0 || rules[r].alias == r0)) mask |= 1 << (r - HEMO_Q_UU);
+        if (mask != (P2_UP | P2_PU) && mask != 15) mask = 1 << (r0 - HEMO_Q_UU);      // not a fused combination: r0 alone
+        for (int r = HEMO_Q_UU; r <= HEMO_Q_PP; ++r)
+            if (mask & (1 << (r - HEMO_Q_UU))) done[r] = true;
+        passes[np][0] = r0; passes[np][1] = mask;
+        ++np;
+    }
+    return np;
+}
+
+template <typename Emit>
+HEMO_HD void p2_jac_pass_rt(const P2Cell& c, const HemoForm& par, const HemoP2Rule& ru, int a, int mask, Emit emit) {
+    switch (mask) {
+        case P2_UU: p2_jac_pass_node<P2_UU>(c, par, ru, a, emit); break;
+        case P2_UP: p2_jac_pass_node<P2_UP>(c, par, ru, a, emit); break;
+        case P2_PU: p2_jac_pass_node<P2_PU>(c, par, ru, a, emit); break;
+        case P2_PP: p2_jac_pass_node<P2_PP>(c, par, ru, a, emit); break;
+        case (P2_UP | P2_PU): p2_jac_pass_node<(P2_UP | P2_PU)>(c, par, ru, a, emit); break;
+        default: p2_jac_pass_node<15>(c, par, ru, a, emit); break;
+    }
+}
+
+// all rows of test node a (host checks, lifting of boundary-adjacent cells)
+template <typename Emit>
+inline void p2_cell_jacobian_rows(const P2Cell& c, const HemoForm& par, const HemoP2Rule* rules, int a, Emit emit) {
+    int passes[4][2];
+    const int np = hemo_p2_jacobian_passes(rules, passes);
+    for (int i = 0; i < np; ++i) p2_jac_pass_rt(c, par, rules[passes[i][0]], a, passes[i][1], emit);
 }
 
 // ---- exterior facets ------------------------------------------------------------------------------------------------

@@ -271,16 +271,46 @@ k_l2_partial(int E, int bs, const int32_t* __restrict__ cells, const double* __r
 }
 
 // ---- tetrahedra (bodies in tet_items.cuh) ------------------------------------------------------
-// A boundary vertex of a tetrahedral mesh collects the traction of every tagged facet around it, so
-// unlike in 2-D (two contributions per vertex) the atomic sums depend on the arrival order at
-// round-off level: the wall-shear-stress output is not bitwise reproducible in 3-D.
-__global__ void k_tet_wss(int m, const int32_t* __restrict__ fcells, const int32_t* __restrict__ fmask,
-                          const int32_t* __restrict__ cells, const double* __restrict__ x,
-                          const double* __restrict__ sol, double mu, double* __restrict__ out) {
+// A boundary vertex of a tetrahedral mesh collects the traction of every tagged facet around it.  Like every other
+// reduction of the library this one is atomic-free with a fixed order: pass 1 stores the contributions of each tagged
+// cell to its four vertices, pass 2 sums them per node in the order of the node's cell list (vseg) — bitwise
+// reproducible.
+__global__ void k_tet_wss_items(int m, const int32_t* __restrict__ fcells, const int32_t* __restrict__ fmask,
+                                const int32_t* __restrict__ cells, const double* __restrict__ x,
+                                const double* __restrict__ sol, double mu, double* __restrict__ tmp /* [m][4][3] */) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m) return;
-    tet_wss_item(t, fcells, fmask, cells, x, sol, mu,
-                 [out](int node, int k, double val) { atomicAdd(&out[3 * (int64_t)node + k], val); });
+    double acc[4][3];
+    for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = acc[a][2] = 0.0;
+    int v[4];
+    const int c = fcells[t];
+    for (int a = 0; a < 4; ++a) v[a] = cells[4 * (int64_t)c + a];
+    tet_wss_item(t, fcells, fmask, cells, x, sol, mu, [&](int node, int k, double val) {
+        for (int a = 0; a < 4; ++a)
+            if (v[a] == node) { acc[a][k] += val; break; }
+    });
+    for (int a = 0; a < 4; ++a)
+        for (int k = 0; k < 3; ++k) tmp[(int64_t)t * 12 + a * 3 + k] = acc[a][k];
+}
+
+__global__ void k_set_cell_index(int m, const int32_t* __restrict__ fcells, int32_t* __restrict__ cell2t) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < m) cell2t[fcells[t]] = t;
+}
+
+__global__ void k_tet_wss_gather(int n, const int32_t* __restrict__ vseg_ptr, const int32_t* __restrict__ vseg_src,
+                                 const int32_t* __restrict__ cell2t, const double* __restrict__ tmp, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int q = vseg_ptr[i]; q < vseg_ptr[i + 1]; ++q) {
+        const int src = vseg_src[q];
+        const int t = cell2t[src >> 2];
+        if (t < 0) continue;
+        const double* p = tmp + (int64_t)t * 12 + (src & 3) * 3;
+        a0 += p[0]; a1 += p[1]; a2 += p[2];
+    }
+    out[3 * (int64_t)i] = a0; out[3 * (int64_t)i + 1] = a1; out[3 * (int64_t)i + 2] = a2;
 }
 
 __global__ void __launch_bounds__(PP_THREADS)
@@ -312,9 +342,23 @@ extern "C" int hemo_wall_shear_stress(hemo_ctx* ctx, int set_id, const double* x
     HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(wss_dev, 0, sizeof(double) * ctx->dim * ctx->n, ctx->stream));
     if (fs.m == 0) return 0;
     const int grid = hemo_grid(fs.m, 128);
-    if (ctx->dim == 3)
-        k_tet_wss<<<grid, 128, 0, ctx->stream>>>(fs.m, fs.cells, fs.mask, ctx->cells, ctx->x, x_dev, ctx->par.mu, wss_dev);
-    else if (ctx->nv == 4)
+    if (ctx->dim == 3) {
+        if (!ctx->vseg_ptr) HEMO_FAIL(ctx, HEMO_ESTATE, "node graph not set");
+        int rc;
+        if (ctx->wss_set != set_id || ctx->wss_version != ctx->fset_version) {
+            if ((rc = hemo_alloc(ctx, &ctx->wss_cell2t, (size_t)ctx->E))) return rc;
+            if ((rc = hemo_alloc(ctx, &ctx->wss_tmp, (size_t)fs.m * 12))) return rc;
+            HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->wss_cell2t, 0xff, sizeof(int32_t) * ctx->E, ctx->stream));
+            k_set_cell_index<<<grid, 128, 0, ctx->stream>>>(fs.m, fs.cells, ctx->wss_cell2t);
+            HEMO_LAUNCH_CHECK(ctx);
+            ctx->wss_set = set_id;
+            ctx->wss_version = ctx->fset_version;
+        }
+        k_tet_wss_items<<<grid, 128, 0, ctx->stream>>>(fs.m, fs.cells, fs.mask, ctx->cells, ctx->x, x_dev, ctx->par.mu, ctx->wss_tmp);
+        HEMO_LAUNCH_CHECK(ctx);
+        k_tet_wss_gather<<<hemo_grid(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->n, ctx->vseg_ptr, ctx->vseg_src, ctx->wss_cell2t,
+                                                                         ctx->wss_tmp, wss_dev);
+    } else if (ctx->nv == 4)
         k_wss<4><<<grid, 128, 0, ctx->stream>>>(fs.m, ctx->n, fs.cells, fs.mask, ctx->cells, ctx->x, x_dev, ctx->par.mu, wss_dev);
     else
         k_wss<3><<<grid, 128, 0, ctx->stream>>>(fs.m, ctx->n, fs.cells, fs.mask, ctx->cells, ctx->x, x_dev, ctx->par.mu, wss_dev);

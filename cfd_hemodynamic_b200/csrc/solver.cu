@@ -596,6 +596,7 @@ extern "C" int hemo_ctx_destroy(hemo_ctx* ctx) {
     if (ctx->pc_graph_exec) cudaGraphExecDestroy(ctx->pc_graph_exec);
     if (ctx->pc_graph) cudaGraphDestroy(ctx->pc_graph);
     cudaFree(ctx->npconv); cudaFree(ctx->schur_mask); cudaFree(ctx->schur_tmp);
+    cudaFree(ctx->wss_cell2t); cudaFree(ctx->wss_tmp);
     free(ctx->qrules);
     free(ctx->p2rules);
     hemo_tet_free(ctx);

@@ -5,7 +5,8 @@ cube split into tetrahedra).
 `StabilizedSchurTetB200` sits between `StabilizedSchurB200` and the plugin's `Solver`: on triangles
 and quadrilaterals every method defers to the 2-D implementation unchanged; on tetrahedra it
 sequences the same C-ABI calls with the `[u interleaved (3n) | p (n)]` layout.
-Only the plain `stabilized_schur` variant is wired in 3-D.  Both time loops run: `Scenario.solve` (host
+Every variant of the family runs in 3-D (the boundary terms of stabilized_schur_pressure_backflow.py:170-217 are
+dimension-generic in csrc/simplex_element.cuh; production use: src/experiments/config/arteria_lad.yaml:19).  Both time loops run: `Scenario.solve` (host
 post-processing) and `Scenario.solve_device` (wall shear stress, early-stop and L2 norms as kernels).
 """
 from __future__ import annotations
@@ -30,8 +31,6 @@ class StabilizedSchurTetB200(StabilizedSchurB200):
 
     def __init__(self, mesh, dt, rho, mu, f, initial_velocity=None, **kw):
         self._tet = mesh.topology.cell_name() == "tetrahedron"
-        if self._tet and self.variant != "schur":
-            raise NotImplementedError("tetrahedra: only the plain stabilized_schur variant is implemented")
         super().__init__(mesh, dt, rho, mu, f, initial_velocity, **kw)
         if self._tet:
             self.N = 4 * self.n
@@ -59,7 +58,8 @@ class StabilizedSchurTetB200(StabilizedSchurB200):
         for block, deg in BLOCK_DEGREE.items():          # affine P1: the same estimated degrees as on triangles
             pts, wts = self._rules[block] if self._rules else Q.tetrahedron_rule(deg)
             self.hemo.set_quadrature(block, pts, wts)
-        self.hemo.set_facet_quadrature(*Q.triangle_rule(FACET_DEGREE_TET))
+        # all-facet term: degree 2; the backflow term (u_n.n)_- (u_m.v) and the Nitsche penalty of the hemodynamic variants: 4
+        self.hemo.set_facet_quadrature(*Q.triangle_rule(FACET_DEGREE_TET if self.variant == "schur" else 4))
         eps0 = float(np.finfo(np.float64).resolution)
         fval = np.zeros(3)
         fv = np.asarray(self.f.value, dtype=np.float64).reshape(-1)
@@ -84,8 +84,10 @@ class StabilizedSchurTetB200(StabilizedSchurB200):
             t.numpy()[:] = fn.x.array
             fn.x.array = t.numpy()
             self._pin[name] = t
-        # stabilized_schur.py:79 — the all-facet term is part of F in the ctor
-        self._register_facets(SET_ALL, exterior_facet_indices(mesh.topology), a_p=1.0, a_g=1.0)
+        # stabilized_schur.py:79 — the all-facet term is part of F in the ctor (the hemodynamic variants drop it,
+        # stabilized_schur_pressure_backflow.py:121-125)
+        if self.variant == "schur":
+            self._register_facets(SET_ALL, exterior_facet_indices(mesh.topology), a_p=1.0, a_g=1.0)
         self.linear = None
 
     def export_tables(self) -> dict:
@@ -121,6 +123,7 @@ class StabilizedSchurTetB200(StabilizedSchurB200):
             return super().setup(bcu, bcp, facet_tags=facet_tags, tags=tags)
         n = self.n
         self._setup_count += 1
+        self._facet_setup(facet_tags, tags)          # boundary terms of the variant (a second call doubles them)
         bcs = self._bc_tables(bcu, bcp)
         if self._host_only:
             return
@@ -147,9 +150,14 @@ class StabilizedSchurTetB200(StabilizedSchurB200):
         fu = flag[:3 * n].reshape(n, 3)
         u_nodes = np.nonzero(fu.any(axis=1))[0]
         p_nodes = np.nonzero(flag[3 * n:])[0]
+        p_open = None
+        if self.variant != "schur" and self.schur_open == "dirichlet":
+            # open (traction) boundaries: Dirichlet rows in the pressure operator of the Schur approximation (as in 2-D)
+            ext = exterior_facet_indices(self.mesh.topology)
+            p_open = np.setdiff1d(np.unique(self.mesh.topology.facet_vertices[ext]), u_nodes)
         self._nullspace = self._test_nullspace()
         self.linear = BlockSchurSolver(
-            self.hemo, self._nrowptr, self._ncol, u_nodes, p_nodes, p_open_nodes=None,
+            self.hemo, self._nrowptr, self._ncol, u_nodes, p_nodes, p_open_nodes=p_open,
             dt=float(self.dt.value), rho=float(self.rho.value), mu=float(self.mu.value),
             restart=self.ksp_restart, max_it=self.ksp_max_it, rtol=self.ksp_rtol, atol=self.ksp_atol,
             project_pressure=self._nullspace, **self._pc_kw)

@@ -7,7 +7,8 @@ from typing import Callable
 import numpy as np
 
 from ...fem import discretization as D
-from ._stabilized_common import SET_OUTLET, StabilizedSchurB200
+from ._stabilized_common import SET_OUTLET
+from ._stabilized_tet import StabilizedSchurTetB200 as StabilizedSchurB200      # triangles, quadrilaterals and tetrahedra
 
 
 class Solver(StabilizedSchurB200):

@@ -13,7 +13,8 @@ from typing import Callable
 import numpy as np
 
 from ...fem.space import Function
-from ._stabilized_common import StabilizedSchurB200
+from ._stabilized_common import SET_ALL
+from ._stabilized_tet import StabilizedSchurTetB200 as StabilizedSchurB200      # triangles, quadrilaterals and tetrahedra
 
 
 class Solver(StabilizedSchurB200):

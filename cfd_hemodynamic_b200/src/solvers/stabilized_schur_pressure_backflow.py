@@ -14,7 +14,8 @@ import numpy as np
 
 from ...fem import discretization as D
 from ...fem.mesh import QUAD_FACETS
-from ._stabilized_common import SET_INLET, SET_OUTLET, StabilizedSchurB200
+from ._stabilized_common import SET_INLET, SET_OUTLET
+from ._stabilized_tet import StabilizedSchurTetB200 as StabilizedSchurB200      # triangles, quadrilaterals and tetrahedra
 
 
 class Solver(StabilizedSchurB200):

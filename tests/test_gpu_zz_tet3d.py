@@ -303,3 +303,58 @@ def test_tet_schur_operators_and_loud_failures():
     with pytest.raises(HemoError):
         hemo.l2_norm_sq(T(u), 2)
     hemo.close()
+
+
+@pytest.mark.parametrize("double_setup", [False, True])
+def test_tet_pressure_backflow_plugin_matches_oracle(double_setup):
+    """The hemodynamic variant on tetrahedra (production use of the reference: src/experiments/config/arteria_lad.yaml:19
+    runs the stabilized_schur family on P1 tetrahedral artery meshes): weak inlet pressure + Nitsche, resistance outlet,
+    backflow stabilisation on a box channel through the plugin API, against the 3-D oracle's LU Newton (1e-8)."""
+    from cfd_hemodynamic_b200.fem import mesh as M
+    from cfd_hemodynamic_b200.fem import quadrature as Q
+    from cfd_hemodynamic_b200.fem.space import Function
+    from cfd_hemodynamic_b200.src.boundaryCondition import BoundaryCondition
+    from cfd_hemodynamic_b200.src.solvers.stabilized_schur_pressure_backflow import Solver
+    dt, rho, mu, p_in, R = 0.01, 1.0, 0.05, 3.0, 4.0
+    mesh = M.create_box((0.0, 0.0, 0.0), (2.0, 1.0, 1.0), 6, 3, 3)
+    x = mesh.geometry.x
+    cells = mesh.geometry.dofmap
+    n = x.shape[0]
+    ext = M.exterior_facet_indices(mesh.topology)
+    xm = x[mesh.topology.facet_vertices[ext]].mean(axis=1)
+    vals = np.where(xm[:, 0] < 1e-9, 2, np.where(xm[:, 0] > 2 - 1e-9, 3, 4)).astype(np.int32)
+    ft = M.MeshTags(mesh, 2, ext, vals)
+    tags = {"inlet": 2, "outlet": 3, "wall": 4, "obstacle": None}
+    tight = dict(snes_rtol=1e-12, snes_stol=0.0, ksp_rtol=1e-11, ksp_restart=150, amg_cycles_p=2)
+    s = Solver(mesh, dt, rho, mu, [0.0, 0.0, 0.0], None, p_inlet=p_in, R_resistance=R, **tight)
+    noslip = Function(s.V)
+    bcw = BoundaryCondition(noslip)
+    bcw.initTopological(2, ft.find(4))
+    s.setup([bcw], [], facet_tags=ft, tags=tags)
+    if double_setup:
+        s.setup([bcw], [], facet_tags=ft, tags=tags)
+    c = float(s._setup_count)
+    assert s._tet and s.variant == "pressure_backflow" and c == (2.0 if double_setup else 1.0)
+    rules = {k: Q.tetrahedron_rule(d) for k, d in dict(Fu=12, Fp=11, uu=12, up=11, pu=11, pp=10).items()}
+    pairs = mesh.topology.facet_cell_pairs
+    fs_in = O.FacetSet(pairs=pairs(ft.find(2)), pconst=c * p_in, a_n=c, beta_n=s.beta_nitsche)
+    fs_out = O.FacetSet(pairs=pairs(ft.find(3)), pconst=0.0, a_s=c, a_b=c, beta_b=s.beta_backflow)
+    prob = O3.Problem3D(x=x, cells=cells, dt=dt, rho=rho, mu=mu, f=np.zeros(3), rules=rules, facet_sets=[fs_in, fs_out],
+                        facet_rule=Q.triangle_rule(4))
+    wall_nodes = np.unique(mesh.topology.facet_vertices[ft.find(4)])
+    prob.bc_dofs = (3 * wall_nodes[:, None] + np.arange(3)[None, :]).reshape(-1)
+    xk, un, g = np.zeros(4 * n), np.zeros(3 * n), np.zeros(4 * n)
+    frozen, pc = [0.0] * (s._setup_count - 1), 0.0
+    for _ in range(3):
+        s.solveStep()
+        s.u_prev.x.array[:] = s.u_sol.x.array[:]
+        s.p_prev.x.array[:] = s.p_sol.x.array[:]
+        fs_out.pconst = 0.5 * (sum(frozen) + pc)
+        xk, _ = O3.newton_step(prob, xk, un, g, rtol=1e-12)
+        q = S.outlet_flux(x, cells, fs_out.pairs, un)                  # Q from the old u_prev (one-step lag)
+        pc = s.alpha_damping * R * abs(q) + (1.0 - s.alpha_damping) * pc
+        un = xk[:3 * n].copy()
+    assert pc > 0.0 and abs(s._p_c - pc) <= 1e-9 * max(1.0, pc)
+    eu = np.linalg.norm(s.u_sol.x.array - xk[:3 * n]) / np.linalg.norm(xk[:3 * n])
+    ep = np.linalg.norm(s.p_sol.x.array - xk[3 * n:]) / np.linalg.norm(xk[3 * n:])
+    assert eu < 1e-8 and ep < 1e-8, (eu, ep)
