@@ -377,13 +377,68 @@ k_cheb_start(int n, const int32_t* __restrict__ rowptr, const int32_t* __restric
     }
 }
 
+// Pre-smoothing from a zero iterate with one Chebyshev step, fused with the residual that follows it:
+//   x = D^-1 b / theta ;  r = b - A x
+// x_j is formed on the fly from (dinv_j, b_j) inside the row product, so the separate start kernel and its round trip
+// through x disappear (one launch less per level and cycle).  TB = double at the top level of the first cycle: the
+// fp64 right-hand side is read directly and its storage-precision copy written as a by-product (no conversion kernel).
+template <int BS, typename TB>
+__global__ void __launch_bounds__(256)
+k_presmooth_residual(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                     const areal* __restrict__ val, const areal* __restrict__ dinv, const TB* __restrict__ b,
+                     double inv_theta, areal* __restrict__ x, areal* __restrict__ r, areal* __restrict__ bcopy) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt >> 2, lane = gt & 3;
+    const bool ok = i < n;
+    const int r0 = ok ? rowptr[i] : 0, r1 = ok ? rowptr[i + 1] : 0;
+    double acc[BS];
+#pragma unroll
+    for (int k = 0; k < BS; ++k) acc[k] = 0.0;
+    for (int t = r0 + lane; t < r1; t += 8) {
+        const int t1 = t + 4;
+        const bool p1 = t1 < r1;
+        const int j0 = col[t];
+        const int j1 = p1 ? col[t1] : j0;
+        if (BS == 1) {
+            const double x0 = (double)dinv[j0] * (double)b[j0] * inv_theta;
+            const double x1 = (double)dinv[j1] * (double)b[j1] * inv_theta;
+            acc[0] = fma((double)val[t], x0, acc[0]);
+            acc[0] = fma(p1 ? (double)val[t1] : 0.0, x1, acc[0]);
+        } else {
+            const areal2* v2p = reinterpret_cast<const areal2*>(val);
+            const areal2 a0 = v2p[2 * (int64_t)t], b0 = v2p[2 * (int64_t)t + 1];
+            areal2 a1, b1;
+            a1.x = a1.y = b1.x = b1.y = 0;
+            if (p1) { a1 = v2p[2 * (int64_t)t1]; b1 = v2p[2 * (int64_t)t1 + 1]; }
+            const double xa0 = (double)dinv[2 * (int64_t)j0] * (double)b[2 * (int64_t)j0] * inv_theta;
+            const double xa1 = (double)dinv[2 * (int64_t)j0 + 1] * (double)b[2 * (int64_t)j0 + 1] * inv_theta;
+            const double xb0 = (double)dinv[2 * (int64_t)j1] * (double)b[2 * (int64_t)j1] * inv_theta;
+            const double xb1 = (double)dinv[2 * (int64_t)j1 + 1] * (double)b[2 * (int64_t)j1 + 1] * inv_theta;
+            acc[0] += (double)a0.x * xa0 + (double)a0.y * xa1 + (double)a1.x * xb0 + (double)a1.y * xb1;
+            acc[BS - 1] += (double)b0.x * xa0 + (double)b0.y * xa1 + (double)b1.x * xb0 + (double)b1.y * xb1;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < BS; ++k) {
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1, 4);
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2, 4);
+    }
+    if (ok && lane < BS) {
+        const int64_t q = (int64_t)i * BS + lane;
+        const double bv = (double)b[q];
+        x[q] = (areal)((double)dinv[q] * bv * inv_theta);
+        r[q] = (areal)(bv - (lane == 0 ? acc[0] : acc[BS - 1]));
+        if (bcopy) bcopy[q] = (areal)bv;
+    }
+}
+
 // one step: r -= D^-1 A d_old ; d_new = c1 d_old + c2 r ; x += d_new (+ d_old)
 template <int BS>
 __global__ void __launch_bounds__(256)
 k_cheb_step(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
             const areal* __restrict__ val, const areal* __restrict__ dinv, double c1, double c2,
             const areal* __restrict__ dold, areal* __restrict__ dnew, areal* __restrict__ r,
-            areal* __restrict__ x, int add_old) {
+            areal* __restrict__ x, int add_old, double* __restrict__ x64 /* optional fp64 copy of the result */) {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = gt >> 2, lane = gt & 3;
     const bool ok = i < n;
@@ -395,7 +450,9 @@ k_cheb_step(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict
         r[q] = rv;
         const double dv = c1 * dold[q] + c2 * rv;
         dnew[q] = dv;
-        x[q] += add_old ? (dv + dold[q]) : dv;
+        const double xn = (double)x[q] + (add_old ? (dv + (double)dold[q]) : dv);
+        x[q] = (areal)xn;
+        if (x64) x64[q] = xn;
     }
 }
 
@@ -995,7 +1052,7 @@ int hemo_amg_numeric(hemo_ctx* ctx, HemoAmg* amg) { return hemo_amg_numeric_shif
 
 template <int BS>
 static int smooth_t(hemo_ctx* ctx, const HemoAmgOp& A, const areal* b, areal* x, bool x_is_zero, int degree,
-                    double ratio) {
+                    double ratio, double* x64 = nullptr, bool* wrote64 = nullptr) {
     cudaStream_t st = ctx->stream;
     const double lmax = A.lmax, lmin = lmax / ratio;
     const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
@@ -1017,8 +1074,10 @@ static int smooth_t(hemo_ctx* ctx, const HemoAmgOp& A, const areal* b, areal* x,
         const double c1 = rho_new * rho, c2 = 2.0 * rho_new / delta;
         const bool fine = (A.n == ctx->n);
         if (fine) HEMO_PROF_BEGIN(ctx, BS == 2 ? HEMO_PROF_CHEB_U0 : HEMO_PROF_CHEB_P0);
+        const bool last = (k == degree - 1);
         k_cheb_step<BS><<<hemo_grid((int64_t)A.n * 4, 256), 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, A.dinv, c1, c2, d0, d1, A.r, x,
-                                                             pending ? 1 : 0);
+                                                             pending ? 1 : 0, last ? x64 : nullptr);
+        if (last && x64 && wrote64) *wrote64 = true;
         HEMO_LAUNCH_CHECK(ctx);
         if (fine) HEMO_PROF_END(ctx, BS == 2 ? HEMO_PROF_CHEB_U0 : HEMO_PROF_CHEB_P0);
         pending = false;
@@ -1033,7 +1092,8 @@ static int smooth_t(hemo_ctx* ctx, const HemoAmgOp& A, const areal* b, areal* x,
 }
 
 template <int BS>
-static int vcycle_t(hemo_ctx* ctx, HemoAmg* amg, int l, const areal* b, areal* x, bool x_is_zero) {
+static int vcycle_t(hemo_ctx* ctx, HemoAmg* amg, int l, const areal* b, areal* x, bool x_is_zero,
+                    const double* b64 = nullptr, double* x64 = nullptr, bool* wrote64 = nullptr) {
     cudaStream_t st = ctx->stream;
     const HemoAmgOp& A = amg->op[l];
     const int degree = ctx->opts.cheb_degree > 0 ? ctx->opts.cheb_degree : 2;
@@ -1072,9 +1132,25 @@ static int vcycle_t(hemo_ctx* ctx, HemoAmg* amg, int l, const areal* b, areal* x
         return 0;
     }
     int rc;
-    if ((rc = smooth_t<BS>(ctx, A, b, x, x_is_zero, degree_pre, ratio))) return rc;
-    // residual and restriction
-    if ((rc = hemo_bsr_spmv_ex(ctx, BS, A.n, A.rowptr, A.col, A.val, x, -1.0, b, A.r))) return rc;
+    if (x_is_zero && degree_pre == 1) {
+        // one Chebyshev step from zero + residual in one kernel
+        const double lmax = A.lmax, lmin = lmax / ratio;
+        const double inv_theta = 1.0 / (0.5 * (lmax + lmin));
+        const int g = hemo_grid((int64_t)A.n * 4, 256);
+        if (b64) k_presmooth_residual<BS, double><<<g, 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, A.dinv, b64, inv_theta, x, A.r,
+                                                                      const_cast<areal*>(b));
+        else k_presmooth_residual<BS, areal><<<g, 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, A.dinv, b, inv_theta, x, A.r, nullptr);
+        HEMO_LAUNCH_CHECK(ctx);
+    } else {
+        if (b64) {          // the fused kernel is not used: convert the right-hand side first
+            const int64_t N = (int64_t)A.n * BS;
+            k_to_areal<<<hemo_grid(N, 256), 256, 0, st>>>(N, b64, const_cast<areal*>(b));
+            HEMO_LAUNCH_CHECK(ctx);
+        }
+        if ((rc = smooth_t<BS>(ctx, A, b, x, x_is_zero, degree_pre, ratio))) return rc;
+        // residual and restriction
+        if ((rc = hemo_bsr_spmv_ex(ctx, BS, A.n, A.rowptr, A.col, A.val, x, -1.0, b, A.r))) return rc;
+    }
     const HemoAmgLevel& L = amg->lev[l];
     HemoAmgOp& C = amg->op[l + 1];
     k_transfer<BS, false><<<hemo_grid((int64_t)C.n * 4, 256), 256, 0, st>>>(C.n, L.r_rowptr, L.r_col, L.r_val, A.r, C.b);
@@ -1082,7 +1158,7 @@ static int vcycle_t(hemo_ctx* ctx, HemoAmg* amg, int l, const areal* b, areal* x
     if ((rc = vcycle_t<BS>(ctx, amg, l + 1, C.b, C.x, true))) return rc;
     k_transfer<BS, true><<<hemo_grid((int64_t)A.n * 4, 256), 256, 0, st>>>(A.n, L.p_rowptr, L.p_col, L.p_val, C.x, x);
     HEMO_LAUNCH_CHECK(ctx);
-    if ((rc = smooth_t<BS>(ctx, A, b, x, false, degree, ratio))) return rc;
+    if ((rc = smooth_t<BS>(ctx, A, b, x, false, degree, ratio, x64, wrote64))) return rc;
     return 0;
 }
 
@@ -1093,14 +1169,25 @@ int hemo_amg_vcycle(hemo_ctx* ctx, HemoAmg* amg, const double* b, double* x, int
     int rc;
     HemoAmgOp& top = amg->op[0];
     const int64_t N = (int64_t)top.n * amg->bs;
-    k_to_areal<<<hemo_grid(N, 256), 256, 0, ctx->stream>>>(N, b, top.b);
-    HEMO_LAUNCH_CHECK(ctx);
-    for (int c = 0; c < (ncycles > 0 ? ncycles : 1); ++c) {
-        if (amg->bs == 2) rc = vcycle_t<2>(ctx, amg, 0, top.b, top.x, c == 0);
-        else rc = vcycle_t<1>(ctx, amg, 0, top.b, top.x, c == 0);
+    const int nc = ncycles > 0 ? ncycles : 1;
+    // the top level runs per-level kernels (not inside a fused kernel, not the dense coarsest solve): its first kernel
+    // reads the fp64 right-hand side and its last one writes the fp64 result — no conversion kernels
+    const bool per_level_top = amg->nlev > 1 && amg->fuse_level != 0 && !(amg->fuse_level_grid == 0 && amg->grid_blocks > 0);
+    if (!per_level_top) {
+        k_to_areal<<<hemo_grid(N, 256), 256, 0, ctx->stream>>>(N, b, top.b);
+        HEMO_LAUNCH_CHECK(ctx);
+    }
+    bool wrote64 = false;
+    for (int c = 0; c < nc; ++c) {
+        const double* b64 = (per_level_top && c == 0) ? b : nullptr;
+        double* x64 = (per_level_top && c == nc - 1) ? x : nullptr;
+        if (amg->bs == 2) rc = vcycle_t<2>(ctx, amg, 0, top.b, top.x, c == 0, b64, x64, &wrote64);
+        else rc = vcycle_t<1>(ctx, amg, 0, top.b, top.x, c == 0, b64, x64, &wrote64);
         if (rc) return rc;
     }
-    k_from_areal<<<hemo_grid(N, 256), 256, 0, ctx->stream>>>(N, top.x, x);
-    HEMO_LAUNCH_CHECK(ctx);
+    if (!wrote64) {
+        k_from_areal<<<hemo_grid(N, 256), 256, 0, ctx->stream>>>(N, top.x, x);
+        HEMO_LAUNCH_CHECK(ctx);
+    }
     return 0;
 }
