@@ -81,10 +81,13 @@ def test_p2_assembly_matches_oracle():
 
 @pytest.mark.parametrize("double_setup", [False, True])
 def test_p2_pressure_backflow_plugin_matches_oracle(double_setup):
+    # R_resistance is chosen so that the outlet pressure stays of the order of p_inlet on this coarse mesh: with the
+    # scenario's R = 50 the outlet fixed point jumps to p_c ~ 5e3 after the start-up transient and Newton diverges in
+    # the reference algorithm itself (oracle LU path, reason -6) once the weak terms are doubled by a second setup().
     from cfd_hemodynamic_b200.src.scenarios.stenosis_pressure_structured import StenosisPressureStructuredSimulation
     from oracle.workload import CpuMarcher
     sc = StenosisPressureStructuredSimulation("stabilized_schur_pressure_backflow", 0.005, 0.02, grade="moderate",
-                                              cell_type="triangle", p_inlet=2.0, R_resistance=50.0, res=0.8, L=20.0,
+                                              cell_type="triangle", p_inlet=2.0, R_resistance=0.01, res=0.8, L=20.0,
                                               x_position_stenosis=8.0, p_grade=2, **TIGHT)
     if double_setup:
         sc.setup()

@@ -225,3 +225,31 @@ def test_dfg_drag_lift_on_device():
     cd, cl = sc.drag_lift()
     cd_d, cl_d = sc.drag_lift_device()
     assert abs(cd - cd_d) <= 1e-11 * abs(cd) and abs(cl - cl_d) <= 1e-11 * max(abs(cl), abs(cd))
+
+
+def test_time_dependent_dirichlet_data_reaches_the_device_loop():
+    """bc.update() + refresh of the Dirichlet values happen in every residual evaluation of the reference
+    (stabilized_schur.py:170): the host loop (solveStep) and the device-resident loop (step_device) must see a lid velocity
+    that changes from step to step alike (the device loop froze it)."""
+    from cfd_hemodynamic_b200.src.scenarios.lid_driven2D import LidDriven2DSimulation
+
+    def run(device_loop):
+        sc = LidDriven2DSimulation("stabilized_schur", 0.01, 0.04, rho=1, mu=0.01, nx=12)
+        s = sc.solver
+        lid_bc = sc.bcu[1]
+        for k in range(4):
+            lid_bc.f.x.array[0::2] = 1.0 + 0.5 * k          # the value Function the BoundaryCondition interpolates from
+            if device_loop:
+                s.step_device()
+            else:
+                s.solveStep()
+                s.u_prev.x.array[:] = s.u_sol.x.array[:]
+                s.p_prev.x.array[:] = s.p_sol.x.array[:]
+        if device_loop:
+            s.download_solution()
+        return s.u_sol.x.array.copy(), s.p_sol.x.array.copy()
+
+    uh, ph = run(False)
+    ud, pd = run(True)
+    assert np.abs(uh).max() > 2.0                          # the last lid speed (2.5) is what drives the flow
+    assert np.array_equal(uh, ud) and np.array_equal(ph, pd)
