@@ -11,6 +11,7 @@
 // iteration is the numeric Galerkin product R*A*P on fixed patterns, the
 // smoother set-up, and the cycles.
 #include <cooperative_groups.h>
+#include <type_traits>
 #include <cub/device/device_scan.cuh>
 
 #include "hemo_internal.cuh"
@@ -456,6 +457,260 @@ k_cheb_step(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict
     }
 }
 
+// ---------------------------------------------------------------------------
+// Sliced-ELL versions of the same kernels (HemoAmgOp::sell_*): ONE thread per block row.  The finest operators have
+// 7-9 blocks per row; with 4 lanes per CSR row half the lanes idle in the second trip and every thread has two loads
+// in flight (ncu: 33-47 % of DRAM peak).  Here a warp reads 32 consecutive column indices / blocks per trip (one
+// 128 B / 512 B run) and every thread has its whole row in flight.
+// ---------------------------------------------------------------------------
+// Loads as volatile asm: the compiler keeps their program order, so the column indices, blocks and vector entries of
+// four trips are requested back to back before the first use (left to itself nvcc interleaves load and use to save
+// registers and the dependent chain col -> x is paid once per trip).  Non-coherent path: none of the arrays read this
+// way is written by the kernel that reads it.
+__device__ __forceinline__ int ldg_nc(const int32_t* p) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_nc(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ldg_nc(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ldg_nc(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ldg_nc(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_nc(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double4 ldg_nc(const double4* p) {
+    double4 v;
+    const double2 lo = ldg_nc(reinterpret_cast<const double2*>(p)), hi = ldg_nc(reinterpret_cast<const double2*>(p) + 1);
+    v.x = lo.x; v.y = lo.y; v.z = hi.x; v.w = hi.y;
+    return v;
+}
+
+// gathered vector entry of block column j (BS components, storage type)
+template <int BS>
+struct VecLoad {
+    typedef typename std::conditional<BS == 1, areal, areal2>::type raw;
+    const areal* __restrict__ x;
+    __device__ __forceinline__ raw load(int j) const { return ldg_nc(reinterpret_cast<const raw*>(x) + j); }
+    __device__ __forceinline__ void value(const raw& t, double* out) const {
+        if constexpr (BS == 1) out[0] = (double)t;
+        else { out[0] = (double)t.x; out[1] = (double)t.y; }
+    }
+};
+
+// x_j = D_j^-1 b_j / theta formed on the fly (pre-smoothing from zero fused with the residual)
+template <int BS, typename TB>
+struct JacobiLoad {
+    struct raw { areal d[BS]; TB b[BS]; };
+    const areal* __restrict__ dinv;
+    const TB* __restrict__ b;
+    double inv_theta;
+    __device__ __forceinline__ raw load(int j) const {
+        raw t;
+#pragma unroll
+        for (int k = 0; k < BS; ++k) {
+            t.d[k] = ldg_nc(dinv + (int64_t)j * BS + k);
+            t.b[k] = ldg_nc(b + (int64_t)j * BS + k);
+        }
+        return t;
+    }
+    __device__ __forceinline__ void value(const raw& t, double* out) const {
+#pragma unroll
+        for (int k = 0; k < BS; ++k) out[k] = (double)t.d[k] * (double)t.b[k] * inv_theta;
+    }
+};
+
+template <int BS, typename XF>
+__device__ __forceinline__ void sell_row_product(const int32_t* __restrict__ sptr, const int32_t* __restrict__ scol,
+                                                 const areal* __restrict__ sval, int i, const XF xf, double acc[BS]) {
+    typedef typename std::conditional<BS == 1, areal, areal4>::type blk;
+#pragma unroll
+    for (int k = 0; k < BS; ++k) acc[k] = 0.0;
+    const int s = i >> 5, lane = i & 31;
+    const int base = sptr[s];
+    const int W = (sptr[s + 1] - base) >> 5;         // uniform over the warp
+    const int32_t* __restrict__ c = scol + base + lane;
+    const blk* __restrict__ v = reinterpret_cast<const blk*>(sval) + base + lane;
+    for (int k = 0; k < W; k += 4) {
+        // trips beyond the row end repeat the last one with a zero weight
+        int kk[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { ok[u] = k + u < W; kk[u] = 32 * (ok[u] ? k + u : W - 1); }
+        int j[4];
+        blk a[4];
+        typename XF::raw xr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) j[u] = ldg_nc(c + kk[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = ldg_nc(v + kk[u]);
+        __syncwarp();                    // scheduling fence: the eight loads above are in flight before the first use
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xr[u] = xf.load(j[u]);
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            double xv[BS];
+            xf.value(xr[u], xv);
+            if constexpr (BS == 1) {
+                acc[0] = fma(ok[u] ? (double)a[u] : 0.0, xv[0], acc[0]);
+            } else {
+                const double m = ok[u] ? 1.0 : 0.0;
+                acc[0] += m * ((double)a[u].x * xv[0] + (double)a[u].y * xv[1]);
+                acc[1] += m * ((double)a[u].z * xv[0] + (double)a[u].w * xv[1]);
+            }
+        }
+    }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(256)
+k_sell_cheb_start(int n, const int32_t* __restrict__ sptr, const int32_t* __restrict__ scol, const areal* __restrict__ sval,
+                  const areal* __restrict__ dinv, const areal* __restrict__ b, double inv_theta,
+                  const areal* __restrict__ xin, areal* __restrict__ r, areal* __restrict__ d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc[BS];
+    sell_row_product<BS>(sptr, scol, sval, i, VecLoad<BS>{xin}, acc);
+#pragma unroll
+    for (int k = 0; k < BS; ++k) {
+        const int64_t q = (int64_t)i * BS + k;
+        const double rv = (double)dinv[q] * ((double)b[q] - acc[k]);
+        r[q] = (areal)rv;
+        d[q] = (areal)(rv * inv_theta);
+    }
+}
+
+template <int BS, typename TB>
+__global__ void __launch_bounds__(256)
+k_sell_presmooth_residual(int n, const int32_t* __restrict__ sptr, const int32_t* __restrict__ scol,
+                          const areal* __restrict__ sval, const areal* __restrict__ dinv, const TB* __restrict__ b,
+                          double inv_theta, areal* __restrict__ x, areal* __restrict__ r, areal* __restrict__ bcopy) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc[BS];
+    sell_row_product<BS>(sptr, scol, sval, i, JacobiLoad<BS, TB>{dinv, b, inv_theta}, acc);
+#pragma unroll
+    for (int k = 0; k < BS; ++k) {
+        const int64_t q = (int64_t)i * BS + k;
+        const double bv = (double)b[q];
+        x[q] = (areal)((double)dinv[q] * bv * inv_theta);
+        r[q] = (areal)(bv - acc[k]);
+        if (bcopy) bcopy[q] = (areal)bv;
+    }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(256)
+k_sell_cheb_step(int n, const int32_t* __restrict__ sptr, const int32_t* __restrict__ scol, const areal* __restrict__ sval,
+                 const areal* __restrict__ dinv, double c1, double c2, const areal* __restrict__ dold,
+                 areal* __restrict__ dnew, areal* __restrict__ r, areal* __restrict__ x, int add_old,
+                 double* __restrict__ x64) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc[BS];
+    sell_row_product<BS>(sptr, scol, sval, i, VecLoad<BS>{dold}, acc);
+#pragma unroll
+    for (int k = 0; k < BS; ++k) {
+        const int64_t q = (int64_t)i * BS + k;
+        const double dq = (double)dold[q];
+        const double rv = (double)r[q] - (double)dinv[q] * acc[k];
+        r[q] = (areal)rv;
+        const double dv = c1 * dq + c2 * rv;
+        dnew[q] = (areal)dv;
+        const double xn = (double)x[q] + (add_old ? (dv + dq) : dv);
+        x[q] = (areal)xn;
+        if (x64) x64[q] = xn;
+    }
+}
+
+// y = b - A x
+template <int BS>
+__global__ void __launch_bounds__(256)
+k_sell_residual(int n, const int32_t* __restrict__ sptr, const int32_t* __restrict__ scol, const areal* __restrict__ sval,
+                const areal* __restrict__ x, const areal* __restrict__ b, areal* __restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc[BS];
+    sell_row_product<BS>(sptr, scol, sval, i, VecLoad<BS>{x}, acc);
+#pragma unroll
+    for (int k = 0; k < BS; ++k) {
+        const int64_t q = (int64_t)i * BS + k;
+        y[q] = (areal)((double)b[q] - acc[k]);
+    }
+}
+
+// pattern of the sliced-ELL copy: one thread per (padded) row
+__global__ void k_sell_fill_col(int n, int nrows_padded, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                const int32_t* __restrict__ sptr, int32_t* __restrict__ scol) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows_padded) return;
+    const int s = i >> 5, lane = i & 31;
+    const int base = sptr[s], W = (sptr[s + 1] - base) >> 5;
+    const int r0 = i < n ? rowptr[i] : 0, deg = i < n ? rowptr[i + 1] - r0 : 0;
+    const int self = i < n ? i : n - 1;
+    for (int k = 0; k < W; ++k) scol[base + 32 * k + lane] = k < deg ? col[r0 + k] : self;
+}
+
+// values of the sliced-ELL copy from the CSR values (padding stays zero): 4 lanes per row
+template <int BS>
+__global__ void __launch_bounds__(256)
+k_sell_fill_val(int n, const int32_t* __restrict__ rowptr, const areal* __restrict__ val,
+                const int32_t* __restrict__ sptr, areal* __restrict__ sval) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt >> 2, sub = gt & 3;
+    if (i >= n) return;
+    const int base = sptr[i >> 5] + (i & 31);
+    const int r0 = rowptr[i], deg = rowptr[i + 1] - r0;
+    for (int k = sub; k < deg; k += 4) {
+#pragma unroll
+        for (int c = 0; c < BS * BS; ++c)
+            sval[((int64_t)base + 32 * k) * (BS * BS) + c] = val[((int64_t)r0 + k) * (BS * BS) + c];
+    }
+}
+
+// y[i] += sum_t w_t x[col_t]: prolongation rows are 1-4 entries long — one thread per row
+template <int BS>
+__global__ void __launch_bounds__(256)
+k_prolong_add_row(int nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                  const double* __restrict__ w, const areal* __restrict__ x, areal* __restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    const int r0 = rowptr[i], r1 = rowptr[i + 1];
+    double acc[BS];
+#pragma unroll
+    for (int k = 0; k < BS; ++k) acc[k] = 0.0;
+    for (int t = r0; t < r1; ++t) {
+        const int j = col[t];
+        const double wt = w[t];
+#pragma unroll
+        for (int k = 0; k < BS; ++k) acc[k] = fma(wt, (double)x[(int64_t)j * BS + k], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < BS; ++k) {
+        const int64_t q = (int64_t)i * BS + k;
+        y[q] = (areal)((double)y[q] + acc[k]);
+    }
+}
+
 // y[I] (+)= sum_t w_t x[col_t]  with bs components per node (restriction / prolongation);
 // 4 lanes per row, column loads of three strided entries issued first
 template <int BS, bool ADD>
@@ -517,6 +772,21 @@ struct GridScope {
     __device__ __forceinline__ int tid() const { return blockIdx.x * blockDim.x + threadIdx.x; }
     __device__ __forceinline__ int nthreads() const { return gridDim.x * blockDim.x; }
     __device__ __forceinline__ void sync() const { g.sync(); }
+};
+
+// one thread-block cluster: hardware barrier with release / acquire semantics at cluster scope (global-memory writes of
+// the other CTAs are visible after it)
+struct ClusterScope {
+    unsigned rank, nctas;
+    __device__ __forceinline__ ClusterScope() {
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+        asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(nctas));
+    }
+    __device__ __forceinline__ int tid() const { return (int)(rank * blockDim.x + threadIdx.x); }
+    __device__ __forceinline__ int nthreads() const { return (int)(nctas * blockDim.x); }
+    __device__ __forceinline__ void sync() const {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
 };
 
 // Row loops: 8 lanes cooperate on one block row (coarse Galerkin rows hold 20-60 blocks; a thread-serial
@@ -707,6 +977,14 @@ k_coarse_vcycle(const HemoCoarseLevel* __restrict__ desc, int nl, const areal* _
 }
 
 template <int BS>
+__global__ void __launch_bounds__(1024)
+k_coarse_vcycle_cluster(const HemoCoarseLevel* __restrict__ desc, int nl, const areal* __restrict__ b0, areal* __restrict__ x0,
+                        int degree_pre, int degree, double ratio, const double* __restrict__ dense_inv, int dense_n) {
+    ClusterScope sc;
+    coarse_vcycle_body<BS>(sc, desc, nl, b0, x0, degree_pre, degree, ratio, dense_inv, dense_n);
+}
+
+template <int BS>
 __global__ void __launch_bounds__(512)
 k_coarse_vcycle_grid(const HemoCoarseLevel* __restrict__ desc, int nl, const areal* __restrict__ b0, areal* __restrict__ x0,
                      int degree_pre, int degree, double ratio, const double* __restrict__ dense_inv, int dense_n) {
@@ -805,6 +1083,7 @@ void hemo_amg_free(HemoAmg* amg) {
         free_level(amg->lev[l]);
         HemoAmgOp& o = amg->op[l];
         cudaFree(o.val); cudaFree(o.dinv); cudaFree(o.x); cudaFree(o.b); cudaFree(o.r); cudaFree(o.d);
+        cudaFree(o.sell_ptr); cudaFree(o.sell_col); cudaFree(o.sell_val);
         o = HemoAmgOp();
     }
     if (amg->apply_exec) { cudaGraphExecDestroy(amg->apply_exec); amg->apply_exec = nullptr; }
@@ -812,8 +1091,8 @@ void hemo_amg_free(HemoAmg* amg) {
     cudaFree(amg->fine_rowptr); cudaFree(amg->fine_col); cudaFree(amg->fine_rowof);
     amg->fine_rowptr = amg->fine_col = amg->fine_rowof = nullptr; amg->fine_nnz = 0;
     cudaFree(amg->dense_inv); cudaFree(amg->dense_work); cudaFree(amg->fuse_desc); cudaFree(amg->lmax_dev);
-    amg->fuse_desc = nullptr; amg->lmax_dev = nullptr; amg->fuse_level = amg->fuse_level_grid = amg->fuse_base = -1;
-    amg->grid_blocks = 0;
+    amg->fuse_desc = nullptr; amg->lmax_dev = nullptr; amg->fuse_level = amg->fuse_level_grid = amg->fuse_level_cluster = amg->fuse_base = -1;
+    amg->grid_blocks = amg->cluster_ctas = 0;
     amg->dense_inv = amg->dense_work = nullptr;
     amg->nlev = 0;
     amg->ready = false;
@@ -879,6 +1158,43 @@ extern "C" int hemo_amg_set_fine_pattern(hemo_ctx* ctx, int which, const int32_t
     HEMO_LAUNCH_CHECK(ctx);
     HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     amg.fine_nnz = nnz;
+    return 0;
+}
+
+// sliced-ELL pattern of one operator (kept when the padding stays below half of the entries)
+static int build_sell(hemo_ctx* ctx, HemoAmgOp& o, int bs) {
+    cudaFree(o.sell_ptr); cudaFree(o.sell_col); cudaFree(o.sell_val);
+    o.sell_ptr = o.sell_col = nullptr; o.sell_val = nullptr; o.sell_entries = 0;
+    const char* env = getenv("HEMO_SELL");
+    if (env && atoi(env) == 0) return 0;
+    const int n = o.n;
+    // long rows / small levels: thread-serial rows lose against 4 lanes per row (measured: 10-11 us against 5.5-6 us
+    // per kernel at 9.6 k nodes with ~25 blocks per row)
+    if (n < 32768 || o.nnzb > 16 * (int64_t)n) return 0;
+    std::vector<int32_t> rp((size_t)n + 1);
+    HEMO_CHECK_CUDA(ctx, cudaMemcpy(rp.data(), o.rowptr, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost));
+    const int nsl = (n + 31) / 32;
+    std::vector<int32_t> sp((size_t)nsl + 1);
+    int64_t total = 0;
+    sp[0] = 0;
+    for (int s = 0; s < nsl; ++s) {
+        int w = 0;
+        const int hi = std::min(n, 32 * s + 32);
+        for (int i = 32 * s; i < hi; ++i) w = std::max(w, rp[i + 1] - rp[i]);
+        total += 32 * (int64_t)w;
+        if (total > 0x7fffffffLL) return 0;
+        sp[s + 1] = (int32_t)total;
+    }
+    if (total > o.nnzb + o.nnzb / 2) return 0;
+    int rc;
+    if ((rc = hemo_upload(ctx, &o.sell_ptr, sp.data(), (size_t)nsl + 1, false))) return rc;
+    if ((rc = hemo_alloc(ctx, &o.sell_col, (size_t)total))) return rc;
+    if ((rc = hemo_alloc(ctx, &o.sell_val, (size_t)total * bs * bs))) return rc;
+    HEMO_CHECK_CUDA(ctx, cudaMemsetAsync(o.sell_val, 0, sizeof(areal) * (size_t)total * bs * bs, ctx->stream));
+    k_sell_fill_col<<<hemo_grid((int64_t)nsl * 32, 256), 256, 0, ctx->stream>>>(n, nsl * 32, o.rowptr, o.col, o.sell_ptr, o.sell_col);
+    HEMO_LAUNCH_CHECK(ctx);
+    HEMO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    o.sell_entries = total;
     return 0;
 }
 
@@ -951,7 +1267,41 @@ extern "C" int hemo_amg_finalize(hemo_ctx* ctx, int which, int n_levels) {
         }
         cudaGetLastError();
     }
-    amg.fuse_base = amg.fuse_level_grid >= 0 ? amg.fuse_level_grid : amg.fuse_level;
+    amg.fuse_level_cluster = -1;
+    amg.cluster_ctas = 0;
+    {
+        const char* env = getenv("HEMO_CLUSTER_FUSE_MAX");
+        const int cap = env ? atoi(env) : HEMO_CLUSTER_FUSE_MAX_NODES;
+        const char* envc = getenv("HEMO_CLUSTER_CTAS");
+        int want = envc ? atoi(envc) : 16;
+        if (want > 16) want = 16;
+        if (cap > HEMO_FUSE_MAX_NODES && want > 1 && amg.fuse_level_grid < 0) {
+            const void* fn = (bs == 2) ? (const void*)k_coarse_vcycle_cluster<2> : (const void*)k_coarse_vcycle_cluster<1>;
+            if (want > 8) cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            for (int c = want; c >= 2 && amg.cluster_ctas == 0; c >>= 1) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(c); cfg.blockDim = dim3(1024);
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                int nclusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) == cudaSuccess && nclusters >= 1) amg.cluster_ctas = c;
+            }
+            cudaGetLastError();
+            if (amg.cluster_ctas > 0)
+                for (int l = 1; l < n_levels; ++l)
+                    if (amg.op[l].n <= cap) {
+                        if (amg.op[l].n > HEMO_FUSE_MAX_NODES) amg.fuse_level_cluster = l;
+                        break;
+                    }
+        }
+    }
+    amg.fuse_base = amg.fuse_level_grid >= 0 ? amg.fuse_level_grid
+                  : (amg.fuse_level_cluster >= 0 ? amg.fuse_level_cluster : amg.fuse_level);
+    // the levels that keep per-level kernels get the sliced-ELL copy
+    for (int l = 0; l < (amg.fuse_base >= 0 ? amg.fuse_base : n_levels - 1); ++l)
+        if ((rc = build_sell(ctx, amg.op[l], bs))) return rc;
     if (amg.fuse_base >= 0) {
         std::vector<HemoCoarseLevel> d;
         for (int l = amg.fuse_base; l < n_levels; ++l) {
@@ -980,6 +1330,13 @@ extern "C" int hemo_amg_finalize(hemo_ctx* ctx, int which, int n_levels) {
 template <int BS>
 static int amg_numeric_t(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift) {
     cudaStream_t st = ctx->stream;
+#define HEMO_FILL_SELL(A)                                                                                                  \
+    if ((A).sell_ptr) {                                                                                                    \
+        k_sell_fill_val<BS><<<hemo_grid((int64_t)(A).n * 4, 256), 256, 0, st>>>((A).n, (A).rowptr, (A).val, (A).sell_ptr,   \
+                                                                                 (A).sell_val);                            \
+        HEMO_LAUNCH_CHECK(ctx);                                                                                            \
+    }
+    HEMO_FILL_SELL(amg->op[0]);
     for (int l = 0; l + 1 < amg->nlev; ++l) {
         const HemoAmgOp& A = amg->op[l];
         HemoAmgOp& C = amg->op[l + 1];
@@ -1001,7 +1358,9 @@ static int amg_numeric_t(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift) {
             HEMO_LAUNCH_CHECK(ctx);
         }
         if (l == 0) HEMO_PROF_END(ctx, HEMO_PROF_RAP);
+        HEMO_FILL_SELL(C);
     }
+#undef HEMO_FILL_SELL
     // smoother data; bounds are read back in one copy
     for (int l = 0; l + 1 < amg->nlev; ++l) {
         HemoAmgOp& A = amg->op[l];
@@ -1063,6 +1422,9 @@ static int smooth_t(hemo_ctx* ctx, const HemoAmgOp& A, const areal* b, areal* x,
     areal* d1 = A.d + N;
     if (x_is_zero) {
         k_cheb_start_zero<BS><<<hemo_grid(N, 256), 256, 0, st>>>(N, A.dinv, b, 1.0 / theta, A.r, d0, x);
+    } else if (A.sell_ptr) {
+        k_sell_cheb_start<BS><<<hemo_grid(A.n, 256), 256, 0, st>>>(A.n, A.sell_ptr, A.sell_col, A.sell_val, A.dinv, b, 1.0 / theta,
+                                                                    x, A.r, d0);
     } else {
         k_cheb_start<BS><<<hemo_grid((int64_t)A.n * 4, 256), 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, A.dinv, b, 1.0 / theta, x,
                                                               A.r, d0);
@@ -1075,8 +1437,12 @@ static int smooth_t(hemo_ctx* ctx, const HemoAmgOp& A, const areal* b, areal* x,
         const bool fine = (A.n == ctx->n);
         if (fine) HEMO_PROF_BEGIN(ctx, BS == 2 ? HEMO_PROF_CHEB_U0 : HEMO_PROF_CHEB_P0);
         const bool last = (k == degree - 1);
-        k_cheb_step<BS><<<hemo_grid((int64_t)A.n * 4, 256), 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, A.dinv, c1, c2, d0, d1, A.r, x,
-                                                             pending ? 1 : 0, last ? x64 : nullptr);
+        if (A.sell_ptr)
+            k_sell_cheb_step<BS><<<hemo_grid(A.n, 256), 256, 0, st>>>(A.n, A.sell_ptr, A.sell_col, A.sell_val, A.dinv, c1, c2, d0, d1,
+                                                                       A.r, x, pending ? 1 : 0, last ? x64 : nullptr);
+        else
+            k_cheb_step<BS><<<hemo_grid((int64_t)A.n * 4, 256), 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, A.dinv, c1, c2, d0, d1, A.r, x,
+                                                                 pending ? 1 : 0, last ? x64 : nullptr);
         if (last && x64 && wrote64) *wrote64 = true;
         HEMO_LAUNCH_CHECK(ctx);
         if (fine) HEMO_PROF_END(ctx, BS == 2 ? HEMO_PROF_CHEB_U0 : HEMO_PROF_CHEB_P0);
@@ -1117,6 +1483,21 @@ static int vcycle_t(hemo_ctx* ctx, HemoAmg* amg, int l, const areal* b, areal* x
         ctx->amg[0].grid_blocks = ctx->amg[1].grid_blocks = 0;
         if (ctx->capturing) HEMO_FAIL(ctx, HEMO_ERETRY, "cooperative launch not capturable: capture is repeated without it");
     }
+    if (l == amg->fuse_level_cluster && amg->cluster_ctas > 0) {
+        // every remaining level inside one thread-block cluster
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(amg->cluster_ctas); cfg.blockDim = dim3(1024); cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = amg->cluster_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const HemoCoarseLevel* desc = amg->fuse_desc + (l - amg->fuse_base);
+        const double* dinv = amg->dense_inv;
+        HEMO_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_coarse_vcycle_cluster<BS>, desc, amg->nlev - l, b, x, degree_pre, degree,
+                                                ratio, dinv, amg->dense_n));
+        ctx->launches++;
+        return 0;
+    }
     if (l == amg->fuse_level) {
         // every remaining level fits one CTA
         k_coarse_vcycle<BS><<<1, 1024, 0, st>>>(amg->fuse_desc + (l - amg->fuse_base), amg->nlev - l, b, x, degree_pre, degree, ratio,
@@ -1137,7 +1518,13 @@ static int vcycle_t(hemo_ctx* ctx, HemoAmg* amg, int l, const areal* b, areal* x
         const double lmax = A.lmax, lmin = lmax / ratio;
         const double inv_theta = 1.0 / (0.5 * (lmax + lmin));
         const int g = hemo_grid((int64_t)A.n * 4, 256);
-        if (b64) k_presmooth_residual<BS, double><<<g, 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, A.dinv, b64, inv_theta, x, A.r,
+        if (A.sell_ptr) {
+            const int gs = hemo_grid(A.n, 256);
+            if (b64) k_sell_presmooth_residual<BS, double><<<gs, 256, 0, st>>>(A.n, A.sell_ptr, A.sell_col, A.sell_val, A.dinv, b64,
+                                                                                inv_theta, x, A.r, const_cast<areal*>(b));
+            else k_sell_presmooth_residual<BS, areal><<<gs, 256, 0, st>>>(A.n, A.sell_ptr, A.sell_col, A.sell_val, A.dinv, b,
+                                                                          inv_theta, x, A.r, nullptr);
+        } else if (b64) k_presmooth_residual<BS, double><<<g, 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, A.dinv, b64, inv_theta, x, A.r,
                                                                       const_cast<areal*>(b));
         else k_presmooth_residual<BS, areal><<<g, 256, 0, st>>>(A.n, A.rowptr, A.col, A.val, A.dinv, b, inv_theta, x, A.r, nullptr);
         HEMO_LAUNCH_CHECK(ctx);
@@ -1149,14 +1536,20 @@ static int vcycle_t(hemo_ctx* ctx, HemoAmg* amg, int l, const areal* b, areal* x
         }
         if ((rc = smooth_t<BS>(ctx, A, b, x, x_is_zero, degree_pre, ratio))) return rc;
         // residual and restriction
-        if ((rc = hemo_bsr_spmv_ex(ctx, BS, A.n, A.rowptr, A.col, A.val, x, -1.0, b, A.r))) return rc;
+        if (A.sell_ptr) {
+            k_sell_residual<BS><<<hemo_grid(A.n, 256), 256, 0, st>>>(A.n, A.sell_ptr, A.sell_col, A.sell_val, x, b, A.r);
+            HEMO_LAUNCH_CHECK(ctx);
+        } else if ((rc = hemo_bsr_spmv_ex(ctx, BS, A.n, A.rowptr, A.col, A.val, x, -1.0, b, A.r))) return rc;
     }
     const HemoAmgLevel& L = amg->lev[l];
     HemoAmgOp& C = amg->op[l + 1];
     k_transfer<BS, false><<<hemo_grid((int64_t)C.n * 4, 256), 256, 0, st>>>(C.n, L.r_rowptr, L.r_col, L.r_val, A.r, C.b);
     HEMO_LAUNCH_CHECK(ctx);
     if ((rc = vcycle_t<BS>(ctx, amg, l + 1, C.b, C.x, true))) return rc;
-    k_transfer<BS, true><<<hemo_grid((int64_t)A.n * 4, 256), 256, 0, st>>>(A.n, L.p_rowptr, L.p_col, L.p_val, C.x, x);
+    if (L.nnz_p <= 6 * (int64_t)A.n && A.n >= 32768)
+        k_prolong_add_row<BS><<<hemo_grid(A.n, 256), 256, 0, st>>>(A.n, L.p_rowptr, L.p_col, L.p_val, C.x, x);
+    else
+        k_transfer<BS, true><<<hemo_grid((int64_t)A.n * 4, 256), 256, 0, st>>>(A.n, L.p_rowptr, L.p_col, L.p_val, C.x, x);
     HEMO_LAUNCH_CHECK(ctx);
     if ((rc = smooth_t<BS>(ctx, A, b, x, false, degree, ratio, x64, wrote64))) return rc;
     return 0;

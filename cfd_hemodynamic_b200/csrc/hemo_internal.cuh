@@ -23,9 +23,11 @@
 #ifdef HEMO_AMG_FP64
 typedef double areal;
 typedef double2 areal2;
+typedef double4 areal4;
 #else
 typedef float areal;
 typedef float2 areal2;
+typedef float4 areal4;
 #endif
 
 #define HEMO_ERETRY (-3)      // internal: a stream capture has to be repeated (never returned through the C ABI)
@@ -55,6 +57,13 @@ struct HemoAmgOp {
     areal* dinv = nullptr;     // n*bs   inverse diagonal
     double lmax = 2.0;         // bound of spectrum of D^-1 A
     areal *x = nullptr, *b = nullptr, *r = nullptr, *d = nullptr;  // n*bs work vectors
+    // Sliced-ELL copy of the operator for the smoother / residual kernels of the large levels: slices of 32 block rows,
+    // entries of a slice stored column-major (entry k of lane's row at sell_ptr[slice] + 32 k + lane), padded to the
+    // longest row of the slice with zero blocks.  One thread per row, every load of a warp is one contiguous run.
+    int32_t* sell_ptr = nullptr;   // nslices + 1
+    int32_t* sell_col = nullptr;
+    areal* sell_val = nullptr;     // sell_entries*bs*bs
+    int64_t sell_entries = 0;
 };
 
 struct HemoAmgLevel {
@@ -86,6 +95,13 @@ struct HemoCoarseLevel {
 // default: measured on a B200 (lid cavity 707^2) the grid.sync between the ~40 phases costs more than the graph-
 // scheduled per-level launches it replaces (36.9 vs 29.7 ms per time step); HEMO_GRID_FUSE_MAX=<nodes> turns it on.
 #define HEMO_GRID_FUSE_MAX_NODES 0
+// Levels at or below this size (and above HEMO_FUSE_MAX_NODES) run inside ONE thread-block cluster, phases separated
+// by the hardware cluster barrier (~0.2 us against 3-5 us for a grid-wide barrier or a kernel boundary).  0 = off, the
+// default: measured on a B200 (lid cavity 707^2, levels of 9.6 k / 1.2 k nodes) 16 SMs do not hide the three dependent
+// L2 accesses of a phase as well as 150-CTA launches spread over the GPU do (29.5 ms per time step with a cluster of
+// 16, 32.6 with 8, against 27.6 with per-level launches).  HEMO_CLUSTER_FUSE_MAX=<nodes> turns it on,
+// HEMO_CLUSTER_CTAS=<2..16> sets the cluster size.
+#define HEMO_CLUSTER_FUSE_MAX_NODES 0
 
 struct HemoAmg {
     // cached CUDA graph of hemo_amg_apply(b, x, ncycles) (replicated global pressure solve)
@@ -102,6 +118,8 @@ struct HemoAmg {
     int fuse_level_grid = -1;      // first level handled by the cooperative persistent-grid kernel (-1: none)
     int fuse_base = -1;            // level of fuse_desc[0]
     int grid_blocks = 0;           // CTAs of the cooperative kernel (one per SM); 0: cooperative launch unavailable
+    int fuse_level_cluster = -1;   // first level handled by the one-cluster fused kernel (-1: none)
+    int cluster_ctas = 0;          // CTAs of that cluster; 0: cluster launch unavailable
     HemoCoarseLevel* fuse_desc = nullptr;   // device array, one per level from fuse_level
     double* lmax_dev = nullptr;    // HEMO_MAX_LEVELS Gershgorin bounds kept on the device
     int bs = 1;

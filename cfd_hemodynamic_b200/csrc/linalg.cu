@@ -496,32 +496,47 @@ int hemo_maxpy(hemo_ctx* ctx, int64_t n, int k, const double* V, int64_t ldv, co
     return 0;
 }
 
-// mean removal on the device (constant-pressure null space): x -= sum(x)/n
-__global__ void k_sub_mean(int64_t n, const double* __restrict__ sum, double* __restrict__ x) {
-    const double m = sum[0] / (double)n;
+// mean removal on the device (constant-pressure null space): x -= sum(x)/n.  Two launches: per-block partial sums
+// (optionally copying src -> x on the way), then every block re-reduces the partials in the same fixed order and
+// subtracts (no single-block reduction kernel in between).
+__global__ void __launch_bounds__(RED_THREADS)
+k_sub_mean_partials(int64_t n, int nparts, const double* __restrict__ partial, double* __restrict__ x) {
+    __shared__ double sh[32];
+    __shared__ double mean;
+    double acc = 0.0;
+    for (int t = threadIdx.x; t < nparts; t += blockDim.x) acc += partial[t];
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) mean = acc / (double)n;
+    __syncthreads();
+    const double m = mean;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         x[i] -= m;
 }
 
+// partial[b] = sum of this block's entries of src; dst = src when they differ
 __global__ void __launch_bounds__(RED_THREADS)
-k_sum_partial(int64_t n, const double* __restrict__ x, double* __restrict__ partial) {
+k_sum_partial(int64_t n, const double* src, double* dst, double* __restrict__ partial) {
     __shared__ double sh[32];
     double acc = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        acc += x[i];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = src[i];
+        if (dst != src) dst[i] = v;
+        acc += v;
+    }
     acc = block_sum(acc, sh);
     if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
-int hemo_remove_mean(hemo_ctx* ctx, int64_t n, double* x) {
+// x = src - mean(src)  (src == x: in place)
+int hemo_copy_remove_mean(hemo_ctx* ctx, int64_t n, const double* src, double* x) {
     int rc = hemo_ensure_reduce(ctx, (size_t)RED_BLOCKS * 2, 512);
     if (rc) return rc;
     const int g = grid_for(n);
-    k_sum_partial<<<g, RED_THREADS, 0, ctx->stream>>>(n, x, ctx->red_partial);
+    k_sum_partial<<<g, RED_THREADS, 0, ctx->stream>>>(n, src, x, ctx->red_partial);
     HEMO_LAUNCH_CHECK(ctx);
-    k_reduce_final<<<1, RED_THREADS, 0, ctx->stream>>>(g, ctx->red_partial, ctx->red_out + 501, -1);
-    HEMO_LAUNCH_CHECK(ctx);
-    k_sub_mean<<<g, RED_THREADS, 0, ctx->stream>>>(n, ctx->red_out + 501, x);
+    k_sub_mean_partials<<<g, RED_THREADS, 0, ctx->stream>>>(n, g, ctx->red_partial, x);
     HEMO_LAUNCH_CHECK(ctx);
     return 0;
 }
+
+int hemo_remove_mean(hemo_ctx* ctx, int64_t n, double* x) { return hemo_copy_remove_mean(ctx, n, x, x); }

@@ -19,6 +19,7 @@ int hemo_mdot(hemo_ctx* ctx, int64_t n, int k, const double* V, int64_t ldv, con
 int hemo_maxpy(hemo_ctx* ctx, int64_t n, int k, const double* V, int64_t ldv, const double* hcoef_dev, double sign,
                double* w, double* norm_host);
 int hemo_remove_mean(hemo_ctx* ctx, int64_t n, double* x);
+int hemo_copy_remove_mean(hemo_ctx* ctx, int64_t n, const double* src, double* x);
 int hemo_amg_numeric_shift(hemo_ctx* ctx, HemoAmg* amg, double coarse_shift);
 
 // A00 (2x2 node blocks) out of the monolithic CSR values
@@ -115,6 +116,41 @@ k_a01_residual(int n, const int32_t* __restrict__ nrowptr, const int32_t* __rest
         tu[2 * (int64_t)i] = ru[2 * (int64_t)i] - a0;
         tu[2 * (int64_t)i + 1] = ru[2 * (int64_t)i + 1] - a1;
     }
+}
+
+// the same with one thread per node row: the 7-9 entries of a fine-mesh row are requested four at a time before the
+// first use (see sell_row_product in amg.cu for the scheduling fences)
+__global__ void __launch_bounds__(256)
+k_a01_residual_row(int n, const int32_t* __restrict__ nrowptr, const int32_t* __restrict__ ncol,
+                   const areal2* __restrict__ a01, const double* __restrict__ zp, const double* __restrict__ ru,
+                   double* __restrict__ tu) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r0 = nrowptr[i], r1 = nrowptr[i + 1];
+    double a0 = 0.0, a1 = 0.0;
+    for (int s = r0; s < r1; s += 4) {
+        int t[4], j[4];
+        areal2 g[4];
+        double z[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) t[u] = s + u < r1 ? s + u : r1 - 1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) j[u] = ncol[t[u]];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) g[u] = a01[t[u]];
+        __syncwarp(__activemask());
+#pragma unroll
+        for (int u = 0; u < 4; ++u) z[u] = zp[j[u]];
+        __syncwarp(__activemask());
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double m = s + u < r1 ? z[u] : 0.0;
+            a0 = fma((double)g[u].x, m, a0);
+            a1 = fma((double)g[u].y, m, a1);
+        }
+    }
+    tu[2 * (int64_t)i] = ru[2 * (int64_t)i] - a0;          // (r_u may be a Krylov column: 8-byte alignment only)
+    tu[2 * (int64_t)i + 1] = ru[2 * (int64_t)i + 1] - a1;
 }
 
 // c = N_p q on the node graph (4 lanes per row)
@@ -451,12 +487,16 @@ int hemo_pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_de
     double* tu = ctx->pc_tmp_u;
     int rc;
     if (!ctx->external_schur) {
-    HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(tp, rp, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-    if (ctx->pc_mask) {
-        k_mask_nodes<<<hemo_grid(n, 256), 256, 0, st>>>(n, 1, ctx->pc_mask, tp);
-        HEMO_LAUNCH_CHECK(ctx);
+    if (ctx->opts.project_pressure && !ctx->pc_mask) {
+        if ((rc = hemo_copy_remove_mean(ctx, n, rp, tp))) return rc;      // the copy rides on the summation pass
+    } else {
+        HEMO_CHECK_CUDA(ctx, cudaMemcpyAsync(tp, rp, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+        if (ctx->pc_mask) {
+            k_mask_nodes<<<hemo_grid(n, 256), 256, 0, st>>>(n, 1, ctx->pc_mask, tp);
+            HEMO_LAUNCH_CHECK(ctx);
+        }
+        if (ctx->opts.project_pressure && (rc = hemo_remove_mean(ctx, n, tp))) return rc;
     }
-    if (ctx->opts.project_pressure && (rc = hemo_remove_mean(ctx, n, tp))) return rc;
     if (ctx->coarse_ctx && (rc = coarse_pressure_fork(ctx, tp))) return rc;
     if ((rc = hemo_amg_vcycle(ctx, &ctx->amg[1], tp, qp, ctx->opts.amg_cycles_p))) return rc;
     if (ctx->coarse_ctx) {
@@ -480,7 +520,10 @@ int hemo_pc_apply_body(hemo_ctx* ctx, const double* vals_dev, const double* r_de
     if (ctx->dim == 3)    // t_u = r_u - A01 z_p, then damped block-Jacobi sweeps on A00 (amg_cycles_u * 4 sweeps)
         return hemo_tet_velocity_solve(ctx, vals_dev, ru, zp, tu, ctx->pc_tmp_u2, zu, 4 * ctx->opts.amg_cycles_u, 2.0 / 3.0);
     // t_u = r_u - A01 z_p
-    k_a01_residual<<<hemo_grid((int64_t)n * 4, 256), 256, 0, st>>>(n, ctx->nrowptr, ctx->ncol, ctx->a01, zp, ru, tu);
+    if (n >= 32768 && ctx->nnz_node <= 12 * (int64_t)n)
+        k_a01_residual_row<<<hemo_grid(n, 256), 256, 0, st>>>(n, ctx->nrowptr, ctx->ncol, ctx->a01, zp, ru, tu);
+    else
+        k_a01_residual<<<hemo_grid((int64_t)n * 4, 256), 256, 0, st>>>(n, ctx->nrowptr, ctx->ncol, ctx->a01, zp, ru, tu);
     HEMO_LAUNCH_CHECK(ctx);
     if (ctx->pc_mask) {
         k_mask_nodes<<<hemo_grid(n, 256), 256, 0, st>>>(n, 2, ctx->pc_mask, tu);
