@@ -348,7 +348,10 @@ def measure_workload(name, W, K, local_rank, want_e2e=True, want_prof=True, solv
     peak, peak_kind = measured_peaks()
     ae_bytes = 72 * nv * nv * E
     its_per_solve = max(ksp / max(newton, 1), 1.0)
-    kavg = 0.5 * its_per_solve + 1.0                       # average number of basis vectors per Gram-Schmidt pass
+    # average number of basis vectors per Gram-Schmidt pass: iteration i of a solve works on (i mod restart) + 1
+    restart = max(int(getattr(s, "ksp_restart", 60)), 1)
+    L = max(int(round(its_per_solve)), 1)
+    kavg = sum((i % restart) + 1 for i in range(L)) / L
     alg_bytes = {
         0: 76 * nnz_node + 52 * n + 24 * n,               # J values + node cols + rowptr + x + y (+ the Z_j copy)
         1: 4 * nv * E + 8 * E + 56 * n + ae_bytes,        # cells, h, nodal gathers, element matrices out

@@ -1170,7 +1170,7 @@ static int build_sell(hemo_ctx* ctx, HemoAmgOp& o, int bs) {
     const int n = o.n;
     // long rows / small levels: thread-serial rows lose against 4 lanes per row (measured: 10-11 us against 5.5-6 us
     // per kernel at 9.6 k nodes with ~25 blocks per row)
-    if (n < 32768 || o.nnzb > 16 * (int64_t)n) return 0;
+    if (n < 32768 || o.nnzb > 24 * (int64_t)n) return 0;
     std::vector<int32_t> rp((size_t)n + 1);
     HEMO_CHECK_CUDA(ctx, cudaMemcpy(rp.data(), o.rowptr, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost));
     const int nsl = (n + 31) / 32;
