@@ -57,6 +57,7 @@ SYMBOLS = {
     "hemo_prof_enable": (_I, [_VP, _I]),
     "hemo_prof_get": (_I, [_VP, _I, C.POINTER(_D), C.POINTER(_L)]),
     "hemo_set_cell_type": (_I, [_VP, _I]),
+    "hemo_set_formulation": (_I, [_VP, _I]),
     "hemo_set_mesh": (_I, [_VP, _VP, _I, _VP, _I, _VP]),
     "hemo_set_node_graph": (_I, [_VP, _VP, _VP, _L]),
     "hemo_matrix_nnz": (_I, [_VP, C.POINTER(_L)]),
@@ -228,6 +229,11 @@ class Hemo:
         self.E = cells.shape[0]
         self._check(self.lib.hemo_set_mesh(self._ctx, _ptr(x2), self.n, _ptr(cells), self.E, _ptr(h)),
                     "hemo_set_mesh")
+
+    def set_formulation(self, name: str):
+        """"standard" (stabilized_schur.py:69-121) or "curlcurl" (stabilized_schur_pressurebc.py:85-160)."""
+        code = {"standard": 0, "curlcurl": 1}[name]
+        self._check(self.lib.hemo_set_formulation(self._ctx, code), "hemo_set_formulation")
 
     def set_node_graph(self, nrowptr, ncol):
         self._keep.update(nrowptr=nrowptr, ncol=ncol)

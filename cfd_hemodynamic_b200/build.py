@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libhemo_sm100.so")
-SOURCES = ["assembly.cu", "assembly_q1.cu", "assembly_p2.cu", "assembly_tet.cu", "postproc.cu", "linalg.cu", "amg.cu", "solver.cu",
+SOURCES = ["assembly.cu", "assembly_q1.cu", "assembly_p2.cu", "assembly_tet.cu", "assembly_curlcurl.cu", "postproc.cu", "linalg.cu", "amg.cu", "solver.cu",
            "krylov.cu", "comm.cu", "host_setup.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--extended-lambda",
          "-Xcompiler", "-fPIC"]

@@ -891,6 +891,15 @@ static int upload_constants(hemo_ctx* ctx) {
     return 0;
 }
 
+int hemo_cc_cells(hemo_ctx* ctx, const double* x_dev, const double* un_dev, int jac_mode);   // assembly_curlcurl.cu
+int hemo_cc_lift2d(hemo_ctx* ctx);
+
+extern "C" int hemo_set_formulation(hemo_ctx* ctx, int formulation) {
+    if (!ctx || (formulation != HEMO_FORM_STANDARD && formulation != HEMO_FORM_CURLCURL)) return HEMO_EINVAL;
+    ctx->formulation = formulation;
+    return 0;
+}
+
 extern "C" int hemo_set_cell_type(hemo_ctx* ctx, int cell_type) {
     if (!ctx || (cell_type != HEMO_CELL_TRIANGLE && cell_type != HEMO_CELL_QUADRILATERAL &&
                  cell_type != HEMO_CELL_TETRAHEDRON && cell_type != HEMO_CELL_TRIANGLE_P2))
@@ -1063,6 +1072,7 @@ static int set_quadrature_quad(hemo_ctx* ctx, int block, const double* pts, cons
 
 extern "C" int hemo_set_quadrature(hemo_ctx* ctx, int block, const double* pts, const double* wts, int nq) {
     if (!ctx || block < 0 || block >= HEMO_NRULES || !pts || !wts || nq <= 0) return HEMO_EINVAL;
+    ctx->rule_version++;
     if (ctx->dim == 3) return hemo_tet_set_quadrature(ctx, block, pts, wts, nq);
     if (ctx->nv == 4) return set_quadrature_quad(ctx, block, pts, wts, nq);
     if (ctx->nv == 6) return hemo_p2_set_quadrature(ctx, block, pts, wts, nq);
@@ -1107,6 +1117,7 @@ extern "C" int hemo_set_quadrature(hemo_ctx* ctx, int block, const double* pts, 
 
 extern "C" int hemo_set_facet_quadrature(hemo_ctx* ctx, const double* pts, const double* wts, int nq) {
     if (!ctx || !pts || !wts || nq <= 0) return HEMO_EINVAL;
+    ctx->rule_version++;
     if (ctx->dim == 3) return hemo_tet_set_facet_quadrature(ctx, pts, wts, nq);   // (s, t) pairs on the reference triangle
     if (nq > HEMO_MAXFQ) return HEMO_EINVAL;
     ctx->frule.nq = nq;
@@ -1225,6 +1236,16 @@ extern "C" int hemo_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const 
     if ((rc = ensure_elem(ctx, (size_t)9 * nv * nv * E, 0))) return rc;
     cudaStream_t st = ctx->stream;
     const double* uh = ctx->uh ? ctx->uh : un_dev;
+    if (ctx->formulation == HEMO_FORM_CURLCURL) {
+        // stabilized_schur_pressurebc.py: cells + facets of the rotational form, then the standard gather
+        if ((rc = ensure_elem(ctx, (size_t)9 * nv * nv * E, (size_t)3 * nv * E))) return rc;
+        if ((rc = hemo_cc_cells(ctx, x_dev, un_dev, 0))) return rc;
+        k_gather_matrix<<<hemo_grid(ctx->nnz_node, 256), 256, 0, st>>>(
+            n, nv * nv, ctx->nnz_node, E, ctx->nrowptr, ctx->ncol, ctx->rowof, ctx->mseg_ptr, ctx->mseg_src, ctx->Ae,
+            ctx->have_bc ? ctx->dofflag : nullptr, ctx->dofmult, vals_dev);
+        HEMO_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     HEMO_PROF_BEGIN(ctx, HEMO_PROF_CELL_JAC);
     if (nv == 4) {
         if ((rc = hemo_q1_cell_jacobian(ctx, x_dev, un_dev))) return rc;
@@ -1274,6 +1295,16 @@ extern "C" int hemo_assemble_residual(hemo_ctx* ctx, const double* x_dev, const 
     if (ctx->have_bc) {
         k_lift_vector<<<hemo_grid(3 * (int64_t)n, 256), 256, 0, st>>>(3 * (int64_t)n, ctx->dofflag, x_dev, g_dev, ctx->dvec);
         HEMO_LAUNCH_CHECK(ctx);
+    }
+    if (ctx->formulation == HEMO_FORM_CURLCURL) {
+        // element Jacobians only on Dirichlet-adjacent cells (lifting), like the tetrahedron path
+        if ((rc = ensure_elem(ctx, (size_t)9 * nv * nv * E, (size_t)3 * nv * E))) return rc;
+        if ((rc = hemo_cc_cells(ctx, x_dev, un_dev, ctx->have_bc ? 1 : 2))) return rc;
+        if (ctx->have_bc && (rc = hemo_cc_lift2d(ctx))) return rc;
+        k_gather_vector<<<hemo_grid(n, 256), 256, 0, st>>>(n, nv, E, ctx->vseg_ptr, ctx->vseg_src, ctx->Fe,
+                                                           ctx->have_bc ? ctx->dofflag : nullptr, x_dev, g_dev, b_dev);
+        HEMO_LAUNCH_CHECK(ctx);
+        return 0;
     }
     HEMO_PROF_BEGIN(ctx, HEMO_PROF_CELL_RES);
     if (nv == 4) {

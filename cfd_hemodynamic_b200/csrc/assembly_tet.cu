@@ -345,11 +345,25 @@ static bool tet_facet_set_active(const HemoFacetSet& fs) {
     return fs.m > 0 && (c.a_p != 0.0 || c.pconst != 0.0 || c.a_g != 0.0 || c.a_s != 0.0 || c.a_n != 0.0 || c.a_b != 0.0);
 }
 
+int hemo_cc_cells(hemo_ctx* ctx, const double* x_dev, const double* un_dev, int jac_mode);   // assembly_curlcurl.cu
+
+// host-side rule tables for the curl-curl kernels (same rules, FFCx-style evaluation)
+int hemo_tet_get_rules(hemo_ctx* ctx, const SimplexRule<3>** rules, const int** alias, const SimplexFacetRule<3>** frule) {
+    hemo_tet_state* st = tet_state(ctx);
+    for (int r = 0; r < HEMO_NRULES; ++r)
+        if (!st->have[r]) HEMO_FAIL(ctx, HEMO_ESTATE, "tetrahedron quadrature rule missing for a block form");
+    *rules = st->host->r;
+    *alias = st->host->alias;
+    *frule = st->have_frule ? &st->frule : nullptr;
+    return 0;
+}
+
 // cell tensors (residual, and the Jacobian where jac_mode asks for it), then the facet terms of every active set
 static int tet_cells(hemo_ctx* ctx, const double* x_dev, const double* un_dev, int jac_mode) {
     if (!ctx->cells || !ctx->nrowptr) HEMO_FAIL(ctx, HEMO_ESTATE, "mesh / node graph not set");
     int rc = hemo_ensure_elem(ctx, (size_t)256 * ctx->E, (size_t)16 * ctx->E);
     if (rc) return rc;
+    if (ctx->formulation == HEMO_FORM_CURLCURL) return hemo_cc_cells(ctx, x_dev, un_dev, jac_mode);
     const double f3[3] = {ctx->par.f[0], ctx->par.f[1], ctx->fz};
     if (!ctx->have_par) HEMO_FAIL(ctx, HEMO_ESTATE, "hemo_set_params not called");
     if ((rc = tet_launch_cells(ctx, ctx->n, ctx->E, ctx->x, ctx->cells, ctx->h, x_dev, un_dev, ctx->uh, f3, jac_mode,

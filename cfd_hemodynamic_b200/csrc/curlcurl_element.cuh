@@ -1,7 +1,7 @@
-// GROUNDWORK: dimension-generic P1–P1 simplex element routine of the curl-curl /
-// rotational formulation of src/solvers/stabilized_schur_pressurebc.py:85-160 (and the `vascularbc` family
-// built on it).  Not wired into libhemo_sm100.so yet: checked on the host against oracle/curlcurl_oracle.py
-// (tests/test_curlcurl_host.py, compiled with g++: test infrastructure only).
+// Dimension-generic P1–P1 simplex element routine of the curl-curl / rotational formulation of
+// src/solvers/stabilized_schur_pressurebc.py:85-160 (the `vascularbc` family is built on
+// it).  Kernels: assembly_curlcurl.cu (hemo_set_formulation(ctx, HEMO_FORM_CURLCURL)).  Also checked on the host
+// against oracle/curlcurl_oracle.py (tests/test_curlcurl_host.py, compiled with g++: test infrastructure only).
 //
 // With G_ij = d_i u_mj and the antisymmetric W_ij = G_ij - G_ji both curl expressions of the form are
 // dimension-independent:
@@ -18,16 +18,23 @@
 #pragma once
 #include "simplex_element.cuh"
 
+// Which block forms a rule integrates (each block form of form(extract_blocks(..)) has its own rule,
+// stabilized_schur_pressurebc.py:205-206).
+enum { CC_FU = 1, CC_FP = 2, CC_UU = 4, CC_UP = 8, CC_PU = 16, CC_PP = 32 };
+
 // Residual and Jacobian of one cell with one rule.  `c` needs g, detJ, U, N, P, h, fbody
 // (simplex_geometry + nodal values; simplex_derive is not used).  Outputs are ADDED:
-//   Fu[a][k], Fp[a];  J[r][s] with r, s in the cell-local order (a*D + k for velocity, D*NV + a for pressure).
-// rows_u / rows_p select which rows this rule integrates (each block form has its own rule).
+//   Fu[a][k], Fp[a];  J[r * NL + s] with s in the cell-local order (b*D + l for velocity, D*NV + b for pressure).
+// `mask` (CC_*) selects the block forms this rule integrates.  `a_only` < 0: every test node, rows r in the
+// cell-local order too (J is NL x NL); `a_only` = a: only the rows of test node a, r = k for its velocity
+// components and r = D for its pressure row (J is (D+1) x NL) — one thread per (cell, test node) on the device.
 template <int D>
-HEMO_HD void curlcurl_cell(const SimplexCell<D>& c, const HemoForm& par, const SimplexRule<D>& r, bool rows_u,
-                           bool rows_p, bool want_jac, double Fu[D + 1][D], double Fp[D + 1],
-                           double* J /* [(D+1)^2][(D+1)^2] or nullptr */) {
+HEMO_HD void curlcurl_cell_ex(const SimplexCell<D>& c, const HemoForm& par, const SimplexRule<D>& r, int mask,
+                              int a_only, double Fu[D + 1][D], double Fp[D + 1], double* J) {
     constexpr int NV = D + 1, NL = (D + 1) * (D + 1), PO = D * NV;
     const double rho = par.rho, mu = par.mu, idt = 1.0 / par.dt, th = 0.5;
+    const bool rows_u = (mask & (CC_FU | CC_UU | CC_UP)) != 0, rows_p = (mask & (CC_FP | CC_PU | CC_PP)) != 0;
+    const bool want_jac = (mask & (CC_UU | CC_UP | CC_PU | CC_PP)) != 0;
     double G[D][D], W[D][D], gp[D], divu = 0.0;
     for (int i = 0; i < D; ++i) {
         for (int j = 0; j < D; ++j) {
@@ -85,14 +92,15 @@ HEMO_HD void curlcurl_cell(const SimplexCell<D>& c, const HemoForm& par, const S
         }
         const double bern = p + 0.5 * rho * um2;
         for (int a = 0; a < NV; ++a) {
-            if (rows_u)
+            if (a_only >= 0 && a != a_only) continue;
+            if (mask & CC_FU)
                 for (int k = 0; k < D; ++k) {
                     double cc = 0.0;
                     for (int i = 0; i < D; ++i) cc += W[i][k] * c.g[a][i];
                     Fu[a][k] += w * (rho * phi[a] * acc[k] + mu * cc - bern * c.g[a][k] + tau * s[a] * R[k] +
                                      tl * rho * divu * c.g[a][k]);
                 }
-            if (rows_p) {
+            if (mask & CC_FP) {
                 double rg = 0.0;
                 for (int i = 0; i < D; ++i) rg += R[i] * c.g[a][i];
                 Fp[a] += w * (phi[a] * divu + tau / rho * rg);
@@ -109,32 +117,46 @@ HEMO_HD void curlcurl_cell(const SimplexCell<D>& c, const HemoForm& par, const S
                     dR[k][l] = rho * (phi[b] * idt * dkl + drot);
                 }
             for (int a = 0; a < NV; ++a) {
+                if (a_only >= 0 && a != a_only) continue;
                 if (rows_u)
                     for (int k = 0; k < D; ++k) {
-                        const int row = a * D + k;
-                        for (int l = 0; l < D; ++l) {
-                            const double dkl = (k == l) ? 1.0 : 0.0;
-                            double v = phi[a] * dR[k][l];                                         // rho phi_a d(acc_k)
-                            v += mu * th * (gg[a][b] * dkl - c.g[b][k] * c.g[a][l]);              // curl-curl
-                            v -= rho * th * um[l] * phi[b] * c.g[a][k];                           // -rho/2 |u_m|^2 div v
-                            v += tau * (th * phi[b] * c.g[a][l] * R[k] + s[a] * dR[k][l]);        // SUPG
-                            v += tl * rho * th * c.g[b][l] * c.g[a][k];                           // LSIC
-                            J[row * NL + b * D + l] += w * v;
-                        }
-                        J[row * NL + PO + b] += w * (-phi[b] * c.g[a][k] + tau * s[a] * c.g[b][k]);   // J_up
+                        const int row = (a_only >= 0) ? k : a * D + k;
+                        if (mask & CC_UU)
+                            for (int l = 0; l < D; ++l) {
+                                const double dkl = (k == l) ? 1.0 : 0.0;
+                                double v = phi[a] * dR[k][l];                                         // rho phi_a d(acc_k)
+                                v += mu * th * (gg[a][b] * dkl - c.g[b][k] * c.g[a][l]);              // curl-curl
+                                v -= rho * th * um[l] * phi[b] * c.g[a][k];                           // -rho/2 |u_m|^2 div v
+                                v += tau * (th * phi[b] * c.g[a][l] * R[k] + s[a] * dR[k][l]);        // SUPG
+                                v += tl * rho * th * c.g[b][l] * c.g[a][k];                           // LSIC
+                                J[row * NL + b * D + l] += w * v;
+                            }
+                        if (mask & CC_UP) J[row * NL + PO + b] += w * (-phi[b] * c.g[a][k] + tau * s[a] * c.g[b][k]);
                     }
                 if (rows_p) {
-                    const int row = PO + a;
-                    for (int l = 0; l < D; ++l) {
-                        double v = phi[a] * th * c.g[b][l];
-                        for (int i = 0; i < D; ++i) v += tau / rho * dR[i][l] * c.g[a][i];
-                        J[row * NL + b * D + l] += w * v;                                          // J_pu
-                    }
-                    J[row * NL + PO + b] += w * tau / rho * gg[a][b];                              // J_pp
+                    const int row = (a_only >= 0) ? D : PO + a;
+                    if (mask & CC_PU)
+                        for (int l = 0; l < D; ++l) {
+                            double v = phi[a] * th * c.g[b][l];
+                            for (int i = 0; i < D; ++i) v += tau / rho * dR[i][l] * c.g[a][i];
+                            J[row * NL + b * D + l] += w * v;
+                        }
+                    if (mask & CC_PP) J[row * NL + PO + b] += w * tau / rho * gg[a][b];
                 }
             }
         }
     }
+}
+
+// rows_u / rows_p: the rule integrates F_u, J_uu, J_up resp. F_p, J_pu, J_pp (the host checks' calling convention)
+template <int D>
+HEMO_HD void curlcurl_cell(const SimplexCell<D>& c, const HemoForm& par, const SimplexRule<D>& r, bool rows_u,
+                           bool rows_p, bool want_jac, double Fu[D + 1][D], double Fp[D + 1],
+                           double* J /* [(D+1)^2][(D+1)^2] or nullptr */) {
+    int mask = 0;
+    if (rows_u) mask |= CC_FU | (want_jac ? (CC_UU | CC_UP) : 0);
+    if (rows_p) mask |= CC_FP | (want_jac ? (CC_PU | CC_PP) : 0);
+    curlcurl_cell_ex<D>(c, par, r, mask, -1, Fu, Fp, J);
 }
 
 // Exterior-facet terms of stabilized_schur_pressurebc.setup (:189-201) on local facet lf: weak pressure

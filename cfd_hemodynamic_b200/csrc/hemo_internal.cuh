@@ -145,6 +145,7 @@ struct HemoProf {
 };
 
 struct hemo_tet_state;      // assembly_tet.cu
+struct hemo_cc_state;       // assembly_curlcurl.cu
 struct HemoComm;            // comm.cu (NCCL communicator + halo plan of a mesh partition)
 
 // device-resident FGMRES (krylov.cu)
@@ -171,6 +172,9 @@ struct HemoKrylov {
 struct hemo_ctx {
     HemoProf prof;
     hemo_tet_state* tet = nullptr;   // tetrahedron rule tables (allocated on first use)
+    hemo_cc_state* cc = nullptr;     // rule tables of the curl-curl formulation (allocated on first use)
+    int formulation = 0;             // HEMO_FORM_STANDARD | HEMO_FORM_CURLCURL (hemo_set_formulation)
+    int64_t rule_version = 0;        // bumped by every quadrature setter
     int device = 0;
     cudaStream_t stream = 0;
     std::string err;
@@ -361,6 +365,7 @@ int hemo_p2_facet_flux(hemo_ctx* ctx, const HemoFacetSet& fs, const double* un_d
 int hemo_p2_laplace_mass(hemo_ctx* ctx);
 // implemented in assembly_tet.cu
 void hemo_tet_free(hemo_ctx* ctx);
+void hemo_cc_free(hemo_ctx* ctx);
 int hemo_tet_pattern(hemo_ctx* ctx, int64_t* rowptr_dev, int32_t* colind_dev);
 int hemo_tet_assemble_jacobian(hemo_ctx* ctx, const double* x_dev, const double* un_dev, double* vals_dev);
 int hemo_tet_assemble_residual(hemo_ctx* ctx, const double* x_dev, const double* un_dev, const double* g_dev,

@@ -643,6 +643,7 @@ extern "C" int hemo_ctx_destroy(hemo_ctx* ctx) {
     free(ctx->qrules);
     free(ctx->p2rules);
     hemo_tet_free(ctx);
+    hemo_cc_free(ctx);
     cudaFree(ctx->pc_in); cudaFree(ctx->pc_out); cudaFree(ctx->pc_mask); cudaFree(ctx->kry_coef); cudaFree(ctx->a01);
     cudaFree(ctx->pc_tmp_u); cudaFree(ctx->pc_tmp_u2); cudaFree(ctx->pc_tmp_p); cudaFree(ctx->pc_tmp_p2);
     cudaFree(ctx->kry_V); cudaFree(ctx->kry_Z); cudaFree(ctx->kry_w);

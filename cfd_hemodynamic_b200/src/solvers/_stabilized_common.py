@@ -45,7 +45,8 @@ SNES_DIVERGED_FNORM_NAN = -4
 
 
 class StabilizedSchurB200(SolverBase):
-    variant = "schur"          # "schur" | "backflow" | "pressure_backflow"
+    variant = "schur"          # "schur" | "backflow" | "pressure_backflow" | ... | "pressurebc"
+    formulation = "standard"   # weak form the library assembles ("curlcurl": stabilized_schur_pressurebc.py)
     _supported_cells = ("triangle", "quadrilateral")
 
     def __init__(self, mesh, dt, rho, mu, f, initial_velocity: Callable | None = None, **kw):
@@ -128,6 +129,7 @@ class StabilizedSchurB200(SolverBase):
         self._cells_host = cells
         self.hemo.set_mesh(torch.from_numpy(x).to(dev), torch.from_numpy(cells).to(dev),
                            torch.from_numpy(np.ascontiguousarray(h)).to(dev))
+        self.hemo.set_formulation(self.formulation)
         self._nrowptr, self._ncol = D.node_graph(cells, n)
         self.hemo.set_node_graph(torch.from_numpy(self._nrowptr).to(dev), torch.from_numpy(self._ncol).to(dev))
         for block, deg in (BLOCK_DEGREE_QUAD if self._quad else BLOCK_DEGREE_P2 if self._p2 else BLOCK_DEGREE).items():

@@ -53,6 +53,7 @@ class StabilizedSchurTetB200(StabilizedSchurB200):
         self._cells_host = cells
         self.hemo.set_mesh(torch.from_numpy(x).to(dev), torch.from_numpy(cells).to(dev),
                            torch.from_numpy(np.ascontiguousarray(h)).to(dev))
+        self.hemo.set_formulation(self.formulation)
         self._nrowptr, self._ncol = D.node_graph(cells, n)
         self.hemo.set_node_graph(torch.from_numpy(self._nrowptr).to(dev), torch.from_numpy(self._ncol).to(dev))
         for block, deg in BLOCK_DEGREE.items():          # affine P1: the same estimated degrees as on triangles

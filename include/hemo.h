@@ -112,6 +112,17 @@ int hemo_prof_get(hemo_ctx* ctx, int kernel_class, double* ms_total, int64_t* la
  * facet rule on [0,1], nq <= 8.  The per-step post-processing kernels are P1 / Q1 only. */
 enum { HEMO_CELL_TRIANGLE = 0, HEMO_CELL_QUADRILATERAL = 1, HEMO_CELL_TETRAHEDRON = 2, HEMO_CELL_TRIANGLE_P2 = 3 };
 int hemo_set_cell_type(hemo_ctx* ctx, int cell_type);
+
+/* Weak form assembled by hemo_assemble_jacobian / hemo_assemble_residual.
+ * HEMO_FORM_STANDARD: src/solvers/stabilized_schur.py:69-121 (and the boundary terms of its variants).
+ * HEMO_FORM_CURLCURL: the rotational form of src/solvers/stabilized_schur_pressurebc.py:85-160 — curl-curl viscous
+ *   term, (curl u x u) + grad(|u|^2/2) convection, SUPG/PSPG/LSIC with the viscous part of the strong residual
+ *   dropped — with its boundary terms (:189-201): facet sets use pconst (weak pressure, the reference passes
+ *   p/2) and a_n / beta_n (Nitsche for u_T = 0 written with curl x n).  P1 triangles and tetrahedra, default time
+ *   scheme only. */
+#define HEMO_FORM_STANDARD 0
+#define HEMO_FORM_CURLCURL 1
+int hemo_set_formulation(hemo_ctx* ctx, int formulation);
 /* mesh.geometry.x / .dofmap / mesh.h (src/solvers/stabilized_schur.py:55-58,83-88).
  * x: n_nodes*2 doubles, cells: n_cells*(3|4) int32, h: n_cells doubles; borrowed. */
 int hemo_set_mesh(hemo_ctx* ctx, const double* x_dev, int n_nodes,

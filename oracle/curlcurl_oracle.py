@@ -138,3 +138,72 @@ def facet_F(x, cells, h, pairs, coef, U, P, Un, facet_rule, mu):
         val = val + coef.a_n * (coef.beta_n * mu / hh)[:, None, None] * phi[:, :, None] * uT[:, None, :]
         Fu = Fu + w[:, None, None] * val
     return Fu
+
+
+# --------------------------------------------------------------------------
+# Adapters: the element routines above behind the kernel interfaces of the global oracles, so that
+# their assembly, Dirichlet treatment (assemble_*_block semantics) and Newton drivers serve the curl-curl
+# formulation unchanged.  Selected with `prob.formulation = "curlcurl"`.
+# --------------------------------------------------------------------------
+def _blocks(J, d, nv):
+    E = J.shape[0]
+    nu = d * nv
+    return (J[:, :nu, :nu].reshape(E, nu, nu), J[:, :nu, nu:].reshape(E, nu, nv), J[:, nu:, :nu].reshape(E, nv, nu),
+            J[:, nu:, nu:].reshape(E, nv, nv))
+
+
+class Kernels2D:
+    """Interface of oracle/ns_oracle.py:_kernels (P1 triangles)."""
+
+    @staticmethod
+    def _check(prob, Uh):
+        assert prob.theta == 0.5 and prob.a0 == 1.0 and Uh is None, "curl-curl form: default time scheme only"
+
+    @staticmethod
+    def element_F(prob, U, P, Un, rule, Uh=None):
+        Kernels2D._check(prob, Uh)
+        return element_F(prob.x, prob.cells, prob.h, U, P, Un, rule, prob.dt, prob.rho, prob.mu, prob.f, prob.eps0)
+
+    @staticmethod
+    def element_J(prob, U, P, Un, rule, Uh=None):
+        Kernels2D._check(prob, Uh)
+        J = element_J(prob.x, prob.cells, prob.h, U, P, Un, rule, rule, prob.dt, prob.rho, prob.mu, prob.f, prob.eps0)
+        return _blocks(J, 2, 3)
+
+    @staticmethod
+    def facet_F(prob, fs, U, P, Un):
+        return facet_F(prob.x, prob.cells, prob.h, fs.pairs, fs, U, P, Un, prob.facet_rule, prob.mu)
+
+
+class KernelsSimplex:
+    """Interface of oracle/simplex_oracle.py as oracle/ns3d_oracle.py calls it (any d)."""
+
+    @staticmethod
+    def element_F(x, cells, h, U, P, Un, rule, Uh=None, *, dt, rho, mu, f, eps0, theta=0.5, a0=1.0):
+        assert theta == 0.5 and a0 == 1.0 and Uh is None, "curl-curl form: default time scheme only"
+        return element_F(x, cells, h, U, P, Un, rule, dt, rho, mu, f, eps0)
+
+    @staticmethod
+    def element_J(x, cells, h, U, P, Un, rule, Uh=None, *, dt, rho, mu, f, eps0, theta=0.5, a0=1.0):
+        assert theta == 0.5 and a0 == 1.0 and Uh is None, "curl-curl form: default time scheme only"
+        d = x.shape[1]
+        return _blocks(element_J(x, cells, h, U, P, Un, rule, rule, dt, rho, mu, f, eps0), d, d + 1)
+
+    @staticmethod
+    def facet_F(x, cells, h, pairs, fs, U, P, Un, facet_rule, rho, mu, theta=0.5):
+        return facet_F(x, cells, h, pairs, fs, U, P, Un, facet_rule, mu)
+
+    @staticmethod
+    def facet_J(x, cells, h, pairs, fs, Un, facet_rule, rho, mu, theta=0.5):
+        """(m, d nv, (d+1) nv): the facet terms are affine in (U, P) — exact derivative from unit vectors."""
+        d = x.shape[1]
+        nv = d + 1
+        m = pairs.shape[0]
+        Z2, Z1 = np.zeros((m, nv, d)), np.zeros((m, nv))
+        F0 = facet_F(x, cells, h, pairs, fs, Z2, Z1, Un, facet_rule, mu)
+        out = np.zeros((m, d * nv, (d + 1) * nv))
+        for j in range(d * nv):                  # independent of P
+            U = Z2.copy()
+            U[:, j // d, j % d] = 1.0
+            out[:, :, j] = (facet_F(x, cells, h, pairs, fs, U, Z1, Un, facet_rule, mu) - F0).reshape(m, d * nv)
+        return out

@@ -59,6 +59,7 @@ class Problem3D:
     eps0: float = EPS0
     theta: float = 0.5
     a0: float = 1.0
+    formulation: str = "standard"     # "curlcurl": stabilized_schur_pressurebc.py (oracle/curlcurl_oracle.py)
 
     def __post_init__(self):
         self.h = S.cell_diameter(self.x, self.cells)
@@ -78,7 +79,15 @@ class Problem3D:
         return dict(dt=self.dt, rho=self.rho, mu=self.mu, f=self.f, eps0=self.eps0, theta=self.theta, a0=self.a0)
 
 
+def _kern(prob):
+    if prob.formulation == "curlcurl":
+        from .curlcurl_oracle import KernelsSimplex
+        return KernelsSimplex
+    return S
+
+
 def assemble_F_raw(prob, xk, un, uh=None):
+    S = _kern(prob)
     n = prob.n
     c = prob.cells
     U, P, Un = xk[:3 * n].reshape(-1, 3)[c], xk[3 * n:][c], un.reshape(-1, 3)[c]
@@ -97,6 +106,7 @@ def assemble_F_raw(prob, xk, un, uh=None):
 
 
 def assemble_J_raw(prob, xk, un, uh=None):
+    S = _kern(prob)
     n = prob.n
     c = prob.cells
     E = c.shape[0]

@@ -92,6 +92,7 @@ class Problem:
     theta: float = 0.5
     a0: float = 1.0
     uh: np.ndarray | None = None
+    formulation: str = "standard"     # "curlcurl": stabilized_schur_pressurebc.py (oracle/curlcurl_oracle.py)
 
     @property
     def n(self):
@@ -356,7 +357,12 @@ def _gather_history(prob):
 
 def _kernels(prob):
     """Element routines for the problem's cell type: this module for P1
-    triangles, oracle/q1_oracle.py for Q1 quadrilaterals (4 nodes per cell)."""
+    triangles, oracle/q1_oracle.py for Q1 quadrilaterals (4 nodes per cell); `prob.formulation = "curlcurl"` selects
+    the rotational form of stabilized_schur_pressurebc.py (oracle/curlcurl_oracle.py, P1 triangles)."""
+    if getattr(prob, "formulation", "standard") == "curlcurl":
+        assert prob.cells.shape[1] == 3
+        from .curlcurl_oracle import Kernels2D
+        return Kernels2D
     if prob.cells.shape[1] == 4:
         from . import q1_oracle
         return q1_oracle

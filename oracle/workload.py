@@ -53,6 +53,12 @@ def problem_from_solver(s, facet_tags=None, tags=None, rules=None):
     elif s.variant == "velocity_vascular_backflow":
         prob.facet_sets = [O.FacetSet(pairs=pairs(facet_tags.find(tags["outlet"])), pconst=0.0, a_s=c, a_b=c,
                                       beta_b=s.beta_backflow)]
+    elif s.variant == "pressurebc":      # stabilized_schur_pressurebc.py:189-201 on the curl-curl form
+        prob.formulation = "curlcurl"
+        prob.facet_sets = [O.FacetSet(pairs=pairs(facet_tags.find(tags["inlet"])), pconst=c * s._p_inlet_val, a_n=c,
+                                      beta_n=s.beta_nitsche),
+                           O.FacetSet(pairs=pairs(facet_tags.find(tags["outlet"])), pconst=c * s._p_outlet_val, a_n=c,
+                                      beta_n=s.beta_nitsche)]
     else:
         prob.facet_sets = [O.FacetSet(pairs=pairs(facet_tags.find(tags["inlet"])), pconst=c * s.p_inlet, a_n=c,
                                       beta_n=s.beta_nitsche),
