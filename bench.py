@@ -381,8 +381,7 @@ def measure_workload(name, W, K, local_rank, want_e2e=True, want_prof=True, solv
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            if tj.get("workload") == name:
-                traffic = tj.get("dram_bytes_per_launch", {}).get(PROF_CLASSES[dom])
+            traffic = tj.get("workloads", {}).get(name, {}).get("dram_bytes_per_launch", {}).get(PROF_CLASSES[dom])
         # whole step: algorithmic bytes of everything executed / step time
         step_bytes = (ksp / K) * (alg_bytes[0] + alg_bytes[6] + alg_bytes[7] + hierarchy_bytes(s) + 16 * ndof) \
             + (newton / K) * (alg_bytes[1] + alg_bytes[2]) + (newton / K + 1) * alg_bytes[3]

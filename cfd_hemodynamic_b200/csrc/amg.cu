@@ -922,7 +922,7 @@ __device__ void coarse_vcycle_body(const Scope& sc, const HemoCoarseLevel* __res
         const areal* b = (l == 0) ? b0 : L.b;
         areal* x = (l == 0) ? x0 : L.x;
         // the levels small enough for one CTA keep the stronger pre-smoother they have always had
-        fused_smooth<BS>(sc, L, b, x, true, L.n <= HEMO_FUSE_MAX_NODES ? degree : degree_pre, ratio);
+        fused_smooth<BS>(sc, L, b, x, true, L.n <= HEMO_FUSE_STRONG_PRE_NODES ? degree : degree_pre, ratio);
         rows_matvec<BS>(sc, L, x, [&](int i, const double* acc) {
 #pragma unroll
             for (int k = 0; k < BS; ++k) L.r[i * BS + k] = (areal)((double)b[i * BS + k] - acc[k]);
@@ -1161,6 +1161,12 @@ extern "C" int hemo_amg_set_fine_pattern(hemo_ctx* ctx, int which, const int32_t
     return 0;
 }
 
+static int fuse_max_nodes() {
+    const char* env = getenv("HEMO_FUSE_MAX");
+    const int v = env ? atoi(env) : HEMO_FUSE_MAX_NODES;
+    return v > 0 ? v : HEMO_FUSE_MAX_NODES;
+}
+
 // sliced-ELL pattern of one operator (kept when the padding stays below half of the entries)
 static int build_sell(hemo_ctx* ctx, HemoAmgOp& o, int bs) {
     cudaFree(o.sell_ptr); cudaFree(o.sell_col); cudaFree(o.sell_val);
@@ -1247,7 +1253,7 @@ extern "C" int hemo_amg_finalize(hemo_ctx* ctx, int which, int n_levels) {
     // `fuse_level` (<= HEMO_FUSE_MAX_NODES nodes) down by one CTA when a cooperative launch is not possible
     amg.fuse_level = amg.fuse_level_grid = -1;
     for (int l = 0; l < n_levels; ++l)
-        if (amg.op[l].n <= HEMO_FUSE_MAX_NODES) { amg.fuse_level = l; break; }
+        if (amg.op[l].n <= fuse_max_nodes()) { amg.fuse_level = l; break; }
     {
         int coop = 0, sms = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
@@ -1275,7 +1281,7 @@ extern "C" int hemo_amg_finalize(hemo_ctx* ctx, int which, int n_levels) {
         const char* envc = getenv("HEMO_CLUSTER_CTAS");
         int want = envc ? atoi(envc) : 16;
         if (want > 16) want = 16;
-        if (cap > HEMO_FUSE_MAX_NODES && want > 1 && amg.fuse_level_grid < 0) {
+        if (cap > fuse_max_nodes() && want > 1 && amg.fuse_level_grid < 0) {
             const void* fn = (bs == 2) ? (const void*)k_coarse_vcycle_cluster<2> : (const void*)k_coarse_vcycle_cluster<1>;
             if (want > 8) cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             for (int c = want; c >= 2 && amg.cluster_ctas == 0; c >>= 1) {
@@ -1292,7 +1298,7 @@ extern "C" int hemo_amg_finalize(hemo_ctx* ctx, int which, int n_levels) {
             if (amg.cluster_ctas > 0)
                 for (int l = 1; l < n_levels; ++l)
                     if (amg.op[l].n <= cap) {
-                        if (amg.op[l].n > HEMO_FUSE_MAX_NODES) amg.fuse_level_cluster = l;
+                        if (amg.op[l].n > fuse_max_nodes()) amg.fuse_level_cluster = l;
                         break;
                     }
         }

@@ -90,7 +90,8 @@ struct HemoCoarseLevel {
     const double* lmax;
 };
 
-#define HEMO_FUSE_MAX_NODES 256    // levels at or below this size run inside one CTA
+#define HEMO_FUSE_MAX_NODES 256    // levels at or below this size run inside one CTA (HEMO_FUSE_MAX=<nodes> overrides)
+#define HEMO_FUSE_STRONG_PRE_NODES 256   // levels at or below this size pre-smooth with the full Chebyshev degree
 // Levels (below the finest) at or below this size run inside the cooperative persistent-grid kernel.  0 = off, the
 // default: measured on a B200 (lid cavity 707^2) the grid.sync between the ~40 phases costs more than the graph-
 // scheduled per-level launches it replaces (36.9 vs 29.7 ms per time step); HEMO_GRID_FUSE_MAX=<nodes> turns it on.
