@@ -8,9 +8,12 @@ from cfd_hemodynamic_b200.src.scenarios.stenosis_pressure_structured import Sten
 res = float(sys.argv[1]) if len(sys.argv) > 1 else 0.015
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 W = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-only = sys.argv[4].split(",") if len(sys.argv) > 4 else None
+only = sys.argv[4].split(";") if len(sys.argv) > 4 else None      # configuration names separated by ";"
 CONFIGS = {
     "base(selfp,restart60,step)": dict(),
+    "restart20": dict(ksp_restart=20),
+    "restart30": dict(ksp_restart=30),
+    "restart40": dict(ksp_restart=40),
     "restart120": dict(ksp_restart=120),
     "restart200": dict(ksp_restart=200),
     "pc_newton": dict(pc_rebuild="newton"),
