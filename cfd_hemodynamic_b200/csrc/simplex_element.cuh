@@ -1,7 +1,7 @@
 // Dimension-generic P1–P1 simplex element routines (D = 2 triangles, D = 3 tetrahedra) of the
 // stabilized Navier–Stokes forms, src/solvers/stabilized_schur.py:60-123.
 //
-// GROUNDWORK for the tetrahedral kernels the north star names (the reference reaches them through
+// Written for the tetrahedral kernels the north star names (the reference reaches them through
 // `mesh.topology.cell_name()`, e.g. src/scenarios/taylor_green.py:34): the arithmetic below is the
 // moment factorisation of assembly.cu written once for any D — on an affine simplex every field of
 // the integrand is linear in the barycentric coordinates, so the quadrature only enters through

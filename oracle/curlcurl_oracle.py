@@ -1,6 +1,6 @@
 """CPU ORACLE — TEST INFRASTRUCTURE ONLY.  **PARITY UNPINNED** (see ns_oracle.py).
 
-GROUNDWORK for SURVEY.md §8(f) rank 4: the cell integrals of the curl-curl ("rotational") formulation of
+SURVEY.md §8(f) rank 4: the cell integrals of the curl-curl ("rotational") formulation of
 src/solvers/stabilized_schur_pressurebc.py:85-160 on P1–P1 simplices (d = 2 triangles, d = 3 tetrahedra),
 FFCx-style (full integrand at every quadrature point):
 
@@ -12,7 +12,7 @@ FFCx-style (full integrand at every quadrature point):
 
 with u_m = (u + u_n)/2 (:89), tau / tau_lsic as in stabilized_schur.py (:147-157, functions of u_n only).
 In 2-D, curl u is the scalar omega = d_x u_y - d_y u_x and curl u x w = (-omega w_y, omega w_x) (:96-110).
-No CUDA kernel follows this oracle yet; the Jacobian is the complex-step derivative of the residual (exact to
+The CUDA kernels of csrc/assembly_curlcurl.cu are checked against this oracle (tests/test_gpu_curlcurl.py); the Jacobian is the complex-step derivative of the residual (exact to
 round-off: the residual is analytic in (U, P), tau depends on u_n only).
 Layout as in simplex_oracle: U, Un (E, d+1, d), P (E, d+1) -> Fu (E, d+1, d), Fp (E, d+1).
 """

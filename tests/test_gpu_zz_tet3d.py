@@ -4,10 +4,8 @@ matrix-vector product on the reference's CSR layout and the outlet flux — agai
 oracle/ns3d_oracle.py (assemble_matrix_block / assemble_vector_block semantics,
 src/solvers/stabilized_schur.py:144-175).  Tolerances: pattern bit-exact, matrices and vectors 1e-12.
 
-Written when the round-1 GPU budget was all but used up: the per-thread bodies of these kernels are
-checked on the host by tests/test_tet_host.py, `test_golden_tet_case_on_gpu` ran green on a B200 with the
-last seconds of the budget (profiles/r01_pytest_gpu_tet_golden.log), the other tests have their first GPU
-run at round end; this file sorts last so that it runs after the suites that were green during the round."""
+The per-thread bodies of these kernels are also checked on the host (tests/test_tet_host.py); all of this file runs
+green on a B200 (round 2), including the hemodynamic variants on a tetrahedral channel."""
 import numpy as np
 import pytest
 import scipy.sparse as sp

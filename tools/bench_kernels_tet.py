@@ -1,8 +1,7 @@
 """Micro-benchmark of the tetrahedron kernels (CUDA events, L2 flushed between reps):
     python tools/bench_kernels_tet.py [cubes per edge, default 55 -> 1.0 M tetrahedra] [degree of the J_uu / F_u rule, default 12]
 Jacobian / residual assembly (cell + all-facet terms + Dirichlet rows on the boundary), SpMV on the 3-D CSR
-layout and one application of the first 3-D preconditioner.  Prints one JSON line; written for the first GPU
-call of round 2 (these kernels had only been host-verified when round 1 ran out of GPU minutes)."""
+layout and one application of the first 3-D preconditioner.  Prints one JSON line (profiles/r02_tet_kernels_280k.json)."""
 import json
 import os
 import sys
