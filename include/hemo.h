@@ -204,8 +204,8 @@ int hemo_assemble_laplace_mass(hemo_ctx* ctx, double* lap_vals_dev, double* mass
  *   hemo_pc_setup / hemo_pc_apply / hemo_fgmres with the first 3-D preconditioner (only the
  *   scalar pressure hierarchy `which = 1` is needed; the velocity block runs 4 * amg_cycles_u damped
  *   block-Jacobi sweeps).
- *   hemo_pc_set_schur_selfp (SELFP from the 3-D CSR values), hemo_wall_shear_stress (3n output; atomic
- *   sums, not bitwise reproducible in 3-D), hemo_early_stop_norms, hemo_l2_norm_sq (bs = 1 or 3).
+ *   hemo_pc_set_schur_selfp (SELFP from the 3-D CSR values), hemo_wall_shear_stress (3n output; per-vertex
+ *   gather in a fixed order, bitwise reproducible), hemo_early_stop_norms, hemo_l2_norm_sq (bs = 1 or 3).
  * Still 2-D only (HEMO_ESTATE on tetrahedra): hemo_boundary_force, the assembled Schur operator and pressure
  * convection term, partition masks. */
 int hemo_set_body_force3(hemo_ctx* ctx, const double* f3_host);
