@@ -50,6 +50,8 @@ WORKLOADS = {
     "stenosis_backflow_1m": dict(scenario="stenosis_mesh_variable", res=0.03, dt=1e-3, v_max=100.0),
     "stenosis_backflow_4m": dict(scenario="stenosis_mesh_variable", res=0.015, dt=1e-3, v_max=100.0),
     "stenosis_pressure_4m": dict(scenario="stenosis_pressure", res=0.015, dt=1e-3, p_inlet=80.0, R_resistance=10.0),
+    "stenosis_pressure_structured_250k": dict(scenario="stenosis_pressure_structured", res=0.06, dt=1e-3,
+                                              p_inlet=80.0, R_resistance=10.0),
     "stenosis_pressure_structured_1m": dict(scenario="stenosis_pressure_structured", res=0.03, dt=1e-3,
                                             p_inlet=80.0, R_resistance=10.0),
     "stenosis_pressure_structured_16m": dict(scenario="stenosis_pressure_structured", res=0.0075, dt=1e-3,
@@ -158,6 +160,12 @@ def workload_config(name, sc):
 # ------------------------------------------------------------------------------------------------------
 # CPU arm
 # ------------------------------------------------------------------------------------------------------
+def cpu_sub_pc(name):
+    """Sub-solvers of the reference for this workload's solver module: asm/ilu(0) for stabilized_schur
+    (stabilized_schur.py:256-267), lu for the pressure variants (stabilized_schur_pressure_backflow.py:284-288)."""
+    return "ilu" if WORKLOADS[name]["scenario"] == "lid_driven2D" else "lu"
+
+
 def cpu_steps(name, n_warm, n_steps, budget_s, nranks=None):
     """The reference's solver configuration restated on host cores (oracle/cpu_reference.CReferenceSolver:
     C + OpenMP, one thread per `mpirun` rank) marching the same scenario.  Returns a dict."""
@@ -167,7 +175,7 @@ def cpu_steps(name, n_warm, n_steps, budget_s, nranks=None):
         sc = build_scenario(w, host_only=True)
     cores = int(nranks or os.cpu_count() or 1)
     t_setup = time.perf_counter()
-    m = CpuMarcher(sc, solver="reference", nranks=cores)
+    m = CpuMarcher(sc, solver="reference", nranks=cores, sub_pc=cpu_sub_pc(name))
     t_setup = time.perf_counter() - t_setup
     t_begin = time.perf_counter()
     for _ in range(n_warm):
@@ -191,17 +199,24 @@ def run_reference(args):
     if rank != 0:
         return
     name = args.workload
-    if WORKLOADS[name]["scenario"] != "lid_driven2D":
-        raise SystemExit("bench.py --impl reference: the CPU arm (asm/ilu(0) sub-solves, stabilized_schur.py:256-267) is "
-                         "wired for the lid_driven2D workloads; the hemodynamic variants ask for `lu` sub-solves "
-                         "(stabilized_schur_pressure_backflow.py:284-288)")
+    w = WORKLOADS[name]
+    if w["scenario"] == "stenosis_mesh_variable" or w.get("cell_type", "triangle") != "triangle":
+        raise SystemExit("bench.py --impl reference: the CPU arm is written for P1 triangles and for the lid_driven2D "
+                         "(asm/ilu(0) sub-solves, stabilized_schur.py:256-267) and stenosis_pressure_structured (lu sub-solves, "
+                         "stabilized_schur_pressure_backflow.py:284-288) workloads")
     W = max(0, args.warmup)
     K = max(1, args.steps)
     r = cpu_steps(name, W, K, CPU_BUDGET_S)
     val = r["ndof"] * r["steps"] / r["seconds"]
+    if cpu_sub_pc(name) == "lu":
+        how = (f"FGMRES(200) + fieldsplit Schur FULL/SELFP + gmres/lu + preonly/lu (stabilized_schur_pressure_backflow.py:255-297): "
+               f"cell kernels in C + OpenMP on {r['cores']} threads, A00 and Sp factorised by SciPy's SuperLU for every Jacobian "
+               f"(sequential, like PETSc's own lu); ")
+    else:
+        how = (f"FGMRES(200) + fieldsplit Schur FULL/SELFP + GMRES(30)/ASM-ILU(0) (stabilized_schur.py:226-275) restated in "
+               f"C + OpenMP, {r['cores']} threads = {r['cores']} ASM blocks; ")
     sample = (f"{r['steps']} timed time step(s) after {W} warm-up step(s) of {name} ({r['ndof']} DOFs), the same mesh and "
-              f"steps as the GPU arm; FGMRES(200) + fieldsplit Schur FULL/SELFP + GMRES(30)/ASM-ILU(0) "
-              f"(stabilized_schur.py:226-275) restated in C + OpenMP, {r['cores']} threads = {r['cores']} ASM blocks; "
+              f"steps as the GPU arm; " + how + 
               f"{r['newton_its']} Newton, {r['outer_its']} outer and {r['inner_its']} inner Krylov iterations in "
               f"{r['total_steps']} steps; assembly {r['timers']['assembly']:.1f} s, PCSetUp {r['timers']['pc_setup']:.1f} s, "
               f"KSPSolve {r['timers']['ksp']:.1f} s")

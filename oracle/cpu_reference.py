@@ -220,12 +220,13 @@ class CReferenceSolver:
     """SNES newtonls + bt (oracle/ns_oracle.newton_solve) around the C restatement of
     KSP fgmres(200) / fieldsplit Schur FULL + SELFP / gmres(30)+asm-ilu0 / preonly+asm-ilu0
     (/root/reference/src/solvers/stabilized_schur.py:202-275).  P1 triangles.  `nranks` threads stand for the
-    MPI ranks of `mpirun -n nranks` (default: all cores).  The hemodynamic variants that ask for `lu` sub-solvers
-    (stabilized_schur_pressure_backflow.py:284-288) get the same asm/ilu(0) blocks here: PETSc's `lu` is sequential
-    (a parallel run needs an external package), and ILU(0) is the cheaper choice for the CPU arm."""
+    MPI ranks of `mpirun -n nranks` (default: all cores).  `sub_pc="lu"` is the configuration of the hemodynamic variants
+    (stabilized_schur_pressure_backflow.py:255-297: gmres/lu on A00, preonly/lu on Sp): SciPy's SuperLU, sequential like
+    PETSc's own `lu` (a parallel PETSc run needs an external package), factorised for every Jacobian; the ASM/ILU(0) blocks
+    do not converge on the stenosis workloads (1000 outer iterations)."""
 
     def __init__(self, prob: O.Problem, nranks: int | None = None, nullspace: bool | None = None,
-                 ksp_rtol: float = 1e-5, ksp_max_it: int = 1000, restart: int = 200, node_graph=None):
+                 ksp_rtol: float = 1e-5, ksp_max_it: int = 1000, restart: int = 200, node_graph=None, sub_pc: str = "ilu"):
         from cfd_hemodynamic_b200.fem import discretization as D
         L = _ksp()
         self.prob = prob
@@ -254,6 +255,14 @@ class CReferenceSolver:
             self.diag_val = self.mult[md]
         self.ksp = L.refksp_create(2 * n, n, self.nranks, restart)
         self.ksp_rtol, self.ksp_max_it = ksp_rtol, ksp_max_it
+        # "ilu": gmres(30)+asm/ilu(0) and preonly+asm/ilu(0) in C (stabilized_schur.py:256-267);
+        # "lu":  gmres+lu and preonly+lu (stabilized_schur_pressure_backflow.py:284-288) with SciPy's SuperLU — sequential
+        #        like PETSc's own `lu` (a parallel run needs MUMPS / SuperLU_DIST); factorised for every Jacobian.
+        if sub_pc not in ("ilu", "lu"):
+            raise ValueError(sub_pc)
+        self.sub_pc = sub_pc
+        self.restart = restart
+        self._lu_outer = 0
         self._nullspace = nullspace
         self.timers = {"assembly": 0.0, "pc_setup": 0.0, "ksp": 0.0}
         self.lin_its = 0
@@ -310,10 +319,48 @@ class CReferenceSolver:
         return b
 
     # --- KSPSolve -----------------------------------------------------------------------------------
+    def _linear_solve_lu(self, A, f):
+        """FGMRES(restart) + fieldsplit Schur FULL, SELFP, exact (LU) sub-solves: the inner gmres on A00 converges in one
+        iteration with an exact preconditioner, so it is applied directly."""
+        n = self.n
+        t0 = time.perf_counter()
+        A = A.tocsr()
+        A00 = A[:2 * n, :2 * n].tocsc()
+        A01 = A[:2 * n, 2 * n:].tocsr()
+        A10 = A[2 * n:, :2 * n].tocsr()
+        A11 = A[2 * n:, 2 * n:].tocsr()
+        Sp = (A11 - A10 @ sp.diags(1.0 / A00.diagonal()) @ A01).tocsc()          # SELFP (:253)
+        singular = bool(self._nullspace)
+        if singular:
+            Sp = (Sp + 1e-10 * abs(Sp.diagonal()).max() * sp.identity(n)).tocsc()
+        lu0 = spla.splu(A00)
+        lus = spla.splu(Sp)
+        t1 = time.perf_counter()
+
+        def pc(r):
+            zu = lu0.solve(r[:2 * n])
+            rp = r[2 * n:] - A10 @ zu
+            if singular:
+                rp = rp - rp.mean()
+            zp = lus.solve(rp)
+            if singular:
+                zp = zp - zp.mean()
+            zu = zu - lu0.solve(A01 @ zp)
+            return np.concatenate([zu, zp])
+
+        y, its = _fgmres(A, np.asarray(f, dtype=np.float64), pc, rtol=self.ksp_rtol, restart=self.restart, maxit=self.ksp_max_it)
+        self.timers["pc_setup"] += t1 - t0
+        self.timers["ksp"] += time.perf_counter() - t1
+        self.lin_its += its
+        self._lu_outer += its
+        return y
+
     def linear_solve(self, A, f):
         L = _ksp()
         if self._nullspace is None:
             self._nullspace = bool(O.has_constant_pressure_nullspace(self.prob, A))
+        if self.sub_pc == "lu":
+            return self._linear_solve_lu(A, f)
         L.refksp_set_nullspace(self.ksp, int(self._nullspace))
         t0 = time.perf_counter()
         L.refksp_setup(self.ksp, _ptr(self.rowptr), _ptr(self.colind), _ptr(self.vals))
@@ -331,6 +378,8 @@ class CReferenceSolver:
         return y
 
     def stats(self):
+        if self.sub_pc == "lu":
+            return dict(outer_its=int(self._lu_outer), inner_its=int(self._lu_outer), inner_solves=int(2 * self._lu_outer))
         out = np.zeros(3, dtype=np.int64)
         _ksp().refksp_stats(self.ksp, _ptr(out))
         return dict(outer_its=int(out[0]), inner_its=int(out[1]), inner_solves=int(out[2]))

@@ -72,7 +72,7 @@ class CpuMarcher:
     of the pressure variants (`_update_outlet_pressure`, stabilized_schur_pressure_backflow.py:387-396, Q from the old
     u_prev) and the host's u_prev <- u_sol shift."""
 
-    def __init__(self, scenario, solver="reference", nranks=None, **tol):
+    def __init__(self, scenario, solver="reference", nranks=None, sub_pc="ilu", **tol):
         s = scenario.solver
         self.s = s
         self.prob = problem_from_solver(s, getattr(scenario, "facet_tags", None), getattr(scenario, "tags", None))
@@ -88,7 +88,7 @@ class CpuMarcher:
         self.kind = solver
         if solver == "reference":
             from .cpu_reference import CReferenceSolver
-            self.ref = CReferenceSolver(self.prob, nranks=nranks)
+            self.ref = CReferenceSolver(self.prob, nranks=nranks, sub_pc=sub_pc)
         else:
             from .c_oracle import FastAssembler
             self.ref = None

@@ -67,3 +67,27 @@ def test_reference_configuration_converges_to_the_lu_solution():
     pk, pr = xk[2 * n:] - xk[2 * n:].mean(), xr[2 * n:] - xr[2 * n:].mean()
     assert eu < 1e-8 and np.linalg.norm(pk - pr) / np.linalg.norm(pr) < 1e-8
     S.close()
+
+
+def test_lu_subsolve_configuration_on_the_pressure_driven_stenosis():
+    """The hemodynamic variants ask for `lu` sub-solves (stabilized_schur_pressure_backflow.py:284-288): FGMRES(200) +
+    Schur FULL + SELFP with exact A00 / Sp solves needs a handful of outer iterations (ILU(0) blocks stall on this problem)
+    and marches to the same solution as the plain sparse-LU Newton, resistance outlet included."""
+    import contextlib
+    import sys
+    from cfd_hemodynamic_b200.src.scenarios.stenosis_pressure_structured import StenosisPressureStructuredSimulation
+    from oracle.workload import CpuMarcher
+    with contextlib.redirect_stdout(sys.stderr):
+        sc = StenosisPressureStructuredSimulation("stabilized_schur_pressure_backflow", 1e-3, 1.0, grade="severe", p_inlet=80.0,
+                                                  R_resistance=10.0, res=0.6, cell_type="triangle", host_only=True)
+    a = CpuMarcher(sc, solver="reference", nranks=2, sub_pc="lu", rtol=1e-10, stol=0.0)
+    b = CpuMarcher(sc, solver="lu", rtol=1e-10, stol=0.0)
+    for _ in range(3):
+        a.step()
+        b.step()
+    n = a.n
+    st = a.ref.stats()
+    assert 0 < st["outer_its"] <= 25 * a.ref.newton_its                     # SELFP with exact sub-solves: O(10) iterations per solve
+    assert abs(a.outlet["pc"] - b.outlet["pc"]) <= 1e-6 * max(1.0, abs(b.outlet["pc"]))
+    assert np.linalg.norm(a.x[:2 * n] - b.x[:2 * n]) <= 1e-6 * np.linalg.norm(b.x[:2 * n])
+    assert np.linalg.norm(a.x[2 * n:] - b.x[2 * n:]) <= 1e-6 * np.linalg.norm(b.x[2 * n:])
