@@ -115,3 +115,26 @@ def test_partition_halo_world2(cell_type):
         assert abs(dsum - dref) < 1e-12 * dref
         assert n_local > n_owned
     assert res[0][4] + res[1][4] == (64 if cell_type == "tetrahedron" else 70)
+
+
+def test_partition_halo_world3_two_neighbours():
+    """Three slabs: the middle rank has two neighbours and, with an overlap of three cell layers on this narrow mesh, the
+    outer ranks hold ghosts owned by the non-adjacent rank as well (the plans of N = 4 / 8 runs have this shape)."""
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 3, port, q, "triangle")) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(3))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, dsum, dref, n_owned, n_local in res:
+        assert err < 1e-14, err
+        assert abs(dsum - dref) < 1e-12 * dref
+        assert n_local > n_owned
+    assert sum(r[4] for r in res) == 70
