@@ -68,6 +68,7 @@ DEFAULT_WORKLOAD = "lid_driven2D_nx512"
 # measured on the GPU arm in the same run (N = 1, default workload only): (name, warm-up, steps)
 EXTRA_WORKLOADS = [("lid_driven2D_nx707", 3, 10), ("stenosis_pressure_structured_16m", 2, 4)]
 CPU_BUDGET_S = 1500.0        # the CPU arm stops taking new steps beyond this (driver limit: 1800 s per arm)
+CPU_BUDGET_WEAK_S = 420.0    # the same for the weak-scaled meshes of the N > 1 lines (minutes per time step)
 
 PROF_CLASSES = {0: "spmv_node(J)", 1: "cell_jacobian", 2: "gather_matrix", 3: "cell_residual",
                 4: "cheb_step<2>(A00,l0)", 5: "cheb_step<1>(Lp,l0)", 6: "mdot", 7: "maxpy_norm",
@@ -166,11 +167,14 @@ def cpu_sub_pc(name):
     return "ilu" if WORKLOADS[name]["scenario"] == "lid_driven2D" else "lu"
 
 
-def cpu_steps(name, n_warm, n_steps, budget_s, nranks=None):
+def cpu_steps(name, n_warm, n_steps, budget_s, nranks=None, nx=None):
     """The reference's solver configuration restated on host cores (oracle/cpu_reference.CReferenceSolver:
-    C + OpenMP, one thread per `mpirun` rank) marching the same scenario.  Returns a dict."""
+    C + OpenMP, one thread per `mpirun` rank) marching the same scenario.  `nx` overrides the cavity resolution (the
+    weak-scaled mesh of an N-GPU run).  Returns a dict."""
     from oracle.workload import CpuMarcher
-    w = WORKLOADS[name]
+    w = dict(WORKLOADS[name])
+    if nx is not None:
+        w["nx"] = int(nx)
     with contextlib.redirect_stdout(sys.stderr):
         sc = build_scenario(w, host_only=True)
     cores = int(nranks or os.cpu_count() or 1)
@@ -206,7 +210,23 @@ def run_reference(args):
                          "stabilized_schur_pressure_backflow.py:284-288) workloads")
     W = max(0, args.warmup)
     K = max(1, args.steps)
-    r = cpu_steps(name, W, K, CPU_BUDGET_S)
+    N = max(int(args.gpus), 1)
+    nx = None
+    budget = CPU_BUDGET_S
+    if N > 1:
+        # the GPU arm at N > 1 solves ONE lid cavity of nx * sqrt(N) squared (run_distributed, weak scaling): the same mesh
+        # here, on the same host cores whatever N is — one time step of it costs minutes, so at most one warm-up step and
+        # a tighter budget (the number of timed steps is reported)
+        if w["scenario"] != "lid_driven2D":
+            name = "lid_driven2D_nx707"
+            w = WORKLOADS[name]
+        nx = int(round(w["nx"] * math.sqrt(N)))
+        W = min(W, 1)
+        budget = CPU_BUDGET_WEAK_S
+    r = cpu_steps(name, W, K, budget, nx=nx)
+    if nx is not None:
+        r["config"]["global_nx"] = nx
+        r["config"]["cells_per_gpu"] = r["config"]["cells"] // N
     val = r["ndof"] * r["steps"] / r["seconds"]
     if cpu_sub_pc(name) == "lu":
         how = (f"FGMRES(200) + fieldsplit Schur FULL/SELFP + gmres/lu + preonly/lu (stabilized_schur_pressure_backflow.py:255-297): "

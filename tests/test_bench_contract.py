@@ -35,3 +35,12 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
 def test_reference_arm_is_silent_on_other_ranks():
     r = _run(["--gpus", "2"], env={"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_follows_the_weak_scaled_mesh_of_an_n_gpu_run():
+    """At N > 1 the GPU arm solves one cavity of nx * sqrt(N) squared: rank 0 of the reference arm marches the same mesh."""
+    r = _run(["--gpus", "4"], env={"RANK": "0", "LOCAL_RANK": "0", "WORLD_SIZE": "4"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][-1])
+    assert line["n_gpus"] == 4 and line["config"]["global_nx"] == 128 and line["config"]["dofs"] == 3 * 129 * 129
+    assert line["config"]["cells_per_gpu"] == 2 * 128 * 128 // 4
