@@ -56,6 +56,31 @@ def slab_partition(x_coord, n_parts: int):
     return owner
 
 
+def rcb_partition(x, n_parts: int):
+    """Recursive coordinate bisection of the vertex set (the partitioner for unstructured meshes such as the
+    graded DFG cylinder mesh or gmsh artery meshes — no METIS in the image): split along the longest extent of the current
+    box at the weighted median so that part sizes differ by at most one vertex, recurse with n_parts // 2 and
+    n_parts - n_parts // 2.  x: (n, 2 | 3).  Returns the owner rank of every vertex (deterministic: stable sorts)."""
+    import numpy as np
+    x = np.asarray(x, dtype=np.float64)
+    owner = np.zeros(x.shape[0], dtype=np.int32)
+
+    def split(idx, first, parts):
+        if parts == 1:
+            owner[idx] = first
+            return
+        left = parts // 2
+        pts = x[idx]
+        axis = int(np.argmax(pts.max(axis=0) - pts.min(axis=0)))
+        order = np.argsort(pts[:, axis], kind="stable")
+        cut = int(round(idx.shape[0] * left / parts))
+        split(idx[order[:cut]], first, left)
+        split(idx[order[cut:]], first + left, parts - left)
+
+    split(np.arange(x.shape[0]), 0, int(n_parts))
+    return owner
+
+
 # ---------------------------------------------------------------------------
 # domain decomposition: vertex ownership + one layer of ghost cells
 # (SURVEY.md §8(e); mirrors how DOLFINx distributes a mesh under mpirun, §2.4)

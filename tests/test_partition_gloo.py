@@ -11,12 +11,12 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 
-def _worker(rank, world, port, out, cell_type="triangle"):
+def _worker(rank, world, port, out, cell_type="triangle", partitioner="slab"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import scipy.sparse as sp
-    from cfd_hemodynamic_b200.parallel import HaloExchange, HaloExchangeAllGather, Partition, slab_partition
+    from cfd_hemodynamic_b200.parallel import HaloExchange, HaloExchangeAllGather, Partition, rcb_partition, slab_partition
     from oracle import ns_oracle as O
     from tests import common as T
     gd = 3 if cell_type == "tetrahedron" else 2
@@ -36,7 +36,7 @@ def _worker(rank, world, port, out, cell_type="triangle"):
         n = prob.n
         u, p, un = T.smooth_fields(prob.x)
         A = O.assemble_J_raw(prob, u, p, un).tocsr()
-    owner = slab_partition(prob.x[:, 0], world)
+    owner = slab_partition(prob.x[:, 0], world) if partitioner == "slab" else rcb_partition(prob.x, world)
     part = Partition(prob.x, prob.cells, owner, rank, gdim=gd)
     # local matrix: rows/cols of the local nodes in local [u|p] numbering
     gl = part.glob_nodes
@@ -130,6 +130,48 @@ def test_partition_halo_world3_two_neighbours():
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=240) for _ in range(3))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, dsum, dref, n_owned, n_local in res:
+        assert err < 1e-14, err
+        assert abs(dsum - dref) < 1e-12 * dref
+        assert n_local > n_owned
+    assert sum(r[4] for r in res) == 70
+
+
+def test_rcb_partition_balance_and_determinism():
+    from cfd_hemodynamic_b200.parallel import rcb_partition
+    rng = np.random.default_rng(0)
+    x = rng.random((1003, 2)) * np.array([2.2, 0.41])
+    for parts in (1, 2, 3, 5, 8):
+        owner = rcb_partition(x, parts)
+        counts = np.bincount(owner, minlength=parts)
+        assert counts.sum() == 1003 and counts.max() - counts.min() <= 2 and owner.min() == 0 and owner.max() == parts - 1
+        assert np.array_equal(owner, rcb_partition(x, parts))
+    # boxes: every part is a union of axis-aligned cuts -> the bounding boxes of two parts overlap in at most a face
+    owner = rcb_partition(x, 4)
+    boxes = [(x[owner == r].min(axis=0), x[owner == r].max(axis=0)) for r in range(4)]
+    for a in range(4):
+        for b in range(a + 1, 4):
+            lo = np.maximum(boxes[a][0], boxes[b][0])
+            hi = np.minimum(boxes[a][1], boxes[b][1])
+            assert (hi - lo).min() <= 1e-12
+
+
+def test_partition_halo_world4_rcb():
+    """Four RCB parts of the square: ranks with two or three neighbours (2-D decomposition, the shape an unstructured
+    mesh produces); halo plan, library plan with overlap and owned-row SpMV against the global product."""
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 4, port, q, "triangle", "rcb")) for r in range(4)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(4))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
